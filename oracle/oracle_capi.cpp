@@ -1,0 +1,220 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  C entry points used through ctypes by tests/, smoke() and bench.py's CPU legs.
+// The product library (gxbeam_b200/csrc) never includes, links or calls anything in this directory.
+#include <complex>
+#include <cstring>
+#include <vector>
+#include <atomic>
+#include <thread>
+#include "gxb_math.hpp"
+#include "gxb_static.hpp"
+#include "gxb_solve.hpp"
+
+using namespace gxo;
+typedef std::complex<double> cplx;
+
+extern "C" {
+
+// mirrors gxo::Problem field by field (ctypes Structure in tests/oracle.py)
+struct gxo_problem {
+    int64_t np, ne;
+    const int64_t* start;
+    const int64_t* stop;
+    const double* elems;
+    const double* points;
+    const uint8_t* pd;
+    const uint8_t* pl;
+    const double* bc;
+    const double* dload;
+    const double* pmass;
+    double gravity[3];
+    double force_scaling;
+    int32_t two_dimensional;
+};
+
+struct gxo_opts {
+    int32_t linear;
+    double ftol;
+    int64_t iterations;
+    double maxstep, c1, rho_hi, rho_lo;
+};
+}
+
+static Problem to_problem(const gxo_problem* q) {
+    Problem P;
+    P.np = q->np; P.ne = q->ne; P.start = q->start; P.stop = q->stop; P.elems = q->elems; P.points = q->points;
+    P.pd = q->pd; P.pl = q->pl; P.bc = q->bc; P.dload = q->dload; P.pmass = q->pmass;
+    for (int i = 0; i < 3; i++) P.gravity[i] = q->gravity[i];
+    P.force_scaling = q->force_scaling; P.two_dimensional = q->two_dimensional;
+    return P;
+}
+static NewtonOpts to_opts(const gxo_opts* o) {
+    NewtonOpts r;
+    if (o) { r.linear = o->linear; r.ftol = o->ftol; r.iterations = o->iterations; r.maxstep = o->maxstep; r.c1 = o->c1; r.rho_hi = o->rho_hi; r.rho_lo = o->rho_lo; }
+    return r;
+}
+
+// scalar bandwidths of the static Jacobian from the 3x3-block insertion pattern (element.jl:2487-2552, point.jl:1795-1797)
+static void static_bandwidth(const Problem& P, const Indices& idx, int64_t& kl, int64_t& ku) {
+    kl = 0; ku = 0;
+    auto blk = [&](int64_t r0, int64_t nr, int64_t c0, int64_t nc) {
+        kl = std::max(kl, (r0 + nr - 1) - c0);
+        ku = std::max(ku, (c0 + nc - 1) - r0);
+    };
+    for (int64_t ip = 0; ip < P.np; ip++) blk(idx.irow_point[ip], 6, idx.icol_point[ip], 6);
+    for (int64_t ie = 0; ie < P.ne; ie++) {
+        int64_t ic = idx.icol_elem[ie], ic1 = idx.icol_point[P.start[ie] - 1], ic2 = idx.icol_point[P.stop[ie] - 1];
+        int64_t ir = idx.irow_elem[ie], ir1 = idx.irow_point[P.start[ie] - 1], ir2 = idx.irow_point[P.stop[ie] - 1];
+        blk(ir, 3, ic1, 6); blk(ir, 3, ic2, 6); blk(ir, 6, ic, 6); blk(ir + 3, 3, ic1 + 3, 3); blk(ir + 3, 3, ic2 + 3, 3);
+        for (int64_t irp : {ir1, ir2}) {
+            blk(irp, 6, ic1 + 3, 3); blk(irp, 6, ic2 + 3, 3); blk(irp, 3, ic, 3); blk(irp + 3, 3, ic, 6);
+        }
+    }
+    if (P.two_dimensional) { kl = std::max<int64_t>(kl, 0); ku = std::max<int64_t>(ku, 0); }
+}
+
+extern "C" {
+
+int gxo_indices(int64_t ne, const int64_t* start, const int64_t* stop, int is_static, int64_t* nstates, int64_t* irow_point,
+                int64_t* irow_elem, int64_t* icol_point, int64_t* icol_elem) {
+    Indices idx = system_indices(ne, start, stop, is_static != 0);
+    *nstates = idx.nstates;
+    std::memcpy(irow_point, idx.irow_point.data(), idx.irow_point.size() * 8);
+    std::memcpy(icol_point, idx.icol_point.data(), idx.icol_point.size() * 8);
+    std::memcpy(irow_elem, idx.irow_elem.data(), idx.irow_elem.size() * 8);
+    std::memcpy(icol_elem, idx.icol_elem.data(), idx.icol_elem.size() * 8);
+    return 0;
+}
+
+static void put33(double* out, const M3<double>& A) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[3 * i + j] = A.m[i][j]; }
+
+// Rotation kernels and their analytic derivatives at (θ, Δθ); every 3x3 is written row-major.
+//   out: C[9] C_θ[27] Q[9] Q_θ[27] Qinv[9] Qinv_θ[27] ΔQ[9] ΔQ_θ[27] scaling[1]   (145 doubles)
+void gxo_rotation(const double* th_, const double* dth_, double* out) {
+    V3<double> th = cvec<double>(th_), dth = cvec<double>(dth_);
+    M3<double> C = get_C(th), A1, A2, A3;
+    put33(out, C); get_C_th(C, th, A1, A2, A3); put33(out + 9, A1); put33(out + 18, A2); put33(out + 27, A3);
+    M3<double> Q = get_Q(th), Q1, Q2, Q3;
+    put33(out + 36, Q); get_Q_th(Q, th, Q1, Q2, Q3); put33(out + 45, Q1); put33(out + 54, Q2); put33(out + 63, Q3);
+    put33(out + 72, get_Qinv(th)); get_Qinv_th(th, A1, A2, A3); put33(out + 81, A1); put33(out + 90, A2); put33(out + 99, A3);
+    put33(out + 108, get_dQ(th, dth, Q)); get_dQ_th(th, dth, Q, Q1, Q2, Q3, A1, A2, A3);
+    put33(out + 117, A1); put33(out + 126, A2); put33(out + 135, A3);
+    out[144] = rotation_parameter_scaling(th);
+}
+// Same derivatives by complex step (the oracle's stand-in for ForwardDiff in test/jacobians.jl:3-39):
+//   out: C_θ[27] Q_θ[27] Qinv_θ[27] ΔQ_θ[27]
+void gxo_rotation_cs(const double* th_, const double* dth_, double* out) {
+    const double h = 1e-30;
+    for (int k = 0; k < 3; k++) {
+        V3<cplx> th = cvec<cplx>(th_), dth = cvec<cplx>(dth_);
+        th.v[k] += cplx(0, h);
+        M3<cplx> C = get_C(th), Q = get_Q(th), Qi = get_Qinv(th), dQ = get_dQ(th, dth, Q);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                out[9 * k + 3 * i + j] = C.m[i][j].imag() / h;
+                out[27 + 9 * k + 3 * i + j] = Q.m[i][j].imag() / h;
+                out[54 + 9 * k + 3 * i + j] = Qi.m[i][j].imag() / h;
+                out[81 + 9 * k + 3 * i + j] = dQ.m[i][j].imag() / h;
+            }
+    }
+}
+
+int gxo_static_residual(const gxo_problem* q, const double* x, double* r) {
+    Problem P = to_problem(q);
+    Indices idx = system_indices(P.ne, P.start, P.stop, true);
+    static_system_residual<double>(P, idx, x, r);
+    return 0;
+}
+// dense column-major n x n
+int gxo_static_jacobian(const gxo_problem* q, const double* x, double* J) {
+    Problem P = to_problem(q);
+    Indices idx = system_indices(P.ne, P.start, P.stop, true);
+    DenseMat<double> D{idx.nstates, J};
+    static_system_jacobian<double>(P, idx, x, D);
+    return 0;
+}
+// complex-step derivative of the residual, dense column-major
+int gxo_static_jacobian_cs(const gxo_problem* q, const double* x, double* J) {
+    Problem P = to_problem(q);
+    Indices idx = system_indices(P.ne, P.start, P.stop, true);
+    int64_t n = idx.nstates;
+    const double h = 1e-30;
+    std::vector<cplx> xc(n), rc(n);
+    for (int64_t j = 0; j < n; j++) {
+        for (int64_t i = 0; i < n; i++) xc[i] = cplx(x[i], 0);
+        xc[j] += cplx(0, h);
+        for (int64_t i = 0; i < n; i++) rc[i] = cplx(0, 0);
+        static_system_residual<cplx>(P, idx, xc.data(), rc.data());
+        for (int64_t i = 0; i < n; i++) J[i + n * j] = rc[i].imag() / h;
+    }
+    return 0;
+}
+int gxo_static_bandwidth(const gxo_problem* q, int64_t* kl, int64_t* ku) {
+    Problem P = to_problem(q);
+    Indices idx = system_indices(P.ne, P.start, P.stop, true);
+    static_bandwidth(P, idx, *kl, *ku);
+    return 0;
+}
+
+static NewtonResult static_solve_one(const Problem& P, const Indices& idx, int64_t kl, int64_t ku, const NewtonOpts& o, const double* x0,
+                                     double* x, double* F) {
+    int64_t n = idx.nstates;
+    BandMat J; J.init(n, kl, ku);
+    for (int64_t i = 0; i < n; i++) x[i] = x0 ? x0[i] : 0.0;
+    auto rf = [&](const double* xx, double* FF) { static_system_residual<double>(P, idx, xx, FF); };
+    auto jf = [&](const double* xx, BandMat& JJ) { static_system_jacobian<double>(P, idx, xx, JJ); };
+    return newton_solve(n, x, F, J, rf, jf, o);
+}
+
+// static_analysis for one instance (analyses.jl:78-179 with a single time step)
+//   stats[4] = {converged, iters, f_calls, ls_backtracks}
+int gxo_static_solve(const gxo_problem* q, const gxo_opts* opts, const double* x0, double* x, double* resid, int64_t* stats,
+                     double* resid_inf) {
+    Problem P = to_problem(q);
+    Indices idx = system_indices(P.ne, P.start, P.stop, true);
+    int64_t kl, ku; static_bandwidth(P, idx, kl, ku);
+    NewtonResult r = static_solve_one(P, idx, kl, ku, to_opts(opts), x0, x, resid);
+    stats[0] = r.converged; stats[1] = r.iters; stats[2] = r.f_calls; stats[3] = r.ls_backtracks;
+    *resid_inf = r.resid_inf;
+    return r.error;
+}
+
+// Batched static_analysis, instances independent, a std::thread pool with a dynamic schedule over instances (the analogue of
+// Threads.@threads over reference GXBeam instances).  Topology + pd/pl shared; per-instance arrays are contiguous
+// [nbatch][...] in the layouts of include/gxbeam_b200.h.  gravity: nbatch x 3 ; force_scaling: nbatch.
+int gxo_static_solve_batch(int64_t nbatch, const gxo_problem* q0, const double* gravity, const double* force_scaling, const gxo_opts* opts,
+                           const double* x0, double* x, int32_t* converged, int32_t* iters, double* resid_inf, int nthreads) {
+    Problem P0 = to_problem(q0);
+    Indices idx = system_indices(P0.ne, P0.start, P0.stop, true);
+    int64_t kl, ku; static_bandwidth(P0, idx, kl, ku);
+    int64_t n = idx.nstates;
+    NewtonOpts o = to_opts(opts);
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+      for (;;) {
+        int64_t b = next.fetch_add(1);   // dynamic schedule, one instance at a time
+        if (b >= nbatch) break;
+        Problem P = P0;
+        P.elems = P0.elems + b * P0.ne * 91;
+        P.points = P0.points ? P0.points + b * P0.np * 3 : nullptr;
+        P.bc = P0.bc + b * P0.np * 18;
+        P.dload = P0.dload ? P0.dload + b * P0.ne * 24 : nullptr;
+        P.pmass = P0.pmass ? P0.pmass + b * P0.np * 36 : nullptr;
+        if (gravity) for (int i = 0; i < 3; i++) P.gravity[i] = gravity[3 * b + i];
+        if (force_scaling) P.force_scaling = force_scaling[b];
+        std::vector<double> F(n);
+        NewtonResult r = static_solve_one(P, idx, kl, ku, o, x0 ? x0 + b * n : nullptr, x + b * n, F.data());
+        converged[b] = r.converged; iters[b] = (int32_t)r.iters; resid_inf[b] = r.resid_inf;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
+int gxo_num_threads() { int n = (int)std::thread::hardware_concurrency(); return n > 0 ? n : 1; }
+
+}  // extern "C"
