@@ -1,0 +1,283 @@
+"""ctypes binding of libgxbeam_b200.so (include/gxbeam_b200.h) and the batched analysis entry point.
+
+`static_analysis_batch` mirrors the reference's `static_analysis(assembly; prescribed_conditions, distributed_loads,
+point_masses, gravity, linear, two_dimensional, ftol, iterations, ...)` (src/analyses.jl:66-179) for a batch of
+independent assemblies that share one topology and one pd/pl pattern.  The product path is the CUDA library only: if the
+library is missing or no GPU is usable this module raises, it never falls back to a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import assembly as asm_mod
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def library_path():
+    return os.path.join(_HERE, "libgxbeam_b200.so")
+
+
+class GXBError(RuntimeError):
+    pass
+
+
+class Opts(C.Structure):
+    _fields_ = [("linear", C.c_int32), ("two_dimensional", C.c_int32), ("ftol", C.c_double), ("iterations", C.c_int64),
+                ("maxstep", C.c_double), ("c1", C.c_double), ("rho_hi", C.c_double), ("rho_lo", C.c_double),
+                ("profile", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("rounds", C.c_int64), ("launches", C.c_int64), ("newton_iters", C.c_int64), ("resid_evals", C.c_int64),
+                ("n_assemble", C.c_int64), ("n_factor", C.c_int64), ("n_update", C.c_int64), ("ms_assemble", C.c_double),
+                ("ms_factor", C.c_double), ("ms_update", C.c_double), ("ms_total", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "gxb_topology", "gxb_pattern", "gxb_set_batch",
+           "gxb_set_elements", "gxb_set_points", "gxb_set_bc", "gxb_set_dloads", "gxb_set_pmass", "gxb_set_body",
+           "gxb_static_solve", "gxb_upload_x0", "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats",
+           "gxb_static_residual_jacobian", "gxb_static_newton_direction"]
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library.  Fails loudly when it has not been built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise GXBError(f"{path} not found: build it with gxbeam_b200/csrc/build.sh (there is no CPU fallback)")
+        lib = C.CDLL(path)
+        lib.gxb_last_error.restype = C.c_char_p
+        for name in EXPORTS:
+            getattr(lib, name)  # AttributeError if a declared symbol is missing
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_void_p(int(a))
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def make_opts(linear=False, two_dimensional=False, ftol=1e-9, iterations=1000, maxstep=1e6, c1=1e-4, rho_hi=0.5, rho_lo=0.1,
+              profile=False):
+    return Opts(int(linear), int(two_dimensional), ftol, iterations, maxstep, c1, rho_hi, rho_lo, int(profile), 0)
+
+
+class Context:
+    """One gxb_ctx = one CUDA device.  Thin, literal wrapper over the C-ABI (host pointers in, host pointers out)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        self._ck(self.lib.gxb_create(C.byref(self.h), int(device)))
+        self.device = device
+        self.n = 0
+        self.nbatch = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GXBError(f"gxbeam_b200 error {rc}: {self.lib.gxb_last_error().decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.gxb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- topology / pattern ---
+    def topology(self, start, stop, pd=None, pl=None, kind=0):
+        start = np.ascontiguousarray(start, dtype=np.int64)
+        stop = np.ascontiguousarray(stop, dtype=np.int64)
+        ne = len(start)
+        npnt = int(max(start.max(), stop.max()))
+        pd = None if pd is None else np.ascontiguousarray(pd, dtype=np.uint8)
+        pl = None if pl is None else np.ascontiguousarray(pl, dtype=np.uint8)
+        n = C.c_int64(0)
+        irp, icp = np.zeros(npnt, np.int64), np.zeros(npnt, np.int64)
+        ire, ice = np.zeros(ne, np.int64), np.zeros(ne, np.int64)
+        self._ck(self.lib.gxb_topology(self.h, int(kind), C.c_int64(npnt), C.c_int64(ne), _ptr(start), _ptr(stop), _ptr(pd), _ptr(pl),
+                                       C.byref(n), _ptr(irp), _ptr(ire), _ptr(icp), _ptr(ice)))
+        self.n, self.np, self.ne = n.value, npnt, ne
+        self.start, self.stop = start, stop
+        self.indices = dict(nstates=n.value, irow_point=irp, irow_elem=ire, icol_point=icp, icol_elem=ice)
+        return self.indices
+
+    def pattern(self):
+        nb = C.c_int64(0)
+        self._ck(self.lib.gxb_pattern(self.h, C.byref(nb), None, None))
+        brow, bcol = np.zeros(nb.value, np.int64), np.zeros(nb.value, np.int64)
+        self._ck(self.lib.gxb_pattern(self.h, C.byref(nb), _ptr(brow), _ptr(bcol)))
+        return brow, bcol
+
+    # --- inputs ---
+    def set_batch(self, nbatch):
+        self._ck(self.lib.gxb_set_batch(self.h, C.c_int64(nbatch)))
+        self.nbatch = nbatch
+
+    def set_elements(self, elems):
+        e = _f64(elems)
+        assert e.size == self.nbatch * self.ne * asm_mod.ELEM_STRIDE, "elements must be nbatch x ne x 91"
+        self._ck(self.lib.gxb_set_elements(self.h, _ptr(e)))
+
+    def set_points(self, xyz):
+        self._ck(self.lib.gxb_set_points(self.h, _ptr(_f64(xyz))))
+
+    def set_bc(self, bc):
+        b = _f64(bc)
+        assert b.size == self.nbatch * self.np * asm_mod.BC_STRIDE, "bc must be nbatch x np x 18"
+        self._ck(self.lib.gxb_set_bc(self.h, _ptr(b)))
+
+    def set_dloads(self, dl):
+        d = _f64(dl)
+        assert d is None or d.size == self.nbatch * self.ne * asm_mod.DLOAD_STRIDE
+        self._ck(self.lib.gxb_set_dloads(self.h, _ptr(d)))
+
+    def set_pmass(self, pm):
+        p = _f64(pm)
+        assert p is None or p.size == self.nbatch * self.np * 36
+        self._ck(self.lib.gxb_set_pmass(self.h, _ptr(p)))
+
+    def set_body(self, gravity=None, force_scaling=None):
+        g = _f64(gravity)
+        fs = _f64(force_scaling)
+        assert g is None or g.size == self.nbatch * 3
+        assert fs is None or fs.size == self.nbatch
+        self._ck(self.lib.gxb_set_body(self.h, _ptr(g), _ptr(fs)))
+
+    # --- solves ---
+    def static_solve(self, opts=None, x0=None, out=None):
+        """Host buffers in / out (the e2e path).  `out` may carry preallocated (pinned) arrays x, converged, iters, resid_inf."""
+        o = opts or make_opts()
+        nb, n = self.nbatch, self.n
+        out = out or {}
+        x = out.get("x") if out.get("x") is not None else np.empty((nb, n))
+        conv = out.get("converged") if out.get("converged") is not None else np.empty(nb, np.int32)
+        its = out.get("iters") if out.get("iters") is not None else np.empty(nb, np.int32)
+        rinf = out.get("resid_inf") if out.get("resid_inf") is not None else np.empty(nb)
+        x0a = _f64(x0)
+        self._ck(self.lib.gxb_static_solve(self.h, C.byref(o), _ptr(x0a), _ptr(x), _ptr(conv), _ptr(its), _ptr(rinf)))
+        return dict(x=x, converged=conv.astype(bool), iters=its, resid_inf=rinf)
+
+    def upload_x0(self, x0=None):
+        self._ck(self.lib.gxb_upload_x0(self.h, _ptr(_f64(x0))))
+
+    def static_solve_resident(self, opts=None):
+        o = opts or make_opts()
+        self._ck(self.lib.gxb_static_solve_resident(self.h, C.byref(o)))
+
+    def fetch(self):
+        nb, n = self.nbatch, self.n
+        x = np.empty((nb, n)); conv = np.empty(nb, np.int32); its = np.empty(nb, np.int32); rinf = np.empty(nb)
+        self._ck(self.lib.gxb_fetch(self.h, _ptr(x), _ptr(conv), _ptr(its), _ptr(rinf)))
+        return dict(x=x, converged=conv.astype(bool), iters=its, resid_inf=rinf)
+
+    def stats(self):
+        st = Stats()
+        self._ck(self.lib.gxb_get_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def static_residual_jacobian(self, x, opts=None, want_jacobian=True):
+        o = opts or make_opts()
+        x = _f64(x).reshape(self.nbatch, self.n)
+        r = np.empty_like(x)
+        J = None
+        if want_jacobian:
+            brow, _ = self.pattern()
+            J = np.empty((self.nbatch, len(brow), 9))
+        self._ck(self.lib.gxb_static_residual_jacobian(self.h, C.byref(o), _ptr(x), _ptr(r), _ptr(J)))
+        return r, J
+
+    def static_newton_direction(self, x, opts=None):
+        o = opts or make_opts()
+        x = _f64(x).reshape(self.nbatch, self.n)
+        p = np.empty_like(x)
+        self._ck(self.lib.gxb_static_newton_direction(self.h, C.byref(o), _ptr(x), _ptr(p)))
+        return p
+
+
+def blocks_to_dense(n, brow, bcol, Jblk):
+    """Scatter one instance's 3x3 pattern blocks into a dense n x n matrix (tests only)."""
+    J = np.zeros((n, n))
+    for k in range(len(brow)):
+        J[brow[k]:brow[k] + 3, bcol[k]:bcol[k] + 3] = Jblk[k].reshape(3, 3)
+    return J
+
+
+@dataclass
+class BatchResult:
+    x: np.ndarray          # [nbatch, nstates]
+    converged: np.ndarray  # [nbatch] bool
+    iters: np.ndarray      # [nbatch] Newton iterations
+    resid_inf: np.ndarray  # [nbatch]
+    indices: dict
+    stats: dict
+
+
+def _solve_shard(device, start, stop, pd, pl, elems, bc, dl, pm, grav, fs, x0, opts):
+    ctx = Context(device)
+    try:
+        idx = ctx.topology(start, stop, pd, pl)
+        ctx.set_batch(elems.shape[0])
+        ctx.set_elements(elems)
+        ctx.set_bc(bc)
+        if dl is not None:
+            ctx.set_dloads(dl)
+        if pm is not None:
+            ctx.set_pmass(pm)
+        ctx.set_body(grav, fs)
+        res = ctx.static_solve(opts, x0)
+        return res, idx, ctx.stats()
+    finally:
+        ctx.close()
+
+
+def static_analysis_batch(start, stop, elements, prescribed_pd, prescribed_pl, prescribed_values, distributed_loads=None,
+                          point_masses=None, gravity=None, force_scaling=None, x0=None, linear=False, two_dimensional=False,
+                          ftol=1e-9, iterations=1000, devices=(0,), profile=False) -> BatchResult:
+    """Batched `static_analysis` (src/analyses.jl:66-179) over nbatch independent assemblies sharing a topology.
+
+    elements: [nbatch, ne, 91]; prescribed_values: [nbatch, np, 18]; pd/pl: [np, 6]; distributed_loads: [nbatch, ne, 24] | None;
+    point_masses: [nbatch, np, 36] | None; gravity: [nbatch, 3] | None; force_scaling: [nbatch] | None (-> 1.0).
+    The batch is sharded contiguously over `devices` (one context and one host thread per GPU, no collective); results
+    are gathered into single host arrays.
+    """
+    elements = _f64(elements)
+    nbatch = elements.shape[0]
+    bc = _f64(prescribed_values).reshape(nbatch, -1, 18)
+    opts = make_opts(linear=linear, two_dimensional=two_dimensional, ftol=ftol, iterations=iterations, profile=profile)
+    fs = np.ones(nbatch) if force_scaling is None else _f64(force_scaling)
+    bounds = np.linspace(0, nbatch, len(devices) + 1).astype(int)
+    sl = [slice(bounds[i], bounds[i + 1]) for i in range(len(devices)) if bounds[i + 1] > bounds[i]]
+    cut = lambda a, s: None if a is None else _f64(a)[s]
+    args = [(devices[i], start, stop, prescribed_pd, prescribed_pl, elements[s], bc[s], cut(distributed_loads, s), cut(point_masses, s),
+             cut(gravity, s), fs[s], cut(x0, s), opts) for i, s in enumerate(sl)]
+    if len(args) == 1:
+        outs = [_solve_shard(*args[0])]
+    else:
+        with ThreadPoolExecutor(len(args)) as ex:
+            outs = list(ex.map(lambda a: _solve_shard(*a), args))
+    x = np.concatenate([o[0]["x"] for o in outs])
+    conv = np.concatenate([o[0]["converged"] for o in outs])
+    its = np.concatenate([o[0]["iters"] for o in outs])
+    rinf = np.concatenate([o[0]["resid_inf"] for o in outs])
+    return BatchResult(x, conv, its, rinf, outs[0][1], outs[0][2])

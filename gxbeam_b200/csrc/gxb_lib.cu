@@ -1,0 +1,680 @@
+// gxbeam_b200 — host side of the C-ABI (include/gxbeam_b200.h) and the kernels that wrap the device code in
+// gxb_static.cuh (assembly) and gxb_lu.cuh (batched pivoted block-banded LU).
+//
+// Newton driver = NLsolve `newton` + LineSearches `BackTracking(order 3)` as reached from nlsolve!
+// (reference: src/analyses.jl:3556-3599; algorithm restated in SURVEY.md App. C), run as a per-instance state machine
+// that lives entirely in device memory.  One host-visible "round" is three launches:
+//     k_factor_solve   instances in state SOLVE : p = -(J \ F), first trial point xt = x + α0 p        -> state TRIAL
+//     k_assemble       instances in state TRIAL : Ft = r(xt), J = ∂r/∂x(xt)   (fused, one pass)
+//     k_update         instances in state TRIAL : Armijo test; accept (x = xt, F = Ft, J already at xt -> SOLVE / DONE)
+//                                                 or backtrack (new α, new xt, stay in TRIAL)
+// The host only reads one counter per round (instances still running).  There is no CPU fallback anywhere.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/gxbeam_b200.h"
+#include "gxb_lu.cuh"
+#include "gxb_static.cuh"
+
+// ------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(GXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+enum { ST_SOLVE = 0, ST_TRIAL = 1, ST_DONE = 2, ST_FAILED = 3 };
+enum { FAIL_NONE = 0, FAIL_NONFINITE = 1, FAIL_LINESEARCH = 2, FAIL_MAXITER = 3, FAIL_SINGULAR = 4 };
+
+// per-instance Newton / line-search scalars (structure of arrays)
+struct NewtonState {
+    int* status; int* failcode; int* iters; int* fcalls; int* ls_k; int* ls_finite;
+    double* a1; double* a2; double* phi0; double* dphi0; double* phx0; double* finf;
+};
+
+struct gxb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    // topology
+    int kind = -1;
+    int64_t np = 0, ne = 0, n = 0;
+    bool chain = false;
+    std::vector<int64_t> start, stop, irow_point, irow_elem, icol_point, icol_elem;
+    std::vector<uint8_t> pd, pl;
+    std::vector<int64_t> brow, bcol;   // canonical 3x3 pattern
+    unsigned short* d_flags = nullptr;
+    int64_t* d_brow = nullptr; int64_t* d_bcol = nullptr;
+    // batch
+    int64_t nbatch = 0;
+    double *d_elemS = nullptr, *d_bcS = nullptr, *d_dlS = nullptr, *d_pmS = nullptr, *d_grav = nullptr, *d_fs = nullptr, *d_xyz = nullptr;
+    int has_grav = 0;
+    double* d_stage = nullptr; size_t stage_bytes = 0;
+    // solver state
+    double *d_x = nullptr, *d_xt = nullptr, *d_F = nullptr, *d_Ft = nullptr, *d_p = nullptr, *d_J = nullptr, *d_U = nullptr;
+    NewtonState ns{};
+    int* d_counter = nullptr; int* h_counter = nullptr;
+    bool have_x0 = false;
+    gxb_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// packing kernels: caller's array-of-structs (the reference's memory layout) -> structure-of-arrays in HBM
+// elemS[b][f][e]: f=0 L; 1..9 Cab (row-major); 10..45 S11,S12,S21,S22 = L*compliance; 46..81 m11,m12,m21,m22 = L*mass
+#define GXB_ELEM_NF 82
+__global__ void k_pack_elements(const double* __restrict__ raw, double* __restrict__ out, int N, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * N) return;
+    int64_t b = t / N; int e = (int)(t % N);
+    const double* s = raw + t * GXB_ELEM_STRIDE;
+    double* o = out + (size_t)b * GXB_ELEM_NF * N + e;
+    const double L = s[0];
+    o[0] = L;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[(size_t)(1 + 3 * i + j) * N] = s[76 + i + 3 * j];
+    for (int bi = 0; bi < 2; bi++) for (int bj = 0; bj < 2; bj++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        int f = 9 * (2 * bi + bj) + 3 * i + j;
+        int src = (3 * bi + i) + 6 * (3 * bj + j);
+        o[(size_t)(10 + f) * N] = s[4 + src] * L;     // compliance *= L   (element.jl:69)
+        o[(size_t)(46 + f) * N] = s[40 + src] * L;    // mass *= L         (element.jl:70)
+    }
+}
+// out[b][f][p] = raw[b][p][f]
+__global__ void k_pack_transpose(const double* __restrict__ raw, double* __restrict__ out, int P, int F, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * P * F) return;
+    int f = (int)(t % F); int64_t q = t / F; int p = (int)(q % P); int64_t b = q / P;
+    out[((size_t)b * F + f) * P + p] = raw[t];
+}
+// point masses: raw[b][p][36 col-major] -> out[b][9*(2bi+bj)+3i+j][p]
+__global__ void k_pack_pmass(const double* __restrict__ raw, double* __restrict__ out, int P, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * P * 36) return;
+    int f = (int)(t % 36); int64_t q = t / 36; int p = (int)(q % P); int64_t b = q / P;
+    int blk = f / 9, i = (f % 9) / 3, j = f % 3, bi = blk / 2, bj = blk % 2;
+    out[((size_t)b * 36 + f) * P + p] = raw[q * 36 + (3 * bi + i) + 6 * (3 * bj + j)];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble(StaticArgs A) {
+    extern __shared__ double xch[];
+    const int b = blockIdx.x;
+    if (A.status && A.status[b] != A.want_status) return;
+    static_station<WANT_J>(A, b, threadIdx.x, xch);
+}
+
+struct SolveArgs {
+    int nb, n; int64_t nbatch;
+    const double* J; const double* F; const double* x; double* U; double* p; double* xt;
+    NewtonState ns;
+    double maxstep; int linear;
+    int direction_only;   // parity entry point: just p, no state change
+};
+
+template <int KLB, int KUB> __global__ void __launch_bounds__(128) k_factor_solve(SolveArgs A) {
+    using S = LuShape<KLB, KUB>;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= A.nbatch) return;
+    if (!A.direction_only && A.ns.status[b] != ST_SOLVE) return;
+    double* sm = smem + (size_t)warp * S::SM_DOUBLES;
+    const size_t n = A.n;
+    const double* F = A.F + b * n;
+    double* p = A.p + b * n;
+    int bad = warp_band_solve<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * n * S::UW, p, A.nb, -1.0, sm);
+    __syncwarp();
+    if (A.direction_only) return;
+    if (bad) { if (lane == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
+    // |p|_inf, φ0 = ½ F'F, dφ0 = g'p with g = J'F and J p = -F  =>  dφ0 = -F'F
+    double pm = 0.0, ff = 0.0;
+    for (int c = lane; c < (int)n; c += 32) { pm = fmax(pm, fabs(p[c])); double f = F[c]; ff = fma(f, f, ff); }
+    for (int o = 16; o; o >>= 1) { pm = fmax(pm, __shfl_xor_sync(GXB_FULL, pm, o)); ff += __shfl_xor_sync(GXB_FULL, ff, o); }
+    const double a0 = A.linear ? 1.0 : fmin(1.0, A.maxstep / pm);
+    const double* x = A.x + b * n; double* xt = A.xt + b * n;
+    for (int c = lane; c < (int)n; c += 32) xt[c] = x[c] + a0 * p[c];
+    if (lane == 0) {
+        A.ns.a1[b] = a0; A.ns.a2[b] = a0; A.ns.phi0[b] = 0.5 * ff; A.ns.dphi0[b] = -ff; A.ns.phx0[b] = 0.5 * ff;
+        A.ns.ls_k[b] = 0; A.ns.ls_finite[b] = 0; A.ns.status[b] = ST_TRIAL;
+    }
+}
+
+struct UpdateArgs {
+    int n; int mode;   // mode 0: initial evaluation, 1: line-search step, 2: linear (accept unconditionally, converged)
+    double* x; double* xt; double* F; const double* Ft; const double* p;
+    NewtonState ns;
+    double ftol, c1, rho_hi, rho_lo; int64_t iterations; int ls_iterations;
+    int* counter;
+};
+
+__global__ void __launch_bounds__(128) k_update(UpdateArgs A) {
+    const int b = blockIdx.x;
+    if (A.ns.status[b] != ST_TRIAL) return;
+    const size_t n = A.n;
+    const double* Ft = A.Ft + b * n;
+    // all per-instance scalars are read before the reduction barrier; thread 0 rewrites them only after it
+    const double a1 = A.ns.a1[b], a2 = A.ns.a2[b], phi0 = A.ns.phi0[b], dphi0 = A.ns.dphi0[b], phx0 = A.ns.phx0[b];
+    int k = A.ns.ls_k[b], nf = A.ns.ls_finite[b];
+    int iters = A.ns.iters[b];
+    __shared__ double s_sum[4], s_max[4]; __shared__ int s_nan[4];
+    double ss = 0.0, mx = 0.0; int nan = 0;
+    for (int c = threadIdx.x; c < (int)n; c += blockDim.x) { double f = Ft[c]; ss = fma(f, f, ss); mx = fmax(mx, fabs(f)); nan |= (f != f); }
+    for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(GXB_FULL, ss, o); mx = fmax(mx, __shfl_xor_sync(GXB_FULL, mx, o)); nan |= __shfl_xor_sync(GXB_FULL, nan, o); }
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = ss; s_max[threadIdx.x >> 5] = mx; s_nan[threadIdx.x >> 5] = nan; }
+    __syncthreads();
+    ss = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
+    mx = fmax(fmax(s_max[0], s_max[1]), fmax(s_max[2], s_max[3]));
+    nan = s_nan[0] | s_nan[1] | s_nan[2] | s_nan[3];
+    const double phx1 = 0.5 * ss;
+    const bool finite = isfinite(ss) && !nan;
+    double* x = A.x + b * n; double* xt = A.xt + b * n; double* F = A.F + b * n; const double* p = A.p + b * n;
+    // every thread takes the same decision from the same scalars
+    bool accept = false; int newstatus = ST_TRIAL; int failcode = FAIL_NONE; double a_new = 0.0;
+    if (A.mode == 0) {
+        accept = true;
+        if (!finite) { newstatus = ST_FAILED; failcode = FAIL_NONFINITE; }     // NLsolve check_isfinite
+        else newstatus = (mx <= A.ftol) ? ST_DONE : ST_SOLVE;
+        if (newstatus == ST_SOLVE && A.iterations <= 0) { newstatus = ST_FAILED; failcode = FAIL_MAXITER; }
+    } else if (A.mode == 2) {
+        accept = true; newstatus = ST_DONE; iters = 1;
+    } else {
+        double n_a1 = a1, n_a2 = a2, n_phx0 = phx0;
+        if (k == 0 && !isfinite(phx1) && nf < 52) {                 // back off until finite (LineSearches iterfinite loop)
+            nf++; n_a1 = a2; n_a2 = a2 / 2;
+        } else if (phx1 > phi0 + A.c1 * a2 * dphi0) {               // Armijo fails -> interpolate
+            k++;
+            if (k > A.ls_iterations) { newstatus = ST_FAILED; failcode = FAIL_LINESEARCH; }
+            double at;
+            if (k == 1) at = -(dphi0 * a2 * a2) / (2 * (phx1 - phi0 - dphi0 * a2));
+            else {
+                double dv = 1.0 / (a1 * a1 * a2 * a2 * (a2 - a1));
+                double ca = (a1 * a1 * (phx1 - phi0 - dphi0 * a2) - a2 * a2 * (phx0 - phi0 - dphi0 * a1)) * dv;
+                double cb = (-a1 * a1 * a1 * (phx1 - phi0 - dphi0 * a2) + a2 * a2 * a2 * (phx0 - phi0 - dphi0 * a1)) * dv;
+                if (fabs(ca) <= 2.220446049250313e-16) at = dphi0 / (2 * cb);
+                else { double d = fmax(cb * cb - 3 * ca * dphi0, 0.0); at = (-cb + sqrt(d)) / (3 * ca); }
+            }
+            n_a1 = a2;
+            double hi = a2 * A.rho_hi, lo = a2 * A.rho_lo;
+            at = (at != at) ? hi : fmin(at, hi);
+            n_a2 = fmax(at, lo);
+            n_phx0 = phx1;
+        } else {
+            accept = true;
+        }
+        if (!accept && newstatus == ST_TRIAL) {
+            a_new = n_a2;
+            if (threadIdx.x == 0) { A.ns.a1[b] = n_a1; A.ns.a2[b] = n_a2; A.ns.phx0[b] = n_phx0; A.ns.ls_k[b] = k; A.ns.ls_finite[b] = nf; }
+        }
+        if (accept) {
+            iters++;
+            const bool fconv = mx <= A.ftol;                         // maximum(abs, F) <= ftol ; NaN compares false
+            bool stopped = nan != 0;
+            bool xzero = true;                                       // x-convergence: ||x - xold||_inf <= xtol = 0
+            for (int c = threadIdx.x; c < (int)n; c += blockDim.x) { if (xt[c] != x[c]) xzero = false; if (xt[c] != xt[c]) stopped = true; }
+            xzero = __syncthreads_and(xzero); stopped = __syncthreads_or(stopped);
+            if (fconv) newstatus = ST_DONE;
+            else if (stopped) { newstatus = ST_FAILED; failcode = FAIL_NONFINITE; }
+            else if (xzero) { newstatus = ST_FAILED; failcode = FAIL_LINESEARCH; }
+            else if (iters >= A.iterations) { newstatus = ST_FAILED; failcode = FAIL_MAXITER; }
+            else newstatus = ST_SOLVE;
+        }
+    }
+    if (accept) {
+        for (int c = threadIdx.x; c < (int)n; c += blockDim.x) { x[c] = xt[c]; F[c] = Ft[c]; }
+        if (threadIdx.x == 0) { A.ns.finf[b] = mx; A.ns.iters[b] = iters; }
+    } else if (newstatus == ST_TRIAL) {
+        for (int c = threadIdx.x; c < (int)n; c += blockDim.x) xt[c] = x[c] + a_new * p[c];
+    }
+    if (threadIdx.x == 0) {
+        A.ns.fcalls[b] += 1;
+        A.ns.status[b] = newstatus;
+        if (failcode) A.ns.failcode[b] = failcode;
+        if (newstatus == ST_SOLVE || newstatus == ST_TRIAL) atomicAdd(A.counter, 1);
+    }
+}
+
+__global__ void k_fill_int(int* p, int v, int64_t n) { int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (t < n) p[t] = v; }
+
+// Jblk[b][k][3i+j] = J[brow[k]+i, bcol[k]+j] read back from the row-block storage
+__global__ void k_extract_blocks(const double* __restrict__ Jrow, const int64_t* __restrict__ brow, const int64_t* __restrict__ bcol,
+                                 double* __restrict__ out, int64_t nblk, int n, int W, int KLB, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * nblk * 9) return;
+    int e = (int)(t % 9); int64_t q = t / 9; int64_t k = q % nblk; int64_t b = q / nblk;
+    int64_t r = brow[k] + e / 3, c = bcol[k] + e % 3;
+    int64_t slot = c - 6 * (r / 6 - KLB);
+    out[t] = (slot >= 0 && slot < W) ? Jrow[((size_t)b * n + r) * W + slot] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+static void free_batch(gxb_ctx* c) {
+    cudaFree(c->d_elemS); cudaFree(c->d_bcS); cudaFree(c->d_dlS); cudaFree(c->d_pmS); cudaFree(c->d_grav); cudaFree(c->d_fs); cudaFree(c->d_xyz);
+    cudaFree(c->d_x); cudaFree(c->d_xt); cudaFree(c->d_F); cudaFree(c->d_Ft); cudaFree(c->d_p); cudaFree(c->d_J); cudaFree(c->d_U);
+    cudaFree(c->ns.status); cudaFree(c->ns.failcode); cudaFree(c->ns.iters); cudaFree(c->ns.fcalls); cudaFree(c->ns.ls_k); cudaFree(c->ns.ls_finite);
+    cudaFree(c->ns.a1); cudaFree(c->ns.a2); cudaFree(c->ns.phi0); cudaFree(c->ns.dphi0); cudaFree(c->ns.phx0); cudaFree(c->ns.finf);
+    cudaFree(c->d_stage);
+    c->d_elemS = c->d_bcS = c->d_dlS = c->d_pmS = c->d_grav = c->d_fs = c->d_xyz = nullptr;
+    c->d_x = c->d_xt = c->d_F = c->d_Ft = c->d_p = c->d_J = c->d_U = nullptr;
+    c->ns = NewtonState{};
+    c->d_stage = nullptr; c->stage_bytes = 0; c->nbatch = 0;
+}
+
+static int stage_upload(gxb_ctx* c, const void* host, size_t bytes) {
+    if (bytes > c->stage_bytes) {
+        cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0;
+        CK(cudaMalloc(&c->d_stage, bytes));
+        c->stage_bytes = bytes;
+    }
+    CK(cudaMemcpyAsync(c->d_stage, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return GXB_OK;
+}
+
+template <class T> static int dalloc(T** p, size_t count) { CK(cudaMalloc((void**)p, count * sizeof(T))); return GXB_OK; }
+
+static inline unsigned grid1(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+extern "C" {
+
+void gxb_default_opts(gxb_opts* o) {
+    memset(o, 0, sizeof(*o));
+    o->ftol = 1e-9; o->iterations = 1000; o->maxstep = 1e6; o->c1 = 1e-4; o->rho_hi = 0.5; o->rho_lo = 0.1;
+}
+
+const char* gxb_last_error(void) { return g_err.c_str(); }
+
+int gxb_create(gxb_ctx** out, int device) {
+    if (!out) return fail(GXB_ERR_INVALID, "gxb_create: null ctx pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(GXB_ERR_CUDA, std::string("gxb_create: no usable CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(GXB_ERR_INVALID, "gxb_create: bad device index");
+    CK(cudaSetDevice(device));
+    gxb_ctx* c = new gxb_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->d_counter, sizeof(int)));
+    CK(cudaMallocHost(&c->h_counter, sizeof(int)));
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); CK(cudaEventCreate(&c->evA)); CK(cudaEventCreate(&c->evB));
+    *out = c;
+    return GXB_OK;
+}
+
+void gxb_destroy(gxb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_batch(c);
+    cudaFree(c->d_flags); cudaFree(c->d_brow); cudaFree(c->d_bcol); cudaFree(c->d_counter); cudaFreeHost(c->h_counter);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evA); cudaEventDestroy(c->evB);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int gxb_topology(gxb_ctx* c, int kind, int64_t np, int64_t ne, const int64_t* start, const int64_t* stop, const uint8_t* pd,
+                 const uint8_t* pl, int64_t* nstates, int64_t* irow_point, int64_t* irow_elem, int64_t* icol_point, int64_t* icol_elem) {
+    if (!c || !start || !stop || ne < 1 || np < 2) return fail(GXB_ERR_INVALID, "gxb_topology: bad arguments");
+    if (kind != 0 && kind != 1) return fail(GXB_ERR_INVALID, "gxb_topology: kind must be 0 (static) or 1 (dynamic)");
+    CK(cudaSetDevice(c->device));
+    int64_t pmax = 0;
+    for (int64_t e = 0; e < ne; e++) {
+        if (start[e] < 1 || stop[e] < 1) return fail(GXB_ERR_INVALID, "gxb_topology: point indices are 1-based");
+        pmax = std::max(pmax, std::max(start[e], stop[e]));
+    }
+    if (pmax != np) return fail(GXB_ERR_INVALID, "gxb_topology: np must equal max(maximum(start), maximum(stop)) (system.jl:32)");
+    // SystemIndices (system.jl:29-122): walk the elements; a point gets its rows/cols the first time it is seen
+    const bool is_static = kind == 0;
+    c->kind = kind; c->np = np; c->ne = ne;
+    c->start.assign(start, start + ne); c->stop.assign(stop, stop + ne);
+    c->irow_point.assign(np, 0); c->icol_point.assign(np, 0); c->irow_elem.assign(ne, 0); c->icol_elem.assign(ne, 0);
+    std::vector<char> seen(np, 0);
+    int64_t cur = 1;
+    for (int64_t e = 0; e < ne; e++) {
+        for (int side = 0; side < 2; side++) {
+            int64_t ip = (side ? stop[e] : start[e]) - 1;
+            if (side == 1) { c->irow_elem[e] = cur; c->icol_elem[e] = cur; cur += 6; }
+            if (!seen[ip]) { seen[ip] = 1; c->irow_point[ip] = cur; c->icol_point[ip] = cur; cur += is_static ? 6 : 12; }
+        }
+    }
+    c->n = cur - 1;
+    c->pd.assign((size_t)np * 6, 0); c->pl.assign((size_t)np * 6, 1);
+    if (pd) c->pd.assign(pd, pd + np * 6);
+    if (pl) c->pl.assign(pl, pl + np * 6);
+    c->chain = true;
+    for (int64_t e = 0; e < ne; e++) if (start[e] != e + 1 || stop[e] != e + 2) c->chain = false;
+    if (np != ne + 1) c->chain = false;
+    // canonical 3x3-block pattern (static): point.jl:1795-1797, element.jl:2507-2549
+    c->brow.clear(); c->bcol.clear();
+    if (is_static) {
+        auto blk = [&](int64_t r, int64_t cc) { c->brow.push_back(r - 1); c->bcol.push_back(cc - 1); };
+        for (int64_t ip = 0; ip < np; ip++) {
+            int64_t ir = c->irow_point[ip], ic = c->icol_point[ip];
+            blk(ir, ic); blk(ir, ic + 3); blk(ir + 3, ic + 3);
+        }
+        for (int64_t e = 0; e < ne; e++) {
+            int64_t ic = c->icol_elem[e], ic1 = c->icol_point[start[e] - 1], ic2 = c->icol_point[stop[e] - 1];
+            int64_t ir = c->irow_elem[e], ir1 = c->irow_point[start[e] - 1], ir2 = c->irow_point[stop[e] - 1];
+            blk(ir, ic1); blk(ir, ic1 + 3); blk(ir, ic2); blk(ir, ic2 + 3); blk(ir, ic); blk(ir, ic + 3);
+            blk(ir + 3, ic1 + 3); blk(ir + 3, ic2 + 3); blk(ir + 3, ic); blk(ir + 3, ic + 3);
+            for (int64_t irp : {ir1, ir2}) {
+                blk(irp, ic1 + 3); blk(irp, ic2 + 3); blk(irp, ic);
+                blk(irp + 3, ic1 + 3); blk(irp + 3, ic2 + 3); blk(irp + 3, ic); blk(irp + 3, ic + 3);
+            }
+        }
+        // unique (a point's own θ-block is also touched by its elements)
+        std::vector<std::pair<int64_t, int64_t>> v;
+        for (size_t k = 0; k < c->brow.size(); k++) v.push_back({c->brow[k], c->bcol[k]});
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        c->brow.clear(); c->bcol.clear();
+        for (auto& q : v) { c->brow.push_back(q.first); c->bcol.push_back(q.second); }
+    }
+    std::vector<unsigned short> flags(np);
+    for (int64_t ip = 0; ip < np; ip++) {
+        unsigned f = 0;
+        for (int k = 0; k < 6; k++) { if (c->pd[ip * 6 + k]) f |= 1u << k; if (c->pl[ip * 6 + k]) f |= 64u << k; }
+        flags[ip] = (unsigned short)f;
+    }
+    cudaFree(c->d_flags); cudaFree(c->d_brow); cudaFree(c->d_bcol); c->d_flags = nullptr; c->d_brow = c->d_bcol = nullptr;
+    CK(cudaMalloc(&c->d_flags, np * sizeof(unsigned short)));
+    CK(cudaMemcpy(c->d_flags, flags.data(), np * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    if (!c->brow.empty()) {
+        CK(cudaMalloc(&c->d_brow, c->brow.size() * 8)); CK(cudaMalloc(&c->d_bcol, c->bcol.size() * 8));
+        CK(cudaMemcpy(c->d_brow, c->brow.data(), c->brow.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_bcol, c->bcol.data(), c->bcol.size() * 8, cudaMemcpyHostToDevice));
+    }
+    free_batch(c);
+    if (nstates) *nstates = c->n;
+    if (irow_point) memcpy(irow_point, c->irow_point.data(), np * 8);
+    if (icol_point) memcpy(icol_point, c->icol_point.data(), np * 8);
+    if (irow_elem) memcpy(irow_elem, c->irow_elem.data(), ne * 8);
+    if (icol_elem) memcpy(icol_elem, c->icol_elem.data(), ne * 8);
+    return GXB_OK;
+}
+
+int gxb_pattern(gxb_ctx* c, int64_t* nblocks, int64_t* brow, int64_t* bcol) {
+    if (!c || c->kind < 0) return fail(GXB_ERR_INVALID, "gxb_pattern: call gxb_topology first");
+    if (c->kind != 0) return fail(GXB_ERR_UNSUPPORTED, "gxb_pattern: only the static system is implemented on the device");
+    if (nblocks) *nblocks = (int64_t)c->brow.size();
+    if (brow) memcpy(brow, c->brow.data(), c->brow.size() * 8);
+    if (bcol) memcpy(bcol, c->bcol.data(), c->bcol.size() * 8);
+    return GXB_OK;
+}
+
+static int require_static_chain(gxb_ctx* c, const char* who) {
+    if (!c || c->kind < 0) return fail(GXB_ERR_INVALID, std::string(who) + ": call gxb_topology first");
+    if (c->kind != 0) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": only kind=0 (StaticSystem) is implemented on the device so far");
+    if (!c->chain) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": only chain topologies (start = 1:n, stop = 2:n+1) are implemented on the device");
+    if (c->np > 256) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": more than 255 elements per assembly not supported yet");
+    return GXB_OK;
+}
+
+int gxb_set_batch(gxb_ctx* c, int64_t nbatch) {
+    int rc = require_static_chain(c, "gxb_set_batch"); if (rc) return rc;
+    if (nbatch < 1) return fail(GXB_ERR_INVALID, "gxb_set_batch: nbatch < 1");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_batch(c);
+    c->nbatch = nbatch;
+    const size_t nb = (size_t)nbatch, n = (size_t)c->n, N = (size_t)c->ne, P = (size_t)c->np;
+    if ((rc = dalloc(&c->d_elemS, nb * GXB_ELEM_NF * N))) return rc;
+    if ((rc = dalloc(&c->d_bcS, nb * 18 * P))) return rc;
+    if ((rc = dalloc(&c->d_fs, nb))) return rc;
+    if ((rc = dalloc(&c->d_grav, nb * 3))) return rc;
+    if ((rc = dalloc(&c->d_x, nb * n)) || (rc = dalloc(&c->d_xt, nb * n)) || (rc = dalloc(&c->d_F, nb * n)) || (rc = dalloc(&c->d_Ft, nb * n)) ||
+        (rc = dalloc(&c->d_p, nb * n))) return rc;
+    if ((rc = dalloc(&c->d_J, nb * n * LuShape<2, 2>::W)) || (rc = dalloc(&c->d_U, nb * n * LuShape<2, 2>::UW))) return rc;
+    if ((rc = dalloc(&c->ns.status, nb)) || (rc = dalloc(&c->ns.failcode, nb)) || (rc = dalloc(&c->ns.iters, nb)) || (rc = dalloc(&c->ns.fcalls, nb)) ||
+        (rc = dalloc(&c->ns.ls_k, nb)) || (rc = dalloc(&c->ns.ls_finite, nb))) return rc;
+    if ((rc = dalloc(&c->ns.a1, nb)) || (rc = dalloc(&c->ns.a2, nb)) || (rc = dalloc(&c->ns.phi0, nb)) || (rc = dalloc(&c->ns.dphi0, nb)) ||
+        (rc = dalloc(&c->ns.phx0, nb)) || (rc = dalloc(&c->ns.finf, nb))) return rc;
+    // structural zeros of the row-block storage are written once, here
+    CK(cudaMemsetAsync(c->d_J, 0, nb * n * LuShape<2, 2>::W * 8, c->stream));
+    CK(cudaMemsetAsync(c->d_grav, 0, nb * 3 * 8, c->stream));
+    CK(cudaMemsetAsync(c->d_x, 0, nb * n * 8, c->stream));
+    std::vector<double> ones(nb, 1.0);
+    CK(cudaMemcpyAsync(c->d_fs, ones.data(), nb * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->has_grav = 0; c->have_x0 = false;
+    return GXB_OK;
+}
+
+#define NEED_BATCH(who) do { if (!c || c->nbatch < 1) return fail(GXB_ERR_INVALID, who ": call gxb_set_batch first"); CK(cudaSetDevice(c->device)); } while (0)
+
+int gxb_set_elements(gxb_ctx* c, const double* elems) {
+    NEED_BATCH("gxb_set_elements");
+    if (!elems) return fail(GXB_ERR_INVALID, "gxb_set_elements: null");
+    int rc = stage_upload(c, elems, (size_t)c->nbatch * c->ne * GXB_ELEM_STRIDE * 8); if (rc) return rc;
+    k_pack_elements<<<grid1(c->nbatch * c->ne, 128), 128, 0, c->stream>>>(c->d_stage, c->d_elemS, (int)c->ne, c->nbatch);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));   // the caller may reuse its buffer
+    return GXB_OK;
+}
+int gxb_set_points(gxb_ctx* c, const double* xyz) {
+    NEED_BATCH("gxb_set_points");
+    (void)xyz;   // point coordinates only enter the dynamic residuals (Δx in point.jl:643); unused by the static path
+    return GXB_OK;
+}
+int gxb_set_bc(gxb_ctx* c, const double* bc) {
+    NEED_BATCH("gxb_set_bc");
+    if (!bc) return fail(GXB_ERR_INVALID, "gxb_set_bc: null");
+    int rc = stage_upload(c, bc, (size_t)c->nbatch * c->np * 18 * 8); if (rc) return rc;
+    k_pack_transpose<<<grid1(c->nbatch * c->np * 18, 256), 256, 0, c->stream>>>(c->d_stage, c->d_bcS, (int)c->np, 18, c->nbatch);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return GXB_OK;
+}
+int gxb_set_dloads(gxb_ctx* c, const double* dl) {
+    NEED_BATCH("gxb_set_dloads");
+    if (!dl) { cudaFree(c->d_dlS); c->d_dlS = nullptr; return GXB_OK; }
+    if (!c->d_dlS) { int rc = dalloc(&c->d_dlS, (size_t)c->nbatch * 24 * c->ne); if (rc) return rc; }
+    int rc = stage_upload(c, dl, (size_t)c->nbatch * c->ne * 24 * 8); if (rc) return rc;
+    k_pack_transpose<<<grid1(c->nbatch * c->ne * 24, 256), 256, 0, c->stream>>>(c->d_stage, c->d_dlS, (int)c->ne, 24, c->nbatch);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return GXB_OK;
+}
+int gxb_set_pmass(gxb_ctx* c, const double* pm) {
+    NEED_BATCH("gxb_set_pmass");
+    if (!pm) { cudaFree(c->d_pmS); c->d_pmS = nullptr; return GXB_OK; }
+    if (!c->d_pmS) { int rc = dalloc(&c->d_pmS, (size_t)c->nbatch * 36 * c->np); if (rc) return rc; }
+    int rc = stage_upload(c, pm, (size_t)c->nbatch * c->np * 36 * 8); if (rc) return rc;
+    k_pack_pmass<<<grid1(c->nbatch * c->np * 36, 256), 256, 0, c->stream>>>(c->d_stage, c->d_pmS, (int)c->np, c->nbatch);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return GXB_OK;
+}
+int gxb_set_body(gxb_ctx* c, const double* gravity, const double* force_scaling) {
+    NEED_BATCH("gxb_set_body");
+    c->has_grav = 0;
+    if (gravity) {
+        for (int64_t i = 0; i < c->nbatch * 3; i++) if (gravity[i] != 0.0) { c->has_grav = 1; break; }
+        CK(cudaMemcpyAsync(c->d_grav, gravity, (size_t)c->nbatch * 24, cudaMemcpyHostToDevice, c->stream));
+    } else CK(cudaMemsetAsync(c->d_grav, 0, (size_t)c->nbatch * 24, c->stream));
+    if (force_scaling) {
+        for (int64_t i = 0; i < c->nbatch; i++) if (!(force_scaling[i] > 0.0)) return fail(GXB_ERR_INVALID, "gxb_set_body: force_scaling must be positive");
+        CK(cudaMemcpyAsync(c->d_fs, force_scaling, (size_t)c->nbatch * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return GXB_OK;
+}
+
+int gxb_upload_x0(gxb_ctx* c, const double* x0) {
+    NEED_BATCH("gxb_upload_x0");
+    if (x0) { CK(cudaMemcpyAsync(c->d_x, x0, (size_t)c->nbatch * c->n * 8, cudaMemcpyHostToDevice, c->stream)); c->have_x0 = true; }
+    else c->have_x0 = false;
+    return GXB_OK;
+}
+
+// ---- launch helpers ----
+struct Prof {
+    gxb_ctx* c; bool on;
+    void begin() { if (on) cudaEventRecord(c->evA, c->stream); }
+    void end(double& acc) { if (on) { cudaEventRecord(c->evB, c->stream); cudaEventSynchronize(c->evB); float ms = 0; cudaEventElapsedTime(&ms, c->evA, c->evB); acc += ms; } }
+};
+
+static StaticArgs make_static_args(gxb_ctx* c, const gxb_opts* o, const double* x, double* r, bool want_j, int want_status, bool use_status) {
+    StaticArgs A{};
+    A.N = (int)c->ne; A.n = (int)c->n; A.two_d = o->two_dimensional; A.has_grav = c->has_grav;
+    A.elemS = c->d_elemS; A.elem_nf = GXB_ELEM_NF; A.bcS = c->d_bcS; A.dlS = c->d_dlS; A.pmS = c->d_pmS; A.grav = c->d_grav; A.fs = c->d_fs;
+    A.flags = c->d_flags; A.x = x; A.r = r; A.Jrow = want_j ? c->d_J : nullptr;
+    A.status = use_status ? c->ns.status : nullptr; A.want_status = want_status;
+    return A;
+}
+static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
+    int bs = (int)((c->np + 31) / 32) * 32;
+    size_t sm = (size_t)bs * GXB_XCH * 8;
+    if (want_j) k_assemble<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
+    else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
+    CK(cudaGetLastError());
+    c->stats.launches++; c->stats.n_assemble++;
+    return GXB_OK;
+}
+static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only) {
+    using S = LuShape<2, 2>;
+    SolveArgs A{};
+    A.nb = (int)(c->n / 6); A.n = (int)c->n; A.nbatch = c->nbatch;
+    A.J = c->d_J; A.F = direction_only ? c->d_Ft : c->d_F; A.x = c->d_x; A.U = c->d_U; A.p = c->d_p; A.xt = c->d_xt; A.ns = c->ns;
+    A.maxstep = o->maxstep; A.linear = o->linear; A.direction_only = direction_only;
+    const int wpc = 4;
+    size_t sm = (size_t)wpc * S::SM_DOUBLES * 8;
+    k_factor_solve<2, 2><<<grid1(c->nbatch, wpc), 32 * wpc, sm, c->stream>>>(A);
+    CK(cudaGetLastError());
+    c->stats.launches++; c->stats.n_factor++;
+    return GXB_OK;
+}
+static int launch_update(gxb_ctx* c, const gxb_opts* o, int mode) {
+    UpdateArgs A{};
+    A.n = (int)c->n; A.mode = mode; A.x = c->d_x; A.xt = c->d_xt; A.F = c->d_F; A.Ft = c->d_Ft; A.p = c->d_p; A.ns = c->ns;
+    A.ftol = o->ftol; A.c1 = o->c1; A.rho_hi = o->rho_hi; A.rho_lo = o->rho_lo; A.iterations = o->iterations; A.ls_iterations = 1000;
+    A.counter = c->d_counter;
+    k_update<<<(unsigned)c->nbatch, 128, 0, c->stream>>>(A);
+    CK(cudaGetLastError());
+    c->stats.launches++; c->stats.n_update++;
+    return GXB_OK;
+}
+
+int gxb_static_solve_resident(gxb_ctx* c, const gxb_opts* opts) {
+    NEED_BATCH("gxb_static_solve_resident");
+    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    c->stats = gxb_stats{};
+    Prof prof{c, o.profile != 0};
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    int rc;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (!c->have_x0) CK(cudaMemsetAsync(c->d_x, 0, nb * n * 8, c->stream));   // reset_state (system.jl:383-386)
+    CK(cudaMemcpyAsync(c->d_xt, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, ST_TRIAL, nb);
+    CK(cudaMemsetAsync(c->ns.failcode, 0, nb * 4, c->stream)); CK(cudaMemsetAsync(c->ns.iters, 0, nb * 4, c->stream));
+    CK(cudaMemsetAsync(c->ns.fcalls, 0, nb * 4, c->stream));
+    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+    // initial value_jacobian!!(df, x0)
+    StaticArgs A = make_static_args(c, &o, c->d_xt, c->d_Ft, true, ST_TRIAL, true);
+    prof.begin(); if ((rc = launch_assemble(c, A, true))) return rc; prof.end(c->stats.ms_assemble);
+    prof.begin(); if ((rc = launch_update(c, &o, 0))) return rc; prof.end(c->stats.ms_update);
+    if (o.linear) {
+        // lsolve! (analyses.jl:3506-3524): x = x0 - J\r, converged = true.  State after mode 0 may be DONE (r == 0): force one step.
+        k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, ST_SOLVE, nb);
+        prof.begin(); if ((rc = launch_factor(c, &o, 0))) return rc; prof.end(c->stats.ms_factor);
+        // final residual r(x) is not re-evaluated by the reference; keep F = r(x0) like lsolve! leaves `resid`
+        CK(cudaMemcpyAsync(c->d_Ft, c->d_F, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        prof.begin(); if ((rc = launch_update(c, &o, 2))) return rc; prof.end(c->stats.ms_update);
+        c->stats.rounds = 1;
+    } else {
+        for (int64_t round = 0;; round++) {
+            CK(cudaMemcpyAsync(c->h_counter, c->d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (*c->h_counter == 0) break;
+            CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+            prof.begin(); if ((rc = launch_factor(c, &o, 0))) return rc; prof.end(c->stats.ms_factor);
+            prof.begin(); if ((rc = launch_assemble(c, A, true))) return rc; prof.end(c->stats.ms_assemble);
+            prof.begin(); if ((rc = launch_update(c, &o, 1))) return rc; prof.end(c->stats.ms_update);
+            c->stats.rounds = round + 1;
+        }
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->stats.ms_total = ms;
+    // totals
+    std::vector<int> it(nb), fc(nb);
+    CK(cudaMemcpy(it.data(), c->ns.iters, nb * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(fc.data(), c->ns.fcalls, nb * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nb; i++) { c->stats.newton_iters += it[i]; c->stats.resid_evals += fc[i]; }
+    c->have_x0 = false;
+    return GXB_OK;
+}
+
+int gxb_fetch(gxb_ctx* c, double* x, int32_t* converged, int32_t* iters, double* resid_inf) {
+    NEED_BATCH("gxb_fetch");
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    if (x) CK(cudaMemcpyAsync(x, c->d_x, nb * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (iters) CK(cudaMemcpyAsync(iters, c->ns.iters, nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (resid_inf) CK(cudaMemcpyAsync(resid_inf, c->ns.finf, nb * 8, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int> st;
+    if (converged) { st.resize(nb); CK(cudaMemcpyAsync(st.data(), c->ns.status, nb * 4, cudaMemcpyDeviceToHost, c->stream)); }
+    CK(cudaStreamSynchronize(c->stream));
+    if (converged) for (size_t i = 0; i < nb; i++) converged[i] = st[i] == ST_DONE;
+    return GXB_OK;
+}
+
+int gxb_get_stats(gxb_ctx* c, gxb_stats* st) {
+    if (!c || !st) return fail(GXB_ERR_INVALID, "gxb_get_stats: null");
+    *st = c->stats;
+    return GXB_OK;
+}
+
+int gxb_static_solve(gxb_ctx* c, const gxb_opts* opts, const double* x0, double* x, int32_t* converged, int32_t* iters, double* resid_inf) {
+    int rc;
+    if ((rc = gxb_upload_x0(c, x0))) return rc;
+    if ((rc = gxb_static_solve_resident(c, opts))) return rc;
+    return gxb_fetch(c, x, converged, iters, resid_inf);
+}
+
+int gxb_static_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double* x, double* r, double* Jblk) {
+    NEED_BATCH("gxb_static_residual_jacobian");
+    if (!x) return fail(GXB_ERR_INVALID, "gxb_static_residual_jacobian: x is null");
+    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    CK(cudaMemcpyAsync(c->d_xt, x, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
+    StaticArgs A = make_static_args(c, &o, c->d_xt, c->d_Ft, Jblk != nullptr, 0, false);
+    int rc = launch_assemble(c, A, Jblk != nullptr); if (rc) return rc;
+    if (r) CK(cudaMemcpyAsync(r, c->d_Ft, nb * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (Jblk) {
+        const size_t nblk = c->brow.size();
+        size_t bytes = nb * nblk * 9 * 8;
+        if (bytes > c->stage_bytes) { cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0; CK(cudaMalloc(&c->d_stage, bytes)); c->stage_bytes = bytes; }
+        k_extract_blocks<<<grid1(nb * nblk * 9, 256), 256, 0, c->stream>>>(c->d_J, c->d_brow, c->d_bcol, c->d_stage, (int64_t)nblk, (int)n, LuShape<2, 2>::W, 2, c->nbatch);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(Jblk, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return GXB_OK;
+}
+
+int gxb_static_newton_direction(gxb_ctx* c, const gxb_opts* opts, const double* x, double* p) {
+    NEED_BATCH("gxb_static_newton_direction");
+    if (!x || !p) return fail(GXB_ERR_INVALID, "gxb_static_newton_direction: null");
+    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    CK(cudaMemcpyAsync(c->d_xt, x, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
+    StaticArgs A = make_static_args(c, &o, c->d_xt, c->d_Ft, true, 0, false);
+    int rc = launch_assemble(c, A, true); if (rc) return rc;
+    if ((rc = launch_factor(c, &o, 1))) return rc;
+    CK(cudaMemcpyAsync(p, c->d_p, nb * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return GXB_OK;
+}
+
+}  // extern "C"

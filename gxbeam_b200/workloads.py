@@ -1,0 +1,75 @@
+"""Synthetic batches of the BASELINE.json configurations, shared by bench.py and the parity tests.
+
+All draws come from numpy.random.default_rng(1234 + cfg) so that the GPU run, the CPU oracle and every rank of a
+multi-GPU run see identical inputs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .assembly import Assembly, PrescribedConditions, pack_prescribed_conditions
+
+
+def cantilever_tipmoment_batch(nbatch=4096, nelem=100, seed=1234 + 2, shear_rigid=False, tip_force=False):
+    """BASELINE config 2: `nbatch` independent `nelem`-element nonlinear cantilevers under a tip moment (static_analysis).
+
+    Base case = test/examples/tipmoment.jl:5-50 (L = 12, E = 30e6, h = w = 1, root clamped, Mz at the tip) with
+    randomised stiffness (E_i = E·U(0.8,1.2), h_i, w_i = U(0.9,1.1)) and load factor λ_i = U(0.1,1.0) of π E Izz / L.
+    Finite shear/torsion compliance (G = E/2.6) unless `shear_rigid` (the test's zeros).
+    Returns a dict of packed arrays in the C-ABI layouts.
+    """
+    rng = np.random.default_rng(seed)
+    L = 12.0
+    E0 = 30e6
+    xs = np.linspace(0.0, L, nelem + 1)
+    points = np.stack([xs, 0 * xs, 0 * xs], 1)
+    start = np.arange(1, nelem + 1, dtype=np.int64)
+    stop = np.arange(2, nelem + 2, dtype=np.int64)
+    E = E0 * rng.uniform(0.8, 1.2, nbatch)
+    h = rng.uniform(0.9, 1.1, nbatch)
+    w = rng.uniform(0.9, 1.1, nbatch)
+    lam = rng.uniform(0.1, 1.0, nbatch)
+    fz = rng.uniform(0.0, 1.0, nbatch)
+    A = h * w
+    Iyy = w * h ** 3 / 12
+    Izz = w ** 3 * h / 12
+    G = E / 2.6
+    diag = np.zeros((nbatch, 6))
+    diag[:, 0] = 1 / (E * A)
+    if not shear_rigid:
+        diag[:, 1] = 1 / (G * A * 5 / 6)
+        diag[:, 2] = 1 / (G * A * 5 / 6)
+        diag[:, 3] = 1 / (G * (Iyy + Izz))
+    diag[:, 4] = 1 / (E * Iyy)
+    diag[:, 5] = 1 / (E * Izz)
+    # Element{Float64} records: L, x[3], compliance[36], mass[36], Cab[9], mu[6]
+    elems = np.zeros((nbatch, nelem, 91))
+    dL = L / nelem
+    elems[:, :, 0] = dL
+    elems[:, :, 1] = ((xs[:-1] + xs[1:]) / 2)[None, :]
+    for k in range(6):
+        elems[:, :, 4 + 7 * k] = diag[:, k][:, None]      # diagonal of the column-major 6x6
+    elems[:, :, 76] = elems[:, :, 80] = elems[:, :, 84] = 1.0  # Cab = I
+    elems[:, :, 85:91] = 0.01
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0), nelem + 1: PrescribedConditions(Mz=1.0)}
+    pd, pl, bc1 = pack_prescribed_conditions(nelem + 1, pcs)
+    bc = np.tile(bc1[None], (nbatch, 1, 1))
+    bc[:, nelem, 11] = lam * np.pi * E * Izz / L          # Mz
+    if tip_force:
+        bc[:, nelem, 8] = fz * E * Iyy / L ** 2           # Fz
+    # default_force_scaling (system.jl:190-208) per instance
+    nnz = (diag > np.finfo(float).eps).sum(1) * nelem
+    csum = diag.sum(1) * nelem
+    fs = 2.0 ** np.ceil(np.log2(nnz / csum / 100))
+    return dict(start=start, stop=stop, points=points, pd=pd, pl=pl, elems=elems, bc=bc, force_scaling=fs, nelem=nelem,
+                nbatch=nbatch, lam=lam)
+
+
+def single_assembly_arrays(assembly: Assembly, prescribed_conditions, dloads=None, pmasses=None):
+    """Pack one Assembly + loads into batch-of-one arrays."""
+    from .assembly import pack_distributed_loads, pack_point_masses
+    pd, pl, bc = pack_prescribed_conditions(assembly.np_, prescribed_conditions)
+    return dict(start=assembly.start, stop=assembly.stop, points=assembly.points, pd=pd, pl=pl,
+                elems=assembly.pack_elements()[None], bc=bc[None],
+                dload=None if not dloads else pack_distributed_loads(assembly.ne, dloads)[None],
+                pmass=None if not pmasses else pack_point_masses(assembly.np_, pmasses)[None])

@@ -1,0 +1,111 @@
+/* gxbeam_b200 — C-ABI of the B200-native batched Newton solver for GXBeam's residual/Jacobian/solve hot path.
+ *
+ * The reference (byuflowlab/GXBeam.jl, pure Julia) has no FFI layer.  The seam this library sits behind is the pair
+ *     nlsolve!(p, constants, residual!, jacobian!)         src/analyses.jl:3556-3599
+ *     lsolve!(x0, p, constants, residual!, jacobian!)      src/analyses.jl:3506-3524
+ * as reached from static_analysis! (src/analyses.jl:78-179).  Every entry point below names the reference code it
+ * replaces.  Julia binds these with `ccall` from a new `static_analysis_batch`; in this repository
+ * the same symbols are bound with ctypes (gxbeam_b200/api.py).
+ *
+ * Conventions: every function returns 0 on success and a GXB_ERR_* code otherwise (message via gxb_last_error());
+ * nothing throws across the boundary; the caller owns every host buffer (plain contiguous Float64 / Int64 / UInt8
+ * arrays, Julia column-major == "last index slowest" as written below); the library owns all device memory.
+ * A context is bound to one CUDA device and must be used by one host thread at a time.  There is no CPU fallback:
+ * if no CUDA device is usable gxb_create fails.
+ */
+#ifndef GXBEAM_B200_H
+#define GXBEAM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GXB_OK 0
+#define GXB_ERR_INVALID 1      /* bad argument / call order */
+#define GXB_ERR_CUDA 2         /* CUDA runtime error */
+#define GXB_ERR_UNSUPPORTED 3  /* topology or option the device path does not implement (fails loudly) */
+
+#define GXB_ELEM_STRIDE 91  /* Element{Float64}: L, x[3], compliance[36], mass[36], Cab[9], mu[6]  (src/assembly.jl:14-21) */
+#define GXB_BC_STRIDE 18    /* PrescribedConditions: u, theta, F, M, Ff, Mf                      (src/loads.jl:16-25)   */
+#define GXB_DLOAD_STRIDE 24 /* DistributedLoads: f1,f2,m1,m2,f1_follower,...,m2_follower          (src/loads.jl:262-271) */
+
+typedef struct gxb_ctx gxb_ctx;
+
+/* Keyword arguments of static_analysis! that reach the solver (src/analyses.jl:78-102) plus the BackTracking constants
+ * of LineSearches (c_1, rho_hi, rho_lo). */
+typedef struct gxb_opts {
+    int32_t linear;          /* linear=true: one step x = x0 - J\r, converged = true   (analyses.jl:3506-3524) */
+    int32_t two_dimensional; /* system.jl:1072-1103 */
+    double ftol;             /* 1e-9 */
+    int64_t iterations;      /* 1000 */
+    double maxstep;          /* 1e6 */
+    double c1, rho_hi, rho_lo; /* 1e-4, 0.5, 0.1 */
+    int32_t profile;         /* !=0: time every kernel class with CUDA events (gxb_get_stats) */
+    int32_t reserved;
+} gxb_opts;
+
+/* Filled by gxb_get_stats after a solve. */
+typedef struct gxb_stats {
+    int64_t rounds;            /* host-visible Newton/line-search rounds */
+    int64_t launches;          /* kernels launched by the last solve */
+    int64_t newton_iters;      /* sum over instances of Newton iterations (= linear solves) */
+    int64_t resid_evals;       /* sum over instances of residual evaluations */
+    int64_t n_assemble, n_factor, n_update; /* launches per kernel class */
+    double ms_assemble, ms_factor, ms_update; /* summed device time per class (only with opts.profile) */
+    double ms_total;           /* device time of the whole resident solve */
+} gxb_stats;
+
+void gxb_default_opts(gxb_opts* o);
+
+/* Create / destroy a context on CUDA device `device`. */
+int gxb_create(gxb_ctx** ctx, int device);
+void gxb_destroy(gxb_ctx* ctx);
+const char* gxb_last_error(void);
+
+/* SystemIndices(start, stop; static = kind==0)                                        src/system.jl:29-122
+ * kind: 0 = StaticSystem (6 states / point), 1 = DynamicSystem (12 states / point).
+ * start/stop: ne, 1-based.  pd/pl: np x 6 flags shared by the whole batch (they fix the sparsity pattern).
+ * Outputs (may be NULL): nstates, irow_point[np], irow_elem[ne], icol_point[np], icol_elem[ne], 1-based, bit-exact. */
+int gxb_topology(gxb_ctx* ctx, int kind, int64_t np, int64_t ne, const int64_t* start, const int64_t* stop, const uint8_t* pd,
+                 const uint8_t* pl, int64_t* nstates, int64_t* irow_point, int64_t* irow_elem, int64_t* icol_point,
+                 int64_t* icol_elem);
+
+/* Canonical structural pattern of the Jacobian at 3x3-block granularity (what insert_static_point_jacobians!
+ * src/point.jl:1785-1800 and insert_static_element_jacobians! src/element.jl:2487-2552 can touch).
+ * Returns the number of blocks in *nblocks; brow/bcol (may be NULL) receive the 0-based scalar row/col of each block. */
+int gxb_pattern(gxb_ctx* ctx, int64_t* nblocks, int64_t* brow, int64_t* bcol);
+
+/* Per-instance inputs.  All arrays are [nbatch][...] contiguous.  gxb_set_batch first. */
+int gxb_set_batch(gxb_ctx* ctx, int64_t nbatch);
+int gxb_set_elements(gxb_ctx* ctx, const double* elems);   /* nbatch x ne x 91   assembly.elements            */
+int gxb_set_points(gxb_ctx* ctx, const double* xyz);       /* nbatch x np x 3    assembly.points (dynamic only) */
+int gxb_set_bc(gxb_ctx* ctx, const double* bc);            /* nbatch x np x 18   prescribed_conditions values  */
+int gxb_set_dloads(gxb_ctx* ctx, const double* dl);        /* nbatch x ne x 24 or NULL   distributed_loads     */
+int gxb_set_pmass(gxb_ctx* ctx, const double* pm);         /* nbatch x np x 36 (col-major 6x6) or NULL  point_masses */
+int gxb_set_body(gxb_ctx* ctx, const double* gravity /* nbatch x 3 or NULL */, const double* force_scaling /* nbatch */);
+
+/* static_analysis!: nlsolve!/lsolve! over the batch                       src/analyses.jl:137-171, 3506-3599
+ * x0: nbatch x nstates initial guess or NULL (zeros, = reset_state).  Outputs: x (nbatch x nstates), converged, iters
+ * (Newton iterations), resid_inf (||r||_inf of the final residual); each may be NULL. */
+int gxb_static_solve(gxb_ctx* ctx, const gxb_opts* opts, const double* x0, double* x, int32_t* converged, int32_t* iters,
+                     double* resid_inf);
+
+/* The same solve on inputs already resident in HBM (no host<->device traffic): x0 from gxb_upload_x0 or zeros. */
+int gxb_upload_x0(gxb_ctx* ctx, const double* x0 /* or NULL */);
+int gxb_static_solve_resident(gxb_ctx* ctx, const gxb_opts* opts);
+int gxb_fetch(gxb_ctx* ctx, double* x, int32_t* converged, int32_t* iters, double* resid_inf);
+int gxb_get_stats(gxb_ctx* ctx, gxb_stats* st);
+
+/* static_system_residual! + static_system_jacobian! at given states      src/system.jl:400-418, 663-683
+ * x: nbatch x nstates.  r: nbatch x nstates.  Jblk: nbatch x nblocks x 9, each 3x3 row-major on gxb_pattern's blocks. */
+int gxb_static_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* r, double* Jblk);
+
+/* One Newton direction p = -(J(x) \ r(x)) per instance (the `linsolve` of analyses.jl:3585), for parity tests of the
+ * batched pivoted block-banded LU in isolation.  p: nbatch x nstates. */
+int gxb_static_newton_direction(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

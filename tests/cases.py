@@ -1,0 +1,156 @@
+"""Test cases restated from the reference's own tests (test/examples/*.jl, test/jacobians.jl) as packed C-ABI arrays.
+
+Each builder returns a dict with start, stop, points, pd, pl, elems[1,ne,91], bc[1,np,18], dload, pmass, gravity,
+force_scaling plus case-specific extras.  Used for the oracle tests (CPU) and the GPU parity tests alike.
+"""
+import numpy as np
+
+from gxbeam_b200.assembly import (Assembly, PrescribedConditions, default_force_scaling, discretize_beam, distributed_loads,
+                                  pack_distributed_loads, pack_point_masses, pack_prescribed_conditions)
+
+
+def _pack(asm, pcs, dl=None, pm=None, gravity=(0.0, 0.0, 0.0), **extra):
+    pd, pl, bc = pack_prescribed_conditions(asm.np_, pcs)
+    d = dict(start=asm.start, stop=asm.stop, points=asm.points, pd=pd, pl=pl, elems=asm.pack_elements()[None], bc=bc[None],
+             dload=None if not dl else pack_distributed_loads(asm.ne, dl)[None],
+             pmass=None if not pm else pack_point_masses(asm.np_, pm)[None], gravity=np.asarray(gravity, float),
+             force_scaling=default_force_scaling(asm), asm=asm)
+    d.update(extra)
+    return d
+
+
+def tipmoment(lam, nelem=16):
+    """test/examples/tipmoment.jl:5-50"""
+    L, h, w, E = 12.0, 1.0, 1.0, 30e6
+    A, Iyy, Izz = h * w, w * h ** 3 / 12, w ** 3 * h / 12
+    M = lam * np.pi * E * Iyy / L
+    x = np.linspace(0, L, nelem + 1)
+    points = np.stack([x, 0 * x, 0 * x], 1)
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    comp = [np.diag([1 / (E * A), 0, 0, 0, 1 / (E * Iyy), 1 / (E * Izz)])] * nelem
+    asm = Assembly(points, start, stop, compliance=comp)
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0), nelem + 1: PrescribedConditions(Mz=M)}
+    rho = E * Iyy / M if M != 0 else np.inf
+    return _pack(asm, pcs, rho=rho)
+
+
+def tipforce(lam, nelem=16):
+    """test/examples/tipforce.jl:5-45"""
+    L, EI = 1.0, 1e6
+    P = lam * EI / L ** 2
+    x = np.linspace(0, L, nelem + 1)
+    points = np.stack([x, 0 * x, 0 * x], 1)
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    comp = [np.diag([0, 0, 0, 0, 1 / EI, 0])] * nelem
+    asm = Assembly(points, start, stop, compliance=comp)
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0), nelem + 1: PrescribedConditions(Fz=P)}
+    return _pack(asm, pcs)
+
+
+def curved(nelem=16, P=600.0):
+    """test/examples/curved.jl:5-58 (Bathe-Bolourchi 45-degree bend); reference output recorded to 16 digits at :56-58."""
+    R = 100.0
+    L = R * np.pi / 4
+    h = w = 1.0
+    E = 1e7
+    G = E / 2
+    frame = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+    A = h * w
+    Iyy, Izz = w * h ** 3 / 12, w ** 3 * h / 12
+    Jt = Iyy + Izz
+    dL, xp, xm, Cab = discretize_beam(L, [0, 0, 0], nelem, frame=frame, curvature=[0, 0, -1 / R])
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    comp = [np.diag([1 / (E * A), 1 / (G * A), 1 / (G * A), 1 / (G * Jt), 1 / (E * Iyy), 1 / (E * Izz)])] * nelem
+    asm = Assembly(xp, start, stop, compliance=comp, frames=Cab, lengths=dL, midpoints=xm)
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0), nelem + 1: PrescribedConditions(Fz=P)}
+    return _pack(asm, pcs, ref_tip_u=np.array([-13.577383726758564, -23.545303336988038, 53.45800757548929]))
+
+
+def cantilever_partial_load(nelem=12):
+    """test/examples/cantilever.jl:5-96 (linear, uniform load on the middle third, clamped at the right end)."""
+    a, b, L = 0.3, 0.7, 1.0
+    n1 = n3 = nelem // 3
+    n2 = nelem - n1 - n3
+    x = np.concatenate([np.linspace(0, a, n1 + 1), np.linspace(a, b, n2 + 1)[1:], np.linspace(b, L, n3 + 1)[1:]])
+    points = np.stack([x, 0 * x, 0 * x], 1)
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    EI = 1e9
+    asm = Assembly(points, start, stop, stiffness=[np.diag([0, 0, 0, 0, EI, 0])] * nelem)
+    pcs = {nelem + 1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
+    q = 1000.0
+    dl = {ie: distributed_loads(asm, ie, fz=lambda s: q) for ie in range(n1 + 1, n1 + n2 + 1)}
+
+    def defl(xx):
+        s0 = -q / (6 * EI) * ((L - a) ** 3 - (L - b) ** 3)
+        d0 = q / (24 * EI) * ((L - a) ** 3 * (3 * L + a) - (L - b) ** 3 * (3 * L + b))
+        d = d0 + s0 * xx
+        if a < xx <= b:
+            d += q / (24 * EI) * (xx - a) ** 4
+        elif xx > b:
+            d += q / (24 * EI) * ((xx - a) ** 4 - (xx - b) ** 4)
+        return d
+
+    return _pack(asm, pcs, dl=dl, deflection=defl)
+
+
+def overdetermined(nelem=16):
+    """test/examples/overdetermined.jl:5-68 (linear, propped cantilever under a linearly varying load)."""
+    L, EI, qmax = 1.0, 1e7, 1000.0
+    x = np.linspace(0, L, nelem + 1)
+    points = np.stack([x, 0 * x, 0 * x], 1)
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    asm = Assembly(points, start, stop, compliance=[np.diag([0, 0, 0, 0, 1 / EI, 0])] * nelem)
+    pcs = {1: PrescribedConditions(uz=0), nelem + 1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
+    dl = {i: distributed_loads(asm, i, s1=x[i - 1], s2=x[i], fz=lambda s: qmax * s) for i in range(1, nelem + 1)}
+    defl = lambda xx: qmax * (1 - xx) ** 2 / (120 * EI) * (4 - 8 * (1 - xx) + 5 * (1 - xx) ** 2 - (1 - xx) ** 3)
+    return _pack(asm, pcs, dl=dl, deflection=defl)
+
+
+def random_anisotropic(seed=0, nelem=2, followers=True, gravity=True, pmass=True, dloads=True):
+    """The system of test/jacobians.jl:98-175 (fully populated 6x6 stiffness/mass, tip point mass, gravity, follower loads,
+    a DOF with theta_y = 0 prescribed) with our own seeded draws of the same magnitudes (Julia's RNG is unavailable)."""
+    rng = np.random.default_rng(seed)
+    L = 60.0
+    x = np.linspace(0, L, nelem + 1)
+    points = np.stack([x, 0 * x, 0 * x], 1)
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    A = rng.random((6, 6))
+    stiff = (A @ A.T + 6 * np.eye(6)) * 1e5
+    B = rng.random((6, 6))
+    mass = B @ B.T + np.eye(6)
+    frames = []
+    for _ in range(nelem):
+        q, _r = np.linalg.qr(rng.standard_normal((3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        frames.append(q)
+    asm = Assembly(points, start, stop, stiffness=[stiff] * nelem, mass=[mass] * nelem, frames=frames)
+    tip = dict(Fx=1e3 * rng.random(), Mz=1e3 * rng.random(), theta_y=0.0)
+    if followers:
+        tip.update(Fy_follower=1e3 * rng.random(), Mx_follower=1e2 * rng.random())
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0), nelem + 1: PrescribedConditions(**tip)}
+    if nelem > 2 and followers:
+        pcs[2] = PrescribedConditions(Fz_follower=50.0 * rng.random(), My=10.0)
+    dl = None
+    if dloads:
+        dl = {1: distributed_loads(asm, 1, fx=lambda s: 10 * s, fz_follower=lambda s: 3.0, my=lambda s: 2.0, mz_follower=lambda s: s)}
+    pm = None
+    if pmass:
+        M = rng.random((6, 6))
+        pm = {nelem + 1: 1e3 * (M + M.T) / 2}
+    g = 1e3 * rng.random(3) if gravity else (0, 0, 0)
+    return _pack(asm, pcs, dl=dl, pm=pm, gravity=g)
+
+
+def oracle_packed(case, b=0, two_dimensional=False):
+    """Build the oracle's Problem for instance b of a (possibly batched) case."""
+    from oracle import pyoracle as O
+    g = np.asarray(case.get("gravity", np.zeros(3)), float)
+    g = g[b] if g.ndim == 2 else g
+    fs = case["force_scaling"]
+    fs = float(fs[b]) if np.ndim(fs) else float(fs)
+    dl = case.get("dload")
+    pm = case.get("pmass")
+    return O.Packed(case["start"], case["stop"], case["elems"][b], case["points"], case["pd"], case["pl"], case["bc"][b],
+                    None if dl is None else dl[b], None if pm is None else pm[b], gravity=g, force_scaling=fs,
+                    two_dimensional=two_dimensional)

@@ -1,0 +1,268 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): indices and sparsity pattern bit-exact; states / reactions within 1e-9 relative;
+`converged` flags and Newton iteration counts identical on well-conditioned cases.
+"""
+import numpy as np
+import pytest
+
+import cases
+from gxbeam_b200 import api, workloads
+from gxbeam_b200.state import assembly_state
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9  # north_star tolerance on states and reactions
+
+
+def _oracle():
+    from oracle import pyoracle as O
+    return O
+
+
+def _ctx_for(case, nbatch=None):
+    ctx = api.Context(0)
+    ctx.topology(case["start"], case["stop"], case["pd"], case["pl"])
+    nb = case["elems"].shape[0] if nbatch is None else nbatch
+    ctx.set_batch(nb)
+    ctx.set_elements(case["elems"][:nb])
+    ctx.set_bc(case["bc"][:nb])
+    if case.get("dload") is not None:
+        ctx.set_dloads(case["dload"][:nb])
+    if case.get("pmass") is not None:
+        ctx.set_pmass(case["pmass"][:nb])
+    g = case.get("gravity")
+    if g is not None:
+        g = np.broadcast_to(np.asarray(g, float).reshape(-1, 3), (nb, 3)).copy()
+    fs = np.broadcast_to(np.asarray(case["force_scaling"], float).reshape(-1), (nb,)).copy()
+    ctx.set_body(g, fs)
+    return ctx
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_indices_bit_exact():
+    O = _oracle()
+    for n in (1, 2, 16, 100):
+        start, stop = np.arange(1, n + 1), np.arange(2, n + 2)
+        ctx = api.Context(0)
+        idx = ctx.topology(start, stop)
+        ref = O.indices(start, stop, True)
+        assert idx["nstates"] == ref["nstates"]
+        for k in ("irow_point", "irow_elem", "icol_point", "icol_elem"):
+            assert np.array_equal(idx[k], ref[k])
+        ctx.close()
+
+
+def test_unsupported_topology_fails_loudly():
+    ctx = api.Context(0)
+    ctx.topology([1, 2, 2], [2, 3, 4])          # indices are still produced (bit-exact, general connectivity)
+    assert list(ctx.indices["icol_point"]) == [1, 13, 25, 37]
+    with pytest.raises(api.GXBError, match="chain"):
+        ctx.set_batch(4)
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed,nelem", [(0, 2), (1, 3), (2, 7)])
+@pytest.mark.parametrize("two_d", [False, True])
+def test_residual_and_jacobian_parity_random_states(seed, nelem, two_d):
+    O = _oracle()
+    case = cases.random_anisotropic(seed, nelem=nelem)
+    pk = cases.oracle_packed(case, two_dimensional=two_d)
+    ctx = _ctx_for(case)
+    n = ctx.n
+    rng = np.random.default_rng(seed)
+    brow, bcol = ctx.pattern()
+    for scale in (1.0, 1e2):                       # 1e2 exercises rotation_parameter_scaling != 1
+        x = scale * rng.random((1, n))
+        r, Jb = ctx.static_residual_jacobian(x, api.make_opts(two_dimensional=two_d))
+        r_ref = O.static_residual(pk, x[0])
+        J_ref = O.static_jacobian(pk, x[0])
+        assert _relerr(r[0], r_ref) < 1e-12
+        J = api.blocks_to_dense(n, brow, bcol, Jb[0])
+        assert np.abs(J - J_ref).max() <= 1e-12 * np.abs(J_ref).max()
+        # sparsity pattern: everything the reference can touch lies inside the canonical pattern ...
+        mask = api.blocks_to_dense(n, brow, bcol, np.ones((len(brow), 9))) != 0
+        assert np.all(J_ref[~mask] == 0.0)
+    ctx.close()
+
+
+def test_pattern_is_canonical_and_bit_exact():
+    # 24 blocks / element + 3 / point, minus the shared point θ-blocks counted twice
+    O = _oracle()
+    case = cases.random_anisotropic(0, nelem=5)
+    ctx = _ctx_for(case)
+    brow, bcol = ctx.pattern()
+    n = ctx.n
+    # oracle-side structural pattern: union over random states of the nonzeros of the oracle Jacobian, grown to 3x3 blocks
+    pk = cases.oracle_packed(case)
+    rng = np.random.default_rng(1)
+    nz = np.zeros((n, n), bool)
+    for _ in range(3):
+        nz |= O.static_jacobian(pk, 10 * rng.random(n)) != 0
+    blocks = {(3 * (i // 3), 3 * (j // 3)) for i, j in zip(*np.nonzero(nz))}
+    ours = set(zip(brow.tolist(), bcol.tolist()))
+    assert blocks <= ours
+    # blocks of ours that are numerically empty here must be structurally reachable ones only (zero 3x3 writes)
+    assert len(ours) == 24 * 5 + 3 * 6 - 4 * 5
+    assert sorted(ours) == list(zip(brow.tolist(), bcol.tolist()))
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_newton_direction_parity(seed):
+    """Batched pivoted block-banded LU vs a dense LAPACK solve of the oracle's Jacobian."""
+    O = _oracle()
+    case = cases.random_anisotropic(seed, nelem=9)
+    pk = cases.oracle_packed(case)
+    ctx = _ctx_for(case)
+    rng = np.random.default_rng(seed)
+    x = rng.random((1, ctx.n))
+    p = ctx.static_newton_direction(x)
+    J = O.static_jacobian(pk, x[0])
+    r = O.static_residual(pk, x[0])
+    p_ref = -np.linalg.solve(J, r)
+    assert _relerr(p[0], p_ref) < 1e-9
+    ctx.close()
+
+
+def _solve_case(case, **kw):
+    ctx = _ctx_for(case)
+    res = ctx.static_solve(api.make_opts(**kw))
+    st = ctx.stats()
+    idx = ctx.indices
+    ctx.close()
+    return res, st, idx
+
+
+def _check_states(case, x_gpu, x_ref, idx, b=0):
+    a = assembly_state(x_gpu, case["start"], case["stop"], idx["icol_point"], idx["icol_elem"], case["pd"], case["pl"], case["bc"][b],
+                       float(np.ravel(case["force_scaling"])[b] if np.ndim(case["force_scaling"]) else case["force_scaling"]))
+    r = assembly_state(x_ref, case["start"], case["stop"], idx["icol_point"], idx["icol_elem"], case["pd"], case["pl"], case["bc"][b],
+                       float(np.ravel(case["force_scaling"])[b] if np.ndim(case["force_scaling"]) else case["force_scaling"]))
+    for f in ("point_u", "point_theta", "point_F", "point_M", "elem_u", "elem_theta", "elem_Fi", "elem_Mi"):
+        va, vr = getattr(a, f), getattr(r, f)
+        scale = max(np.abs(vr).max(), 1e-12)
+        assert np.abs(va - vr).max() <= RTOL * scale, f
+
+
+@pytest.mark.parametrize("lam", [0.0, 0.4, 1.2, 2.0])
+def test_tipmoment_solve_parity(lam):
+    O = _oracle()
+    case = cases.tipmoment(lam)
+    ref = O.static_solve(cases.oracle_packed(case))
+    res, st, idx = _solve_case(case)
+    assert bool(res["converged"][0]) == ref["converged"]
+    assert int(res["iters"][0]) == ref["iters"]
+    _check_states(case, res["x"][0], ref["x"], idx)
+
+
+def test_curved_beam_parity_and_recorded_reference_output():
+    O = _oracle()
+    case = cases.curved()
+    ref = O.static_solve(cases.oracle_packed(case))
+    res, st, idx = _solve_case(case)
+    assert res["converged"][0] and ref["converged"]
+    _check_states(case, res["x"][0], ref["x"], idx)
+    ic = idx["icol_point"][-1] - 1
+    assert np.allclose(res["x"][0, ic:ic + 3], case["ref_tip_u"], rtol=1e-9, atol=0)   # curved.jl:56-58
+
+
+@pytest.mark.parametrize("builder", [cases.cantilever_partial_load, cases.overdetermined])
+def test_linear_analysis_parity(builder):
+    O = _oracle()
+    case = builder()
+    ref = O.static_solve(cases.oracle_packed(case), linear=True)
+    res, st, idx = _solve_case(case, linear=True)
+    assert res["converged"][0] and res["iters"][0] == 1
+    _check_states(case, res["x"][0], ref["x"], idx)
+    a = assembly_state(res["x"][0], case["start"], case["stop"], idx["icol_point"], idx["icol_elem"], case["pd"], case["pl"], case["bc"][0],
+                       case["force_scaling"])
+    for ip, xi in enumerate(case["points"][:, 0]):
+        assert abs(a.point_u[ip, 2] - case["deflection"](xi)) <= 1e-8
+
+
+@pytest.mark.parametrize("two_d", [False, True])
+def test_gravity_pointmass_follower_solve_parity(two_d):
+    O = _oracle()
+    case = cases.random_anisotropic(5, nelem=6)
+    case["gravity"] = np.array([0.0, 0.0, -9.81])
+    if two_d:   # keep the planar problem well posed: loads in the x-y plane only
+        case = cases.random_anisotropic(5, nelem=6, followers=False, pmass=False, dloads=False, gravity=False)
+    ref = O.static_solve(cases.oracle_packed(case, two_dimensional=two_d))
+    res, st, idx = _solve_case(case, two_dimensional=two_d)
+    assert bool(res["converged"][0]) == ref["converged"]
+    if ref["converged"]:
+        assert int(res["iters"][0]) == ref["iters"]
+        _check_states(case, res["x"][0], ref["x"], idx)
+
+
+def test_tipforce_batch_with_backtracking_parity():
+    """A mixed batch (different loads -> different iteration counts and line-search paths) against per-instance oracle solves."""
+    O = _oracle()
+    lams = [0.5, 2.0, 4.0, 8.0, 12.0, 16.0]
+    cs = [cases.tipforce(l) for l in lams]
+    case = dict(cs[0])
+    case["elems"] = np.concatenate([c["elems"] for c in cs])
+    case["bc"] = np.concatenate([c["bc"] for c in cs])
+    case["force_scaling"] = np.array([c["force_scaling"] for c in cs])
+    res, st, idx = _solve_case(case)
+    for b, c in enumerate(cs):
+        ref = O.static_solve(cases.oracle_packed(c))
+        assert bool(res["converged"][b]) == ref["converged"]
+        assert int(res["iters"][b]) == ref["iters"], (lams[b], res["iters"][b], ref["iters"])
+        _check_states(case, res["x"][b], ref["x"], idx, b)
+    assert st["newton_iters"] == int(res["iters"].sum())
+
+
+def test_c2_subset_parity_against_oracle():
+    """BASELINE config 2 at reduced batch: every instance checked against the oracle."""
+    O = _oracle()
+    w = workloads.cantilever_tipmoment_batch(48, 100)
+    ctx = _ctx_for(w)
+    res = ctx.static_solve()
+    idx = ctx.indices
+    ctx.close()
+    pk = O.Packed(w["start"], w["stop"], w["elems"], w["points"], w["pd"], w["pl"], w["bc"])
+    ref = O.static_solve_batch(pk, 48, force_scaling=w["force_scaling"])
+    assert np.array_equal(res["converged"], ref["converged"].astype(bool)) and res["converged"].all()
+    assert np.array_equal(res["iters"], ref["iters"])
+    for b in range(48):
+        _check_states(w, res["x"][b], ref["x"][b], idx, b)
+
+
+def test_c2_full_size_properties():
+    """BASELINE config 2 at full size (4096 x 100 elements): size-independent properties + a sampled oracle check."""
+    O = _oracle()
+    w = workloads.cantilever_tipmoment_batch(4096, 100)
+    ctx = _ctx_for(w)
+    res = ctx.static_solve()
+    st = ctx.stats()
+    idx = ctx.indices
+    # (1) everything converged, residual norms under ftol
+    assert res["converged"].all() and (res["resid_inf"] <= 1e-9).all()
+    assert st["newton_iters"] == int(res["iters"].sum())
+    # (2) idempotence: restarting from the solution takes zero iterations and returns the same state bit for bit
+    res2 = ctx.static_solve(x0=res["x"])
+    assert (res2["iters"] == 0).all() and np.array_equal(res2["x"], res["x"])
+    # (3) physics: pure bending -> tip rotation = λ π about z (Wiener-Milenkovic parameter 4 tan(φ/4)), |error| from discretisation only
+    ic = idx["icol_point"][-1] - 1
+    thz = res["x"][:, ic + 5]
+    assert np.allclose(thz, 4 * np.tan(w["lam"] * np.pi / 4), rtol=1e-6)
+    # (4) the oracle's residual at the GPU solution is below ftol on a sample, and the sample agrees with oracle solves
+    pick = np.random.default_rng(0).choice(4096, 24, replace=False)
+    for b in pick:
+        pk = cases.oracle_packed(w, int(b))
+        assert np.abs(O.static_residual(pk, res["x"][b])).max() <= 1e-9
+        ref = O.static_solve(pk)
+        assert ref["iters"] == res["iters"][b]
+        _check_states(w, res["x"][b], ref["x"], idx, int(b))
+    ctx.close()
+
+
+def test_multi_device_entry_point_single_gpu():
+    w = workloads.cantilever_tipmoment_batch(32, 20)
+    out = api.static_analysis_batch(w["start"], w["stop"], w["elems"], w["pd"], w["pl"], w["bc"], force_scaling=w["force_scaling"], devices=(0,))
+    assert out.converged.all() and out.x.shape == (32, 12 * 20 + 6)
