@@ -121,7 +121,7 @@ struct SolveArgs {
     int direction_only;   // parity entry point: just p, no state change
 };
 
-template <int KLB, int KUB> __global__ void __launch_bounds__(128) k_factor_solve(SolveArgs A) {
+template <int KLB, int KUB> __global__ void __launch_bounds__(128, 4) k_factor_solve(SolveArgs A) {
     using S = LuShape<KLB, KUB>;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

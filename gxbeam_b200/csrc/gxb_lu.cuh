@@ -7,13 +7,19 @@
 // block bandwidths KLB = KUB = 2.  Its diagonal blocks are structurally singular (free points have no
 // ∂F/∂u), so partial pivoting is mandatory; row pivoting inside the band lets U grow to KLB+KUB block super-diagonals.
 //
-// Mapping: lane = one row of the active window (rows of block-rows J..J+KLB, at most 6(KLB+1) <= 32), the lane keeps its
+// Mapping: lane = one row of the active window (rows of block-rows J..J+KLB, at most 6(KLB+1) <= 32); the lane keeps its
 // row segment (window columns = blocks J..J+KLB+KUB, W = 6(KLB+KUB+1) doubles) plus its right-hand side in registers.
-// Per pivot: warp arg-max on the pivot column (two REDUX + one VOTE), the pivot lane stages its row through shared
-// memory, every other live lane does W-k FMAs.  The pivot row, scaled by 1/pivot, is the U row and is streamed to global
-// memory with one coalesced 32-double store; L is never stored (each Jacobian is used for exactly one right-hand side,
-// which is eliminated on the fly).  After 6 pivots the window slides by one block: survivors shift their registers,
-// the 6 retired lanes pick up the rows of block-row J+KLB+1, which were prefetched with cp.async during the elimination.
+// Right-looking blocked elimination with block size 6, per block column J:
+//   A. panel: 6 pivots on window columns 0..5 — warp arg-max (two REDUX + one VOTE), pivot-row panel entries by shuffle,
+//      every live row records its multipliers m[0..5];
+//   B. the six pivot lanes publish their multipliers (= L11) through shared memory; every lane turns its multipliers into
+//      effective ones e = m L11^{-1}, so that the trailing update can use the *unmodified* pivot rows;
+//   C. the six pivot lanes publish their trailing entries + rhs in ONE set of vector stores (they are different lanes of
+//      the same warp), then every lane does a rank-6 update of its 24 trailing entries, written straight into the
+//      shifted register positions (the window slide costs no moves).  Pivot lanes end up holding their final U row, which
+//      they stream to global memory (again one set of stores for all six), and then pick up the rows of block-row
+//      J+KLB+1 that were prefetched with cp.async during the elimination.
+// L is never stored: each Jacobian is used for exactly one right-hand side, which is eliminated on the fly.
 // Back substitution walks the blocks backwards, lane k < 6 owns row k of the block.
 #pragma once
 #include <cuda_runtime.h>
@@ -24,10 +30,16 @@
 template <int KLB, int KUB> struct LuShape {
     static constexpr int W = 6 * (KLB + KUB + 1);   // window / stored-row width
     static constexpr int ROWS = 6 * (KLB + 1);      // live rows in the window
-    static constexpr int UW = ((W + 2 + 31) / 32) * 32;  // stored U row: W entries (scaled), rhs (scaled), pad
-    // per-warp shared memory (doubles): 2 pivot-row buffers, staged next block-row (6 rows + 6 rhs), x window
-    static constexpr int PROW = W + 2;
-    static constexpr int SM_DOUBLES = 2 * PROW + 6 * W + 6 + W + 2;
+    static constexpr int T = W - 6;                 // trailing columns
+    static constexpr int UW = ((W + 2 + 31) / 32) * 32;  // stored U row: W entries, rhs, 1/pivot, pad
+    // per-warp shared memory (doubles)
+    static constexpr int PSTRIDE = T + 2;           // one published pivot row: T trailing entries, rhs, pad (16B multiple)
+    static constexpr int SM_P = 6 * PSTRIDE;        // published pivot rows
+    static constexpr int SM_L = 6 * 6;              // published multipliers (L11)
+    static constexpr int USTRIDE = W + 4;           // padded U row in shared memory (bank-conflict-free for W = 30)
+    static constexpr int SM_STAGE = (6 * W + 6 > 12 * USTRIDE) ? (6 * W + 6) : 12 * USTRIDE;  // next block-row + rhs | 2x6 U rows
+    static constexpr int SM_X = W + 2;              // x window for the back substitution
+    static constexpr int SM_DOUBLES = SM_P + SM_L + SM_STAGE + SM_X;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -38,18 +50,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Solve J y = rhs for one instance; writes sol = sign * y.  Returns 0, or 1 if an exactly-zero / non-finite pivot was hit.
 //   Jrow : [n][W]  row-block storage (see gxb_static.cuh)      rhs : [n]
-//   U    : [n][UW] scratch for the scaled U rows                sol : [n]
+//   U    : [n][UW] scratch for the U rows                       sol : [n]
 template <int KLB, int KUB>
 __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __restrict__ rhs, double* __restrict__ U,
                                double* __restrict__ sol, int nb, double sign, double* sm) {
     using S = LuShape<KLB, KUB>;
-    constexpr int W = S::W, ROWS = S::ROWS, UW = S::UW, PROW = S::PROW;
+    constexpr int W = S::W, ROWS = S::ROWS, UW = S::UW, T = S::T, PS = S::PSTRIDE;
+    static_assert(T % 2 == 0 && W % 2 == 0, "vector access needs even widths");
     const int lane = threadIdx.x & 31;
     const int n = 6 * nb;
-    double* prow0 = sm;
-    double* prow1 = sm + PROW;
-    double* stage = sm + 2 * PROW;        // 6*W row entries, then 6 rhs
-    double* xs = stage + 6 * W + 6;       // x window for the back substitution
+    double* Psm = sm;                      // [6][PS]
+    double* Lsm = sm + S::SM_P;            // [6][6]
+    double* stage = Lsm + S::SM_L;         // 6*W row entries, then 6 rhs
+    double* xs = stage + S::SM_STAGE;      // x window
 
     double a[W];
     double b = 0.0;
@@ -82,11 +95,12 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
             for (int c = lane; c < (6 * W * 8) / 16; c += 32) cp_async16(s + 16 * c, g + 16 * c);
             if (lane < 3) cp_async16(reinterpret_cast<char*>(stage + 6 * W) + 16 * lane, reinterpret_cast<const char*>(rhs + nrow0) + 16 * lane);
         }
-        unsigned retired = 0;
+        // ---- A. panel factorisation on window columns 0..5 ----
+        double m[6];
+        int kp = 6;            // which pivot this lane became (6 = none)
+        double myrinv = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            double* prow = (k & 1) ? prow1 : prow0;
-            // --- pivot search: max |a[k]| over live lanes, lowest lane wins ties ---
             const double v = fabs(a[k]);
             const unsigned hi = live ? (unsigned)__double2hiint(v) : 0u;
             const unsigned mhi = __reduce_max_sync(GXB_FULL, hi);
@@ -95,38 +109,69 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
             const unsigned mlo = __reduce_max_sync(GXB_FULL, lo);
             const unsigned cand = __ballot_sync(GXB_FULL, c1 && lo == mlo);
             const int p = cand ? (__ffs(cand) - 1) : 0;
-            const bool is_piv = (lane == p) && cand;
-            if (is_piv) {
-#pragma unroll
-                for (int j = 0; j < W; j += 2) *reinterpret_cast<double2*>(prow + j) = make_double2(a[j], a[j + 1]);
-                prow[W] = b;
-                live = false;
-                retired |= 1u;   // marker, the lane mask is rebuilt by ballot below
-            }
-            __syncwarp();
-            const double piv = prow[k];
+            const double piv = __shfl_sync(GXB_FULL, a[k], p);
             if (!(fabs(piv) > 0.0) || !isfinite(piv) || !cand) bad = 1;
             const double rinv = 1.0 / piv;
-            if (live) {
-                const double m = a[k] * rinv;
-                a[k] = 0.0;
+            if (lane == p && cand) { live = false; kp = k; myrinv = rinv; }
+            m[k] = live ? a[k] * rinv : 0.0;
 #pragma unroll
-                for (int j = k + 1; j < W; j++) a[j] = fma(-m, prow[j], a[j]);
-                b = fma(-m, prow[W], b);
-            }
-            // scaled U row: entries 0..W-1, rhs at W; the diagonal slot k holds 1 and is never read back
-            {
-                double* urow = U + (size_t)(6 * J + k) * UW;
-                for (int c = lane; c < UW; c += 32) urow[c] = (c <= W) ? prow[c] * rinv : 0.0;
+            for (int j = k + 1; j < 6; j++) {
+                const double pj = __shfl_sync(GXB_FULL, a[j], p);
+                a[j] = fma(-m[k], pj, a[j]);
             }
         }
-        const unsigned rmask = __ballot_sync(GXB_FULL, retired != 0);
-        // --- slide the window by one block ---
+        // ---- B/C. publish L11 rows, original trailing parts and rhs of the six pivot rows (one store set for all six) ----
+        if (kp < 6) {
+            double* Lr = Lsm + kp * 6;
+#pragma unroll
+            for (int j = 0; j < 6; j += 2) *reinterpret_cast<double2*>(Lr + j) = make_double2(m[j], m[j + 1]);
+            double* Pr = Psm + kp * PS;
+#pragma unroll
+            for (int j = 0; j < T; j += 2) *reinterpret_cast<double2*>(Pr + j) = make_double2(a[6 + j], a[6 + j + 1]);
+            Pr[T] = b;
+            // panel part of the U row goes straight to global memory (entries left of the diagonal are never read back)
+            double* urow = U + (size_t)(6 * J + kp) * UW;
+#pragma unroll
+            for (int j = 0; j < 6; j += 2) *reinterpret_cast<double2*>(urow + j) = make_double2(a[j], a[j + 1]);
+        }
+        __syncwarp();
+        // effective multipliers: e L11 = m, L11 unit lower triangular with L11[k][k'] = m_{pivot k}[k']
+        double e[6];
+        e[5] = m[5];
+#pragma unroll
+        for (int kk = 4; kk >= 0; kk--) {
+            double acc = m[kk];
+#pragma unroll
+            for (int k = kk + 1; k < 6; k++) acc = fma(-e[k], Lsm[k * 6 + kk], acc);
+            e[kk] = acc;
+        }
+        // rank-6 trailing update, written into the shifted positions (window slides by one block)
+#pragma unroll
+        for (int j = 0; j < T; j += 2) {
+            double x0 = a[6 + j], x1 = a[6 + j + 1];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const double2 pv = *reinterpret_cast<const double2*>(Psm + k * PS + j);
+                x0 = fma(-e[k], pv.x, x0);
+                x1 = fma(-e[k], pv.y, x1);
+            }
+            a[j] = x0; a[j + 1] = x1;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) b = fma(-e[k], Psm[k * PS + T], b);
+#pragma unroll
+        for (int j = T; j < W; j++) a[j] = 0.0;
+        const unsigned rmask = __ballot_sync(GXB_FULL, kp < 6);
         if (have_next) cp_async_wait_all();
         __syncwarp();
-        if (retired) {
+        if (kp < 6) {
+            // this lane now holds the final U row of pivot kp (trailing part + rhs): stream it out, then take a new row
+            double* urow = U + (size_t)(6 * J + kp) * UW;
+#pragma unroll
+            for (int j = 0; j < T; j += 2) *reinterpret_cast<double2*>(urow + 6 + j) = make_double2(a[j], a[j + 1]);
+            *reinterpret_cast<double2*>(urow + W) = make_double2(b, myrinv);
             const int rank = __popc(rmask & ((1u << lane) - 1u));
-            if (have_next && rank < 6) {
+            if (have_next) {
                 const double* src = stage + rank * W;
 #pragma unroll
                 for (int j = 0; j < W; j += 2) { double2 t = *reinterpret_cast<const double2*>(src + j); a[j] = t.x; a[j + 1] = t.y; }
@@ -137,65 +182,70 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
                 for (int j = 0; j < W; j++) a[j] = 0.0;
                 b = 0.0;
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < W - 6; j++) a[j] = a[j + 6];
-#pragma unroll
-            for (int j = W - 6; j < W; j++) a[j] = 0.0;
         }
         __syncwarp();
     }
 
     // ---- back substitution, block by block from the end; lane k < 6 owns row 6J+k ----
+    // U rows of block J-1 are prefetched (cp.async, double buffered) while block J is being solved.
+    constexpr int US = S::USTRIDE;
+    double* ub = stage;                                  // [2][6][US], reuses the factorisation's staging area
+    auto prefetch_u = [&](int Jb) {
+        double* dst = ub + (Jb & 1) * 6 * US;
+        const double* src = U + (size_t)(6 * Jb) * UW;
+        constexpr int CH = (W + 2) / 2;                  // 16-byte chunks per row
+        for (int c = lane; c < 6 * CH; c += 32) {
+            const int r = c / CH, q = c % CH;
+            cp_async16(dst + r * US + 2 * q, src + (size_t)r * UW + 2 * q);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
     for (int c = lane; c < W + 2; c += 32) xs[c] = 0.0;
     __syncwarp();
-    double u[W + 2];
-    {
-        const int J = nb - 1;
-        if (lane < 6) {
-            const double* urow = U + (size_t)(6 * J + lane) * UW;
-#pragma unroll
-            for (int j = 0; j < W + 2; j += 2) { double2 t = *reinterpret_cast<const double2*>(urow + j); u[j] = t.x; u[j + 1] = t.y; }
-        }
-    }
+    prefetch_u(nb - 1);
     for (int J = nb - 1; J >= 0; J--) {
+        if (J > 0) { prefetch_u(J - 1); asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+        const double* row = ub + (J & 1) * 6 * US + (lane < 6 ? lane : 0) * US;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (lane < 6) {
-            s0 = u[W];
+        double up[6];
+        {
+            const double2 t = *reinterpret_cast<const double2*>(row + W);   // rhs, 1/pivot
+            s0 = t.x;
+            const double myr_ = t.y;
+#pragma unroll
+            for (int j = 0; j < 6; j += 2) { const double2 q = *reinterpret_cast<const double2*>(row + j); up[j] = q.x; up[j + 1] = q.y; }
 #pragma unroll
             for (int j = 6; j < W; j += 4) {
-                s0 = fma(-u[j], xs[j], s0);
-                s1 = fma(-u[j + 1], xs[j + 1], s1);
-                if (j + 2 < W) s2 = fma(-u[j + 2], xs[j + 2], s2);
-                if (j + 3 < W) s3 = fma(-u[j + 3], xs[j + 3], s3);
+                const double2 u0 = *reinterpret_cast<const double2*>(row + j);
+                const double2 x0 = *reinterpret_cast<const double2*>(xs + j);
+                s0 = fma(-u0.x, x0.x, s0);
+                s1 = fma(-u0.y, x0.y, s1);
+                if (j + 2 < W) {
+                    const double2 u1 = *reinterpret_cast<const double2*>(row + j + 2);
+                    const double2 x1 = *reinterpret_cast<const double2*>(xs + j + 2);
+                    s2 = fma(-u1.x, x1.x, s2);
+                    s3 = fma(-u1.y, x1.y, s3);
+                }
             }
-        }
-        double s = (s0 + s1) + (s2 + s3);
-        // prefetch the previous block's U rows while the 6x6 triangle is solved
-        double un[W + 2];
-        if (J > 0 && lane < 6) {
-            const double* urow = U + (size_t)(6 * (J - 1) + lane) * UW;
+            double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
-            for (int j = 0; j < W + 2; j += 2) { double2 t = *reinterpret_cast<const double2*>(urow + j); un[j] = t.x; un[j + 1] = t.y; }
+            for (int k = 5; k >= 0; k--) {
+                const double xk = __shfl_sync(GXB_FULL, s * myr_, k);
+                if (lane < k) s = fma(-up[k], xk, s);
+            }
+            s *= myr_;
+            // slide the x window for block J-1: xs'[6..11] = this block's solution, xs'[j+6] = xs[j] for the older
+            // entries (xs[0..5] is never read)
+            double keep0 = (lane < 6) ? s : xs[lane];
+            double keep1 = (lane + 32 < W - 6) ? xs[lane + 32] : 0.0;
+            __syncwarp();
+            if (lane < W - 6) xs[lane + 6] = keep0;
+            if (lane + 32 < W - 6) xs[lane + 38] = keep1;
+            if (lane < 6) sol[6 * J + lane] = sign * s;
         }
-#pragma unroll
-        for (int k = 5; k >= 0; k--) {
-            const double xk = __shfl_sync(GXB_FULL, s, k);
-            if (lane < k) s = fma(-u[k], xk, s);
-        }
-        // slide the x window for block J-1: xs'[6..11] = this block's solution, xs'[j+6] = xs[j] for the older entries
-        // (xs[0..5] is never read)
-        double keep0 = (lane < 6) ? s : xs[lane];
-        double keep1 = (lane + 32 < W - 6) ? xs[lane + 32] : 0.0;
         __syncwarp();
-        if (lane < W - 6) xs[lane + 6] = keep0;
-        if (lane + 32 < W - 6) xs[lane + 38] = keep1;
-        if (lane < 6) sol[6 * J + lane] = sign * s;
-        __syncwarp();
-        if (J > 0) {
-#pragma unroll
-            for (int j = 0; j < W + 2; j++) u[j] = un[j];
-        }
     }
     return __any_sync(GXB_FULL, bad) ? 1 : 0;
 }
