@@ -20,6 +20,9 @@
 #include <vector>
 
 #include "../../include/gxbeam_b200.h"
+#ifndef GXB_LU_MINBLOCKS
+#define GXB_LU_MINBLOCKS 4
+#endif
 #include "gxb_lu.cuh"
 #include "gxb_static.cuh"
 
@@ -107,10 +110,10 @@ __global__ void k_pack_pmass(const double* __restrict__ raw, double* __restrict_
 
 // ------------------------------------------------------------------------------------------------------------------
 template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble(StaticArgs A) {
-    extern __shared__ double xch[];
+    extern __shared__ __align__(16) double asm_smem[];
     const int b = blockIdx.x;
     if (A.status && A.status[b] != A.want_status) return;
-    static_station<WANT_J>(A, b, threadIdx.x, xch);
+    static_station<WANT_J>(A, b, threadIdx.x, asm_smem);
 }
 
 struct SolveArgs {
@@ -121,7 +124,7 @@ struct SolveArgs {
     int direction_only;   // parity entry point: just p, no state change
 };
 
-template <int KLB, int KUB> __global__ void __launch_bounds__(128, 4) k_factor_solve(SolveArgs A) {
+template <int KLB, int KUB> __global__ void __launch_bounds__(128, GXB_LU_MINBLOCKS) k_factor_solve(SolveArgs A) {
     using S = LuShape<KLB, KUB>;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -417,7 +420,7 @@ static int require_static_chain(gxb_ctx* c, const char* who) {
     if (!c || c->kind < 0) return fail(GXB_ERR_INVALID, std::string(who) + ": call gxb_topology first");
     if (c->kind != 0) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": only kind=0 (StaticSystem) is implemented on the device so far");
     if (!c->chain) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": only chain topologies (start = 1:n, stop = 2:n+1) are implemented on the device");
-    if (c->np > 256) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": more than 255 elements per assembly not supported yet");
+    if (c->np > 256) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": more than 255 elements per assembly not supported yet (one CTA per instance, shared-memory tile per station)");
     return GXB_OK;
 }
 
@@ -535,9 +538,12 @@ static StaticArgs make_static_args(gxb_ctx* c, const gxb_opts* o, const double* 
 }
 static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
     int bs = (int)((c->np + 31) / 32) * 32;
-    size_t sm = (size_t)bs * GXB_XCH * 8;
-    if (want_j) k_assemble<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
-    else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
+    size_t sm = (size_t)bs * (GXB_XCH + (want_j ? GXB_TILE : 0)) * 8;
+    if (want_j) {
+        static thread_local size_t configured = 0;
+        if (sm > configured) { CK(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+        k_assemble<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
+    } else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
     CK(cudaGetLastError());
     c->stats.launches++; c->stats.n_assemble++;
     return GXB_OK;

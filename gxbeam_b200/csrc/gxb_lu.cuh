@@ -37,7 +37,9 @@ template <int KLB, int KUB> struct LuShape {
     static constexpr int SM_P = 6 * PSTRIDE;        // published pivot rows
     static constexpr int SM_L = 6 * 6;              // published multipliers (L11)
     static constexpr int USTRIDE = W + 4;           // padded U row in shared memory (bank-conflict-free for W = 30)
-    static constexpr int SM_STAGE = (6 * W + 6 > 12 * USTRIDE) ? (6 * W + 6) : 12 * USTRIDE;  // next block-row + rhs | 2x6 U rows
+    static constexpr int NS = 4;                    // prefetch ring depth (block-rows in flight: NS-1)
+    static constexpr int STG = 6 * W + 6;           // one staged block-row: 6 rows + 6 rhs
+    static constexpr int SM_STAGE = NS * ((STG > 6 * USTRIDE) ? STG : 6 * USTRIDE);
     static constexpr int SM_X = W + 2;              // x window for the back substitution
     static constexpr int SM_DOUBLES = SM_P + SM_L + SM_STAGE + SM_X;
 };
@@ -47,6 +49,18 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// 1/x without the slow-path branch of the IEEE division: hardware seed (MUFU.RCP64H) + three Newton steps (< 2 ulp),
+// so that it can be scheduled in the shadow of the warp arg-max.  x = 0 / denormal / inf give inf or NaN, which the
+// caller flags (zero pivot) or which surfaces as a non-finite Newton step.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    return r;
+}
 
 // Solve J y = rhs for one instance; writes sol = sign * y.  Returns 0, or 1 if an exactly-zero / non-finite pivot was hit.
 //   Jrow : [n][W]  row-block storage (see gxb_static.cuh)      rhs : [n]
@@ -85,34 +99,43 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
         }
     }
 
-    for (int J = 0; J < nb; J++) {
-        // prefetch block-row J+KLB+1 (6 rows, contiguous 6*W doubles) and its rhs into shared memory
-        const int nrow0 = 6 * (J + KLB + 1);
-        const bool have_next = nrow0 < n;
-        if (have_next) {
-            const char* g = reinterpret_cast<const char*>(Jrow + (size_t)nrow0 * W);
-            char* s = reinterpret_cast<char*>(stage);
-            for (int c = lane; c < (6 * W * 8) / 16; c += 32) cp_async16(s + 16 * c, g + 16 * c);
-            if (lane < 3) cp_async16(reinterpret_cast<char*>(stage + 6 * W) + 16 * lane, reinterpret_cast<const char*>(rhs + nrow0) + 16 * lane);
+    // block-rows are prefetched NS-1 steps ahead into a ring of shared-memory buffers (cp.async groups, one per step)
+    constexpr int NS = S::NS, STG = S::STG;
+    auto prefetch_rows = [&](int step) {               // block-row needed at the end of elimination step `step`
+        const int r0 = 6 * (step + KLB + 1);
+        if (r0 < n) {
+            double* dst = stage + (step % NS) * STG;
+            const char* g = reinterpret_cast<const char*>(Jrow + (size_t)r0 * W);
+            char* sdst = reinterpret_cast<char*>(dst);
+            for (int c = lane; c < (6 * W * 8) / 16; c += 32) cp_async16(sdst + 16 * c, g + 16 * c);
+            if (lane < 3) cp_async16(reinterpret_cast<char*>(dst + 6 * W) + 16 * lane, reinterpret_cast<const char*>(rhs + r0) + 16 * lane);
         }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+#pragma unroll
+    for (int q = 0; q < NS - 1; q++) prefetch_rows(q);
+
+    for (int J = 0; J < nb; J++) {
+        prefetch_rows(J + NS - 1);
+        const bool have_next = 6 * (J + KLB + 1) < n;
         // ---- A. panel factorisation on window columns 0..5 ----
         double m[6];
         int kp = 6;            // which pivot this lane became (6 = none)
         double myrinv = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            const double v = fabs(a[k]);
-            const unsigned hi = live ? (unsigned)__double2hiint(v) : 0u;
-            const unsigned mhi = __reduce_max_sync(GXB_FULL, hi);
-            const bool c1 = live && hi == mhi;
-            const unsigned lo = c1 ? (unsigned)__double2loint(v) : 0u;
-            const unsigned mlo = __reduce_max_sync(GXB_FULL, lo);
-            const unsigned cand = __ballot_sync(GXB_FULL, c1 && lo == mlo);
-            const int p = cand ? (__ffs(cand) - 1) : 0;
-            const double piv = __shfl_sync(GXB_FULL, a[k], p);
-            if (!(fabs(piv) > 0.0) || !isfinite(piv) || !cand) bad = 1;
-            const double rinv = 1.0 / piv;
-            if (lane == p && cand) { live = false; kp = k; myrinv = rinv; }
+            // arg-max of |a[k]| over live lanes with ONE warp reduction: key = float(|a|) with the 5 low mantissa bits
+            // replaced by (31 - lane).  Partial pivoting only needs a near-maximal pivot (relative slack 2^-18); exact ties
+            // go to the lowest lane, so the choice is deterministic.
+            const unsigned fk = __float_as_uint(__double2float_ru(fabs(a[k])));
+            const unsigned key = live ? ((fk & 0xffffffe0u) | (31u - (unsigned)lane)) : 0u;
+            const double rc = fast_rcp(a[k]);                  // every lane inverts its own candidate meanwhile
+            const unsigned mk = __reduce_max_sync(GXB_FULL, key);
+            const int p = 31 - (int)(mk & 31u);
+            const double rinv = __shfl_sync(GXB_FULL, rc, p);
+            const bool is_piv = (lane == p) && live;
+            if (!(mk >> 5) || !isfinite(rinv)) bad = 1;        // zero (or sub-float-denormal) / NaN pivot column
+            if (is_piv) { live = false; kp = k; myrinv = rinv; }
             m[k] = live ? a[k] * rinv : 0.0;
 #pragma unroll
             for (int j = k + 1; j < 6; j++) {
@@ -162,7 +185,7 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
 #pragma unroll
         for (int j = T; j < W; j++) a[j] = 0.0;
         const unsigned rmask = __ballot_sync(GXB_FULL, kp < 6);
-        if (have_next) cp_async_wait_all();
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(S::NS - 1) : "memory");   // the group of this step has landed
         __syncwarp();
         if (kp < 6) {
             // this lane now holds the final U row of pivot kp (trailing part + rhs): stream it out, then take a new row
@@ -172,10 +195,11 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
             *reinterpret_cast<double2*>(urow + W) = make_double2(b, myrinv);
             const int rank = __popc(rmask & ((1u << lane) - 1u));
             if (have_next) {
-                const double* src = stage + rank * W;
+                const double* sbuf = stage + (J % NS) * STG;
+                const double* src = sbuf + rank * W;
 #pragma unroll
                 for (int j = 0; j < W; j += 2) { double2 t = *reinterpret_cast<const double2*>(src + j); a[j] = t.x; a[j + 1] = t.y; }
-                b = stage[6 * W + rank];
+                b = sbuf[6 * W + rank];
                 live = true;
             } else {
 #pragma unroll
@@ -189,25 +213,30 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
     // ---- back substitution, block by block from the end; lane k < 6 owns row 6J+k ----
     // U rows of block J-1 are prefetched (cp.async, double buffered) while block J is being solved.
     constexpr int US = S::USTRIDE;
-    double* ub = stage;                                  // [2][6][US], reuses the factorisation's staging area
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+    double* ub = stage;                                  // [NS][6][US], reuses the factorisation's staging area
     auto prefetch_u = [&](int Jb) {
-        double* dst = ub + (Jb & 1) * 6 * US;
-        const double* src = U + (size_t)(6 * Jb) * UW;
-        constexpr int CH = (W + 2) / 2;                  // 16-byte chunks per row
-        for (int c = lane; c < 6 * CH; c += 32) {
-            const int r = c / CH, q = c % CH;
-            cp_async16(dst + r * US + 2 * q, src + (size_t)r * UW + 2 * q);
+        if (Jb >= 0) {
+            double* dst = ub + (Jb % NS) * 6 * US;
+            const double* src = U + (size_t)(6 * Jb) * UW;
+            constexpr int CH = (W + 2) / 2;                  // 16-byte chunks per row
+            for (int c = lane; c < 6 * CH; c += 32) {
+                const int r = c / CH, q = c % CH;
+                cp_async16(dst + r * US + 2 * q, src + (size_t)r * UW + 2 * q);
+            }
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
     for (int c = lane; c < W + 2; c += 32) xs[c] = 0.0;
     __syncwarp();
-    prefetch_u(nb - 1);
+#pragma unroll
+    for (int q = 0; q < NS - 1; q++) prefetch_u(nb - 1 - q);
     for (int J = nb - 1; J >= 0; J--) {
-        if (J > 0) { prefetch_u(J - 1); asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
-        else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        prefetch_u(J - (NS - 1));
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(S::NS - 1) : "memory");
         __syncwarp();
-        const double* row = ub + (J & 1) * 6 * US + (lane < 6 ? lane : 0) * US;
+        const double* row = ub + (J % NS) * 6 * US + (lane < 6 ? lane : 0) * US;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         double up[6];
         {

@@ -8,20 +8,28 @@
 //   Jrow[b][r][30] : row r (natural SystemIndices order) holds the 5 column 6-blocks B-2..B+2 around its own 6-block
 //   B = r / 6.  Chain layout [p0 e0 p1 e1 ... pN]: point i is block 2i, element i is block 2i+1.
 //
+// The rows are produced in four passes of three rows per station (point F rows, point M rows, element ru rows, element
+// rθ rows).  In each pass every thread deposits its 3x3 blocks into a shared-memory tile [station][3 rows x 30 slots];
+// the tile is then streamed to HBM by the whole CTA with 16-byte, fully coalesced stores (per-thread strided stores cost
+// 3x the L2 write sectors and throttled the LSU in the first version of this kernel, profiles/r1_v1_*).
+//
 // Summation order in point rows is the reference's (point term assigned first, then element i-1 `+=`, then element i
-// `-=`; system.jl:668-676, element.jl:2526-2549): the i-1 contribution to the shared θ-block travels through shared
-// memory instead of atomics, so results are deterministic.
+// `-=`; system.jl:668-676, element.jl:2526-2549): element i-1's contribution to the shared θ-block is parked in the
+// structurally-zero slots 0..2 of the tile row and folded in by the owning thread, so results are deterministic
+// (no atomics).
 #pragma once
 #include "gxb_math.cuh"
 
-#define GXB_ROWW 30  // doubles per stored Jacobian row (static): 5 blocks x 6
+#define GXB_ROWW 30      // doubles per stored Jacobian row (static): 5 blocks x 6
+#define GXB_TILE 94      // tile stride per station: 3 rows x 30 slots + 4 pad (16-byte aligned, 2-way bank conflicts at most)
+#define GXB_XCH 6        // residual exchange record per thread
 
 struct StaticArgs {
     int N;                 // elements in the chain (points = N+1)
     int n;                 // 12 N + 6
     int two_d;
     int has_grav;          // gravity != 0 for some instance (element mass / point mass terms evaluated)
-    const double* elemS;   // [b][47 or 83][N]  : L, Cab[9], S11,S12,S21,S22 (=L*compliance, 3x3 row-major each) [, m11,m12,m21,m22 (=L*mass)]
+    const double* elemS;   // [b][82][N]  : L, Cab[9], S11,S12,S21,S22 (=L*compliance, 3x3 row-major each), m11,m12,m21,m22 (=L*mass)
     int elem_nf;           // number of element fields stored
     const double* bcS;     // [b][18][N+1]
     const double* dlS;     // [b][24][N] or null
@@ -41,22 +49,56 @@ GXD m3 ldm(const double* p, int stride) { m3 r;
 #pragma unroll
     for (int i = 0; i < 9; i++) r.a[i] = p[i * stride]; return r; }
 
-GXD void st3(double* row, int slot, double a, double b, double c) { row[slot] = a; row[slot + 1] = b; row[slot + 2] = c; }
-// write 3 rows x 3 cols block B at rows (r0..r0+2), slot s
-GXD void stblk(double* J, int r0, int s, const m3& B) {
+// deposit a 3x3 block into a tile (3 rows x 30 slots) at slot s
+GXD void tblk(double* t, int s, const m3& B) {
 #pragma unroll
-    for (int i = 0; i < 3; i++) st3(J + (size_t)(r0 + i) * GXB_ROWW, s, B.a[3 * i], B.a[3 * i + 1], B.a[3 * i + 2]);
+    for (int i = 0; i < 3; i++) { t[30 * i + s] = B.a[3 * i]; t[30 * i + s + 1] = B.a[3 * i + 1]; t[30 * i + s + 2] = B.a[3 * i + 2]; }
+}
+GXD m3 tget(const double* t, int s) { m3 B;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { B.a[3 * i] = t[30 * i + s]; B.a[3 * i + 1] = t[30 * i + s + 1]; B.a[3 * i + 2] = t[30 * i + s + 2]; }
+    return B; }
+GXD m3 mul3t(const Rot& R, v3 w) { return cols(tmul(R.C1, w), tmul(R.C2, w), tmul(R.C3, w)); }   // mul3(C_θ1', C_θ2', C_θ3', w)
+// zero rows of M whose flag bit is clear (loads that are state variables have no θ-dependence, point.jl:86-105)
+GXD m3 rowmask(const m3& M, unsigned f0, unsigned f1, unsigned f2) { m3 r = M;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { if (!f0) r.a[k] = 0.0; if (!f1) r.a[3 + k] = 0.0; if (!f2) r.a[6 + k] = 0.0; }
+    return r; }
+
+// zero this thread's tile, CTA-wide barrier afterwards is the caller's job
+GXD void tile_clear(double* t) {
+#pragma unroll
+    for (int j = 0; j < 90; j += 2) *reinterpret_cast<double2*>(t + j) = make_double2(0.0, 0.0);
+}
+// stream the tiles of stations [0, nst) to rows 12*st + roff .. +2 of the instance's row-block storage
+GXD void tile_flush(const double* tiles, double* J, int nst, int roff) {
+    for (int c = threadIdx.x; c < nst * 45; c += blockDim.x) {
+        const int st = c / 45, q = c - 45 * st;
+        const double2 v = *reinterpret_cast<const double2*>(tiles + (size_t)st * GXB_TILE + 2 * q);
+        *reinterpret_cast<double2*>(J + (size_t)(12 * st + roff) * GXB_ROWW + 2 * q) = v;
+    }
+}
+// planar analysis (system.jl:1072-1103): rows 2,3,4 of every 6-slot become  x_k = 0
+GXD void tile_planar(double* t, int first_row_in_slot) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int k = first_row_in_slot + i;
+        if (k >= 2 && k <= 4) {
+#pragma unroll
+            for (int c = 0; c < 30; c++) t[30 * i + c] = (c == 12 + k) ? 1.0 : 0.0;
+        }
+    }
 }
 
-// Per-thread exchange record: element i's contribution to the rows of its stop point (i+1) that overlaps with what
-// thread i+1 writes: the (F,M)x θ block (18) and the residual (6).
-#define GXB_XCH 24
-
 template <bool WANT_J>
-__device__ void static_station(const StaticArgs& A, int b, int i, double* xch /* smem [blockDim][24] */) {
+__device__ void static_station(const StaticArgs& A, int b, int i, double* smem) {
     const int N = A.N, NP = N + 1;
+    double* xch = smem;                                             // [blockDim][6]
+    double* tiles = smem + (size_t)blockDim.x * GXB_XCH;            // [blockDim][94]   (WANT_J only)
+    double* mytile = tiles + (size_t)threadIdx.x * GXB_TILE;
+    double* nexttile = mytile + GXB_TILE;                           // station i+1 (valid when has_elem)
     const double fs = A.fs[b];
-    const double rfs = 1.0 / fs;   // NOTE: reference divides by fs; fs is a power of two by default so this is exact
+    const double rfs = 1.0 / fs;   // the reference divides by fs; fs is a power of two by default so this is exact
     const double* x = A.x + (size_t)b * A.n;
     double* r = A.r + (size_t)b * A.n;
     double* J = WANT_J ? A.Jrow + (size_t)b * A.n * GXB_ROWW : nullptr;
@@ -67,10 +109,10 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* xch /*
     if (A.has_grav && A.grav) g = mk(A.grav[3 * b], A.grav[3 * b + 1], A.grav[3 * b + 2]);
 
     // ---- point i: displacement / load selection (point.jl:20-39, 147-167) ----
-    v3 u1 = mk(0, 0, 0), th1 = u1, Fp = u1, Mp = u1;       // point i
+    v3 u1 = mk(0, 0, 0), th1 = u1, Fp = u1, Mp = u1;
     v3 mu1 = mk(1, 1, 1), mth1 = mu1;                       // u_u, θ_θ diagonal masks (1 = free)
     unsigned fl1 = 0;
-    m3 pJFth = zero33(), pJMth = zero33();                  // point-own ∂F/∂θ, ∂M/∂θ (follower loads, point-mass gravity)
+    bool point_rot = false;                                 // follower loads or point-mass gravity present at this point
     if (valid) {
         fl1 = A.flags[i];
         const double* bc = A.bcS + ((size_t)b * 18) * NP + i;
@@ -82,42 +124,16 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* xch /*
         v3 F = ldv(bc + 6 * NP, NP), M = ldv(bc + 9 * NP, NP), Ff = ldv(bc + 12 * NP, NP), Mf = ldv(bc + 15 * NP, NP);
         const bool follower = (Ff.x != 0.0) | (Ff.y != 0.0) | (Ff.z != 0.0) | (Mf.x != 0.0) | (Mf.y != 0.0) | (Mf.z != 0.0);
         const bool pmass = A.has_grav && A.pmS != nullptr;
+        point_rot = follower || pmass;
         v3 Fg = mk(0, 0, 0), Mg = Fg;
-        if (follower || pmass) {
-            Rot R;
-            if (WANT_J) rot_C_dC(th1, R); else R.C = rot_C(th1);
-            F = F + tmul(R.C, Ff);                 // F + C' Ff
-            M = M + tmul(R.C, Mf);
-            if (WANT_J) {                          // F_θ = mul3(C_θ1', C_θ2', C_θ3', Ff), rows of non-prescribed loads zeroed (point.jl:75-105)
-                pJFth = cols(tmul(R.C1, Ff), tmul(R.C2, Ff), tmul(R.C3, Ff));
-                pJMth = cols(tmul(R.C1, Mf), tmul(R.C2, Mf), tmul(R.C3, Mf));
-            }
-            if (pmass) {                           // point.jl:1422-1431, 1476-1487
+        if (point_rot) {
+            m3 C = rot_C(th1);
+            F = F + tmul(C, Ff);                   // F + C' Ff
+            M = M + tmul(C, Mf);
+            if (pmass) {                           // point.jl:1422-1431
                 const double* pm = A.pmS + ((size_t)b * 36) * NP + i;
-                m3 m11 = ldm(pm, NP), m21 = ldm(pm + 18 * NP, NP);
-                v3 Cg = R.C * g;
-                v3 a1 = m11 * Cg, a2 = m21 * Cg;
-                Fg = tmul(R.C, a1); Mg = tmul(R.C, a2);
-                if (WANT_J) {
-                    m3 Cthg = cols(R.C1 * g, R.C2 * g, R.C3 * g);
-                    m3 t1 = cols(tmul(R.C1, a1), tmul(R.C2, a1), tmul(R.C3, a1)) + tmul(R.C, m11 * Cthg);
-                    m3 t2 = cols(tmul(R.C1, a2), tmul(R.C2, a2), tmul(R.C3, a2)) + tmul(R.C, m21 * Cthg);
-                    // rows of the *load* jacobian are masked by pl, the gravity part is not (point.jl:86-105 vs 1484-1485)
-                    m3 ml = pJFth;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) { if (!(fl1 & (64 << 0))) ml.a[k] = 0.0; if (!(fl1 & (64 << 1))) ml.a[3 + k] = 0.0; if (!(fl1 & (64 << 2))) ml.a[6 + k] = 0.0; }
-                    pJFth = ml + t1;
-                    ml = pJMth;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) { if (!(fl1 & (64 << 3))) ml.a[k] = 0.0; if (!(fl1 & (64 << 4))) ml.a[3 + k] = 0.0; if (!(fl1 & (64 << 5))) ml.a[6 + k] = 0.0; }
-                    pJMth = ml + t2;
-                }
-            } else if (WANT_J) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    if (!(fl1 & (64 << 0))) pJFth.a[k] = 0.0; if (!(fl1 & (64 << 1))) pJFth.a[3 + k] = 0.0; if (!(fl1 & (64 << 2))) pJFth.a[6 + k] = 0.0;
-                    if (!(fl1 & (64 << 3))) pJMth.a[k] = 0.0; if (!(fl1 & (64 << 4))) pJMth.a[3 + k] = 0.0; if (!(fl1 & (64 << 5))) pJMth.a[6 + k] = 0.0;
-                }
+                v3 Cg = C * g;
+                Fg = tmul(C, ldm(pm, NP) * Cg); Mg = tmul(C, ldm(pm + 18 * NP, NP) * Cg);
             }
         }
         // loads: prescribed value where pl, else the state variable times fs  (NaN-safe: selected by flag)
@@ -126,52 +142,53 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* xch /*
         Fp = Fp + Fg; Mp = Mp + Mg;
     }
 
-    // ---- element i (element.jl:62-107, 1478-1490, 1860-1893) ----
-    v3 ru = mk(0, 0, 0), rth = ru, F1 = ru, M1 = ru, F2 = ru, M2 = ru;
-    m3 JF1th, JM1th, JF2th, JM2th;   // ∂(F1,M1,F2,M2)/∂θ (same for θ1 and θ2 before masking)
+    // ---- element i core quantities (element.jl:62-107) ----
+    const double* es = A.elemS + ((size_t)b * A.elem_nf) * N + (has_elem ? i : 0);
+    double L = 0.0;
+    m3 Cab = zero33(), CtCab = zero33();
+    Rot R;
+    v3 th = mk(0, 0, 0), F = th, M = th, Le1g = th, kap = th, u2 = th, th2 = th;
     v3 mth2 = mk(1, 1, 1), mu2 = mth2;
+    v3 ru = mk(0, 0, 0), rth = ru, F1 = ru, M1 = ru, F2 = ru, M2 = ru;
+    v3 f1f = ru, f2f = ru, m1f = ru, m2f = ru, CtCabTg = ru;
     if (has_elem) {
-        const double* es = A.elemS + ((size_t)b * A.elem_nf) * N + i;
-        const double L = es[0];
-        m3 Cab = ldm(es + N, N);
-        m3 S11 = ldm(es + 10 * N, N), S12 = ldm(es + 19 * N, N), S21 = ldm(es + 28 * N, N), S22 = ldm(es + 37 * N, N);
+        L = es[0];
+        Cab = ldm(es + N, N);
         const unsigned fl2 = A.flags[i + 1];
         const double* bc2 = A.bcS + ((size_t)b * 18) * NP + i + 1;
         const double* xq = x + 12 * (i + 1);
-        v3 u2 = mk((fl2 & 1) ? bc2[0] : xq[0], (fl2 & 2) ? bc2[NP] : xq[1], (fl2 & 4) ? bc2[2 * NP] : xq[2]);
-        v3 th2 = mk((fl2 & 8) ? bc2[3 * NP] : xq[3], (fl2 & 16) ? bc2[4 * NP] : xq[4], (fl2 & 32) ? bc2[5 * NP] : xq[5]);
+        u2 = mk((fl2 & 1) ? bc2[0] : xq[0], (fl2 & 2) ? bc2[NP] : xq[1], (fl2 & 4) ? bc2[2 * NP] : xq[2]);
+        th2 = mk((fl2 & 8) ? bc2[3 * NP] : xq[3], (fl2 & 16) ? bc2[4 * NP] : xq[4], (fl2 & 32) ? bc2[5 * NP] : xq[5]);
         mu2 = mk((fl2 & 1) ? 0.0 : 1.0, (fl2 & 2) ? 0.0 : 1.0, (fl2 & 4) ? 0.0 : 1.0);
         mth2 = mk((fl2 & 8) ? 0.0 : 1.0, (fl2 & 16) ? 0.0 : 1.0, (fl2 & 32) ? 0.0 : 1.0);
         const double* xe = x + 12 * i + 6;
-        v3 F = mk(xe[0] * fs, xe[1] * fs, xe[2] * fs), M = mk(xe[3] * fs, xe[4] * fs, xe[5] * fs);
-        v3 th = 0.5 * (th1 + th2);
-        Rot R;
+        F = mk(xe[0] * fs, xe[1] * fs, xe[2] * fs); M = mk(xe[3] * fs, xe[4] * fs, xe[5] * fs);
+        th = 0.5 * (th1 + th2);
         if (WANT_J) rot_C_dC(th, R); else R.C = rot_C(th);
-        m3 CtCab = tmul(R.C, Cab);
-        v3 gam = S11 * F + S12 * M, kap = S21 * F + S22 * M;
-        v3 Le1g = mk(L + gam.x, gam.y, gam.z);                 // L e1 + γ
+        CtCab = tmul(R.C, Cab);
+        {
+            m3 S11 = ldm(es + 10 * N, N), S12 = ldm(es + 19 * N, N);
+            v3 gam = S11 * F + S12 * M;
+            Le1g = mk(L + gam.x, gam.y, gam.z);                // L e1 + γ
+        }
+        {
+            m3 S21 = ldm(es + 28 * N, N), S22 = ldm(es + 37 * N, N);
+            kap = S21 * F + S22 * M;
+        }
         v3 Cab1 = mk(Cab.a[0], Cab.a[3], Cab.a[6]);            // Cab e1
-        v3 du = CtCab * Le1g - L * Cab1;
-        v3 Cabk = Cab * kap;
-        m3 Qinv, dQb;
-        if (WANT_J) dQb = rot_Qinv_dQinv_b(th, Cabk, Qinv); else Qinv = rot_Qinv_from_c(rot_scaling(th) * th);
-        ru = (u2 - u1) - du;
-        rth = (th2 - th1) - Qinv * Cabk;
+        // compatibility (element.jl:1478-1490) and resultants (element.jl:1860-1893)
+        ru = (u2 - u1) - (CtCab * Le1g - L * Cab1);
+        rth = (th2 - th1) - rot_Qinv_from_c(rot_scaling(th) * th) * (Cab * kap);
         v3 CF = CtCab * F;
-        v3 LgxF = cross(Le1g, F);
-        v3 t1 = CtCab * M, t2 = 0.5 * (CtCab * LgxF);
+        v3 t1 = CtCab * M, t2 = 0.5 * (CtCab * cross(Le1g, F));
         F1 = CF; F2 = CF; M1 = t1 + t2; M2 = t1 - t2;
-        m3 m11, m21;
-        v3 CtCabTg = mk(0, 0, 0);
         if (A.has_grav) {
-            m11 = ldm(es + 46 * N, N); m21 = ldm(es + 64 * N, N);
             CtCabTg = tmul(CtCab, g);
-            v3 tg = -(CtCab * (m11 * CtCabTg));
+            v3 tg = -(CtCab * (ldm(es + 46 * N, N) * CtCabTg));
             F1 = F1 - 0.5 * tg; F2 = F2 + 0.5 * tg;
-            tg = -(CtCab * (m21 * CtCabTg));
+            tg = -(CtCab * (ldm(es + 64 * N, N) * CtCabTg));
             M1 = M1 - 0.5 * tg; M2 = M2 + 0.5 * tg;
         }
-        v3 f1f, f2f, m1f, m2f;
         if (A.dlS) {
             const double* d = A.dlS + ((size_t)b * 24) * N + i;
             f1f = ldv(d + 12 * N, N); f2f = ldv(d + 15 * N, N); m1f = ldv(d + 18 * N, N); m2f = ldv(d + 21 * N, N);
@@ -180,125 +197,166 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* xch /*
             M1 = M1 + (ldv(d + 6 * N, N) + tmul(R.C, m1f));
             M2 = M2 - (ldv(d + 9 * N, N) + tmul(R.C, m2f));
         }
-        if (WANT_J) {
-            double* Je = J + (size_t)(12 * i + 6) * GXB_ROWW;
-            // compatibility rows (element.jl:1492-1521, 2507-2524)
-            v3 w = Cab * Le1g;
-            m3 duth = cols(tmul(R.C1, w), tmul(R.C2, w), tmul(R.C3, w));
-            m3 ruth = -0.5 * duth;
-            stblk(Je, 0, 6, colmask(-eye33(), mu1));
-            stblk(Je, 0, 9, colmask(ruth, mth1));
-            stblk(Je, 0, 12, (-fs) * (CtCab * S11));
-            stblk(Je, 0, 15, (-fs) * (CtCab * S12));
-            stblk(Je, 0, 18, colmask(eye33(), mu2));
-            stblk(Je, 0, 21, colmask(ruth, mth2));
-            m3 hd = -0.5 * dQb;
-            m3 QC = Qinv * Cab;
-            stblk(Je, 3, 6, zero33());
-            stblk(Je, 3, 9, colmask(hd - eye33(), mth1));
-            stblk(Je, 3, 12, (-fs) * (QC * S21));
-            stblk(Je, 3, 15, (-fs) * (QC * S22));
-            stblk(Je, 3, 18, zero33());
-            stblk(Je, 3, 21, colmask(hd + eye33(), mth2));
-            // resultant jacobians (element.jl:1945-2027)
-            v3 wF = Cab * F, wM = Cab * M, wX = Cab * LgxF;
-            m3 Fth = 0.5 * cols(tmul(R.C1, wF), tmul(R.C2, wF), tmul(R.C3, wF));
-            m3 tm1 = cols(tmul(R.C1, wM), tmul(R.C2, wM), tmul(R.C3, wM));
-            m3 tm2 = 0.5 * cols(tmul(R.C1, wX), tmul(R.C2, wX), tmul(R.C3, wX));
-            JF1th = Fth; JF2th = Fth;
-            JM1th = 0.5 * (tm1 + tm2); JM2th = 0.5 * (tm1 - tm2);
-            if (A.has_grav) {
-                m3 Cthg = cols(R.C1 * g, R.C2 * g, R.C3 * g);
-                v3 a1 = Cab * (m11 * CtCabTg);
-                m3 tg = -0.5 * (cols(tmul(R.C1, a1), tmul(R.C2, a1), tmul(R.C3, a1)) + CtCab * (m11 * tmul(Cab, Cthg)));
-                JF1th = JF1th - 0.5 * tg; JF2th = JF2th + 0.5 * tg;
-                v3 a2 = Cab * (m21 * CtCabTg);
-                tg = -0.5 * (cols(tmul(R.C1, a2), tmul(R.C2, a2), tmul(R.C3, a2)) + CtCab * (m21 * tmul(Cab, Cthg)));
-                JM1th = JM1th - 0.5 * tg; JM2th = JM2th + 0.5 * tg;
-            }
-            if (A.dlS) {
-                JF1th = JF1th + 0.5 * cols(tmul(R.C1, f1f), tmul(R.C2, f1f), tmul(R.C3, f1f));
-                JF2th = JF2th - 0.5 * cols(tmul(R.C1, f2f), tmul(R.C2, f2f), tmul(R.C3, f2f));
-                JM1th = JM1th + 0.5 * cols(tmul(R.C1, m1f), tmul(R.C2, m1f), tmul(R.C3, m1f));
-                JM2th = JM2th - 0.5 * cols(tmul(R.C1, m2f), tmul(R.C2, m2f), tmul(R.C3, m2f));
-            }
-            m3 M1F = 0.5 * (CtCab * (tilde(Le1g) - tilde(F) * S11));
-            m3 hM = 0.5 * ((CtCab * tilde(F)) * S12);
-            // rows of point i (start): element columns assigned, θ columns of point i+1 own to this element alone
-            double* Ja = J + (size_t)(12 * i) * GXB_ROWW;
-            stblk(Ja, 0, 18, -CtCab); stblk(Ja, 0, 21, zero33());
-            stblk(Ja, 0, 27, (-rfs) * colmask(JF1th, mth2));
-            stblk(Ja, 3, 18, -M1F); stblk(Ja, 3, 21, hM - CtCab);
-            stblk(Ja, 3, 27, (-rfs) * colmask(JM1th, mth2));
-            // rows of point i+1 (stop): columns of point i and of this element
-            double* Jb = J + (size_t)(12 * (i + 1)) * GXB_ROWW;
-            stblk(Jb, 0, 3, rfs * colmask(JF2th, mth1));
-            stblk(Jb, 0, 6, CtCab); stblk(Jb, 0, 9, zero33());
-            stblk(Jb, 3, 3, rfs * colmask(JM2th, mth1));
-            stblk(Jb, 3, 6, -M1F); stblk(Jb, 3, 9, CtCab + hM);
-        }
+        double* mine = xch + (size_t)threadIdx.x * GXB_XCH;
+        mine[0] = F2.x * rfs; mine[1] = F2.y * rfs; mine[2] = F2.z * rfs;
+        mine[3] = M2.x * rfs; mine[4] = M2.y * rfs; mine[5] = M2.z * rfs;
     }
-
-    // ---- exchange: element i -> thread i+1 (its stop point's shared θ block and residual) ----
-    double* mine = xch + (size_t)threadIdx.x * GXB_XCH;
-    if (has_elem) {
-        if (WANT_J) {
-            m3 bF = rfs * colmask(JF2th, mth2), bM = rfs * colmask(JM2th, mth2);
-#pragma unroll
-            for (int k = 0; k < 9; k++) { mine[k] = bF.a[k]; mine[9 + k] = bM.a[k]; }
-        }
-        mine[18] = F2.x * rfs; mine[19] = F2.y * rfs; mine[20] = F2.z * rfs;
-        mine[21] = M2.x * rfs; mine[22] = M2.y * rfs; mine[23] = M2.z * rfs;
-    }
+    if (WANT_J) tile_clear(mytile);
     __syncthreads();
-    if (!valid) return;
-    const double* prev = xch + (size_t)(i > 0 ? threadIdx.x - 1 : 0) * GXB_XCH;   // element i-1's record, used when i > 0
-    double* rp = r + 12 * i;
-    // ---- point i rows: own term, += element i-1, -= element i ----
-    {
+
+    // ---- residual: point rows = own term, += element i-1, -= element i ; element rows = compatibility ----
+    if (valid) {
+        const double* prev = xch + (size_t)(i > 0 ? threadIdx.x - 1 : 0) * GXB_XCH;
+        double* rp = r + 12 * i;
         double own[6] = {-Fp.x * rfs, -Fp.y * rfs, -Fp.z * rfs, -Mp.x * rfs, -Mp.y * rfs, -Mp.z * rfs};
         double sub[6] = {F1.x * rfs, F1.y * rfs, F1.z * rfs, M1.x * rfs, M1.y * rfs, M1.z * rfs};
 #pragma unroll
         for (int k = 0; k < 6; k++) {
             double v = own[k];
-            if (i > 0) v += prev[18 + k];
+            if (i > 0) v += prev[k];
             if (has_elem) v -= sub[k];
+            if (A.two_d && k >= 2 && k <= 4) v = x[12 * i + k];
             rp[k] = v;
         }
-    }
-    if (has_elem) { double* re = rp + 6; re[0] = ru.x; re[1] = ru.y; re[2] = ru.z; re[3] = rth.x; re[4] = rth.y; re[5] = rth.z; }
-    if (WANT_J) {
-        double* Ja = J + (size_t)(12 * i) * GXB_ROWW;
-        // -F_F : identity on DOFs whose load is the unknown (point.jl:107-115, 1795)
-        m3 FF = zero33(), MM = zero33();
-        FF.a[0] = (fl1 & 64) ? 0.0 : -1.0; FF.a[4] = (fl1 & 128) ? 0.0 : -1.0; FF.a[8] = (fl1 & 256) ? 0.0 : -1.0;
-        MM.a[0] = (fl1 & 512) ? 0.0 : -1.0; MM.a[4] = (fl1 & 1024) ? 0.0 : -1.0; MM.a[8] = (fl1 & 2048) ? 0.0 : -1.0;
-        m3 JFth = (-rfs) * colmask(pJFth, mth1);                 // -F_θ θ_θ / fs
-        m3 JMth = MM - rfs * colmask(pJMth, mth1);               // -M_M - M_θ θ_θ / fs
-        if (i > 0) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) { JFth.a[k] += prev[k]; JMth.a[k] += prev[9 + k]; }
-        }
         if (has_elem) {
-            JFth = JFth - rfs * colmask(JF1th, mth1);
-            JMth = JMth - rfs * colmask(JM1th, mth1);
+            double re[6] = {ru.x, ru.y, ru.z, rth.x, rth.y, rth.z};
+#pragma unroll
+            for (int k = 0; k < 6; k++) rp[6 + k] = (A.two_d && k >= 2 && k <= 4) ? x[12 * i + 6 + k] : re[k];
         }
-        stblk(Ja, 0, 12, FF); stblk(Ja, 0, 15, JFth);
-        stblk(Ja, 3, 12, zero33()); stblk(Ja, 3, 15, JMth);
     }
-    // ---- planar constraint rows (system.jl:1072-1103): rows 2,3,4 of every 6-slot become x = 0 ----
-    if (A.two_d) {
-        const int nslots = has_elem ? 2 : 1;
-        for (int s = 0; s < nslots; s++) {
-            const double* xs = x + 12 * i + 6 * s;
-            double* rs = rp + 6 * s;
-            for (int k = 2; k <= 4; k++) {
-                rs[k] = xs[k];
-                if (WANT_J) {
-                    double* row = J + (size_t)(12 * i + 6 * s + k) * GXB_ROWW;
-                    for (int c = 0; c < GXB_ROWW; c++) row[c] = (c == 12 + k) ? 1.0 : 0.0;
-                }
+    if (!WANT_J) return;
+
+    // =================== pass P1: force-equilibrium rows of point i (rows 12i+0..2) ===================
+    m3 JFa, JFb;                                             // ∂F1/∂θ, ∂F2/∂θ of element i (element.jl:1954-2000)
+    if (has_elem) {
+        m3 Fth = 0.5 * mul3t(R, Cab * F);
+        JFa = Fth; JFb = Fth;
+        if (A.has_grav) {
+            m3 m11 = ldm(es + 46 * N, N);
+            m3 Cthg = cols(R.C1 * g, R.C2 * g, R.C3 * g);
+            m3 tg = -0.5 * (mul3t(R, Cab * (m11 * CtCabTg)) + CtCab * (m11 * tmul(Cab, Cthg)));
+            JFa = JFa - 0.5 * tg; JFb = JFb + 0.5 * tg;
+        }
+        if (A.dlS) { JFa = JFa + 0.5 * mul3t(R, f1f); JFb = JFb - 0.5 * mul3t(R, f2f); }
+        // stop-point rows (station i+1): columns of point i (slots 0..5), of this element (6..11); shared θ-block parked in 0..2
+        tblk(nexttile, 0, rfs * colmask(JFb, mth2));
+        tblk(nexttile, 3, rfs * colmask(JFb, mth1));
+        tblk(nexttile, 6, CtCab);                            // F2_F
+    }
+    __syncthreads();
+    if (valid) {
+        m3 own = zero33();                                   // -F_θ θ_θ / fs of the point itself
+        if (point_rot) {
+            Rot Rp; rot_C_dC(th1, Rp);
+            const double* bc = A.bcS + ((size_t)b * 18) * NP + i;
+            m3 Fth = rowmask(mul3t(Rp, ldv(bc + 12 * NP, NP)), fl1 & 64, fl1 & 128, fl1 & 256);
+            if (A.has_grav && A.pmS) {                       // point.jl:1476-1487
+                m3 m11 = ldm(A.pmS + ((size_t)b * 36) * NP + i, NP);
+                m3 Cthg = cols(Rp.C1 * g, Rp.C2 * g, Rp.C3 * g);
+                Fth = Fth + mul3t(Rp, m11 * (Rp.C * g)) + tmul(Rp.C, m11 * Cthg);
             }
+            own = (-rfs) * colmask(Fth, mth1);
         }
+        m3 blk = own + tget(mytile, 0);                      // += element i-1
+        tblk(mytile, 0, zero33());
+        if (has_elem) blk = blk - rfs * colmask(JFa, mth1);  // -= element i
+        m3 FF = zero33();                                    // -F_F : identity on DOFs whose load is the unknown (point.jl:107-115)
+        FF.a[0] = (fl1 & 64) ? 0.0 : -1.0; FF.a[4] = (fl1 & 128) ? 0.0 : -1.0; FF.a[8] = (fl1 & 256) ? 0.0 : -1.0;
+        tblk(mytile, 12, FF);
+        tblk(mytile, 15, blk);
+        if (has_elem) {
+            tblk(mytile, 18, -CtCab);                        // -F1_F
+            tblk(mytile, 27, (-rfs) * colmask(JFa, mth2));
+        }
+        if (A.two_d) tile_planar(mytile, 0);
     }
+    __syncthreads();
+    tile_flush(tiles, J, NP, 0);
+    __syncthreads();
+
+    // =================== pass P2: moment-equilibrium rows of point i (rows 12i+3..5) ===================
+    tile_clear(mytile);
+    __syncthreads();
+    m3 JMa, M1F, hM;
+    if (has_elem) {
+        m3 tm1 = mul3t(R, Cab * M);
+        m3 tm2 = 0.5 * mul3t(R, Cab * cross(Le1g, F));
+        JMa = 0.5 * (tm1 + tm2);
+        m3 JMb = 0.5 * (tm1 - tm2);
+        if (A.has_grav) {
+            m3 m21 = ldm(es + 64 * N, N);
+            m3 Cthg = cols(R.C1 * g, R.C2 * g, R.C3 * g);
+            m3 tg = -0.5 * (mul3t(R, Cab * (m21 * CtCabTg)) + CtCab * (m21 * tmul(Cab, Cthg)));
+            JMa = JMa - 0.5 * tg; JMb = JMb + 0.5 * tg;
+        }
+        if (A.dlS) { JMa = JMa + 0.5 * mul3t(R, m1f); JMb = JMb - 0.5 * mul3t(R, m2f); }
+        m3 CtF = CtCab * tilde(F);
+        M1F = 0.5 * (CtCab * tilde(Le1g) - CtF * ldm(es + 10 * N, N));     // ½ CtCab (tilde(L e1+γ) - F~ S11)
+        hM = 0.5 * (CtF * ldm(es + 19 * N, N));                            // ½ CtCab F~ S12
+        tblk(nexttile, 0, rfs * colmask(JMb, mth2));
+        tblk(nexttile, 3, rfs * colmask(JMb, mth1));
+        tblk(nexttile, 6, -M1F);                             // M2_F
+        tblk(nexttile, 9, CtCab + hM);                       // M2_M
+    }
+    __syncthreads();
+    if (valid) {
+        m3 MM = zero33();                                    // -M_M
+        MM.a[0] = (fl1 & 512) ? 0.0 : -1.0; MM.a[4] = (fl1 & 1024) ? 0.0 : -1.0; MM.a[8] = (fl1 & 2048) ? 0.0 : -1.0;
+        m3 own = MM;
+        if (point_rot) {
+            Rot Rp; rot_C_dC(th1, Rp);
+            const double* bc = A.bcS + ((size_t)b * 18) * NP + i;
+            m3 Mth = rowmask(mul3t(Rp, ldv(bc + 15 * NP, NP)), fl1 & 512, fl1 & 1024, fl1 & 2048);
+            if (A.has_grav && A.pmS) {
+                m3 m21 = ldm(A.pmS + ((size_t)b * 36 + 18) * NP + i, NP);
+                m3 Cthg = cols(Rp.C1 * g, Rp.C2 * g, Rp.C3 * g);
+                Mth = Mth + mul3t(Rp, m21 * (Rp.C * g)) + tmul(Rp.C, m21 * Cthg);
+            }
+            own = MM - rfs * colmask(Mth, mth1);             // -M_M - M_θ θ_θ / fs
+        }
+        m3 blk = own + tget(mytile, 0);
+        tblk(mytile, 0, zero33());
+        if (has_elem) blk = blk - rfs * colmask(JMa, mth1);
+        tblk(mytile, 15, blk);
+        if (has_elem) {
+            tblk(mytile, 18, -M1F);                          // -M1_F
+            tblk(mytile, 21, hM - CtCab);                    // -M1_M
+            tblk(mytile, 27, (-rfs) * colmask(JMa, mth2));
+        }
+        if (A.two_d) tile_planar(mytile, 3);
+    }
+    __syncthreads();
+    tile_flush(tiles, J, NP, 3);
+    __syncthreads();
+
+    // =================== pass E1: compatibility rows ru of element i (rows 12i+6..8) ===================
+    tile_clear(mytile);
+    if (has_elem) {                                          // element.jl:1492-1505, 2507-2515
+        m3 ruth = -0.5 * mul3t(R, Cab * Le1g);
+        tblk(mytile, 6, colmask(-eye33(), mu1));
+        tblk(mytile, 9, colmask(ruth, mth1));
+        tblk(mytile, 12, (-fs) * (CtCab * ldm(es + 10 * N, N)));
+        tblk(mytile, 15, (-fs) * (CtCab * ldm(es + 19 * N, N)));
+        tblk(mytile, 18, colmask(eye33(), mu2));
+        tblk(mytile, 21, colmask(ruth, mth2));
+        if (A.two_d) tile_planar(mytile, 0);
+    }
+    __syncthreads();
+    tile_flush(tiles, J, N, 6);
+    __syncthreads();
+
+    // =================== pass E2: compatibility rows rθ of element i (rows 12i+9..11) ===================
+    tile_clear(mytile);
+    if (has_elem) {                                          // element.jl:1507-1518, 2517-2524
+        m3 Qinv;
+        m3 hd = -0.5 * rot_Qinv_dQinv_b(th, Cab * kap, Qinv);
+        m3 QC = Qinv * Cab;
+        tblk(mytile, 9, colmask(hd - eye33(), mth1));
+        tblk(mytile, 12, (-fs) * (QC * ldm(es + 28 * N, N)));
+        tblk(mytile, 15, (-fs) * (QC * ldm(es + 37 * N, N)));
+        tblk(mytile, 21, colmask(hd + eye33(), mth2));
+        if (A.two_d) tile_planar(mytile, 3);
+    }
+    __syncthreads();
+    tile_flush(tiles, J, N, 9);
 }
