@@ -1,0 +1,429 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see gxb_math.hpp).
+//
+// CPU restatement of GXBeam.jl's steady-state residual / Jacobian assembly on a DynamicSystem (12 states per point):
+//   update_body_acceleration_indices!, body_accelerations     src/system.jl:138-182
+//   point_velocities                                          src/point.jl:228-234
+//   steady_point_properties / _jacobian_properties            src/point.jl:630-672, 964-1023
+//   dynamic/steady_point_resultants (+ jacobians)             src/point.jl:1438-1449, 1495-1540
+//   point_velocity_residuals / dynamic_point_velocity_jacobians  src/point.jl:1658-1666, 1728-1739
+//   insert_dynamic/steady_point_jacobians!                    src/point.jl:1907-1935, 1809-1844
+//   steady_point_residual! / _jacobian!                       src/point.jl:2137-2158, 2346-2367
+//   steady_element_properties / _jacobian_properties          src/element.jl:117-217, 649-840   (incl. structural damping)
+//   dynamic_compatibility_jacobians                           src/element.jl:1550-1578
+//   dynamic_element_resultants (+ jacobians)                  src/element.jl:1901-1919, 2035-2064, 2219-2328
+//   insert_dynamic/steady_element_jacobians!                  src/element.jl:2685-2759, 2554-2583
+//   steady_element_residual! / _jacobian!                     src/element.jl:3019-3035, 3209-3229
+//   steady_system_residual! / _jacobian!                      src/system.jl:427-455, 693-720
+#pragma once
+#include "gxb_static.hpp"
+
+namespace gxo {
+
+struct DynParams {
+    double vb[3] = {0, 0, 0}, wb[3] = {0, 0, 0}, ab[3] = {0, 0, 0}, alb[3] = {0, 0, 0};
+    int structural_damping = 0;
+};
+
+// system.jl:138-150 (first point, in ascending index order, that has pd & pl on DOF i)
+inline void update_body_acceleration_indices(const Problem& P, Indices& idx) {
+    for (int i = 0; i < 6; i++) {
+        idx.icol_body[i] = 0;
+        for (int64_t ip = 0; ip < P.np; ip++)
+            if (P.pd[6 * ip + i] && P.pl[6 * ip + i]) { idx.icol_body[i] = idx.icol_point[ip] + i; break; }
+    }
+}
+// system.jl:167-182
+template <class T> void body_accelerations(const Indices& idx, const T* x, const DynParams& D, V3<T>& ab, V3<T>& alb) {
+    for (int i = 0; i < 3; i++) {
+        ab.v[i] = idx.icol_body[i] ? x[idx.icol_body[i] - 1] : T(D.ab[i]);
+        alb.v[i] = idx.icol_body[3 + i] ? x[idx.icol_body[3 + i] - 1] : T(D.alb[i]);
+    }
+}
+
+template <class T> struct DynPoint : PointProps<T> {
+    M3<T> Qinv, Qi_t1, Qi_t2, Qi_t3;
+    V3<T> dx, vb, wb, ab, alb, V, Om, Pm, H, udot, thdot, Vdot, Omdot, Pdot, Hdot;
+    M3<T> P_th, P_V, P_Om, H_th, H_V, H_Om;
+    M3<T> Pdot_ab, Pdot_alb, Pdot_u, Pdot_th, Pdot_V, Pdot_Om, Hdot_ab, Hdot_alb, Hdot_u, Hdot_th, Hdot_V, Hdot_Om;
+};
+
+// point.jl:630-672
+template <class T> DynPoint<T> steady_point_properties(const Problem& P, const Indices& idx, const T* x, int64_t ip, const DynParams& D,
+                                                       const V3<T>& ab, const V3<T>& alb) {
+    DynPoint<T> p;
+    static_cast<PointProps<T>&>(p) = static_point_properties(P, idx, x, ip);
+    p.Qinv = get_Qinv(p.th);
+    p.dx = cvec<T>(P.points + 3 * ip);
+    p.vb = cvec<T>(D.vb); p.wb = cvec<T>(D.wb); p.ab = ab; p.alb = alb;
+    int64_t icol = idx.icol_point[ip] - 1;
+    p.V = ld3(x, icol + 6); p.Om = ld3(x, icol + 9);
+    M3<T> Ct = tr(p.C);
+    p.Pm = Ct * (p.mass11 * (p.C * p.V)) + Ct * (p.mass12 * (p.C * p.Om));
+    p.H = Ct * (p.mass21 * (p.C * p.V)) + Ct * (p.mass22 * (p.C * p.Om));
+    p.udot = zero3<T>(); p.thdot = zero3<T>();
+    p.Vdot = ab + cross(alb, p.dx + p.u) + cross(p.wb, p.udot);
+    p.Omdot = alb;
+    p.Pdot = Ct * (p.mass11 * (p.C * p.Vdot)) + Ct * (p.mass12 * (p.C * p.Omdot));
+    p.Hdot = Ct * (p.mass21 * (p.C * p.Vdot)) + Ct * (p.mass22 * (p.C * p.Omdot));
+    return p;
+}
+// point.jl:964-1023
+template <class T> void steady_point_jacobian_properties(const Problem& P, const Indices& idx, const T* x, int64_t ip, DynPoint<T>& p) {
+    static_point_jacobian_properties(P, idx, x, ip, p);
+    get_Qinv_th(p.th, p.Qi_t1, p.Qi_t2, p.Qi_t3);
+    M3<T> Ct = tr(p.C), Ct1 = tr(p.C_t1), Ct2 = tr(p.C_t2), Ct3 = tr(p.C_t3);
+    auto m3c = [&](const V3<T>& w) { return mul3(p.C_t1, p.C_t2, p.C_t3, w); };
+    auto m3t = [&](const V3<T>& w) { return mul3(Ct1, Ct2, Ct3, w); };
+    p.P_th = m3t(p.mass11 * (p.C * p.V) + p.mass12 * (p.C * p.Om)) + Ct * (p.mass11 * m3c(p.V)) + Ct * (p.mass12 * m3c(p.Om));
+    p.P_V = Ct * p.mass11 * p.C; p.P_Om = Ct * p.mass12 * p.C;
+    p.H_th = m3t(p.mass21 * (p.C * p.V) + p.mass22 * (p.C * p.Om)) + Ct * (p.mass21 * m3c(p.V)) + Ct * (p.mass22 * m3c(p.Om));
+    p.H_V = Ct * p.mass21 * p.C; p.H_Om = Ct * p.mass22 * p.C;
+    M3<T> Vdot_alb = -tilde(p.dx + p.u), Vdot_u = tilde(p.alb);
+    M3<T> Pdot_Vdot = Ct * p.mass11 * p.C, Pdot_Omdot = Ct * p.mass12 * p.C, Hdot_Vdot = Ct * p.mass21 * p.C, Hdot_Omdot = Ct * p.mass22 * p.C;
+    p.Pdot_ab = Pdot_Vdot; p.Pdot_alb = Pdot_Vdot * Vdot_alb + Pdot_Omdot;
+    p.Hdot_ab = Hdot_Vdot; p.Hdot_alb = Hdot_Vdot * Vdot_alb + Hdot_Omdot;
+    p.Pdot_u = Pdot_Vdot * Vdot_u; p.Hdot_u = Hdot_Vdot * Vdot_u;
+    p.Pdot_th = m3t(p.mass11 * (p.C * p.Vdot)) + Ct * (p.mass11 * m3c(p.Vdot)) + m3t(p.mass12 * (p.C * p.Omdot)) + Ct * (p.mass12 * m3c(p.Omdot));
+    p.Hdot_th = m3t(p.mass21 * (p.C * p.Vdot)) + Ct * (p.mass21 * m3c(p.Vdot)) + m3t(p.mass22 * (p.C * p.Omdot)) + Ct * (p.mass22 * m3c(p.Omdot));
+    p.Pdot_V = zero33<T>(); p.Hdot_V = zero33<T>(); p.Pdot_Om = zero33<T>(); p.Hdot_Om = zero33<T>();
+}
+// point.jl:1438-1449
+template <class T> void dynamic_point_resultants(const DynPoint<T>& p, V3<T>& F, V3<T>& M) {
+    static_point_resultants(p, F, M);
+    F = F - (cross(p.wb, p.Pm) + p.Pdot);
+    M = M - (cross(p.wb, p.H) + cross(p.V, p.Pm) + p.Hdot);
+}
+template <class T> struct PointResJac { M3<T> F_th, M_th, F_u, F_V, F_Om, M_u, M_V, M_Om, F_ab, F_alb, M_ab, M_alb; };
+// point.jl:1495-1540
+template <class T> PointResJac<T> steady_point_resultant_jacobians(const DynPoint<T>& p) {
+    PointResJac<T> j;
+    static_point_resultant_jacobians(p, j.F_th, j.M_th);
+    M3<T> wt = tilde(p.wb), Vt = tilde(p.V);
+    j.F_u = -p.Pdot_u;
+    j.F_th = j.F_th - (wt * p.P_th + p.Pdot_th);
+    j.F_V = -(wt * p.P_V) - p.Pdot_V;
+    j.F_Om = -(wt * p.P_Om) - p.Pdot_Om;
+    j.M_u = -p.Hdot_u;
+    j.M_th = j.M_th - (wt * p.H_th + Vt * p.P_th + p.Hdot_th);
+    j.M_V = -(wt * p.H_V) - Vt * p.P_V + tilde(p.Pm) - p.Hdot_V;
+    j.M_Om = -(wt * p.H_Om) - Vt * p.P_Om - p.Hdot_Om;
+    j.F_ab = -p.Pdot_ab; j.F_alb = -p.Pdot_alb; j.M_ab = -p.Hdot_ab; j.M_alb = -p.Hdot_alb;
+    return j;
+}
+// point.jl:1658-1666
+template <class T> void point_velocity_residuals(const DynPoint<T>& p, V3<T>& rV, V3<T>& rOm) {
+    rV = p.V - p.vb - cross(p.wb, p.dx) - cross(p.wb, p.u) - p.udot;
+    rOm = p.Qinv * (p.C * (p.Om - p.wb)) - p.thdot;
+}
+// point.jl:2137-2158
+template <class T> void steady_point_residual(const Problem& P, const Indices& idx, const T* x, int64_t ip, const DynParams& D, const V3<T>& ab,
+                                              const V3<T>& alb, T* resid) {
+    int64_t irow = idx.irow_point[ip] - 1;
+    DynPoint<T> p = steady_point_properties(P, idx, x, ip, D, ab, alb);
+    V3<T> F, M, rV, rOm;
+    dynamic_point_resultants(p, F, M);
+    point_velocity_residuals(p, rV, rOm);
+    T fs = T(P.force_scaling);
+    for (int i = 0; i < 3; i++) { resid[irow + i] = -F[i] / fs; resid[irow + 3 + i] = -M[i] / fs; resid[irow + 6 + i] = rV[i]; resid[irow + 9 + i] = rOm[i]; }
+}
+template <class J, class T> void setcol3(J& jac, int64_t r0, int64_t c, const V3<T>& v) { for (int i = 0; i < 3; i++) jac.set(r0 + i, c, v[i]); }
+template <class J, class T> void addcol3(J& jac, int64_t r0, int64_t c, const V3<T>& v) { for (int i = 0; i < 3; i++) jac.add(r0 + i, c, v[i]); }
+// point.jl:2346-2367, 1785-1800, 1907-1935, 1809-1844
+template <class T, class J> void steady_point_jacobian(const Problem& P, const Indices& idx, const T* x, int64_t ip, const DynParams& D, const V3<T>& ab,
+                                                       const V3<T>& alb, J& jac) {
+    DynPoint<T> p = steady_point_properties(P, idx, x, ip, D, ab, alb);
+    steady_point_jacobian_properties(P, idx, x, ip, p);
+    PointResJac<T> r = steady_point_resultant_jacobians(p);
+    // dynamic_point_velocity_jacobians (point.jl:1728-1739)
+    M3<T> rV_u = -tilde(p.wb), rV_V = eye3<T>();
+    M3<T> rOm_th = mul3(p.Qi_t1, p.Qi_t2, p.Qi_t3, p.C * (p.Om - p.wb)) + p.Qinv * mul3(p.C_t1, p.C_t2, p.C_t3, p.Om - p.wb);
+    M3<T> rOm_Om = p.Qinv * p.C;
+    int64_t irow = idx.irow_point[ip] - 1, icol = idx.icol_point[ip] - 1;
+    T fs = T(P.force_scaling);
+    // insert_static_point_jacobians!
+    set33(jac, irow, icol, -p.F_F);
+    set33(jac, irow, icol + 3, (-(r.F_th * p.th_th)) / fs);
+    set33(jac, irow + 3, icol + 3, -p.M_M - (r.M_th * p.th_th) / fs);
+    // insert_dynamic_point_jacobians!
+    set33(jac, irow, icol + 6, (-r.F_V) / fs);
+    set33(jac, irow, icol + 9, (-r.F_Om) / fs);
+    set33(jac, irow + 3, icol + 6, (-r.M_V) / fs);
+    set33(jac, irow + 3, icol + 9, (-r.M_Om) / fs);
+    set33(jac, irow + 6, icol, rV_u * p.u_u);
+    set33(jac, irow + 6, icol + 6, rV_V);
+    set33(jac, irow + 9, icol + 3, rOm_th * p.th_th);
+    set33(jac, irow + 9, icol + 9, rOm_Om);
+    // insert_steady_point_jacobians!
+    sub33m(jac, irow, icol, (r.F_u * p.u_u) / fs);
+    sub33m(jac, irow + 3, icol, (r.M_u * p.u_u) / fs);
+    for (int i = 0; i < 3; i++) {
+        if (idx.icol_body[i]) { setcol3(jac, irow, idx.icol_body[i] - 1, (-col(r.F_ab, i)) / fs); setcol3(jac, irow + 3, idx.icol_body[i] - 1, (-col(r.M_ab, i)) / fs); }
+        if (idx.icol_body[3 + i]) { setcol3(jac, irow, idx.icol_body[3 + i] - 1, (-col(r.F_alb, i)) / fs); setcol3(jac, irow + 3, idx.icol_body[3 + i] - 1, (-col(r.M_alb, i)) / fs); }
+    }
+}
+
+// ---------------------------------------------------------------- elements ----
+template <class T> struct DynElem : ElemProps<T> {
+    M3<T> Q;
+    V3<T> dx, vb, wb, ab, alb, V1, V2, Om1, Om2, V, Om, Pm, H, udot, thdot, Vdot, Omdot, Pdot, Hdot;
+    // structural damping
+    int damping = 0;
+    M3<T> mu11, mu22, C1, C2, Qinv1, Qinv2, dQ;
+    V3<T> dx1, dx2, udot1, udot2, uedot, thdot1, thdot2, thedot, du, dth, dudot, dthdot, gamdot, kapdot;
+    // jacobian properties
+    M3<T> gam_u1, gam_u2, gam_th1, gam_th2, gam_V1, gam_V2, gam_Om1, gam_Om2, kap_th1, kap_th2, kap_Om1, kap_Om2;
+    M3<T> P_th, P_V, P_Om, H_th, H_V, H_Om;
+    M3<T> Pdot_ab, Pdot_alb, Pdot_u, Pdot_th, Pdot_V, Pdot_Om, Hdot_ab, Hdot_alb, Hdot_u, Hdot_th, Hdot_V, Hdot_Om;
+};
+// element.jl:117-217
+template <class T> DynElem<T> steady_element_properties(const Problem& P, const Indices& idx, const T* x, int64_t ie, const DynParams& D,
+                                                        const V3<T>& ab, const V3<T>& alb) {
+    DynElem<T> p;
+    static_cast<ElemProps<T>&>(p) = static_element_properties(P, idx, x, ie);
+    const double* e = P.elems + 91 * ie;
+    V3<T> e1 = unit<T>(0);
+    p.Q = get_Q(p.th);
+    p.dx = cvec<T>(e + 1);
+    p.vb = cvec<T>(D.vb); p.wb = cvec<T>(D.wb); p.ab = ab; p.alb = alb;
+    int64_t ia = P.start[ie] - 1, ib = P.stop[ie] - 1;
+    int64_t ic1 = idx.icol_point[ia] - 1, ic2 = idx.icol_point[ib] - 1;
+    p.V1 = ld3(x, ic1 + 6); p.Om1 = ld3(x, ic1 + 9); p.V2 = ld3(x, ic2 + 6); p.Om2 = ld3(x, ic2 + 9);
+    p.V = (p.V1 + p.V2) / T(2); p.Om = (p.Om1 + p.Om2) / T(2);
+    M3<T> CtCabT = tr(p.CtCab);
+    p.Pm = p.CtCab * (p.mass11 * (CtCabT * p.V)) + p.CtCab * (p.mass12 * (CtCabT * p.Om));
+    p.H = p.CtCab * (p.mass21 * (CtCabT * p.V)) + p.CtCab * (p.mass22 * (CtCabT * p.Om));
+    p.udot = zero3<T>(); p.thdot = zero3<T>();
+    p.Vdot = ab + cross(alb, p.dx + p.u) + cross(p.wb, p.udot);
+    p.Omdot = alb;
+    p.Pdot = p.CtCab * (p.mass11 * (CtCabT * p.Vdot)) + p.CtCab * (p.mass12 * (CtCabT * p.Omdot));
+    p.Hdot = p.CtCab * (p.mass21 * (CtCabT * p.Vdot)) + p.CtCab * (p.mass22 * (CtCabT * p.Omdot));
+    p.damping = D.structural_damping;
+    if (p.damping) {
+        const double* mu = e + 85;
+        p.mu11 = zero33<T>(); p.mu22 = zero33<T>();
+        for (int i = 0; i < 3; i++) { p.mu11.m[i][i] = T(mu[i]); p.mu22.m[i][i] = T(mu[3 + i]); }
+        p.C1 = get_C(p.th1); p.C2 = get_C(p.th2); p.Qinv1 = get_Qinv(p.th1); p.Qinv2 = get_Qinv(p.th2);
+        p.dx1 = cvec<T>(P.points + 3 * ia); p.dx2 = cvec<T>(P.points + 3 * ib);
+        p.udot1 = p.V1 - p.vb - cross(p.wb, p.dx1 + p.u1);
+        p.udot2 = p.V2 - p.vb - cross(p.wb, p.dx2 + p.u2);
+        p.uedot = (p.udot1 + p.udot2) / T(2);
+        p.thdot1 = p.Qinv1 * (p.C1 * (p.Om1 - p.wb));
+        p.thdot2 = p.Qinv2 * (p.C2 * (p.Om2 - p.wb));
+        p.thedot = (p.thdot1 + p.thdot2) / T(2);
+        p.du = p.u2 - p.u1; p.dth = p.th2 - p.th1;
+        p.dudot = p.udot2 - p.udot1; p.dthdot = p.thdot2 - p.thdot1;
+        p.dQ = get_dQ(p.th, p.dth, p.Q);
+        M3<T> Wt = tilde(p.Om - p.wb);
+        p.gamdot = -(CtCabT * (Wt * p.du)) + CtCabT * p.dudot - p.L * (CtCabT * (Wt * (p.Cab * e1)));
+        M3<T> CabT = tr(p.Cab);
+        p.kapdot = CabT * (p.Q * p.dthdot) + CabT * (p.dQ * p.thedot);
+        p.gam = p.gam - p.mu11 * p.gamdot;
+        p.kap = p.kap - p.mu22 * p.kapdot;
+    }
+    return p;
+}
+// element.jl:649-840
+template <class T> void steady_element_jacobian_properties(const Problem& P, int64_t ie, DynElem<T>& p) {
+    static_element_jacobian_properties(P, ie, p);
+    V3<T> e1 = unit<T>(0);
+    M3<T> Q_t1, Q_t2, Q_t3;
+    get_Q_th(p.Q, p.th, Q_t1, Q_t2, Q_t3);
+    M3<T> Ct1 = tr(p.C_t1), Ct2 = tr(p.C_t2), Ct3 = tr(p.C_t3), CtCabT = tr(p.CtCab), CabT = tr(p.Cab);
+    auto m3c = [&](const V3<T>& w) { return mul3(p.C_t1, p.C_t2, p.C_t3, w); };
+    auto m3t = [&](const V3<T>& w) { return mul3(Ct1, Ct2, Ct3, w); };
+    p.P_th = m3t(p.Cab * (p.mass11 * (CtCabT * p.V) + p.mass12 * (CtCabT * p.Om))) + p.CtCab * (p.mass11 * (CabT * m3c(p.V))) +
+             p.CtCab * (p.mass12 * (CabT * m3c(p.Om)));
+    p.P_V = p.CtCab * p.mass11 * CtCabT; p.P_Om = p.CtCab * p.mass12 * CtCabT;
+    p.H_th = m3t(p.Cab * (p.mass21 * (CtCabT * p.V) + p.mass22 * (CtCabT * p.Om))) + p.CtCab * (p.mass21 * (CabT * m3c(p.V))) +
+             p.CtCab * (p.mass22 * (CabT * m3c(p.Om)));
+    p.H_V = p.CtCab * p.mass21 * CtCabT; p.H_Om = p.CtCab * p.mass22 * CtCabT;
+    M3<T> Vdot_alb = -tilde(p.dx + p.u), Vdot_u = tilde(p.alb);
+    M3<T> Pdot_Vdot = p.P_V, Pdot_Omdot = p.P_Om, Hdot_Vdot = p.H_V, Hdot_Omdot = p.H_Om;
+    p.Pdot_ab = Pdot_Vdot; p.Pdot_alb = Pdot_Vdot * Vdot_alb + Pdot_Omdot;
+    p.Hdot_ab = Hdot_Vdot; p.Hdot_alb = Hdot_Vdot * Vdot_alb + Hdot_Omdot;
+    p.Pdot_u = Pdot_Vdot * Vdot_u; p.Hdot_u = Hdot_Vdot * Vdot_u;
+    p.Pdot_th = m3t(p.Cab * (p.mass11 * (CtCabT * p.Vdot))) + m3t(p.Cab * (p.mass12 * (CtCabT * p.Omdot))) + p.CtCab * (p.mass11 * (CabT * m3c(p.Vdot))) +
+                p.CtCab * (p.mass12 * (CabT * m3c(p.Omdot)));
+    p.Hdot_th = m3t(p.Cab * (p.mass21 * (CtCabT * p.Vdot))) + m3t(p.Cab * (p.mass22 * (CtCabT * p.Omdot))) + p.CtCab * (p.mass21 * (CabT * m3c(p.Vdot))) +
+                p.CtCab * (p.mass22 * (CabT * m3c(p.Omdot)));
+    p.Pdot_V = zero33<T>(); p.Pdot_Om = zero33<T>(); p.Hdot_V = zero33<T>(); p.Hdot_Om = zero33<T>();
+    M3<T> Z = zero33<T>();
+    p.gam_u1 = p.gam_u2 = p.gam_th1 = p.gam_th2 = p.gam_V1 = p.gam_V2 = p.gam_Om1 = p.gam_Om2 = Z;
+    p.kap_th1 = p.kap_th2 = p.kap_Om1 = p.kap_Om2 = Z;
+    if (p.damping) {
+        M3<T> I = eye3<T>();
+        M3<T> C1_1, C1_2, C1_3, C2_1, C2_2, C2_3, Qi1_1, Qi1_2, Qi1_3, Qi2_1, Qi2_2, Qi2_3;
+        get_C_th(p.C1, p.th1, C1_1, C1_2, C1_3); get_C_th(p.C2, p.th2, C2_1, C2_2, C2_3);
+        get_Qinv_th(p.th1, Qi1_1, Qi1_2, Qi1_3); get_Qinv_th(p.th2, Qi2_1, Qi2_2, Qi2_3);
+        M3<T> udot1_u1 = -tilde(p.wb), udot2_u2 = -tilde(p.wb), udot1_V1 = I, udot2_V2 = I;
+        M3<T> thdot1_th1 = mul3(Qi1_1, Qi1_2, Qi1_3, p.C1 * (p.Om1 - p.wb)) + p.Qinv1 * mul3(C1_1, C1_2, C1_3, p.Om1 - p.wb);
+        M3<T> thdot2_th2 = mul3(Qi2_1, Qi2_2, Qi2_3, p.C2 * (p.Om2 - p.wb)) + p.Qinv2 * mul3(C2_1, C2_2, C2_3, p.Om2 - p.wb);
+        M3<T> thdot1_Om1 = p.Qinv1 * p.C1, thdot2_Om2 = p.Qinv2 * p.C2;
+        M3<T> thdot_th1 = thdot1_th1 / T(2), thdot_th2 = thdot2_th2 / T(2), thdot_Om1 = thdot1_Om1 / T(2), thdot_Om2 = thdot2_Om2 / T(2);
+        M3<T> du_u1 = -I, du_u2 = I, dth_th1 = -I, dth_th2 = I;
+        M3<T> dudot_u1 = -udot1_u1, dudot_u2 = udot2_u2, dudot_V1 = -udot1_V1, dudot_V2 = udot2_V2;
+        M3<T> dthdot_th1 = -thdot1_th1, dthdot_th2 = thdot2_th2, dthdot_Om1 = -thdot1_Om1, dthdot_Om2 = thdot2_Om2;
+        M3<T> dQ_t1, dQ_t2, dQ_t3;
+        get_dQ_th(p.th, p.dth, p.Q, Q_t1, Q_t2, Q_t3, dQ_t1, dQ_t2, dQ_t3);
+        M3<T> dQ_d1 = mul3(Q_t1, Q_t2, Q_t3, unit<T>(0)), dQ_d2 = mul3(Q_t1, Q_t2, Q_t3, unit<T>(1)), dQ_d3 = mul3(Q_t1, Q_t2, Q_t3, unit<T>(2));
+        M3<T> Wt = tilde(p.Om - p.wb);
+        M3<T> tmp = CtCabT * Wt;
+        M3<T> gamdot_u1 = -(tmp * du_u1) + CtCabT * dudot_u1;
+        M3<T> gamdot_u2 = -(tmp * du_u2) + CtCabT * dudot_u2;
+        tmp = -(CabT * m3c(Wt * p.du)) + CabT * m3c(p.dudot) - p.L * (CabT * m3c(Wt * (p.Cab * e1)));
+        M3<T> gamdot_th1 = T(0.5) * tmp, gamdot_th2 = T(0.5) * tmp;
+        M3<T> gamdot_V1 = CtCabT * dudot_V1, gamdot_V2 = CtCabT * dudot_V2;
+        tmp = CtCabT * tilde(p.du) + p.L * (CtCabT * tilde(p.Cab * e1));
+        M3<T> gamdot_Om1 = T(0.5) * tmp, gamdot_Om2 = T(0.5) * tmp;
+        M3<T> tmp1 = CabT * mul3(Q_t1, Q_t2, Q_t3, p.dthdot);
+        M3<T> tmp2 = CabT * mul3(dQ_t1, dQ_t2, dQ_t3, p.thedot);
+        M3<T> tmp3 = CabT * mul3(dQ_d1, dQ_d2, dQ_d3, p.thedot);
+        M3<T> CQ = CabT * p.Q, CdQ = CabT * p.dQ;
+        M3<T> kapdot_th1 = T(0.5) * tmp1 + T(0.5) * tmp2 + tmp3 * dth_th1 + CQ * dthdot_th1 + CdQ * thdot_th1;
+        M3<T> kapdot_th2 = T(0.5) * tmp1 + T(0.5) * tmp2 + tmp3 * dth_th2 + CQ * dthdot_th2 + CdQ * thdot_th2;
+        M3<T> kapdot_Om1 = CQ * dthdot_Om1 + CdQ * thdot_Om1;
+        M3<T> kapdot_Om2 = CQ * dthdot_Om2 + CdQ * thdot_Om2;
+        p.gam_u1 = -(p.mu11 * gamdot_u1); p.gam_u2 = -(p.mu11 * gamdot_u2);
+        p.gam_th1 = -(p.mu11 * gamdot_th1); p.gam_th2 = -(p.mu11 * gamdot_th2);
+        p.gam_V1 = -(p.mu11 * gamdot_V1); p.gam_V2 = -(p.mu11 * gamdot_V2);
+        p.gam_Om1 = -(p.mu11 * gamdot_Om1); p.gam_Om2 = -(p.mu11 * gamdot_Om2);
+        p.kap_th1 = -(p.mu22 * kapdot_th1); p.kap_th2 = -(p.mu22 * kapdot_th2);
+        p.kap_Om1 = -(p.mu22 * kapdot_Om1); p.kap_Om2 = -(p.mu22 * kapdot_Om2);
+    }
+}
+template <class T> struct DynCompatJac : CompatJac<T> { M3<T> ru_V1, ru_V2, ru_Om1, ru_Om2, rth_Om1, rth_Om2; };
+// element.jl:1550-1578
+template <class T> DynCompatJac<T> dynamic_compatibility_jacobians(const DynElem<T>& p) {
+    DynCompatJac<T> c;
+    static_cast<CompatJac<T>&>(c) = static_compatibility_jacobians(p);
+    M3<T> QC = p.Qinv * p.Cab;
+    c.ru_u1 = c.ru_u1 - p.CtCab * p.gam_u1; c.ru_u2 = c.ru_u2 - p.CtCab * p.gam_u2;
+    c.ru_th1 = c.ru_th1 - p.CtCab * p.gam_th1; c.ru_th2 = c.ru_th2 - p.CtCab * p.gam_th2;
+    c.ru_V1 = -(p.CtCab * p.gam_V1); c.ru_V2 = -(p.CtCab * p.gam_V2);
+    c.ru_Om1 = -(p.CtCab * p.gam_Om1); c.ru_Om2 = -(p.CtCab * p.gam_Om2);
+    c.rth_th1 = c.rth_th1 - QC * p.kap_th1; c.rth_th2 = c.rth_th2 - QC * p.kap_th2;
+    c.rth_Om1 = -(QC * p.kap_Om1); c.rth_Om2 = -(QC * p.kap_Om2);
+    return c;
+}
+// element.jl:1901-1919
+template <class T> Resultants<T> dynamic_element_resultants(const Problem& P, const DynElem<T>& p, int64_t ie) {
+    Resultants<T> r = static_element_resultants(P, p, ie);
+    V3<T> tmp = cross(p.wb, p.Pm) + p.Pdot;
+    r.F1 = r.F1 - T(0.5) * tmp; r.F2 = r.F2 + T(0.5) * tmp;
+    tmp = cross(p.wb, p.H) + cross(p.V, p.Pm) + p.Hdot;
+    r.M1 = r.M1 - T(0.5) * tmp; r.M2 = r.M2 + T(0.5) * tmp;
+    return r;
+}
+template <class T> struct DynResultantJac : ResultantJac<T> {
+    M3<T> F1_u1, F1_u2, F1_V1, F1_V2, F1_Om1, F1_Om2, F2_u1, F2_u2, F2_V1, F2_V2, F2_Om1, F2_Om2;
+    M3<T> M1_u1, M1_u2, M1_V1, M1_V2, M1_Om1, M1_Om2, M2_u1, M2_u2, M2_V1, M2_V2, M2_Om1, M2_Om2;
+    M3<T> F1_ab, F1_alb, F2_ab, F2_alb, M1_ab, M1_alb, M2_ab, M2_alb;
+};
+// element.jl:2219-2328, 2035-2064
+template <class T> DynResultantJac<T> steady_element_resultant_jacobians(const Problem& P, const DynElem<T>& p, int64_t ie) {
+    DynResultantJac<T> r;
+    static_cast<ResultantJac<T>&>(r) = static_element_resultant_jacobians(P, p, ie);
+    M3<T> wt = tilde(p.wb), Vt = tilde(p.V);
+    M3<T> tmp = T(0.5) * (p.CtCab * tilde(p.F));
+    r.M1_u1 = -(tmp * p.gam_u1); r.M2_u1 = tmp * p.gam_u1;
+    r.M1_u2 = -(tmp * p.gam_u2); r.M2_u2 = tmp * p.gam_u2;
+    r.M1_th1 = r.M1_th1 - tmp * p.gam_th1; r.M2_th1 = r.M2_th1 + tmp * p.gam_th1;
+    r.M1_th2 = r.M1_th2 - tmp * p.gam_th2; r.M2_th2 = r.M2_th2 + tmp * p.gam_th2;
+    r.M1_V1 = -(tmp * p.gam_V1); r.M2_V1 = tmp * p.gam_V1;
+    r.M1_V2 = -(tmp * p.gam_V2); r.M2_V2 = tmp * p.gam_V2;
+    r.M1_Om1 = -(tmp * p.gam_Om1); r.M2_Om1 = tmp * p.gam_Om1;
+    r.M1_Om2 = -(tmp * p.gam_Om2); r.M2_Om2 = tmp * p.gam_Om2;
+    T h = T(0.5);
+    tmp = h * p.Pdot_u;
+    r.F1_u1 = -(h * tmp); r.F2_u1 = h * tmp; r.F1_u2 = -(h * tmp); r.F2_u2 = h * tmp;
+    tmp = h * (wt * p.P_th + p.Pdot_th);
+    r.F1_th1 = r.F1_th1 - h * tmp; r.F2_th1 = r.F2_th1 + h * tmp; r.F1_th2 = r.F1_th2 - h * tmp; r.F2_th2 = r.F2_th2 + h * tmp;
+    tmp = h * (wt * p.P_V + p.Pdot_V);
+    r.F1_V1 = -(h * tmp); r.F2_V1 = h * tmp; r.F1_V2 = -(h * tmp); r.F2_V2 = h * tmp;
+    tmp = h * (wt * p.P_Om + p.Pdot_Om);
+    r.F1_Om1 = -(h * tmp); r.F2_Om1 = h * tmp; r.F1_Om2 = -(h * tmp); r.F2_Om2 = h * tmp;
+    tmp = h * p.Hdot_u;
+    r.M1_u1 = r.M1_u1 - h * tmp; r.M2_u1 = r.M2_u1 + h * tmp; r.M1_u2 = r.M1_u2 - h * tmp; r.M2_u2 = r.M2_u2 + h * tmp;
+    tmp = h * (wt * p.H_th + Vt * p.P_th + p.Hdot_th);
+    r.M1_th1 = r.M1_th1 - h * tmp; r.M2_th1 = r.M2_th1 + h * tmp; r.M1_th2 = r.M1_th2 - h * tmp; r.M2_th2 = r.M2_th2 + h * tmp;
+    tmp = h * (wt * p.H_V + Vt * p.P_V - tilde(p.Pm) + p.Hdot_V);
+    r.M1_V1 = r.M1_V1 - h * tmp; r.M2_V1 = r.M2_V1 + h * tmp; r.M1_V2 = r.M1_V2 - h * tmp; r.M2_V2 = r.M2_V2 + h * tmp;
+    tmp = h * (wt * p.H_Om + Vt * p.P_Om + p.Hdot_Om);
+    r.M1_Om1 = r.M1_Om1 - h * tmp; r.M2_Om1 = r.M2_Om1 + h * tmp; r.M1_Om2 = r.M1_Om2 - h * tmp; r.M2_Om2 = r.M2_Om2 + h * tmp;
+    // steady: prescribed / state body accelerations
+    tmp = h * p.Pdot_ab; r.F1_ab = -tmp; r.F2_ab = tmp;
+    tmp = h * p.Pdot_alb; r.F1_alb = -tmp; r.F2_alb = tmp;
+    tmp = h * p.Hdot_ab; r.M1_ab = -tmp; r.M2_ab = tmp;
+    tmp = h * p.Hdot_alb; r.M1_alb = -tmp; r.M2_alb = tmp;
+    return r;
+}
+// element.jl:3019-3035
+template <class T> void steady_element_residual(const Problem& P, const Indices& idx, const T* x, int64_t ie, const DynParams& D, const V3<T>& ab,
+                                                const V3<T>& alb, T* resid) {
+    DynElem<T> p = steady_element_properties(P, idx, x, ie, D, ab, alb);
+    V3<T> ru, rth;
+    compatibility_residuals(p, ru, rth);
+    Resultants<T> r = dynamic_element_resultants(P, p, ie);
+    insert_element_residuals(P, idx, ie, ru, rth, r, resid);
+}
+// element.jl:3209-3229, 2685-2759, 2554-2583
+template <class T, class J> void steady_element_jacobian(const Problem& P, const Indices& idx, const T* x, int64_t ie, const DynParams& D,
+                                                         const V3<T>& ab, const V3<T>& alb, J& jac) {
+    DynElem<T> p = steady_element_properties(P, idx, x, ie, D, ab, alb);
+    steady_element_jacobian_properties(P, ie, p);
+    DynCompatJac<T> c = dynamic_compatibility_jacobians(p);
+    DynResultantJac<T> r = steady_element_resultant_jacobians(P, p, ie);
+    insert_static_element_jacobians(P, idx, ie, p, c, r, jac);
+    T fs = T(P.force_scaling);
+    int64_t icol1 = idx.icol_point[P.start[ie] - 1] - 1, icol2 = idx.icol_point[P.stop[ie] - 1] - 1;
+    int64_t irow = idx.irow_elem[ie] - 1;
+    set33(jac, irow, icol1 + 6, c.ru_V1); set33(jac, irow, icol1 + 9, c.ru_Om1);
+    set33(jac, irow, icol2 + 6, c.ru_V2); set33(jac, irow, icol2 + 9, c.ru_Om2);
+    set33(jac, irow + 3, icol1 + 9, c.rth_Om1); set33(jac, irow + 3, icol2 + 9, c.rth_Om2);
+    int64_t irow1 = idx.irow_point[P.start[ie] - 1] - 1;
+    sub33m(jac, irow1, icol1, (r.F1_u1 * p.u1_u1) / fs); sub33m(jac, irow1, icol2, (r.F1_u2 * p.u2_u2) / fs);
+    sub33m(jac, irow1, icol1 + 6, r.F1_V1 / fs); sub33m(jac, irow1, icol1 + 9, r.F1_Om1 / fs);
+    sub33m(jac, irow1, icol2 + 6, r.F1_V2 / fs); sub33m(jac, irow1, icol2 + 9, r.F1_Om2 / fs);
+    sub33m(jac, irow1 + 3, icol1, (r.M1_u1 * p.u1_u1) / fs); sub33m(jac, irow1 + 3, icol2, (r.M1_u2 * p.u2_u2) / fs);
+    sub33m(jac, irow1 + 3, icol1 + 6, r.M1_V1 / fs); sub33m(jac, irow1 + 3, icol1 + 9, r.M1_Om1 / fs);
+    sub33m(jac, irow1 + 3, icol2 + 6, r.M1_V2 / fs); sub33m(jac, irow1 + 3, icol2 + 9, r.M1_Om2 / fs);
+    int64_t irow2 = idx.irow_point[P.stop[ie] - 1] - 1;
+    add33(jac, irow2, icol1, (r.F2_u1 * p.u1_u1) / fs); add33(jac, irow2, icol2, (r.F2_u2 * p.u2_u2) / fs);
+    add33(jac, irow2, icol1 + 6, r.F2_V1 / fs); add33(jac, irow2, icol1 + 9, r.F2_Om1 / fs);
+    add33(jac, irow2, icol2 + 6, r.F2_V2 / fs); add33(jac, irow2, icol2 + 9, r.F2_Om2 / fs);
+    add33(jac, irow2 + 3, icol1, (r.M2_u1 * p.u1_u1) / fs); add33(jac, irow2 + 3, icol2, (r.M2_u2 * p.u2_u2) / fs);
+    add33(jac, irow2 + 3, icol1 + 6, r.M2_V1 / fs); add33(jac, irow2 + 3, icol1 + 9, r.M2_Om1 / fs);
+    add33(jac, irow2 + 3, icol2 + 6, r.M2_V2 / fs); add33(jac, irow2 + 3, icol2 + 9, r.M2_Om2 / fs);
+    for (int i = 0; i < 3; i++) {
+        if (idx.icol_body[i]) {
+            int64_t cb = idx.icol_body[i] - 1;
+            addcol3(jac, irow1, cb, (-col(r.F1_ab, i)) / fs); addcol3(jac, irow1 + 3, cb, (-col(r.M1_ab, i)) / fs);
+            addcol3(jac, irow2, cb, col(r.F2_ab, i) / fs); addcol3(jac, irow2 + 3, cb, col(r.M2_ab, i) / fs);
+        }
+        if (idx.icol_body[3 + i]) {
+            int64_t cb = idx.icol_body[3 + i] - 1;
+            addcol3(jac, irow1, cb, (-col(r.F1_alb, i)) / fs); addcol3(jac, irow1 + 3, cb, (-col(r.M1_alb, i)) / fs);
+            addcol3(jac, irow2, cb, col(r.F2_alb, i) / fs); addcol3(jac, irow2 + 3, cb, col(r.M2_alb, i) / fs);
+        }
+    }
+}
+
+// system.jl:427-455
+template <class T> void steady_system_residual(const Problem& P, const Indices& idx, const DynParams& D, const T* x, T* resid) {
+    V3<T> ab, alb;
+    body_accelerations(idx, x, D, ab, alb);
+    for (int64_t ip = 0; ip < P.np; ip++) steady_point_residual(P, idx, x, ip, D, ab, alb, resid);
+    for (int64_t ie = 0; ie < P.ne; ie++) steady_element_residual(P, idx, x, ie, D, ab, alb, resid);
+    if (P.two_dimensional) two_dimensional_residual(idx.nstates, x, resid);
+}
+// system.jl:693-720
+template <class T, class J> void steady_system_jacobian(const Problem& P, const Indices& idx, const DynParams& D, const T* x, J& jac) {
+    jac.zero();
+    V3<T> ab, alb;
+    body_accelerations(idx, x, D, ab, alb);
+    for (int64_t ip = 0; ip < P.np; ip++) steady_point_jacobian(P, idx, x, ip, D, ab, alb, jac);
+    for (int64_t ie = 0; ie < P.ne; ie++) steady_element_jacobian(P, idx, x, ie, D, ab, alb, jac);
+    if (P.two_dimensional) two_dimensional_jacobian<T>(idx.nstates, jac);
+}
+
+}  // namespace gxo

@@ -7,6 +7,7 @@
 #include <thread>
 #include "gxb_math.hpp"
 #include "gxb_static.hpp"
+#include "gxb_dynamic.hpp"
 #include "gxb_solve.hpp"
 
 using namespace gxo;
@@ -29,6 +30,11 @@ struct gxo_problem {
     double gravity[3];
     double force_scaling;
     int32_t two_dimensional;
+};
+
+struct gxo_dyn {       // mirrors gxo::DynParams
+    double vb[3], wb[3], ab[3], alb[3];
+    int32_t structural_damping;
 };
 
 struct gxo_opts {
@@ -216,5 +222,124 @@ int gxo_static_solve_batch(int64_t nbatch, const gxo_problem* q0, const double* 
 }
 
 int gxo_num_threads() { int n = (int)std::thread::hardware_concurrency(); return n > 0 ? n : 1; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- steady state (DynamicSystem) ----
+static DynParams to_dyn(const gxo_dyn* d) {
+    DynParams D;
+    if (d) { for (int i = 0; i < 3; i++) { D.vb[i] = d->vb[i]; D.wb[i] = d->wb[i]; D.ab[i] = d->ab[i]; D.alb[i] = d->alb[i]; } D.structural_damping = d->structural_damping; }
+    return D;
+}
+static void dynamic_bandwidth(const Problem& P, const Indices& idx, int64_t& kl, int64_t& ku) {
+    kl = 0; ku = 0;
+    auto blk = [&](int64_t r0, int64_t nr, int64_t c0, int64_t nc) { kl = std::max(kl, (r0 + nr - 1) - c0); ku = std::max(ku, (c0 + nc - 1) - r0); };
+    for (int64_t ip = 0; ip < P.np; ip++) blk(idx.irow_point[ip], 12, idx.icol_point[ip], 12);
+    for (int64_t ie = 0; ie < P.ne; ie++) {
+        int64_t ic = idx.icol_elem[ie], ic1 = idx.icol_point[P.start[ie] - 1], ic2 = idx.icol_point[P.stop[ie] - 1];
+        int64_t ir = idx.irow_elem[ie], ir1 = idx.irow_point[P.start[ie] - 1], ir2 = idx.irow_point[P.stop[ie] - 1];
+        blk(ir, 6, ic1, 12); blk(ir, 6, ic2, 12); blk(ir, 6, ic, 6);
+        for (int64_t irp : {ir1, ir2}) { blk(irp, 6, ic1, 12); blk(irp, 6, ic2, 12); blk(irp, 6, ic, 6); }
+    }
+    for (int i = 0; i < 6; i++)
+        if (idx.icol_body[i]) for (int64_t ip = 0; ip < P.np; ip++) blk(idx.irow_point[ip], 6, idx.icol_body[i], 1);
+}
+
+extern "C" {
+
+int gxo_steady_residual(const gxo_problem* q, const gxo_dyn* d, const double* x, double* r) {
+    Problem P = to_problem(q); DynParams D = to_dyn(d);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    update_body_acceleration_indices(P, idx);
+    static_assert(sizeof(double) == 8, "");
+    steady_system_residual<double>(P, idx, D, x, r);
+    return 0;
+}
+int gxo_steady_jacobian(const gxo_problem* q, const gxo_dyn* d, const double* x, double* J, int complex_step) {
+    Problem P = to_problem(q); DynParams D = to_dyn(d);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    update_body_acceleration_indices(P, idx);
+    int64_t n = idx.nstates;
+    if (!complex_step) {
+        DenseMat<double> M{n, J};
+        steady_system_jacobian<double>(P, idx, D, x, M);
+        return 0;
+    }
+    const double h = 1e-30;
+    std::vector<cplx> xc(n), rc(n);
+    for (int64_t j = 0; j < n; j++) {
+        for (int64_t i = 0; i < n; i++) xc[i] = cplx(x[i], 0);
+        xc[j] += cplx(0, h);
+        for (int64_t i = 0; i < n; i++) rc[i] = cplx(0, 0);
+        steady_system_residual<cplx>(P, idx, D, xc.data(), rc.data());
+        for (int64_t i = 0; i < n; i++) J[i + n * j] = rc[i].imag() / h;
+    }
+    return 0;
+}
+int gxo_steady_bandwidth(const gxo_problem* q, int64_t* kl, int64_t* ku, int64_t* icol_body) {
+    Problem P = to_problem(q);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    update_body_acceleration_indices(P, idx);
+    dynamic_bandwidth(P, idx, *kl, *ku);
+    if (icol_body) for (int i = 0; i < 6; i++) icol_body[i] = idx.icol_body[i];
+    return 0;
+}
+static NewtonResult steady_solve_one(const Problem& P, const Indices& idx, const DynParams& D, int64_t kl, int64_t ku, const NewtonOpts& o,
+                                     const double* x0, double* x, double* F) {
+    int64_t n = idx.nstates;
+    BandMat J; J.init(n, kl, ku);
+    for (int64_t i = 0; i < n; i++) x[i] = x0 ? x0[i] : 0.0;
+    auto rf = [&](const double* xx, double* FF) { steady_system_residual<double>(P, idx, D, xx, FF); };
+    auto jf = [&](const double* xx, BandMat& JJ) { steady_system_jacobian<double>(P, idx, D, xx, JJ); };
+    return newton_solve(n, x, F, J, rf, jf, o);
+}
+// steady_state_analysis for one instance (analyses.jl:383-527 with a single time step)
+int gxo_steady_solve(const gxo_problem* q, const gxo_dyn* d, const gxo_opts* opts, const double* x0, double* x, double* resid, int64_t* stats,
+                     double* resid_inf) {
+    Problem P = to_problem(q); DynParams D = to_dyn(d);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    update_body_acceleration_indices(P, idx);
+    int64_t kl, ku; dynamic_bandwidth(P, idx, kl, ku);
+    NewtonResult r = steady_solve_one(P, idx, D, kl, ku, to_opts(opts), x0, x, resid);
+    stats[0] = r.converged; stats[1] = r.iters; stats[2] = r.f_calls; stats[3] = r.ls_backtracks;
+    *resid_inf = r.resid_inf;
+    return r.error;
+}
+// batched; dyn: nbatch records (vb, wb, ab, alb may differ per instance)
+int gxo_steady_solve_batch(int64_t nbatch, const gxo_problem* q0, const gxo_dyn* dyn, const double* gravity, const double* force_scaling,
+                           const gxo_opts* opts, const double* x0, double* x, int32_t* converged, int32_t* iters, double* resid_inf, int nthreads) {
+    Problem P0 = to_problem(q0);
+    Indices idx = system_indices(P0.ne, P0.start, P0.stop, false);
+    update_body_acceleration_indices(P0, idx);
+    int64_t kl, ku; dynamic_bandwidth(P0, idx, kl, ku);
+    int64_t n = idx.nstates;
+    NewtonOpts o = to_opts(opts);
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+      for (;;) {
+        int64_t b = next.fetch_add(1);
+        if (b >= nbatch) break;
+        Problem P = P0;
+        P.elems = P0.elems + b * P0.ne * 91;
+        P.points = P0.points + b * P0.np * 3;
+        P.bc = P0.bc + b * P0.np * 18;
+        P.dload = P0.dload ? P0.dload + b * P0.ne * 24 : nullptr;
+        P.pmass = P0.pmass ? P0.pmass + b * P0.np * 36 : nullptr;
+        if (gravity) for (int i = 0; i < 3; i++) P.gravity[i] = gravity[3 * b + i];
+        if (force_scaling) P.force_scaling = force_scaling[b];
+        DynParams D = to_dyn(dyn + b);
+        std::vector<double> F(n);
+        NewtonResult r = steady_solve_one(P, idx, D, kl, ku, o, x0 ? x0 + b * n : nullptr, x + b * n, F.data());
+        converged[b] = r.converged; iters[b] = (int32_t)r.iters; resid_inf[b] = r.resid_inf;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    return 0;
+}
 
 }  // extern "C"

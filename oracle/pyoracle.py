@@ -33,6 +33,15 @@ class Opts(C.Structure):
                 ("c1", C.c_double), ("rho_hi", C.c_double), ("rho_lo", C.c_double)]
 
 
+class Dyn(C.Structure):
+    _fields_ = [("vb", C.c_double * 3), ("wb", C.c_double * 3), ("ab", C.c_double * 3), ("alb", C.c_double * 3),
+                ("structural_damping", C.c_int32)]
+
+
+def make_dyn(vb=(0, 0, 0), wb=(0, 0, 0), ab=(0, 0, 0), alb=(0, 0, 0), structural_damping=False):
+    return Dyn((C.c_double * 3)(*vb), (C.c_double * 3)(*wb), (C.c_double * 3)(*ab), (C.c_double * 3)(*alb), int(structural_damping))
+
+
 def make_opts(linear=False, ftol=1e-9, iterations=1000, maxstep=1e6, c1=1e-4, rho_hi=0.5, rho_lo=0.1):
     return Opts(int(linear), ftol, iterations, maxstep, c1, rho_hi, rho_lo)
 
@@ -160,3 +169,56 @@ def static_solve_batch(pk0: Packed, nbatch, gravity=None, force_scaling=None, x0
 
 def num_threads():
     return lib().gxo_num_threads()
+
+
+# ---------------------------------------------------------------- steady state (DynamicSystem) ----
+def steady_residual(pk: Packed, dyn: Dyn, x):
+    x = np.ascontiguousarray(x, float)
+    r = np.zeros_like(x)
+    lib().gxo_steady_residual(C.byref(pk.c), C.byref(dyn), _p(x), _p(r))
+    return r
+
+
+def steady_jacobian(pk: Packed, dyn: Dyn, x, complex_step=False):
+    x = np.ascontiguousarray(x, float)
+    n = len(x)
+    J = np.zeros((n, n), order="F")
+    lib().gxo_steady_jacobian(C.byref(pk.c), C.byref(dyn), _p(x), _p(J), int(complex_step))
+    return J
+
+
+def steady_bandwidth(pk: Packed):
+    kl, ku = C.c_int64(0), C.c_int64(0)
+    icb = np.zeros(6, np.int64)
+    lib().gxo_steady_bandwidth(C.byref(pk.c), C.byref(kl), C.byref(ku), _p(icb))
+    return kl.value, ku.value, icb
+
+
+def steady_solve(pk: Packed, dyn: Dyn, x0=None, **kw):
+    n = nstates(pk, static=False)
+    x = np.zeros(n)
+    r = np.zeros(n)
+    stats = np.zeros(4, np.int64)
+    rinf = C.c_double(0)
+    o = make_opts(**kw)
+    x0a = None if x0 is None else np.ascontiguousarray(x0, float)
+    err = lib().gxo_steady_solve(C.byref(pk.c), C.byref(dyn), C.byref(o), _p(x0a), _p(x), _p(r), _p(stats), C.byref(rinf))
+    return dict(x=x, resid=r, converged=bool(stats[0]), iters=int(stats[1]), f_calls=int(stats[2]),
+                ls_backtracks=int(stats[3]), resid_inf=rinf.value, error=err)
+
+
+def steady_solve_batch(pk0: Packed, nbatch, dyns, gravity=None, force_scaling=None, x0=None, nthreads=0, **kw):
+    """dyns: list of Dyn (one per instance).  pk0's per-instance arrays (elems, points, bc, ...) hold the whole batch."""
+    n = nstates(pk0, static=False)
+    x = np.zeros((nbatch, n))
+    conv = np.zeros(nbatch, np.int32)
+    its = np.zeros(nbatch, np.int32)
+    rinf = np.zeros(nbatch)
+    o = make_opts(**kw)
+    arr = (Dyn * nbatch)(*dyns)
+    g = None if gravity is None else np.ascontiguousarray(gravity, float)
+    fs = None if force_scaling is None else np.ascontiguousarray(force_scaling, float)
+    x0a = None if x0 is None else np.ascontiguousarray(x0, float)
+    lib().gxo_steady_solve_batch(C.c_int64(nbatch), C.byref(pk0.c), arr, _p(g), _p(fs), C.byref(o), _p(x0a), _p(x), _p(conv),
+                                 _p(its), _p(rinf), int(nthreads))
+    return dict(x=x, converged=conv, iters=its, resid_inf=rinf)

@@ -154,3 +154,32 @@ def oracle_packed(case, b=0, two_dimensional=False):
     return O.Packed(case["start"], case["stop"], case["elems"][b], case["points"], case["pd"], case["pl"], case["bc"][b],
                     None if dl is None else dl[b], None if pm is None else pm[b], gravity=g, force_scaling=fs,
                     two_dimensional=two_dimensional)
+
+
+def jacobians_jl(seed=0, nelem=2):
+    """The exact system of test/jacobians.jl:98-150: L = 60, 2 elements, the test's own 6x6 stiffness and mass matrices, root with
+    `theta_y = 0, My = 0` (a DOF with pd & pl -> body-frame angular acceleration becomes a state, system.jl:138-150), tip point
+    mass, gravity; random draws (damping, point mass, gravity) from our own seeded generator with the test's magnitudes."""
+    rng = np.random.default_rng(seed)
+    L = 60.0
+    x = np.linspace(0, L, nelem + 1)
+    points = np.stack([x, 0 * x, 0 * x], 1)
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    stiff = np.array([[2.389e9, 1.524e6, 6.734e6, -3.382e7, -2.627e7, -4.736e8],
+                      [1.524e6, 4.334e8, -3.741e6, -2.935e5, 1.527e7, 3.835e5],
+                      [6.734e6, -3.741e6, 2.743e7, -4.592e5, -6.869e5, -4.742e6],
+                      [-3.382e7, -2.935e5, -4.592e5, 2.167e7, -6.279e5, 1.430e6],
+                      [-2.627e7, 1.527e7, -6.869e5, -6.279e5, 1.970e7, 1.209e7],
+                      [-4.736e8, 3.835e5, -4.742e6, 1.430e6, 1.209e7, 4.406e8]])
+    mass = np.array([[258.053, 0.0, 0.0, 0.0, 7.07839, -71.6871],
+                     [0.0, 258.053, 0.0, -7.07839, 0.0, 0.0],
+                     [0.0, 0.0, 258.053, 71.6871, 0.0, 0.0],
+                     [0.0, -7.07839, 71.6871, 48.59, 0.0, 0.0],
+                     [7.07839, 0.0, 0.0, 0.0, 2.172, 0.0],
+                     [-71.6871, 0.0, 0.0, 0.0, 0.0, 46.418]])
+    damping = [0.1 * rng.random(6)] * nelem
+    asm = Assembly(points, start, stop, stiffness=[stiff] * nelem, mass=[mass] * nelem, damping=damping)
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, My=0, theta_z=0)}
+    M = rng.random((6, 6))
+    pm = {nelem + 1: 1e3 * (np.triu(M) + np.triu(M, 1).T)}     # Symmetric(1e3*rand(6,6))
+    return _pack(asm, pcs, pm=pm, gravity=1e3 * rng.random(3))
