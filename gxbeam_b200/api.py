@@ -30,7 +30,7 @@ class GXBError(RuntimeError):
 class Opts(C.Structure):
     _fields_ = [("linear", C.c_int32), ("two_dimensional", C.c_int32), ("ftol", C.c_double), ("iterations", C.c_int64),
                 ("maxstep", C.c_double), ("c1", C.c_double), ("rho_hi", C.c_double), ("rho_lo", C.c_double),
-                ("profile", C.c_int32), ("reserved", C.c_int32)]
+                ("profile", C.c_int32), ("structural_damping", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -44,8 +44,8 @@ class Stats(C.Structure):
 
 EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "gxb_topology", "gxb_pattern", "gxb_set_batch",
            "gxb_set_elements", "gxb_set_points", "gxb_set_bc", "gxb_set_dloads", "gxb_set_pmass", "gxb_set_body",
-           "gxb_static_solve", "gxb_upload_x0", "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats",
-           "gxb_static_residual_jacobian", "gxb_static_newton_direction"]
+           "gxb_set_motion", "gxb_static_solve", "gxb_steady_solve", "gxb_steady_solve_resident", "gxb_upload_x0",
+           "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction"]
 
 _lib = None
 
@@ -74,8 +74,8 @@ def _f64(a):
 
 
 def make_opts(linear=False, two_dimensional=False, ftol=1e-9, iterations=1000, maxstep=1e6, c1=1e-4, rho_hi=0.5, rho_lo=0.1,
-              profile=False):
-    return Opts(int(linear), int(two_dimensional), ftol, iterations, maxstep, c1, rho_hi, rho_lo, int(profile), 0)
+              profile=False, structural_damping=False):
+    return Opts(int(linear), int(two_dimensional), ftol, iterations, maxstep, c1, rho_hi, rho_lo, int(profile), int(structural_damping))
 
 
 class Context:
@@ -117,7 +117,7 @@ class Context:
         ire, ice = np.zeros(ne, np.int64), np.zeros(ne, np.int64)
         self._ck(self.lib.gxb_topology(self.h, int(kind), C.c_int64(npnt), C.c_int64(ne), _ptr(start), _ptr(stop), _ptr(pd), _ptr(pl),
                                        C.byref(n), _ptr(irp), _ptr(ire), _ptr(icp), _ptr(ice)))
-        self.n, self.np, self.ne = n.value, npnt, ne
+        self.n, self.np, self.ne, self.kind = n.value, npnt, ne, int(kind)
         self.start, self.stop = start, stop
         self.indices = dict(nstates=n.value, irow_point=irp, irow_elem=ire, icol_point=icp, icol_elem=ice)
         return self.indices
@@ -140,7 +140,15 @@ class Context:
         self._ck(self.lib.gxb_set_elements(self.h, _ptr(e)))
 
     def set_points(self, xyz):
-        self._ck(self.lib.gxb_set_points(self.h, _ptr(_f64(xyz))))
+        x = _f64(xyz)
+        assert x.size == self.nbatch * self.np * 3, "points must be nbatch x np x 3"
+        self._ck(self.lib.gxb_set_points(self.h, _ptr(x)))
+
+    def set_motion(self, motion):
+        """nbatch x 12: linear_velocity, angular_velocity, linear_acceleration, angular_acceleration (kind=1)."""
+        m = _f64(motion)
+        assert m is None or m.size == self.nbatch * 12
+        self._ck(self.lib.gxb_set_motion(self.h, _ptr(m)))
 
     def set_bc(self, bc):
         b = _f64(bc)
@@ -175,15 +183,21 @@ class Context:
         its = out.get("iters") if out.get("iters") is not None else np.empty(nb, np.int32)
         rinf = out.get("resid_inf") if out.get("resid_inf") is not None else np.empty(nb)
         x0a = _f64(x0)
-        self._ck(self.lib.gxb_static_solve(self.h, C.byref(o), _ptr(x0a), _ptr(x), _ptr(conv), _ptr(its), _ptr(rinf)))
+        fn = self.lib.gxb_static_solve if self.kind == 0 else self.lib.gxb_steady_solve
+        self._ck(fn(self.h, C.byref(o), _ptr(x0a), _ptr(x), _ptr(conv), _ptr(its), _ptr(rinf)))
         return dict(x=x, converged=conv.astype(bool), iters=its, resid_inf=rinf)
+
+    steady_solve = static_solve   # same call shape; dispatches on the context's kind
 
     def upload_x0(self, x0=None):
         self._ck(self.lib.gxb_upload_x0(self.h, _ptr(_f64(x0))))
 
     def static_solve_resident(self, opts=None):
         o = opts or make_opts()
-        self._ck(self.lib.gxb_static_solve_resident(self.h, C.byref(o)))
+        fn = self.lib.gxb_static_solve_resident if self.kind == 0 else self.lib.gxb_steady_solve_resident
+        self._ck(fn(self.h, C.byref(o)))
+
+    steady_solve_resident = static_solve_resident
 
     def fetch(self):
         nb, n = self.nbatch, self.n
@@ -204,15 +218,19 @@ class Context:
         if want_jacobian:
             brow, _ = self.pattern()
             J = np.empty((self.nbatch, len(brow), 9))
-        self._ck(self.lib.gxb_static_residual_jacobian(self.h, C.byref(o), _ptr(x), _ptr(r), _ptr(J)))
+        self._ck(self.lib.gxb_residual_jacobian(self.h, C.byref(o), _ptr(x), _ptr(r), _ptr(J)))
         return r, J
+
+    residual_jacobian = static_residual_jacobian
 
     def static_newton_direction(self, x, opts=None):
         o = opts or make_opts()
         x = _f64(x).reshape(self.nbatch, self.n)
         p = np.empty_like(x)
-        self._ck(self.lib.gxb_static_newton_direction(self.h, C.byref(o), _ptr(x), _ptr(p)))
+        self._ck(self.lib.gxb_newton_direction(self.h, C.byref(o), _ptr(x), _ptr(p)))
         return p
+
+    newton_direction = static_newton_direction
 
 
 def blocks_to_dense(n, brow, bcol, Jblk):

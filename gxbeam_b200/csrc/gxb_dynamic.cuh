@@ -1,0 +1,447 @@
+// Fused steady-state residual + Jacobian assembly on a DynamicSystem (12 states per point: u/F, θ/M, V, Ω; 6 per element),
+// one thread per station (point i + element i of a chain), one CTA per instance.  Replaces
+//     steady_system_residual!  src/system.jl:427-455  -> steady_point_residual! (point.jl:2137), steady_element_residual! (element.jl:3019)
+//     steady_system_jacobian!  src/system.jl:693-720  -> steady_point_jacobian! (point.jl:2346), steady_element_jacobian! (element.jl:3209)
+// (properties element.jl:117-160, 649-710; resultants element.jl:1901-1919, 2219-2328; point.jl:630-672, 1438-1449, 1658-1666,
+//  1728-1739; inserts element.jl:2685-2759, point.jl:1907-1935, 1809-1826).
+//
+// Chain layout [p0(12) e0(6) p1(12) e1(6) ... pN(12)]; in 6-blocks station i owns blocks 3i (point equilibrium rows, columns
+// u/θ), 3i+1 (velocity rows rV, rΩ; columns V/Ω) and 3i+2 (element).  Block bandwidths are KLB = 3, KUB = 4, so a stored row
+// holds the 8 column blocks B-3 .. B+4 (48 doubles).
+//
+// Not implemented on the device yet (the host refuses them): structural damping, point masses on a DynamicSystem and
+// body-frame accelerations as state variables (a DOF with pd & pl).
+#pragma once
+#include "gxb_static.cuh"
+
+#define GXB_DROWW 48      // doubles per stored Jacobian row (dynamic): 8 blocks x 6
+#define GXB_DPARK 48      // first parking slot of a tile row (12 slots: the four column groups both neighbours add into)
+#define GXB_DTROW 60      // tile row: 48 slots + 12 parking
+#define GXB_DTILE 182     // tile stride per station: 3 rows x 60 + 2 pad
+
+struct DynArgs {
+    StaticArgs s;             // shared inputs (elemS incl. mass blocks, bcS, dlS, grav, fs, flags, x, r, Jrow = [b][n][48], status)
+    const double* exS;        // [b][3][N]    element midpoints Δx (Element.x)
+    const double* pxS;        // [b][3][N+1]  point coordinates Δx
+    const double* motion;     // [b][12]      vb, ωb, ab, αb
+    int chunk;                // stations per tile flush (shared-memory tile holds `chunk` stations)
+};
+
+GXD void dblk(double* t, int s, const m3& B) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { t[GXB_DTROW * i + s] = B.a[3 * i]; t[GXB_DTROW * i + s + 1] = B.a[3 * i + 1]; t[GXB_DTROW * i + s + 2] = B.a[3 * i + 2]; }
+}
+GXD m3 dget(const double* t, int s) { m3 B;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { B.a[3 * i] = t[GXB_DTROW * i + s]; B.a[3 * i + 1] = t[GXB_DTROW * i + s + 1]; B.a[3 * i + 2] = t[GXB_DTROW * i + s + 2]; }
+    return B; }
+GXD void dtile_clear(double* t) {
+#pragma unroll
+    for (int j = 0; j < 3 * GXB_DTROW; j += 2) *reinterpret_cast<double2*>(t + j) = make_double2(0.0, 0.0);
+}
+// stream rows of the tiles of stations [c0, c0+cnt) to rows rowof(st) + roff .. +2
+GXD void dtile_flush(const double* tiles, double* J, int c0, int cnt, int roff) {
+    for (int c = threadIdx.x; c < cnt * 72; c += blockDim.x) {           // 3 rows x 24 16-byte chunks per station
+        const int st = c / 72, q = c - 72 * st, row = q / 24, qq = q - 24 * row;
+        const double2 v = *reinterpret_cast<const double2*>(tiles + (size_t)st * GXB_DTILE + row * GXB_DTROW + 2 * qq);
+        *reinterpret_cast<double2*>(J + (size_t)(18 * (c0 + st) + roff + row) * GXB_DROWW + 2 * qq) = v;
+    }
+}
+GXD void dtile_planar(double* t, int first_row_in_slot, int diag_slot0) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int k = first_row_in_slot + i;
+        if (k >= 2 && k <= 4) {
+#pragma unroll
+            for (int c = 0; c < GXB_DROWW; c++) t[GXB_DTROW * i + c] = (c == diag_slot0 + k) ? 1.0 : 0.0;
+        }
+    }
+}
+GXD m3 mul3c(const Rot& R, v3 w) { return cols(R.C1 * w, R.C2 * w, R.C3 * w); }   // mul3(C_θ1, C_θ2, C_θ3, w)
+
+// One tile pass: every thread may deposit into the tile of station `i+1` (nb) before the barrier and into its own afterwards.
+// The CTA walks the instance in chunks of A.chunk stations; deposits happen when the target station is in the current chunk.
+#define GXB_PASS_BEGIN(c0)  for (int c0 = 0; c0 < NP; c0 += A.chunk) { const int cnt_ = min(A.chunk, NP - c0);
+#define GXB_PASS_END        }
+
+template <bool WANT_J>
+__device__ void steady_station(const DynArgs& A, int b, int i, double* smem) {
+    const StaticArgs& S = A.s;
+    const int N = S.N, NP = N + 1;
+    double* xch = smem;                                             // [blockDim][6]
+    double* tiles = smem + (size_t)blockDim.x * GXB_XCH;            // [chunk][GXB_DTILE]   (WANT_J only)
+    const double fs = S.fs[b];
+    const double rfs = 1.0 / fs;
+    const double* x = S.x + (size_t)b * S.n;
+    double* r = S.r + (size_t)b * S.n;
+    double* J = WANT_J ? S.Jrow + (size_t)b * S.n * GXB_DROWW : nullptr;
+    const bool has_elem = i < N;
+    const bool valid = i <= N;
+
+    v3 g = mk(0, 0, 0);
+    if (S.has_grav && S.grav) g = mk(S.grav[3 * b], S.grav[3 * b + 1], S.grav[3 * b + 2]);
+    const double* mo = A.motion + 12 * (size_t)b;
+    const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]), ab = mk(mo[6], mo[7], mo[8]), alb = mk(mo[9], mo[10], mo[11]);
+    const m3 wbt = tilde(wb);
+
+    // ---- point i (point.jl:630-672): displacements, loads, velocities ----
+    v3 u1 = mk(0, 0, 0), th1 = u1, Fp = u1, Mp = u1, V1 = u1, Om1 = u1, dxp = u1;
+    v3 mu1 = mk(1, 1, 1), mth1 = mu1;
+    unsigned fl1 = 0;
+    bool follower = false;
+    if (valid) {
+        fl1 = S.flags[i];
+        const double* bc = S.bcS + ((size_t)b * 18) * NP + i;
+        const double* xp = x + 18 * i;
+        u1 = mk((fl1 & 1) ? bc[0] : xp[0], (fl1 & 2) ? bc[NP] : xp[1], (fl1 & 4) ? bc[2 * NP] : xp[2]);
+        th1 = mk((fl1 & 8) ? bc[3 * NP] : xp[3], (fl1 & 16) ? bc[4 * NP] : xp[4], (fl1 & 32) ? bc[5 * NP] : xp[5]);
+        mu1 = mk((fl1 & 1) ? 0.0 : 1.0, (fl1 & 2) ? 0.0 : 1.0, (fl1 & 4) ? 0.0 : 1.0);
+        mth1 = mk((fl1 & 8) ? 0.0 : 1.0, (fl1 & 16) ? 0.0 : 1.0, (fl1 & 32) ? 0.0 : 1.0);
+        V1 = mk(xp[6], xp[7], xp[8]); Om1 = mk(xp[9], xp[10], xp[11]);
+        const double* px = A.pxS + ((size_t)b * 3) * NP + i;
+        dxp = ldv(px, NP);
+        v3 F = ldv(bc + 6 * NP, NP), M = ldv(bc + 9 * NP, NP), Ff = ldv(bc + 12 * NP, NP), Mf = ldv(bc + 15 * NP, NP);
+        follower = (Ff.x != 0.0) | (Ff.y != 0.0) | (Ff.z != 0.0) | (Mf.x != 0.0) | (Mf.y != 0.0) | (Mf.z != 0.0);
+        if (follower) { m3 C = rot_C(th1); F = F + tmul(C, Ff); M = M + tmul(C, Mf); }
+        Fp = mk((fl1 & 64) ? F.x : xp[0] * fs, (fl1 & 128) ? F.y : xp[1] * fs, (fl1 & 256) ? F.z : xp[2] * fs);
+        Mp = mk((fl1 & 512) ? M.x : xp[3] * fs, (fl1 & 1024) ? M.y : xp[4] * fs, (fl1 & 2048) ? M.z : xp[5] * fs);
+    }
+
+    // ---- element i core (element.jl:62-107, 117-160) ----
+    const double* es = S.elemS + ((size_t)b * S.elem_nf) * N + (has_elem ? i : 0);
+    double L = 0.0;
+    m3 Cab = zero33(), CtCab = zero33();
+    Rot R;
+    v3 th = mk(0, 0, 0), F = th, M = th, Le1g = th, kap = th, u2 = th, th2 = th, V = th, Om = th, Vdot = th, Pm = th, H = th;
+    v3 mth2 = mk(1, 1, 1), mu2 = mth2;
+    v3 ru = th, rth = th, F1 = th, M1 = th, F2 = th, M2 = th;
+    v3 f1f = th, f2f = th, m1f = th, m2f = th, CtCabTg = th;
+    if (has_elem) {
+        L = es[0];
+        Cab = ldm(es + N, N);
+        const unsigned fl2 = S.flags[i + 1];
+        const double* bc2 = S.bcS + ((size_t)b * 18) * NP + i + 1;
+        const double* xq = x + 18 * (i + 1);
+        u2 = mk((fl2 & 1) ? bc2[0] : xq[0], (fl2 & 2) ? bc2[NP] : xq[1], (fl2 & 4) ? bc2[2 * NP] : xq[2]);
+        th2 = mk((fl2 & 8) ? bc2[3 * NP] : xq[3], (fl2 & 16) ? bc2[4 * NP] : xq[4], (fl2 & 32) ? bc2[5 * NP] : xq[5]);
+        mu2 = mk((fl2 & 1) ? 0.0 : 1.0, (fl2 & 2) ? 0.0 : 1.0, (fl2 & 4) ? 0.0 : 1.0);
+        mth2 = mk((fl2 & 8) ? 0.0 : 1.0, (fl2 & 16) ? 0.0 : 1.0, (fl2 & 32) ? 0.0 : 1.0);
+        const v3 V2 = mk(xq[6], xq[7], xq[8]), Om2 = mk(xq[9], xq[10], xq[11]);
+        const double* xe = x + 18 * i + 12;
+        F = mk(xe[0] * fs, xe[1] * fs, xe[2] * fs); M = mk(xe[3] * fs, xe[4] * fs, xe[5] * fs);
+        th = 0.5 * (th1 + th2);
+        const v3 u = 0.5 * (u1 + u2);
+        V = 0.5 * (V1 + V2); Om = 0.5 * (Om1 + Om2);
+        if (WANT_J) rot_C_dC(th, R); else R.C = rot_C(th);
+        CtCab = tmul(R.C, Cab);
+        {
+            m3 S11 = ldm(es + 10 * N, N), S12 = ldm(es + 19 * N, N);
+            v3 gam = S11 * F + S12 * M;
+            Le1g = mk(L + gam.x, gam.y, gam.z);
+        }
+        {
+            m3 S21 = ldm(es + 28 * N, N), S22 = ldm(es + 37 * N, N);
+            kap = S21 * F + S22 * M;
+        }
+        v3 Cab1 = mk(Cab.a[0], Cab.a[3], Cab.a[6]);
+        ru = (u2 - u1) - (CtCab * Le1g - L * Cab1);
+        rth = (th2 - th1) - rot_Qinv_from_c(rot_scaling(th) * th) * (Cab * kap);
+        v3 CF = CtCab * F;
+        v3 t1 = CtCab * M, t2 = 0.5 * (CtCab * cross(Le1g, F));
+        F1 = CF; F2 = CF; M1 = t1 + t2; M2 = t1 - t2;
+        if (S.has_grav) {
+            CtCabTg = tmul(CtCab, g);
+            v3 tg = -(CtCab * (ldm(es + 46 * N, N) * CtCabTg));
+            F1 = F1 - 0.5 * tg; F2 = F2 + 0.5 * tg;
+            tg = -(CtCab * (ldm(es + 64 * N, N) * CtCabTg));
+            M1 = M1 - 0.5 * tg; M2 = M2 + 0.5 * tg;
+        }
+        if (S.dlS) {
+            const double* d = S.dlS + ((size_t)b * 24) * N + i;
+            f1f = ldv(d + 12 * N, N); f2f = ldv(d + 15 * N, N); m1f = ldv(d + 18 * N, N); m2f = ldv(d + 21 * N, N);
+            F1 = F1 + (ldv(d, N) + tmul(R.C, f1f));
+            F2 = F2 - (ldv(d + 3 * N, N) + tmul(R.C, f2f));
+            M1 = M1 + (ldv(d + 6 * N, N) + tmul(R.C, m1f));
+            M2 = M2 - (ldv(d + 9 * N, N) + tmul(R.C, m2f));
+        }
+        // inertial loads (element.jl:138-155, 1901-1919)
+        const v3 dxe = ldv(A.exS + ((size_t)b * 3) * N + i, N);
+        Vdot = ab + cross(alb, dxe + u);
+        {
+            const m3 m11 = ldm(es + 46 * N, N), m12 = ldm(es + 55 * N, N), m21 = ldm(es + 64 * N, N), m22 = ldm(es + 73 * N, N);
+            const v3 cV = tmul(CtCab, V), cO = tmul(CtCab, Om), cVd = tmul(CtCab, Vdot), cOd = tmul(CtCab, alb);
+            Pm = CtCab * (m11 * cV) + CtCab * (m12 * cO);
+            H = CtCab * (m21 * cV) + CtCab * (m22 * cO);
+            const v3 Pdot = CtCab * (m11 * cVd) + CtCab * (m12 * cOd);
+            const v3 Hdot = CtCab * (m21 * cVd) + CtCab * (m22 * cOd);
+            v3 tf = cross(wb, Pm) + Pdot;
+            F1 = F1 - 0.5 * tf; F2 = F2 + 0.5 * tf;
+            v3 tm = cross(wb, H) + cross(V, Pm) + Hdot;
+            M1 = M1 - 0.5 * tm; M2 = M2 + 0.5 * tm;
+        }
+        double* mine = xch + (size_t)threadIdx.x * GXB_XCH;
+        mine[0] = F2.x * rfs; mine[1] = F2.y * rfs; mine[2] = F2.z * rfs;
+        mine[3] = M2.x * rfs; mine[4] = M2.y * rfs; mine[5] = M2.z * rfs;
+    }
+    __syncthreads();
+
+    // ---- residual ----
+    m3 Cp = zero33(), Qp = zero33();       // C(θ_p), Qinv(θ_p) of the point (velocity rows)
+    if (valid) {
+        const double* prev = xch + (size_t)(i > 0 ? threadIdx.x - 1 : 0) * GXB_XCH;
+        double* rp = r + 18 * i;
+        double own[6] = {-Fp.x * rfs, -Fp.y * rfs, -Fp.z * rfs, -Mp.x * rfs, -Mp.y * rfs, -Mp.z * rfs};
+        double sub[6] = {F1.x * rfs, F1.y * rfs, F1.z * rfs, M1.x * rfs, M1.y * rfs, M1.z * rfs};
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            double v = own[k];
+            if (i > 0) v += prev[k];
+            if (has_elem) v -= sub[k];
+            if (S.two_d && k >= 2 && k <= 4) v = x[18 * i + k];
+            rp[k] = v;
+        }
+        // velocity rows (point.jl:1658-1666): rV = V - vb - ωb x (Δx + u),  rΩ = Qinv C (Ω - ωb)
+        Cp = rot_C(th1); Qp = rot_Qinv_from_c(rot_scaling(th1) * th1);
+        const v3 rV = V1 - vb - cross(wb, dxp) - cross(wb, u1);
+        const v3 rO = Qp * (Cp * (Om1 - wb));
+        double rv[6] = {rV.x, rV.y, rV.z, rO.x, rO.y, rO.z};
+#pragma unroll
+        for (int k = 0; k < 6; k++) rp[6 + k] = (S.two_d && k >= 2 && k <= 4) ? x[18 * i + 6 + k] : rv[k];
+        if (has_elem) {
+            double re[6] = {ru.x, ru.y, ru.z, rth.x, rth.y, rth.z};
+#pragma unroll
+            for (int k = 0; k < 6; k++) rp[12 + k] = (S.two_d && k >= 2 && k <= 4) ? x[18 * i + 12 + k] : re[k];
+        }
+    }
+    if (!WANT_J) return;
+
+    // ---- element Jacobian pieces shared by the two equilibrium passes (element.jl:649-710, 2219-2328) ----
+    // "h" quantities are the ½·½ inertial terms that enter BOTH end points with the same sign:
+    //   rows of the start point:  -= F1_x / fs = + hF_x / fs ;  rows of the stop point: += F2_x / fs = + hF_x / fs
+    m3 hFu, hFth, hFV, hFO, hMu, hMth, hMV, hMO;
+    if (has_elem) {
+        const m3 m11 = ldm(es + 46 * N, N), m12 = ldm(es + 55 * N, N), m21 = ldm(es + 64 * N, N), m22 = ldm(es + 73 * N, N);
+        const m3 CtCabT = transpose(CtCab);
+        const m3 A11 = (CtCab * m11) * CtCabT, A12 = (CtCab * m12) * CtCabT, A21 = (CtCab * m21) * CtCabT, A22 = (CtCab * m22) * CtCabT;
+        const v3 cV = tmul(CtCab, V), cO = tmul(CtCab, Om), cVd = tmul(CtCab, Vdot), cOd = tmul(CtCab, alb);
+        const m3 cthV = tmul(Cab, mul3c(R, V)), cthO = tmul(Cab, mul3c(R, Om)), cthVd = tmul(Cab, mul3c(R, Vdot)), cthOd = tmul(Cab, mul3c(R, alb));
+        const m3 P_th = mul3t(R, Cab * (m11 * cV + m12 * cO)) + CtCab * (m11 * cthV) + CtCab * (m12 * cthO);
+        const m3 H_th = mul3t(R, Cab * (m21 * cV + m22 * cO)) + CtCab * (m21 * cthV) + CtCab * (m22 * cthO);
+        const m3 Pd_th = mul3t(R, Cab * (m11 * cVd)) + mul3t(R, Cab * (m12 * cOd)) + CtCab * (m11 * cthVd) + CtCab * (m12 * cthOd);
+        const m3 Hd_th = mul3t(R, Cab * (m21 * cVd)) + mul3t(R, Cab * (m22 * cOd)) + CtCab * (m21 * cthVd) + CtCab * (m22 * cthOd);
+        const m3 albt = tilde(alb), Vt = tilde(V);
+        hFu = 0.25 * (A11 * albt);
+        hFth = 0.25 * (wbt * P_th + Pd_th);
+        hFV = 0.25 * (wbt * A11);
+        hFO = 0.25 * (wbt * A12);
+        hMu = 0.25 * (A21 * albt);
+        hMth = 0.25 * (wbt * H_th + Vt * P_th + Hd_th);
+        hMV = 0.25 * (wbt * A21 + Vt * A11 - tilde(Pm));
+        hMO = 0.25 * (wbt * A22 + Vt * A12);
+    }
+
+    // =================== pass P1: force rows of point i (rows 18i+0..2) ===================
+    m3 JFa = zero33(), JFb = zero33();
+    if (has_elem) {
+        m3 Fth = 0.5 * mul3t(R, Cab * F);
+        JFa = Fth; JFb = Fth;
+        if (S.has_grav) {
+            m3 m11 = ldm(es + 46 * N, N);
+            m3 Cthg = mul3c(R, g);
+            m3 tg = -0.5 * (mul3t(R, Cab * (m11 * CtCabTg)) + CtCab * (m11 * tmul(Cab, Cthg)));
+            JFa = JFa - 0.5 * tg; JFb = JFb + 0.5 * tg;
+        }
+        if (S.dlS) { JFa = JFa + 0.5 * mul3t(R, f1f); JFb = JFb - 0.5 * mul3t(R, f2f); }
+        JFa = JFa - hFth; JFb = JFb + hFth;
+    }
+    GXB_PASS_BEGIN(c0)
+        double* mytile = tiles + (size_t)(i - c0) * GXB_DTILE;
+        const bool mine_in = valid && i >= c0 && i < c0 + cnt_;
+        const bool next_in = has_elem && i + 1 >= c0 && i + 1 < c0 + cnt_;
+        if (mine_in) dtile_clear(mytile);
+        __syncthreads();
+        if (next_in) {      // rows of the stop point (station i+1): columns of point i (slots 0..11), of this element (12..17); shared groups parked
+            double* nt = tiles + (size_t)(i + 1 - c0) * GXB_DTILE;
+            dblk(nt, 0, rfs * colmask(hFu, mu1));
+            dblk(nt, 3, rfs * colmask(JFb, mth1));
+            dblk(nt, 6, rfs * hFV);
+            dblk(nt, 9, rfs * hFO);
+            dblk(nt, 12, CtCab);                                  // F2_F
+            dblk(nt, GXB_DPARK + 0, rfs * colmask(hFu, mu2));
+            dblk(nt, GXB_DPARK + 3, rfs * colmask(JFb, mth2));
+            dblk(nt, GXB_DPARK + 6, rfs * hFV);
+            dblk(nt, GXB_DPARK + 9, rfs * hFO);
+        }
+        __syncthreads();
+        if (mine_in) {
+            m3 own = zero33();
+            if (follower) {
+                Rot Rp; rot_C_dC(th1, Rp);
+                const double* bc = S.bcS + ((size_t)b * 18) * NP + i;
+                own = (-rfs) * colmask(rowmask(mul3t(Rp, ldv(bc + 12 * NP, NP)), fl1 & 64, fl1 & 128, fl1 & 256), mth1);
+            }
+            m3 FF = zero33();
+            FF.a[0] = (fl1 & 64) ? 0.0 : -1.0; FF.a[4] = (fl1 & 128) ? 0.0 : -1.0; FF.a[8] = (fl1 & 256) ? 0.0 : -1.0;
+            m3 bu = FF + dget(mytile, GXB_DPARK + 0), bt = own + dget(mytile, GXB_DPARK + 3);
+            m3 bV = dget(mytile, GXB_DPARK + 6), bO = dget(mytile, GXB_DPARK + 9);
+            if (has_elem) {
+                bu = bu + rfs * colmask(hFu, mu1);                // -= F1_u1 u1_u1 / fs
+                bt = bt - rfs * colmask(JFa, mth1);
+                bV = bV + rfs * hFV;
+                bO = bO + rfs * hFO;
+                dblk(mytile, 30, -CtCab);                         // -F1_F
+                dblk(mytile, 36, rfs * colmask(hFu, mu2));
+                dblk(mytile, 39, (-rfs) * colmask(JFa, mth2));
+                dblk(mytile, 42, rfs * hFV);
+                dblk(mytile, 45, rfs * hFO);
+            }
+            dblk(mytile, 18, bu); dblk(mytile, 21, bt); dblk(mytile, 24, bV); dblk(mytile, 27, bO);
+            if (S.two_d) dtile_planar(mytile, 0, 18);
+        }
+        __syncthreads();
+        dtile_flush(tiles, J, c0, cnt_, 0);
+        __syncthreads();
+    GXB_PASS_END
+
+    // =================== pass P2: moment rows of point i (rows 18i+3..5) ===================
+    m3 JMa = zero33(), JMb = zero33(), M1F = zero33(), hM = zero33();
+    if (has_elem) {
+        m3 tm1 = mul3t(R, Cab * M);
+        m3 tm2 = 0.5 * mul3t(R, Cab * cross(Le1g, F));
+        JMa = 0.5 * (tm1 + tm2);
+        JMb = 0.5 * (tm1 - tm2);
+        if (S.has_grav) {
+            m3 m21 = ldm(es + 64 * N, N);
+            m3 Cthg = mul3c(R, g);
+            m3 tg = -0.5 * (mul3t(R, Cab * (m21 * CtCabTg)) + CtCab * (m21 * tmul(Cab, Cthg)));
+            JMa = JMa - 0.5 * tg; JMb = JMb + 0.5 * tg;
+        }
+        if (S.dlS) { JMa = JMa + 0.5 * mul3t(R, m1f); JMb = JMb - 0.5 * mul3t(R, m2f); }
+        JMa = JMa - hMth; JMb = JMb + hMth;
+        m3 CtF = CtCab * tilde(F);
+        M1F = 0.5 * (CtCab * tilde(Le1g) - CtF * ldm(es + 10 * N, N));
+        hM = 0.5 * (CtF * ldm(es + 19 * N, N));
+    }
+    GXB_PASS_BEGIN(c0)
+        double* mytile = tiles + (size_t)(i - c0) * GXB_DTILE;
+        const bool mine_in = valid && i >= c0 && i < c0 + cnt_;
+        const bool next_in = has_elem && i + 1 >= c0 && i + 1 < c0 + cnt_;
+        if (mine_in) dtile_clear(mytile);
+        __syncthreads();
+        if (next_in) {
+            double* nt = tiles + (size_t)(i + 1 - c0) * GXB_DTILE;
+            dblk(nt, 0, rfs * colmask(hMu, mu1));
+            dblk(nt, 3, rfs * colmask(JMb, mth1));
+            dblk(nt, 6, rfs * hMV);
+            dblk(nt, 9, rfs * hMO);
+            dblk(nt, 12, -M1F);                                   // M2_F
+            dblk(nt, 15, CtCab + hM);                             // M2_M
+            dblk(nt, GXB_DPARK + 0, rfs * colmask(hMu, mu2));
+            dblk(nt, GXB_DPARK + 3, rfs * colmask(JMb, mth2));
+            dblk(nt, GXB_DPARK + 6, rfs * hMV);
+            dblk(nt, GXB_DPARK + 9, rfs * hMO);
+        }
+        __syncthreads();
+        if (mine_in) {
+            m3 MM = zero33();
+            MM.a[0] = (fl1 & 512) ? 0.0 : -1.0; MM.a[4] = (fl1 & 1024) ? 0.0 : -1.0; MM.a[8] = (fl1 & 2048) ? 0.0 : -1.0;
+            m3 own = MM;
+            if (follower) {
+                Rot Rp; rot_C_dC(th1, Rp);
+                const double* bc = S.bcS + ((size_t)b * 18) * NP + i;
+                own = MM - rfs * colmask(rowmask(mul3t(Rp, ldv(bc + 15 * NP, NP)), fl1 & 512, fl1 & 1024, fl1 & 2048), mth1);
+            }
+            m3 bu = dget(mytile, GXB_DPARK + 0), bt = own + dget(mytile, GXB_DPARK + 3);
+            m3 bV = dget(mytile, GXB_DPARK + 6), bO = dget(mytile, GXB_DPARK + 9);
+            if (has_elem) {
+                bu = bu + rfs * colmask(hMu, mu1);
+                bt = bt - rfs * colmask(JMa, mth1);
+                bV = bV + rfs * hMV;
+                bO = bO + rfs * hMO;
+                dblk(mytile, 30, -M1F);                           // -M1_F
+                dblk(mytile, 33, hM - CtCab);                     // -M1_M
+                dblk(mytile, 36, rfs * colmask(hMu, mu2));
+                dblk(mytile, 39, (-rfs) * colmask(JMa, mth2));
+                dblk(mytile, 42, rfs * hMV);
+                dblk(mytile, 45, rfs * hMO);
+            }
+            dblk(mytile, 18, bu); dblk(mytile, 21, bt); dblk(mytile, 24, bV); dblk(mytile, 27, bO);
+            if (S.two_d) dtile_planar(mytile, 3, 18);
+        }
+        __syncthreads();
+        dtile_flush(tiles, J, c0, cnt_, 3);
+        __syncthreads();
+    GXB_PASS_END
+
+    // =================== passes V1/V2: velocity rows of point i (rows 18i+6..8, 18i+9..11; block 3i+1) ===================
+    // row block 3i+1 stores column blocks 3i-2 ..: point i u/θ at slots 12..17, V/Ω at 18..23   (point.jl:1728-1739, 1928-1932)
+    GXB_PASS_BEGIN(c0)
+        double* mytile = tiles + (size_t)(i - c0) * GXB_DTILE;
+        const bool mine_in = valid && i >= c0 && i < c0 + cnt_;
+        if (mine_in) {
+            dtile_clear(mytile);
+            dblk(mytile, 12, colmask(-wbt, mu1));                 // rV_u u_u = -tilde(ωb) u_u
+            dblk(mytile, 18, eye33());                            // rV_V
+            if (S.two_d) dtile_planar(mytile, 0, 18);
+        }
+        __syncthreads();
+        dtile_flush(tiles, J, c0, cnt_, 6);
+        __syncthreads();
+    GXB_PASS_END
+    GXB_PASS_BEGIN(c0)
+        double* mytile = tiles + (size_t)(i - c0) * GXB_DTILE;
+        const bool mine_in = valid && i >= c0 && i < c0 + cnt_;
+        if (mine_in) {
+            dtile_clear(mytile);
+            Rot Rp; rot_C_dC(th1, Rp);
+            const v3 dO = Om1 - wb;
+            m3 Qi;
+            m3 rOth = rot_Qinv_dQinv_b(th1, Rp.C * dO, Qi) + Qi * mul3c(Rp, dO);
+            dblk(mytile, 15, colmask(rOth, mth1));                // rΩ_θ θ_θ
+            dblk(mytile, 21, Qi * Rp.C);                          // rΩ_Ω = Qinv C
+            if (S.two_d) dtile_planar(mytile, 3, 18);
+        }
+        __syncthreads();
+        dtile_flush(tiles, J, c0, cnt_, 9);
+        __syncthreads();
+    GXB_PASS_END
+
+    // =================== passes E1/E2: compatibility rows of element i (rows 18i+12..14, 18i+15..17; block 3i+2) ===================
+    // row block 3i+2 stores column blocks 3i-1 ..: point i u/θ at slots 6..11, V/Ω 12..17, element 18..23, point i+1 u/θ 24..29
+    GXB_PASS_BEGIN(c0)
+        double* mytile = tiles + (size_t)(i - c0) * GXB_DTILE;
+        const bool mine_in = has_elem && i >= c0 && i < c0 + cnt_;
+        if (mine_in) {
+            dtile_clear(mytile);
+            m3 ruth = -0.5 * mul3t(R, Cab * Le1g);
+            dblk(mytile, 6, colmask(-eye33(), mu1));
+            dblk(mytile, 9, colmask(ruth, mth1));
+            dblk(mytile, 18, (-fs) * (CtCab * ldm(es + 10 * N, N)));
+            dblk(mytile, 21, (-fs) * (CtCab * ldm(es + 19 * N, N)));
+            dblk(mytile, 24, colmask(eye33(), mu2));
+            dblk(mytile, 27, colmask(ruth, mth2));
+            if (S.two_d) dtile_planar(mytile, 0, 18);
+        }
+        __syncthreads();
+        dtile_flush(tiles, J, c0, min(cnt_, N - c0), 12);
+        __syncthreads();
+    GXB_PASS_END
+    GXB_PASS_BEGIN(c0)
+        double* mytile = tiles + (size_t)(i - c0) * GXB_DTILE;
+        const bool mine_in = has_elem && i >= c0 && i < c0 + cnt_;
+        if (mine_in) {
+            dtile_clear(mytile);
+            m3 Qinv;
+            m3 hd = -0.5 * rot_Qinv_dQinv_b(th, Cab * kap, Qinv);
+            m3 QC = Qinv * Cab;
+            dblk(mytile, 9, colmask(hd - eye33(), mth1));
+            dblk(mytile, 18, (-fs) * (QC * ldm(es + 28 * N, N)));
+            dblk(mytile, 21, (-fs) * (QC * ldm(es + 37 * N, N)));
+            dblk(mytile, 27, colmask(hd + eye33(), mth2));
+            if (S.two_d) dtile_planar(mytile, 3, 18);
+        }
+        __syncthreads();
+        dtile_flush(tiles, J, c0, min(cnt_, N - c0), 15);
+        __syncthreads();
+    GXB_PASS_END
+}

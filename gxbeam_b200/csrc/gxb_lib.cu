@@ -25,6 +25,7 @@
 #endif
 #include "gxb_lu.cuh"
 #include "gxb_static.cuh"
+#include "gxb_dynamic.cuh"
 
 // ------------------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -61,6 +62,9 @@ struct gxb_ctx {
     // batch
     int64_t nbatch = 0;
     double *d_elemS = nullptr, *d_bcS = nullptr, *d_dlS = nullptr, *d_pmS = nullptr, *d_grav = nullptr, *d_fs = nullptr, *d_xyz = nullptr;
+    double *d_exS = nullptr, *d_motion = nullptr;     // dynamic only: element midpoints [b][3][N], body motion [b][12]
+    bool body_state = false;                          // some DOF has pd & pl (body-frame acceleration would be a state)
+    int W = 30, UW = 32, KLB = 2, rows_per_station = 12;
     int has_grav = 0;
     double* d_stage = nullptr; size_t stage_bytes = 0;
     // solver state
@@ -76,7 +80,7 @@ struct gxb_ctx {
 // packing kernels: caller's array-of-structs (the reference's memory layout) -> structure-of-arrays in HBM
 // elemS[b][f][e]: f=0 L; 1..9 Cab (row-major); 10..45 S11,S12,S21,S22 = L*compliance; 46..81 m11,m12,m21,m22 = L*mass
 #define GXB_ELEM_NF 82
-__global__ void k_pack_elements(const double* __restrict__ raw, double* __restrict__ out, int N, int64_t nbatch) {
+__global__ void k_pack_elements(const double* __restrict__ raw, double* __restrict__ out, double* __restrict__ exS, int N, int64_t nbatch) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= nbatch * N) return;
     int64_t b = t / N; int e = (int)(t % N);
@@ -84,6 +88,7 @@ __global__ void k_pack_elements(const double* __restrict__ raw, double* __restri
     double* o = out + (size_t)b * GXB_ELEM_NF * N + e;
     const double L = s[0];
     o[0] = L;
+    if (exS) for (int k = 0; k < 3; k++) exS[((size_t)b * 3 + k) * N + e] = s[1 + k];    // Element.x (midpoint)
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[(size_t)(1 + 3 * i + j) * N] = s[76 + i + 3 * j];
     for (int bi = 0; bi < 2; bi++) for (int bj = 0; bj < 2; bj++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
         int f = 9 * (2 * bi + bj) + 3 * i + j;
@@ -116,6 +121,13 @@ template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble(StaticA
     static_station<WANT_J>(A, b, threadIdx.x, asm_smem);
 }
 
+template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble_steady(DynArgs A) {
+    extern __shared__ __align__(16) double asm_smem[];
+    const int b = blockIdx.x;
+    if (A.s.status && A.s.status[b] != A.s.want_status) return;
+    steady_station<WANT_J>(A, b, threadIdx.x, asm_smem);
+}
+
 struct SolveArgs {
     int nb, n; int64_t nbatch;
     const double* J; const double* F; const double* x; double* U; double* p; double* xt;
@@ -124,7 +136,7 @@ struct SolveArgs {
     int direction_only;   // parity entry point: just p, no state change
 };
 
-template <int KLB, int KUB> __global__ void __launch_bounds__(128, GXB_LU_MINBLOCKS) k_factor_solve(SolveArgs A) {
+template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? GXB_LU_MINBLOCKS : 2)) k_factor_solve(SolveArgs A) {
     using S = LuShape<KLB, KUB>;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,6 +273,7 @@ __global__ void k_extract_blocks(const double* __restrict__ Jrow, const int64_t*
 
 // ------------------------------------------------------------------------------------------------------------------
 static void free_batch(gxb_ctx* c) {
+    cudaFree(c->d_exS); cudaFree(c->d_motion); c->d_exS = c->d_motion = nullptr;
     cudaFree(c->d_elemS); cudaFree(c->d_bcS); cudaFree(c->d_dlS); cudaFree(c->d_pmS); cudaFree(c->d_grav); cudaFree(c->d_fs); cudaFree(c->d_xyz);
     cudaFree(c->d_x); cudaFree(c->d_xt); cudaFree(c->d_F); cudaFree(c->d_Ft); cudaFree(c->d_p); cudaFree(c->d_J); cudaFree(c->d_U);
     cudaFree(c->ns.status); cudaFree(c->ns.failcode); cudaFree(c->ns.iters); cudaFree(c->ns.fcalls); cudaFree(c->ns.ls_k); cudaFree(c->ns.ls_finite);
@@ -384,6 +397,39 @@ int gxb_topology(gxb_ctx* c, int kind, int64_t np, int64_t ne, const int64_t* st
         c->brow.clear(); c->bcol.clear();
         for (auto& q : v) { c->brow.push_back(q.first); c->bcol.push_back(q.second); }
     }
+    if (!is_static) {
+        // canonical 3x3-block pattern (dynamic, incl. the structural-damping blocks): point.jl:1795-1797, 1809-1826, 1920-1932;
+        // element.jl:2507-2549, 2702-2757
+        auto blk = [&](int64_t r, int64_t cc) { c->brow.push_back(r - 1); c->bcol.push_back(cc - 1); };
+        for (int64_t ip = 0; ip < np; ip++) {
+            int64_t ir = c->irow_point[ip], ic = c->icol_point[ip];
+            for (int q = 0; q < 4; q++) { blk(ir, ic + 3 * q); blk(ir + 3, ic + 3 * q); }
+            blk(ir + 6, ic); blk(ir + 6, ic + 6); blk(ir + 9, ic + 3); blk(ir + 9, ic + 9);
+        }
+        for (int64_t e = 0; e < ne; e++) {
+            int64_t ic = c->icol_elem[e], ic1 = c->icol_point[start[e] - 1], ic2 = c->icol_point[stop[e] - 1];
+            int64_t ir = c->irow_elem[e], ir1 = c->irow_point[start[e] - 1], ir2 = c->irow_point[stop[e] - 1];
+            for (int64_t icp : {ic1, ic2}) {
+                for (int q = 0; q < 4; q++) blk(ir, icp + 3 * q);
+                blk(ir + 3, icp + 3); blk(ir + 3, icp + 9);
+            }
+            blk(ir, ic); blk(ir, ic + 3); blk(ir + 3, ic); blk(ir + 3, ic + 3);
+            for (int64_t irp : {ir1, ir2}) {
+                for (int64_t icp : {ic1, ic2}) for (int q = 0; q < 4; q++) { blk(irp, icp + 3 * q); blk(irp + 3, icp + 3 * q); }
+                blk(irp, ic); blk(irp + 3, ic); blk(irp + 3, ic + 3);
+            }
+        }
+        std::vector<std::pair<int64_t, int64_t>> v;
+        for (size_t k = 0; k < c->brow.size(); k++) v.push_back({c->brow[k], c->bcol[k]});
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        c->brow.clear(); c->bcol.clear();
+        for (auto& q : v) { c->brow.push_back(q.first); c->bcol.push_back(q.second); }
+    }
+    c->body_state = false;
+    for (int64_t k = 0; k < np * 6; k++) if (c->pd[k] && c->pl[k]) c->body_state = true;
+    if (is_static) { c->W = LuShape<2, 2>::W; c->UW = LuShape<2, 2>::UW; c->KLB = 2; c->rows_per_station = 12; }
+    else { c->W = LuShape<3, 4>::W; c->UW = LuShape<3, 4>::UW; c->KLB = 3; c->rows_per_station = 18; }
     std::vector<unsigned short> flags(np);
     for (int64_t ip = 0; ip < np; ip++) {
         unsigned f = 0;
@@ -409,23 +455,23 @@ int gxb_topology(gxb_ctx* c, int kind, int64_t np, int64_t ne, const int64_t* st
 
 int gxb_pattern(gxb_ctx* c, int64_t* nblocks, int64_t* brow, int64_t* bcol) {
     if (!c || c->kind < 0) return fail(GXB_ERR_INVALID, "gxb_pattern: call gxb_topology first");
-    if (c->kind != 0) return fail(GXB_ERR_UNSUPPORTED, "gxb_pattern: only the static system is implemented on the device");
     if (nblocks) *nblocks = (int64_t)c->brow.size();
     if (brow) memcpy(brow, c->brow.data(), c->brow.size() * 8);
     if (bcol) memcpy(bcol, c->bcol.data(), c->bcol.size() * 8);
     return GXB_OK;
 }
 
-static int require_static_chain(gxb_ctx* c, const char* who) {
+static int require_chain(gxb_ctx* c, const char* who) {
     if (!c || c->kind < 0) return fail(GXB_ERR_INVALID, std::string(who) + ": call gxb_topology first");
-    if (c->kind != 0) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": only kind=0 (StaticSystem) is implemented on the device so far");
+    if (c->kind == 1 && c->body_state)
+        return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": a DOF with both displacement and load prescribed makes a body-frame acceleration a state variable (system.jl:138-150); not implemented on the device");
     if (!c->chain) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": only chain topologies (start = 1:n, stop = 2:n+1) are implemented on the device");
     if (c->np > 256) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": more than 255 elements per assembly not supported yet (one CTA per instance, shared-memory tile per station)");
     return GXB_OK;
 }
 
 int gxb_set_batch(gxb_ctx* c, int64_t nbatch) {
-    int rc = require_static_chain(c, "gxb_set_batch"); if (rc) return rc;
+    int rc = require_chain(c, "gxb_set_batch"); if (rc) return rc;
     if (nbatch < 1) return fail(GXB_ERR_INVALID, "gxb_set_batch: nbatch < 1");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
@@ -438,13 +484,18 @@ int gxb_set_batch(gxb_ctx* c, int64_t nbatch) {
     if ((rc = dalloc(&c->d_grav, nb * 3))) return rc;
     if ((rc = dalloc(&c->d_x, nb * n)) || (rc = dalloc(&c->d_xt, nb * n)) || (rc = dalloc(&c->d_F, nb * n)) || (rc = dalloc(&c->d_Ft, nb * n)) ||
         (rc = dalloc(&c->d_p, nb * n))) return rc;
-    if ((rc = dalloc(&c->d_J, nb * n * LuShape<2, 2>::W)) || (rc = dalloc(&c->d_U, nb * n * LuShape<2, 2>::UW))) return rc;
+    if ((rc = dalloc(&c->d_J, nb * n * c->W)) || (rc = dalloc(&c->d_U, nb * n * c->UW))) return rc;
+    if (c->kind == 1) {
+        if ((rc = dalloc(&c->d_exS, nb * 3 * N)) || (rc = dalloc(&c->d_xyz, nb * 3 * P)) || (rc = dalloc(&c->d_motion, nb * 12))) return rc;
+        CK(cudaMemsetAsync(c->d_xyz, 0, nb * 3 * P * 8, c->stream));
+        CK(cudaMemsetAsync(c->d_motion, 0, nb * 12 * 8, c->stream));
+    }
     if ((rc = dalloc(&c->ns.status, nb)) || (rc = dalloc(&c->ns.failcode, nb)) || (rc = dalloc(&c->ns.iters, nb)) || (rc = dalloc(&c->ns.fcalls, nb)) ||
         (rc = dalloc(&c->ns.ls_k, nb)) || (rc = dalloc(&c->ns.ls_finite, nb))) return rc;
     if ((rc = dalloc(&c->ns.a1, nb)) || (rc = dalloc(&c->ns.a2, nb)) || (rc = dalloc(&c->ns.phi0, nb)) || (rc = dalloc(&c->ns.dphi0, nb)) ||
         (rc = dalloc(&c->ns.phx0, nb)) || (rc = dalloc(&c->ns.finf, nb))) return rc;
     // structural zeros of the row-block storage are written once, here
-    CK(cudaMemsetAsync(c->d_J, 0, nb * n * LuShape<2, 2>::W * 8, c->stream));
+    CK(cudaMemsetAsync(c->d_J, 0, nb * n * c->W * 8, c->stream));
     CK(cudaMemsetAsync(c->d_grav, 0, nb * 3 * 8, c->stream));
     CK(cudaMemsetAsync(c->d_x, 0, nb * n * 8, c->stream));
     std::vector<double> ones(nb, 1.0);
@@ -460,14 +511,20 @@ int gxb_set_elements(gxb_ctx* c, const double* elems) {
     NEED_BATCH("gxb_set_elements");
     if (!elems) return fail(GXB_ERR_INVALID, "gxb_set_elements: null");
     int rc = stage_upload(c, elems, (size_t)c->nbatch * c->ne * GXB_ELEM_STRIDE * 8); if (rc) return rc;
-    k_pack_elements<<<grid1(c->nbatch * c->ne, 128), 128, 0, c->stream>>>(c->d_stage, c->d_elemS, (int)c->ne, c->nbatch);
+    k_pack_elements<<<grid1(c->nbatch * c->ne, 128), 128, 0, c->stream>>>(c->d_stage, c->d_elemS, c->d_exS, (int)c->ne, c->nbatch);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));   // the caller may reuse its buffer
     return GXB_OK;
 }
 int gxb_set_points(gxb_ctx* c, const double* xyz) {
     NEED_BATCH("gxb_set_points");
-    (void)xyz;   // point coordinates only enter the dynamic residuals (Δx in point.jl:643); unused by the static path
+    // point coordinates only enter the dynamic residuals (Δx in point.jl:643, element.jl:186-187); unused by the static path
+    if (c->kind != 1) return GXB_OK;
+    if (!xyz) return fail(GXB_ERR_INVALID, "gxb_set_points: null");
+    int rc = stage_upload(c, xyz, (size_t)c->nbatch * c->np * 3 * 8); if (rc) return rc;
+    k_pack_transpose<<<grid1(c->nbatch * c->np * 3, 256), 256, 0, c->stream>>>(c->d_stage, c->d_xyz, (int)c->np, 3, c->nbatch);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
     return GXB_OK;
 }
 int gxb_set_bc(gxb_ctx* c, const double* bc) {
@@ -489,8 +546,17 @@ int gxb_set_dloads(gxb_ctx* c, const double* dl) {
     CK(cudaStreamSynchronize(c->stream));
     return GXB_OK;
 }
+int gxb_set_motion(gxb_ctx* c, const double* motion) {
+    NEED_BATCH("gxb_set_motion");
+    if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_set_motion: body-frame motion only applies to kind=1 (DynamicSystem)");
+    if (motion) CK(cudaMemcpyAsync(c->d_motion, motion, (size_t)c->nbatch * 96, cudaMemcpyHostToDevice, c->stream));
+    else CK(cudaMemsetAsync(c->d_motion, 0, (size_t)c->nbatch * 96, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return GXB_OK;
+}
 int gxb_set_pmass(gxb_ctx* c, const double* pm) {
     NEED_BATCH("gxb_set_pmass");
+    if (pm && c->kind == 1) return fail(GXB_ERR_UNSUPPORTED, "gxb_set_pmass: point masses on a DynamicSystem are not implemented on the device yet");
     if (!pm) { cudaFree(c->d_pmS); c->d_pmS = nullptr; return GXB_OK; }
     if (!c->d_pmS) { int rc = dalloc(&c->d_pmS, (size_t)c->nbatch * 36 * c->np); if (rc) return rc; }
     int rc = stage_upload(c, pm, (size_t)c->nbatch * c->np * 36 * 8); if (rc) return rc;
@@ -521,6 +587,8 @@ int gxb_upload_x0(gxb_ctx* c, const double* x0) {
     return GXB_OK;
 }
 
+}  // extern "C"
+
 // ---- launch helpers ----
 struct Prof {
     gxb_ctx* c; bool on;
@@ -538,26 +606,48 @@ static StaticArgs make_static_args(gxb_ctx* c, const gxb_opts* o, const double* 
 }
 static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
     int bs = (int)((c->np + 31) / 32) * 32;
-    size_t sm = (size_t)bs * (GXB_XCH + (want_j ? GXB_TILE : 0)) * 8;
-    if (want_j) {
-        static thread_local size_t configured = 0;
-        if (sm > configured) { CK(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
-        k_assemble<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
-    } else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
+    if (c->kind == 0) {
+        size_t sm = (size_t)bs * (GXB_XCH + (want_j ? GXB_TILE : 0)) * 8;
+        if (want_j) {
+            static thread_local size_t configured = 0;
+            if (sm > configured) { CK(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+            k_assemble<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
+        } else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
+    } else {
+        DynArgs D{};
+        D.s = A; D.exS = c->d_exS; D.pxS = c->d_xyz; D.motion = c->d_motion;
+        // the shared-memory tile holds `chunk` stations; longer chains are flushed chunk by chunk
+        const size_t budget = 200 * 1024;
+        int chunk = (int)std::min<size_t>((size_t)bs, (budget - (size_t)bs * GXB_XCH * 8) / (GXB_DTILE * 8));
+        D.chunk = chunk;
+        size_t sm = ((size_t)bs * GXB_XCH + (want_j ? (size_t)chunk * GXB_DTILE : 0)) * 8;
+        if (want_j) {
+            static thread_local size_t configured = 0;
+            if (sm > configured) { CK(cudaFuncSetAttribute(k_assemble_steady<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+            k_assemble_steady<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+        } else k_assemble_steady<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+    }
     CK(cudaGetLastError());
     c->stats.launches++; c->stats.n_assemble++;
     return GXB_OK;
 }
+template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveArgs& A) {
+    using S = LuShape<KLB, KUB>;
+    const int wpc = 4;
+    size_t sm = (size_t)wpc * S::SM_DOUBLES * 8;
+    static thread_local size_t configured = 0;
+    if (sm > 48 * 1024 && sm > configured) { CK(cudaFuncSetAttribute(k_factor_solve<KLB, KUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+    k_factor_solve<KLB, KUB><<<grid1(c->nbatch, wpc), 32 * wpc, sm, c->stream>>>(A);
+    CK(cudaGetLastError());
+    return GXB_OK;
+}
 static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only) {
-    using S = LuShape<2, 2>;
     SolveArgs A{};
     A.nb = (int)(c->n / 6); A.n = (int)c->n; A.nbatch = c->nbatch;
     A.J = c->d_J; A.F = direction_only ? c->d_Ft : c->d_F; A.x = c->d_x; A.U = c->d_U; A.p = c->d_p; A.xt = c->d_xt; A.ns = c->ns;
     A.maxstep = o->maxstep; A.linear = o->linear; A.direction_only = direction_only;
-    const int wpc = 4;
-    size_t sm = (size_t)wpc * S::SM_DOUBLES * 8;
-    k_factor_solve<2, 2><<<grid1(c->nbatch, wpc), 32 * wpc, sm, c->stream>>>(A);
-    CK(cudaGetLastError());
+    int rc = c->kind == 0 ? launch_factor_t<2, 2>(c, A) : launch_factor_t<3, 4>(c, A);
+    if (rc) return rc;
     c->stats.launches++; c->stats.n_factor++;
     return GXB_OK;
 }
@@ -572,8 +662,28 @@ static int launch_update(gxb_ctx* c, const gxb_opts* o, int mode) {
     return GXB_OK;
 }
 
+extern "C" {
+
+static int solve_resident(gxb_ctx* c, const gxb_opts* opts);
+
 int gxb_static_solve_resident(gxb_ctx* c, const gxb_opts* opts) {
     NEED_BATCH("gxb_static_solve_resident");
+    if (c->kind != 0) return fail(GXB_ERR_INVALID, "gxb_static_solve_resident: context topology is not kind=0 (StaticSystem)");
+    return solve_resident(c, opts);
+}
+int gxb_steady_solve_resident(gxb_ctx* c, const gxb_opts* opts) {
+    NEED_BATCH("gxb_steady_solve_resident");
+    if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_steady_solve_resident: context topology is not kind=1 (DynamicSystem)");
+    if (opts && opts->structural_damping) return fail(GXB_ERR_UNSUPPORTED, "structural_damping=true is not implemented on the device yet (steady_state_analysis defaults to false)");
+    return solve_resident(c, opts);
+}
+int gxb_steady_solve(gxb_ctx* c, const gxb_opts* opts, const double* x0, double* x, int32_t* converged, int32_t* iters, double* resid_inf) {
+    int rc;
+    if ((rc = gxb_upload_x0(c, x0))) return rc;
+    if ((rc = gxb_steady_solve_resident(c, opts))) return rc;
+    return gxb_fetch(c, x, converged, iters, resid_inf);
+}
+static int solve_resident(gxb_ctx* c, const gxb_opts* opts) {
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     c->stats = gxb_stats{};
     Prof prof{c, o.profile != 0};
@@ -648,9 +758,10 @@ int gxb_static_solve(gxb_ctx* c, const gxb_opts* opts, const double* x0, double*
     return gxb_fetch(c, x, converged, iters, resid_inf);
 }
 
-int gxb_static_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double* x, double* r, double* Jblk) {
-    NEED_BATCH("gxb_static_residual_jacobian");
-    if (!x) return fail(GXB_ERR_INVALID, "gxb_static_residual_jacobian: x is null");
+int gxb_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double* x, double* r, double* Jblk) {
+    NEED_BATCH("gxb_residual_jacobian");
+    if (c->kind == 1 && opts && opts->structural_damping) return fail(GXB_ERR_UNSUPPORTED, "structural_damping=true is not implemented on the device yet");
+    if (!x) return fail(GXB_ERR_INVALID, "gxb_residual_jacobian: x is null");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
     CK(cudaMemcpyAsync(c->d_xt, x, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
@@ -661,7 +772,7 @@ int gxb_static_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double*
         const size_t nblk = c->brow.size();
         size_t bytes = nb * nblk * 9 * 8;
         if (bytes > c->stage_bytes) { cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0; CK(cudaMalloc(&c->d_stage, bytes)); c->stage_bytes = bytes; }
-        k_extract_blocks<<<grid1(nb * nblk * 9, 256), 256, 0, c->stream>>>(c->d_J, c->d_brow, c->d_bcol, c->d_stage, (int64_t)nblk, (int)n, LuShape<2, 2>::W, 2, c->nbatch);
+        k_extract_blocks<<<grid1(nb * nblk * 9, 256), 256, 0, c->stream>>>(c->d_J, c->d_brow, c->d_bcol, c->d_stage, (int64_t)nblk, (int)n, c->W, c->KLB, c->nbatch);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(Jblk, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -669,9 +780,9 @@ int gxb_static_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double*
     return GXB_OK;
 }
 
-int gxb_static_newton_direction(gxb_ctx* c, const gxb_opts* opts, const double* x, double* p) {
-    NEED_BATCH("gxb_static_newton_direction");
-    if (!x || !p) return fail(GXB_ERR_INVALID, "gxb_static_newton_direction: null");
+int gxb_newton_direction(gxb_ctx* c, const gxb_opts* opts, const double* x, double* p) {
+    NEED_BATCH("gxb_newton_direction");
+    if (!x || !p) return fail(GXB_ERR_INVALID, "gxb_newton_direction: null");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
     CK(cudaMemcpyAsync(c->d_xt, x, nb * n * 8, cudaMemcpyHostToDevice, c->stream));

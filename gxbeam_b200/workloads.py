@@ -73,3 +73,36 @@ def single_assembly_arrays(assembly: Assembly, prescribed_conditions, dloads=Non
                 elems=assembly.pack_elements()[None], bc=bc[None],
                 dload=None if not dloads else pack_distributed_loads(assembly.ne, dloads)[None],
                 pmass=None if not pmasses else pack_point_masses(assembly.np_, pmasses)[None])
+
+
+def rotating_blade_batch(nbatch=1, seed=1234 + 1, rpm_jitter=0.0):
+    """BASELINE config 1 (benchmark/benchmarks.jl:3-65): 20 + 4 element swept-tip blade, root clamped, rotating at 750 rpm about z
+    (linear_velocity = (0, 196.349540849362, 0), angular_velocity = (0, 0, 78.5398163397448)), steady_state_analysis, n = 444.
+    For nbatch > 1 the rotor speed of instance i is scaled by U(1 - rpm_jitter, 1 + rpm_jitter) (design-sweep style batch).
+    """
+    from .assembly import discretize_beam
+    rng = np.random.default_rng(seed)
+    l1, xp1, xm1, c1 = discretize_beam(31.5, [0, 0, 0], 20)
+    frame = np.array([[0.707106781186548, 0.707106781186548, 0.0], [-0.707106781186548, 0.707106781186548, 0.0], [0.0, 0.0, 1.0]])
+    l2, xp2, xm2, c2 = discretize_beam(6.0, [31.5, 0, 0], 4, frame=frame)
+    nelem = 24
+    points = np.vstack([xp1, xp2[1:]])
+    start = np.arange(1, nelem + 1, dtype=np.int64)
+    stop = np.arange(2, nelem + 2, dtype=np.int64)
+    comp = np.diag([1.4974543276E-06, 4.7619054919E-06, 5.8036221902E-05, 3.1234387938E-03, 4.5274507258E-03, 1.7969451932E-05])
+    mass = np.diag([1.5813000000E-05, 1.5813000000E-05, 1.5813000000E-05, 1.3229801498E-06, 5.2301497500E-09, 1.3177500000E-06])
+    asm = Assembly(points, start, stop, compliance=[comp] * nelem, mass=[mass] * nelem, frames=list(c1) + list(c2),
+                   lengths=np.concatenate([l1, l2]), midpoints=np.vstack([xm1, xm2]))
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
+    pd, pl, bc1 = pack_prescribed_conditions(nelem + 1, pcs)
+    elems = np.tile(asm.pack_elements()[None], (nbatch, 1, 1))
+    bc = np.tile(bc1[None], (nbatch, 1, 1))
+    pts = np.tile(points[None], (nbatch, 1, 1))
+    scale = np.ones(nbatch) if rpm_jitter == 0.0 else rng.uniform(1 - rpm_jitter, 1 + rpm_jitter, nbatch)
+    motion = np.zeros((nbatch, 12))
+    motion[:, 1] = 196.349540849362 * scale
+    motion[:, 5] = 78.5398163397448 * scale
+    from .assembly import default_force_scaling
+    fs = np.full(nbatch, default_force_scaling(asm))
+    return dict(start=start, stop=stop, points=points, points_b=pts, pd=pd, pl=pl, elems=elems, bc=bc, motion=motion, force_scaling=fs,
+                nelem=nelem, nbatch=nbatch, asm=asm)

@@ -42,7 +42,7 @@ typedef struct gxb_opts {
     double maxstep;          /* 1e6 */
     double c1, rho_hi, rho_lo; /* 1e-4, 0.5, 0.1 */
     int32_t profile;         /* !=0: time every kernel class with CUDA events (gxb_get_stats) */
-    int32_t reserved;
+    int32_t structural_damping; /* steady/time-domain only (analyses.jl:397); must be 0 on the device for now */
 } gxb_opts;
 
 /* Filled by gxb_get_stats after a solve. */
@@ -73,6 +73,8 @@ int gxb_topology(gxb_ctx* ctx, int kind, int64_t np, int64_t ne, const int64_t* 
 
 /* Canonical structural pattern of the Jacobian at 3x3-block granularity (what insert_static_point_jacobians!
  * src/point.jl:1785-1800 and insert_static_element_jacobians! src/element.jl:2487-2552 can touch).
+ * For kind=1: insert_dynamic/steady_point_jacobians! src/point.jl:1907-1935, 1809-1826 and insert_dynamic_element_jacobians!
+ * src/element.jl:2685-2759 (the structural-damping blocks included; body-acceleration columns excluded).
  * Returns the number of blocks in *nblocks; brow/bcol (may be NULL) receive the 0-based scalar row/col of each block. */
 int gxb_pattern(gxb_ctx* ctx, int64_t* nblocks, int64_t* brow, int64_t* bcol);
 
@@ -84,6 +86,9 @@ int gxb_set_bc(gxb_ctx* ctx, const double* bc);            /* nbatch x np x 18  
 int gxb_set_dloads(gxb_ctx* ctx, const double* dl);        /* nbatch x ne x 24 or NULL   distributed_loads     */
 int gxb_set_pmass(gxb_ctx* ctx, const double* pm);         /* nbatch x np x 36 (col-major 6x6) or NULL  point_masses */
 int gxb_set_body(gxb_ctx* ctx, const double* gravity /* nbatch x 3 or NULL */, const double* force_scaling /* nbatch */);
+/* kind=1 only: linear_velocity, angular_velocity, linear_acceleration, angular_acceleration of the body frame
+ * (steady_state_analysis keyword arguments, src/analyses.jl:388-391): nbatch x 12 = vb, ωb, ab, αb; NULL = zeros. */
+int gxb_set_motion(gxb_ctx* ctx, const double* motion);
 
 /* static_analysis!: nlsolve!/lsolve! over the batch                       src/analyses.jl:137-171, 3506-3599
  * x0: nbatch x nstates initial guess or NULL (zeros, = reset_state).  Outputs: x (nbatch x nstates), converged, iters
@@ -91,19 +96,26 @@ int gxb_set_body(gxb_ctx* ctx, const double* gravity /* nbatch x 3 or NULL */, c
 int gxb_static_solve(gxb_ctx* ctx, const gxb_opts* opts, const double* x0, double* x, int32_t* converged, int32_t* iters,
                      double* resid_inf);
 
+/* steady_state_analysis!: the same Newton driver on a DynamicSystem (kind=1)          src/analyses.jl:383-527, 3556-3599
+ * with steady_system_residual!/jacobian! (src/system.jl:427-455, 693-720).  structural_damping must be 0 (its default). */
+int gxb_steady_solve(gxb_ctx* ctx, const gxb_opts* opts, const double* x0, double* x, int32_t* converged, int32_t* iters,
+                     double* resid_inf);
+int gxb_steady_solve_resident(gxb_ctx* ctx, const gxb_opts* opts);
+
 /* The same solve on inputs already resident in HBM (no host<->device traffic): x0 from gxb_upload_x0 or zeros. */
 int gxb_upload_x0(gxb_ctx* ctx, const double* x0 /* or NULL */);
 int gxb_static_solve_resident(gxb_ctx* ctx, const gxb_opts* opts);
 int gxb_fetch(gxb_ctx* ctx, double* x, int32_t* converged, int32_t* iters, double* resid_inf);
 int gxb_get_stats(gxb_ctx* ctx, gxb_stats* st);
 
-/* static_system_residual! + static_system_jacobian! at given states      src/system.jl:400-418, 663-683
+/* {static,steady}_system_residual! + _jacobian! at given states (by the context's kind)
+ *                                                          src/system.jl:400-418, 663-683 | 427-455, 693-720
  * x: nbatch x nstates.  r: nbatch x nstates.  Jblk: nbatch x nblocks x 9, each 3x3 row-major on gxb_pattern's blocks. */
-int gxb_static_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* r, double* Jblk);
+int gxb_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* r, double* Jblk);
 
 /* One Newton direction p = -(J(x) \ r(x)) per instance (the `linsolve` of analyses.jl:3585), for parity tests of the
  * batched pivoted block-banded LU in isolation.  p: nbatch x nstates. */
-int gxb_static_newton_direction(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* p);
+int gxb_newton_direction(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* p);
 
 #ifdef __cplusplus
 }

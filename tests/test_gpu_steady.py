@@ -1,0 +1,148 @@
+"""GPU parity tests for the steady-state (DynamicSystem) path: CUDA through the C-ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+import cases
+from gxbeam_b200 import api, workloads
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _oracle():
+    from oracle import pyoracle as O
+    return O
+
+
+def _ctx(case, motion, nb=1, pts=None):
+    ctx = api.Context(0)
+    ctx.topology(case["start"], case["stop"], case["pd"], case["pl"], kind=1)
+    ctx.set_batch(nb)
+    ctx.set_elements(case["elems"][:nb])
+    ctx.set_points(np.broadcast_to(case["points"], (nb,) + case["points"].shape).copy() if pts is None else pts)
+    ctx.set_bc(case["bc"][:nb])
+    if case.get("dload") is not None:
+        ctx.set_dloads(case["dload"][:nb])
+    g = case.get("gravity")
+    if g is not None:
+        g = np.broadcast_to(np.asarray(g, float).reshape(-1, 3), (nb, 3)).copy()
+    ctx.set_body(g, np.broadcast_to(np.asarray(case["force_scaling"], float).reshape(-1), (nb,)).copy())
+    ctx.set_motion(motion)
+    return ctx
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_dynamic_indices_bit_exact():
+    O = _oracle()
+    for n in (1, 3, 24):
+        start, stop = np.arange(1, n + 1), np.arange(2, n + 2)
+        ctx = api.Context(0)
+        idx = ctx.topology(start, stop, kind=1)
+        ref = O.indices(start, stop, False)
+        assert idx["nstates"] == ref["nstates"] == 18 * n + 12
+        for k in ("irow_point", "irow_elem", "icol_point", "icol_elem"):
+            assert np.array_equal(idx[k], ref[k])
+        ctx.close()
+
+
+def test_body_acceleration_state_is_refused():
+    case = cases.jacobians_jl(0)
+    ctx = api.Context(0)
+    ctx.topology(case["start"], case["stop"], case["pd"], case["pl"], kind=1)
+    with pytest.raises(api.GXBError, match="body-frame acceleration"):
+        ctx.set_batch(1)
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed,nelem", [(0, 2), (1, 5), (2, 9)])
+@pytest.mark.parametrize("two_d", [False, True])
+def test_steady_residual_and_jacobian_parity(seed, nelem, two_d):
+    O = _oracle()
+    case = cases.random_anisotropic(seed, nelem=nelem, pmass=False)
+    pk = cases.oracle_packed(case, two_dimensional=two_d)
+    rng = np.random.default_rng(seed + 40)
+    mo = 1e2 * rng.random(12)
+    dyn = O.make_dyn(vb=mo[0:3], wb=mo[3:6], ab=mo[6:9], alb=mo[9:12])
+    ctx = _ctx(case, mo[None])
+    n = ctx.n
+    brow, bcol = ctx.pattern()
+    mask = api.blocks_to_dense(n, brow, bcol, np.ones((len(brow), 9))) != 0
+    for scale in (1.0, 1e2):
+        x = scale * rng.random((1, n))
+        r, Jb = ctx.residual_jacobian(x, api.make_opts(two_dimensional=two_d))
+        r_ref = O.steady_residual(pk, dyn, x[0])
+        J_ref = O.steady_jacobian(pk, dyn, x[0])
+        assert _relerr(r[0], r_ref) < 1e-12
+        J = api.blocks_to_dense(n, brow, bcol, Jb[0])
+        assert np.abs(J - J_ref).max() <= 1e-12 * np.abs(J_ref).max()
+        assert np.all(J_ref[~mask] == 0.0)
+    ctx.close()
+
+
+def test_steady_newton_direction_parity():
+    O = _oracle()
+    case = cases.random_anisotropic(4, nelem=8, pmass=False)
+    pk = cases.oracle_packed(case)
+    rng = np.random.default_rng(3)
+    mo = 10 * rng.random(12)
+    dyn = O.make_dyn(vb=mo[0:3], wb=mo[3:6], ab=mo[6:9], alb=mo[9:12])
+    ctx = _ctx(case, mo[None])
+    x = rng.random((1, ctx.n))
+    p = ctx.newton_direction(x)
+    J = O.steady_jacobian(pk, dyn, x[0])
+    r = O.steady_residual(pk, dyn, x[0])
+    assert _relerr(p[0], -np.linalg.solve(J, r)) < 1e-9
+    ctx.close()
+
+
+def test_rotating_blade_config1_parity():
+    """BASELINE config 1 (benchmark/benchmarks.jl steady_benchmark): single Assembly, n = 444."""
+    O = _oracle()
+    w = workloads.rotating_blade_batch(1)
+    ctx = _ctx(w, w["motion"], 1, w["points_b"])
+    res = ctx.steady_solve()
+    assert ctx.n == 444
+    ctx.close()
+    pk = O.Packed(w["start"], w["stop"], w["elems"][0], w["points"], w["pd"], w["pl"], w["bc"][0], force_scaling=w["force_scaling"][0])
+    dyn = O.make_dyn(vb=w["motion"][0, 0:3], wb=w["motion"][0, 3:6])
+    ref = O.steady_solve(pk, dyn)
+    assert ref["converged"] and res["converged"][0]
+    assert int(res["iters"][0]) == ref["iters"]
+    # compare per physical group (displacement-like, velocity-like, load-like)
+    idx = O.indices(w["start"], w["stop"], False)
+    xg, xr = res["x"][0], ref["x"]
+    groups = {"disp": [], "vel": [], "load": []}
+    for ic in idx["icol_point"]:
+        groups["disp"] += list(range(ic - 1, ic + 5)); groups["vel"] += list(range(ic + 5, ic + 11))
+    for ic in idx["icol_elem"]:
+        groups["load"] += list(range(ic - 1, ic + 5))
+    # root point holds reactions, not displacements
+    root = list(range(0, 6))
+    groups["disp"] = [k for k in groups["disp"] if k not in root]; groups["load"] += root
+    for name, ids in groups.items():
+        assert np.abs(xg[ids] - xr[ids]).max() <= RTOL * np.abs(xr[ids]).max(), name
+    # centrifugal stiffening sanity: the blade stretches outward (tip u_x > 0)
+    tip = idx["icol_point"][-1] - 1
+    assert xg[tip] > 0
+
+
+def test_rotor_speed_sweep_batch_parity():
+    """A design-sweep style batch: 32 blades at different rotor speeds, every instance against the oracle."""
+    O = _oracle()
+    nb = 32
+    w = workloads.rotating_blade_batch(nb, rpm_jitter=0.5)
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    res = ctx.steady_solve()
+    st = ctx.stats()
+    ctx.close()
+    pk = O.Packed(w["start"], w["stop"], w["elems"], w["points_b"], w["pd"], w["pl"], w["bc"])
+    dyns = [O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6]) for b in range(nb)]
+    ref = O.steady_solve_batch(pk, nb, dyns, force_scaling=w["force_scaling"])
+    assert res["converged"].all() and ref["converged"].all()
+    assert np.array_equal(res["iters"], ref["iters"])
+    assert st["newton_iters"] == int(res["iters"].sum())
+    for b in range(nb):
+        assert np.abs(res["x"][b] - ref["x"][b]).max() <= 1e-9 * np.abs(ref["x"][b]).max()
