@@ -426,4 +426,198 @@ template <class T, class J> void steady_system_jacobian(const Problem& P, const 
     if (P.two_dimensional) two_dimensional_jacobian<T>(idx.nstates, jac);
 }
 
+// ================================================================= Newmark time marching =================================
+//   newmark_point_properties / _jacobian_properties          src/point.jl:766-795, 1134-1200
+//   newmark_point_velocity_jacobians                         src/point.jl:1708-1720
+//   newmark_point_residual! / _jacobian!                     src/point.jl:2200-2221, 2410-2432
+//   newmark_element_properties / _jacobian_properties        src/element.jl:381-412, 1049-1112
+//   newmark_element_residual! / _jacobian!                   src/element.jl:3074-3090, 3271-3292
+//   newmark_system_residual! / _jacobian!                    src/system.jl:530-554, 829-852
+struct NewmarkParams {
+    const double* init = nullptr;   // [np][12]: udot_init, θdot_init, Vdot_init, Ωdot_init  (`paug`, analyses.jl:2693-2738)
+    double dt = 1.0;
+};
+
+template <class T> void newmark_point_rates(DynPoint<T>& p, const NewmarkParams& N, int64_t ip) {
+    const double* q = N.init + 12 * ip;
+    T c = T(2.0 / N.dt);
+    p.udot = c * p.u - cvec<T>(q); p.thdot = c * p.th - cvec<T>(q + 3);
+    p.Vdot = c * p.V - cvec<T>(q + 6); p.Omdot = c * p.Om - cvec<T>(q + 9);
+}
+// point.jl:766-795
+template <class T> DynPoint<T> newmark_point_properties(const Problem& P, const Indices& idx, const T* x, int64_t ip, const DynParams& D,
+                                                        const NewmarkParams& N, M3<T>& Cdot) {
+    V3<T> z = zero3<T>();
+    DynPoint<T> p = steady_point_properties(P, idx, x, ip, D, z, z);
+    newmark_point_rates(p, N, ip);
+    Cdot = -(p.C * tilde(p.Om - p.wb));
+    M3<T> Ct = tr(p.C), Cdt = tr(Cdot);
+    p.Pdot = Ct * (p.mass11 * (p.C * p.Vdot)) + Ct * (p.mass12 * (p.C * p.Omdot)) + Ct * (p.mass11 * (Cdot * p.V)) + Ct * (p.mass12 * (Cdot * p.Om)) +
+             Cdt * (p.mass11 * (p.C * p.V)) + Cdt * (p.mass12 * (p.C * p.Om));
+    p.Hdot = Ct * (p.mass21 * (p.C * p.Vdot)) + Ct * (p.mass22 * (p.C * p.Omdot)) + Ct * (p.mass21 * (Cdot * p.V)) + Ct * (p.mass22 * (Cdot * p.Om)) +
+             Cdt * (p.mass21 * (p.C * p.V)) + Cdt * (p.mass22 * (p.C * p.Om));
+    return p;
+}
+// point.jl:1134-1200
+template <class T> void newmark_point_jacobian_properties(const Problem& P, const Indices& idx, const T* x, int64_t ip, DynPoint<T>& p,
+                                                          const M3<T>& Cdot, const NewmarkParams& N) {
+    steady_point_jacobian_properties(P, idx, x, ip, p);
+    M3<T> Ct = tr(p.C), Cdt = tr(Cdot), Ct1 = tr(p.C_t1), Ct2 = tr(p.C_t2), Ct3 = tr(p.C_t3);
+    auto m3c = [&](const V3<T>& w) { return mul3(p.C_t1, p.C_t2, p.C_t3, w); };
+    auto m3t = [&](const V3<T>& w) { return mul3(Ct1, Ct2, Ct3, w); };
+    M3<T> Wt = tilde(p.Om - p.wb);
+    T c = T(2.0 / N.dt);
+    auto rate_th = [&](const M3<T>& ma, const M3<T>& mb) {
+        return m3t(ma * (p.C * p.Vdot)) + m3t(mb * (p.C * p.Omdot)) + Ct * (ma * m3c(p.Vdot)) + Ct * (mb * m3c(p.Omdot)) +
+               Wt * m3t(ma * (p.C * p.V)) + Wt * m3t(mb * (p.C * p.Om)) + Cdt * (ma * m3c(p.V)) + Cdt * (mb * m3c(p.Om)) +
+               m3t(ma * (Cdot * p.V)) + m3t(mb * (Cdot * p.Om)) - Ct * (ma * m3c(Wt * p.V)) - Ct * (mb * m3c(Wt * p.Om));
+    };
+    p.Pdot_u = zero33<T>(); p.Hdot_u = zero33<T>();
+    p.Pdot_th = rate_th(p.mass11, p.mass12);
+    p.Hdot_th = rate_th(p.mass21, p.mass22);
+    p.Pdot_V = Ct * p.mass11 * Cdot + Cdt * p.mass11 * p.C + c * (Ct * p.mass11 * p.C);
+    p.Pdot_Om = Ct * p.mass12 * Cdot + Cdt * p.mass12 * p.C + Ct * p.mass11 * p.C * tilde(p.V) + Ct * p.mass12 * p.C * tilde(p.Om) -
+                tilde(Ct * (p.mass11 * (p.C * p.V))) - tilde(Ct * (p.mass12 * (p.C * p.Om))) + c * (Ct * p.mass12 * p.C);
+    p.Hdot_V = Ct * p.mass21 * Cdot + Cdt * p.mass21 * p.C + c * (Ct * p.mass21 * p.C);
+    p.Hdot_Om = Ct * p.mass22 * Cdot + Cdt * p.mass22 * p.C + Ct * p.mass21 * p.C * tilde(p.V) + Ct * p.mass22 * p.C * tilde(p.Om) -
+                tilde(Ct * (p.mass21 * (p.C * p.V))) - tilde(Ct * (p.mass22 * (p.C * p.Om))) + c * (Ct * p.mass22 * p.C);
+}
+// point.jl:2200-2221
+template <class T> void newmark_point_residual(const Problem& P, const Indices& idx, const T* x, int64_t ip, const DynParams& D, const NewmarkParams& N,
+                                               T* resid) {
+    int64_t irow = idx.irow_point[ip] - 1;
+    M3<T> Cdot;
+    DynPoint<T> p = newmark_point_properties(P, idx, x, ip, D, N, Cdot);
+    V3<T> F, M, rV, rOm;
+    dynamic_point_resultants(p, F, M);
+    point_velocity_residuals(p, rV, rOm);
+    T fs = T(P.force_scaling);
+    for (int i = 0; i < 3; i++) { resid[irow + i] = -F[i] / fs; resid[irow + 3 + i] = -M[i] / fs; resid[irow + 6 + i] = rV[i]; resid[irow + 9 + i] = rOm[i]; }
+}
+// point.jl:2410-2432 (+ 1708-1720, 1907-1935)
+template <class T, class J> void newmark_point_jacobian(const Problem& P, const Indices& idx, const T* x, int64_t ip, const DynParams& D,
+                                                        const NewmarkParams& N, J& jac) {
+    M3<T> Cdot;
+    DynPoint<T> p = newmark_point_properties(P, idx, x, ip, D, N, Cdot);
+    newmark_point_jacobian_properties(P, idx, x, ip, p, Cdot, N);
+    PointResJac<T> r = steady_point_resultant_jacobians(p);   // the dynamic part of it (F_ab.. unused here)
+    T c = T(2.0 / N.dt);
+    M3<T> rV_u = -tilde(p.wb) - c * eye3<T>(), rV_V = eye3<T>();
+    M3<T> rOm_th = mul3(p.Qi_t1, p.Qi_t2, p.Qi_t3, p.C * (p.Om - p.wb)) + p.Qinv * mul3(p.C_t1, p.C_t2, p.C_t3, p.Om - p.wb) - c * eye3<T>();
+    M3<T> rOm_Om = p.Qinv * p.C;
+    int64_t irow = idx.irow_point[ip] - 1, icol = idx.icol_point[ip] - 1;
+    T fs = T(P.force_scaling);
+    set33(jac, irow, icol, -p.F_F);
+    set33(jac, irow, icol + 3, (-(r.F_th * p.th_th)) / fs);
+    set33(jac, irow + 3, icol + 3, -p.M_M - (r.M_th * p.th_th) / fs);
+    set33(jac, irow, icol + 6, (-r.F_V) / fs);
+    set33(jac, irow, icol + 9, (-r.F_Om) / fs);
+    set33(jac, irow + 3, icol + 6, (-r.M_V) / fs);
+    set33(jac, irow + 3, icol + 9, (-r.M_Om) / fs);
+    set33(jac, irow + 6, icol, rV_u * p.u_u);
+    set33(jac, irow + 6, icol + 6, rV_V);
+    set33(jac, irow + 9, icol + 3, rOm_th * p.th_th);
+    set33(jac, irow + 9, icol + 9, rOm_Om);
+}
+// element.jl:381-412
+template <class T> DynElem<T> newmark_element_properties(const Problem& P, const Indices& idx, const T* x, int64_t ie, const DynParams& D,
+                                                         const NewmarkParams& N, M3<T>& CtCabdot) {
+    V3<T> z = zero3<T>();
+    DynElem<T> p = steady_element_properties(P, idx, x, ie, D, z, z);
+    int64_t ia = P.start[ie] - 1, ib = P.stop[ie] - 1;
+    T c = T(2.0 / N.dt);
+    V3<T> V1dot = c * p.V1 - cvec<T>(N.init + 12 * ia + 6), Om1dot = c * p.Om1 - cvec<T>(N.init + 12 * ia + 9);
+    V3<T> V2dot = c * p.V2 - cvec<T>(N.init + 12 * ib + 6), Om2dot = c * p.Om2 - cvec<T>(N.init + 12 * ib + 9);
+    p.Vdot = (V1dot + V2dot) / T(2); p.Omdot = (Om1dot + Om2dot) / T(2);
+    CtCabdot = tilde(p.Om - p.wb) * p.CtCab;
+    M3<T> A = p.CtCab, At = tr(p.CtCab), B = CtCabdot, Bt = tr(CtCabdot);
+    p.Pdot = A * (p.mass11 * (At * p.Vdot)) + A * (p.mass12 * (At * p.Omdot)) + A * (p.mass11 * (Bt * p.V)) + A * (p.mass12 * (Bt * p.Om)) +
+             B * (p.mass11 * (At * p.V)) + B * (p.mass12 * (At * p.Om));
+    p.Hdot = A * (p.mass21 * (At * p.Vdot)) + A * (p.mass22 * (At * p.Omdot)) + A * (p.mass21 * (Bt * p.V)) + A * (p.mass22 * (Bt * p.Om)) +
+             B * (p.mass21 * (At * p.V)) + B * (p.mass22 * (At * p.Om));
+    return p;
+}
+// element.jl:1049-1112
+template <class T> void newmark_element_jacobian_properties(const Problem& P, int64_t ie, DynElem<T>& p, const M3<T>& CtCabdot, const NewmarkParams& N) {
+    steady_element_jacobian_properties(P, ie, p);
+    M3<T> Ct1 = tr(p.C_t1), Ct2 = tr(p.C_t2), Ct3 = tr(p.C_t3), At = tr(p.CtCab), Bt = tr(CtCabdot), CabT = tr(p.Cab);
+    const M3<T>&A = p.CtCab, &B = CtCabdot;
+    auto m3c = [&](const V3<T>& w) { return mul3(p.C_t1, p.C_t2, p.C_t3, w); };
+    auto m3t = [&](const V3<T>& w) { return mul3(Ct1, Ct2, Ct3, w); };
+    M3<T> Wt = tilde(p.Om - p.wb);
+    T c = T(2.0 / N.dt);
+    auto rate_th = [&](const M3<T>& ma, const M3<T>& mb) {
+        return m3t(p.Cab * (ma * (At * p.Vdot))) + m3t(p.Cab * (mb * (At * p.Omdot))) + A * (ma * (CabT * m3c(p.Vdot))) + A * (mb * (CabT * m3c(p.Omdot))) +
+               Wt * m3t(p.Cab * (ma * (At * p.V))) + Wt * m3t(p.Cab * (mb * (At * p.Om))) + B * (ma * (CabT * m3c(p.V))) + B * (mb * (CabT * m3c(p.Om))) +
+               m3t(p.Cab * (ma * (Bt * p.V))) + m3t(p.Cab * (mb * (Bt * p.Om))) - A * (ma * (CabT * m3c(Wt * p.V))) - A * (mb * (CabT * m3c(Wt * p.Om)));
+    };
+    p.Pdot_u = zero33<T>(); p.Hdot_u = zero33<T>();
+    p.Pdot_th = rate_th(p.mass11, p.mass12);
+    p.Hdot_th = rate_th(p.mass21, p.mass22);
+    p.Pdot_V = A * p.mass11 * Bt + B * p.mass11 * At + c * (A * p.mass11 * At);
+    p.Pdot_Om = A * p.mass12 * Bt + B * p.mass12 * At + A * p.mass11 * At * tilde(p.V) + A * p.mass12 * At * tilde(p.Om) -
+                tilde(A * (p.mass11 * (At * p.V))) - tilde(A * (p.mass12 * (At * p.Om))) + c * (A * p.mass12 * At);
+    p.Hdot_V = A * p.mass21 * Bt + B * p.mass21 * At + c * (A * p.mass21 * At);
+    p.Hdot_Om = A * p.mass22 * Bt + B * p.mass22 * At + A * p.mass21 * At * tilde(p.V) + A * p.mass22 * At * tilde(p.Om) -
+                tilde(A * (p.mass21 * (At * p.V))) - tilde(A * (p.mass22 * (At * p.Om))) + c * (A * p.mass22 * At);
+}
+// element.jl:3074-3090
+template <class T> void newmark_element_residual(const Problem& P, const Indices& idx, const T* x, int64_t ie, const DynParams& D, const NewmarkParams& N,
+                                                 T* resid) {
+    M3<T> Bd;
+    DynElem<T> p = newmark_element_properties(P, idx, x, ie, D, N, Bd);
+    V3<T> ru, rth;
+    compatibility_residuals(p, ru, rth);
+    Resultants<T> r = dynamic_element_resultants(P, p, ie);
+    insert_element_residuals(P, idx, ie, ru, rth, r, resid);
+}
+// shared tail of steady_element_jacobian / newmark_element_jacobian: insert_dynamic_element_jacobians! (element.jl:2685-2759)
+template <class T, class J> void insert_dynamic_element_jacobians(const Problem& P, const Indices& idx, int64_t ie, const DynElem<T>& p,
+                                                                  const DynCompatJac<T>& c, const DynResultantJac<T>& r, J& jac) {
+    insert_static_element_jacobians(P, idx, ie, p, c, r, jac);
+    T fs = T(P.force_scaling);
+    int64_t icol1 = idx.icol_point[P.start[ie] - 1] - 1, icol2 = idx.icol_point[P.stop[ie] - 1] - 1;
+    int64_t irow = idx.irow_elem[ie] - 1;
+    set33(jac, irow, icol1 + 6, c.ru_V1); set33(jac, irow, icol1 + 9, c.ru_Om1);
+    set33(jac, irow, icol2 + 6, c.ru_V2); set33(jac, irow, icol2 + 9, c.ru_Om2);
+    set33(jac, irow + 3, icol1 + 9, c.rth_Om1); set33(jac, irow + 3, icol2 + 9, c.rth_Om2);
+    int64_t irow1 = idx.irow_point[P.start[ie] - 1] - 1;
+    sub33m(jac, irow1, icol1, (r.F1_u1 * p.u1_u1) / fs); sub33m(jac, irow1, icol2, (r.F1_u2 * p.u2_u2) / fs);
+    sub33m(jac, irow1, icol1 + 6, r.F1_V1 / fs); sub33m(jac, irow1, icol1 + 9, r.F1_Om1 / fs);
+    sub33m(jac, irow1, icol2 + 6, r.F1_V2 / fs); sub33m(jac, irow1, icol2 + 9, r.F1_Om2 / fs);
+    sub33m(jac, irow1 + 3, icol1, (r.M1_u1 * p.u1_u1) / fs); sub33m(jac, irow1 + 3, icol2, (r.M1_u2 * p.u2_u2) / fs);
+    sub33m(jac, irow1 + 3, icol1 + 6, r.M1_V1 / fs); sub33m(jac, irow1 + 3, icol1 + 9, r.M1_Om1 / fs);
+    sub33m(jac, irow1 + 3, icol2 + 6, r.M1_V2 / fs); sub33m(jac, irow1 + 3, icol2 + 9, r.M1_Om2 / fs);
+    int64_t irow2 = idx.irow_point[P.stop[ie] - 1] - 1;
+    add33(jac, irow2, icol1, (r.F2_u1 * p.u1_u1) / fs); add33(jac, irow2, icol2, (r.F2_u2 * p.u2_u2) / fs);
+    add33(jac, irow2, icol1 + 6, r.F2_V1 / fs); add33(jac, irow2, icol1 + 9, r.F2_Om1 / fs);
+    add33(jac, irow2, icol2 + 6, r.F2_V2 / fs); add33(jac, irow2, icol2 + 9, r.F2_Om2 / fs);
+    add33(jac, irow2 + 3, icol1, (r.M2_u1 * p.u1_u1) / fs); add33(jac, irow2 + 3, icol2, (r.M2_u2 * p.u2_u2) / fs);
+    add33(jac, irow2 + 3, icol1 + 6, r.M2_V1 / fs); add33(jac, irow2 + 3, icol1 + 9, r.M2_Om1 / fs);
+    add33(jac, irow2 + 3, icol2 + 6, r.M2_V2 / fs); add33(jac, irow2 + 3, icol2 + 9, r.M2_Om2 / fs);
+}
+// element.jl:3271-3292
+template <class T, class J> void newmark_element_jacobian(const Problem& P, const Indices& idx, const T* x, int64_t ie, const DynParams& D,
+                                                          const NewmarkParams& N, J& jac) {
+    M3<T> Bd;
+    DynElem<T> p = newmark_element_properties(P, idx, x, ie, D, N, Bd);
+    newmark_element_jacobian_properties(P, ie, p, Bd, N);
+    DynCompatJac<T> c = dynamic_compatibility_jacobians(p);
+    DynResultantJac<T> r = steady_element_resultant_jacobians(P, p, ie);   // = dynamic_element_resultant_jacobians + unused ab/αb parts
+    insert_dynamic_element_jacobians(P, idx, ie, p, c, r, jac);
+}
+// system.jl:530-554
+template <class T> void newmark_system_residual(const Problem& P, const Indices& idx, const DynParams& D, const NewmarkParams& N, const T* x, T* resid) {
+    for (int64_t ip = 0; ip < P.np; ip++) newmark_point_residual(P, idx, x, ip, D, N, resid);
+    for (int64_t ie = 0; ie < P.ne; ie++) newmark_element_residual(P, idx, x, ie, D, N, resid);
+    if (P.two_dimensional) two_dimensional_residual(idx.nstates, x, resid);
+}
+// system.jl:829-852
+template <class T, class J> void newmark_system_jacobian(const Problem& P, const Indices& idx, const DynParams& D, const NewmarkParams& N, const T* x, J& jac) {
+    jac.zero();
+    for (int64_t ip = 0; ip < P.np; ip++) newmark_point_jacobian(P, idx, x, ip, D, N, jac);
+    for (int64_t ie = 0; ie < P.ne; ie++) newmark_element_jacobian(P, idx, x, ie, D, N, jac);
+    if (P.two_dimensional) two_dimensional_jacobian<T>(idx.nstates, jac);
+}
+
 }  // namespace gxo

@@ -343,3 +343,80 @@ int gxo_steady_solve_batch(int64_t nbatch, const gxo_problem* q0, const gxo_dyn*
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- Newmark time marching ----
+extern "C" {
+
+int gxo_newmark_residual(const gxo_problem* q, const gxo_dyn* d, const double* init, double dt, const double* x, double* r) {
+    Problem P = to_problem(q); DynParams D = to_dyn(d);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    NewmarkParams N; N.init = init; N.dt = dt;
+    newmark_system_residual<double>(P, idx, D, N, x, r);
+    return 0;
+}
+int gxo_newmark_jacobian(const gxo_problem* q, const gxo_dyn* d, const double* init, double dt, const double* x, double* J, int complex_step) {
+    Problem P = to_problem(q); DynParams D = to_dyn(d);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    NewmarkParams N; N.init = init; N.dt = dt;
+    int64_t n = idx.nstates;
+    if (!complex_step) { DenseMat<double> M{n, J}; newmark_system_jacobian<double>(P, idx, D, N, x, M); return 0; }
+    const double h = 1e-30;
+    std::vector<cplx> xc(n), rc(n);
+    for (int64_t j = 0; j < n; j++) {
+        for (int64_t i = 0; i < n; i++) xc[i] = cplx(x[i], 0);
+        xc[j] += cplx(0, h);
+        for (int64_t i = 0; i < n; i++) rc[i] = cplx(0, 0);
+        newmark_system_residual<cplx>(P, idx, D, N, xc.data(), rc.data());
+        for (int64_t i = 0; i < n; i++) J[i + n * j] = rc[i].imag() / h;
+    }
+    return 0;
+}
+
+// time_domain_analysis! with a given initial state (src/analyses.jl:2600-2790), one instance.
+//   tvec: nt times.  bc_t: nt x np x 18 prescribed values per time (NULL: constant = q->bc).  x0: nstates.  rates0: np x 12
+//   (udot, θdot, Vdot, Ωdot of the initial state).  x_hist: nt x nstates (row 0 = x0).  iters: nt (iters[0] = 0).
+//   Returns the number of time levels completed (stops early when a step does not converge).
+int64_t gxo_newmark_run(const gxo_problem* q, const gxo_dyn* d, const gxo_opts* opts, int64_t nt, const double* tvec, const double* bc_t,
+                        const double* x0, const double* rates0, double* x_hist, int32_t* iters, int32_t* converged) {
+    Problem P = to_problem(q); DynParams D = to_dyn(d);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    int64_t kl, ku; dynamic_bandwidth(P, idx, kl, ku);
+    int64_t n = idx.nstates;
+    NewtonOpts o = to_opts(opts);
+    std::vector<double> x(x0, x0 + n), F(n), paug(12 * P.np, 0.0);
+    std::copy(x.begin(), x.end(), x_hist);
+    iters[0] = 0; *converged = 1;
+    BandMat J; J.init(n, kl, ku);
+    int64_t done = 1;
+    for (int64_t it = 1; it < nt; it++) {
+        double dt = tvec[it] - tvec[it - 1];
+        if (bc_t) P.bc = bc_t + it * P.np * 18;
+        for (int64_t ip = 0; ip < P.np; ip++) {
+            V3<double> u, th;
+            int64_t icol = idx.icol_point[ip] - 1;
+            point_displacement(P, x.data(), ip, icol, u, th);
+            V3<double> V = ld3(x.data(), icol + 6), Om = ld3(x.data(), icol + 9);
+            double* pa = &paug[12 * ip];
+            V3<double> r[4];
+            if (it <= 1) { for (int k = 0; k < 4; k++) r[k] = cvec<double>(rates0 + 12 * ip + 3 * k); }
+            else {
+                double c = 2.0 / (tvec[it - 1] - tvec[it - 2]);
+                r[0] = c * u - cvec<double>(pa); r[1] = c * th - cvec<double>(pa + 3); r[2] = c * V - cvec<double>(pa + 6); r[3] = c * Om - cvec<double>(pa + 9);
+            }
+            double c = 2.0 / dt;
+            V3<double> s[4] = {c * u + r[0], c * th + r[1], c * V + r[2], c * Om + r[3]};
+            for (int k = 0; k < 4; k++) for (int i = 0; i < 3; i++) pa[3 * k + i] = s[k][i];
+        }
+        NewmarkParams N; N.init = paug.data(); N.dt = dt;
+        auto rf = [&](const double* xx, double* FF) { newmark_system_residual<double>(P, idx, D, N, xx, FF); };
+        auto jf = [&](const double* xx, BandMat& JJ) { newmark_system_jacobian<double>(P, idx, D, N, xx, JJ); };
+        NewtonResult res = newton_solve(n, x.data(), F.data(), J, rf, jf, o);
+        std::copy(x.begin(), x.end(), x_hist + it * n);
+        iters[it] = (int32_t)res.iters;
+        done = it + 1;
+        if (!res.converged) { *converged = 0; break; }
+    }
+    return done;
+}
+
+}  // extern "C"

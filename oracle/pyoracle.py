@@ -222,3 +222,37 @@ def steady_solve_batch(pk0: Packed, nbatch, dyns, gravity=None, force_scaling=No
     lib().gxo_steady_solve_batch(C.c_int64(nbatch), C.byref(pk0.c), arr, _p(g), _p(fs), C.byref(o), _p(x0a), _p(x), _p(conv),
                                  _p(its), _p(rinf), int(nthreads))
     return dict(x=x, converged=conv, iters=its, resid_inf=rinf)
+
+
+# ---------------------------------------------------------------- Newmark time marching ----
+def newmark_residual(pk: Packed, dyn: Dyn, init, dt, x):
+    x = np.ascontiguousarray(x, float)
+    init = np.ascontiguousarray(init, float)
+    r = np.zeros_like(x)
+    lib().gxo_newmark_residual(C.byref(pk.c), C.byref(dyn), _p(init), C.c_double(dt), _p(x), _p(r))
+    return r
+
+
+def newmark_jacobian(pk: Packed, dyn: Dyn, init, dt, x, complex_step=False):
+    x = np.ascontiguousarray(x, float)
+    init = np.ascontiguousarray(init, float)
+    n = len(x)
+    J = np.zeros((n, n), order="F")
+    lib().gxo_newmark_jacobian(C.byref(pk.c), C.byref(dyn), _p(init), C.c_double(dt), _p(x), _p(J), int(complex_step))
+    return J
+
+
+def newmark_run(pk: Packed, dyn: Dyn, tvec, x0, rates0, bc_t=None, **kw):
+    """time_domain_analysis! from a given initial state.  rates0: [np,12] = udot, θdot, Vdot, Ωdot at t0.  bc_t: [nt,np,18] or None."""
+    tvec = np.ascontiguousarray(tvec, float)
+    nt = len(tvec)
+    n = nstates(pk, static=False)
+    xh = np.zeros((nt, n))
+    its = np.zeros(nt, np.int32)
+    conv = C.c_int32(0)
+    o = make_opts(**kw)
+    bct = None if bc_t is None else np.ascontiguousarray(bc_t, float)
+    lib().gxo_newmark_run.restype = C.c_int64
+    done = lib().gxo_newmark_run(C.byref(pk.c), C.byref(dyn), C.byref(o), C.c_int64(nt), _p(tvec), _p(bct), _p(np.ascontiguousarray(x0, float)),
+                                 _p(np.ascontiguousarray(rates0, float)), _p(xh), _p(its), C.byref(conv))
+    return dict(x=xh, iters=its, converged=bool(conv.value), steps_done=int(done))
