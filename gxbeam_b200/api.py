@@ -45,7 +45,8 @@ class Stats(C.Structure):
 EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "gxb_topology", "gxb_pattern", "gxb_set_batch",
            "gxb_set_elements", "gxb_set_points", "gxb_set_bc", "gxb_set_dloads", "gxb_set_pmass", "gxb_set_body",
            "gxb_set_motion", "gxb_static_solve", "gxb_steady_solve", "gxb_steady_solve_resident", "gxb_upload_x0",
-           "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction"]
+           "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction",
+           "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian"]
 
 _lib = None
 
@@ -222,6 +223,40 @@ class Context:
         return r, J
 
     residual_jacobian = static_residual_jacobian
+
+    def newmark_residual_jacobian(self, init, dt, x, opts=None):
+        o = opts or make_opts()
+        x = _f64(x).reshape(self.nbatch, self.n)
+        init = _f64(init).reshape(self.nbatch, self.np, 12)
+        r = np.empty_like(x)
+        brow, _ = self.pattern()
+        J = np.empty((self.nbatch, len(brow), 9))
+        self._ck(self.lib.gxb_newmark_residual_jacobian(self.h, C.byref(o), _ptr(init), C.c_double(dt), _ptr(x), _ptr(r), _ptr(J)))
+        return r, J
+
+    # --- time marching ---
+    def set_bc_series(self, point, field, values):
+        """Time-varying prescribed values: values[b, step, k] goes to field[k] (0..17: u,theta,F,M,Ff,Mf) of point[k] (1-based)."""
+        v = _f64(values)
+        nb, nt, K = v.shape
+        assert nb == self.nbatch
+        pt = np.ascontiguousarray(point, dtype=np.int32)
+        fd = np.ascontiguousarray(field, dtype=np.int32)
+        self._ck(self.lib.gxb_set_bc_series(self.h, C.c_int64(nt), C.c_int32(K), _ptr(pt), _ptr(fd), _ptr(v)))
+
+    def newmark_run(self, tvec, x0, rates0, opts=None, save_every=1, want_history=True):
+        """time_domain_analysis! from the initial state (x0 [nb,n], rates0 [nb,np,12] = udot, θdot, Vdot, Ωdot)."""
+        o = opts or make_opts()
+        tvec = _f64(tvec)
+        nt = len(tvec)
+        nb, n = self.nbatch, self.n
+        nsave = (nt - 1) // save_every + 1
+        xh = np.empty((nb, nsave, n)) if want_history else None
+        steps = np.empty(nb, np.int32); itot = np.empty(nb, np.int32); conv = np.empty(nb, np.int32)
+        self._ck(self.lib.gxb_newmark_run(self.h, C.byref(o), C.c_int64(nt), _ptr(tvec), _ptr(_f64(x0).reshape(nb, n)),
+                                          _ptr(_f64(rates0).reshape(nb, self.np, 12)), C.c_int64(save_every), _ptr(xh), _ptr(steps),
+                                          _ptr(itot), _ptr(conv)))
+        return dict(x=xh, steps_done=steps, iters_total=itot, converged=conv.astype(bool))
 
     def static_newton_direction(self, x, opts=None):
         o = opts or make_opts()

@@ -25,6 +25,9 @@ struct DynArgs {
     const double* pxS;        // [b][3][N+1]  point coordinates Δx
     const double* motion;     // [b][12]      vb, ωb, ab, αb
     int chunk;                // stations per tile flush (shared-memory tile holds `chunk` stations)
+    // Newmark time marching (MODE 1): rate initialisation terms `paug` (analyses.jl:2693-2738) and 2/dt
+    const double* init;       // [b][12][N+1] udot_init, θdot_init, Vdot_init, Ωdot_init
+    double c2dt;              // 2/dt
 };
 
 GXD void dblk(double* t, int s, const m3& B) {
@@ -64,8 +67,10 @@ GXD m3 mul3c(const Rot& R, v3 w) { return cols(R.C1 * w, R.C2 * w, R.C3 * w); } 
 #define GXB_PASS_BEGIN(c0)  for (int c0 = 0; c0 < NP; c0 += A.chunk) { const int cnt_ = min(A.chunk, NP - c0);
 #define GXB_PASS_END        }
 
-template <bool WANT_J>
-__device__ void steady_station(const DynArgs& A, int b, int i, double* smem) {
+// MODE 0: steady state (udot = θdot = 0, Vdot = ab + αb x (Δx + u), Ωdot = αb)
+// MODE 1: Newmark step  (xdot = 2/dt x - xdot_init for u, θ, V, Ω; point.jl:766-795, element.jl:381-412)
+template <bool WANT_J, int MODE>
+__device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
     const StaticArgs& S = A.s;
     const int N = S.N, NP = N + 1;
     double* xch = smem;                                             // [blockDim][6]
@@ -81,8 +86,11 @@ __device__ void steady_station(const DynArgs& A, int b, int i, double* smem) {
     v3 g = mk(0, 0, 0);
     if (S.has_grav && S.grav) g = mk(S.grav[3 * b], S.grav[3 * b + 1], S.grav[3 * b + 2]);
     const double* mo = A.motion + 12 * (size_t)b;
-    const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]), ab = mk(mo[6], mo[7], mo[8]), alb = mk(mo[9], mo[10], mo[11]);
+    const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]);
+    const v3 ab = MODE == 0 ? mk(mo[6], mo[7], mo[8]) : mk(0, 0, 0), alb = MODE == 0 ? mk(mo[9], mo[10], mo[11]) : mk(0, 0, 0);
     const m3 wbt = tilde(wb);
+    const double c2 = MODE == 1 ? A.c2dt : 0.0;
+    const double* ini = (MODE == 1) ? A.init + ((size_t)b * 12) * NP : nullptr;   // field f of point p at ini[f*NP + p]
 
     // ---- point i (point.jl:630-672): displacements, loads, velocities ----
     v3 u1 = mk(0, 0, 0), th1 = u1, Fp = u1, Mp = u1, V1 = u1, Om1 = u1, dxp = u1;
@@ -112,7 +120,7 @@ __device__ void steady_station(const DynArgs& A, int b, int i, double* smem) {
     double L = 0.0;
     m3 Cab = zero33(), CtCab = zero33();
     Rot R;
-    v3 th = mk(0, 0, 0), F = th, M = th, Le1g = th, kap = th, u2 = th, th2 = th, V = th, Om = th, Vdot = th, Pm = th, H = th;
+    v3 th = mk(0, 0, 0), F = th, M = th, Le1g = th, kap = th, u2 = th, th2 = th, V = th, Om = th, Vdot = th, Omdot = th, Pm = th, H = th;
     v3 mth2 = mk(1, 1, 1), mu2 = mth2;
     v3 ru = th, rth = th, F1 = th, M1 = th, F2 = th, M2 = th;
     v3 f1f = th, f2f = th, m1f = th, m2f = th, CtCabTg = th;
@@ -166,14 +174,26 @@ __device__ void steady_station(const DynArgs& A, int b, int i, double* smem) {
         }
         // inertial loads (element.jl:138-155, 1901-1919)
         const v3 dxe = ldv(A.exS + ((size_t)b * 3) * N + i, N);
-        Vdot = ab + cross(alb, dxe + u);
+        if (MODE == 0) { Vdot = ab + cross(alb, dxe + u); Omdot = alb; }
+        else {
+            const v3 V1d = c2 * V1 - ldv(ini + 6 * NP + i, NP), O1d = c2 * Om1 - ldv(ini + 9 * NP + i, NP);
+            const v3 V2d = c2 * V2 - ldv(ini + 6 * NP + i + 1, NP), O2d = c2 * Om2 - ldv(ini + 9 * NP + i + 1, NP);
+            Vdot = 0.5 * (V1d + V2d); Omdot = 0.5 * (O1d + O2d);
+        }
         {
             const m3 m11 = ldm(es + 46 * N, N), m12 = ldm(es + 55 * N, N), m21 = ldm(es + 64 * N, N), m22 = ldm(es + 73 * N, N);
-            const v3 cV = tmul(CtCab, V), cO = tmul(CtCab, Om), cVd = tmul(CtCab, Vdot), cOd = tmul(CtCab, alb);
+            const v3 cV = tmul(CtCab, V), cO = tmul(CtCab, Om), cVd = tmul(CtCab, Vdot), cOd = tmul(CtCab, Omdot);
             Pm = CtCab * (m11 * cV) + CtCab * (m12 * cO);
             H = CtCab * (m21 * cV) + CtCab * (m22 * cO);
-            const v3 Pdot = CtCab * (m11 * cVd) + CtCab * (m12 * cOd);
-            const v3 Hdot = CtCab * (m21 * cVd) + CtCab * (m22 * cOd);
+            v3 Pdot = CtCab * (m11 * cVd) + CtCab * (m12 * cOd);
+            v3 Hdot = CtCab * (m21 * cVd) + CtCab * (m22 * cOd);
+            if (MODE == 1) {
+                // CtCabdot = tilde(Ω - ωb) CtCab =: W A ;  A m Bᵀ V = -A m Aᵀ (W x V),  B m Aᵀ V = W x (A m Aᵀ V)   (element.jl:397-407)
+                const v3 W = Om - wb;
+                const v3 cWV = tmul(CtCab, cross(W, V)), cWO = tmul(CtCab, cross(W, Om));
+                Pdot = Pdot - (CtCab * (m11 * cWV) + CtCab * (m12 * cWO)) + cross(W, Pm);
+                Hdot = Hdot - (CtCab * (m21 * cWV) + CtCab * (m22 * cWO)) + cross(W, H);
+            }
             v3 tf = cross(wb, Pm) + Pdot;
             F1 = F1 - 0.5 * tf; F2 = F2 + 0.5 * tf;
             v3 tm = cross(wb, H) + cross(V, Pm) + Hdot;
@@ -202,8 +222,12 @@ __device__ void steady_station(const DynArgs& A, int b, int i, double* smem) {
         }
         // velocity rows (point.jl:1658-1666): rV = V - vb - ωb x (Δx + u),  rΩ = Qinv C (Ω - ωb)
         Cp = rot_C(th1); Qp = rot_Qinv_from_c(rot_scaling(th1) * th1);
-        const v3 rV = V1 - vb - cross(wb, dxp) - cross(wb, u1);
-        const v3 rO = Qp * (Cp * (Om1 - wb));
+        v3 rV = V1 - vb - cross(wb, dxp) - cross(wb, u1);
+        v3 rO = Qp * (Cp * (Om1 - wb));
+        if (MODE == 1) {     // - udot, - θdot with xdot = 2/dt x - xdot_init   (point.jl:776-777, 1663-1664)
+            rV = rV - (c2 * u1 - ldv(ini + i, NP));
+            rO = rO - (c2 * th1 - ldv(ini + 3 * NP + i, NP));
+        }
         double rv[6] = {rV.x, rV.y, rV.z, rO.x, rO.y, rO.z};
 #pragma unroll
         for (int k = 0; k < 6; k++) rp[6 + k] = (S.two_d && k >= 2 && k <= 4) ? x[18 * i + 6 + k] : rv[k];
@@ -223,21 +247,41 @@ __device__ void steady_station(const DynArgs& A, int b, int i, double* smem) {
         const m3 m11 = ldm(es + 46 * N, N), m12 = ldm(es + 55 * N, N), m21 = ldm(es + 64 * N, N), m22 = ldm(es + 73 * N, N);
         const m3 CtCabT = transpose(CtCab);
         const m3 A11 = (CtCab * m11) * CtCabT, A12 = (CtCab * m12) * CtCabT, A21 = (CtCab * m21) * CtCabT, A22 = (CtCab * m22) * CtCabT;
-        const v3 cV = tmul(CtCab, V), cO = tmul(CtCab, Om), cVd = tmul(CtCab, Vdot), cOd = tmul(CtCab, alb);
-        const m3 cthV = tmul(Cab, mul3c(R, V)), cthO = tmul(Cab, mul3c(R, Om)), cthVd = tmul(Cab, mul3c(R, Vdot)), cthOd = tmul(Cab, mul3c(R, alb));
+        const v3 cV = tmul(CtCab, V), cO = tmul(CtCab, Om), cVd = tmul(CtCab, Vdot), cOd = tmul(CtCab, Omdot);
+        const m3 cthV = tmul(Cab, mul3c(R, V)), cthO = tmul(Cab, mul3c(R, Om)), cthVd = tmul(Cab, mul3c(R, Vdot)), cthOd = tmul(Cab, mul3c(R, Omdot));
         const m3 P_th = mul3t(R, Cab * (m11 * cV + m12 * cO)) + CtCab * (m11 * cthV) + CtCab * (m12 * cthO);
         const m3 H_th = mul3t(R, Cab * (m21 * cV + m22 * cO)) + CtCab * (m21 * cthV) + CtCab * (m22 * cthO);
         const m3 Pd_th = mul3t(R, Cab * (m11 * cVd)) + mul3t(R, Cab * (m12 * cOd)) + CtCab * (m11 * cthVd) + CtCab * (m12 * cthOd);
         const m3 Hd_th = mul3t(R, Cab * (m21 * cVd)) + mul3t(R, Cab * (m22 * cOd)) + CtCab * (m21 * cthVd) + CtCab * (m22 * cthOd);
         const m3 albt = tilde(alb), Vt = tilde(V);
-        hFu = 0.25 * (A11 * albt);
-        hFth = 0.25 * (wbt * P_th + Pd_th);
-        hFV = 0.25 * (wbt * A11);
-        hFO = 0.25 * (wbt * A12);
-        hMu = 0.25 * (A21 * albt);
-        hMth = 0.25 * (wbt * H_th + Vt * P_th + Hd_th);
-        hMV = 0.25 * (wbt * A21 + Vt * A11 - tilde(Pm));
-        hMO = 0.25 * (wbt * A22 + Vt * A12);
+        m3 PdV = zero33(), PdO = zero33(), HdV = zero33(), HdO = zero33();
+        m3 Pd_th_x = Pd_th, Hd_th_x = Hd_th;
+        if (MODE == 1) {
+            // element.jl:1049-1112 with B = CtCabdot = W A (W = tilde(Ω - ωb)):
+            //   Pdot_θ += W mul3t(Cab m Aᵀ V) + B m Cabᵀ mul3c(V) + mul3t(Cab m Bᵀ V) - A m Cabᵀ mul3c(W V)   (and the Ω / m12 twins)
+            const v3 Wv = Om - wb;
+            const m3 Wt = tilde(Wv);
+            const m3 Bm = Wt * CtCab;                       // CtCabdot
+            const v3 bV = tmul(Bm, V), bO = tmul(Bm, Om);   // Bᵀ V, Bᵀ Ω
+            const m3 cthWV = tmul(Cab, mul3c(R, Wt * V)), cthWO = tmul(Cab, mul3c(R, Wt * Om));
+            Pd_th_x = Pd_th + Wt * mul3t(R, Cab * (m11 * cV + m12 * cO)) + Bm * (m11 * cthV) + Bm * (m12 * cthO) +
+                      mul3t(R, Cab * (m11 * bV + m12 * bO)) - CtCab * (m11 * cthWV) - CtCab * (m12 * cthWO);
+            Hd_th_x = Hd_th + Wt * mul3t(R, Cab * (m21 * cV + m22 * cO)) + Bm * (m21 * cthV) + Bm * (m22 * cthO) +
+                      mul3t(R, Cab * (m21 * bV + m22 * bO)) - CtCab * (m21 * cthWV) - CtCab * (m22 * cthWO);
+            const m3 BmT = transpose(Bm), Ot = tilde(Om);
+            PdV = (CtCab * m11) * BmT + (Bm * m11) * CtCabT + c2 * A11;
+            PdO = (CtCab * m12) * BmT + (Bm * m12) * CtCabT + A11 * Vt + A12 * Ot - tilde(A11 * V) - tilde(A12 * Om) + c2 * A12;
+            HdV = (CtCab * m21) * BmT + (Bm * m21) * CtCabT + c2 * A21;
+            HdO = (CtCab * m22) * BmT + (Bm * m22) * CtCabT + A21 * Vt + A22 * Ot - tilde(A21 * V) - tilde(A22 * Om) + c2 * A22;
+        }
+        hFu = (MODE == 0) ? 0.25 * (A11 * albt) : zero33();
+        hFth = 0.25 * (wbt * P_th + Pd_th_x);
+        hFV = 0.25 * (wbt * A11 + PdV);
+        hFO = 0.25 * (wbt * A12 + PdO);
+        hMu = (MODE == 0) ? 0.25 * (A21 * albt) : zero33();
+        hMth = 0.25 * (wbt * H_th + Vt * P_th + Hd_th_x);
+        hMV = 0.25 * (wbt * A21 + Vt * A11 - tilde(Pm) + HdV);
+        hMO = 0.25 * (wbt * A22 + Vt * A12 + HdO);
     }
 
     // =================== pass P1: force rows of point i (rows 18i+0..2) ===================
@@ -380,7 +424,9 @@ __device__ void steady_station(const DynArgs& A, int b, int i, double* smem) {
         const bool mine_in = valid && i >= c0 && i < c0 + cnt_;
         if (mine_in) {
             dtile_clear(mytile);
-            dblk(mytile, 12, colmask(-wbt, mu1));                 // rV_u u_u = -tilde(ωb) u_u
+            m3 rVu = -wbt;
+            if (MODE == 1) { rVu.a[0] -= c2; rVu.a[4] -= c2; rVu.a[8] -= c2; }   // - udot_u = -(2/dt) I   (point.jl:1708-1720)
+            dblk(mytile, 12, colmask(rVu, mu1));                  // rV_u u_u
             dblk(mytile, 18, eye33());                            // rV_V
             if (S.two_d) dtile_planar(mytile, 0, 18);
         }
@@ -397,6 +443,7 @@ __device__ void steady_station(const DynArgs& A, int b, int i, double* smem) {
             const v3 dO = Om1 - wb;
             m3 Qi;
             m3 rOth = rot_Qinv_dQinv_b(th1, Rp.C * dO, Qi) + Qi * mul3c(Rp, dO);
+            if (MODE == 1) { rOth.a[0] -= c2; rOth.a[4] -= c2; rOth.a[8] -= c2; }
             dblk(mytile, 15, colmask(rOth, mth1));                // rΩ_θ θ_θ
             dblk(mytile, 21, Qi * Rp.C);                          // rΩ_Ω = Qinv C
             if (S.two_d) dtile_planar(mytile, 3, 18);

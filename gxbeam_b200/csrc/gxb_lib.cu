@@ -63,6 +63,10 @@ struct gxb_ctx {
     int64_t nbatch = 0;
     double *d_elemS = nullptr, *d_bcS = nullptr, *d_dlS = nullptr, *d_pmS = nullptr, *d_grav = nullptr, *d_fs = nullptr, *d_xyz = nullptr;
     double *d_exS = nullptr, *d_motion = nullptr;     // dynamic only: element midpoints [b][3][N], body motion [b][12]
+    double *d_paug = nullptr, *d_rates0 = nullptr, *d_series = nullptr; int *d_ser_point = nullptr, *d_ser_field = nullptr;
+    int64_t ser_nt = 0; int ser_K = 0;
+    int mode = 0;            // 0: steady residual, 1: Newmark residual (set by the time-marching driver)
+    double c2dt = 0.0;
     bool body_state = false;                          // some DOF has pd & pl (body-frame acceleration would be a state)
     int W = 30, UW = 32, KLB = 2, rows_per_station = 12;
     int has_grav = 0;
@@ -121,11 +125,47 @@ template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble(StaticA
     static_station<WANT_J>(A, b, threadIdx.x, asm_smem);
 }
 
-template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble_steady(DynArgs A) {
+template <bool WANT_J, int MODE> __global__ void __launch_bounds__(256) k_assemble_dynamic(DynArgs A) {
     extern __shared__ __align__(16) double asm_smem[];
     const int b = blockIdx.x;
     if (A.s.status && A.s.status[b] != A.s.want_status) return;
-    steady_station<WANT_J>(A, b, threadIdx.x, asm_smem);
+    dynamic_station<WANT_J, MODE>(A, b, threadIdx.x, asm_smem);
+}
+
+// Newmark bookkeeping (src/analyses.jl:2693-2738): per point, rates at the previous time level from the old initialisation
+// terms (or the initial state on the first step), then the new terms  2/dt x + xdot.  paug layout [b][12][NP].
+__global__ void k_newmark_paug(const double* __restrict__ x, const double* __restrict__ bcS, const unsigned short* __restrict__ flags,
+                               double* __restrict__ paug, const double* __restrict__ rates0, int NP, int n, int64_t nbatch,
+                               int first, double c_prev, double c_new) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * NP) return;
+    int64_t b = t / NP; int p = (int)(t % NP);
+    const double* xp = x + b * n + 18 * p;
+    const double* bc = bcS + ((size_t)b * 18) * NP + p;
+    const unsigned fl = flags[p];
+    double* pa = paug + ((size_t)b * 12) * NP + p;
+    double s[12];
+    for (int k = 0; k < 6; k++) s[k] = (fl & (1u << k)) ? bc[k * NP] : xp[k];      // u, θ honour prescribed displacements at the new time
+    for (int k = 0; k < 6; k++) s[6 + k] = xp[6 + k];                              // V, Ω
+    for (int k = 0; k < 12; k++) {
+        double rate = first ? rates0[((size_t)b * NP + p) * 12 + k] : c_prev * s[k] - pa[(size_t)k * NP];
+        pa[(size_t)k * NP] = c_new * s[k] + rate;
+    }
+}
+// time-varying prescribed values: bcS[b][field[k]][point[k]] = series[b][step][k]
+__global__ void k_apply_bc_series(double* __restrict__ bcS, const double* __restrict__ series, const int* __restrict__ point,
+                                  const int* __restrict__ field, int K, int NP, int64_t nt, int64_t step, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * K) return;
+    int64_t b = t / K; int k = (int)(t % K);
+    bcS[((size_t)b * 18 + field[k]) * NP + point[k]] = series[((size_t)b * nt + step) * K + k];
+}
+// xhist[b][slot][:] = x[b][:]
+__global__ void k_save_state(const double* __restrict__ x, double* __restrict__ xhist, int n, int64_t nsave, int64_t slot, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * n) return;
+    int64_t b = t / n; int c = (int)(t % n);
+    xhist[((size_t)b * nsave + slot) * n + c] = x[t];
 }
 
 struct SolveArgs {
@@ -274,6 +314,8 @@ __global__ void k_extract_blocks(const double* __restrict__ Jrow, const int64_t*
 // ------------------------------------------------------------------------------------------------------------------
 static void free_batch(gxb_ctx* c) {
     cudaFree(c->d_exS); cudaFree(c->d_motion); c->d_exS = c->d_motion = nullptr;
+    cudaFree(c->d_paug); cudaFree(c->d_rates0); cudaFree(c->d_series); cudaFree(c->d_ser_point); cudaFree(c->d_ser_field);
+    c->d_paug = c->d_rates0 = c->d_series = nullptr; c->d_ser_point = c->d_ser_field = nullptr; c->ser_nt = 0; c->ser_K = 0; c->mode = 0;
     cudaFree(c->d_elemS); cudaFree(c->d_bcS); cudaFree(c->d_dlS); cudaFree(c->d_pmS); cudaFree(c->d_grav); cudaFree(c->d_fs); cudaFree(c->d_xyz);
     cudaFree(c->d_x); cudaFree(c->d_xt); cudaFree(c->d_F); cudaFree(c->d_Ft); cudaFree(c->d_p); cudaFree(c->d_J); cudaFree(c->d_U);
     cudaFree(c->ns.status); cudaFree(c->ns.failcode); cudaFree(c->ns.iters); cudaFree(c->ns.fcalls); cudaFree(c->ns.ls_k); cudaFree(c->ns.ls_finite);
@@ -487,6 +529,8 @@ int gxb_set_batch(gxb_ctx* c, int64_t nbatch) {
     if ((rc = dalloc(&c->d_J, nb * n * c->W)) || (rc = dalloc(&c->d_U, nb * n * c->UW))) return rc;
     if (c->kind == 1) {
         if ((rc = dalloc(&c->d_exS, nb * 3 * N)) || (rc = dalloc(&c->d_xyz, nb * 3 * P)) || (rc = dalloc(&c->d_motion, nb * 12))) return rc;
+        if ((rc = dalloc(&c->d_paug, nb * 12 * P)) || (rc = dalloc(&c->d_rates0, nb * 12 * P))) return rc;
+        CK(cudaMemsetAsync(c->d_paug, 0, nb * 12 * P * 8, c->stream));
         CK(cudaMemsetAsync(c->d_xyz, 0, nb * 3 * P * 8, c->stream));
         CK(cudaMemsetAsync(c->d_motion, 0, nb * 12 * 8, c->stream));
     }
@@ -615,7 +659,7 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
         } else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
     } else {
         DynArgs D{};
-        D.s = A; D.exS = c->d_exS; D.pxS = c->d_xyz; D.motion = c->d_motion;
+        D.s = A; D.exS = c->d_exS; D.pxS = c->d_xyz; D.motion = c->d_motion; D.init = c->d_paug; D.c2dt = c->c2dt;
         // the shared-memory tile holds `chunk` stations; longer chains are flushed chunk by chunk
         const size_t budget = 200 * 1024;
         int chunk = (int)std::min<size_t>((size_t)bs, (budget - (size_t)bs * GXB_XCH * 8) / (GXB_DTILE * 8));
@@ -623,9 +667,17 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
         size_t sm = ((size_t)bs * GXB_XCH + (want_j ? (size_t)chunk * GXB_DTILE : 0)) * 8;
         if (want_j) {
             static thread_local size_t configured = 0;
-            if (sm > configured) { CK(cudaFuncSetAttribute(k_assemble_steady<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
-            k_assemble_steady<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
-        } else k_assemble_steady<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+            if (sm > configured) {
+                CK(cudaFuncSetAttribute(k_assemble_dynamic<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                CK(cudaFuncSetAttribute(k_assemble_dynamic<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                configured = sm;
+            }
+            if (c->mode == 0) k_assemble_dynamic<true, 0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+            else k_assemble_dynamic<true, 1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+        } else {
+            if (c->mode == 0) k_assemble_dynamic<false, 0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+            else k_assemble_dynamic<false, 1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+        }
     }
     CK(cudaGetLastError());
     c->stats.launches++; c->stats.n_assemble++;
@@ -683,18 +735,11 @@ int gxb_steady_solve(gxb_ctx* c, const gxb_opts* opts, const double* x0, double*
     if ((rc = gxb_steady_solve_resident(c, opts))) return rc;
     return gxb_fetch(c, x, converged, iters, resid_inf);
 }
-static int solve_resident(gxb_ctx* c, const gxb_opts* opts) {
-    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
-    c->stats = gxb_stats{};
-    Prof prof{c, o.profile != 0};
+// Newton rounds on whatever is in d_xt / status (instances in state TRIAL are evaluated first).  `burst` rounds are launched
+// between two reads of the unfinished-instance counter (kernels early-exit on finished instances, so surplus rounds are cheap).
+static int newton_rounds(gxb_ctx* c, const gxb_opts& o, Prof& prof, int burst) {
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
     int rc;
-    CK(cudaEventRecord(c->ev0, c->stream));
-    if (!c->have_x0) CK(cudaMemsetAsync(c->d_x, 0, nb * n * 8, c->stream));   // reset_state (system.jl:383-386)
-    CK(cudaMemcpyAsync(c->d_xt, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));
-    k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, ST_TRIAL, nb);
-    CK(cudaMemsetAsync(c->ns.failcode, 0, nb * 4, c->stream)); CK(cudaMemsetAsync(c->ns.iters, 0, nb * 4, c->stream));
-    CK(cudaMemsetAsync(c->ns.fcalls, 0, nb * 4, c->stream));
     CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
     // initial value_jacobian!!(df, x0)
     StaticArgs A = make_static_args(c, &o, c->d_xt, c->d_Ft, true, ST_TRIAL, true);
@@ -707,19 +752,38 @@ static int solve_resident(gxb_ctx* c, const gxb_opts* opts) {
         // final residual r(x) is not re-evaluated by the reference; keep F = r(x0) like lsolve! leaves `resid`
         CK(cudaMemcpyAsync(c->d_Ft, c->d_F, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));
         prof.begin(); if ((rc = launch_update(c, &o, 2))) return rc; prof.end(c->stats.ms_update);
-        c->stats.rounds = 1;
-    } else {
-        for (int64_t round = 0;; round++) {
-            CK(cudaMemcpyAsync(c->h_counter, c->d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            if (*c->h_counter == 0) break;
+        c->stats.rounds += 1;
+        return GXB_OK;
+    }
+    for (;;) {
+        CK(cudaMemcpyAsync(c->h_counter, c->d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (*c->h_counter == 0) break;
+        for (int q = 0; q < burst; q++) {
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
             prof.begin(); if ((rc = launch_factor(c, &o, 0))) return rc; prof.end(c->stats.ms_factor);
             prof.begin(); if ((rc = launch_assemble(c, A, true))) return rc; prof.end(c->stats.ms_assemble);
             prof.begin(); if ((rc = launch_update(c, &o, 1))) return rc; prof.end(c->stats.ms_update);
-            c->stats.rounds = round + 1;
+            c->stats.rounds += 1;
         }
     }
+    return GXB_OK;
+}
+
+static int solve_resident(gxb_ctx* c, const gxb_opts* opts) {
+    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    c->stats = gxb_stats{};
+    Prof prof{c, o.profile != 0};
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    int rc;
+    c->mode = 0;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (!c->have_x0) CK(cudaMemsetAsync(c->d_x, 0, nb * n * 8, c->stream));   // reset_state (system.jl:383-386)
+    CK(cudaMemcpyAsync(c->d_xt, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, ST_TRIAL, nb);
+    CK(cudaMemsetAsync(c->ns.failcode, 0, nb * 4, c->stream)); CK(cudaMemsetAsync(c->ns.iters, 0, nb * 4, c->stream));
+    CK(cudaMemsetAsync(c->ns.fcalls, 0, nb * 4, c->stream));
+    if ((rc = newton_rounds(c, o, prof, 1))) return rc;
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->stats.ms_total = ms;
@@ -729,6 +793,103 @@ static int solve_resident(gxb_ctx* c, const gxb_opts* opts) {
     CK(cudaMemcpy(fc.data(), c->ns.fcalls, nb * 4, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < nb; i++) { c->stats.newton_iters += it[i]; c->stats.resid_evals += fc[i]; }
     c->have_x0 = false;
+    return GXB_OK;
+}
+
+// ---- Newmark time marching (time_domain_analysis! from a given initial state, src/analyses.jl:2600-2790) ----
+// per-instance bookkeeping of the time loop: an instance whose step does not converge stops marching (analyses.jl:2781-2790)
+__global__ void k_step_begin(int* status, int* iters, int* fcalls, const int* alive, int64_t nbatch) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= nbatch) return;
+    status[b] = alive[b] ? ST_TRIAL : ST_FAILED;
+    iters[b] = 0; fcalls[b] = 0;
+}
+__global__ void k_step_end(const int* status, const int* iters, int* alive, int* steps_done, int* iters_total, int64_t nbatch) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= nbatch) return;
+    if (!alive[b]) return;
+    steps_done[b] += 1;
+    iters_total[b] += iters[b];
+    if (status[b] != ST_DONE) alive[b] = 0;
+}
+
+int gxb_set_bc_series(gxb_ctx* c, int64_t nt, int32_t K, const int32_t* point, const int32_t* field, const double* values) {
+    NEED_BATCH("gxb_set_bc_series");
+    cudaFree(c->d_series); cudaFree(c->d_ser_point); cudaFree(c->d_ser_field);
+    c->d_series = nullptr; c->d_ser_point = c->d_ser_field = nullptr; c->ser_nt = 0; c->ser_K = 0;
+    if (K == 0 || !values) return GXB_OK;
+    if (nt < 1 || K < 0 || !point || !field) return fail(GXB_ERR_INVALID, "gxb_set_bc_series: bad arguments");
+    std::vector<int> pt(K), fd(K);
+    for (int k = 0; k < K; k++) {
+        if (point[k] < 1 || point[k] > c->np || field[k] < 0 || field[k] >= 18) return fail(GXB_ERR_INVALID, "gxb_set_bc_series: point is 1-based, field in 0..17");
+        pt[k] = point[k] - 1; fd[k] = field[k];
+    }
+    CK(cudaMalloc(&c->d_series, (size_t)c->nbatch * nt * K * 8));
+    CK(cudaMalloc(&c->d_ser_point, K * 4)); CK(cudaMalloc(&c->d_ser_field, K * 4));
+    CK(cudaMemcpy(c->d_series, values, (size_t)c->nbatch * nt * K * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_ser_point, pt.data(), K * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_ser_field, fd.data(), K * 4, cudaMemcpyHostToDevice));
+    c->ser_nt = nt; c->ser_K = K;
+    return GXB_OK;
+}
+
+int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* tvec, const double* x0, const double* rates0,
+                    int64_t save_every, double* x_hist, int32_t* steps_done, int32_t* iters_total, int32_t* converged) {
+    NEED_BATCH("gxb_newmark_run");
+    if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_newmark_run: context topology is not kind=1 (DynamicSystem)");
+    if (nt < 2 || !tvec || !x0 || !rates0) return fail(GXB_ERR_INVALID, "gxb_newmark_run: need nt >= 2, tvec, x0 and the initial rates");
+    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    if (o.structural_damping) return fail(GXB_ERR_UNSUPPORTED, "structural_damping=true is not implemented on the device yet (pass structural_damping=false)");
+    if (o.linear) return fail(GXB_ERR_UNSUPPORTED, "gxb_newmark_run: linear=true is not implemented on the device");
+    if (c->ser_K && c->ser_nt != nt) return fail(GXB_ERR_INVALID, "gxb_newmark_run: the bc series has a different number of time levels");
+    if (save_every < 1) save_every = 1;
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n, P = (size_t)c->np;
+    const int64_t nsave = (nt - 1) / save_every + 1;      // time levels 0, save_every, 2 save_every, ...
+    c->stats = gxb_stats{};
+    Prof prof{c, o.profile != 0};
+    int rc;
+    int *d_alive = nullptr, *d_steps = nullptr, *d_itot = nullptr; double* d_hist = nullptr;
+    CK(cudaMalloc(&d_alive, nb * 4)); CK(cudaMalloc(&d_steps, nb * 4)); CK(cudaMalloc(&d_itot, nb * 4));
+    if (x_hist) CK(cudaMalloc(&d_hist, nb * nsave * n * 8));
+    k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(d_alive, 1, nb);
+    k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(d_steps, 1, nb);
+    CK(cudaMemsetAsync(d_itot, 0, nb * 4, c->stream));
+    CK(cudaMemsetAsync(c->ns.failcode, 0, nb * 4, c->stream));
+    CK(cudaMemcpyAsync(c->d_x, x0, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_rates0, rates0, nb * P * 12 * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_paug, 0, nb * 12 * P * 8, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (d_hist) k_save_state<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_x, d_hist, (int)n, nsave, 0, c->nbatch);
+    c->mode = 1;
+    for (int64_t it = 1; it < nt; it++) {
+        const double dt = tvec[it] - tvec[it - 1];
+        if (!(dt > 0.0)) { c->mode = 0; return fail(GXB_ERR_INVALID, "gxb_newmark_run: tvec must be strictly increasing"); }
+        const double c_prev = it > 1 ? 2.0 / (tvec[it - 1] - tvec[it - 2]) : 0.0;
+        c->c2dt = 2.0 / dt;
+        if (c->ser_K) k_apply_bc_series<<<grid1(nb * c->ser_K, 128), 128, 0, c->stream>>>(c->d_bcS, c->d_series, c->d_ser_point, c->d_ser_field, c->ser_K, (int)P, nt, it, c->nbatch);
+        k_newmark_paug<<<grid1(nb * P, 128), 128, 0, c->stream>>>(c->d_x, c->d_bcS, c->d_flags, c->d_paug, c->d_rates0, (int)P, (int)n, c->nbatch, it == 1, c_prev, c->c2dt);
+        k_step_begin<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, c->ns.iters, c->ns.fcalls, d_alive, c->nbatch);
+        CK(cudaMemcpyAsync(c->d_xt, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));   // initial guess = previous state (analyses.jl:3592)
+        c->stats.launches += 3 + (c->ser_K ? 1 : 0);
+        if ((rc = newton_rounds(c, o, prof, 2))) { c->mode = 0; return rc; }
+        k_step_end<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, c->ns.iters, d_alive, d_steps, d_itot, c->nbatch);
+        c->stats.launches += 1;
+        if (d_hist && it % save_every == 0) { k_save_state<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_x, d_hist, (int)n, nsave, it / save_every, c->nbatch); c->stats.launches += 1; }
+    }
+    c->mode = 0;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->stats.ms_total = ms;
+    std::vector<int> al(nb), itot(nb);
+    CK(cudaMemcpy(al.data(), d_alive, nb * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(itot.data(), d_itot, nb * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nb; i++) c->stats.newton_iters += itot[i];
+    if (converged) for (size_t i = 0; i < nb; i++) converged[i] = al[i];
+    if (iters_total) memcpy(iters_total, itot.data(), nb * 4);
+    if (steps_done) CK(cudaMemcpy(steps_done, d_steps, nb * 4, cudaMemcpyDeviceToHost));
+    if (x_hist) CK(cudaMemcpy(x_hist, d_hist, nb * nsave * n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_alive); cudaFree(d_steps); cudaFree(d_itot); cudaFree(d_hist);
+    CK(cudaGetLastError());
     return GXB_OK;
 }
 
@@ -778,6 +939,20 @@ int gxb_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double* x, dou
     }
     CK(cudaStreamSynchronize(c->stream));
     return GXB_OK;
+}
+
+int gxb_newmark_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double* init, double dt, const double* x, double* r, double* Jblk) {
+    NEED_BATCH("gxb_newmark_residual_jacobian");
+    if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_newmark_residual_jacobian: context topology is not kind=1 (DynamicSystem)");
+    if (!init || !(dt > 0.0)) return fail(GXB_ERR_INVALID, "gxb_newmark_residual_jacobian: need the initialisation terms and dt > 0");
+    int rc = stage_upload(c, init, (size_t)c->nbatch * c->np * 12 * 8); if (rc) return rc;
+    k_pack_transpose<<<grid1(c->nbatch * c->np * 12, 256), 256, 0, c->stream>>>(c->d_stage, c->d_paug, (int)c->np, 12, c->nbatch);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->mode = 1; c->c2dt = 2.0 / dt;
+    rc = gxb_residual_jacobian(c, opts, x, r, Jblk);
+    c->mode = 0;
+    return rc;
 }
 
 int gxb_newton_direction(gxb_ctx* c, const gxb_opts* opts, const double* x, double* p) {

@@ -102,6 +102,20 @@ int gxb_steady_solve(gxb_ctx* ctx, const gxb_opts* opts, const double* x0, doubl
                      double* resid_inf);
 int gxb_steady_solve_resident(gxb_ctx* ctx, const gxb_opts* opts);
 
+/* time_domain_analysis! from a given initial state: Newmark time marching                src/analyses.jl:2600-2790
+ *   per step: prescribed conditions of the new time (gxb_set_bc_series), the `paug` initialisation terms (analyses.jl:2693-2738),
+ *   nlsolve! with newmark_system_residual!/jacobian! (src/system.jl:530-554, 829-852) starting from the previous state.
+ * The initial state is what the reference obtains from initial_condition_analysis! or takes from `initial_state=`
+ * (analyses.jl:2549-2596): x0 (nbatch x nstates) and the point rates udot, θdot, Vdot, Ωdot at t0 (nbatch x np x 12).
+ * tvec: nt times.  Saved time levels: 0, save_every, 2 save_every, ...  -> x_hist (nbatch x nsave x nstates, may be NULL).
+ * steps_done[b]: time levels reached (an instance stops at its first unconverged step, analyses.jl:2781-2790);
+ * iters_total[b]: Newton iterations over all steps; converged[b].  opts->structural_damping must be 0 for now (the reference
+ * defaults to true for time-domain analyses). */
+int gxb_set_bc_series(gxb_ctx* ctx, int64_t nt, int32_t K, const int32_t* point /* 1-based */, const int32_t* field /* 0..17 */,
+                      const double* values /* nbatch x nt x K */);
+int gxb_newmark_run(gxb_ctx* ctx, const gxb_opts* opts, int64_t nt, const double* tvec, const double* x0, const double* rates0,
+                    int64_t save_every, double* x_hist, int32_t* steps_done, int32_t* iters_total, int32_t* converged);
+
 /* The same solve on inputs already resident in HBM (no host<->device traffic): x0 from gxb_upload_x0 or zeros. */
 int gxb_upload_x0(gxb_ctx* ctx, const double* x0 /* or NULL */);
 int gxb_static_solve_resident(gxb_ctx* ctx, const gxb_opts* opts);
@@ -112,6 +126,10 @@ int gxb_get_stats(gxb_ctx* ctx, gxb_stats* st);
  *                                                          src/system.jl:400-418, 663-683 | 427-455, 693-720
  * x: nbatch x nstates.  r: nbatch x nstates.  Jblk: nbatch x nblocks x 9, each 3x3 row-major on gxb_pattern's blocks. */
 int gxb_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* r, double* Jblk);
+/* newmark_system_residual! + newmark_system_jacobian! (src/system.jl:530-554, 829-852) at given states, with the rate
+ * initialisation terms init (nbatch x np x 12: udot_init, θdot_init, Vdot_init, Ωdot_init) and the step size dt. */
+int gxb_newmark_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* init, double dt, const double* x, double* r,
+                                  double* Jblk);
 
 /* One Newton direction p = -(J(x) \ r(x)) per instance (the `linsolve` of analyses.jl:3585), for parity tests of the
  * batched pivoted block-banded LU in isolation.  p: nbatch x nstates. */

@@ -1,0 +1,105 @@
+"""GPU parity tests for Newmark time marching (time_domain_analysis! from a given initial state) vs the CPU oracle.
+structural_damping = False on both sides (the device path does not implement damping yet; the reference's time-domain default is
+True, which the oracle covers on the CPU — tests/test_oracle_newmark.py)."""
+import numpy as np
+import pytest
+
+import cases
+from gxbeam_b200 import api, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import pyoracle as O
+    return O
+
+
+def _ctx(case, motion, nb=1, pts=None):
+    ctx = api.Context(0)
+    ctx.topology(case["start"], case["stop"], case["pd"], case["pl"], kind=1)
+    ctx.set_batch(nb)
+    ctx.set_elements(case["elems"][:nb])
+    ctx.set_points(np.broadcast_to(case["points"], (nb,) + case["points"].shape).copy() if pts is None else pts)
+    ctx.set_bc(case["bc"][:nb])
+    if case.get("dload") is not None:
+        ctx.set_dloads(case["dload"][:nb])
+    g = case.get("gravity")
+    if g is not None:
+        g = np.broadcast_to(np.asarray(g, float).reshape(-1, 3), (nb, 3)).copy()
+    ctx.set_body(g, np.broadcast_to(np.asarray(case["force_scaling"], float).reshape(-1), (nb,)).copy())
+    ctx.set_motion(motion)
+    return ctx
+
+
+@pytest.mark.parametrize("seed,nelem", [(0, 2), (1, 6)])
+def test_newmark_residual_and_jacobian_parity(seed, nelem):
+    O = _oracle()
+    case = cases.random_anisotropic(seed, nelem=nelem, pmass=False)
+    pk = cases.oracle_packed(case)
+    rng = np.random.default_rng(seed + 60)
+    mo = np.zeros(12); mo[:6] = 1e2 * rng.random(6)
+    dyn = O.make_dyn(vb=mo[0:3], wb=mo[3:6])
+    ctx = _ctx(case, mo[None])
+    n, npnt = ctx.n, len(case["points"])
+    brow, bcol = ctx.pattern()
+    init = rng.random((1, npnt, 12)); dt = 0.1 + rng.random()
+    for scale in (1.0, 1e2):
+        x = scale * rng.random((1, n))
+        r, Jb = ctx.newmark_residual_jacobian(init, dt, x)
+        r_ref = O.newmark_residual(pk, dyn, init[0], dt, x[0])
+        J_ref = O.newmark_jacobian(pk, dyn, init[0], dt, x[0])
+        assert np.abs(r[0] - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
+        J = api.blocks_to_dense(n, brow, bcol, Jb[0])
+        assert np.abs(J - J_ref).max() <= 1e-12 * np.abs(J_ref).max()
+    ctx.close()
+
+
+def _gust(nb, nt, tend, seed=1234 + 4):
+    """BASELINE config 4 style ensemble: C1 topology, force pulse A_i tf1(t) in y at point 21 (benchmarks.jl:198-204)."""
+    rng = np.random.default_rng(seed)
+    w = workloads.rotating_blade_batch(nb)
+    tvec = np.linspace(0, tend, nt)
+    amp = 100 * rng.uniform(0.5, 1.5, nb)
+    tf1 = np.where(tvec < 0.2, 0.1 * (1 - np.sin(2 * np.pi * (tvec / 0.4 + 0.25))), 0.0)
+    series = (amp[:, None] * tf1[None, :])[:, :, None]          # [nb, nt, 1]
+    return w, tvec, series
+
+
+def test_time_marching_gust_ensemble_parity():
+    O = _oracle()
+    nb, nt = 8, 41
+    w, tvec, series = _gust(nb, nt, 0.01)
+    # initial state = steady rotating equilibrium with zero rates (time_domain_analysis(...; initial_state = steady state))
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    st = ctx.steady_solve()
+    assert st["converged"].all()
+    ctx.set_bc_series([21], [7], series)                          # Fy of point 21
+    rates0 = np.zeros((nb, 25, 12))
+    res = ctx.newmark_run(tvec, st["x"], rates0, api.make_opts(structural_damping=False))
+    stats = ctx.stats()
+    ctx.close()
+    assert res["converged"].all() and (res["steps_done"] == nt).all()
+    for b in range(nb):
+        pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
+        dyn = O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6], structural_damping=False)
+        bct = np.tile(w["bc"][b][None], (nt, 1, 1))
+        bct[:, 20, 7] = series[b, :, 0]
+        ref = O.newmark_run(pk, dyn, tvec, st["x"][b], rates0[b], bct)
+        assert ref["converged"]
+        assert int(res["iters_total"][b]) == int(ref["iters"].sum())
+        scale = np.abs(ref["x"]).max(axis=0) + 1e-300
+        # per-state-variable relative agreement over the whole history
+        assert (np.abs(res["x"][b] - ref["x"]).max(axis=0) <= 1e-9 * np.maximum(scale, np.abs(ref["x"]).max() * 1e-6)).all()
+    assert stats["newton_iters"] == int(res["iters_total"].sum())
+
+
+def test_time_marching_from_steady_state_is_a_fixed_point():
+    nb, nt = 4, 11
+    w, tvec, _ = _gust(nb, nt, 0.0025)
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    st = ctx.steady_solve(api.make_opts(ftol=1e-12))
+    res = ctx.newmark_run(tvec, st["x"], np.zeros((nb, 25, 12)), api.make_opts(structural_damping=False), save_every=5)
+    ctx.close()
+    assert res["converged"].all() and res["x"].shape == (nb, 3, 444)
+    assert np.abs(res["x"] - st["x"][:, None, :]).max() <= 1e-8 * np.abs(st["x"]).max()
