@@ -9,8 +9,10 @@
 // u/θ), 3i+1 (velocity rows rV, rΩ; columns V/Ω) and 3i+2 (element).  Block bandwidths are KLB = 3, KUB = 4, so a stored row
 // holds the 8 column blocks B-3 .. B+4 (48 doubles).
 //
-// Not implemented on the device yet (the host refuses them): structural damping, point masses on a DynamicSystem and
-// body-frame accelerations as state variables (a DOF with pd & pl).
+// Structural damping (element.jl:165-217, 713-820; docs/src/theory.md): γ -= μ11 γdot, κ -= μ22 κdot, with the strain rates built
+// from the *velocity states* of the two end points; evaluated by damping_terms() below.
+// Not implemented on the device yet (the host refuses them): point masses on a DynamicSystem and body-frame accelerations as
+// state variables (a DOF with pd & pl).
 #pragma once
 #include "gxb_static.cuh"
 
@@ -28,6 +30,7 @@ struct DynArgs {
     // Newmark time marching (MODE 1): rate initialisation terms `paug` (analyses.jl:2693-2738) and 2/dt
     const double* init;       // [b][12][N+1] udot_init, θdot_init, Vdot_init, Ωdot_init
     double c2dt;              // 2/dt
+    int damping;              // structural_damping (elemS fields 82..87 hold Element.mu)
 };
 
 GXD void dblk(double* t, int s, const m3& B) {
@@ -61,6 +64,63 @@ GXD void dtile_planar(double* t, int first_row_in_slot, int diag_slot0) {
     }
 }
 GXD m3 mul3c(const Rot& R, v3 w) { return cols(R.C1 * w, R.C2 * w, R.C3 * w); }   // mul3(C_θ1, C_θ2, C_θ3, w)
+
+
+// ---- structural damping: strain rates and their derivatives (element.jl:165-217, 713-820) ----
+struct DampOut {
+    v3 gamdot, kapdot;
+    // ∂γ/∂(u1, θ, V1, Ω) and ∂κ/∂(θ1, θ2, Ω1, Ω2), damping coefficients already applied (γ_u2 = -γ_u1, γ_V2 = -γ_V1,
+    // γ_θ1 = γ_θ2, γ_Ω1 = γ_Ω2)
+    m3 g_u1, g_th, g_V1, g_Om, k_th1, k_th2, k_Om1, k_Om2;
+};
+GXD m3 rowscale(const m3& A, v3 m) { m3 r;
+#pragma unroll
+    for (int j = 0; j < 3; j++) { r.a[j] = A.a[j] * m.x; r.a[3 + j] = A.a[3 + j] * m.y; r.a[6 + j] = A.a[6 + j] * m.z; } return r; }
+
+template <bool WANT_J>
+__device__ __noinline__ void damping_terms(const m3& Cab, const m3& CtCab, const Rot& R, v3 th, v3 th1, v3 th2, v3 u1, v3 u2, v3 V1, v3 V2,
+                                           v3 Om1, v3 Om2, v3 Om, v3 vb, v3 wb, v3 dx1, v3 dx2, double L, v3 mua, v3 mub, DampOut& o) {
+    Rot R1, R2;
+    if (WANT_J) { rot_C_dC(th1, R1); rot_C_dC(th2, R2); } else { R1.C = rot_C(th1); R2.C = rot_C(th2); }
+    const v3 w1 = Om1 - wb, w2 = Om2 - wb;
+    const v3 udot1 = V1 - vb - cross(wb, dx1 + u1), udot2 = V2 - vb - cross(wb, dx2 + u2);
+    m3 Qi1, Qi2, tth1, tth2;             // θdot_i = Qinv_i C_i (Ω_i - ωb) and ∂θdot_i/∂θ_i
+    if (WANT_J) {
+        tth1 = rot_Qinv_dQinv_b(th1, R1.C * w1, Qi1) + Qi1 * mul3c(R1, w1);
+        tth2 = rot_Qinv_dQinv_b(th2, R2.C * w2, Qi2) + Qi2 * mul3c(R2, w2);
+    } else { Qi1 = rot_Qinv_from_c(rot_scaling(th1) * th1); Qi2 = rot_Qinv_from_c(rot_scaling(th2) * th2); }
+    const v3 thd1 = Qi1 * (R1.C * w1), thd2 = Qi2 * (R2.C * w2);
+    const v3 thed = 0.5 * (thd1 + thd2);
+    const v3 du = u2 - u1, dth = th2 - th1, dud = udot2 - udot1, dthd = thd2 - thd1;
+    RotQ RQ;
+    if (WANT_J) rot_Q_dQ(th, RQ); else RQ.Q = rot_Q(th);
+    const m3 dQ = rot_dQ(th, dth, RQ.Q);
+    const v3 W = Om - wb;
+    const v3 Cab1 = mk(Cab.a[0], Cab.a[3], Cab.a[6]);
+    o.gamdot = tmul(CtCab, dud - cross(W, du) - L * cross(W, Cab1));
+    o.kapdot = tmul(Cab, RQ.Q * dthd + dQ * thed);
+    if (!WANT_J) return;
+    const m3 At = transpose(CtCab), Wt = tilde(W);
+    o.g_u1 = -rowscale(At * Wt + At * tilde(wb), mua);
+    {
+        const m3 t = tmul(Cab, mul3c(R, dud - Wt * du - L * (Wt * Cab1)));
+        o.g_th = -0.5 * rowscale(t, mua);
+    }
+    o.g_V1 = rowscale(At, mua);
+    o.g_Om = -0.5 * rowscale(At * tilde(du) + L * (At * tilde(Cab1)), mua);
+    m3 D1, D2, D3;
+    rot_dQ_dth(th, dth, RQ, D1, D2, D3);
+    const m3 t1 = tmul(Cab, cols(RQ.Q1 * dthd, RQ.Q2 * dthd, RQ.Q3 * dthd));
+    const m3 t2 = tmul(Cab, cols(D1 * thed, D2 * thed, D3 * thed));
+    const m3 t3 = tmul(Cab, thed.x * RQ.Q1 + thed.y * RQ.Q2 + thed.z * RQ.Q3);
+    const m3 CQ = tmul(Cab, RQ.Q), CdQ = tmul(Cab, dQ);
+    const m3 Km = 0.5 * CdQ - CQ, Kp = 0.5 * CdQ + CQ;
+    const m3 half = 0.5 * (t1 + t2);
+    o.k_th1 = -rowscale(half - t3 + Km * tth1, mub);
+    o.k_th2 = -rowscale(half + t3 + Kp * tth2, mub);
+    o.k_Om1 = -rowscale(Km * (Qi1 * R1.C), mub);
+    o.k_Om2 = -rowscale(Kp * (Qi2 * R2.C), mub);
+}
 
 // One tile pass: every thread may deposit into the tile of station `i+1` (nb) before the barrier and into its own afterwards.
 // The CTA walks the instance in chunks of A.chunk stations; deposits happen when the target station is in the current chunk.
@@ -124,6 +184,7 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
     v3 mth2 = mk(1, 1, 1), mu2 = mth2;
     v3 ru = th, rth = th, F1 = th, M1 = th, F2 = th, M2 = th;
     v3 f1f = th, f2f = th, m1f = th, m2f = th, CtCabTg = th;
+    DampOut dmp;
     if (has_elem) {
         L = es[0];
         Cab = ldm(es + N, N);
@@ -142,15 +203,23 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         V = 0.5 * (V1 + V2); Om = 0.5 * (Om1 + Om2);
         if (WANT_J) rot_C_dC(th, R); else R.C = rot_C(th);
         CtCab = tmul(R.C, Cab);
+        v3 gam;
         {
             m3 S11 = ldm(es + 10 * N, N), S12 = ldm(es + 19 * N, N);
-            v3 gam = S11 * F + S12 * M;
-            Le1g = mk(L + gam.x, gam.y, gam.z);
+            gam = S11 * F + S12 * M;
         }
         {
             m3 S21 = ldm(es + 28 * N, N), S22 = ldm(es + 37 * N, N);
             kap = S21 * F + S22 * M;
         }
+        if (A.damping) {      // γ -= μ11 γdot, κ -= μ22 κdot   (element.jl:207-209)
+            const v3 mua = ldv(es + 82 * N, N), mub = ldv(es + 85 * N, N);
+            const v3 dx2 = ldv(A.pxS + ((size_t)b * 3) * NP + i + 1, NP);
+            damping_terms<WANT_J>(Cab, CtCab, R, th, th1, th2, u1, u2, V1, V2, Om1, Om2, Om, vb, wb, dxp, dx2, L, mua, mub, dmp);
+            gam = gam - mk(mua.x * dmp.gamdot.x, mua.y * dmp.gamdot.y, mua.z * dmp.gamdot.z);
+            kap = kap - mk(mub.x * dmp.kapdot.x, mub.y * dmp.kapdot.y, mub.z * dmp.kapdot.z);
+        }
+        Le1g = mk(L + gam.x, gam.y, gam.z);
         v3 Cab1 = mk(Cab.a[0], Cab.a[3], Cab.a[6]);
         ru = (u2 - u1) - (CtCab * Le1g - L * Cab1);
         rth = (th2 - th1) - rot_Qinv_from_c(rot_scaling(th) * th) * (Cab * kap);
@@ -349,6 +418,7 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
 
     // =================== pass P2: moment rows of point i (rows 18i+3..5) ===================
     m3 JMa = zero33(), JMb = zero33(), M1F = zero33(), hM = zero33();
+    m3 dMu1 = zero33(), dMV1 = zero33(), dMO = zero33();      // structural-damping parts (u2, V2 carry the opposite sign)
     if (has_elem) {
         m3 tm1 = mul3t(R, Cab * M);
         m3 tm2 = 0.5 * mul3t(R, Cab * cross(Le1g, F));
@@ -363,6 +433,12 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         if (S.dlS) { JMa = JMa + 0.5 * mul3t(R, m1f); JMb = JMb - 0.5 * mul3t(R, m2f); }
         JMa = JMa - hMth; JMb = JMb + hMth;
         m3 CtF = CtCab * tilde(F);
+        if (A.damping) {      // M1_x -= ½ CtCab F~ γ_x,  M2_x += ½ CtCab F~ γ_x   (element.jl:2232-2256)
+            const m3 tF = 0.5 * CtF;
+            const m3 dth_ = tF * dmp.g_th;
+            JMa = JMa - dth_; JMb = JMb + dth_;
+            dMu1 = tF * dmp.g_u1; dMV1 = tF * dmp.g_V1; dMO = tF * dmp.g_Om;
+        }
         M1F = 0.5 * (CtCab * tilde(Le1g) - CtF * ldm(es + 10 * N, N));
         hM = 0.5 * (CtF * ldm(es + 19 * N, N));
     }
@@ -374,16 +450,16 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         __syncthreads();
         if (next_in) {
             double* nt = tiles + (size_t)(i + 1 - c0) * GXB_DTILE;
-            dblk(nt, 0, rfs * colmask(hMu, mu1));
+            dblk(nt, 0, rfs * colmask(hMu + dMu1, mu1));
             dblk(nt, 3, rfs * colmask(JMb, mth1));
-            dblk(nt, 6, rfs * hMV);
-            dblk(nt, 9, rfs * hMO);
+            dblk(nt, 6, rfs * (hMV + dMV1));
+            dblk(nt, 9, rfs * (hMO + dMO));
             dblk(nt, 12, -M1F);                                   // M2_F
             dblk(nt, 15, CtCab + hM);                             // M2_M
-            dblk(nt, GXB_DPARK + 0, rfs * colmask(hMu, mu2));
+            dblk(nt, GXB_DPARK + 0, rfs * colmask(hMu - dMu1, mu2));
             dblk(nt, GXB_DPARK + 3, rfs * colmask(JMb, mth2));
-            dblk(nt, GXB_DPARK + 6, rfs * hMV);
-            dblk(nt, GXB_DPARK + 9, rfs * hMO);
+            dblk(nt, GXB_DPARK + 6, rfs * (hMV - dMV1));
+            dblk(nt, GXB_DPARK + 9, rfs * (hMO + dMO));
         }
         __syncthreads();
         if (mine_in) {
@@ -398,16 +474,16 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
             m3 bu = dget(mytile, GXB_DPARK + 0), bt = own + dget(mytile, GXB_DPARK + 3);
             m3 bV = dget(mytile, GXB_DPARK + 6), bO = dget(mytile, GXB_DPARK + 9);
             if (has_elem) {
-                bu = bu + rfs * colmask(hMu, mu1);
+                bu = bu + rfs * colmask(hMu + dMu1, mu1);
                 bt = bt - rfs * colmask(JMa, mth1);
-                bV = bV + rfs * hMV;
-                bO = bO + rfs * hMO;
+                bV = bV + rfs * (hMV + dMV1);
+                bO = bO + rfs * (hMO + dMO);
                 dblk(mytile, 30, -M1F);                           // -M1_F
                 dblk(mytile, 33, hM - CtCab);                     // -M1_M
-                dblk(mytile, 36, rfs * colmask(hMu, mu2));
+                dblk(mytile, 36, rfs * colmask(hMu - dMu1, mu2));
                 dblk(mytile, 39, (-rfs) * colmask(JMa, mth2));
-                dblk(mytile, 42, rfs * hMV);
-                dblk(mytile, 45, rfs * hMO);
+                dblk(mytile, 42, rfs * (hMV - dMV1));
+                dblk(mytile, 45, rfs * (hMO + dMO));
             }
             dblk(mytile, 18, bu); dblk(mytile, 21, bt); dblk(mytile, 24, bV); dblk(mytile, 27, bO);
             if (S.two_d) dtile_planar(mytile, 3, 18);
@@ -461,11 +537,20 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         if (mine_in) {
             dtile_clear(mytile);
             m3 ruth = -0.5 * mul3t(R, Cab * Le1g);
-            dblk(mytile, 6, colmask(-eye33(), mu1));
+            m3 ruu1 = -eye33(), ruu2 = eye33();
+            if (A.damping) {      // dynamic_compatibility_jacobians (element.jl:1550-1565)
+                const m3 Agu = CtCab * dmp.g_u1;
+                ruu1 = ruu1 - Agu; ruu2 = ruu2 + Agu;             // γ_u2 = -γ_u1
+                ruth = ruth - CtCab * dmp.g_th;
+                const m3 AgV = CtCab * dmp.g_V1, AgO = CtCab * dmp.g_Om;
+                dblk(mytile, 12, -AgV); dblk(mytile, 15, -AgO);   // ru_V1, ru_Ω1
+                dblk(mytile, 30, AgV); dblk(mytile, 33, -AgO);    // ru_V2 = +CtCab γ_V1, ru_Ω2
+            }
+            dblk(mytile, 6, colmask(ruu1, mu1));
             dblk(mytile, 9, colmask(ruth, mth1));
             dblk(mytile, 18, (-fs) * (CtCab * ldm(es + 10 * N, N)));
             dblk(mytile, 21, (-fs) * (CtCab * ldm(es + 19 * N, N)));
-            dblk(mytile, 24, colmask(eye33(), mu2));
+            dblk(mytile, 24, colmask(ruu2, mu2));
             dblk(mytile, 27, colmask(ruth, mth2));
             if (S.two_d) dtile_planar(mytile, 0, 18);
         }
@@ -481,10 +566,15 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
             m3 Qinv;
             m3 hd = -0.5 * rot_Qinv_dQinv_b(th, Cab * kap, Qinv);
             m3 QC = Qinv * Cab;
-            dblk(mytile, 9, colmask(hd - eye33(), mth1));
+            m3 rt1 = hd - eye33(), rt2 = hd + eye33();
+            if (A.damping) {      // rθ_θ -= Qinv Cab κ_θ, rθ_Ω = -Qinv Cab κ_Ω   (element.jl:1567-1572)
+                rt1 = rt1 - QC * dmp.k_th1; rt2 = rt2 - QC * dmp.k_th2;
+                dblk(mytile, 15, -(QC * dmp.k_Om1)); dblk(mytile, 33, -(QC * dmp.k_Om2));
+            }
+            dblk(mytile, 9, colmask(rt1, mth1));
             dblk(mytile, 18, (-fs) * (QC * ldm(es + 28 * N, N)));
             dblk(mytile, 21, (-fs) * (QC * ldm(es + 37 * N, N)));
-            dblk(mytile, 27, colmask(hd + eye33(), mth2));
+            dblk(mytile, 27, colmask(rt2, mth2));
             if (S.two_d) dtile_planar(mytile, 3, 18);
         }
         __syncthreads();

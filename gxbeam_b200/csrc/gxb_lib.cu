@@ -65,6 +65,7 @@ struct gxb_ctx {
     double *d_exS = nullptr, *d_motion = nullptr;     // dynamic only: element midpoints [b][3][N], body motion [b][12]
     double *d_paug = nullptr, *d_rates0 = nullptr, *d_series = nullptr; int *d_ser_point = nullptr, *d_ser_field = nullptr;
     int64_t ser_nt = 0; int ser_K = 0;
+    int damping = 0;         // structural_damping of the current solve
     int mode = 0;            // 0: steady residual, 1: Newmark residual (set by the time-marching driver)
     double c2dt = 0.0;
     bool body_state = false;                          // some DOF has pd & pl (body-frame acceleration would be a state)
@@ -82,8 +83,9 @@ struct gxb_ctx {
 
 // ------------------------------------------------------------------------------------------------------------------
 // packing kernels: caller's array-of-structs (the reference's memory layout) -> structure-of-arrays in HBM
-// elemS[b][f][e]: f=0 L; 1..9 Cab (row-major); 10..45 S11,S12,S21,S22 = L*compliance; 46..81 m11,m12,m21,m22 = L*mass
-#define GXB_ELEM_NF 82
+// elemS[b][f][e]: f=0 L; 1..9 Cab (row-major); 10..45 S11,S12,S21,S22 = L*compliance; 46..81 m11,m12,m21,m22 = L*mass;
+// 82..87 mu (structural damping coefficients)
+#define GXB_ELEM_NF 88
 __global__ void k_pack_elements(const double* __restrict__ raw, double* __restrict__ out, double* __restrict__ exS, int N, int64_t nbatch) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= nbatch * N) return;
@@ -93,6 +95,7 @@ __global__ void k_pack_elements(const double* __restrict__ raw, double* __restri
     const double L = s[0];
     o[0] = L;
     if (exS) for (int k = 0; k < 3; k++) exS[((size_t)b * 3 + k) * N + e] = s[1 + k];    // Element.x (midpoint)
+    for (int k = 0; k < 6; k++) o[(size_t)(82 + k) * N] = s[85 + k];                       // Element.mu
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[(size_t)(1 + 3 * i + j) * N] = s[76 + i + 3 * j];
     for (int bi = 0; bi < 2; bi++) for (int bj = 0; bj < 2; bj++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
         int f = 9 * (2 * bi + bj) + 3 * i + j;
@@ -659,7 +662,7 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
         } else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
     } else {
         DynArgs D{};
-        D.s = A; D.exS = c->d_exS; D.pxS = c->d_xyz; D.motion = c->d_motion; D.init = c->d_paug; D.c2dt = c->c2dt;
+        D.s = A; D.exS = c->d_exS; D.pxS = c->d_xyz; D.motion = c->d_motion; D.init = c->d_paug; D.c2dt = c->c2dt; D.damping = c->damping;
         // the shared-memory tile holds `chunk` stations; longer chains are flushed chunk by chunk
         const size_t budget = 200 * 1024;
         int chunk = (int)std::min<size_t>((size_t)bs, (budget - (size_t)bs * GXB_XCH * 8) / (GXB_DTILE * 8));
@@ -726,8 +729,10 @@ int gxb_static_solve_resident(gxb_ctx* c, const gxb_opts* opts) {
 int gxb_steady_solve_resident(gxb_ctx* c, const gxb_opts* opts) {
     NEED_BATCH("gxb_steady_solve_resident");
     if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_steady_solve_resident: context topology is not kind=1 (DynamicSystem)");
-    if (opts && opts->structural_damping) return fail(GXB_ERR_UNSUPPORTED, "structural_damping=true is not implemented on the device yet (steady_state_analysis defaults to false)");
-    return solve_resident(c, opts);
+    c->damping = (opts && opts->structural_damping) ? 1 : 0;
+    int rc = solve_resident(c, opts);
+    c->damping = 0;
+    return rc;
 }
 int gxb_steady_solve(gxb_ctx* c, const gxb_opts* opts, const double* x0, double* x, int32_t* converged, int32_t* iters, double* resid_inf) {
     int rc;
@@ -839,7 +844,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_newmark_run: context topology is not kind=1 (DynamicSystem)");
     if (nt < 2 || !tvec || !x0 || !rates0) return fail(GXB_ERR_INVALID, "gxb_newmark_run: need nt >= 2, tvec, x0 and the initial rates");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
-    if (o.structural_damping) return fail(GXB_ERR_UNSUPPORTED, "structural_damping=true is not implemented on the device yet (pass structural_damping=false)");
+    c->damping = o.structural_damping ? 1 : 0;
     if (o.linear) return fail(GXB_ERR_UNSUPPORTED, "gxb_newmark_run: linear=true is not implemented on the device");
     if (c->ser_K && c->ser_nt != nt) return fail(GXB_ERR_INVALID, "gxb_newmark_run: the bc series has a different number of time levels");
     if (save_every < 1) save_every = 1;
@@ -921,7 +926,7 @@ int gxb_static_solve(gxb_ctx* c, const gxb_opts* opts, const double* x0, double*
 
 int gxb_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double* x, double* r, double* Jblk) {
     NEED_BATCH("gxb_residual_jacobian");
-    if (c->kind == 1 && opts && opts->structural_damping) return fail(GXB_ERR_UNSUPPORTED, "structural_damping=true is not implemented on the device yet");
+    c->damping = (c->kind == 1 && opts && opts->structural_damping) ? 1 : 0;
     if (!x) return fail(GXB_ERR_INVALID, "gxb_residual_jacobian: x is null");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;

@@ -191,3 +191,77 @@ GXD m3 rot_Qinv_dQinv_b(v3 th, v3 b, m3& Qinv) {
     if (rot_c_theta(th, s, cth)) D = D * cth;   // column j = Σ_k D[:,k] c_θ[k,j]
     return D;
 }
+
+// ---- Q, ∂Q/∂θ, ΔQ, ∂ΔQ/∂θ for structural damping (math.jl:160-280) ----
+GXD m3 outer(v3 a, v3 b) { m3 r; r.a[0] = a.x * b.x; r.a[1] = a.x * b.y; r.a[2] = a.x * b.z; r.a[3] = a.y * b.x; r.a[4] = a.y * b.y; r.a[5] = a.y * b.z; r.a[6] = a.z * b.x; r.a[7] = a.z * b.y; r.a[8] = a.z * b.z; return r; }
+GXD v3 rowv(const m3& A, int i) { return mk(A.a[3 * i], A.a[3 * i + 1], A.a[3 * i + 2]); }
+GXD m3 diagm(double d) { m3 r = zero33(); r.a[0] = r.a[4] = r.a[8] = d; return r; }
+
+struct RotQ { m3 Q, Q1, Q2, Q3; };      // Q(θ) and ∂Q/∂θ_k
+
+// c, c_θ (identity when the scaling is 1)
+GXD void rot_c(v3 th, v3& c, m3& cth, double& s, v3& sth) {
+    s = rot_scaling(th);
+    c = s * th;
+    if (s == 1.0) { cth = eye33(); sth = mk(0, 0, 0); }
+    else { double tt = dot(th, th); sth = ((1.0 - s) / tt) * th; cth = outer(sth, th) + diagm(s); }
+}
+GXD m3 rot_Q_from_c(v3 c, double& c0, double& tmp) {
+    c0 = 2.0 - dot(c, c) / 8.0;
+    const double d = 4.0 - c0;
+    tmp = 1.0 / (d * d);
+    return tmp * (diagm(4.0 - 0.25 * dot(c, c)) - 2.0 * tilde(c) + 0.5 * outer(c, c));
+}
+GXD m3 rot_Q(v3 th) { double c0, tmp; return rot_Q_from_c(rot_scaling(th) * th, c0, tmp); }
+// math.jl:180-205:  ∂Q/∂c_k = f_k Q + tmp (-c_k/2 I - 2 tilde(e_k) + (e_k c' + c e_k')/2),  f_k = -c_k / (2 (4 - c0))
+GXD void rot_Q_dQ(v3 th, RotQ& R) {
+    v3 c, sth; m3 cth; double s, c0, tmp;
+    rot_c(th, c, cth, s, sth);
+    R.Q = rot_Q_from_c(c, c0, tmp);
+    const double q = -0.5 / (4.0 - c0);
+    m3* out[3] = {&R.Q1, &R.Q2, &R.Q3};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const v3 e = mk(k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0);
+        const double ck = comp(c, k);
+        *out[k] = (q * ck) * R.Q + tmp * (diagm(-0.5 * ck) - 2.0 * tilde(e) + 0.5 * (outer(e, c) + outer(c, e)));
+    }
+    if (s != 1.0) rot_chain(cth, R.Q1, R.Q2, R.Q3);
+}
+// math.jl:212-231
+GXD m3 rot_dQ(v3 th, v3 dth, const m3& Q) {
+    v3 c, sth; m3 cth; double s;
+    rot_c(th, c, cth, s, sth);
+    const double c0 = 2.0 - dot(c, c) / 8.0, d = 4.0 - c0, tmp1 = 1.0 / (d * d);
+    const v3 c0th = tmul(cth, -0.25 * c);                     // row vector -c'/4 c_θ
+    const m3 tmp2 = -outer(dth, c) + 4.0 * tilde(dth) + diagm(dot(c, dth)) + outer(c, dth);
+    return outer(Q * dth, (2.0 / d) * c0th) + (0.5 * tmp1) * (tmp2 * cth);
+}
+// math.jl:241-280
+GXD void rot_dQ_dth(v3 th, v3 dth, const RotQ& R, m3& D1, m3& D2, m3& D3) {
+    v3 c, sth; m3 cth; double s;
+    rot_c(th, c, cth, s, sth);
+    m3 sthth = zero33();
+    if (s != 1.0) { const double tt = dot(th, th); sthth = ((1.0 - s) / tt) * (eye33() - (3.0 / tt) * outer(th, th)); }
+    const double c0 = 2.0 - dot(c, c) / 8.0, d = 4.0 - c0;
+    const v3 c0th = tmul(cth, -0.25 * c);
+    const m3 c0thth = (-0.25) * tmul(cth, cth) - 0.5 * outer(c, sth) - (0.25 * dot(c, th)) * sthth;
+    const double tmp1 = 1.0 / (d * d);
+    const v3 tmp1th = (2.0 / (d * d * d)) * c0th;
+    const m3 tmp1thth = (6.0 / (d * d * d * d)) * outer(c0th, c0th) + (2.0 / (d * d * d)) * c0thth;
+    const m3 tmp2 = -outer(dth, c) + 4.0 * tilde(dth) + diagm(dot(c, dth)) + outer(c, dth);
+    const m3 t2SI = tmp2 * cth;
+    const v3 Qd = R.Q * dth;
+    const m3* Qk[3] = {&R.Q1, &R.Q2, &R.Q3};
+    m3* out[3] = {&D1, &D2, &D3};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const v3 ck = rowv(cth, k);
+        const m3 tmp2k = -outer(dth, ck) + diagm(dot(ck, dth)) + outer(ck, dth);
+        const v3 e = mk(k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0);
+        const double t1k = comp(tmp1th, k);
+        *out[k] = (1.0 / tmp1) * outer((*Qk[k]) * dth, tmp1th) + (1.0 / tmp1) * outer(Qd, rowv(tmp1thth, k)) - (t1k / (tmp1 * tmp1)) * outer(Qd, tmp1th) +
+                  (0.5 * t1k) * t2SI + (0.5 * tmp1) * (tmp2k * cth) +
+                  (0.5 * tmp1) * (tmp2 * (diagm(comp(sth, k)) + outer(rowv(sthth, k), th) + outer(sth, e)));
+    }
+}

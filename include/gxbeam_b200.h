@@ -42,7 +42,7 @@ typedef struct gxb_opts {
     double maxstep;          /* 1e6 */
     double c1, rho_hi, rho_lo; /* 1e-4, 0.5, 0.1 */
     int32_t profile;         /* !=0: time every kernel class with CUDA events (gxb_get_stats) */
-    int32_t structural_damping; /* steady/time-domain only (analyses.jl:397); must be 0 on the device for now */
+    int32_t structural_damping; /* kind=1 only: structural_damping keyword (analyses.jl:397 default false, :1708 default true) */
 } gxb_opts;
 
 /* Filled by gxb_get_stats after a solve. */
@@ -97,7 +97,7 @@ int gxb_static_solve(gxb_ctx* ctx, const gxb_opts* opts, const double* x0, doubl
                      double* resid_inf);
 
 /* steady_state_analysis!: the same Newton driver on a DynamicSystem (kind=1)          src/analyses.jl:383-527, 3556-3599
- * with steady_system_residual!/jacobian! (src/system.jl:427-455, 693-720).  structural_damping must be 0 (its default). */
+ * with steady_system_residual!/jacobian! (src/system.jl:427-455, 693-720). */
 int gxb_steady_solve(gxb_ctx* ctx, const gxb_opts* opts, const double* x0, double* x, int32_t* converged, int32_t* iters,
                      double* resid_inf);
 int gxb_steady_solve_resident(gxb_ctx* ctx, const gxb_opts* opts);
@@ -109,8 +109,8 @@ int gxb_steady_solve_resident(gxb_ctx* ctx, const gxb_opts* opts);
  * (analyses.jl:2549-2596): x0 (nbatch x nstates) and the point rates udot, θdot, Vdot, Ωdot at t0 (nbatch x np x 12).
  * tvec: nt times.  Saved time levels: 0, save_every, 2 save_every, ...  -> x_hist (nbatch x nsave x nstates, may be NULL).
  * steps_done[b]: time levels reached (an instance stops at its first unconverged step, analyses.jl:2781-2790);
- * iters_total[b]: Newton iterations over all steps; converged[b].  opts->structural_damping must be 0 for now (the reference
- * defaults to true for time-domain analyses). */
+ * iters_total[b]: Newton iterations over all steps; converged[b].  The reference's time-domain default is
+ * structural_damping = true: set opts->structural_damping accordingly. */
 int gxb_set_bc_series(gxb_ctx* ctx, int64_t nt, int32_t K, const int32_t* point /* 1-based */, const int32_t* field /* 0..17 */,
                       const double* values /* nbatch x nt x K */);
 int gxb_newmark_run(gxb_ctx* ctx, const gxb_opts* opts, int64_t nt, const double* tvec, const double* x0, const double* rates0,

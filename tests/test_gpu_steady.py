@@ -59,20 +59,21 @@ def test_body_acceleration_state_is_refused():
 
 @pytest.mark.parametrize("seed,nelem", [(0, 2), (1, 5), (2, 9)])
 @pytest.mark.parametrize("two_d", [False, True])
-def test_steady_residual_and_jacobian_parity(seed, nelem, two_d):
+@pytest.mark.parametrize("damping", [False, True])
+def test_steady_residual_and_jacobian_parity(seed, nelem, two_d, damping):
     O = _oracle()
     case = cases.random_anisotropic(seed, nelem=nelem, pmass=False)
     pk = cases.oracle_packed(case, two_dimensional=two_d)
     rng = np.random.default_rng(seed + 40)
     mo = 1e2 * rng.random(12)
-    dyn = O.make_dyn(vb=mo[0:3], wb=mo[3:6], ab=mo[6:9], alb=mo[9:12])
+    dyn = O.make_dyn(vb=mo[0:3], wb=mo[3:6], ab=mo[6:9], alb=mo[9:12], structural_damping=damping)
     ctx = _ctx(case, mo[None])
     n = ctx.n
     brow, bcol = ctx.pattern()
     mask = api.blocks_to_dense(n, brow, bcol, np.ones((len(brow), 9))) != 0
     for scale in (1.0, 1e2):
         x = scale * rng.random((1, n))
-        r, Jb = ctx.residual_jacobian(x, api.make_opts(two_dimensional=two_d))
+        r, Jb = ctx.residual_jacobian(x, api.make_opts(two_dimensional=two_d, structural_damping=damping))
         r_ref = O.steady_residual(pk, dyn, x[0])
         J_ref = O.steady_jacobian(pk, dyn, x[0])
         assert _relerr(r[0], r_ref) < 1e-12
@@ -144,5 +145,23 @@ def test_rotor_speed_sweep_batch_parity():
     assert res["converged"].all() and ref["converged"].all()
     assert np.array_equal(res["iters"], ref["iters"])
     assert st["newton_iters"] == int(res["iters"].sum())
+    for b in range(nb):
+        assert np.abs(res["x"][b] - ref["x"][b]).max() <= 1e-9 * np.abs(ref["x"][b]).max()
+
+
+def test_steady_solve_with_structural_damping_parity():
+    """steady_state_analysis(...; structural_damping=true): with zero strain rates at equilibrium the solution equals the
+    undamped one, but the Newton path goes through the damped residual/Jacobian on both sides."""
+    O = _oracle()
+    nb = 6
+    w = workloads.rotating_blade_batch(nb, rpm_jitter=0.3)
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    res = ctx.steady_solve(api.make_opts(structural_damping=True))
+    ctx.close()
+    pk = O.Packed(w["start"], w["stop"], w["elems"], w["points_b"], w["pd"], w["pl"], w["bc"])
+    dyns = [O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6], structural_damping=True) for b in range(nb)]
+    ref = O.steady_solve_batch(pk, nb, dyns, force_scaling=w["force_scaling"])
+    assert res["converged"].all() and ref["converged"].all()
+    assert np.array_equal(res["iters"], ref["iters"])
     for b in range(nb):
         assert np.abs(res["x"][b] - ref["x"][b]).max() <= 1e-9 * np.abs(ref["x"][b]).max()
