@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's bench.py): BASELINE configs 1 and 4 on the device next to the CPU oracle port.
+
+  steady : config-1 topology (24-element swept-tip rotating blade, n = 444), batch of rotor-speed variants, steady_state_analysis
+  gust   : config 4 — 512-member gust ensemble, time_domain_analysis of 2000 Newmark steps (dt = 0.25 ms) on the same topology,
+           initial state = steady rotating equilibrium, structural damping on (the reference's default)
+Prints one JSON line per workload.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gxbeam_b200 import api, workloads  # noqa: E402
+
+
+def make_ctx(w, nb):
+    ctx = api.Context(0)
+    ctx.topology(w["start"], w["stop"], w["pd"], w["pl"], kind=1)
+    ctx.set_batch(nb)
+    ctx.set_elements(w["elems"]); ctx.set_points(w["points_b"]); ctx.set_bc(w["bc"]); ctx.set_body(None, w["force_scaling"])
+    ctx.set_motion(w["motion"])
+    return ctx
+
+
+def steady(nb, cpu_sample):
+    from oracle import pyoracle as O
+    w = workloads.rotating_blade_batch(nb, rpm_jitter=0.5)
+    ctx = make_ctx(w, nb)
+    for _ in range(3):
+        ctx.steady_solve_resident()
+    ms, its = 0.0, 0
+    for _ in range(10):
+        ctx.steady_solve_resident(); st = ctx.stats(); ms += st["ms_total"]; its += st["newton_iters"]
+    res = ctx.fetch(); ctx.close()
+    ns = min(nb, cpu_sample)
+    pk = O.Packed(w["start"], w["stop"], w["elems"][:ns], w["points_b"][:ns], w["pd"], w["pl"], w["bc"][:ns])
+    dyns = [O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6]) for b in range(ns)]
+    t0 = time.perf_counter(); ref = O.steady_solve_batch(pk, ns, dyns, force_scaling=w["force_scaling"][:ns]); dt = time.perf_counter() - t0
+    err = float(np.abs(res["x"][:ns] - ref["x"]).max() / np.abs(ref["x"]).max())
+    print(json.dumps({"workload": f"steady_state_analysis, {nb} rotating blades (config-1 topology, n=444)", "gpu_newton_iters_per_s": its / (ms * 1e-3),
+                      "gpu_ms_per_batch": ms / 10, "cpu_newton_iters_per_s": float(ref["iters"].sum() / dt), "cpu_cores": O.num_threads(),
+                      "cpu_sample": ns, "iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "max_rel_diff": err}), flush=True)
+
+
+def gust(nb, nt, cpu_sample, damping=True):
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(1234 + 4)
+    w = workloads.rotating_blade_batch(nb)
+    tvec = np.linspace(0.0, 0.5 * (nt - 1) / 2000, nt)
+    amp = 100 * rng.uniform(0.5, 1.5, nb)
+    tf1 = np.where(tvec < 0.2, 0.1 * (1 - np.sin(2 * np.pi * (tvec / 0.4 + 0.25))), 0.0)
+    series = (amp[:, None] * tf1[None, :])[:, :, None]
+    ctx = make_ctx(w, nb)
+    st = ctx.steady_solve()
+    ctx.set_bc_series([21], [7], series)
+    rates0 = np.zeros((nb, 25, 12))
+    opts = api.make_opts(structural_damping=damping)
+    ctx.newmark_run(tvec[:21], st["x"], rates0, opts, want_history=False)      # warm-up
+    t0 = time.perf_counter()
+    res = ctx.newmark_run(tvec, st["x"], rates0, opts, save_every=nt - 1)
+    wall = time.perf_counter() - t0
+    s = ctx.stats(); ctx.close()
+    ns = min(nb, cpu_sample)
+    t0 = time.perf_counter(); cpu_iters = 0; err = 0.0
+    for b in range(ns):
+        pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
+        dyn = O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6], structural_damping=damping)
+        bct = np.tile(w["bc"][b][None], (nt, 1, 1)); bct[:, 20, 7] = series[b, :, 0]
+        ref = O.newmark_run(pk, dyn, tvec, st["x"][b], rates0[b], bct)
+        cpu_iters += int(ref["iters"].sum())
+        err = max(err, float(np.abs(res["x"][b, -1] - ref["x"][-1]).max() / np.abs(ref["x"][-1]).max()))
+    dt = time.perf_counter() - t0
+    print(json.dumps({"workload": f"time_domain_analysis, {nb}-member gust ensemble, {nt - 1} Newmark steps (config 4), structural_damping={damping}",
+                      "gpu_newton_iters_per_s": s["newton_iters"] / (s["ms_total"] * 1e-3), "gpu_s_per_run": s["ms_total"] * 1e-3, "gpu_wall_s": wall,
+                      "gpu_launches": s["launches"], "newton_iters": s["newton_iters"], "all_converged": bool(res["converged"].all()),
+                      "cpu_newton_iters_per_s_1core": cpu_iters / dt, "cpu_s_per_instance_1core": dt / ns, "cpu_sample": ns,
+                      "max_rel_diff_final_state": err}), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steady-batch", type=int, default=4096)
+    ap.add_argument("--gust-batch", type=int, default=512)
+    ap.add_argument("--gust-steps", type=int, default=2000)
+    ap.add_argument("--cpu-sample", type=int, default=4)
+    a = ap.parse_args()
+    steady(a.steady_batch, 1024)
+    gust(a.gust_batch, a.gust_steps + 1, a.cpu_sample)
