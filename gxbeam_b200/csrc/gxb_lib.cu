@@ -846,7 +846,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     c->damping = o.structural_damping ? 1 : 0;
     if (o.linear) return fail(GXB_ERR_UNSUPPORTED, "gxb_newmark_run: linear=true is not implemented on the device");
-    if (c->ser_K && c->ser_nt != nt) return fail(GXB_ERR_INVALID, "gxb_newmark_run: the bc series has a different number of time levels");
+    if (c->ser_K && c->ser_nt < nt) return fail(GXB_ERR_INVALID, "gxb_newmark_run: the bc series has fewer time levels than tvec");
     if (save_every < 1) save_every = 1;
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n, P = (size_t)c->np;
     const int64_t nsave = (nt - 1) / save_every + 1;      // time levels 0, save_every, 2 save_every, ...
@@ -871,7 +871,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
         if (!(dt > 0.0)) { c->mode = 0; return fail(GXB_ERR_INVALID, "gxb_newmark_run: tvec must be strictly increasing"); }
         const double c_prev = it > 1 ? 2.0 / (tvec[it - 1] - tvec[it - 2]) : 0.0;
         c->c2dt = 2.0 / dt;
-        if (c->ser_K) k_apply_bc_series<<<grid1(nb * c->ser_K, 128), 128, 0, c->stream>>>(c->d_bcS, c->d_series, c->d_ser_point, c->d_ser_field, c->ser_K, (int)P, nt, it, c->nbatch);
+        if (c->ser_K) k_apply_bc_series<<<grid1(nb * c->ser_K, 128), 128, 0, c->stream>>>(c->d_bcS, c->d_series, c->d_ser_point, c->d_ser_field, c->ser_K, (int)P, c->ser_nt, it, c->nbatch);
         k_newmark_paug<<<grid1(nb * P, 128), 128, 0, c->stream>>>(c->d_x, c->d_bcS, c->d_flags, c->d_paug, c->d_rates0, (int)P, (int)n, c->nbatch, it == 1, c_prev, c->c2dt);
         k_step_begin<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, c->ns.iters, c->ns.fcalls, d_alive, c->nbatch);
         CK(cudaMemcpyAsync(c->d_xt, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));   // initial guess = previous state (analyses.jl:3592)
