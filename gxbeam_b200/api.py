@@ -20,7 +20,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path():
-    return os.path.join(_HERE, "libgxbeam_b200.so")
+    # GXBEAM_B200_LIB lets experiments point at an alternative build of the same CUDA library (never a CPU implementation)
+    return os.environ.get("GXBEAM_B200_LIB") or os.path.join(_HERE, "libgxbeam_b200.so")
 
 
 class GXBError(RuntimeError):

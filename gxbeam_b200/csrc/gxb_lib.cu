@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -688,7 +689,8 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
 }
 template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveArgs& A) {
     using S = LuShape<KLB, KUB>;
-    const int wpc = 4;
+    static const int wpc_env = []() { const char* e = getenv("GXB_LU_WPC"); int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4) ? v : 4; }();
+    const int wpc = wpc_env;      // warps (= instances) per CTA; the kernel is compiled for up to 128 threads per CTA
     size_t sm = (size_t)wpc * S::SM_DOUBLES * 8;
     static thread_local size_t configured = 0;
     if (sm > 48 * 1024 && sm > configured) { CK(cudaFuncSetAttribute(k_factor_solve<KLB, KUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
@@ -760,10 +762,8 @@ static int newton_rounds(gxb_ctx* c, const gxb_opts& o, Prof& prof, int burst) {
         c->stats.rounds += 1;
         return GXB_OK;
     }
+    // the first burst goes out without looking at the counter: instances that were already converged at x0 early-exit
     for (;;) {
-        CK(cudaMemcpyAsync(c->h_counter, c->d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        if (*c->h_counter == 0) break;
         for (int q = 0; q < burst; q++) {
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
             prof.begin(); if ((rc = launch_factor(c, &o, 0))) return rc; prof.end(c->stats.ms_factor);
@@ -771,6 +771,9 @@ static int newton_rounds(gxb_ctx* c, const gxb_opts& o, Prof& prof, int burst) {
             prof.begin(); if ((rc = launch_update(c, &o, 1))) return rc; prof.end(c->stats.ms_update);
             c->stats.rounds += 1;
         }
+        CK(cudaMemcpyAsync(c->h_counter, c->d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (*c->h_counter == 0) break;
     }
     return GXB_OK;
 }
@@ -803,11 +806,29 @@ static int solve_resident(gxb_ctx* c, const gxb_opts* opts) {
 
 // ---- Newmark time marching (time_domain_analysis! from a given initial state, src/analyses.jl:2600-2790) ----
 // per-instance bookkeeping of the time loop: an instance whose step does not converge stops marching (analyses.jl:2781-2790)
-__global__ void k_step_begin(int* status, int* iters, int* fcalls, const int* alive, int64_t nbatch) {
-    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (b >= nbatch) return;
-    status[b] = alive[b] ? ST_TRIAL : ST_FAILED;
-    iters[b] = 0; fcalls[b] = 0;
+// one launch per time step: prescribed values of the new time level, `paug` update (analyses.jl:2693-2738), Newton state reset.
+// One CTA per instance (the series entries are written before the points read bcS: same CTA, one barrier).
+__global__ void k_step_prepare(double* __restrict__ bcS, const double* __restrict__ series, const int* __restrict__ ser_point,
+                               const int* __restrict__ ser_field, int K, int64_t ser_nt, int64_t step,
+                               const double* __restrict__ x, const unsigned short* __restrict__ flags, double* __restrict__ paug,
+                               const double* __restrict__ rates0, int NP, int n, int first, double c_prev, double c_new,
+                               int* status, int* iters, int* fcalls, const int* alive) {
+    const int64_t b = blockIdx.x;
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        bcS[((size_t)b * 18 + ser_field[k]) * NP + ser_point[k]] = series[((size_t)b * ser_nt + step) * K + k];
+    __syncthreads();
+    for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+        const double* xp = x + b * n + 18 * p;
+        const double* bc = bcS + ((size_t)b * 18) * NP + p;
+        const unsigned fl = flags[p];
+        double* pa = paug + ((size_t)b * 12) * NP + p;
+        for (int k = 0; k < 12; k++) {
+            const double sv = (k < 6 && (fl & (1u << k))) ? bc[k * NP] : xp[k];    // u, θ honour prescribed displacements at the new time
+            const double rate = first ? rates0[((size_t)b * NP + p) * 12 + k] : c_prev * sv - pa[(size_t)k * NP];
+            pa[(size_t)k * NP] = c_new * sv + rate;
+        }
+    }
+    if (threadIdx.x == 0) { status[b] = alive[b] ? ST_TRIAL : ST_FAILED; iters[b] = 0; fcalls[b] = 0; }
 }
 __global__ void k_step_end(const int* status, const int* iters, int* alive, int* steps_done, int* iters_total, int64_t nbatch) {
     int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -871,11 +892,11 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
         if (!(dt > 0.0)) { c->mode = 0; return fail(GXB_ERR_INVALID, "gxb_newmark_run: tvec must be strictly increasing"); }
         const double c_prev = it > 1 ? 2.0 / (tvec[it - 1] - tvec[it - 2]) : 0.0;
         c->c2dt = 2.0 / dt;
-        if (c->ser_K) k_apply_bc_series<<<grid1(nb * c->ser_K, 128), 128, 0, c->stream>>>(c->d_bcS, c->d_series, c->d_ser_point, c->d_ser_field, c->ser_K, (int)P, c->ser_nt, it, c->nbatch);
-        k_newmark_paug<<<grid1(nb * P, 128), 128, 0, c->stream>>>(c->d_x, c->d_bcS, c->d_flags, c->d_paug, c->d_rates0, (int)P, (int)n, c->nbatch, it == 1, c_prev, c->c2dt);
-        k_step_begin<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, c->ns.iters, c->ns.fcalls, d_alive, c->nbatch);
+        k_step_prepare<<<(unsigned)nb, 32, 0, c->stream>>>(c->d_bcS, c->d_series, c->d_ser_point, c->d_ser_field, c->ser_K, c->ser_nt, it, c->d_x,
+                                                           c->d_flags, c->d_paug, c->d_rates0, (int)P, (int)n, it == 1, c_prev, c->c2dt,
+                                                           c->ns.status, c->ns.iters, c->ns.fcalls, d_alive);
         CK(cudaMemcpyAsync(c->d_xt, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));   // initial guess = previous state (analyses.jl:3592)
-        c->stats.launches += 3 + (c->ser_K ? 1 : 0);
+        c->stats.launches += 1;
         if ((rc = newton_rounds(c, o, prof, 2))) { c->mode = 0; return rc; }
         k_step_end<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, c->ns.iters, d_alive, d_steps, d_itot, c->nbatch);
         c->stats.launches += 1;
