@@ -620,4 +620,56 @@ template <class T, class J> void newmark_system_jacobian(const Problem& P, const
     if (P.two_dimensional) two_dimensional_jacobian<T>(idx.nstates, jac);
 }
 
+// ================================================================= mass matrix (eigenvalue analysis) ========================
+//   mass_matrix_point_jacobian! (point.jl:2522, 1356-1384, 1586-1597, 1746-1755, 2033-2061)
+//   mass_matrix_element_jacobian! (element.jl:3395, 1408-1441, 2370-2411, 2903-2953)
+//   system_mass_matrix! (system.jl:961-995): M = ∂r/∂ẋ, added to `jac` times gamma
+template <class T, class J> void system_mass_matrix(const Problem& P, const Indices& idx, const T* x, T gamma, J& jac) {
+    T fs = T(P.force_scaling);
+    const bool two_d = P.two_dimensional != 0;
+    auto masked = [&](const M3<T>& A, bool angular) {      // lmask = (1,1,0), amask = (0,0,1) on rows when two_dimensional
+        M3<T> r = A;
+        if (two_d) for (int j = 0; j < 3; j++) { if (angular) { r.m[0][j] = T(0); r.m[1][j] = T(0); } else r.m[2][j] = T(0); }
+        return r;
+    };
+    static const double zeros36[36] = {0};
+    for (int64_t ip = 0; ip < P.np; ip++) {
+        const double* m = P.pmass ? P.pmass + 36 * ip : zeros36;
+        M3<T> m11 = sub33<T>(m, 0, 0), m12 = sub33<T>(m, 0, 1), m21 = sub33<T>(m, 1, 0), m22 = sub33<T>(m, 1, 1);
+        int64_t irow = idx.irow_point[ip] - 1, icol = idx.icol_point[ip] - 1;
+        V3<T> u, th; point_displacement(P, x, ip, icol, u, th);
+        M3<T> u_u, th_th; point_displacement_jacobians(P, ip, u_u, th_th);
+        M3<T> C = get_C(th), Ct = tr(C);
+        M3<T> PV = Ct * m11 * C, PO = Ct * m12 * C, HV = Ct * m21 * C, HO = Ct * m22 * C;
+        // jacob -= F_Vdot gamma / fs with F_Vdot = -Pdot_Vdot
+        add33(jac, irow, icol + 6, masked(PV, false) * gamma / fs); add33(jac, irow, icol + 9, masked(PO, false) * gamma / fs);
+        add33(jac, irow + 3, icol + 6, masked(HV, true) * gamma / fs); add33(jac, irow + 3, icol + 9, masked(HO, true) * gamma / fs);
+        add33(jac, irow + 6, icol, masked(-(u_u * u_u), false) * gamma);
+        add33(jac, irow + 9, icol + 3, masked(-(th_th * th_th), true) * gamma);
+    }
+    for (int64_t ie = 0; ie < P.ne; ie++) {
+        const double* e = P.elems + 91 * ie;
+        double L = e[0];
+        const double* mass = e + 40;
+        M3<T> m11 = sub33<T>(mass, 0, 0, L), m12 = sub33<T>(mass, 0, 1, L), m21 = sub33<T>(mass, 1, 0, L), m22 = sub33<T>(mass, 1, 1, L);
+        M3<T> Cab = cmat33<T>(e + 76);
+        int64_t ia = P.start[ie] - 1, ib = P.stop[ie] - 1;
+        V3<T> u1, th1, u2, th2;
+        point_displacement(P, x, ia, idx.icol_point[ia] - 1, u1, th1);
+        point_displacement(P, x, ib, idx.icol_point[ib] - 1, u2, th2);
+        V3<T> th = (th1 + th2) / T(2);
+        M3<T> A = tr(get_C(th)) * Cab, At = tr(A);
+        T q = T(0.25);
+        M3<T> PV = q * (A * m11 * At), PO = q * (A * m12 * At), HV = q * (A * m21 * At), HO = q * (A * m22 * At);
+        for (int64_t ipr : {ia, ib}) {
+            int64_t irow = idx.irow_point[ipr] - 1;
+            for (int64_t ipc : {ia, ib}) {
+                int64_t icol = idx.icol_point[ipc] - 1;
+                add33(jac, irow, icol + 6, masked(PV, false) * gamma / fs); add33(jac, irow, icol + 9, masked(PO, false) * gamma / fs);
+                add33(jac, irow + 3, icol + 6, masked(HV, true) * gamma / fs); add33(jac, irow + 3, icol + 9, masked(HO, true) * gamma / fs);
+            }
+        }
+    }
+}
+
 }  // namespace gxo

@@ -420,3 +420,17 @@ int64_t gxo_newmark_run(const gxo_problem* q, const gxo_dyn* d, const gxo_opts* 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- mass matrix ----
+extern "C" {
+// system_mass_matrix! (src/system.jl:961-995) as a dense column-major n x n matrix
+int gxo_mass_matrix(const gxo_problem* q, const double* x, double* M) {
+    Problem P = to_problem(q);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    int64_t n = idx.nstates;
+    DenseMat<double> D{n, M};
+    D.zero();
+    system_mass_matrix<double>(P, idx, x, 1.0, D);
+    return 0;
+}
+}  // extern "C"

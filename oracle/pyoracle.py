@@ -256,3 +256,22 @@ def newmark_run(pk: Packed, dyn: Dyn, tvec, x0, rates0, bc_t=None, **kw):
     done = lib().gxo_newmark_run(C.byref(pk.c), C.byref(dyn), C.byref(o), C.c_int64(nt), _p(tvec), _p(bct), _p(np.ascontiguousarray(x0, float)),
                                  _p(np.ascontiguousarray(rates0, float)), _p(xh), _p(its), C.byref(conv))
     return dict(x=xh, iters=its, converged=bool(conv.value), steps_done=int(done))
+
+
+# ---------------------------------------------------------------- mass matrix / eigen ----
+def mass_matrix(pk: Packed, x):
+    x = np.ascontiguousarray(x, float)
+    n = len(x)
+    M = np.zeros((n, n), order="F")
+    lib().gxo_mass_matrix(C.byref(pk.c), _p(x), _p(M))
+    return M
+
+
+def eigenvalues_dense(K, M, nev):
+    """solve_eigensystem (src/analyses.jl:943-965) with a dense solver: eigenvalues of K^{-1} M of largest magnitude, sorted by
+    (abs, imag) descending, returned as lambda = -1/mu together with the eigenvectors."""
+    import scipy.linalg as sla
+    mu, V = sla.eig(np.linalg.solve(K, M))
+    order = sorted(range(len(mu)), key=lambda i: (abs(mu[i]), mu[i].imag), reverse=True)[:nev]
+    mu = mu[order]
+    return -1.0 / mu, V[:, order]

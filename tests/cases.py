@@ -183,3 +183,27 @@ def jacobians_jl(seed=0, nelem=2):
     M = rng.random((6, 6))
     pm = {nelem + 1: 1e3 * (np.triu(M) + np.triu(M, 1).T)}     # Symmetric(1e3*rand(6,6))
     return _pack(asm, pcs, pm=pm, gravity=1e3 * rng.random(3))
+
+
+def pointmass_jl():
+    """test/issues/pointmass.jl:5-45: 10 massless anisotropic elements along y, point masses at every point (transform_properties of
+    the test's 6x6 mass matrix), root clamped.  The reference records five eigen-frequencies to 16 digits (:54-58)."""
+    nodes = np.array([[0, i / 10, 0] for i in range(11)], float)
+    nelem = 10
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    stiff = np.array([[1.0e6, 0, 0, -0.5, -1.0, -50000.0], [0, 3.0e6, 0, 0, 0, 0], [0, 0, 3.0e6, 0, 0, 0],
+                      [-0.5, 0, 0, 7.0, 0.1, -0.02], [-1.0, 0, 0, 0.1, 5.0, 0.1], [-50000.0, 0, 0, -0.02, 0.1, 3000.0]])
+    mass = np.array([[0.02, 0, 0, 0, -5.0e-7, -1.0e-7], [0, 0.02, 0, 5.0e-7, 0, 0.0001], [0, 0, 0.02, 1.0e-7, -0.0001, 0],
+                     [0, 5.0e-7, 1.0e-7, 1.0e-5, 1.0e-8, 2.0e-10], [-5.0e-7, 0, -0.0001, 1.0e-8, 6.0e-7, 9.0e-9],
+                     [-1.0e-7, 0.0001, 0, 2.0e-10, 9.0e-9, 1.0e-5]])
+    T = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+    asm = Assembly(nodes, start, stop, frames=[T] * nelem, stiffness=[stiff] * nelem)
+    Z = np.zeros((3, 3))
+    TT = np.block([[T, Z], [Z, T]])
+    pm = TT.T @ mass @ TT                                    # transform_properties (math.jl:43)
+    pms = {1: pm / 2, nelem + 1: pm / 2}
+    for i in range(2, nelem + 1):
+        pms[i] = pm
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
+    return _pack(asm, pcs, pm=pms, ref_freq=np.array([2.8182004347800804, 17.66611982731975, 27.978670985969078, 49.93431945680836,
+                                                     66.07594270678581]))
