@@ -11,8 +11,8 @@
 //
 // Structural damping (element.jl:165-217, 713-820; docs/src/theory.md): γ -= μ11 γdot, κ -= μ22 κdot, with the strain rates built
 // from the *velocity states* of the two end points; evaluated by damping_terms() below.
-// Not implemented on the device yet (the host refuses them): point masses on a DynamicSystem and body-frame accelerations as
-// state variables (a DOF with pd & pl).
+// Point masses (point.jl:630-672, 964-1023, 1134-1200) reuse the element's inertia routines with the frame A = C(θ_p)'.
+// Not implemented on the device yet (the host refuses it): body-frame accelerations as state variables (a DOF with pd & pl).
 #pragma once
 #include "gxb_static.cuh"
 
@@ -120,6 +120,71 @@ __device__ __noinline__ void damping_terms(const m3& Cab, const m3& CtCab, const
     o.k_th2 = -rowscale(half + t3 + Kp * tth2, mub);
     o.k_Om1 = -rowscale(Km * (Qi1 * R1.C), mub);
     o.k_Om2 = -rowscale(Kp * (Qi2 * R2.C), mub);
+}
+
+
+// ---- inertial loads of a body with mass blocks m11..m22 carried in a frame A (element: A = CtCab, point mass: A = C') ----
+// momenta P = A m11 A' V + A m12 A' Ω, H likewise; rates Pdot, Hdot for MODE 0 (Vdot, Ωdot given, A fixed) or MODE 1 (Newmark:
+// Adot = tilde(Ω - ωb) A; element.jl:397-407, point.jl:779-792).  Returns tf = ωb x P + Pdot and tm = ωb x H + V x P + Hdot.
+template <int MODE>
+GXD void inertia_loads(const m3& A, const m3& m11, const m3& m12, const m3& m21, const m3& m22, v3 V, v3 Om, v3 Vdot, v3 Omdot, v3 wb,
+                       v3& Pm, v3& H, v3& tf, v3& tm) {
+    const v3 cV = tmul(A, V), cO = tmul(A, Om), cVd = tmul(A, Vdot), cOd = tmul(A, Omdot);
+    Pm = A * (m11 * cV) + A * (m12 * cO);
+    H = A * (m21 * cV) + A * (m22 * cO);
+    v3 Pdot = A * (m11 * cVd) + A * (m12 * cOd);
+    v3 Hdot = A * (m21 * cVd) + A * (m22 * cOd);
+    if (MODE == 1) {      // A m Bᵀ V = -A m Aᵀ (W x V),  B m Aᵀ V = W x (A m Aᵀ V)  with B = tilde(W) A, W = Ω - ωb
+        const v3 W = Om - wb;
+        const v3 cWV = tmul(A, cross(W, V)), cWO = tmul(A, cross(W, Om));
+        Pdot = Pdot - (A * (m11 * cWV) + A * (m12 * cWO)) + cross(W, Pm);
+        Hdot = Hdot - (A * (m21 * cWV) + A * (m22 * cWO)) + cross(W, H);
+    }
+    tf = cross(wb, Pm) + Pdot;
+    tm = cross(wb, H) + cross(V, Pm) + Hdot;
+}
+// Derivatives of tf, tm with respect to (u, θ, V, Ω) of the carrying frame (element.jl:649-710, 1049-1112, 2258-2320;
+// point.jl:964-1023, 1134-1200, 1517-1540):  T_u = Pdot_u, T_θ = ω~b P_θ + Pdot_θ, T_V = ω~b P_V + Pdot_V, T_Ω = ω~b P_Ω + Pdot_Ω and the
+// moment twins (with the V~ P_x and -P~ terms).  `Cab` is the fixed part of A = C' Cab (identity for a point mass).
+struct InertiaJac { m3 Fu, Fth, FV, FO, Mu, Mth, MV, MO; };
+template <int MODE>
+GXD void inertia_jacobians(const m3& A, const m3& Cab, const Rot& R, const m3& m11, const m3& m12, const m3& m21, const m3& m22, v3 V, v3 Om,
+                           v3 Vdot, v3 Omdot, v3 wb, v3 alb, v3 Pm, double c2, InertiaJac& o) {
+    const m3 At = transpose(A), wbt = tilde(wb);
+    const m3 A11 = (A * m11) * At, A12 = (A * m12) * At, A21 = (A * m21) * At, A22 = (A * m22) * At;
+    const v3 cV = tmul(A, V), cO = tmul(A, Om), cVd = tmul(A, Vdot), cOd = tmul(A, Omdot);
+    const m3 cthV = tmul(Cab, mul3c(R, V)), cthO = tmul(Cab, mul3c(R, Om)), cthVd = tmul(Cab, mul3c(R, Vdot)), cthOd = tmul(Cab, mul3c(R, Omdot));
+    const m3 P_th = mul3t(R, Cab * (m11 * cV + m12 * cO)) + A * (m11 * cthV) + A * (m12 * cthO);
+    const m3 H_th = mul3t(R, Cab * (m21 * cV + m22 * cO)) + A * (m21 * cthV) + A * (m22 * cthO);
+    m3 Pd_th = mul3t(R, Cab * (m11 * cVd)) + mul3t(R, Cab * (m12 * cOd)) + A * (m11 * cthVd) + A * (m12 * cthOd);
+    m3 Hd_th = mul3t(R, Cab * (m21 * cVd)) + mul3t(R, Cab * (m22 * cOd)) + A * (m21 * cthVd) + A * (m22 * cthOd);
+    const m3 Vt = tilde(V);
+    m3 PdV = zero33(), PdO = zero33(), HdV = zero33(), HdO = zero33();
+    if (MODE == 1) {
+        const v3 Wv = Om - wb;
+        const m3 Wt = tilde(Wv);
+        const m3 Bm = Wt * A;                           // Adot
+        const v3 bV = tmul(Bm, V), bO = tmul(Bm, Om);   // Bᵀ V, Bᵀ Ω
+        const m3 cthWV = tmul(Cab, mul3c(R, Wt * V)), cthWO = tmul(Cab, mul3c(R, Wt * Om));
+        Pd_th = Pd_th + Wt * mul3t(R, Cab * (m11 * cV + m12 * cO)) + Bm * (m11 * cthV) + Bm * (m12 * cthO) +
+                mul3t(R, Cab * (m11 * bV + m12 * bO)) - A * (m11 * cthWV) - A * (m12 * cthWO);
+        Hd_th = Hd_th + Wt * mul3t(R, Cab * (m21 * cV + m22 * cO)) + Bm * (m21 * cthV) + Bm * (m22 * cthO) +
+                mul3t(R, Cab * (m21 * bV + m22 * bO)) - A * (m21 * cthWV) - A * (m22 * cthWO);
+        const m3 BmT = transpose(Bm), Ot = tilde(Om);
+        PdV = (A * m11) * BmT + (Bm * m11) * At + c2 * A11;
+        PdO = (A * m12) * BmT + (Bm * m12) * At + A11 * Vt + A12 * Ot - tilde(A11 * V) - tilde(A12 * Om) + c2 * A12;
+        HdV = (A * m21) * BmT + (Bm * m21) * At + c2 * A21;
+        HdO = (A * m22) * BmT + (Bm * m22) * At + A21 * Vt + A22 * Ot - tilde(A21 * V) - tilde(A22 * Om) + c2 * A22;
+    }
+    const m3 albt = tilde(alb);
+    o.Fu = (MODE == 0) ? A11 * albt : zero33();
+    o.Fth = wbt * P_th + Pd_th;
+    o.FV = wbt * A11 + PdV;
+    o.FO = wbt * A12 + PdO;
+    o.Mu = (MODE == 0) ? A21 * albt : zero33();
+    o.Mth = wbt * H_th + Vt * P_th + Hd_th;
+    o.MV = wbt * A21 + Vt * A11 - tilde(Pm) + HdV;
+    o.MO = wbt * A22 + Vt * A12 + HdO;
 }
 
 // One tile pass: every thread may deposit into the tile of station `i+1` (nb) before the barrier and into its own afterwards.
@@ -251,21 +316,9 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         }
         {
             const m3 m11 = ldm(es + 46 * N, N), m12 = ldm(es + 55 * N, N), m21 = ldm(es + 64 * N, N), m22 = ldm(es + 73 * N, N);
-            const v3 cV = tmul(CtCab, V), cO = tmul(CtCab, Om), cVd = tmul(CtCab, Vdot), cOd = tmul(CtCab, Omdot);
-            Pm = CtCab * (m11 * cV) + CtCab * (m12 * cO);
-            H = CtCab * (m21 * cV) + CtCab * (m22 * cO);
-            v3 Pdot = CtCab * (m11 * cVd) + CtCab * (m12 * cOd);
-            v3 Hdot = CtCab * (m21 * cVd) + CtCab * (m22 * cOd);
-            if (MODE == 1) {
-                // CtCabdot = tilde(Ω - ωb) CtCab =: W A ;  A m Bᵀ V = -A m Aᵀ (W x V),  B m Aᵀ V = W x (A m Aᵀ V)   (element.jl:397-407)
-                const v3 W = Om - wb;
-                const v3 cWV = tmul(CtCab, cross(W, V)), cWO = tmul(CtCab, cross(W, Om));
-                Pdot = Pdot - (CtCab * (m11 * cWV) + CtCab * (m12 * cWO)) + cross(W, Pm);
-                Hdot = Hdot - (CtCab * (m21 * cWV) + CtCab * (m22 * cWO)) + cross(W, H);
-            }
-            v3 tf = cross(wb, Pm) + Pdot;
+            v3 tf, tm;
+            inertia_loads<MODE>(CtCab, m11, m12, m21, m22, V, Om, Vdot, Omdot, wb, Pm, H, tf, tm);
             F1 = F1 - 0.5 * tf; F2 = F2 + 0.5 * tf;
-            v3 tm = cross(wb, H) + cross(V, Pm) + Hdot;
             M1 = M1 - 0.5 * tm; M2 = M2 + 0.5 * tm;
         }
         double* mine = xch + (size_t)threadIdx.x * GXB_XCH;
@@ -276,9 +329,23 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
 
     // ---- residual ----
     m3 Cp = zero33(), Qp = zero33();       // C(θ_p), Qinv(θ_p) of the point (velocity rows)
+    const bool pmass = S.pmS != nullptr;
+    v3 Vdp = mk(0, 0, 0), Odp = Vdp, Pp = Vdp;      // point-mass Vdot, Ωdot, linear momentum
     if (valid) {
         const double* prev = xch + (size_t)(i > 0 ? threadIdx.x - 1 : 0) * GXB_XCH;
         double* rp = r + 18 * i;
+        Cp = rot_C(th1); Qp = rot_Qinv_from_c(rot_scaling(th1) * th1);
+        if (pmass) {       // point.jl:630-672, 766-795, 1422-1449
+            const double* pm = S.pmS + ((size_t)b * 36) * NP + i;
+            const m3 m11 = ldm(pm, NP), m12 = ldm(pm + 9 * NP, NP), m21 = ldm(pm + 18 * NP, NP), m22 = ldm(pm + 27 * NP, NP);
+            if (MODE == 0) { Vdp = ab + cross(alb, dxp + u1); Odp = alb; }
+            else { Vdp = c2 * V1 - ldv(ini + 6 * NP + i, NP); Odp = c2 * Om1 - ldv(ini + 9 * NP + i, NP); }
+            const m3 Ap = transpose(Cp);
+            v3 Hp, tf, tm;
+            inertia_loads<MODE>(Ap, m11, m12, m21, m22, V1, Om1, Vdp, Odp, wb, Pp, Hp, tf, tm);
+            Fp = Fp - tf; Mp = Mp - tm;
+            if (S.has_grav) { const v3 Cg = Cp * g; Fp = Fp + tmul(Cp, m11 * Cg); Mp = Mp + tmul(Cp, m21 * Cg); }
+        }
         double own[6] = {-Fp.x * rfs, -Fp.y * rfs, -Fp.z * rfs, -Mp.x * rfs, -Mp.y * rfs, -Mp.z * rfs};
         double sub[6] = {F1.x * rfs, F1.y * rfs, F1.z * rfs, M1.x * rfs, M1.y * rfs, M1.z * rfs};
 #pragma unroll
@@ -290,7 +357,6 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
             rp[k] = v;
         }
         // velocity rows (point.jl:1658-1666): rV = V - vb - ωb x (Δx + u),  rΩ = Qinv C (Ω - ωb)
-        Cp = rot_C(th1); Qp = rot_Qinv_from_c(rot_scaling(th1) * th1);
         v3 rV = V1 - vb - cross(wb, dxp) - cross(wb, u1);
         v3 rO = Qp * (Cp * (Om1 - wb));
         if (MODE == 1) {     // - udot, - θdot with xdot = 2/dt x - xdot_init   (point.jl:776-777, 1663-1664)
@@ -314,43 +380,10 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
     m3 hFu, hFth, hFV, hFO, hMu, hMth, hMV, hMO;
     if (has_elem) {
         const m3 m11 = ldm(es + 46 * N, N), m12 = ldm(es + 55 * N, N), m21 = ldm(es + 64 * N, N), m22 = ldm(es + 73 * N, N);
-        const m3 CtCabT = transpose(CtCab);
-        const m3 A11 = (CtCab * m11) * CtCabT, A12 = (CtCab * m12) * CtCabT, A21 = (CtCab * m21) * CtCabT, A22 = (CtCab * m22) * CtCabT;
-        const v3 cV = tmul(CtCab, V), cO = tmul(CtCab, Om), cVd = tmul(CtCab, Vdot), cOd = tmul(CtCab, Omdot);
-        const m3 cthV = tmul(Cab, mul3c(R, V)), cthO = tmul(Cab, mul3c(R, Om)), cthVd = tmul(Cab, mul3c(R, Vdot)), cthOd = tmul(Cab, mul3c(R, Omdot));
-        const m3 P_th = mul3t(R, Cab * (m11 * cV + m12 * cO)) + CtCab * (m11 * cthV) + CtCab * (m12 * cthO);
-        const m3 H_th = mul3t(R, Cab * (m21 * cV + m22 * cO)) + CtCab * (m21 * cthV) + CtCab * (m22 * cthO);
-        const m3 Pd_th = mul3t(R, Cab * (m11 * cVd)) + mul3t(R, Cab * (m12 * cOd)) + CtCab * (m11 * cthVd) + CtCab * (m12 * cthOd);
-        const m3 Hd_th = mul3t(R, Cab * (m21 * cVd)) + mul3t(R, Cab * (m22 * cOd)) + CtCab * (m21 * cthVd) + CtCab * (m22 * cthOd);
-        const m3 albt = tilde(alb), Vt = tilde(V);
-        m3 PdV = zero33(), PdO = zero33(), HdV = zero33(), HdO = zero33();
-        m3 Pd_th_x = Pd_th, Hd_th_x = Hd_th;
-        if (MODE == 1) {
-            // element.jl:1049-1112 with B = CtCabdot = W A (W = tilde(Ω - ωb)):
-            //   Pdot_θ += W mul3t(Cab m Aᵀ V) + B m Cabᵀ mul3c(V) + mul3t(Cab m Bᵀ V) - A m Cabᵀ mul3c(W V)   (and the Ω / m12 twins)
-            const v3 Wv = Om - wb;
-            const m3 Wt = tilde(Wv);
-            const m3 Bm = Wt * CtCab;                       // CtCabdot
-            const v3 bV = tmul(Bm, V), bO = tmul(Bm, Om);   // Bᵀ V, Bᵀ Ω
-            const m3 cthWV = tmul(Cab, mul3c(R, Wt * V)), cthWO = tmul(Cab, mul3c(R, Wt * Om));
-            Pd_th_x = Pd_th + Wt * mul3t(R, Cab * (m11 * cV + m12 * cO)) + Bm * (m11 * cthV) + Bm * (m12 * cthO) +
-                      mul3t(R, Cab * (m11 * bV + m12 * bO)) - CtCab * (m11 * cthWV) - CtCab * (m12 * cthWO);
-            Hd_th_x = Hd_th + Wt * mul3t(R, Cab * (m21 * cV + m22 * cO)) + Bm * (m21 * cthV) + Bm * (m22 * cthO) +
-                      mul3t(R, Cab * (m21 * bV + m22 * bO)) - CtCab * (m21 * cthWV) - CtCab * (m22 * cthWO);
-            const m3 BmT = transpose(Bm), Ot = tilde(Om);
-            PdV = (CtCab * m11) * BmT + (Bm * m11) * CtCabT + c2 * A11;
-            PdO = (CtCab * m12) * BmT + (Bm * m12) * CtCabT + A11 * Vt + A12 * Ot - tilde(A11 * V) - tilde(A12 * Om) + c2 * A12;
-            HdV = (CtCab * m21) * BmT + (Bm * m21) * CtCabT + c2 * A21;
-            HdO = (CtCab * m22) * BmT + (Bm * m22) * CtCabT + A21 * Vt + A22 * Ot - tilde(A21 * V) - tilde(A22 * Om) + c2 * A22;
-        }
-        hFu = (MODE == 0) ? 0.25 * (A11 * albt) : zero33();
-        hFth = 0.25 * (wbt * P_th + Pd_th_x);
-        hFV = 0.25 * (wbt * A11 + PdV);
-        hFO = 0.25 * (wbt * A12 + PdO);
-        hMu = (MODE == 0) ? 0.25 * (A21 * albt) : zero33();
-        hMth = 0.25 * (wbt * H_th + Vt * P_th + Hd_th_x);
-        hMV = 0.25 * (wbt * A21 + Vt * A11 - tilde(Pm) + HdV);
-        hMO = 0.25 * (wbt * A22 + Vt * A12 + HdO);
+        InertiaJac ij;
+        inertia_jacobians<MODE>(CtCab, Cab, R, m11, m12, m21, m22, V, Om, Vdot, Omdot, wb, alb, Pm, c2, ij);
+        hFu = 0.25 * ij.Fu; hFth = 0.25 * ij.Fth; hFV = 0.25 * ij.FV; hFO = 0.25 * ij.FO;
+        hMu = 0.25 * ij.Mu; hMth = 0.25 * ij.Mth; hMV = 0.25 * ij.MV; hMO = 0.25 * ij.MO;
     }
 
     // =================== pass P1: force rows of point i (rows 18i+0..2) ===================
@@ -388,15 +421,27 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         __syncthreads();
         if (mine_in) {
             m3 own = zero33();
-            if (follower) {
-                Rot Rp; rot_C_dC(th1, Rp);
-                const double* bc = S.bcS + ((size_t)b * 18) * NP + i;
-                own = (-rfs) * colmask(rowmask(mul3t(Rp, ldv(bc + 12 * NP, NP)), fl1 & 64, fl1 & 128, fl1 & 256), mth1);
-            }
             m3 FF = zero33();
             FF.a[0] = (fl1 & 64) ? 0.0 : -1.0; FF.a[4] = (fl1 & 128) ? 0.0 : -1.0; FF.a[8] = (fl1 & 256) ? 0.0 : -1.0;
-            m3 bu = FF + dget(mytile, GXB_DPARK + 0), bt = own + dget(mytile, GXB_DPARK + 3);
+            m3 bu = FF + dget(mytile, GXB_DPARK + 0);
             m3 bV = dget(mytile, GXB_DPARK + 6), bO = dget(mytile, GXB_DPARK + 9);
+            if (follower || pmass) {
+                Rot Rp; rot_C_dC(th1, Rp);
+                const double* bc = S.bcS + ((size_t)b * 18) * NP + i;
+                m3 Fth = rowmask(mul3t(Rp, ldv(bc + 12 * NP, NP)), fl1 & 64, fl1 & 128, fl1 & 256);     // follower loads (point.jl:75-105)
+                if (pmass) {
+                    const double* pm = S.pmS + ((size_t)b * 36) * NP + i;
+                    const m3 m11 = ldm(pm, NP), m12 = ldm(pm + 9 * NP, NP), m21 = ldm(pm + 18 * NP, NP), m22 = ldm(pm + 27 * NP, NP);
+                    if (S.has_grav) Fth = Fth + mul3t(Rp, m11 * (Rp.C * g)) + tmul(Rp.C, m11 * mul3c(Rp, g));   // point.jl:1484
+                    InertiaJac ij;
+                    inertia_jacobians<MODE>(transpose(Rp.C), eye33(), Rp, m11, m12, m21, m22, V1, Om1, Vdp, Odp, wb, alb, Pp, c2, ij);
+                    Fth = Fth - ij.Fth;                           // F_θ -= ω~b P_θ + Pdot_θ   (point.jl:1527)
+                    bu = bu + rfs * colmask(ij.Fu, mu1);          // -F_u u_u / fs, F_u = -Pdot_u
+                    bV = bV + rfs * ij.FV; bO = bO + rfs * ij.FO; // -F_V / fs, -F_Ω / fs
+                }
+                own = (-rfs) * colmask(Fth, mth1);
+            }
+            m3 bt = own + dget(mytile, GXB_DPARK + 3);
             if (has_elem) {
                 bu = bu + rfs * colmask(hFu, mu1);                // -= F1_u1 u1_u1 / fs
                 bt = bt - rfs * colmask(JFa, mth1);
@@ -466,13 +511,25 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
             m3 MM = zero33();
             MM.a[0] = (fl1 & 512) ? 0.0 : -1.0; MM.a[4] = (fl1 & 1024) ? 0.0 : -1.0; MM.a[8] = (fl1 & 2048) ? 0.0 : -1.0;
             m3 own = MM;
-            if (follower) {
+            m3 bu = dget(mytile, GXB_DPARK + 0);
+            m3 bV = dget(mytile, GXB_DPARK + 6), bO = dget(mytile, GXB_DPARK + 9);
+            if (follower || pmass) {
                 Rot Rp; rot_C_dC(th1, Rp);
                 const double* bc = S.bcS + ((size_t)b * 18) * NP + i;
-                own = MM - rfs * colmask(rowmask(mul3t(Rp, ldv(bc + 15 * NP, NP)), fl1 & 512, fl1 & 1024, fl1 & 2048), mth1);
+                m3 Mth = rowmask(mul3t(Rp, ldv(bc + 15 * NP, NP)), fl1 & 512, fl1 & 1024, fl1 & 2048);
+                if (pmass) {
+                    const double* pm = S.pmS + ((size_t)b * 36) * NP + i;
+                    const m3 m11 = ldm(pm, NP), m12 = ldm(pm + 9 * NP, NP), m21 = ldm(pm + 18 * NP, NP), m22 = ldm(pm + 27 * NP, NP);
+                    if (S.has_grav) Mth = Mth + mul3t(Rp, m21 * (Rp.C * g)) + tmul(Rp.C, m21 * mul3c(Rp, g));
+                    InertiaJac ij;
+                    inertia_jacobians<MODE>(transpose(Rp.C), eye33(), Rp, m11, m12, m21, m22, V1, Om1, Vdp, Odp, wb, alb, Pp, c2, ij);
+                    Mth = Mth - ij.Mth;
+                    bu = bu + rfs * colmask(ij.Mu, mu1);
+                    bV = bV + rfs * ij.MV; bO = bO + rfs * ij.MO;
+                }
+                own = MM - rfs * colmask(Mth, mth1);
             }
-            m3 bu = dget(mytile, GXB_DPARK + 0), bt = own + dget(mytile, GXB_DPARK + 3);
-            m3 bV = dget(mytile, GXB_DPARK + 6), bO = dget(mytile, GXB_DPARK + 9);
+            m3 bt = own + dget(mytile, GXB_DPARK + 3);
             if (has_elem) {
                 bu = bu + rfs * colmask(hMu + dMu1, mu1);
                 bt = bt - rfs * colmask(JMa, mth1);

@@ -604,7 +604,6 @@ int gxb_set_motion(gxb_ctx* c, const double* motion) {
 }
 int gxb_set_pmass(gxb_ctx* c, const double* pm) {
     NEED_BATCH("gxb_set_pmass");
-    if (pm && c->kind == 1) return fail(GXB_ERR_UNSUPPORTED, "gxb_set_pmass: point masses on a DynamicSystem are not implemented on the device yet");
     if (!pm) { cudaFree(c->d_pmS); c->d_pmS = nullptr; return GXB_OK; }
     if (!c->d_pmS) { int rc = dalloc(&c->d_pmS, (size_t)c->nbatch * 36 * c->np); if (rc) return rc; }
     int rc = stage_upload(c, pm, (size_t)c->nbatch * c->np * 36 * 8); if (rc) return rc;

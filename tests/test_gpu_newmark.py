@@ -23,6 +23,8 @@ def _ctx(case, motion, nb=1, pts=None):
     ctx.set_bc(case["bc"][:nb])
     if case.get("dload") is not None:
         ctx.set_dloads(case["dload"][:nb])
+    if case.get("pmass") is not None:
+        ctx.set_pmass(case["pmass"][:nb])
     g = case.get("gravity")
     if g is not None:
         g = np.broadcast_to(np.asarray(g, float).reshape(-1, 3), (nb, 3)).copy()
@@ -35,7 +37,7 @@ def _ctx(case, motion, nb=1, pts=None):
 @pytest.mark.parametrize("damping", [False, True])
 def test_newmark_residual_and_jacobian_parity(seed, nelem, damping):
     O = _oracle()
-    case = cases.random_anisotropic(seed, nelem=nelem, pmass=False)
+    case = cases.random_anisotropic(seed, nelem=nelem, pmass=(seed % 2 == 0))
     pk = cases.oracle_packed(case)
     rng = np.random.default_rng(seed + 60)
     mo = np.zeros(12); mo[:6] = 1e2 * rng.random(6)

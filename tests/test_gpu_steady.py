@@ -23,6 +23,8 @@ def _ctx(case, motion, nb=1, pts=None):
     ctx.set_bc(case["bc"][:nb])
     if case.get("dload") is not None:
         ctx.set_dloads(case["dload"][:nb])
+    if case.get("pmass") is not None:
+        ctx.set_pmass(case["pmass"][:nb])
     g = case.get("gravity")
     if g is not None:
         g = np.broadcast_to(np.asarray(g, float).reshape(-1, 3), (nb, 3)).copy()
@@ -62,7 +64,7 @@ def test_body_acceleration_state_is_refused():
 @pytest.mark.parametrize("damping", [False, True])
 def test_steady_residual_and_jacobian_parity(seed, nelem, two_d, damping):
     O = _oracle()
-    case = cases.random_anisotropic(seed, nelem=nelem, pmass=False)
+    case = cases.random_anisotropic(seed, nelem=nelem, pmass=(seed % 2 == 0))
     pk = cases.oracle_packed(case, two_dimensional=two_d)
     rng = np.random.default_rng(seed + 40)
     mo = 1e2 * rng.random(12)
@@ -85,7 +87,7 @@ def test_steady_residual_and_jacobian_parity(seed, nelem, two_d, damping):
 
 def test_steady_newton_direction_parity():
     O = _oracle()
-    case = cases.random_anisotropic(4, nelem=8, pmass=False)
+    case = cases.random_anisotropic(4, nelem=8, pmass=True)
     pk = cases.oracle_packed(case)
     rng = np.random.default_rng(3)
     mo = 10 * rng.random(12)
@@ -165,3 +167,25 @@ def test_steady_solve_with_structural_damping_parity():
     assert np.array_equal(res["iters"], ref["iters"])
     for b in range(nb):
         assert np.abs(res["x"][b] - ref["x"][b]).max() <= 1e-9 * np.abs(ref["x"][b]).max()
+
+
+def test_pointmass_model_steady_jacobian_parity():
+    """test/issues/pointmass.jl model (point masses at every point, massless elements): K = steady Jacobian at the converged state
+    and at a random state, against the oracle that reproduces the reference's recorded eigen-frequencies."""
+    O = _oracle()
+    case = cases.pointmass_jl()
+    pk = cases.oracle_packed(case)
+    rng = np.random.default_rng(11)
+    mo = np.concatenate([rng.random(6), np.zeros(6)])
+    dyn = O.make_dyn(vb=mo[0:3], wb=mo[3:6])
+    ctx = _ctx(case, mo[None])
+    n = ctx.n
+    brow, bcol = ctx.pattern()
+    for x in (np.zeros((1, n)), rng.random((1, n))):
+        r, Jb = ctx.residual_jacobian(x)
+        J_ref = O.steady_jacobian(pk, dyn, x[0])
+        r_ref = O.steady_residual(pk, dyn, x[0])
+        assert np.abs(r[0] - r_ref).max() <= 1e-12 * max(np.abs(r_ref).max(), 1e-30)
+        J = api.blocks_to_dense(n, brow, bcol, Jb[0])
+        assert np.abs(J - J_ref).max() <= 1e-12 * np.abs(J_ref).max()
+    ctx.close()
