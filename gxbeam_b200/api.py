@@ -47,7 +47,7 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_set_elements", "gxb_set_points", "gxb_set_bc", "gxb_set_dloads", "gxb_set_pmass", "gxb_set_body",
            "gxb_set_motion", "gxb_static_solve", "gxb_steady_solve", "gxb_steady_solve_resident", "gxb_upload_x0",
            "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction",
-           "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian"]
+           "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi"]
 
 _lib = None
 
@@ -234,6 +234,39 @@ class Context:
         J = np.empty((self.nbatch, len(brow), 9))
         self._ck(self.lib.gxb_newmark_residual_jacobian(self.h, C.byref(o), _ptr(init), C.c_double(dt), _ptr(x), _ptr(r), _ptr(J)))
         return r, J
+
+    # --- eigenvalue analysis ---
+    def mass_matrix(self, x, opts=None):
+        o = opts or make_opts()
+        x = _f64(x).reshape(self.nbatch, self.n)
+        brow, _ = self.pattern()
+        M = np.empty((self.nbatch, len(brow), 9))
+        self._ck(self.lib.gxb_mass_matrix(self.h, C.byref(o), _ptr(x), _ptr(M)))
+        return M
+
+    def eigen_arnoldi(self, x, m, opts=None, want_basis=True):
+        o = opts or make_opts()
+        x = _f64(x).reshape(self.nbatch, self.n)
+        H = np.empty((self.nbatch, m + 1, m))
+        V = np.empty((self.nbatch, m + 1, self.n)) if want_basis else None
+        self._ck(self.lib.gxb_eigen_arnoldi(self.h, C.byref(o), _ptr(x), C.c_int32(m), _ptr(H), _ptr(V)))
+        return H, V
+
+    def eigenvalue_analysis(self, x, nev=6, m=None, opts=None, tol=1e-9):
+        """solve_eigensystem (src/analyses.jl:943-965) at the linearisation states x: returns (lam [nb, nev] complex,
+        vec [nb, n, nev] complex, resid [nb, nev] Ritz residual estimates relative to |mu|)."""
+        m = m or min(self.n, max(3 * nev + 10, 30))
+        H, V = self.eigen_arnoldi(x, m, opts)
+        lam = np.empty((self.nbatch, nev), complex); vec = np.empty((self.nbatch, self.n, nev), complex)
+        res = np.empty((self.nbatch, nev))
+        for b in range(self.nbatch):
+            mu, Y = np.linalg.eig(H[b, :m, :m])
+            order = sorted(range(m), key=lambda i: (abs(mu[i]), mu[i].imag), reverse=True)[:nev]
+            mu, Y = mu[order], Y[:, order]
+            lam[b] = -1.0 / mu
+            vec[b] = V[b, :m].T @ Y
+            res[b] = np.abs(H[b, m, m - 1] * Y[m - 1, :]) / np.abs(mu)
+        return lam, vec, res
 
     # --- time marching ---
     def set_bc_series(self, point, field, values):

@@ -66,6 +66,7 @@ struct gxb_ctx {
     double *d_exS = nullptr, *d_motion = nullptr;     // dynamic only: element midpoints [b][3][N], body motion [b][12]
     double *d_paug = nullptr, *d_rates0 = nullptr, *d_series = nullptr; int *d_ser_point = nullptr, *d_ser_field = nullptr;
     int64_t ser_nt = 0; int ser_K = 0;
+    double* d_M = nullptr;   // mass matrix in row-block storage (eigen analysis), allocated on demand
     int damping = 0;         // structural_damping of the current solve
     int mode = 0;            // 0: steady residual, 1: Newmark residual (set by the time-marching driver)
     double c2dt = 0.0;
@@ -178,6 +179,7 @@ struct SolveArgs {
     NewtonState ns;
     double maxstep; int linear;
     int direction_only;   // parity entry point: just p, no state change
+    double sign;          // sol = sign * (J \ F): -1 for the Newton direction, +1 for the eigen operator
 };
 
 template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? GXB_LU_MINBLOCKS : 2)) k_factor_solve(SolveArgs A) {
@@ -191,7 +193,7 @@ template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? G
     const size_t n = A.n;
     const double* F = A.F + b * n;
     double* p = A.p + b * n;
-    int bad = warp_band_solve<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * n * S::UW, p, A.nb, -1.0, sm);
+    int bad = warp_band_solve<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * n * S::UW, p, A.nb, A.sign, sm);
     __syncwarp();
     if (A.direction_only) return;
     if (bad) { if (lane == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
@@ -315,9 +317,143 @@ __global__ void k_extract_blocks(const double* __restrict__ Jrow, const int64_t*
     out[t] = (slot >= 0 && slot < W) ? Jrow[((size_t)b * n + r) * W + slot] : 0.0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Mass matrix M = ∂r/∂ẋ in the same row-block storage as the Jacobian (system_mass_matrix!, src/system.jl:961-995;
+// point.jl:1356-1384, 2033-2061; element.jl:1408-1441, 2370-2411, 2903-2953).  One thread per station; a thread evaluates the
+// frames of element i-1 and element i itself (only C(θ) is needed), so no exchange between threads is required.
+struct MassArgs { StaticArgs s; double* Mrow; };
+__global__ void k_mass_matrix(MassArgs A) {
+    const StaticArgs& S = A.s;
+    const int b = blockIdx.x, i = threadIdx.x, N = S.N, NP = N + 1;
+    if (i > N) return;
+    const double rfs = 1.0 / S.fs[b];
+    const double* x = S.x + (size_t)b * S.n;
+    double* Mr = A.Mrow + ((size_t)b * S.n + 18 * i) * GXB_DROWW;
+    auto theta = [&](int p) {
+        const unsigned fl = S.flags[p];
+        const double* bc = S.bcS + ((size_t)b * 18) * NP + p;
+        const double* xp = x + 18 * p;
+        return mk((fl & 8) ? bc[3 * NP] : xp[3], (fl & 16) ? bc[4 * NP] : xp[4], (fl & 32) ? bc[5 * NP] : xp[5]);
+    };
+    const v3 thi = theta(i);
+    m3 FV[3], FO[3], MV[3], MO[3];       // column points i-1, i, i+1
+    for (int k = 0; k < 3; k++) { FV[k] = zero33(); FO[k] = zero33(); MV[k] = zero33(); MO[k] = zero33(); }
+    if (S.pmS) {
+        const double* pm = S.pmS + ((size_t)b * 36) * NP + i;
+        const m3 C = rot_C(thi);
+        FV[1] = rfs * tmul(C, ldm(pm, NP) * C); FO[1] = rfs * tmul(C, ldm(pm + 9 * NP, NP) * C);
+        MV[1] = rfs * tmul(C, ldm(pm + 18 * NP, NP) * C); MO[1] = rfs * tmul(C, ldm(pm + 27 * NP, NP) * C);
+    }
+    for (int side = 0; side < 2; side++) {       // element i-1 (this point is its stop), then element i (this point is its start)
+        const int e = i - 1 + side;
+        if (e < 0 || e >= N) continue;
+        const double* es = S.elemS + ((size_t)b * S.elem_nf) * N + e;
+        const m3 Cab = ldm(es + N, N);
+        const v3 th = 0.5 * (theta(e) + theta(e + 1));
+        const m3 Am = tmul(rot_C(th), Cab), At = transpose(Am);
+        const double q = 0.25 * rfs;
+        const m3 a11 = q * ((Am * ldm(es + 46 * N, N)) * At), a12 = q * ((Am * ldm(es + 55 * N, N)) * At);
+        const m3 a21 = q * ((Am * ldm(es + 64 * N, N)) * At), a22 = q * ((Am * ldm(es + 73 * N, N)) * At);
+        const int k0 = side;                     // column points (e, e+1) = (i-1, i) or (i, i+1)
+        FV[k0] = FV[k0] + a11; FV[k0 + 1] = FV[k0 + 1] + a11; FO[k0] = FO[k0] + a12; FO[k0 + 1] = FO[k0 + 1] + a12;
+        MV[k0] = MV[k0] + a21; MV[k0 + 1] = MV[k0 + 1] + a21; MO[k0] = MO[k0] + a22; MO[k0 + 1] = MO[k0 + 1] + a22;
+    }
+    const bool two_d = S.two_d != 0;
+    auto put = [&](int r0, int slot, const m3& B, bool angular) {
+        for (int r = 0; r < 3; r++) {
+            const bool zero = two_d && (angular ? r < 2 : r == 2);       // lmask = (1,1,0), amask = (0,0,1)
+            for (int cc = 0; cc < 3; cc++) Mr[(size_t)(r0 + r) * GXB_DROWW + slot + cc] = zero ? 0.0 : B.a[3 * r + cc];
+        }
+    };
+    for (int k = 0; k < 3; k++) {
+        const int p = i - 1 + k;
+        if (p < 0 || p > N) continue;
+        const int sV = 6 + 18 * k, sO = 9 + 18 * k;     // slots of (V, Ω) of points i-1, i, i+1 in an equilibrium row
+        put(0, sV, FV[k], false); put(0, sO, FO[k], false);
+        put(3, sV, MV[k], true); put(3, sO, MO[k], true);
+    }
+    const unsigned fl = S.flags[i];
+    m3 uu = zero33(), tt = zero33();
+    uu.a[0] = (fl & 1) ? 0.0 : -1.0; uu.a[4] = (fl & 2) ? 0.0 : -1.0; uu.a[8] = (fl & 4) ? 0.0 : -1.0;
+    tt.a[0] = (fl & 8) ? 0.0 : -1.0; tt.a[4] = (fl & 16) ? 0.0 : -1.0; tt.a[8] = (fl & 32) ? 0.0 : -1.0;
+    put(6, 12, uu, false);       // rV rows: -u_u
+    put(9, 15, tt, true);        // rΩ rows: -θ_θ
+}
+
+// y = M v in row-block storage: one thread per row
+__global__ void k_rowblock_spmv(const double* __restrict__ Mrow, const double* __restrict__ v, double* __restrict__ y, int n, int W, int KLB,
+                                int64_t nbatch, int64_t vstride) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * n) return;
+    const int64_t b = t / n; const int r = (int)(t % n);
+    const double* row = Mrow + (size_t)t * W;
+    const double* vb = v + b * vstride;
+    const int c0 = 6 * (r / 6 - KLB);
+    double acc = 0.0;
+    for (int j = 0; j < W; j++) { const int c = c0 + j; if (c >= 0 && c < n) acc = fma(row[j], vb[c], acc); }
+    y[t] = acc;
+}
+
+// Arnoldi bookkeeping, one CTA per instance.  Vk: [b][m+1][n] Krylov basis, H: [b][m+1][m] (row-major), w: [b][n] = A v_j.
+__global__ void __launch_bounds__(256) k_arnoldi_start(double* __restrict__ Vk, int n, int m) {
+    const int b = blockIdx.x;
+    double* v0 = Vk + (size_t)b * (m + 1) * n;
+    __shared__ double red[8];
+    double ss = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        // deterministic pseudo-random start vector (the reference's ArnoldiMethod draws a random one)
+        unsigned h = (unsigned)c * 2654435761u + 12345u; h ^= h >> 13; h *= 2246822519u; h ^= h >> 16;
+        const double val = 0.5 + (double)(h & 0xffffff) / 16777216.0;
+        v0[c] = val; ss = fma(val, val, ss);
+    }
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(GXB_FULL, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    double tot = 0.0; for (int k = 0; k < (int)(blockDim.x >> 5); k++) tot += red[k];
+    const double inv = 1.0 / sqrt(tot);
+    for (int c = threadIdx.x; c < n; c += blockDim.x) v0[c] *= inv;
+}
+__global__ void __launch_bounds__(256) k_arnoldi_orth(double* __restrict__ Vk, double* __restrict__ H, const double* __restrict__ w_in, int n, int m, int j) {
+    const int b = blockIdx.x;
+    double* V = Vk + (size_t)b * (m + 1) * n;
+    double* Hb = H + (size_t)b * (m + 1) * m;
+    double* vn = V + (size_t)(j + 1) * n;            // work in place in the slot of v_{j+1}
+    const double* w = w_in + (size_t)b * n;
+    __shared__ double red[8]; __shared__ double bc;
+    const int nw = blockDim.x >> 5;
+    auto block_sum = [&](double x) {
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(GXB_FULL, x, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x == 0) { double t = 0.0; for (int k = 0; k < nw; k++) t += red[k]; bc = t; }
+        __syncthreads();
+        return bc;
+    };
+    for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] = w[c];
+    // modified Gram-Schmidt, two sweeps (the second one only corrects round-off; its coefficients are added to H)
+    for (int sweep = 0; sweep < 2; sweep++)
+        for (int i = 0; i <= j; i++) {
+            const double* vi = V + (size_t)i * n;
+            double d = 0.0;
+            for (int c = threadIdx.x; c < n; c += blockDim.x) d = fma(vi[c], vn[c], d);
+            const double h = block_sum(d);
+            for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] = fma(-h, vi[c], vn[c]);
+            if (threadIdx.x == 0) Hb[(size_t)i * m + j] = (sweep == 0 ? 0.0 : Hb[(size_t)i * m + j]) + h;
+        }
+    double d = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) d = fma(vn[c], vn[c], d);
+    const double nrm = sqrt(block_sum(d));
+    if (threadIdx.x == 0) Hb[(size_t)(j + 1) * m + j] = nrm;
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] *= inv;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 static void free_batch(gxb_ctx* c) {
     cudaFree(c->d_exS); cudaFree(c->d_motion); c->d_exS = c->d_motion = nullptr;
+    cudaFree(c->d_M); c->d_M = nullptr;
     cudaFree(c->d_paug); cudaFree(c->d_rates0); cudaFree(c->d_series); cudaFree(c->d_ser_point); cudaFree(c->d_ser_field);
     c->d_paug = c->d_rates0 = c->d_series = nullptr; c->d_ser_point = c->d_ser_field = nullptr; c->ser_nt = 0; c->ser_K = 0; c->mode = 0;
     cudaFree(c->d_elemS); cudaFree(c->d_bcS); cudaFree(c->d_dlS); cudaFree(c->d_pmS); cudaFree(c->d_grav); cudaFree(c->d_fs); cudaFree(c->d_xyz);
@@ -697,8 +833,9 @@ template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveAr
     CK(cudaGetLastError());
     return GXB_OK;
 }
-static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only) {
+static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, double sign = -1.0) {
     SolveArgs A{};
+    A.sign = sign;
     A.nb = (int)(c->n / 6); A.n = (int)c->n; A.nbatch = c->nbatch;
     A.J = c->d_J; A.F = direction_only ? c->d_Ft : c->d_F; A.x = c->d_x; A.U = c->d_U; A.p = c->d_p; A.xt = c->d_xt; A.ns = c->ns;
     A.maxstep = o->maxstep; A.linear = o->linear; A.direction_only = direction_only;
@@ -978,6 +1115,77 @@ int gxb_newmark_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double
     rc = gxb_residual_jacobian(c, opts, x, r, Jblk);
     c->mode = 0;
     return rc;
+}
+
+// ---- eigenvalue analysis: mass matrix and the Krylov part of solve_eigensystem (src/analyses.jl:943-965) ----
+static int assemble_mass_matrix(gxb_ctx* c, const gxb_opts& o, const double* d_x) {
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    if (!c->d_M) { CK(cudaMalloc(&c->d_M, nb * n * c->W * 8)); CK(cudaMemsetAsync(c->d_M, 0, nb * n * c->W * 8, c->stream)); }
+    MassArgs A{};
+    A.s = make_static_args(c, &o, d_x, nullptr, false, 0, false);
+    A.Mrow = c->d_M;
+    int bs = (int)((c->np + 31) / 32) * 32;
+    k_mass_matrix<<<(unsigned)nb, bs, 0, c->stream>>>(A);
+    CK(cudaGetLastError());
+    c->stats.launches++;
+    return GXB_OK;
+}
+
+int gxb_mass_matrix(gxb_ctx* c, const gxb_opts* opts, const double* x, double* Mblk) {
+    NEED_BATCH("gxb_mass_matrix");
+    if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_mass_matrix: context topology is not kind=1 (DynamicSystem)");
+    if (!x || !Mblk) return fail(GXB_ERR_INVALID, "gxb_mass_matrix: null");
+    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    CK(cudaMemcpyAsync(c->d_xt, x, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
+    int rc = assemble_mass_matrix(c, o, c->d_xt); if (rc) return rc;
+    const size_t nblk = c->brow.size();
+    size_t bytes = nb * nblk * 9 * 8;
+    if (bytes > c->stage_bytes) { cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0; CK(cudaMalloc(&c->d_stage, bytes)); c->stage_bytes = bytes; }
+    k_extract_blocks<<<grid1(nb * nblk * 9, 256), 256, 0, c->stream>>>(c->d_M, c->d_brow, c->d_bcol, c->d_stage, (int64_t)nblk, (int)n, c->W, c->KLB, c->nbatch);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(Mblk, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return GXB_OK;
+}
+
+int gxb_eigen_arnoldi(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t m, double* H, double* V) {
+    NEED_BATCH("gxb_eigen_arnoldi");
+    if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_eigen_arnoldi: context topology is not kind=1 (DynamicSystem)");
+    if (!x || !H || m < 1 || m > c->n) return fail(GXB_ERR_INVALID, "gxb_eigen_arnoldi: need x, H and 1 <= m <= nstates");
+    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    c->stats = gxb_stats{};
+    c->damping = o.structural_damping ? 1 : 0;
+    c->mode = 0;
+    int rc;
+    double *d_V = nullptr, *d_H = nullptr;
+    CK(cudaMalloc(&d_V, nb * (size_t)(m + 1) * n * 8));
+    CK(cudaMalloc(&d_H, nb * (size_t)(m + 1) * m * 8));
+    CK(cudaMemsetAsync(d_H, 0, nb * (size_t)(m + 1) * m * 8, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    // K = steady Jacobian at x (steady_jacobian!, analyses.jl:1358), M = mass matrix at x (mass_matrix!, analyses.jl:1359)
+    CK(cudaMemcpyAsync(c->d_x, x, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
+    StaticArgs A = make_static_args(c, &o, c->d_x, c->d_F, true, 0, false);
+    if ((rc = launch_assemble(c, A, true))) { cudaFree(d_V); cudaFree(d_H); return rc; }
+    if ((rc = assemble_mass_matrix(c, o, c->d_x))) { cudaFree(d_V); cudaFree(d_H); return rc; }
+    k_arnoldi_start<<<(unsigned)nb, 256, 0, c->stream>>>(d_V, (int)n, m);
+    for (int j = 0; j < m; j++) {
+        // w = K^{-1} (M v_j)   (f! of analyses.jl:949)
+        k_rowblock_spmv<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_M, d_V + (size_t)j * n, c->d_Ft, (int)n, c->W, c->KLB, c->nbatch, (int64_t)(m + 1) * n);
+        if ((rc = launch_factor(c, &o, 1, 1.0))) { cudaFree(d_V); cudaFree(d_H); return rc; }
+        k_arnoldi_orth<<<(unsigned)nb, 256, 0, c->stream>>>(d_V, d_H, c->d_p, (int)n, m, j);
+        c->stats.launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(H, d_H, nb * (size_t)(m + 1) * m * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (V) CK(cudaMemcpyAsync(V, d_V, nb * (size_t)(m + 1) * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->stats.ms_total = ms;
+    c->damping = 0;
+    cudaFree(d_V); cudaFree(d_H);
+    return GXB_OK;
 }
 
 int gxb_newton_direction(gxb_ctx* c, const gxb_opts* opts, const double* x, double* p) {

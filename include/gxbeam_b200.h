@@ -131,6 +131,18 @@ int gxb_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* x, d
 int gxb_newmark_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* init, double dt, const double* x, double* r,
                                   double* Jblk);
 
+/* system_mass_matrix! (src/system.jl:961-995): M = d r / d xdot at the states x, on gxb_pattern's blocks (kind=1).
+ * Mblk: nbatch x nblocks x 9. */
+int gxb_mass_matrix(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* Mblk);
+
+/* The Krylov part of solve_eigensystem (src/analyses.jl:943-965): K = steady Jacobian and M = mass matrix at the states x
+ * (what eigenvalue_analysis! builds at src/analyses.jl:1358-1359), then m Arnoldi steps with the operator v -> K^{-1} (M v)
+ * (the LinearMap `f!` of analyses.jl:949; every application re-runs the batched pivoted block-banded LU).
+ * Outputs: H, nbatch x (m+1) x m row-major upper Hessenberg with H[j+1][j] the residual norms; V (may be NULL),
+ * nbatch x (m+1) x nstates, the orthonormal Krylov basis.  The caller finishes like the reference: mu = eig(H[:m,:m]),
+ * sort by (abs, imag) descending, lambda = -1/mu, eigenvectors V[:m]' y   (Julia: `eigen`, Python: numpy.linalg.eig). */
+int gxb_eigen_arnoldi(gxb_ctx* ctx, const gxb_opts* opts, const double* x, int32_t m, double* H, double* V);
+
 /* One Newton direction p = -(J(x) \ r(x)) per instance (the `linsolve` of analyses.jl:3585), for parity tests of the
  * batched pivoted block-banded LU in isolation.  p: nbatch x nstates. */
 int gxb_newton_direction(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* p);
