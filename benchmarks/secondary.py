@@ -83,12 +83,47 @@ def gust(nb, nt, cpu_sample, damping=True):
                       "max_rel_diff_final_state": err}), flush=True)
 
 
+def blades(nb, nelem, nev, m, cpu_sample):
+    """BASELINE config 3: steady_state_analysis + linearised eigenvalue analysis of rotating wind-turbine blades."""
+    from oracle import pyoracle as O
+    w = workloads.wind_turbine_blade_batch(nb, nelem)
+    ctx = make_ctx(w, nb)
+    ctx.steady_solve_resident()
+    ms, its = 0.0, 0
+    for _ in range(3):
+        ctx.steady_solve_resident(); st = ctx.stats(); ms += st["ms_total"]; its += st["newton_iters"]
+    res = ctx.fetch()
+    t0 = time.perf_counter()
+    lam, vec, rr = ctx.eigenvalue_analysis(res["x"], nev=nev, m=m)
+    t_eig = time.perf_counter() - t0
+    es = ctx.stats(); ctx.close()
+    ns = min(nb, cpu_sample)
+    pk = O.Packed(w["start"], w["stop"], w["elems"][:ns], w["points_b"][:ns], w["pd"], w["pl"], w["bc"][:ns])
+    dyns = [O.make_dyn(wb=w["motion"][b, 3:6]) for b in range(ns)]
+    t0 = time.perf_counter(); ref = O.steady_solve_batch(pk, ns, dyns, force_scaling=w["force_scaling"][:ns]); dt = time.perf_counter() - t0
+    err = float(np.abs(res["x"][:ns] - ref["x"]).max() / np.abs(ref["x"]).max())
+    print(json.dumps({"workload": f"config 3: {nb} rotating blades x {nelem} elements (n={18 * nelem + 12}), steady_state_analysis + eigen (nev={nev}, m={m})",
+                      "steady_gpu_newton_iters_per_s": its / (ms * 1e-3), "steady_gpu_ms_per_batch": ms / 3, "steady_all_converged": bool(res["converged"].all()),
+                      "steady_cpu_newton_iters_per_s": float(ref["iters"].sum() / dt), "cpu_cores": O.num_threads(), "cpu_sample": ns,
+                      "steady_iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "steady_max_rel_diff": err,
+                      "eigen_device_s": es["ms_total"] * 1e-3, "eigen_wall_s_incl_host_ritz": t_eig, "eigen_max_ritz_residual": float(rr.max()),
+                      "lowest_freq_hz_first_instance": float(np.sort(np.abs(lam[0].imag))[0] / (2 * np.pi))}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steady-batch", type=int, default=4096)
     ap.add_argument("--gust-batch", type=int, default=512)
     ap.add_argument("--gust-steps", type=int, default=2000)
     ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--blades-batch", type=int, default=1024)
+    ap.add_argument("--blades-nelem", type=int, default=200)
+    ap.add_argument("--only", default="all", choices=["all", "steady", "gust", "blades"])
     a = ap.parse_args()
-    steady(a.steady_batch, 1024)
-    gust(a.gust_batch, a.gust_steps + 1, a.cpu_sample)
+    ap2 = a
+    if a.only in ("all", "steady"):
+        steady(a.steady_batch, 1024)
+    if a.only in ("all", "gust"):
+        gust(a.gust_batch, a.gust_steps + 1, a.cpu_sample)
+    if a.only in ("all", "blades"):
+        blades(a.blades_batch, a.blades_nelem, 20, 70, 64)

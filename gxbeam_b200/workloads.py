@@ -106,3 +106,58 @@ def rotating_blade_batch(nbatch=1, seed=1234 + 1, rpm_jitter=0.0):
     fs = np.full(nbatch, default_force_scaling(asm))
     return dict(start=start, stop=stop, points=points, points_b=pts, pd=pd, pl=pl, elems=elems, bc=bc, motion=motion, force_scaling=fs,
                 nelem=nelem, nbatch=nbatch, asm=asm)
+
+
+WT_STIFFNESS = np.array([[2.389e9, 1.524e6, 6.734e6, -3.382e7, -2.627e7, -4.736e8],
+                         [1.524e6, 4.334e8, -3.741e6, -2.935e5, 1.527e7, 3.835e5],
+                         [6.734e6, -3.741e6, 2.743e7, -4.592e5, -6.869e5, -4.742e6],
+                         [-3.382e7, -2.935e5, -4.592e5, 2.167e7, -6.279e5, 1.430e6],
+                         [-2.627e7, 1.527e7, -6.869e5, -6.279e5, 1.970e7, 1.209e7],
+                         [-4.736e8, 3.835e5, -4.742e6, 1.430e6, 1.209e7, 4.406e8]])
+WT_MASS = np.array([[258.053, 0.0, 0.0, 0.0, 7.07839, -71.6871],
+                    [0.0, 258.053, 0.0, -7.07839, 0.0, 0.0],
+                    [0.0, 0.0, 258.053, 71.6871, 0.0, 0.0],
+                    [0.0, -7.07839, 71.6871, 48.59, 0.0, 0.0],
+                    [7.07839, 0.0, 0.0, 0.0, 2.172, 0.0],
+                    [-71.6871, 0.0, 0.0, 0.0, 0.0, 46.418]])
+
+
+def wind_turbine_blade_batch(nbatch=1024, nelem=200, seed=1234 + 3, nspeeds=16):
+    """BASELINE config 3: rotating wind-turbine blades (straight, L = 60 m, the fully populated 6x6 stiffness / mass of
+    test/examples/wind-turbine-blade.jl:19-37, root clamped), stiffness and mass scaled per design by U(0.8, 1.2), rotor-speed
+    sweep ωb = (0, 0, Ω_j), Ω_j = nspeeds values in [0, 2] rad/s; instance b = (design b // nspeeds, speed b % nspeeds).
+    steady_state_analysis + linearised eigenvalue analysis (nev = 20), n = 18·nelem + 12.
+    """
+    rng = np.random.default_rng(seed)
+    L = 60.0
+    xs = np.linspace(0.0, L, nelem + 1)
+    points = np.stack([xs, 0 * xs, 0 * xs], 1)
+    start = np.arange(1, nelem + 1, dtype=np.int64)
+    stop = np.arange(2, nelem + 2, dtype=np.int64)
+    ndes = (nbatch + nspeeds - 1) // nspeeds
+    ks = rng.uniform(0.8, 1.2, ndes)
+    ms = rng.uniform(0.8, 1.2, ndes)
+    comp0 = np.linalg.inv(WT_STIFFNESS)
+    speeds = np.linspace(0.0, 2.0, nspeeds)
+    elems = np.zeros((nbatch, nelem, 91))
+    elems[:, :, 0] = L / nelem
+    elems[:, :, 1] = ((xs[:-1] + xs[1:]) / 2)[None, :]
+    elems[:, :, 76] = elems[:, :, 80] = elems[:, :, 84] = 1.0
+    elems[:, :, 85:91] = 0.01
+    fs = np.zeros(nbatch)
+    motion = np.zeros((nbatch, 12))
+    for b in range(nbatch):
+        d = b // nspeeds
+        comp = comp0 / ks[d]
+        elems[b, :, 4:40] = comp.ravel(order="F")[None, :]
+        elems[b, :, 40:76] = (WT_MASS * ms[d]).ravel(order="F")[None, :]
+        a = np.abs(comp).ravel()
+        fs[b] = 2.0 ** np.ceil(np.log2((a > np.finfo(float).eps).sum() / a.sum() / 100))
+        om = speeds[b % nspeeds]
+        motion[b, 5] = om                                   # angular_velocity = (0, 0, Ω)
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
+    pd, pl, bc1 = pack_prescribed_conditions(nelem + 1, pcs)
+    bc = np.tile(bc1[None], (nbatch, 1, 1))
+    pts = np.tile(points[None], (nbatch, 1, 1))
+    return dict(start=start, stop=stop, points=points, points_b=pts, pd=pd, pl=pl, elems=elems, bc=bc, motion=motion, force_scaling=fs,
+                nelem=nelem, nbatch=nbatch)

@@ -189,3 +189,33 @@ def test_pointmass_model_steady_jacobian_parity():
         J = api.blocks_to_dense(n, brow, bcol, Jb[0])
         assert np.abs(J - J_ref).max() <= 1e-12 * np.abs(J_ref).max()
     ctx.close()
+
+
+def test_long_chain_chunked_tiles_parity():
+    """N = 150 elements: the shared-memory tile holds fewer stations than the chain (chunked flush); BASELINE config 3 style blade."""
+    O = _oracle()
+    nb = 2
+    w = workloads.wind_turbine_blade_batch(nb, nelem=150, nspeeds=2)
+    w["motion"][:, 5] = [0.7, 1.9]
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    n = ctx.n
+    assert n == 18 * 150 + 12
+    rng = np.random.default_rng(2)
+    x = 0.05 * rng.random((nb, n))
+    brow, bcol = ctx.pattern()
+    r, Jb = ctx.residual_jacobian(x)
+    for b in range(nb):
+        pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
+        dyn = O.make_dyn(wb=w["motion"][b, 3:6])
+        r_ref = O.steady_residual(pk, dyn, x[b])
+        J_ref = O.steady_jacobian(pk, dyn, x[b])
+        assert np.abs(r[b] - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
+        J = api.blocks_to_dense(n, brow, bcol, Jb[b])
+        assert np.abs(J - J_ref).max() <= 1e-12 * np.abs(J_ref).max()
+    res = ctx.steady_solve()
+    ctx.close()
+    pk = O.Packed(w["start"], w["stop"], w["elems"], w["points_b"], w["pd"], w["pl"], w["bc"])
+    ref = O.steady_solve_batch(pk, nb, [O.make_dyn(wb=w["motion"][b, 3:6]) for b in range(nb)], force_scaling=w["force_scaling"])
+    assert res["converged"].all() and ref["converged"].all() and np.array_equal(res["iters"], ref["iters"])
+    for b in range(nb):
+        assert np.abs(res["x"][b] - ref["x"][b]).max() <= 1e-9 * np.abs(ref["x"][b]).max()
