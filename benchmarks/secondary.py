@@ -88,10 +88,13 @@ def blades(nb, nelem, nev, m, cpu_sample):
     from oracle import pyoracle as O
     w = workloads.wind_turbine_blade_batch(nb, nelem)
     ctx = make_ctx(w, nb)
-    ctx.steady_solve_resident()
+    # ~1 % of the designs x speeds never reach ftol = 1e-9 (line search stagnates — identically in the CPU oracle, i.e. in the
+    # reference's algorithm); cap the Newton iterations so that they do not dominate the measurement and report the count
+    opts = api.make_opts(iterations=50)
+    ctx.steady_solve_resident(opts)
     ms, its = 0.0, 0
     for _ in range(3):
-        ctx.steady_solve_resident(); st = ctx.stats(); ms += st["ms_total"]; its += st["newton_iters"]
+        ctx.steady_solve_resident(opts); st = ctx.stats(); ms += st["ms_total"]; its += st["newton_iters"]
     res = ctx.fetch()
     t0 = time.perf_counter()
     lam, vec, rr = ctx.eigenvalue_analysis(res["x"], nev=nev, m=m)
@@ -100,10 +103,10 @@ def blades(nb, nelem, nev, m, cpu_sample):
     ns = min(nb, cpu_sample)
     pk = O.Packed(w["start"], w["stop"], w["elems"][:ns], w["points_b"][:ns], w["pd"], w["pl"], w["bc"][:ns])
     dyns = [O.make_dyn(wb=w["motion"][b, 3:6]) for b in range(ns)]
-    t0 = time.perf_counter(); ref = O.steady_solve_batch(pk, ns, dyns, force_scaling=w["force_scaling"][:ns]); dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); ref = O.steady_solve_batch(pk, ns, dyns, force_scaling=w["force_scaling"][:ns], iterations=50); dt = time.perf_counter() - t0
     err = float(np.abs(res["x"][:ns] - ref["x"]).max() / np.abs(ref["x"]).max())
     print(json.dumps({"workload": f"config 3: {nb} rotating blades x {nelem} elements (n={18 * nelem + 12}), steady_state_analysis + eigen (nev={nev}, m={m})",
-                      "steady_gpu_newton_iters_per_s": its / (ms * 1e-3), "steady_gpu_ms_per_batch": ms / 3, "steady_all_converged": bool(res["converged"].all()),
+                      "steady_gpu_newton_iters_per_s": its / (ms * 1e-3), "steady_gpu_ms_per_batch": ms / 3, "steady_converged": int(res["converged"].sum()), "steady_converged_cpu_sample": int(ref["converged"].sum()),
                       "steady_cpu_newton_iters_per_s": float(ref["iters"].sum() / dt), "cpu_cores": O.num_threads(), "cpu_sample": ns,
                       "steady_iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "steady_max_rel_diff": err,
                       "eigen_device_s": es["ms_total"] * 1e-3, "eigen_wall_s_incl_host_ritz": t_eig, "eigen_max_ritz_residual": float(rr.max()),
@@ -126,4 +129,4 @@ if __name__ == "__main__":
     if a.only in ("all", "gust"):
         gust(a.gust_batch, a.gust_steps + 1, a.cpu_sample)
     if a.only in ("all", "blades"):
-        blades(a.blades_batch, a.blades_nelem, 20, 70, 64)
+        blades(a.blades_batch, a.blades_nelem, 20, 70, 256)
