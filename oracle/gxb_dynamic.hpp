@@ -15,6 +15,7 @@
 //   steady_element_residual! / _jacobian!                     src/element.jl:3019-3035, 3209-3229
 //   steady_system_residual! / _jacobian!                      src/system.jl:427-455, 693-720
 #pragma once
+#include <complex>
 #include "gxb_static.hpp"
 
 namespace gxo {
@@ -668,6 +669,270 @@ template <class T, class J> void system_mass_matrix(const Problem& P, const Indi
                 add33(jac, irow, icol + 6, masked(PV, false) * gamma / fs); add33(jac, irow, icol + 9, masked(PO, false) * gamma / fs);
                 add33(jac, irow + 3, icol + 6, masked(HV, true) * gamma / fs); add33(jac, irow + 3, icol + 9, masked(HO, true) * gamma / fs);
             }
+        }
+    }
+}
+
+// ================================================================= initial condition analysis ============================
+//   initial_point_displacement / _velocity_rates              src/point.jl:305-366, 448-512   (initial_point_displacement_rates = point_velocities :438)
+//   initial_point_properties                                  src/point.jl:683-757
+//   initial_point_residual!                                   src/point.jl:2168-2190
+//   initial_element_properties                                src/element.jl:230-371
+//   initial_element_residual!                                 src/element.jl:3046-3064
+//   initial_system_residual!                                  src/system.jl:466-521  (incl. the "prescribe velocity rates explicitly" rows)
+//   initial_system_jacobian!                                  src/system.jl:731-817
+// In this analysis the point columns are re-interpreted: x[icol..+5] holds (per component) a reaction load (displacement
+// prescribed), a velocity rate Vdot/Ωdot (rate_vars2 set) or a displacement u/θ; x[icol+6..+11] holds udot, θdot.  V, Ω are
+// the given initial values.
+//
+// JACOBIAN: the oracle does not restate the reference's ~600 lines of analytic initial-condition Jacobian blocks
+// (point.jl:1033-1124, 1548-1577, 1690-1701, 1853-1897; element.jl:850-1041, 1523-1548, 2072-2216, 2589-2683).  It takes the
+// complex-step derivative of the restated residual instead (exact to round-off); the reference's own test asserts that its
+// analytic Jacobian equals the ForwardDiff Jacobian of this residual to atol 1e-10 (test/jacobians.jl:207-236).  One
+// deliberate deviation keeps the two identical: follower point loads are rotated with θ taken from x[icol+3..5] even where
+// that slot holds Ωdot (point_loads calls the ordinary point_displacement, point.jl:24), while the analytic Jacobian
+// multiplies F_θ by the *initial* θ_θ mask (point.jl:1866-1871) — so that dependence is frozen (real part only) below.
+struct InitialParams {
+    const uint8_t* rv1 = nullptr;   // rate_vars1 [nstates]   (analyses.jl:1835-1846)
+    const uint8_t* rv2 = nullptr;   // rate_vars2 [nstates]   (analyses.jl:1848-1873)
+    const double* u0 = nullptr;     // [np][3] each
+    const double* th0 = nullptr;
+    const double* V0 = nullptr;
+    const double* Om0 = nullptr;
+    const double* Vdot0 = nullptr;
+    const double* Omdot0 = nullptr;
+};
+template <class T> T frozen(const T& v) { return T(realpart(v)); }
+
+// point.jl:305-366
+template <class T> void initial_point_displacement(const Problem& P, const T* x, int64_t ip, int64_t icol, const InitialParams& I, V3<T>& u, V3<T>& th) {
+    const uint8_t* pd = P.pd + 6 * ip;
+    const double* b = P.bc + 18 * ip;
+    for (int i = 0; i < 3; i++) {
+        u.v[i] = pd[i] ? T(b[i]) : (I.rv2[icol + 6 + i] ? T(I.u0[3 * ip + i]) : x[icol + i]);
+        th.v[i] = pd[3 + i] ? T(b[3 + i]) : (I.rv2[icol + 9 + i] ? T(I.th0[3 * ip + i]) : x[icol + 3 + i]);
+    }
+}
+// point.jl:448-512
+template <class T> void initial_point_velocity_rates(const Problem& P, const T* x, int64_t ip, int64_t icol, const InitialParams& I, V3<T>& Vdot, V3<T>& Omdot) {
+    const uint8_t* pd = P.pd + 6 * ip;
+    for (int i = 0; i < 3; i++) {
+        Vdot.v[i] = pd[i] ? T(0) : (I.rv2[icol + 6 + i] ? x[icol + i] : T(I.Vdot0[3 * ip + i]));
+        Omdot.v[i] = pd[3 + i] ? T(0) : (I.rv2[icol + 9 + i] ? x[icol + 3 + i] : T(I.Omdot0[3 * ip + i]));
+    }
+}
+// point_loads as called from initial_point_properties (point.jl:709, 20-39); see the note on follower loads above
+template <class T> void initial_point_loads(const Problem& P, const T* x, int64_t ip, int64_t icol, const InitialParams& I, V3<T>& F, V3<T>& M) {
+    const uint8_t* pd = P.pd + 6 * ip;
+    const uint8_t* pl = P.pl + 6 * ip;
+    const double* b = P.bc + 18 * ip;
+    V3<T> th;
+    for (int i = 0; i < 3; i++) th.v[i] = pd[3 + i] ? T(b[3 + i]) : (I.rv2[icol + 9 + i] ? frozen(x[icol + 3 + i]) : x[icol + 3 + i]);
+    M3<T> Ct = tr(get_C(th));
+    V3<T> Fc = cvec<T>(b + 6) + Ct * cvec<T>(b + 12);
+    V3<T> Mc = cvec<T>(b + 9) + Ct * cvec<T>(b + 15);
+    T fs = T(P.force_scaling);
+    for (int i = 0; i < 3; i++) {
+        F.v[i] = pl[i] ? Fc[i] : x[icol + i] * fs;
+        M.v[i] = pl[3 + i] ? Mc[i] : x[icol + 3 + i] * fs;
+    }
+}
+// point.jl:683-757
+template <class T> DynPoint<T> initial_point_properties(const Problem& P, const Indices& idx, const T* x, int64_t ip, const DynParams& D,
+                                                        const InitialParams& I, const V3<T>& ab, const V3<T>& alb) {
+    DynPoint<T> p;
+    static const double zeros36[36] = {0};
+    const double* m = P.pmass ? P.pmass + 36 * ip : zeros36;
+    p.mass11 = sub33<T>(m, 0, 0); p.mass12 = sub33<T>(m, 0, 1); p.mass21 = sub33<T>(m, 1, 0); p.mass22 = sub33<T>(m, 1, 1);
+    int64_t icol = idx.icol_point[ip] - 1;
+    initial_point_displacement(P, x, ip, icol, I, p.u, p.th);
+    p.C = get_C(p.th);
+    p.Qinv = get_Qinv(p.th);
+    initial_point_loads(P, x, ip, icol, I, p.F, p.M);
+    p.dx = cvec<T>(P.points + 3 * ip);
+    p.vb = cvec<T>(D.vb); p.wb = cvec<T>(D.wb); p.ab = ab; p.alb = alb;
+    p.gvec = cvec<T>(P.gravity);
+    p.V = cvec<T>(I.V0 + 3 * ip) + p.vb + cross(p.wb, p.dx + p.u);
+    p.Om = cvec<T>(I.Om0 + 3 * ip) + p.wb;
+    M3<T> Ct = tr(p.C);
+    p.Pm = Ct * (p.mass11 * (p.C * p.V)) + Ct * (p.mass12 * (p.C * p.Om));
+    p.H = Ct * (p.mass21 * (p.C * p.V)) + Ct * (p.mass22 * (p.C * p.Om));
+    p.udot = ld3(x, icol + 6); p.thdot = ld3(x, icol + 9);
+    initial_point_velocity_rates(P, x, ip, icol, I, p.Vdot, p.Omdot);
+    p.Vdot = p.Vdot + ab + cross(alb, p.dx + p.u) + cross(p.wb, p.udot);
+    p.Omdot = p.Omdot + alb;
+    M3<T> Cdot = -(p.C * tilde(p.Om - p.wb)), Cdt = tr(Cdot);
+    p.Pdot = Ct * (p.mass11 * (p.C * p.Vdot)) + Ct * (p.mass12 * (p.C * p.Omdot)) + Ct * (p.mass11 * (Cdot * p.V)) + Ct * (p.mass12 * (Cdot * p.Om)) +
+             Cdt * (p.mass11 * (p.C * p.V)) + Cdt * (p.mass12 * (p.C * p.Om));
+    p.Hdot = Ct * (p.mass21 * (p.C * p.Vdot)) + Ct * (p.mass22 * (p.C * p.Omdot)) + Ct * (p.mass21 * (Cdot * p.V)) + Ct * (p.mass22 * (Cdot * p.Om)) +
+             Cdt * (p.mass21 * (p.C * p.V)) + Cdt * (p.mass22 * (p.C * p.Om));
+    return p;
+}
+// point.jl:2168-2190
+template <class T> void initial_point_residual(const Problem& P, const Indices& idx, const T* x, int64_t ip, const DynParams& D, const InitialParams& I,
+                                               const V3<T>& ab, const V3<T>& alb, T* resid) {
+    int64_t irow = idx.irow_point[ip] - 1;
+    DynPoint<T> p = initial_point_properties(P, idx, x, ip, D, I, ab, alb);
+    V3<T> F, M, rV, rOm;
+    dynamic_point_resultants(p, F, M);
+    point_velocity_residuals(p, rV, rOm);
+    T fs = T(P.force_scaling);
+    for (int i = 0; i < 3; i++) { resid[irow + i] = -F[i] / fs; resid[irow + 3 + i] = -M[i] / fs; resid[irow + 6 + i] = rV[i]; resid[irow + 9 + i] = rOm[i]; }
+}
+// element.jl:230-371
+template <class T> DynElem<T> initial_element_properties(const Problem& P, const Indices& idx, const T* x, int64_t ie, const DynParams& D,
+                                                         const InitialParams& I, const V3<T>& ab, const V3<T>& alb) {
+    DynElem<T> p;
+    static_cast<ElemProps<T>&>(p) = static_element_properties(P, idx, x, ie);     // L, Cab, S, mass, F, M, γ, κ, gvec
+    const double* e = P.elems + 91 * ie;
+    V3<T> e1 = unit<T>(0);
+    int64_t ia = P.start[ie] - 1, ib = P.stop[ie] - 1;
+    int64_t ic1 = idx.icol_point[ia] - 1, ic2 = idx.icol_point[ib] - 1;
+    initial_point_displacement(P, x, ia, ic1, I, p.u1, p.th1);
+    initial_point_displacement(P, x, ib, ic2, I, p.u2, p.th2);
+    p.u = (p.u1 + p.u2) / T(2); p.th = (p.th1 + p.th2) / T(2);
+    p.C = get_C(p.th); p.CtCab = tr(p.C) * p.Cab; p.Q = get_Q(p.th); p.Qinv = get_Qinv(p.th);
+    p.dx = cvec<T>(e + 1);
+    p.vb = cvec<T>(D.vb); p.wb = cvec<T>(D.wb); p.ab = ab; p.alb = alb;
+    p.V1 = cvec<T>(I.V0 + 3 * ia); p.V2 = cvec<T>(I.V0 + 3 * ib); p.Om1 = cvec<T>(I.Om0 + 3 * ia); p.Om2 = cvec<T>(I.Om0 + 3 * ib);
+    p.V = (p.V1 + p.V2) / T(2) + p.vb + cross(p.wb, p.dx + p.u);
+    p.Om = (p.Om1 + p.Om2) / T(2) + p.wb;
+    M3<T> A = p.CtCab, At = tr(p.CtCab);
+    p.Pm = A * (p.mass11 * (At * p.V)) + A * (p.mass12 * (At * p.Om));
+    p.H = A * (p.mass21 * (At * p.V)) + A * (p.mass22 * (At * p.Om));
+    p.udot1 = ld3(x, ic1 + 6); p.thdot1 = ld3(x, ic1 + 9); p.udot2 = ld3(x, ic2 + 6); p.thdot2 = ld3(x, ic2 + 9);
+    p.udot = (p.udot1 + p.udot2) / T(2); p.thdot = (p.thdot1 + p.thdot2) / T(2);
+    V3<T> V1d, O1d, V2d, O2d;
+    initial_point_velocity_rates(P, x, ia, ic1, I, V1d, O1d);
+    initial_point_velocity_rates(P, x, ib, ic2, I, V2d, O2d);
+    p.Vdot = (V1d + V2d) / T(2) + ab + cross(alb, p.dx) + cross(alb, p.u) + cross(p.wb, p.udot);
+    p.Omdot = (O1d + O2d) / T(2) + alb;
+    M3<T> B = tilde(p.Om - p.wb) * p.CtCab, Bt = tr(B);
+    p.Pdot = A * (p.mass11 * (At * p.Vdot)) + A * (p.mass12 * (At * p.Omdot)) + A * (p.mass11 * (Bt * p.V)) + A * (p.mass12 * (Bt * p.Om)) +
+             B * (p.mass11 * (At * p.V)) + B * (p.mass12 * (At * p.Om));
+    p.Hdot = A * (p.mass21 * (At * p.Vdot)) + A * (p.mass22 * (At * p.Omdot)) + A * (p.mass21 * (Bt * p.V)) + A * (p.mass22 * (Bt * p.Om)) +
+             B * (p.mass21 * (At * p.V)) + B * (p.mass22 * (At * p.Om));
+    p.damping = D.structural_damping;
+    if (p.damping) {      // element.jl:333-368
+        const double* mu = e + 85;
+        p.mu11 = zero33<T>(); p.mu22 = zero33<T>();
+        for (int i = 0; i < 3; i++) { p.mu11.m[i][i] = T(mu[i]); p.mu22.m[i][i] = T(mu[3 + i]); }
+        p.du = p.u2 - p.u1; p.dth = p.th2 - p.th1;
+        p.dudot = p.udot2 - p.udot1; p.dthdot = p.thdot2 - p.thdot1;
+        p.dQ = get_dQ(p.th, p.dth, p.Q);
+        M3<T> Wt = tilde(p.Om - p.wb);
+        p.gamdot = -(At * (Wt * p.du)) + At * p.dudot - p.L * (At * (Wt * (p.Cab * e1)));
+        M3<T> CabT = tr(p.Cab);
+        p.kapdot = CabT * (p.Q * p.dthdot) + CabT * (p.dQ * p.thdot);
+        p.gam = p.gam - p.mu11 * p.gamdot;
+        p.kap = p.kap - p.mu22 * p.kapdot;
+    }
+    return p;
+}
+// element.jl:3046-3064
+template <class T> void initial_element_residual(const Problem& P, const Indices& idx, const T* x, int64_t ie, const DynParams& D, const InitialParams& I,
+                                                 const V3<T>& ab, const V3<T>& alb, T* resid) {
+    DynElem<T> p = initial_element_properties(P, idx, x, ie, D, I, ab, alb);
+    V3<T> ru, rth;
+    compatibility_residuals(p, ru, rth);
+    Resultants<T> r = dynamic_element_resultants(P, p, ie);
+    insert_element_residuals(P, idx, ie, ru, rth, r, resid);
+}
+// true where the equilibrium row of DOF k of point ip is replaced by `Vdot_k - Vdot0_k = 0`   (system.jl:491-513, 756-813)
+inline bool initial_row_replaced(const Problem& P, const Indices& idx, const InitialParams& I, int64_t ip, int k) {
+    int64_t icol = idx.icol_point[ip] - 1;
+    return !P.pd[6 * ip + k] && !I.rv1[icol + 6 + k] && I.rv2[icol + 6 + k];
+}
+// system.jl:466-521
+template <class T> void initial_system_residual(const Problem& P, const Indices& idx, const DynParams& D, const InitialParams& I, const T* x, T* resid) {
+    V3<T> ab, alb;
+    body_accelerations(idx, x, D, ab, alb);
+    for (int64_t ip = 0; ip < P.np; ip++) initial_point_residual(P, idx, x, ip, D, I, ab, alb, resid);
+    for (int64_t ie = 0; ie < P.ne; ie++) initial_element_residual(P, idx, x, ie, D, I, ab, alb, resid);
+    for (int64_t ip = 0; ip < P.np; ip++) {
+        int64_t irow = idx.irow_point[ip] - 1, icol = idx.icol_point[ip] - 1;
+        V3<T> Vdot, Omdot;
+        initial_point_velocity_rates(P, x, ip, icol, I, Vdot, Omdot);
+        for (int k = 0; k < 6; k++)
+            if (initial_row_replaced(P, idx, I, ip, k))
+                resid[irow + k] = (k < 3 ? Vdot[k] - T(I.Vdot0[3 * ip + k]) : Omdot[k - 3] - T(I.Omdot0[3 * ip + k - 3]));
+    }
+    if (P.two_dimensional) two_dimensional_residual(idx.nstates, x, resid);
+}
+// system.jl:731-817 by complex-step differentiation of initial_system_residual (see the note above).  Column compression: columns
+// further apart than kl+ku cannot share a row, so kl+ku+1 residual evaluations recover the whole band.
+template <class J> void initial_system_jacobian(const Problem& P, const Indices& idx, const DynParams& D, const InitialParams& I, const double* x,
+                                                int64_t kl, int64_t ku, J& jac) {
+    typedef std::complex<double> C;
+    const int64_t n = idx.nstates, stride = std::min<int64_t>(n, kl + ku + 1);
+    const double h = 1e-30;
+    std::vector<C> xc(n), rc(n);
+    jac.zero();
+    for (int64_t c = 0; c < stride; c++) {
+        for (int64_t i = 0; i < n; i++) xc[i] = C(x[i], (i % stride == c) ? h : 0.0);
+        std::fill(rc.begin(), rc.end(), C(0, 0));
+        initial_system_residual<C>(P, idx, D, I, xc.data(), rc.data());
+        for (int64_t i = 0; i < n; i++) {
+            double v = rc[i].imag() / h;
+            if (v == 0.0) continue;
+            // the unique column j ≡ c (mod stride) inside [i-kl, i+ku]
+            int64_t lo = std::max<int64_t>(0, i - kl);
+            int64_t j = lo + ((c - lo % stride) + stride) % stride;
+            if (j <= std::min(n - 1, i + ku)) jac.set(i, j, v);
+        }
+    }
+}
+// accumulates the column sums of a matrix assembled through add()/set()  (rate_vars = .!iszero.(sum(M, dims=1)), analyses.jl:1846)
+struct ColumnSum {
+    std::vector<double> s;
+    void add(int64_t, int64_t j, double v) { s[j] += v; }
+    void set(int64_t, int64_t j, double v) { s[j] += v; }
+};
+// analyses.jl:1835-1873: rate_vars1 from the mass matrix at x = 0, rate_vars2 with the element mass matrices replaced by the
+// compliance matrices and all point masses ignored
+inline void initial_rate_vars(const Problem& P, const Indices& idx, uint8_t* rv1, uint8_t* rv2) {
+    const int64_t n = idx.nstates;
+    std::vector<double> x(n, 0.0);
+    ColumnSum cs; cs.s.assign(n, 0.0);
+    system_mass_matrix<double>(P, idx, x.data(), 1.0, cs);
+    for (int64_t j = 0; j < n; j++) rv1[j] = cs.s[j] != 0.0;
+    std::vector<double> el(P.elems, P.elems + 91 * P.ne);
+    for (int64_t ie = 0; ie < P.ne; ie++) for (int k = 0; k < 36; k++) el[91 * ie + 40 + k] = el[91 * ie + 4 + k];
+    Problem P2 = P; P2.elems = el.data(); P2.pmass = nullptr;
+    cs.s.assign(n, 0.0);
+    system_mass_matrix<double>(P2, idx, x.data(), 1.0, cs);
+    for (int64_t j = 0; j < n; j++) rv2[j] = cs.s[j] != 0.0;
+}
+// initial_output (analyses.jl:2332-2390): the solved initial-condition vector -> DynamicSystem state vector `xx` and the point
+// rates (udot, θdot, Vdot, Ωdot; np x 12) that seed the Newmark march
+inline void initial_output(const Problem& P, const Indices& idx, const DynParams& D, const InitialParams& I, const double* x, double* xx, double* rates) {
+    const int64_t n = idx.nstates;
+    for (int64_t i = 0; i < n; i++) xx[i] = x[i];
+    V3<double> ab, alb;
+    body_accelerations(idx, x, D, ab, alb);
+    V3<double> vb = cvec<double>(D.vb), wb = cvec<double>(D.wb);
+    for (int64_t ip = 0; ip < P.np; ip++) {
+        int64_t icol = idx.icol_point[ip] - 1;
+        V3<double> u, th, F, M, Vdot, Omdot;
+        initial_point_displacement(P, x, ip, icol, I, u, th);
+        initial_point_loads(P, x, ip, icol, I, F, M);
+        V3<double> udot = ld3(x, icol + 6), thdot = ld3(x, icol + 9);
+        initial_point_velocity_rates(P, x, ip, icol, I, Vdot, Omdot);
+        V3<double> dx = cvec<double>(P.points + 3 * ip);
+        V3<double> V = cvec<double>(I.V0 + 3 * ip) + vb + cross(wb, dx + u), Om = cvec<double>(I.Om0 + 3 * ip) + wb;
+        Vdot = Vdot + ab + cross(alb, dx + u) + cross(wb, udot);
+        Omdot = Omdot + alb;
+        const uint8_t* pd = P.pd + 6 * ip; const uint8_t* pl = P.pl + 6 * ip;
+        for (int k = 0; k < 3; k++) {
+            // set_linear/angular_displacement! then set_external_forces/moments! (input.jl): displacement where !pd, load where !pl
+            if (!pd[k]) xx[icol + k] = u[k];
+            if (!pd[3 + k]) xx[icol + 3 + k] = th[k];
+            if (!pl[k]) xx[icol + k] = F[k] / P.force_scaling;
+            if (!pl[3 + k]) xx[icol + 3 + k] = M[k] / P.force_scaling;
+            xx[icol + 6 + k] = V[k]; xx[icol + 9 + k] = Om[k];
+            rates[12 * ip + k] = pd[k] ? 0.0 : udot[k];
+            rates[12 * ip + 3 + k] = pd[3 + k] ? 0.0 : thdot[k];
+            rates[12 * ip + 6 + k] = Vdot[k]; rates[12 * ip + 9 + k] = Omdot[k];
         }
     }
 }

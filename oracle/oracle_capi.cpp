@@ -434,3 +434,70 @@ int gxo_mass_matrix(const gxo_problem* q, const double* x, double* M) {
     return 0;
 }
 }  // extern "C"
+
+// ---------------------------------------------------------------- initial condition analysis ----
+extern "C" {
+struct gxo_initial {   // mirrors gxo::InitialParams
+    const uint8_t* rv1;
+    const uint8_t* rv2;
+    const double* u0; const double* th0; const double* V0; const double* Om0; const double* Vdot0; const double* Omdot0;
+};
+}
+static InitialParams to_initial(const gxo_initial* c) {
+    InitialParams I;
+    I.rv1 = c->rv1; I.rv2 = c->rv2; I.u0 = c->u0; I.th0 = c->th0; I.V0 = c->V0; I.Om0 = c->Om0; I.Vdot0 = c->Vdot0; I.Omdot0 = c->Omdot0;
+    return I;
+}
+extern "C" {
+int gxo_initial_rate_vars(const gxo_problem* q, uint8_t* rv1, uint8_t* rv2) {
+    Problem P = to_problem(q);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    initial_rate_vars(P, idx, rv1, rv2);
+    return 0;
+}
+int gxo_initial_residual(const gxo_problem* q, const gxo_dyn* d, const gxo_initial* c, const double* x, double* r) {
+    Problem P = to_problem(q); DynParams D = to_dyn(d); InitialParams I = to_initial(c);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    update_body_acceleration_indices(P, idx);
+    initial_system_residual<double>(P, idx, D, I, x, r);
+    return 0;
+}
+// dense column-major Jacobian; compressed = 1 uses the banded column compression the solver uses, 0 perturbs one column at a time
+int gxo_initial_jacobian(const gxo_problem* q, const gxo_dyn* d, const gxo_initial* c, const double* x, double* J, int compressed) {
+    Problem P = to_problem(q); DynParams D = to_dyn(d); InitialParams I = to_initial(c);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    update_body_acceleration_indices(P, idx);
+    int64_t n = idx.nstates;
+    DenseMat<double> M{n, J};
+    if (compressed) {
+        int64_t kl, ku; dynamic_bandwidth(P, idx, kl, ku);
+        initial_system_jacobian(P, idx, D, I, x, kl, ku, M);
+    } else {
+        initial_system_jacobian(P, idx, D, I, x, n, n, M);
+    }
+    return 0;
+}
+// initial_condition_analysis! (src/analyses.jl:1695-1945) for one instance.  c->rv1 / c->rv2 are ignored; the rate_vars
+// are computed here and returned in rv1 / rv2 (nstates each).  x0: initial-condition-layout guess or NULL (reset_state).
+// Outputs: x_ic (the solved initial-condition vector), xx (DynamicSystem state vector), rates (np x 12).
+int gxo_initial_condition(const gxo_problem* q, const gxo_dyn* d, const gxo_opts* opts, const gxo_initial* c, const double* x0, double* x_ic,
+                          double* xx, double* rates, uint8_t* rv1, uint8_t* rv2, int64_t* stats, double* resid_inf) {
+    Problem P = to_problem(q); DynParams D = to_dyn(d); InitialParams I = to_initial(c);
+    Indices idx = system_indices(P.ne, P.start, P.stop, false);
+    update_body_acceleration_indices(P, idx);
+    int64_t kl, ku; dynamic_bandwidth(P, idx, kl, ku);
+    int64_t n = idx.nstates;
+    initial_rate_vars(P, idx, rv1, rv2);
+    I.rv1 = rv1; I.rv2 = rv2;
+    BandMat J; J.init(n, kl, ku);
+    std::vector<double> F(n);
+    for (int64_t i = 0; i < n; i++) x_ic[i] = x0 ? x0[i] : 0.0;
+    auto rf = [&](const double* xv, double* FF) { initial_system_residual<double>(P, idx, D, I, xv, FF); };
+    auto jf = [&](const double* xv, BandMat& JJ) { initial_system_jacobian(P, idx, D, I, xv, kl, ku, JJ); };
+    NewtonResult r = newton_solve(n, x_ic, F.data(), J, rf, jf, to_opts(opts));
+    initial_output(P, idx, D, I, x_ic, xx, rates);
+    stats[0] = r.converged; stats[1] = r.iters; stats[2] = r.f_calls; stats[3] = r.ls_backtracks;
+    *resid_inf = r.resid_inf;
+    return r.error;
+}
+}  // extern "C"

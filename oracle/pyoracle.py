@@ -258,6 +258,62 @@ def newmark_run(pk: Packed, dyn: Dyn, tvec, x0, rates0, bc_t=None, **kw):
     return dict(x=xh, iters=its, converged=bool(conv.value), steps_done=int(done))
 
 
+# ---------------------------------------------------------------- initial condition analysis ----
+class Initial(C.Structure):
+    _fields_ = [("rv1", C.c_void_p), ("rv2", C.c_void_p), ("u0", C.c_void_p), ("th0", C.c_void_p), ("V0", C.c_void_p),
+                ("Om0", C.c_void_p), ("Vdot0", C.c_void_p), ("Omdot0", C.c_void_p)]
+
+
+class InitialConditions:
+    """u0, theta0, V0, Omega0, Vdot0, Omegadot0 ([np,3] each, default zeros) + rate_vars1/2 ([nstates] bool)."""
+
+    def __init__(self, npnt, n, u0=None, theta0=None, V0=None, Omega0=None, Vdot0=None, Omegadot0=None, rv1=None, rv2=None):
+        def arr(a):
+            return np.zeros((npnt, 3)) if a is None else np.ascontiguousarray(a, float).reshape(npnt, 3)
+        self.u0, self.th0, self.V0, self.Om0, self.Vdot0, self.Omdot0 = map(arr, (u0, theta0, V0, Omega0, Vdot0, Omegadot0))
+        self.rv1 = np.zeros(n, np.uint8) if rv1 is None else np.ascontiguousarray(rv1, np.uint8)
+        self.rv2 = np.zeros(n, np.uint8) if rv2 is None else np.ascontiguousarray(rv2, np.uint8)
+        self.c = Initial(_p(self.rv1), _p(self.rv2), _p(self.u0), _p(self.th0), _p(self.V0), _p(self.Om0), _p(self.Vdot0),
+                         _p(self.Omdot0))
+
+
+def initial_rate_vars(pk: Packed):
+    n = nstates(pk, static=False)
+    rv1, rv2 = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    lib().gxo_initial_rate_vars(C.byref(pk.c), _p(rv1), _p(rv2))
+    return rv1, rv2
+
+
+def initial_residual(pk: Packed, dyn: Dyn, ic: InitialConditions, x):
+    x = np.ascontiguousarray(x, float)
+    r = np.zeros_like(x)
+    lib().gxo_initial_residual(C.byref(pk.c), C.byref(dyn), C.byref(ic.c), _p(x), _p(r))
+    return r
+
+
+def initial_jacobian(pk: Packed, dyn: Dyn, ic: InitialConditions, x, compressed=True):
+    x = np.ascontiguousarray(x, float)
+    n = len(x)
+    J = np.zeros((n, n), order="F")
+    lib().gxo_initial_jacobian(C.byref(pk.c), C.byref(dyn), C.byref(ic.c), _p(x), _p(J), int(compressed))
+    return J
+
+
+def initial_condition(pk: Packed, dyn: Dyn, ic: InitialConditions, x0=None, **kw):
+    """initial_condition_analysis!: returns the solved initial-condition vector, the DynamicSystem state vector `x`, the point
+    rates [np,12] that seed newmark_run, and the rate_vars."""
+    n = nstates(pk, static=False)
+    x_ic, xx, rates = np.zeros(n), np.zeros(n), np.zeros((pk.np, 12))
+    stats = np.zeros(4, np.int64)
+    rinf = C.c_double(0)
+    o = make_opts(**kw)
+    x0a = None if x0 is None else np.ascontiguousarray(x0, float)
+    err = lib().gxo_initial_condition(C.byref(pk.c), C.byref(dyn), C.byref(o), C.byref(ic.c), _p(x0a), _p(x_ic), _p(xx), _p(rates),
+                                      _p(ic.rv1), _p(ic.rv2), _p(stats), C.byref(rinf))
+    return dict(x_ic=x_ic, x=xx, rates=rates, rv1=ic.rv1.copy(), rv2=ic.rv2.copy(), converged=bool(stats[0]), iters=int(stats[1]),
+                f_calls=int(stats[2]), ls_backtracks=int(stats[3]), resid_inf=rinf.value, error=err)
+
+
 # ---------------------------------------------------------------- mass matrix / eigen ----
 def mass_matrix(pk: Packed, x):
     x = np.ascontiguousarray(x, float)

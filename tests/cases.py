@@ -207,3 +207,50 @@ def pointmass_jl():
     pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
     return _pack(asm, pcs, pm=pms, ref_freq=np.array([2.8182004347800804, 17.66611982731975, 27.978670985969078, 49.93431945680836,
                                                      66.07594270678581]))
+
+
+def initial_jl():
+    """test/initial.jl:5-70: straight 31.5 in section (20 elements) + 6 in tip swept 45 degrees (4 elements), diagonal compliance / mass,
+    root clamped, body frame spinning (angular_velocity) and translating (linear_velocity); structural damping off."""
+    L1, n1, L2, n2 = 31.5, 20, 6.0, 4
+    len1, xp1, xm1, Cab1 = discretize_beam(L1, [0, 0, 0], n1)
+    c = 0.707106781186548
+    frame = np.array([[c, c, 0.0], [-c, c, 0.0], [0.0, 0.0, 1.0]])
+    len2, xp2, xm2, Cab2 = discretize_beam(L2, [31.5, 0, 0], n2, frame=frame)
+    nelem = n1 + n2
+    points = np.array(list(xp1) + list(xp2[1:]))
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    comp = np.diag([1.4974543276E-06, 4.7619054919E-06, 5.8036221902E-05, 3.1234387938E-03, 4.5274507258E-03, 1.7969451932E-05])
+    mass = np.diag([1.5813000000E-05, 1.5813000000E-05, 1.5813000000E-05, 1.3229801498E-06, 5.2301497500E-09, 1.3177500000E-06])
+    asm = Assembly(points, start, stop, compliance=[comp] * nelem, mass=[mass] * nelem, frames=list(Cab1) + list(Cab2),
+                   lengths=list(len1) + list(len2), midpoints=list(xm1) + list(xm2))
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0),
+           n1 + 1: PrescribedConditions(Fx=0, Fy=0, Fz=0, Mx=0, My=0, Mz=0)}
+    return _pack(asm, pcs, linear_velocity=np.array([0, 196.349540849362, 0]), angular_velocity=np.array([0, 0, 78.5398163397448]))
+
+
+def massless_initial_jl():
+    """test/issues/zeros.jl:170-222 "Massless Element Time Domain Initialization": 10 massless elements along y, point masses at points
+    2, 4, 6, 8, 10 (the last one halved), tip loads Fz = 30, My = -0.2.  The reference asserts `converged`."""
+    comp = np.array([[6.00001e-6, 0.0, 0.0, 7.25923e-7, -8.1452e-7, 0.0001], [0.0, 3.33333e-7, 0.0, 0.0, 0.0, 0.0],
+                     [0.0, 0.0, 3.33333e-7, 0.0, 0.0, 0.0], [7.25923e-7, 0.0, 0.0, 0.142898, -0.00285808, 1.31466e-5],
+                     [-8.1452e-7, 0.0, 0.0, -0.00285808, 0.200057, -2.0263e-5], [0.0001, 0.0, 0.0, 1.31466e-5, -2.0263e-5, 0.002]])
+    comp = np.triu(comp) + np.triu(comp, 1).T                      # Symmetric(...)
+    mass = np.array([[0.02, 0.0, 0.0, 0.0, -5.0e-7, -1.0e-7], [0.0, 0.02, 0.0, 5.0e-7, 0.0, 0.0001], [0.0, 0.0, 0.02, 1.0e-7, -0.0001, 0.0],
+                     [0.0, 5.0e-7, 1.0e-7, 1.0e-5, 1.0e-8, 2.0e-10], [-5.0e-7, 0.0, -0.0001, 1.0e-8, 6.0e-7, 9.0e-9],
+                     [-1.0e-7, 0.0001, 0.0, 2.0e-10, 9.0e-9, 1.0e-5]])
+    mass = np.triu(mass) + np.triu(mass, 1).T
+    nodes = np.array([[0, i / 10, 0] for i in range(11)], float)
+    nelem = 10
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    T = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+    asm = Assembly(nodes, start, stop, frames=[T] * nelem, compliance=[comp] * nelem)
+    Z = np.zeros((3, 3))
+    TT = np.block([[T, Z], [Z, T]])
+    pm = TT @ mass @ TT.T                                          # transform_properties(mass, T') = [T 0; 0 T] X [T' 0; 0 T'] (math.jl:43)
+    pms = {2: pm}
+    for i in range(4, nelem + 1, 2):
+        pms[i] = pm
+    pms[nelem] = pm / 2
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0), nelem + 1: PrescribedConditions(Fz=30, My=-0.2)}
+    return _pack(asm, pcs, pm=pms)
