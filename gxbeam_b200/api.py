@@ -47,7 +47,8 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_set_elements", "gxb_set_points", "gxb_set_bc", "gxb_set_dloads", "gxb_set_pmass", "gxb_set_body",
            "gxb_set_motion", "gxb_static_solve", "gxb_steady_solve", "gxb_steady_solve_resident", "gxb_upload_x0",
            "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction",
-           "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi"]
+           "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi",
+           "gxb_initial_condition", "gxb_initial_residual_jacobian"]
 
 _lib = None
 
@@ -235,6 +236,47 @@ class Context:
         self._ck(self.lib.gxb_newmark_residual_jacobian(self.h, C.byref(o), _ptr(init), C.c_double(dt), _ptr(x), _ptr(r), _ptr(J)))
         return r, J
 
+    # --- initial condition analysis ---
+    def _pack_ic(self, u0=None, theta0=None, V0=None, Omega0=None, Vdot0=None, Omegadot0=None):
+        """[nb, np, 18] = u0, theta0, V0, Omega0, Vdot0, Omegadot0 per point ([nb,np,3] or [np,3] each; None = zeros)."""
+        parts = (u0, theta0, V0, Omega0, Vdot0, Omegadot0)
+        if all(a is None for a in parts):
+            return None
+        ic = np.zeros((self.nbatch, self.np, 18))
+        for k, a in enumerate(parts):
+            if a is not None:
+                ic[:, :, 3 * k:3 * k + 3] = np.broadcast_to(np.asarray(a, float).reshape(-1, self.np, 3), (self.nbatch, self.np, 3))
+        return ic
+
+    def initial_condition(self, x0=None, opts=None, want_rate_vars=False, **ic):
+        """initial_condition_analysis! (src/analyses.jl:1695-1945) for the whole batch.  Returns the DynamicSystem states x [nb,n], the
+        point rates [nb,np,12] (udot, θdot, Vdot, Ωdot) and the convergence data; both stay resident for newmark_run(x0=None)."""
+        o = opts or make_opts(structural_damping=True)
+        nb, n = self.nbatch, self.n
+        icv = self._pack_ic(**ic)
+        x = np.empty((nb, n)); rates = np.empty((nb, self.np, 12))
+        conv = np.empty(nb, np.int32); its = np.empty(nb, np.int32); rinf = np.empty(nb)
+        rv = np.empty((nb, self.np, 12), np.uint8) if want_rate_vars else None
+        x0a = None if x0 is None else _f64(x0).reshape(nb, n)
+        self._ck(self.lib.gxb_initial_condition(self.h, C.byref(o), _ptr(icv), _ptr(x0a), _ptr(x), _ptr(rates), _ptr(conv), _ptr(its),
+                                                _ptr(rinf), _ptr(rv)))
+        out = dict(x=x, rates=rates, converged=conv.astype(bool), iters=its, resid_inf=rinf)
+        if want_rate_vars:
+            out["rate_vars1"], out["rate_vars2"] = rv[:, :, :6], rv[:, :, 6:]
+        return out
+
+    def initial_residual_jacobian(self, x, opts=None, rate_vars1=None, rate_vars2=None, **ic):
+        o = opts or make_opts()
+        x = _f64(x).reshape(self.nbatch, self.n)
+        icv = self._pack_ic(**ic)
+        r = np.empty_like(x)
+        brow, _ = self.pattern()
+        J = np.empty((self.nbatch, len(brow), 9))
+        rv1 = None if rate_vars1 is None else np.ascontiguousarray(rate_vars1, np.uint8)
+        rv2 = None if rate_vars2 is None else np.ascontiguousarray(rate_vars2, np.uint8)
+        self._ck(self.lib.gxb_initial_residual_jacobian(self.h, C.byref(o), _ptr(icv), _ptr(rv1), _ptr(rv2), _ptr(x), _ptr(r), _ptr(J)))
+        return r, J
+
     # --- eigenvalue analysis ---
     def mass_matrix(self, x, opts=None):
         o = opts or make_opts()
@@ -278,7 +320,7 @@ class Context:
         fd = np.ascontiguousarray(field, dtype=np.int32)
         self._ck(self.lib.gxb_set_bc_series(self.h, C.c_int64(nt), C.c_int32(K), _ptr(pt), _ptr(fd), _ptr(v)))
 
-    def newmark_run(self, tvec, x0, rates0, opts=None, save_every=1, want_history=True):
+    def newmark_run(self, tvec, x0=None, rates0=None, opts=None, save_every=1, want_history=True):
         """time_domain_analysis! from the initial state (x0 [nb,n], rates0 [nb,np,12] = udot, θdot, Vdot, Ωdot)."""
         o = opts or make_opts()
         tvec = _f64(tvec)
@@ -287,9 +329,10 @@ class Context:
         nsave = (nt - 1) // save_every + 1
         xh = np.empty((nb, nsave, n)) if want_history else None
         steps = np.empty(nb, np.int32); itot = np.empty(nb, np.int32); conv = np.empty(nb, np.int32)
-        self._ck(self.lib.gxb_newmark_run(self.h, C.byref(o), C.c_int64(nt), _ptr(tvec), _ptr(_f64(x0).reshape(nb, n)),
-                                          _ptr(_f64(rates0).reshape(nb, self.np, 12)), C.c_int64(save_every), _ptr(xh), _ptr(steps),
-                                          _ptr(itot), _ptr(conv)))
+        x0a = None if x0 is None else _f64(x0).reshape(nb, n)              # None: march from the state gxb_initial_condition left in HBM
+        r0a = None if rates0 is None else _f64(rates0).reshape(nb, self.np, 12)
+        self._ck(self.lib.gxb_newmark_run(self.h, C.byref(o), C.c_int64(nt), _ptr(tvec), _ptr(x0a), _ptr(r0a), C.c_int64(save_every), _ptr(xh),
+                                          _ptr(steps), _ptr(itot), _ptr(conv)))
         return dict(x=xh, steps_done=steps, iters_total=itot, converged=conv.astype(bool))
 
     def static_newton_direction(self, x, opts=None):

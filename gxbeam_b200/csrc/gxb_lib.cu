@@ -27,6 +27,7 @@
 #include "gxb_lu.cuh"
 #include "gxb_static.cuh"
 #include "gxb_dynamic.cuh"
+#include "gxb_initial.cuh"
 
 // ------------------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -67,8 +68,10 @@ struct gxb_ctx {
     double *d_paug = nullptr, *d_rates0 = nullptr, *d_series = nullptr; int *d_ser_point = nullptr, *d_ser_field = nullptr;
     int64_t ser_nt = 0; int ser_K = 0;
     double* d_M = nullptr;   // mass matrix in row-block storage (eigen analysis), allocated on demand
+    double* d_icS = nullptr; unsigned* d_rvm = nullptr;   // initial-condition analysis: [b][18][NP] initial values, [b][NP] rate_vars masks
+    bool have_initial = false;                            // d_x / d_rates0 hold the output of gxb_initial_condition
     int damping = 0;         // structural_damping of the current solve
-    int mode = 0;            // 0: steady residual, 1: Newmark residual (set by the time-marching driver)
+    int mode = 0;            // 0: steady residual, 1: Newmark residual (set by the time-marching driver), 2: initial-condition residual
     double c2dt = 0.0;
     bool body_state = false;                          // some DOF has pd & pl (body-frame acceleration would be a state)
     int W = 30, UW = 32, KLB = 2, rows_per_station = 12;
@@ -135,6 +138,97 @@ template <bool WANT_J, int MODE> __global__ void __launch_bounds__(256) k_assemb
     const int b = blockIdx.x;
     if (A.s.status && A.s.status[b] != A.s.want_status) return;
     dynamic_station<WANT_J, MODE>(A, b, threadIdx.x, asm_smem);
+}
+
+template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble_initial(InitArgs A) {
+    extern __shared__ __align__(16) double asm_smem[];
+    const int b = blockIdx.x;
+    if (A.d.s.status && A.d.s.status[b] != A.d.s.want_status) return;
+    initial_station<WANT_J>(A, b, threadIdx.x, asm_smem);
+}
+
+// rate_vars of the initial-condition analysis (src/analyses.jl:1835-1873): column sums of the mass matrix at x = 0 over the V/Ω
+// columns of each point (rate_vars1), and the same with the element mass blocks replaced by the compliance blocks and the point
+// masses ignored (rate_vars2).  One thread per (instance, point).  rvm bit k: rate_vars2, bit 8+k: equilibrium row replaced
+// (!pd & !rate_vars1 & rate_vars2, system.jl:491-513), bit 16+k: rate_vars1.
+__global__ void k_initial_rate_vars(const double* __restrict__ elemS, int elem_nf, const double* __restrict__ bcS, const double* __restrict__ pmS,
+                                    const unsigned short* __restrict__ flags, int N, int two_d, unsigned* __restrict__ rvm, int64_t nbatch) {
+    const int NP = N + 1;
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * NP) return;
+    const int64_t b = t / NP; const int p = (int)(t % NP);
+    auto theta = [&](int q) {
+        const unsigned fl = flags[q];
+        const double* bc = bcS + ((size_t)b * 18) * NP + q;
+        return mk((fl & 8) ? bc[3 * NP] : 0.0, (fl & 16) ? bc[4 * NP] : 0.0, (fl & 32) ? bc[5 * NP] : 0.0);
+    };
+    double s1[6] = {0, 0, 0, 0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0};
+    auto addcols = [&](double* s, const m3& PV, const m3& PO, const m3& HV, const m3& HO, double w) {
+        for (int r = 0; r < 3; r++) {
+            const bool lin = !(two_d && r == 2), ang = !(two_d && r < 2);       // lmask = (1,1,0), amask = (0,0,1) (point.jl:2043-2049)
+            for (int cc = 0; cc < 3; cc++) {
+                if (lin) { s[cc] += w * PV.a[3 * r + cc]; s[3 + cc] += w * PO.a[3 * r + cc]; }
+                if (ang) { s[cc] += w * HV.a[3 * r + cc]; s[3 + cc] += w * HO.a[3 * r + cc]; }
+            }
+        }
+    };
+    if (pmS) {
+        const double* pm = pmS + ((size_t)b * 36) * NP + p;
+        const m3 C = rot_C(theta(p));
+        addcols(s1, tmul(C, ldm(pm, NP) * C), tmul(C, ldm(pm + 9 * NP, NP) * C), tmul(C, ldm(pm + 18 * NP, NP) * C), tmul(C, ldm(pm + 27 * NP, NP) * C), 1.0);
+    }
+    for (int side = 0; side < 2; side++) {
+        const int e = p - 1 + side;
+        if (e < 0 || e >= N) continue;
+        const double* es = elemS + ((size_t)b * elem_nf) * N + e;
+        const m3 Cab = ldm(es + N, N);
+        const m3 Am = tmul(rot_C(0.5 * (theta(e) + theta(e + 1))), Cab), At = transpose(Am);
+        // ¼ A m A' enters the rows of both end points of the element
+        addcols(s1, (Am * ldm(es + 46 * N, N)) * At, (Am * ldm(es + 55 * N, N)) * At, (Am * ldm(es + 64 * N, N)) * At, (Am * ldm(es + 73 * N, N)) * At, 0.5);
+        addcols(s2, (Am * ldm(es + 10 * N, N)) * At, (Am * ldm(es + 19 * N, N)) * At, (Am * ldm(es + 28 * N, N)) * At, (Am * ldm(es + 37 * N, N)) * At, 0.5);
+    }
+    const unsigned fl = flags[p];
+    unsigned m = 0;
+    for (int k = 0; k < 6; k++) {
+        const bool r1 = s1[k] != 0.0, r2 = s2[k] != 0.0, pd = (fl >> k) & 1u;
+        if (r2) m |= 1u << k;
+        if (!pd && !r1 && r2) m |= 1u << (8 + k);
+        if (r1) m |= 1u << (16 + k);
+    }
+    rvm[t] = m;
+}
+
+// initial_output (src/analyses.jl:2332-2390): the solved initial-condition vector -> DynamicSystem states (in place) and the point
+// rates udot, θdot, Vdot, Ωdot ([b][NP][12]) that seed the Newmark march.  One thread per (instance, point).
+__global__ void k_initial_output(double* __restrict__ x, const double* __restrict__ bcS, const double* __restrict__ icS, const unsigned* __restrict__ rvm,
+                                 const unsigned short* __restrict__ flags, const double* __restrict__ pxS, const double* __restrict__ motion,
+                                 double* __restrict__ rates, int NP, int n, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * NP) return;
+    const int64_t b = t / NP; const int p = (int)(t % NP);
+    const unsigned fl = flags[p], rv = rvm[t];
+    const double* bc = bcS + ((size_t)b * 18) * NP + p;
+    const double* ic = icS + ((size_t)b * 18) * NP + p;
+    double* xp = x + b * n + 18 * p;
+    const double* mo = motion + 12 * b;
+    const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]), ab = mk(mo[6], mo[7], mo[8]), alb = mk(mo[9], mo[10], mo[11]);
+    double ut[6], rt[6];
+    for (int k = 0; k < 6; k++) {
+        const bool pd = (fl >> k) & 1u, r = (rv >> k) & 1u;
+        ut[k] = pd ? bc[(size_t)k * NP] : (r ? ic[(size_t)k * NP] : xp[k]);
+        rt[k] = pd ? 0.0 : (r ? xp[k] : ic[(size_t)(12 + k) * NP]);
+    }
+    const v3 u = mk(ut[0], ut[1], ut[2]);
+    const v3 udot = mk(xp[6], xp[7], xp[8]), thdot = mk(xp[9], xp[10], xp[11]);
+    const v3 dx = ldv(pxS + ((size_t)b * 3) * NP + p, NP);
+    const v3 V = ldv(ic + (size_t)6 * NP, NP) + vb + cross(wb, dx + u), Om = ldv(ic + (size_t)9 * NP, NP) + wb;
+    const v3 Vd = mk(rt[0], rt[1], rt[2]) + ab + cross(alb, dx + u) + cross(wb, udot), Od = mk(rt[3], rt[4], rt[5]) + alb;
+    double* ra = rates + ((size_t)b * NP + p) * 12;
+    for (int k = 0; k < 6; k++) if (!((fl >> k) & 1u)) xp[k] = ut[k];          // displacement where it is a state; loads stay
+    ra[0] = (fl & 1) ? 0.0 : udot.x; ra[1] = (fl & 2) ? 0.0 : udot.y; ra[2] = (fl & 4) ? 0.0 : udot.z;
+    ra[3] = (fl & 8) ? 0.0 : thdot.x; ra[4] = (fl & 16) ? 0.0 : thdot.y; ra[5] = (fl & 32) ? 0.0 : thdot.z;
+    ra[6] = Vd.x; ra[7] = Vd.y; ra[8] = Vd.z; ra[9] = Od.x; ra[10] = Od.y; ra[11] = Od.z;
+    xp[6] = V.x; xp[7] = V.y; xp[8] = V.z; xp[9] = Om.x; xp[10] = Om.y; xp[11] = Om.z;
 }
 
 // Newmark bookkeeping (src/analyses.jl:2693-2738): per point, rates at the previous time level from the old initialisation
@@ -454,6 +548,7 @@ __global__ void __launch_bounds__(256) k_arnoldi_orth(double* __restrict__ Vk, d
 static void free_batch(gxb_ctx* c) {
     cudaFree(c->d_exS); cudaFree(c->d_motion); c->d_exS = c->d_motion = nullptr;
     cudaFree(c->d_M); c->d_M = nullptr;
+    cudaFree(c->d_icS); cudaFree(c->d_rvm); c->d_icS = nullptr; c->d_rvm = nullptr; c->have_initial = false;
     cudaFree(c->d_paug); cudaFree(c->d_rates0); cudaFree(c->d_series); cudaFree(c->d_ser_point); cudaFree(c->d_ser_field);
     c->d_paug = c->d_rates0 = c->d_series = nullptr; c->d_ser_point = c->d_ser_field = nullptr; c->ser_nt = 0; c->ser_K = 0; c->mode = 0;
     cudaFree(c->d_elemS); cudaFree(c->d_bcS); cudaFree(c->d_dlS); cudaFree(c->d_pmS); cudaFree(c->d_grav); cudaFree(c->d_fs); cudaFree(c->d_xyz);
@@ -809,13 +904,16 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
             if (sm > configured) {
                 CK(cudaFuncSetAttribute(k_assemble_dynamic<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                 CK(cudaFuncSetAttribute(k_assemble_dynamic<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                CK(cudaFuncSetAttribute(k_assemble_initial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                 configured = sm;
             }
             if (c->mode == 0) k_assemble_dynamic<true, 0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
-            else k_assemble_dynamic<true, 1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+            else if (c->mode == 1) k_assemble_dynamic<true, 1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+            else { InitArgs I{D, c->d_icS, c->d_rvm}; k_assemble_initial<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(I); }
         } else {
             if (c->mode == 0) k_assemble_dynamic<false, 0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
-            else k_assemble_dynamic<false, 1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+            else if (c->mode == 1) k_assemble_dynamic<false, 1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+            else { InitArgs I{D, c->d_icS, c->d_rvm}; k_assemble_initial<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(I); }
         }
     }
     CK(cudaGetLastError());
@@ -857,7 +955,7 @@ static int launch_update(gxb_ctx* c, const gxb_opts* o, int mode) {
 
 extern "C" {
 
-static int solve_resident(gxb_ctx* c, const gxb_opts* opts);
+static int solve_resident(gxb_ctx* c, const gxb_opts* opts, int mode = 0);
 
 int gxb_static_solve_resident(gxb_ctx* c, const gxb_opts* opts) {
     NEED_BATCH("gxb_static_solve_resident");
@@ -914,20 +1012,21 @@ static int newton_rounds(gxb_ctx* c, const gxb_opts& o, Prof& prof, int burst) {
     return GXB_OK;
 }
 
-static int solve_resident(gxb_ctx* c, const gxb_opts* opts) {
+static int solve_resident(gxb_ctx* c, const gxb_opts* opts, int mode) {
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     c->stats = gxb_stats{};
     Prof prof{c, o.profile != 0};
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
     int rc;
-    c->mode = 0;
+    c->mode = mode;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (!c->have_x0) CK(cudaMemsetAsync(c->d_x, 0, nb * n * 8, c->stream));   // reset_state (system.jl:383-386)
     CK(cudaMemcpyAsync(c->d_xt, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));
     k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, ST_TRIAL, nb);
     CK(cudaMemsetAsync(c->ns.failcode, 0, nb * 4, c->stream)); CK(cudaMemsetAsync(c->ns.iters, 0, nb * 4, c->stream));
     CK(cudaMemsetAsync(c->ns.fcalls, 0, nb * 4, c->stream));
-    if ((rc = newton_rounds(c, o, prof, 1))) return rc;
+    if ((rc = newton_rounds(c, o, prof, 1))) { c->mode = 0; return rc; }
+    c->mode = 0;
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->stats.ms_total = ms;
@@ -999,7 +1098,9 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
                     int64_t save_every, double* x_hist, int32_t* steps_done, int32_t* iters_total, int32_t* converged) {
     NEED_BATCH("gxb_newmark_run");
     if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_newmark_run: context topology is not kind=1 (DynamicSystem)");
-    if (nt < 2 || !tvec || !x0 || !rates0) return fail(GXB_ERR_INVALID, "gxb_newmark_run: need nt >= 2, tvec, x0 and the initial rates");
+    if (nt < 2 || !tvec) return fail(GXB_ERR_INVALID, "gxb_newmark_run: need nt >= 2 and tvec");
+    if ((x0 == nullptr) != (rates0 == nullptr)) return fail(GXB_ERR_INVALID, "gxb_newmark_run: give both x0 and the initial rates, or neither");
+    if (!x0 && !c->have_initial) return fail(GXB_ERR_INVALID, "gxb_newmark_run: no initial state (pass x0 and rates0, or call gxb_initial_condition first)");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     c->damping = o.structural_damping ? 1 : 0;
     if (o.linear) return fail(GXB_ERR_UNSUPPORTED, "gxb_newmark_run: linear=true is not implemented on the device");
@@ -1017,8 +1118,11 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(d_steps, 1, nb);
     CK(cudaMemsetAsync(d_itot, 0, nb * 4, c->stream));
     CK(cudaMemsetAsync(c->ns.failcode, 0, nb * 4, c->stream));
-    CK(cudaMemcpyAsync(c->d_x, x0, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_rates0, rates0, nb * P * 12 * 8, cudaMemcpyHostToDevice, c->stream));
+    if (x0) {
+        CK(cudaMemcpyAsync(c->d_x, x0, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_rates0, rates0, nb * P * 12 * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->have_initial = false;
     CK(cudaMemsetAsync(c->d_paug, 0, nb * 12 * P * 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     if (d_hist) k_save_state<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_x, d_hist, (int)n, nsave, 0, c->nbatch);
@@ -1115,6 +1219,83 @@ int gxb_newmark_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double
     rc = gxb_residual_jacobian(c, opts, x, r, Jblk);
     c->mode = 0;
     return rc;
+}
+
+// ---- initial condition analysis (initial_condition_analysis!, src/analyses.jl:1695-1945) ----
+// uploads the initial values (ic: nbatch x np x 18 = u0, θ0, V0, Ω0, Vdot0, Ωdot0 per point, NULL = zeros) and builds the rate_vars
+// masks: computed on the device (analyses.jl:1835-1873) unless both rate_vars1 / rate_vars2 (nstates each, shared by the batch) are given
+static int initial_setup(gxb_ctx* c, const gxb_opts& o, const double* ic, const uint8_t* rv1, const uint8_t* rv2, const char* who) {
+    if (c->kind != 1) return fail(GXB_ERR_INVALID, std::string(who) + ": context topology is not kind=1 (DynamicSystem)");
+    if (c->body_state) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": a DOF with both displacement and load prescribed makes a body-frame "
+                                   "acceleration a state variable (system.jl:138-150); not implemented on the device");
+    if ((rv1 == nullptr) != (rv2 == nullptr)) return fail(GXB_ERR_INVALID, std::string(who) + ": give both rate_vars1 and rate_vars2 or neither");
+    const size_t nb = (size_t)c->nbatch, P = (size_t)c->np;
+    if (!c->d_icS) { CK(cudaMalloc(&c->d_icS, nb * 18 * P * 8)); CK(cudaMalloc(&c->d_rvm, nb * P * 4)); }
+    if (ic) {
+        int rc = stage_upload(c, ic, nb * P * 18 * 8); if (rc) return rc;
+        k_pack_transpose<<<grid1(nb * P * 18, 256), 256, 0, c->stream>>>(c->d_stage, c->d_icS, (int)P, 18, c->nbatch);
+        CK(cudaGetLastError());
+    } else CK(cudaMemsetAsync(c->d_icS, 0, nb * 18 * P * 8, c->stream));
+    if (rv1) {
+        std::vector<unsigned> m(nb * P, 0u);
+        for (size_t p = 0; p < P; p++) {
+            unsigned v = 0;
+            for (int k = 0; k < 6; k++) {
+                const bool r1 = rv1[18 * p + 6 + k] != 0, r2 = rv2[18 * p + 6 + k] != 0, pd = c->pd[6 * p + k] != 0;
+                if (r2) v |= 1u << k;
+                if (!pd && !r1 && r2) v |= 1u << (8 + k);
+                if (r1) v |= 1u << (16 + k);
+            }
+            for (size_t b = 0; b < nb; b++) m[b * P + p] = v;
+        }
+        CK(cudaMemcpy(c->d_rvm, m.data(), nb * P * 4, cudaMemcpyHostToDevice));
+    } else {
+        k_initial_rate_vars<<<grid1(nb * P, 128), 128, 0, c->stream>>>(c->d_elemS, GXB_ELEM_NF, c->d_bcS, c->d_pmS, c->d_flags, (int)c->ne,
+                                                                       o.two_dimensional, c->d_rvm, c->nbatch);
+        CK(cudaGetLastError());
+    }
+    c->stats.launches += 1;
+    return GXB_OK;
+}
+
+int gxb_initial_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double* ic, const uint8_t* rate_vars1, const uint8_t* rate_vars2,
+                                  const double* x, double* r, double* Jblk) {
+    NEED_BATCH("gxb_initial_residual_jacobian");
+    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    int rc = initial_setup(c, o, ic, rate_vars1, rate_vars2, "gxb_initial_residual_jacobian"); if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    c->mode = 2;
+    rc = gxb_residual_jacobian(c, opts, x, r, Jblk);
+    c->mode = 0;
+    return rc;
+}
+
+int gxb_initial_condition(gxb_ctx* c, const gxb_opts* opts, const double* ic, const double* x0, double* x, double* rates, int32_t* converged,
+                          int32_t* iters, double* resid_inf, uint8_t* rate_vars) {
+    NEED_BATCH("gxb_initial_condition");
+    gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    int rc = initial_setup(c, o, ic, nullptr, nullptr, "gxb_initial_condition"); if (rc) return rc;
+    if ((rc = gxb_upload_x0(c, x0))) return rc;
+    c->damping = o.structural_damping ? 1 : 0;
+    c->have_initial = false;
+    rc = solve_resident(c, &o, 2);
+    c->damping = 0;
+    if (rc) return rc;
+    const size_t nb = (size_t)c->nbatch, P = (size_t)c->np;
+    k_initial_output<<<grid1(nb * P, 128), 128, 0, c->stream>>>(c->d_x, c->d_bcS, c->d_icS, c->d_rvm, c->d_flags, c->d_xyz, c->d_motion, c->d_rates0,
+                                                                (int)P, (int)c->n, c->nbatch);
+    CK(cudaGetLastError());
+    c->stats.launches += 1;
+    c->have_initial = true;
+    if (rates) CK(cudaMemcpyAsync(rates, c->d_rates0, nb * P * 12 * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (rate_vars) {
+        std::vector<unsigned> m(nb * P);
+        CK(cudaMemcpyAsync(m.data(), c->d_rvm, nb * P * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (size_t t = 0; t < nb * P; t++)
+            for (int k = 0; k < 6; k++) { rate_vars[12 * t + k] = (m[t] >> (16 + k)) & 1u; rate_vars[12 * t + 6 + k] = (m[t] >> k) & 1u; }
+    }
+    return gxb_fetch(c, x, converged, iters, resid_inf);
 }
 
 // ---- eigenvalue analysis: mass matrix and the Krylov part of solve_eigensystem (src/analyses.jl:943-965) ----

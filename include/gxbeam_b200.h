@@ -131,6 +131,23 @@ int gxb_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* x, d
 int gxb_newmark_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* init, double dt, const double* x, double* r,
                                   double* Jblk);
 
+/* initial_condition_analysis! (consistent initial conditions of a time-domain run)        src/analyses.jl:1695-1945
+ *   rate_vars1/2 from two mass-matrix assemblies (analyses.jl:1835-1873), one nlsolve! with initial_system_residual!/jacobian!
+ *   (src/system.jl:466-521, 731-817), then initial_output (analyses.jl:2332-2390).
+ * ic: nbatch x np x 18 = u0, theta0, V0, Omega0, Vdot0, Omegadot0 of every point (NULL = zeros, the reference's default).
+ * x0: nbatch x nstates guess in the initial-condition layout or NULL (reset_state).  opts->structural_damping as in the reference
+ * (its time-domain default is true).  Body-frame velocities AND accelerations come from gxb_set_motion.
+ * Outputs: x (nbatch x nstates, DynamicSystem states), rates (nbatch x np x 12: udot, theta_dot, Vdot, Omegadot) -- exactly the
+ * x0 / rates0 of gxb_newmark_run, which may instead be called with x0 = rates0 = NULL right after this function to march from
+ * the state left in HBM.  rate_vars (optional): nbatch x np x 12 = rate_vars1[icol+6..11], rate_vars2[icol+6..11] per point. */
+int gxb_initial_condition(gxb_ctx* ctx, const gxb_opts* opts, const double* ic, const double* x0, double* x, double* rates,
+                          int32_t* converged, int32_t* iters, double* resid_inf, uint8_t* rate_vars);
+/* initial_system_residual! + initial_system_jacobian! (src/system.jl:466-521, 731-817) at given vectors x (nbatch x nstates, in the
+ * initial-condition layout).  rate_vars1 / rate_vars2: nstates flags each (shared by the batch), or both NULL to compute them
+ * as initial_condition_analysis! does. */
+int gxb_initial_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* ic, const uint8_t* rate_vars1,
+                                  const uint8_t* rate_vars2, const double* x, double* r, double* Jblk);
+
 /* system_mass_matrix! (src/system.jl:961-995): M = d r / d xdot at the states x, on gxb_pattern's blocks (kind=1).
  * Mblk: nbatch x nblocks x 9. */
 int gxb_mass_matrix(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* Mblk);
