@@ -23,7 +23,7 @@ struct Opts            # mirrors gxb_opts
     rho_hi::Float64
     rho_lo::Float64
     profile::Int32
-    reserved::Int32
+    structural_damping::Int32
 end
 
 check(rc) = rc == 0 || error("gxbeam_b200: " * unsafe_string(ccall((:gxb_last_error, LIB), Cstring, ())))
@@ -105,6 +105,75 @@ function static_analysis_batch(assemblies::Vector{<:Assembly};
             AssemblyState(view(x, :, i), system, assemblies[i]; prescribed_conditions=prescribed_conditions[i])
         end
         return states, conv .!= 0, iters
+    finally
+        ccall((:gxb_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
+    end
+end
+
+"""
+    time_domain_analysis_batch(assemblies, tvec; prescribed_conditions, linear_velocity, angular_velocity,
+        linear_acceleration, angular_acceleration, u0, theta0, V0, Omega0, Vdot0, Omegadot0, bc_series, ...)
+        -> (x_hist, rates0, converged)
+
+Batched counterpart of `time_domain_analysis` (src/analyses.jl:2510-2790) for chains: `initial_condition_analysis!`
+(:1695-1945) for every instance with `gxb_initial_condition`, then the Newmark march with `gxb_newmark_run` from the state left
+in HBM.  `bc_series = (points, fields, values[K, nt, nb])` holds the time-varying prescribed values evaluated by the caller from
+its `prescribed_conditions(t)` closures (field 0..17 = u, theta, F, M, Ff, Mf components).  `u0 ... Omegadot0` are `3 x np x nb`
+arrays (zeros by default, like the reference).  Returns the saved state vectors `x_hist[nstates, nsave, nb]`; each column goes
+into `AssemblyState(dx, x, system, assembly; prescribed_conditions)` exactly as at src/analyses.jl:2776.
+"""
+function time_domain_analysis_batch(assemblies::Vector{<:Assembly}, tvec;
+        prescribed_conditions, linear_velocity=[zeros(3) for _ in assemblies], angular_velocity=[zeros(3) for _ in assemblies],
+        linear_acceleration=[zeros(3) for _ in assemblies], angular_acceleration=[zeros(3) for _ in assemblies],
+        gravity=[zeros(3) for _ in assemblies], structural_damping=true, two_dimensional=false, ftol=1e-9, iterations=1000,
+        u0=nothing, theta0=nothing, V0=nothing, Omega0=nothing, Vdot0=nothing, Omegadot0=nothing, bc_series=nothing,
+        save_every=1, device=0)
+    nb = length(assemblies); a1 = assemblies[1]
+    np, ne = length(a1.points), length(a1.elements)
+    start = collect(Int64, a1.start); stop = collect(Int64, a1.stop)
+    pd, pl, _ = pack_conditions(np, prescribed_conditions[1])
+    bc = Array{Float64}(undef, 18, np, nb)
+    for i in 1:nb
+        bc[:, :, i] .= pack_conditions(np, prescribed_conditions[i])[3]
+    end
+    elems = pack_elements(assemblies)
+    pts = reduce(vcat, [reinterpret(Float64, a.points) for a in assemblies])
+    fs = [GXBeam.default_force_scaling(a) for a in assemblies]
+    motion = reduce(hcat, [vcat(linear_velocity[i], angular_velocity[i], linear_acceleration[i], angular_acceleration[i]) for i in 1:nb])
+    ic = zeros(18, np, nb)
+    for (k, a) in enumerate((u0, theta0, V0, Omega0, Vdot0, Omegadot0))
+        isnothing(a) || (ic[3k-2:3k, :, :] .= a)
+    end
+    opts = Ref(Opts(0, two_dimensional, ftol, iterations, 1e6, 1e-4, 0.5, 0.1, 0, structural_damping))
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gxb_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), ctx, device))
+    try
+        nstates = Ref{Int64}(0)
+        check(ccall((:gxb_topology, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+            ctx[], 1, np, ne, start, stop, pd, pl, nstates, C_NULL, C_NULL, C_NULL, C_NULL))
+        check(ccall((:gxb_set_batch, LIB), Cint, (Ptr{Cvoid}, Int64), ctx[], nb))
+        check(ccall((:gxb_set_elements, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], elems))
+        check(ccall((:gxb_set_points, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], pts))
+        check(ccall((:gxb_set_bc, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], bc))
+        check(ccall((:gxb_set_body, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx[], reduce(hcat, gravity), fs))
+        check(ccall((:gxb_set_motion, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], motion))
+        n = nstates[]
+        x0 = zeros(n, nb); rates0 = zeros(12, np, nb); conv0 = zeros(Int32, nb); it0 = zeros(Int32, nb); rinf = zeros(nb)
+        check(ccall((:gxb_initial_condition, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Opts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{UInt8}),
+            ctx[], opts, ic, C_NULL, x0, rates0, conv0, it0, rinf, C_NULL))
+        if !isnothing(bc_series)
+            points, fields, values = bc_series
+            check(ccall((:gxb_set_bc_series, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+                ctx[], length(tvec), length(points), Int32.(points), Int32.(fields), values))
+        end
+        nt = length(tvec); nsave = (nt - 1) ÷ save_every + 1
+        xh = zeros(n, nsave, nb); steps = zeros(Int32, nb); itot = zeros(Int32, nb); conv = zeros(Int32, nb)
+        check(ccall((:gxb_newmark_run, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Opts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+            ctx[], opts, nt, collect(Float64, tvec), C_NULL, C_NULL, save_every, xh, steps, itot, conv))
+        return xh, rates0, (conv0 .!= 0) .& (conv .!= 0)
     finally
         ccall((:gxb_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
     end
