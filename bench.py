@@ -216,6 +216,27 @@ def main():
         e2e_s += time.perf_counter() - t1
         e2e_iters += int(out["iters"].sum())
     barrier()
+    # the same step through the pipelined service (api.PipelinedSolver): 4 chunks on 4 lanes of this GPU, uploads serialised, so the
+    # PCIe transfer of chunk k+1 runs under the Newton solve of chunk k.  This is the reported e2e; the single-call figure is kept.
+    e2e_plain = e2e_iters / e2e_s if e2e_s > 0 else 0.0
+    if nb % 4 == 0 and nb >= 1024:
+        ctx.close()
+        ps = api.PipelinedSolver(w["start"], w["stop"], w["pd"], w["pl"], nb // 4, lanes=4, device=local)
+        for _ in range(2):
+            ps.solve(h_el, h_bc, h_fs, out, opts_fast)
+        barrier()
+        e2e_s, e2e_iters = 0.0, 0
+        for _ in range(args.steps):
+            t1 = time.perf_counter()
+            ps.solve(h_el, h_bc, h_fs, out, opts_fast)
+            e2e_s += time.perf_counter() - t1
+            e2e_iters += int(out["iters"].sum())
+        barrier()
+        assert out["converged"].all()
+        ps.close()
+        e2e_how = "wall clock around api.PipelinedSolver.solve (4 chunks x 4 lanes, host threads), pinned host buffers"
+    else:
+        e2e_how = "wall clock around the synchronous C-ABI calls, pinned host buffers"
     h2d = h_el.nbytes + h_bc.nbytes + h_fs.nbytes
     d2h = out["x"].nbytes + out["iters"].nbytes + out["resid_inf"].nbytes + 4 * nb
 
@@ -249,7 +270,7 @@ def main():
                        "l2": "inputs + Jacobian/U working set (~2.6 GB per step) exceed the 126 MB L2; no explicit flush",
                        "newton_iters_per_step": iters_all / args.steps, "wall_ms_per_step": wall_ms_max / args.steps},
             "e2e": {"value": e2e_iters_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s_max / args.steps, "timing": "wall clock around the synchronous C-ABI calls, pinned host buffers"},
+                    "ms_per_step": 1e3 * e2e_s_max / args.steps, "timing": e2e_how, "single_call_value_rank0": e2e_plain},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_factor_solve<2,2>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

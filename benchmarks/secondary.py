@@ -3,7 +3,8 @@
 
   steady : config-1 topology (24-element swept-tip rotating blade, n = 444), batch of rotor-speed variants, steady_state_analysis
   gust   : config 4 — 512-member gust ensemble, time_domain_analysis of 2000 Newmark steps (dt = 0.25 ms) on the same topology,
-           initial state = steady rotating equilibrium, structural damping on (the reference's default)
+           initial state from initial_condition_analysis like benchmark/benchmarks.jl:143-216 (or --gust-init steady), structural
+           damping on (the reference's default)
 Prints one JSON line per workload.
 """
 import argparse
@@ -48,7 +49,9 @@ def steady(nb, cpu_sample):
                       "cpu_sample": ns, "iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "max_rel_diff": err}), flush=True)
 
 
-def gust(nb, nt, cpu_sample, damping=True):
+def gust(nb, nt, cpu_sample, damping=True, init="ic"):
+    """init="ic": exactly benchmark/benchmarks.jl:143-216 -- time_domain_analysis without initial_state, i.e. initial_condition_analysis
+    of the undeformed spinning blade followed by the Newmark march; init="steady": start from the steady rotating equilibrium."""
     from oracle import pyoracle as O
     rng = np.random.default_rng(1234 + 4)
     w = workloads.rotating_blade_batch(nb)
@@ -57,13 +60,27 @@ def gust(nb, nt, cpu_sample, damping=True):
     tf1 = np.where(tvec < 0.2, 0.1 * (1 - np.sin(2 * np.pi * (tvec / 0.4 + 0.25))), 0.0)
     series = (amp[:, None] * tf1[None, :])[:, :, None]
     ctx = make_ctx(w, nb)
-    st = ctx.steady_solve()
-    ctx.set_bc_series([21], [7], series)
-    rates0 = np.zeros((nb, 25, 12))
     opts = api.make_opts(structural_damping=damping)
-    ctx.newmark_run(tvec[:21], st["x"], rates0, opts, want_history=False)      # warm-up
+    rates0 = np.zeros((nb, 25, 12))
+    ms_init, it_init, launches_init = 0.0, 0, 0
+
+    def start():
+        nonlocal ms_init, it_init, launches_init
+        ctx.set_bc(w["bc"])                                  # the march overwrites the prescribed values with the series
+        if init == "ic":
+            ini = ctx.initial_condition(opts=opts)
+            s0 = ctx.stats(); ms_init, it_init, launches_init = s0["ms_total"], s0["newton_iters"], s0["launches"]
+            assert ini["converged"].all()
+            return ini["x"], ini["rates"]
+        st = ctx.steady_solve()
+        return st["x"], rates0
+
+    ctx.set_bc_series([21], [7], series)
+    x0, r0 = start()
+    ctx.newmark_run(tvec[:21], x0, r0, opts, want_history=False)      # warm-up
     t0 = time.perf_counter()
-    res = ctx.newmark_run(tvec, st["x"], rates0, opts, save_every=nt - 1)
+    x0, r0 = start()
+    res = ctx.newmark_run(tvec, None, None, opts, save_every=nt - 1) if init == "ic" else ctx.newmark_run(tvec, x0, r0, opts, save_every=nt - 1)
     wall = time.perf_counter() - t0
     s = ctx.stats(); ctx.close()
     ns = min(nb, cpu_sample)
@@ -72,13 +89,22 @@ def gust(nb, nt, cpu_sample, damping=True):
         pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
         dyn = O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6], structural_damping=damping)
         bct = np.tile(w["bc"][b][None], (nt, 1, 1)); bct[:, 20, 7] = series[b, :, 0]
-        ref = O.newmark_run(pk, dyn, tvec, st["x"][b], rates0[b], bct)
+        if init == "ic":
+            ri = O.initial_condition(pk, dyn, O.InitialConditions(25, O.nstates(pk, static=False)))
+            cx0, cr0 = ri["x"], ri["rates"]; cpu_iters += ri["iters"]
+        else:
+            cx0, cr0 = x0[b], rates0[b]
+        ref = O.newmark_run(pk, dyn, tvec, cx0, cr0, bct)
         cpu_iters += int(ref["iters"].sum())
         err = max(err, float(np.abs(res["x"][b, -1] - ref["x"][-1]).max() / np.abs(ref["x"][-1]).max()))
     dt = time.perf_counter() - t0
-    print(json.dumps({"workload": f"time_domain_analysis, {nb}-member gust ensemble, {nt - 1} Newmark steps (config 4), structural_damping={damping}",
-                      "gpu_newton_iters_per_s": s["newton_iters"] / (s["ms_total"] * 1e-3), "gpu_s_per_run": s["ms_total"] * 1e-3, "gpu_wall_s": wall,
-                      "gpu_launches": s["launches"], "newton_iters": s["newton_iters"], "all_converged": bool(res["converged"].all()),
+    gpu_ms = s["ms_total"] + ms_init
+    print(json.dumps({"workload": f"time_domain_analysis, {nb}-member gust ensemble, {nt - 1} Newmark steps (config 4), structural_damping={damping}, "
+                                  f"initial state: {'initial_condition_analysis (as benchmarks.jl:143-216)' if init == 'ic' else 'steady state'}",
+                      "gpu_newton_iters_per_s": (s["newton_iters"] + it_init) / (gpu_ms * 1e-3), "gpu_s_per_run": gpu_ms * 1e-3,
+                      "gpu_s_initial_condition": ms_init * 1e-3, "gpu_wall_s": wall,
+                      "gpu_launches": s["launches"] + launches_init, "newton_iters": s["newton_iters"] + it_init,
+                      "all_converged": bool(res["converged"].all()),
                       "cpu_newton_iters_per_s_1core": cpu_iters / dt, "cpu_s_per_instance_1core": dt / ns, "cpu_sample": ns,
                       "max_rel_diff_final_state": err}), flush=True)
 
@@ -118,6 +144,7 @@ if __name__ == "__main__":
     ap.add_argument("--steady-batch", type=int, default=4096)
     ap.add_argument("--gust-batch", type=int, default=512)
     ap.add_argument("--gust-steps", type=int, default=2000)
+    ap.add_argument("--gust-init", default="ic", choices=["ic", "steady"])
     ap.add_argument("--cpu-sample", type=int, default=4)
     ap.add_argument("--blades-batch", type=int, default=1024)
     ap.add_argument("--blades-nelem", type=int, default=200)
@@ -127,6 +154,6 @@ if __name__ == "__main__":
     if a.only in ("all", "steady"):
         steady(a.steady_batch, 1024)
     if a.only in ("all", "gust"):
-        gust(a.gust_batch, a.gust_steps + 1, a.cpu_sample)
+        gust(a.gust_batch, a.gust_steps + 1, a.cpu_sample, init=a.gust_init)
     if a.only in ("all", "blades"):
         blades(a.blades_batch, a.blades_nelem, 20, 70, 256)

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
@@ -361,6 +362,69 @@ class BatchResult:
     resid_inf: np.ndarray  # [nbatch]
     indices: dict
     stats: dict
+
+
+class PipelinedSolver:
+    """`static_analysis_batch` / `steady_state_analysis_batch` as a persistent service with host buffers in and out.
+
+    `lanes` contexts live on one GPU, each with its own stream and chunk-sized device buffers.  A batch is cut into chunks that the
+    lanes take round-robin from host threads (ctypes releases the GIL), so the host->device copy and packing of chunk k+1 overlap the
+    Newton solve of chunk k and the device->host copy of chunk k-1: the PCIe transfer of the reference-layout inputs (728 B per
+    element) is hidden behind the solve instead of preceding it."""
+
+    def __init__(self, start, stop, pd, pl, chunk, lanes=2, device=0, kind=0):
+        self.chunk, self.kind = int(chunk), kind
+        self.ctxs = []
+        for _ in range(lanes):
+            c = Context(device)
+            self.indices = c.topology(start, stop, pd, pl, kind=kind)
+            c.set_batch(self.chunk)
+            self.ctxs.append(c)
+        self.n = self.ctxs[0].n
+        self.pool = ThreadPoolExecutor(lanes)
+        self.upload_lock = threading.Lock()
+
+    def solve(self, elements, prescribed_values, force_scaling, out, opts=None, gravity=None, points=None, motion=None):
+        """elements [nb, ne, 91], prescribed_values [nb, np, 18], force_scaling [nb]; out: dict of preallocated host arrays x [nb, n],
+        converged, iters (int32 [nb]), resid_inf [nb] (pinned memory makes the copies asynchronous).  nb must be a multiple of `chunk`."""
+        nb = elements.shape[0]
+        if nb % self.chunk:
+            raise GXBError("PipelinedSolver.solve: the batch must be a multiple of the chunk size")
+        o = opts or make_opts()
+        nchunks = nb // self.chunk
+        stats = [None] * len(self.ctxs)
+
+        def run(lane):
+            c = self.ctxs[lane]
+            acc = {}
+            for k in range(lane, nchunks, len(self.ctxs)):
+                sl = slice(k * self.chunk, (k + 1) * self.chunk)
+                # one upload at a time: the PCIe link is the shared resource; serialising the uploads staggers the lanes so that one
+                # lane's Newton solve runs under the other lane's transfer instead of both alternating in lock-step
+                with self.upload_lock:
+                    c.set_elements(elements[sl])
+                    c.set_bc(prescribed_values[sl])
+                    if points is not None:
+                        c.set_points(points[sl])
+                    if motion is not None:
+                        c.set_motion(motion[sl])
+                    c.set_body(None if gravity is None else gravity[sl], force_scaling[sl])
+                c.static_solve(o, None, {key: out[key][sl] for key in ("x", "converged", "iters", "resid_inf")})
+                st = c.stats()
+                for key, v in st.items():
+                    acc[key] = acc.get(key, 0) + v
+            stats[lane] = acc
+        list(self.pool.map(run, range(len(self.ctxs))))
+        tot = {}
+        for a in stats:
+            for key, v in (a or {}).items():
+                tot[key] = tot.get(key, 0) + v
+        return tot
+
+    def close(self):
+        self.pool.shutdown()
+        for c in self.ctxs:
+            c.close()
 
 
 def _solve_shard(device, start, stop, pd, pl, elems, bc, dl, pm, grav, fs, x0, opts):

@@ -24,6 +24,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef GXB_LU_TIMING
+#include <cstdio>
+#endif
 
 #define GXB_FULL 0xffffffffu
 
@@ -41,7 +44,8 @@ template <int KLB, int KUB> struct LuShape {
     static constexpr int STG = 6 * W + 6;           // one staged block-row: 6 rows + 6 rhs
     static constexpr int SM_STAGE = NS * ((STG > 6 * USTRIDE) ? STG : 6 * USTRIDE);
     static constexpr int SM_X = W + 2;              // x window for the back substitution
-    static constexpr int SM_DOUBLES = SM_P + SM_L + SM_STAGE + SM_X;
+    static constexpr int SM_BAR = 2 * NS;           // mbarriers of the two prefetch rings (factorisation, back substitution)
+    static constexpr int SM_DOUBLES = SM_P + SM_L + SM_STAGE + SM_X + SM_BAR;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -49,6 +53,35 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: ONE instruction moves a whole block-row (6 rows of the
+// row-block storage are contiguous in HBM) instead of ~5 predicated LDGSTS rounds with their address arithmetic ----
+#ifndef GXB_LU_TMA
+#define GXB_LU_TMA 1
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Wait for the phase with the given parity.  try_wait suspends the thread in hardware up to a time limit; the retry count is bounded so
+// that a lost transaction surfaces as a kernel error (trap) instead of a hang.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned a = smem_u32(bar);
+    for (int it = 0; it < (1 << 22); it++) {
+        unsigned ok;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
 
 // 1/x without the slow-path branch of the IEEE division: hardware seed (MUFU.RCP64H) + three Newton steps (< 2 ulp),
 // so that it can be scheduled in the shadow of the warp arg-max.  x = 0 / denormal / inf give inf or NaN, which the
@@ -77,6 +110,16 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
     double* Lsm = sm + S::SM_P;            // [6][6]
     double* stage = Lsm + S::SM_L;         // 6*W row entries, then 6 rhs
     double* xs = stage + S::SM_STAGE;      // x window
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + S::SM_X);   // [2][NS]
+#if GXB_LU_TMA
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 2 * S::NS; q++) mbar_init(bars + q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncwarp();
+#endif
 
     double a[W];
     double b = 0.0;
@@ -103,6 +146,15 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
     constexpr int NS = S::NS, STG = S::STG;
     auto prefetch_rows = [&](int step) {               // block-row needed at the end of elimination step `step`
         const int r0 = 6 * (step + KLB + 1);
+#if GXB_LU_TMA
+        if (r0 < n && lane == 0) {
+            double* dst = stage + (step % NS) * STG;
+            uint64_t* bar = bars + (step % NS);
+            mbar_expect_tx(bar, 6 * W * 8 + 48);
+            bulk_g2s(dst, Jrow + (size_t)r0 * W, 6 * W * 8, bar);
+            bulk_g2s(dst + 6 * W, rhs + r0, 48, bar);
+        }
+#else
         if (r0 < n) {
             double* dst = stage + (step % NS) * STG;
             const char* g = reinterpret_cast<const char*>(Jrow + (size_t)r0 * W);
@@ -111,13 +163,21 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
             if (lane < 3) cp_async16(reinterpret_cast<char*>(dst + 6 * W) + 16 * lane, reinterpret_cast<const char*>(rhs + r0) + 16 * lane);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
     };
 #pragma unroll
     for (int q = 0; q < NS - 1; q++) prefetch_rows(q);
 
+#ifdef GXB_LU_TIMING
+    long long tph[5] = {0, 0, 0, 0, 0}, tq = clock64(), tn;
+#define GXB_TICK(i) do { tn = clock64(); tph[i] += tn - tq; tq = tn; } while (0)
+#else
+#define GXB_TICK(i) do { } while (0)
+#endif
     for (int J = 0; J < nb; J++) {
         prefetch_rows(J + NS - 1);
         const bool have_next = 6 * (J + KLB + 1) < n;
+        GXB_TICK(4);
         // ---- A. panel factorisation on window columns 0..5 ----
         double m[6];
         int kp = 6;            // which pivot this lane became (6 = none)
@@ -143,6 +203,7 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
                 a[j] = fma(-m[k], pj, a[j]);
             }
         }
+        GXB_TICK(0);
         // ---- B/C. publish L11 rows, original trailing parts and rhs of the six pivot rows (one store set for all six) ----
         if (kp < 6) {
             double* Lr = Lsm + kp * 6;
@@ -168,6 +229,7 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
             for (int k = kk + 1; k < 6; k++) acc = fma(-e[k], Lsm[k * 6 + kk], acc);
             e[kk] = acc;
         }
+        GXB_TICK(1);
         // rank-6 trailing update, written into the shifted positions (window slides by one block)
 #pragma unroll
         for (int j = 0; j < T; j += 2) {
@@ -185,8 +247,13 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
 #pragma unroll
         for (int j = T; j < W; j++) a[j] = 0.0;
         const unsigned rmask = __ballot_sync(GXB_FULL, kp < 6);
+        GXB_TICK(2);
+#if GXB_LU_TMA
+        if (have_next) mbar_wait(bars + (J % NS), (unsigned)(J / NS) & 1u);        // the block-row of this step has landed
+#else
         asm volatile("cp.async.wait_group %0;\n" ::"n"(S::NS - 1) : "memory");   // the group of this step has landed
         __syncwarp();
+#endif
         if (kp < 6) {
             // this lane now holds the final U row of pivot kp (trailing part + rhs): stream it out, then take a new row
             double* urow = U + (size_t)(6 * J + kp) * UW;
@@ -208,35 +275,63 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
             }
         }
         __syncwarp();
+        GXB_TICK(3);
     }
+#ifdef GXB_LU_TIMING
+    const long long tfac_end = clock64();
+#endif
 
     // ---- back substitution, block by block from the end; lane k < 6 owns row 6J+k ----
     // U rows of block J-1 are prefetched (cp.async, double buffered) while block J is being solved.
     constexpr int US = S::USTRIDE;
+#if !GXB_LU_TMA
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
     __syncwarp();
     double* ub = stage;                                  // [NS][6][US], reuses the factorisation's staging area
-    auto prefetch_u = [&](int Jb) {
+    // q-th prefetch of the back substitution fetches block nb-1-q into slot q % NS (phase parity (q / NS) & 1)
+    auto prefetch_u = [&](int q) {
+        const int Jb = nb - 1 - q;
+#if GXB_LU_TMA
         if (Jb >= 0) {
-            double* dst = ub + (Jb % NS) * 6 * US;
+            uint64_t* bar = bars + NS + (q % NS);
+            if (lane == 0) mbar_expect_tx(bar, 6 * (W + 2) * 8);
+            __syncwarp();
+            if (lane < 6) bulk_g2s(ub + (q % NS) * 6 * US + lane * US, U + (size_t)(6 * Jb + lane) * UW, (W + 2) * 8, bar);
+        }
+#else
+        if (Jb >= 0) {
+            double* dst = ub + (q % NS) * 6 * US;
             const double* src = U + (size_t)(6 * Jb) * UW;
             constexpr int CH = (W + 2) / 2;                  // 16-byte chunks per row
             for (int c = lane; c < 6 * CH; c += 32) {
-                const int r = c / CH, q = c % CH;
-                cp_async16(dst + r * US + 2 * q, src + (size_t)r * UW + 2 * q);
+                const int r = c / CH, qq = c % CH;
+                cp_async16(dst + r * US + 2 * qq, src + (size_t)r * UW + 2 * qq);
             }
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
     };
     for (int c = lane; c < W + 2; c += 32) xs[c] = 0.0;
     __syncwarp();
+#if GXB_LU_TMA
+    // the U rows were written with ordinary stores by this warp: order them before the async-proxy reads of the bulk copies
+    __threadfence_block();
+    asm volatile("fence.proxy.async;\n" ::: "memory");
+    __syncwarp();
+#endif
 #pragma unroll
-    for (int q = 0; q < NS - 1; q++) prefetch_u(nb - 1 - q);
+    for (int q = 0; q < NS - 1; q++) prefetch_u(q);
     for (int J = nb - 1; J >= 0; J--) {
-        prefetch_u(J - (NS - 1));
+        const int qi = nb - 1 - J;                       // index of this block in the prefetch sequence
+        prefetch_u(qi + NS - 1);
+#if GXB_LU_TMA
+        mbar_wait(bars + NS + (qi % NS), (unsigned)(qi / NS) & 1u);
+#else
         asm volatile("cp.async.wait_group %0;\n" ::"n"(S::NS - 1) : "memory");
         __syncwarp();
-        const double* row = ub + (J % NS) * 6 * US + (lane < 6 ? lane : 0) * US;
+#endif
+        const double* row = ub + (qi % NS) * 6 * US + (lane < 6 ? lane : 0) * US;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         double up[6];
         {
@@ -276,5 +371,10 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
         }
         __syncwarp();
     }
+#ifdef GXB_LU_TIMING
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        printf("[lu timing KLB=%d nb=%d] cycles/block-step: panel %lld, publish+e %lld, trailing %lld, tail %lld, prefetch-issue %lld | back-subst/block %lld\n",
+               KLB, nb, tph[0] / nb, tph[1] / nb, tph[2] / nb, tph[3] / nb, tph[4] / nb, (clock64() - tfac_end) / nb);
+#endif
     return __any_sync(GXB_FULL, bad) ? 1 : 0;
 }
