@@ -15,6 +15,7 @@ import time
 
 import numpy as np
 
+PERSISTENT = 0
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gxbeam_b200 import api, workloads  # noqa: E402
@@ -34,10 +35,10 @@ def steady(nb, cpu_sample):
     w = workloads.rotating_blade_batch(nb, rpm_jitter=0.5)
     ctx = make_ctx(w, nb)
     for _ in range(3):
-        ctx.steady_solve_resident()
+        ctx.steady_solve_resident(api.make_opts(persistent=PERSISTENT))
     ms, its = 0.0, 0
     for _ in range(10):
-        ctx.steady_solve_resident(); st = ctx.stats(); ms += st["ms_total"]; its += st["newton_iters"]
+        ctx.steady_solve_resident(api.make_opts(persistent=PERSISTENT)); st = ctx.stats(); ms += st["ms_total"]; its += st["newton_iters"]
     res = ctx.fetch(); ctx.close()
     ns = min(nb, cpu_sample)
     pk = O.Packed(w["start"], w["stop"], w["elems"][:ns], w["points_b"][:ns], w["pd"], w["pl"], w["bc"][:ns])
@@ -60,7 +61,7 @@ def gust(nb, nt, cpu_sample, damping=True, init="ic"):
     tf1 = np.where(tvec < 0.2, 0.1 * (1 - np.sin(2 * np.pi * (tvec / 0.4 + 0.25))), 0.0)
     series = (amp[:, None] * tf1[None, :])[:, :, None]
     ctx = make_ctx(w, nb)
-    opts = api.make_opts(structural_damping=damping)
+    opts = api.make_opts(structural_damping=damping, persistent=PERSISTENT)
     rates0 = np.zeros((nb, 25, 12))
     ms_init, it_init, launches_init = 0.0, 0, 0
 
@@ -116,7 +117,7 @@ def blades(nb, nelem, nev, m, cpu_sample):
     ctx = make_ctx(w, nb)
     # ~1 % of the designs x speeds never reach ftol = 1e-9 (line search stagnates — identically in the CPU oracle, i.e. in the
     # reference's algorithm); cap the Newton iterations so that they do not dominate the measurement and report the count
-    opts = api.make_opts(iterations=50)
+    opts = api.make_opts(iterations=50, persistent=PERSISTENT)
     ctx.steady_solve_resident(opts)
     ms, its = 0.0, 0
     for _ in range(3):
@@ -145,11 +146,13 @@ if __name__ == "__main__":
     ap.add_argument("--gust-batch", type=int, default=512)
     ap.add_argument("--gust-steps", type=int, default=2000)
     ap.add_argument("--gust-init", default="ic", choices=["ic", "steady"])
+    ap.add_argument("--persistent", type=int, default=0, help="0 auto, 1 force, 2 forbid the persistent per-instance kernel")
     ap.add_argument("--cpu-sample", type=int, default=4)
     ap.add_argument("--blades-batch", type=int, default=1024)
     ap.add_argument("--blades-nelem", type=int, default=200)
     ap.add_argument("--only", default="all", choices=["all", "steady", "gust", "blades"])
     a = ap.parse_args()
+    globals()["PERSISTENT"] = a.persistent
     ap2 = a
     if a.only in ("all", "steady"):
         steady(a.steady_batch, 1024)

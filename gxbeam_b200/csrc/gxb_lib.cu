@@ -276,14 +276,10 @@ struct SolveArgs {
     double sign;          // sol = sign * (J \ F): -1 for the Newton direction, +1 for the eigen operator
 };
 
-template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? GXB_LU_MINBLOCKS : 2)) k_factor_solve(SolveArgs A) {
+// one warp: factorise + solve instance b, then start the line search (|p|_inf, φ0, dφ0, first trial point)
+template <int KLB, int KUB> __device__ void factor_instance(const SolveArgs& A, int64_t b, double* sm) {
     using S = LuShape<KLB, KUB>;
-    extern __shared__ __align__(16) double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (b >= A.nbatch) return;
-    if (!A.direction_only && A.ns.status[b] != ST_SOLVE) return;
-    double* sm = smem + (size_t)warp * S::SM_DOUBLES;
+    const int lane = threadIdx.x & 31;
     const size_t n = A.n;
     const double* F = A.F + b * n;
     double* p = A.p + b * n;
@@ -303,6 +299,15 @@ template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? G
         A.ns.ls_k[b] = 0; A.ns.ls_finite[b] = 0; A.ns.status[b] = ST_TRIAL;
     }
 }
+template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? GXB_LU_MINBLOCKS : 2)) k_factor_solve(SolveArgs A) {
+    using S = LuShape<KLB, KUB>;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= A.nbatch) return;
+    if (!A.direction_only && A.ns.status[b] != ST_SOLVE) return;
+    factor_instance<KLB, KUB>(A, b, smem + (size_t)warp * S::SM_DOUBLES);
+}
 
 struct UpdateArgs {
     int n; int mode;   // mode 0: initial evaluation, 1: line-search step, 2: linear (accept unconditionally, converged)
@@ -312,24 +317,29 @@ struct UpdateArgs {
     int* counter;
 };
 
-__global__ void __launch_bounds__(128) k_update(UpdateArgs A) {
-    const int b = blockIdx.x;
-    if (A.ns.status[b] != ST_TRIAL) return;
+// Armijo test / accept / convergence for instance b by the whole CTA (any block size up to 256); returns the new status
+__device__ int update_instance(const UpdateArgs& A, int b) {
     const size_t n = A.n;
     const double* Ft = A.Ft + b * n;
     // all per-instance scalars are read before the reduction barrier; thread 0 rewrites them only after it
     const double a1 = A.ns.a1[b], a2 = A.ns.a2[b], phi0 = A.ns.phi0[b], dphi0 = A.ns.dphi0[b], phx0 = A.ns.phx0[b];
     int k = A.ns.ls_k[b], nf = A.ns.ls_finite[b];
     int iters = A.ns.iters[b];
-    __shared__ double s_sum[4], s_max[4]; __shared__ int s_nan[4];
+    __shared__ double s_sum[8], s_max[8]; __shared__ int s_nan[8];
     double ss = 0.0, mx = 0.0; int nan = 0;
     for (int c = threadIdx.x; c < (int)n; c += blockDim.x) { double f = Ft[c]; ss = fma(f, f, ss); mx = fmax(mx, fabs(f)); nan |= (f != f); }
     for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(GXB_FULL, ss, o); mx = fmax(mx, __shfl_xor_sync(GXB_FULL, mx, o)); nan |= __shfl_xor_sync(GXB_FULL, nan, o); }
     if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = ss; s_max[threadIdx.x >> 5] = mx; s_nan[threadIdx.x >> 5] = nan; }
+    if (threadIdx.x < 8 && threadIdx.x >= (blockDim.x >> 5)) { s_sum[threadIdx.x] = 0.0; s_max[threadIdx.x] = 0.0; s_nan[threadIdx.x] = 0; }
     __syncthreads();
     ss = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
     mx = fmax(fmax(s_max[0], s_max[1]), fmax(s_max[2], s_max[3]));
     nan = s_nan[0] | s_nan[1] | s_nan[2] | s_nan[3];
+    if (blockDim.x > 128) {      // persistent kernels run with up to 8 warps; the 4-warp order above is kept for bit-compatibility
+        ss += (s_sum[4] + s_sum[5]) + (s_sum[6] + s_sum[7]);
+        mx = fmax(mx, fmax(fmax(s_max[4], s_max[5]), fmax(s_max[6], s_max[7])));
+        nan |= s_nan[4] | s_nan[5] | s_nan[6] | s_nan[7];
+    }
     const double phx1 = 0.5 * ss;
     const bool finite = isfinite(ss) && !nan;
     double* x = A.x + b * n; double* xt = A.xt + b * n; double* F = A.F + b * n; const double* p = A.p + b * n;
@@ -394,8 +404,14 @@ __global__ void __launch_bounds__(128) k_update(UpdateArgs A) {
         A.ns.fcalls[b] += 1;
         A.ns.status[b] = newstatus;
         if (failcode) A.ns.failcode[b] = failcode;
-        if (newstatus == ST_SOLVE || newstatus == ST_TRIAL) atomicAdd(A.counter, 1);
+        if (A.counter && (newstatus == ST_SOLVE || newstatus == ST_TRIAL)) atomicAdd(A.counter, 1);
     }
+    return newstatus;
+}
+__global__ void __launch_bounds__(128) k_update(UpdateArgs A) {
+    const int b = blockIdx.x;
+    if (A.ns.status[b] != ST_TRIAL) return;
+    update_instance(A, b);
 }
 
 __global__ void k_fill_int(int* p, int v, int64_t n) { int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (t < n) p[t] = v; }
@@ -956,6 +972,10 @@ static int launch_update(gxb_ctx* c, const gxb_opts* o, int mode) {
 extern "C" {
 
 static int solve_resident(gxb_ctx* c, const gxb_opts* opts, int mode = 0);
+struct MarchBuffers;
+static bool use_persistent(const gxb_ctx* c, const gxb_opts& o, bool marching);
+static int64_t straggler_threshold(const gxb_ctx* c, const gxb_opts& o);
+static int launch_persistent(gxb_ctx* c, const gxb_opts& o, int mode, const MarchBuffers* mb, int resume = 0);
 
 int gxb_static_solve_resident(gxb_ctx* c, const gxb_opts* opts) {
     NEED_BATCH("gxb_static_solve_resident");
@@ -1008,6 +1028,12 @@ static int newton_rounds(gxb_ctx* c, const gxb_opts& o, Prof& prof, int burst) {
         CK(cudaMemcpyAsync(c->h_counter, c->d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         if (*c->h_counter == 0) break;
+        // straggler hand-off: the few instances that are still iterating finish in the persistent kernel (one CTA each, no more
+        // batch-wide rounds paced by the slowest instance); finished instances exit at once
+        if (c->mode != 1 && *c->h_counter <= straggler_threshold(c, o)) {
+            if ((rc = launch_persistent(c, o, c->mode, nullptr, 1))) return rc;
+            break;
+        }
     }
     return GXB_OK;
 }
@@ -1025,7 +1051,9 @@ static int solve_resident(gxb_ctx* c, const gxb_opts* opts, int mode) {
     k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, ST_TRIAL, nb);
     CK(cudaMemsetAsync(c->ns.failcode, 0, nb * 4, c->stream)); CK(cudaMemsetAsync(c->ns.iters, 0, nb * 4, c->stream));
     CK(cudaMemsetAsync(c->ns.fcalls, 0, nb * 4, c->stream));
-    if ((rc = newton_rounds(c, o, prof, 1))) { c->mode = 0; return rc; }
+    if (use_persistent(c, o, false)) rc = launch_persistent(c, o, mode, nullptr);
+    else rc = newton_rounds(c, o, prof, 1);
+    if (rc) { c->mode = 0; return rc; }
     c->mode = 0;
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));
@@ -1072,6 +1100,189 @@ __global__ void k_step_end(const int* status, const int* iters, int* alive, int*
     steps_done[b] += 1;
     iters_total[b] += iters[b];
     if (status[b] != ST_DONE) alive[b] = 0;
+}
+
+}  // extern "C"   (persistent kernels are templates)
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent per-instance solver: ONE CTA owns one instance and runs its whole Newton iteration -- and, for time marching, its
+// whole time loop -- without returning to the host: assembly by the CTA (thread per station), pivoted band LU by warp 0, Armijo /
+// convergence logic by the CTA, all through the same device functions and the same per-instance state as the multi-kernel path.
+// This is the latency regime's answer (few instances per SM: BASELINE config 4 has 512, config 3's stragglers run alone): no
+// launch or host-synchronisation cost per round, and every instance does exactly the rounds IT needs instead of the batch maximum.
+// MODE 0: steady solve, 1: Newmark march (nt time levels), 2: initial-condition solve.
+struct PersistArgs {
+    DynArgs D;                 // D.s.x = xt, D.s.r = Ft, D.s.Jrow = J (as in the multi-kernel rounds)
+    const double* icS; const unsigned* rvm;     // MODE 2
+    SolveArgs S;
+    UpdateArgs Up;             // Up.counter = nullptr
+    int resume;                // MODE 0/2: continue instances left in ST_SOLVE / ST_TRIAL by the multi-kernel rounds (stragglers)
+    // time marching (MODE 1)
+    int64_t nt; const double* tvec;             // device copy of the time vector
+    double* bcS; const double* series; const int* ser_point; const int* ser_field; int K; int64_t ser_nt;
+    double* paug; const double* rates0;
+    int* alive; int* steps; int* itot;
+    double* hist; int64_t nsave, save_every;
+};
+
+// separate (non-inlined) functions: each phase gets its own register allocation instead of one allocation for the fused kernel
+__device__ __noinline__ void persist_factor(const SolveArgs& S, int b, double* smem) { factor_instance<3, 4>(S, b, smem); }
+__device__ __noinline__ int persist_update(const UpdateArgs& U, int b) { return update_instance(U, b); }
+template <int MODE> __device__ __noinline__ void persist_assemble(const PersistArgs& P, const DynArgs& D, int b, double* smem) {
+    if (MODE == 2) { InitArgs I{D, P.icS, P.rvm}; initial_station<true>(I, b, threadIdx.x, smem); }
+    else dynamic_station<true, (MODE == 2 ? 0 : MODE)>(D, b, threadIdx.x, smem);
+}
+
+template <int MODE> __global__ void __launch_bounds__(256) k_persistent_dynamic(PersistArgs P) {
+    extern __shared__ __align__(16) double psm[];
+    const int b = blockIdx.x;
+    const int n = P.Up.n, NP = P.D.s.N + 1;
+    double* x = P.Up.x + (size_t)b * n;
+    double* xt = P.Up.xt + (size_t)b * n;
+    DynArgs D = P.D;
+    const int64_t nsteps = MODE == 1 ? P.nt - 1 : 1;
+#ifdef GXB_PERSIST_TIMING
+    long long ptime[4] = {0, 0, 0, 0};
+    const long long t_begin = clock64();
+#endif
+    for (int64_t it = 1; it <= nsteps; it++) {
+        if (MODE == 1) {
+            if (!P.alive[b]) break;                                   // uniform: written by thread 0 before a barrier
+            const double dt = P.tvec[it] - P.tvec[it - 1];
+            const double c_prev = it > 1 ? 2.0 / (P.tvec[it - 1] - P.tvec[it - 2]) : 0.0;
+            const double c_new = 2.0 / dt;
+            D.c2dt = c_new;
+            // prescribed values of the new time level, then the `paug` update (analyses.jl:2693-2738)
+            for (int k = threadIdx.x; k < P.K; k += blockDim.x)
+                P.bcS[((size_t)b * 18 + P.ser_field[k]) * NP + P.ser_point[k]] = P.series[((size_t)b * P.ser_nt + it) * P.K + k];
+            __syncthreads();
+            for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+                const double* xp = x + 18 * p;
+                const double* bc = P.bcS + ((size_t)b * 18) * NP + p;
+                const unsigned fl = P.D.s.flags[p];
+                double* pa = P.paug + ((size_t)b * 12) * NP + p;
+                for (int k = 0; k < 12; k++) {
+                    const double sv = (k < 6 && (fl & (1u << k))) ? bc[k * NP] : xp[k];
+                    const double rate = it == 1 ? P.rates0[((size_t)b * NP + p) * 12 + k] : c_prev * sv - pa[(size_t)k * NP];
+                    pa[(size_t)k * NP] = c_new * sv + rate;
+                }
+            }
+            for (int c = threadIdx.x; c < n; c += blockDim.x) xt[c] = x[c];     // initial guess = previous state (analyses.jl:3592)
+            if (threadIdx.x == 0) { P.Up.ns.iters[b] = 0; P.Up.ns.fcalls[b] = 0; }
+            __syncthreads();
+        }
+        // value_jacobian!! at the initial guess, then Newton rounds until this instance is done.  One call site per device function:
+        // the station code is tens of thousands of instructions, two inlined copies would thrash the instruction cache.
+        int st = ST_TRIAL;
+        UpdateArgs Uc = P.Up; Uc.mode = 0;
+        if (MODE != 1 && P.resume) {
+            st = P.Up.ns.status[b];
+            if (st != ST_SOLVE && st != ST_TRIAL) return;
+            Uc.mode = 1;
+        }
+#ifdef GXB_PERSIST_TIMING
+        long long tq = clock64(), tn;
+#define GXB_PTICK(i) do { tn = clock64(); ptime[i] += tn - tq; tq = tn; } while (0)
+#else
+#define GXB_PTICK(i) do { } while (0)
+#endif
+        for (;;) {
+            if (st == ST_SOLVE) {
+                // the assembly wrote its tiles into psm with ordinary stores; the factorisation fills the same bytes through the async
+                // proxy (TMA bulk copies): order the two proxies before warp 0 starts
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                __syncthreads();
+                if (threadIdx.x < 32) persist_factor(P.S, b, psm);
+                __syncthreads();
+                st = P.Up.ns.status[b];
+                GXB_PTICK(0);
+                if (st != ST_TRIAL) break;                            // singular Jacobian
+            }
+            persist_assemble<MODE>(P, D, b, psm);
+            __syncthreads();
+            GXB_PTICK(1);
+            st = persist_update(Uc, b);
+            Uc.mode = 1;
+            __syncthreads();
+            GXB_PTICK(2);
+            if (st != ST_SOLVE && st != ST_TRIAL) break;
+        }
+        if (MODE == 1) {
+            if (threadIdx.x == 0) {
+                P.steps[b] += 1; P.itot[b] += P.Up.ns.iters[b];
+                if (st != ST_DONE) P.alive[b] = 0;
+            }
+            if (P.hist && it % P.save_every == 0) {
+                double* h = P.hist + ((size_t)b * P.nsave + it / P.save_every) * n;
+                for (int c = threadIdx.x; c < n; c += blockDim.x) h[c] = x[c];
+            }
+            __syncthreads();
+        }
+    }
+#ifdef GXB_PERSIST_TIMING
+    if (threadIdx.x == 0 && (b == 0 || b == gridDim.x - 1))
+        printf("[persistent MODE=%d b=%d] cycles: factor %lld, assemble %lld, update %lld, total %lld (steps %lld)\n", MODE, b, ptime[0], ptime[1], ptime[2],
+               clock64() - t_begin, (long long)nsteps);
+#endif
+}
+
+extern "C" {
+
+// persistent per-instance path: policy + launch.  opts->persistent: 0 auto, 1 on, 2 off.  Auto picks it in the latency regime
+// (all CTAs co-resident with few warps per SM), where the multi-kernel rounds are bound by launch/synchronisation and by the
+// slowest instance of the batch.
+static bool use_persistent(const gxb_ctx* c, const gxb_opts& o, bool marching) {
+    if (c->kind != 1 || o.linear || o.profile) return false;
+    if (o.persistent == 1) return true;
+    if (o.persistent == 2) return false;
+    // measured on B200: with every instance needing about the same number of rounds the multi-kernel path wins or
+    // ties (its factorisation kernel keeps one warp per SM sub-partition); the persistent kernel pays off when a few instances need
+    // many more rounds than the rest -- which the multi-kernel driver detects itself and hands over (straggler hand-off below)
+    (void)marching;
+    return false;
+}
+// straggler hand-off: once at most this many instances are unfinished, the remaining rounds run in the persistent kernel
+static int64_t straggler_threshold(const gxb_ctx* c, const gxb_opts& o) {
+    if (c->kind != 1 || o.linear || o.profile || o.persistent == 2) return -1;
+    return std::min<int64_t>(c->sm_count, std::max<int64_t>(1, c->nbatch / 8));
+}
+struct MarchBuffers { int64_t nt = 0; const double* d_tvec = nullptr; int* alive = nullptr; int* steps = nullptr; int* itot = nullptr; double* hist = nullptr; int64_t nsave = 0, save_every = 1; };
+static int launch_persistent(gxb_ctx* c, const gxb_opts& o, int mode, const MarchBuffers* mb, int resume) {
+    PersistArgs P{};
+    P.resume = resume;
+    StaticArgs A = make_static_args(c, &o, c->d_xt, c->d_Ft, true, 0, false);
+    P.D.s = A; P.D.exS = c->d_exS; P.D.pxS = c->d_xyz; P.D.motion = c->d_motion; P.D.init = c->d_paug; P.D.c2dt = c->c2dt; P.D.damping = c->damping;
+    P.icS = c->d_icS; P.rvm = c->d_rvm;
+    const int bs = (int)((c->np + 31) / 32) * 32;
+    // a smaller tile chunk than the multi-kernel assembly: shared memory per CTA decides how many instances are resident per SM
+    const size_t budget = 64 * 1024;
+    int chunk = (int)std::min<size_t>((size_t)bs, (budget - (size_t)bs * GXB_XCH * 8) / (GXB_DTILE * 8));
+    P.D.chunk = chunk;
+    size_t sm = std::max(((size_t)bs * GXB_XCH + (size_t)chunk * GXB_DTILE) * 8, (size_t)LuShape<3, 4>::SM_DOUBLES * 8);
+    P.S.sign = -1.0; P.S.nb = (int)(c->n / 6); P.S.n = (int)c->n; P.S.nbatch = c->nbatch;
+    P.S.J = c->d_J; P.S.F = c->d_F; P.S.x = c->d_x; P.S.U = c->d_U; P.S.p = c->d_p; P.S.xt = c->d_xt; P.S.ns = c->ns;
+    P.S.maxstep = o.maxstep; P.S.linear = 0; P.S.direction_only = 0;
+    P.Up.n = (int)c->n; P.Up.x = c->d_x; P.Up.xt = c->d_xt; P.Up.F = c->d_F; P.Up.Ft = c->d_Ft; P.Up.p = c->d_p; P.Up.ns = c->ns;
+    P.Up.ftol = o.ftol; P.Up.c1 = o.c1; P.Up.rho_hi = o.rho_hi; P.Up.rho_lo = o.rho_lo; P.Up.iterations = o.iterations; P.Up.ls_iterations = 1000;
+    P.Up.counter = nullptr;
+    if (mb) {
+        P.nt = mb->nt; P.tvec = mb->d_tvec; P.bcS = c->d_bcS; P.series = c->d_series; P.ser_point = c->d_ser_point; P.ser_field = c->d_ser_field;
+        P.K = c->ser_K; P.ser_nt = c->ser_nt; P.paug = c->d_paug; P.rates0 = c->d_rates0;
+        P.alive = mb->alive; P.steps = mb->steps; P.itot = mb->itot; P.hist = mb->hist; P.nsave = mb->nsave; P.save_every = mb->save_every;
+    }
+    static thread_local size_t configured = 0;
+    if (sm > configured) {
+        CK(cudaFuncSetAttribute(k_persistent_dynamic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CK(cudaFuncSetAttribute(k_persistent_dynamic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CK(cudaFuncSetAttribute(k_persistent_dynamic<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        configured = sm;
+    }
+    if (mode == 0) k_persistent_dynamic<0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(P);
+    else if (mode == 1) k_persistent_dynamic<1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(P);
+    else k_persistent_dynamic<2><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(P);
+    CK(cudaGetLastError());
+    c->stats.launches += 1; c->stats.rounds += 1;
+    return GXB_OK;
 }
 
 int gxb_set_bc_series(gxb_ctx* c, int64_t nt, int32_t K, const int32_t* point, const int32_t* field, const double* values) {
@@ -1127,9 +1338,18 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     CK(cudaEventRecord(c->ev0, c->stream));
     if (d_hist) k_save_state<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_x, d_hist, (int)n, nsave, 0, c->nbatch);
     c->mode = 1;
-    for (int64_t it = 1; it < nt; it++) {
+    for (int64_t it = 1; it < nt; it++)
+        if (!(tvec[it] - tvec[it - 1] > 0.0)) { c->mode = 0; return fail(GXB_ERR_INVALID, "gxb_newmark_run: tvec must be strictly increasing"); }
+    double* d_tvec = nullptr;
+    const bool persistent = use_persistent(c, o, true);
+    if (persistent) {
+        CK(cudaMalloc(&d_tvec, nt * 8));
+        CK(cudaMemcpyAsync(d_tvec, tvec, nt * 8, cudaMemcpyHostToDevice, c->stream));
+        MarchBuffers mb; mb.nt = nt; mb.d_tvec = d_tvec; mb.alive = d_alive; mb.steps = d_steps; mb.itot = d_itot; mb.hist = d_hist; mb.nsave = nsave; mb.save_every = save_every;
+        if ((rc = launch_persistent(c, o, 1, &mb))) { c->mode = 0; cudaFree(d_tvec); return rc; }
+    }
+    for (int64_t it = 1; it < nt && !persistent; it++) {
         const double dt = tvec[it] - tvec[it - 1];
-        if (!(dt > 0.0)) { c->mode = 0; return fail(GXB_ERR_INVALID, "gxb_newmark_run: tvec must be strictly increasing"); }
         const double c_prev = it > 1 ? 2.0 / (tvec[it - 1] - tvec[it - 2]) : 0.0;
         c->c2dt = 2.0 / dt;
         k_step_prepare<<<(unsigned)nb, 32, 0, c->stream>>>(c->d_bcS, c->d_series, c->d_ser_point, c->d_ser_field, c->ser_K, c->ser_nt, it, c->d_x,
@@ -1154,7 +1374,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     if (iters_total) memcpy(iters_total, itot.data(), nb * 4);
     if (steps_done) CK(cudaMemcpy(steps_done, d_steps, nb * 4, cudaMemcpyDeviceToHost));
     if (x_hist) CK(cudaMemcpy(x_hist, d_hist, nb * nsave * n * 8, cudaMemcpyDeviceToHost));
-    cudaFree(d_alive); cudaFree(d_steps); cudaFree(d_itot); cudaFree(d_hist);
+    cudaFree(d_alive); cudaFree(d_steps); cudaFree(d_itot); cudaFree(d_hist); cudaFree(d_tvec);
     CK(cudaGetLastError());
     return GXB_OK;
 }

@@ -371,6 +371,15 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
         }
         __syncwarp();
     }
+#if GXB_LU_TMA
+    // the shared memory is reused by the caller (persistent kernels run assembly tiles through it): retire the barrier objects
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 2 * S::NS; q++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bars + q)) : "memory");
+    }
+    __syncwarp();
+#endif
 #ifdef GXB_LU_TIMING
     if (blockIdx.x == 0 && threadIdx.x == 0)
         printf("[lu timing KLB=%d nb=%d] cycles/block-step: panel %lld, publish+e %lld, trailing %lld, tail %lld, prefetch-issue %lld | back-subst/block %lld\n",

@@ -43,6 +43,10 @@ typedef struct gxb_opts {
     double c1, rho_hi, rho_lo; /* 1e-4, 0.5, 0.1 */
     int32_t profile;         /* !=0: time every kernel class with CUDA events (gxb_get_stats) */
     int32_t structural_damping; /* kind=1 only: structural_damping keyword (analyses.jl:397 default false, :1708 default true) */
+    int32_t persistent;      /* kind=1 only: 0 auto, 1 force, 2 forbid the persistent per-instance kernel (one CTA runs an instance's
+                                whole Newton loop / time loop; chosen automatically for small batches).  No effect on results beyond
+                                round-off in the line search's sums. */
+    int32_t reserved;
 } gxb_opts;
 
 /* Filled by gxb_get_stats after a solve. */

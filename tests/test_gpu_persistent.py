@@ -1,0 +1,106 @@
+"""GPU tests of the persistent per-instance kernel (one CTA runs an instance's whole Newton loop / time loop) against the
+multi-kernel rounds and the CPU oracle.  Both paths call the same device functions in the same order per instance; only the
+partition of the line search's sums over threads differs, so iteration counts must match and states agree to round-off."""
+import numpy as np
+import pytest
+
+from gxbeam_b200 import api, workloads
+from test_gpu_newmark import _ctx, _groups, _gust
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import pyoracle as O
+    return O
+
+
+@pytest.mark.parametrize("damping", [False, True])
+def test_steady_persistent_equals_multikernel_and_oracle(damping):
+    O = _oracle()
+    nb = 48
+    w = workloads.rotating_blade_batch(nb, rpm_jitter=0.5)
+    out = {}
+    for name, flag in (("persistent", 1), ("rounds", 2)):
+        ctx = _ctx(w, w["motion"], nb, w["points_b"])
+        out[name] = ctx.steady_solve(api.make_opts(structural_damping=damping, persistent=flag))
+        out[name + "_launches"] = ctx.stats()["launches"]
+        ctx.close()
+    a, b = out["persistent"], out["rounds"]
+    assert a["converged"].all() and b["converged"].all()
+    assert np.array_equal(a["iters"], b["iters"])
+    assert np.abs(a["x"] - b["x"]).max() <= 1e-11 * np.abs(b["x"]).max()
+    assert out["persistent_launches"] == 1 and out["rounds_launches"] > 5
+    for i in (0, nb - 1):
+        pk = O.Packed(w["start"], w["stop"], w["elems"][i], w["points"], w["pd"], w["pl"], w["bc"][i], force_scaling=w["force_scaling"][i])
+        ref = O.steady_solve(pk, O.make_dyn(vb=w["motion"][i, 0:3], wb=w["motion"][i, 3:6], structural_damping=damping))
+        assert ref["iters"] == int(a["iters"][i])
+        for name, ids in _groups(O, w).items():
+            assert np.abs(a["x"][i][ids] - ref["x"][ids]).max() <= 1e-9 * np.abs(ref["x"][ids]).max(), name
+
+
+def test_time_domain_persistent_equals_multikernel_and_oracle():
+    O = _oracle()
+    nb, nt = 8, 61
+    w, tvec, series = _gust(nb, nt, 0.015)
+    res = {}
+    for name, flag in (("persistent", 1), ("rounds", 2)):
+        opts = api.make_opts(structural_damping=True, persistent=flag)
+        ctx = _ctx(w, w["motion"], nb, w["points_b"])
+        ini = ctx.initial_condition(opts=opts)
+        assert ini["converged"].all()
+        ctx.set_bc_series([21], [7], series)
+        res[name] = ctx.newmark_run(tvec, opts=opts, save_every=5)
+        res[name + "_ini"] = ini
+        res[name + "_launches"] = ctx.stats()["launches"]
+        ctx.close()
+    a, b = res["persistent"], res["rounds"]
+    assert a["converged"].all() and b["converged"].all()
+    assert np.array_equal(res["persistent_ini"]["iters"], res["rounds_ini"]["iters"])
+    assert np.array_equal(a["iters_total"], b["iters_total"]) and np.array_equal(a["steps_done"], b["steps_done"])
+    assert np.abs(a["x"] - b["x"]).max() <= 1e-10 * np.abs(b["x"]).max()
+    assert res["persistent_launches"] == 1 and res["rounds_launches"] > 100
+    i = 3
+    pk = O.Packed(w["start"], w["stop"], w["elems"][i], w["points"], w["pd"], w["pl"], w["bc"][i], force_scaling=w["force_scaling"][i])
+    dyn = O.make_dyn(vb=w["motion"][i, 0:3], wb=w["motion"][i, 3:6], structural_damping=True)
+    ri = O.initial_condition(pk, dyn, O.InitialConditions(25, O.nstates(pk, static=False)))
+    bct = np.tile(w["bc"][i][None], (nt, 1, 1)); bct[:, 20, 7] = series[i, :, 0]
+    ref = O.newmark_run(pk, dyn, tvec, ri["x"], ri["rates"], bct)
+    assert int(a["iters_total"][i]) == int(ref["iters"].sum())
+    for name, ids in _groups(O, w).items():
+        err = np.abs(a["x"][i][:, ids] - ref["x"][::5][:, ids]).max()
+        assert err <= 1e-9 * np.abs(ref["x"][:, ids]).max(), (name, err)
+
+
+def test_persistent_instances_fail_independently():
+    """An instance that cannot converge (iteration cap) must not affect the others, and must stop marching on its own."""
+    nb, nt = 6, 21
+    w, tvec, series = _gust(nb, nt, 0.005)
+    series = series.copy(); series[2] *= 1e6                       # absurd load on one member: its Newton iteration hits the cap
+    opts = api.make_opts(structural_damping=True, persistent=1, iterations=4)
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    st = ctx.steady_solve(api.make_opts(persistent=1))
+    ctx.set_bc_series([21], [7], series)
+    res = ctx.newmark_run(tvec, st["x"], np.zeros((nb, 25, 12)), opts)
+    ctx.close()
+    ok = np.ones(nb, bool); ok[2] = False
+    assert np.array_equal(res["converged"], ok)
+    assert (res["steps_done"][ok] == nt).all() and res["steps_done"][2] < nt
+
+
+def test_straggler_handoff_matches_plain_rounds():
+    """Default policy: multi-kernel rounds, then the last few unfinished instances are handed to the persistent kernel.  Iteration
+    counts, convergence flags and states must equal the pure multi-kernel run (persistent = 2)."""
+    nb = 96
+    w = workloads.rotating_blade_batch(nb, rpm_jitter=0.9)
+    out = {}
+    for name, flag in (("auto", 0), ("rounds", 2)):
+        ctx = _ctx(w, w["motion"], nb, w["points_b"])
+        out[name] = ctx.steady_solve(api.make_opts(persistent=flag, iterations=12))
+        out[name + "_stats"] = ctx.stats()
+        ctx.close()
+    a, b = out["auto"], out["rounds"]
+    assert len(set(b["iters"].tolist())) > 1                       # the batch really has instances that need more rounds than others
+    assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["converged"], b["converged"])
+    assert np.abs(a["x"] - b["x"]).max() <= 1e-11 * np.abs(b["x"]).max()
+    assert out["auto_stats"]["launches"] < out["rounds_stats"]["launches"]
