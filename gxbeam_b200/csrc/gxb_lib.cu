@@ -1016,13 +1016,19 @@ static int newton_rounds(gxb_ctx* c, const gxb_opts& o, Prof& prof, int burst) {
         c->stats.rounds += 1;
         return GXB_OK;
     }
+    // Dynamic systems evaluate the trial point residual-first: the Jacobian (8x the work of the residual) is assembled only for the
+    // instances whose step was accepted AND that have to iterate again -- the Jacobian at the converged point is never needed
+    // (NLsolve evaluates value_jacobian!! at the top of the next iteration only).  Static systems keep the fused evaluation.
+    const bool residual_first = c->kind == 1;
+    StaticArgs A_next = make_static_args(c, &o, c->d_xt, c->d_Ft, true, ST_SOLVE, true);
     // the first burst goes out without looking at the counter: instances that were already converged at x0 early-exit
     for (;;) {
         for (int q = 0; q < burst; q++) {
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
             prof.begin(); if ((rc = launch_factor(c, &o, 0))) return rc; prof.end(c->stats.ms_factor);
-            prof.begin(); if ((rc = launch_assemble(c, A, true))) return rc; prof.end(c->stats.ms_assemble);
+            prof.begin(); if ((rc = launch_assemble(c, A, !residual_first))) return rc; prof.end(c->stats.ms_assemble);
             prof.begin(); if ((rc = launch_update(c, &o, 1))) return rc; prof.end(c->stats.ms_update);
+            if (residual_first) { prof.begin(); if ((rc = launch_assemble(c, A_next, true))) return rc; prof.end(c->stats.ms_assemble); }
             c->stats.rounds += 1;
         }
         CK(cudaMemcpyAsync(c->h_counter, c->d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1128,9 +1134,9 @@ struct PersistArgs {
 // separate (non-inlined) functions: each phase gets its own register allocation instead of one allocation for the fused kernel
 __device__ __noinline__ void persist_factor(const SolveArgs& S, int b, double* smem) { factor_instance<3, 4>(S, b, smem); }
 __device__ __noinline__ int persist_update(const UpdateArgs& U, int b) { return update_instance(U, b); }
-template <int MODE> __device__ __noinline__ void persist_assemble(const PersistArgs& P, const DynArgs& D, int b, double* smem) {
-    if (MODE == 2) { InitArgs I{D, P.icS, P.rvm}; initial_station<true>(I, b, threadIdx.x, smem); }
-    else dynamic_station<true, (MODE == 2 ? 0 : MODE)>(D, b, threadIdx.x, smem);
+template <int MODE, bool WANT_J> __device__ __noinline__ void persist_assemble(const PersistArgs& P, const DynArgs& D, int b, double* smem) {
+    if (MODE == 2) { InitArgs I{D, P.icS, P.rvm}; initial_station<WANT_J>(I, b, threadIdx.x, smem); }
+    else dynamic_station<WANT_J, (MODE == 2 ? 0 : MODE)>(D, b, threadIdx.x, smem);
 }
 
 template <int MODE> __global__ void __launch_bounds__(256) k_persistent_dynamic(PersistArgs P) {
@@ -1198,7 +1204,9 @@ template <int MODE> __global__ void __launch_bounds__(256) k_persistent_dynamic(
                 GXB_PTICK(0);
                 if (st != ST_TRIAL) break;                            // singular Jacobian
             }
-            persist_assemble<MODE>(P, D, b, psm);
+            const bool first_eval = Uc.mode == 0;
+            if (first_eval) persist_assemble<MODE, true>(P, D, b, psm);       // value_jacobian!! at the initial guess
+            else persist_assemble<MODE, false>(P, D, b, psm);                 // trial points: residual only
             __syncthreads();
             GXB_PTICK(1);
             st = persist_update(Uc, b);
@@ -1206,6 +1214,11 @@ template <int MODE> __global__ void __launch_bounds__(256) k_persistent_dynamic(
             __syncthreads();
             GXB_PTICK(2);
             if (st != ST_SOLVE && st != ST_TRIAL) break;
+            if (st == ST_SOLVE && !first_eval) {                              // accepted, iterate again: now the Jacobian at x
+                persist_assemble<MODE, true>(P, D, b, psm);
+                __syncthreads();
+                GXB_PTICK(1);
+            }
         }
         if (MODE == 1) {
             if (threadIdx.x == 0) {
