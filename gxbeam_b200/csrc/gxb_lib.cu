@@ -1016,10 +1016,11 @@ static int newton_rounds(gxb_ctx* c, const gxb_opts& o, Prof& prof, int burst) {
         c->stats.rounds += 1;
         return GXB_OK;
     }
-    // Dynamic systems evaluate the trial point residual-first: the Jacobian (8x the work of the residual) is assembled only for the
-    // instances whose step was accepted AND that have to iterate again -- the Jacobian at the converged point is never needed
-    // (NLsolve evaluates value_jacobian!! at the top of the next iteration only).  Static systems keep the fused evaluation.
-    const bool residual_first = c->kind == 1;
+    // Trial points are evaluated residual-first: the Jacobian (5-8x the work of the residual) is assembled only for the instances
+    // whose step was accepted AND that have to iterate again -- the Jacobian at the converged point is never needed (NLsolve
+    // evaluates value_jacobian!! at the top of the next iteration only), nor is it at rejected line-search points.
+    // Measured (B200): config 4 1.72 -> 1.46 s, config 3 steady 294 -> 130 ms, config 1 8.1 -> 7.5 ms, config 2 9.00 -> 8.91 ms.
+    static const bool residual_first = !(getenv("GXB_RESIDUAL_FIRST") && atoi(getenv("GXB_RESIDUAL_FIRST")) == 0);   // A/B switch
     StaticArgs A_next = make_static_args(c, &o, c->d_xt, c->d_Ft, true, ST_SOLVE, true);
     // the first burst goes out without looking at the counter: instances that were already converged at x0 early-exit
     for (;;) {
