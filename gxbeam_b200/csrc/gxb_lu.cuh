@@ -59,6 +59,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifndef GXB_LU_TMA
 #define GXB_LU_TMA 1
 #endif
+// Back substitution: 1 = column-oriented (each lane owns a pending row, one 6-term axpy per block), 0 = row-oriented dot products
+#ifndef GXB_LU_AXPY
+#define GXB_LU_AXPY 1
+#endif
+#ifndef GXB_LU_NSET
+#define GXB_LU_NSET 2
+#endif
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -106,6 +113,8 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
     static_assert(T % 2 == 0 && W % 2 == 0, "vector access needs even widths");
     const int lane = threadIdx.x & 31;
     const int n = 6 * nb;
+    // stored U row: AXPY layout [rhs, 1/pivot, panel(6), trailing(T)], else [panel(6), trailing(T), rhs, 1/pivot]
+    constexpr int UOFF_PANEL = GXB_LU_AXPY ? 2 : 0, UOFF_HEAD = GXB_LU_AXPY ? 0 : W;
     double* Psm = sm;                      // [6][PS]
     double* Lsm = sm + S::SM_P;            // [6][6]
     double* stage = Lsm + S::SM_L;         // 6*W row entries, then 6 rhs
@@ -214,7 +223,7 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
             for (int j = 0; j < T; j += 2) *reinterpret_cast<double2*>(Pr + j) = make_double2(a[6 + j], a[6 + j + 1]);
             Pr[T] = b;
             // panel part of the U row goes straight to global memory (entries left of the diagonal are never read back)
-            double* urow = U + (size_t)(6 * J + kp) * UW;
+            double* urow = U + (size_t)(6 * J + kp) * UW + UOFF_PANEL;
 #pragma unroll
             for (int j = 0; j < 6; j += 2) *reinterpret_cast<double2*>(urow + j) = make_double2(a[j], a[j + 1]);
         }
@@ -258,8 +267,8 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
             // this lane now holds the final U row of pivot kp (trailing part + rhs): stream it out, then take a new row
             double* urow = U + (size_t)(6 * J + kp) * UW;
 #pragma unroll
-            for (int j = 0; j < T; j += 2) *reinterpret_cast<double2*>(urow + 6 + j) = make_double2(a[j], a[j + 1]);
-            *reinterpret_cast<double2*>(urow + W) = make_double2(b, myrinv);
+            for (int j = 0; j < T; j += 2) *reinterpret_cast<double2*>(urow + UOFF_PANEL + 6 + j) = make_double2(a[j], a[j + 1]);
+            *reinterpret_cast<double2*>(urow + UOFF_HEAD) = make_double2(b, myrinv);
             const int rank = __popc(rmask & ((1u << lane) - 1u));
             if (have_next) {
                 const double* sbuf = stage + (J % NS) * STG;
@@ -281,6 +290,121 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
     const long long tfac_end = clock64();
 #endif
 
+#if GXB_LU_AXPY
+    // ---- back substitution, column-oriented.  A row of block B needs the solutions of blocks B+1 .. B+NBLK (NBLK = KLB + KUB block
+    // super-diagonals of U), so NBLK + 1 blocks of rows are "pending" at any time: each pending row lives in ONE lane (slot) with
+    // its running sum.  Per block J, descending: gather the six finished sums of block J, solve the 6x6 triangle redundantly in
+    // every lane (no shuffle chain), then every pending row subtracts its six entries of column block J times x_J -- one 6-term
+    // axpy per lane, entries prefetched one step ahead straight from global memory into registers.  Only the 64-byte heads of the
+    // rows (rhs, 1/pivot, the triangle) go through shared memory.
+    {
+        constexpr int NBLK = KLB + KUB, M = NBLK + 1, R = 6 * M, PEND = (R + 31) / 32, HS = 4;
+        static_assert(HS * 48 <= S::SM_STAGE, "head ring must fit the staging area");
+#if !GXB_LU_TMA
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
+        __syncwarp();                                    // the U rows written by other lanes of this warp are visible from here on
+        double* hb = stage;                              // [HS][6][8] heads
+        auto prefetch_head = [&](int Jb) {
+            if (Jb >= 0 && lane < 24) cp_async16(hb + (Jb % HS) * 48 + (lane >> 2) * 8 + 2 * (lane & 3), U + (size_t)(6 * Jb + (lane >> 2)) * UW + 2 * (lane & 3));
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
+        double ps[PEND];                                 // running sums of the pending rows of this lane
+        int psb[PEND], pk[PEND];                         // slot block and row within the block
+        bool pv[PEND];
+        // the six entries (and, for a row that enters the pending set, its rhs) for the current step (A) and the next one (B):
+        // loaded two steps ahead so that the L2 latency is off the per-block dependency chain
+        constexpr int NSET = GXB_LU_NSET;                // prefetch distance in block steps
+        double2 f0_[NSET][PEND], f1_[NSET][PEND], f2_[NSET][PEND];
+        double rin_[NSET][PEND];
+#pragma unroll
+        for (int q = 0; q < PEND; q++) { const int pr = lane + 32 * q; pv[q] = pr < R; psb[q] = pr / 6; pk[q] = pr % 6; ps[q] = 0.0; }
+        auto load_step = [&](int Jt, int q, double2& f0, double2& f1, double2& f2, double& rin) {
+            f0 = f1 = f2 = make_double2(0.0, 0.0); rin = 0.0;
+            if (Jt < 0 || !pv[q]) return;
+            const int d = ((Jt - psb[q]) % M + M) % M;   // distance of the slot's row block from block Jt
+            const int B = Jt - d;
+            if (d < 1 || B < 0) return;
+            const double* rp = U + (size_t)(6 * B + pk[q]) * UW;
+            const double* ep = rp + 8 + 6 * (d - 1);
+            f0 = *reinterpret_cast<const double2*>(ep); f1 = *reinterpret_cast<const double2*>(ep + 2); f2 = *reinterpret_cast<const double2*>(ep + 4);
+            if (d == NBLK) rin = rp[0];
+        };
+#pragma unroll
+        for (int q = 0; q < PEND; q++) {
+            const int d = ((nb - 1 - psb[q]) % M + M) % M;
+            const int B = nb - 1 - d;
+            ps[q] = (pv[q] && B >= 0) ? U[(size_t)(6 * B + pk[q]) * UW] : 0.0;      // every row starts from its right-hand side
+#pragma unroll
+            for (int t = 0; t < NSET; t++) load_step(nb - 1 - t, q, f0_[t][q], f1_[t][q], f2_[t][q], rin_[t][q]);
+        }
+#pragma unroll
+        for (int q = 0; q < HS - 1; q++) prefetch_head(nb - 1 - q);
+        // The U rows of a Newton round do not fit the L2 (1.3 GB for C2): by the time the back substitution walks back to a row it
+        // has been evicted to HBM, and a DRAM round trip (~2 us under load) is longer than several block steps.  One TMA L2-prefetch
+        // per step (a block-row of U is contiguous) brings the rows back PD steps before the register prefetch touches them.
+        constexpr int PD = 10;
+        auto prefetch_l2 = [&](int Jb) {
+            if (Jb >= 0 && lane == 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(U + (size_t)(6 * Jb) * UW), "r"(6 * UW * 8) : "memory");
+        };
+        for (int q = 3; q < PD; q++) prefetch_l2(nb - 1 - q);
+        // one block step; (f0, f1, f2, rin) is the register set that was loaded for this step two steps ago and is reloaded for
+        // step J-NSET at the end.  The loop below cycles through the NSET sets (unrolled): rotating them with moves would
+        // make every iteration wait for the load issued by the previous one.
+        auto step = [&](int J, double2 (&f0)[PEND], double2 (&f1)[PEND], double2 (&f2)[PEND], double (&rin)[PEND]) {
+            prefetch_l2(J - PD);
+            prefetch_head(J - (HS - 1));
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(HS - 1) : "memory");
+            __syncwarp();
+            // the six finished sums of block J
+            const int base = 6 * (J % M);
+            double x[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const int idx = base + k;
+                double v = __shfl_sync(GXB_FULL, ps[0], idx & 31);
+                if (PEND > 1) { const double w2 = __shfl_sync(GXB_FULL, ps[PEND - 1], idx & 31); v = idx >= 32 ? w2 : v; }
+                x[k] = v;
+            }
+            // 6x6 upper triangle, the same arithmetic in every lane: x_k = (s_k - sum_{j>k} u_kj x_j) / u_kk
+            const double* h = hb + (J % HS) * 48;
+#pragma unroll
+            for (int k = 5; k >= 0; k--) {
+                x[k] *= h[8 * k + 1];
+#pragma unroll
+                for (int i = 0; i < k; i++) x[i] = fma(-h[8 * i + 2 + k], x[k], x[i]);
+            }
+            if (lane < 6) {
+                double xv = x[0];
+#pragma unroll
+                for (int k = 1; k < 6; k++) xv = lane == k ? x[k] : xv;
+                sol[6 * J + lane] = sign * xv;
+            }
+            // axpy into the pending rows (two interleaved 3-term chains), then reload this register set for step J-NSET
+#pragma unroll
+            for (int q = 0; q < PEND; q++) {
+                const int d = ((J - psb[q]) % M + M) % M;
+                if (pv[q] && d >= 1 && J - d >= 0) {
+                    double acc = (d == NBLK && J != nb - 1) ? rin[q] : ps[q];        // a row entering at this step starts from its rhs
+                    double acc2 = -f0[q].y * x[1];
+                    acc = fma(-f0[q].x, x[0], acc); acc2 = fma(-f1[q].y, x[3], acc2);
+                    acc = fma(-f1[q].x, x[2], acc); acc2 = fma(-f2[q].y, x[5], acc2);
+                    acc = fma(-f2[q].x, x[4], acc);
+                    ps[q] = acc + acc2;
+                }
+                load_step(J - NSET, q, f0[q], f1[q], f2[q], rin[q]);
+            }
+            __syncwarp();
+        };
+        for (int J = nb - 1; J >= 0; J -= NSET) {
+#pragma unroll
+            for (int t = 0; t < NSET; t++)
+                if (J - t >= 0) step(J - t, f0_[t], f1_[t], f2_[t], rin_[t]);
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+#else
     // ---- back substitution, block by block from the end; lane k < 6 owns row 6J+k ----
     // U rows of block J-1 are prefetched (cp.async, double buffered) while block J is being solved.
     constexpr int US = S::USTRIDE;
@@ -371,6 +495,7 @@ __device__ int warp_band_solve(const double* __restrict__ Jrow, const double* __
         }
         __syncwarp();
     }
+#endif
 #if GXB_LU_TMA
     // the shared memory is reused by the caller (persistent kernels run assembly tiles through it): retire the barrier objects
     __syncwarp();
