@@ -83,7 +83,7 @@ struct gxb_ctx {
     int* d_counter = nullptr; int* h_counter = nullptr;
     bool have_x0 = false;
     gxb_stats stats{};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr;   // evC: end of the last host->device copy
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -585,8 +585,12 @@ static int stage_upload(gxb_ctx* c, const void* host, size_t bytes) {
         c->stage_bytes = bytes;
     }
     CK(cudaMemcpyAsync(c->d_stage, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->evC, c->stream));      // the caller's buffer is free once this event has fired
     return GXB_OK;
 }
+// The set_* calls return as soon as the caller's host buffer has been read: the packing kernel that follows is stream-ordered before
+// everything that uses its output, so nobody has to wait for it on the host (this keeps a pipelined caller's upload slot short).
+static int wait_copy(gxb_ctx* c) { CK(cudaEventSynchronize(c->evC)); return GXB_OK; }
 
 template <class T> static int dalloc(T** p, size_t count) { CK(cudaMalloc((void**)p, count * sizeof(T))); return GXB_OK; }
 
@@ -616,7 +620,7 @@ int gxb_create(gxb_ctx** out, int device) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->d_counter, sizeof(int)));
     CK(cudaMallocHost(&c->h_counter, sizeof(int)));
-    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); CK(cudaEventCreate(&c->evA)); CK(cudaEventCreate(&c->evB));
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); CK(cudaEventCreate(&c->evA)); CK(cudaEventCreate(&c->evB)); CK(cudaEventCreateWithFlags(&c->evC, cudaEventDisableTiming));
     *out = c;
     return GXB_OK;
 }
@@ -627,7 +631,7 @@ void gxb_destroy(gxb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     free_batch(c);
     cudaFree(c->d_flags); cudaFree(c->d_brow); cudaFree(c->d_bcol); cudaFree(c->d_counter); cudaFreeHost(c->h_counter);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evA); cudaEventDestroy(c->evB);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaEventDestroy(c->evC);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -808,8 +812,7 @@ int gxb_set_elements(gxb_ctx* c, const double* elems) {
     int rc = stage_upload(c, elems, (size_t)c->nbatch * c->ne * GXB_ELEM_STRIDE * 8); if (rc) return rc;
     k_pack_elements<<<grid1(c->nbatch * c->ne, 128), 128, 0, c->stream>>>(c->d_stage, c->d_elemS, c->d_exS, (int)c->ne, c->nbatch);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));   // the caller may reuse its buffer
-    return GXB_OK;
+    return wait_copy(c);                     // the caller may reuse its buffer
 }
 int gxb_set_points(gxb_ctx* c, const double* xyz) {
     NEED_BATCH("gxb_set_points");
@@ -828,8 +831,7 @@ int gxb_set_bc(gxb_ctx* c, const double* bc) {
     int rc = stage_upload(c, bc, (size_t)c->nbatch * c->np * 18 * 8); if (rc) return rc;
     k_pack_transpose<<<grid1(c->nbatch * c->np * 18, 256), 256, 0, c->stream>>>(c->d_stage, c->d_bcS, (int)c->np, 18, c->nbatch);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));
-    return GXB_OK;
+    return wait_copy(c);
 }
 int gxb_set_dloads(gxb_ctx* c, const double* dl) {
     NEED_BATCH("gxb_set_dloads");
@@ -870,8 +872,8 @@ int gxb_set_body(gxb_ctx* c, const double* gravity, const double* force_scaling)
         for (int64_t i = 0; i < c->nbatch; i++) if (!(force_scaling[i] > 0.0)) return fail(GXB_ERR_INVALID, "gxb_set_body: force_scaling must be positive");
         CK(cudaMemcpyAsync(c->d_fs, force_scaling, (size_t)c->nbatch * 8, cudaMemcpyHostToDevice, c->stream));
     }
-    CK(cudaStreamSynchronize(c->stream));
-    return GXB_OK;
+    CK(cudaEventRecord(c->evC, c->stream));
+    return wait_copy(c);
 }
 
 int gxb_upload_x0(gxb_ctx* c, const double* x0) {
