@@ -32,7 +32,7 @@ class GXBError(RuntimeError):
 class Opts(C.Structure):
     _fields_ = [("linear", C.c_int32), ("two_dimensional", C.c_int32), ("ftol", C.c_double), ("iterations", C.c_int64),
                 ("maxstep", C.c_double), ("c1", C.c_double), ("rho_hi", C.c_double), ("rho_lo", C.c_double),
-                ("profile", C.c_int32), ("structural_damping", C.c_int32), ("persistent", C.c_int32), ("reserved", C.c_int32)]
+                ("profile", C.c_int32), ("structural_damping", C.c_int32), ("persistent", C.c_int32), ("update_linearization", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -78,10 +78,10 @@ def _f64(a):
 
 
 def make_opts(linear=False, two_dimensional=False, ftol=1e-9, iterations=1000, maxstep=1e6, c1=1e-4, rho_hi=0.5, rho_lo=0.1,
-              profile=False, structural_damping=False, persistent=0):
+              profile=False, structural_damping=False, persistent=0, update_linearization=False):
     """persistent: 0 auto, 1 force, 2 forbid the persistent per-instance kernel (kind=1 contexts)."""
     return Opts(int(linear), int(two_dimensional), ftol, iterations, maxstep, c1, rho_hi, rho_lo, int(profile), int(structural_damping),
-                int(persistent), 0)
+                int(persistent), int(update_linearization))
 
 
 class Context:

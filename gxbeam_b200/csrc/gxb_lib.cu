@@ -1330,7 +1330,8 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     if (!x0 && !c->have_initial) return fail(GXB_ERR_INVALID, "gxb_newmark_run: no initial state (pass x0 and rates0, or call gxb_initial_condition first)");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     c->damping = o.structural_damping ? 1 : 0;
-    if (o.linear) return fail(GXB_ERR_UNSUPPORTED, "gxb_newmark_run: linear=true is not implemented on the device");
+    // linear=true: one lsolve! per step, about the current state (update_linearization) or about the initial state (analyses.jl:2741-2755)
+    double* d_xlin = nullptr;
     if (c->ser_K && c->ser_nt < nt) return fail(GXB_ERR_INVALID, "gxb_newmark_run: the bc series has fewer time levels than tvec");
     if (save_every < 1) save_every = 1;
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n, P = (size_t)c->np;
@@ -1350,6 +1351,10 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
         CK(cudaMemcpyAsync(c->d_rates0, rates0, nb * P * 12 * 8, cudaMemcpyHostToDevice, c->stream));
     }
     c->have_initial = false;
+    if (o.linear && !o.update_linearization) {
+        CK(cudaMalloc(&d_xlin, nb * n * 8));
+        CK(cudaMemcpyAsync(d_xlin, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
     CK(cudaMemsetAsync(c->d_paug, 0, nb * 12 * P * 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     if (d_hist) k_save_state<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_x, d_hist, (int)n, nsave, 0, c->nbatch);
@@ -1371,7 +1376,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
         k_step_prepare<<<(unsigned)nb, 32, 0, c->stream>>>(c->d_bcS, c->d_series, c->d_ser_point, c->d_ser_field, c->ser_K, c->ser_nt, it, c->d_x,
                                                            c->d_flags, c->d_paug, c->d_rates0, (int)P, (int)n, it == 1, c_prev, c->c2dt,
                                                            c->ns.status, c->ns.iters, c->ns.fcalls, d_alive);
-        CK(cudaMemcpyAsync(c->d_xt, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));   // initial guess = previous state (analyses.jl:3592)
+        CK(cudaMemcpyAsync(c->d_xt, d_xlin ? d_xlin : c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));   // initial guess = previous state (analyses.jl:3592)
         c->stats.launches += 1;
         if ((rc = newton_rounds(c, o, prof, 2))) { c->mode = 0; return rc; }
         k_step_end<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, c->ns.iters, d_alive, d_steps, d_itot, c->nbatch);
@@ -1390,7 +1395,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     if (iters_total) memcpy(iters_total, itot.data(), nb * 4);
     if (steps_done) CK(cudaMemcpy(steps_done, d_steps, nb * 4, cudaMemcpyDeviceToHost));
     if (x_hist) CK(cudaMemcpy(x_hist, d_hist, nb * nsave * n * 8, cudaMemcpyDeviceToHost));
-    cudaFree(d_alive); cudaFree(d_steps); cudaFree(d_itot); cudaFree(d_hist); cudaFree(d_tvec);
+    cudaFree(d_alive); cudaFree(d_steps); cudaFree(d_itot); cudaFree(d_hist); cudaFree(d_tvec); cudaFree(d_xlin);
     CK(cudaGetLastError());
     return GXB_OK;
 }

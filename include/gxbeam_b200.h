@@ -46,7 +46,8 @@ typedef struct gxb_opts {
     int32_t persistent;      /* kind=1 only: 0 auto, 1 force, 2 forbid the persistent per-instance kernel (one CTA runs an instance's
                                 whole Newton loop / time loop; chosen automatically for small batches).  No effect on results beyond
                                 round-off in the line search's sums. */
-    int32_t reserved;
+    int32_t update_linearization; /* gxb_newmark_run with linear != 0: 0 = linearise every step about the initial state (the reference's
+                                default, analyses.jl:2536), 1 = about the current state */
 } gxb_opts;
 
 /* Filled by gxb_get_stats after a solve. */

@@ -25,7 +25,7 @@ struct Opts            # mirrors gxb_opts
     profile::Int32
     structural_damping::Int32
     persistent::Int32
-    reserved::Int32
+    update_linearization::Int32
 end
 
 check(rc) = rc == 0 || error("gxbeam_b200: " * unsafe_string(ccall((:gxb_last_error, LIB), Cstring, ())))

@@ -376,8 +376,15 @@ int gxo_newmark_jacobian(const gxo_problem* q, const gxo_dyn* d, const double* i
 //   tvec: nt times.  bc_t: nt x np x 18 prescribed values per time (NULL: constant = q->bc).  x0: nstates.  rates0: np x 12
 //   (udot, θdot, Vdot, Ωdot of the initial state).  x_hist: nt x nstates (row 0 = x0).  iters: nt (iters[0] = 0).
 //   Returns the number of time levels completed (stops early when a step does not converge).
+int64_t gxo_newmark_run2(const gxo_problem* q, const gxo_dyn* d, const gxo_opts* opts, int64_t nt, const double* tvec, const double* bc_t,
+                         const double* x0, const double* rates0, double* x_hist, int32_t* iters, int32_t* converged, int update_linearization);
 int64_t gxo_newmark_run(const gxo_problem* q, const gxo_dyn* d, const gxo_opts* opts, int64_t nt, const double* tvec, const double* bc_t,
                         const double* x0, const double* rates0, double* x_hist, int32_t* iters, int32_t* converged) {
+    return gxo_newmark_run2(q, d, opts, nt, tvec, bc_t, x0, rates0, x_hist, iters, converged, 1);
+}
+// update_linearization only matters with opts->linear: false = every step is linearised about the INITIAL state x0 (analyses.jl:2741-2755)
+int64_t gxo_newmark_run2(const gxo_problem* q, const gxo_dyn* d, const gxo_opts* opts, int64_t nt, const double* tvec, const double* bc_t,
+                         const double* x0, const double* rates0, double* x_hist, int32_t* iters, int32_t* converged, int update_linearization) {
     Problem P = to_problem(q); DynParams D = to_dyn(d);
     Indices idx = system_indices(P.ne, P.start, P.stop, false);
     int64_t kl, ku; dynamic_bandwidth(P, idx, kl, ku);
@@ -410,6 +417,7 @@ int64_t gxo_newmark_run(const gxo_problem* q, const gxo_dyn* d, const gxo_opts* 
         NewmarkParams N; N.init = paug.data(); N.dt = dt;
         auto rf = [&](const double* xx, double* FF) { newmark_system_residual<double>(P, idx, D, N, xx, FF); };
         auto jf = [&](const double* xx, BandMat& JJ) { newmark_system_jacobian<double>(P, idx, D, N, xx, JJ); };
+        if (o.linear && !update_linearization) std::copy(x0, x0 + n, x.begin());     // x = newmark_lsolve!(x0, paug, constants)
         NewtonResult res = newton_solve(n, x.data(), F.data(), J, rf, jf, o);
         std::copy(x.begin(), x.end(), x_hist + it * n);
         iters[it] = (int32_t)res.iters;

@@ -242,7 +242,7 @@ def newmark_jacobian(pk: Packed, dyn: Dyn, init, dt, x, complex_step=False):
     return J
 
 
-def newmark_run(pk: Packed, dyn: Dyn, tvec, x0, rates0, bc_t=None, **kw):
+def newmark_run(pk: Packed, dyn: Dyn, tvec, x0, rates0, bc_t=None, update_linearization=True, **kw):
     """time_domain_analysis! from a given initial state.  rates0: [np,12] = udot, θdot, Vdot, Ωdot at t0.  bc_t: [nt,np,18] or None."""
     tvec = np.ascontiguousarray(tvec, float)
     nt = len(tvec)
@@ -252,9 +252,9 @@ def newmark_run(pk: Packed, dyn: Dyn, tvec, x0, rates0, bc_t=None, **kw):
     conv = C.c_int32(0)
     o = make_opts(**kw)
     bct = None if bc_t is None else np.ascontiguousarray(bc_t, float)
-    lib().gxo_newmark_run.restype = C.c_int64
-    done = lib().gxo_newmark_run(C.byref(pk.c), C.byref(dyn), C.byref(o), C.c_int64(nt), _p(tvec), _p(bct), _p(np.ascontiguousarray(x0, float)),
-                                 _p(np.ascontiguousarray(rates0, float)), _p(xh), _p(its), C.byref(conv))
+    lib().gxo_newmark_run2.restype = C.c_int64
+    done = lib().gxo_newmark_run2(C.byref(pk.c), C.byref(dyn), C.byref(o), C.c_int64(nt), _p(tvec), _p(bct), _p(np.ascontiguousarray(x0, float)),
+                                  _p(np.ascontiguousarray(rates0, float)), _p(xh), _p(its), C.byref(conv), int(update_linearization))
     return dict(x=xh, iters=its, converged=bool(conv.value), steps_done=int(done))
 
 

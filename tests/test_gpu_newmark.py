@@ -120,3 +120,27 @@ def test_time_marching_from_steady_state_is_a_fixed_point():
     ctx.close()
     assert res["converged"].all() and res["x"].shape == (nb, 3, 444)
     assert np.abs(res["x"] - st["x"][:, None, :]).max() <= 1e-8 * np.abs(st["x"]).max()
+
+
+@pytest.mark.parametrize("update_linearization", [False, True])
+def test_linear_time_marching_parity(update_linearization):
+    """time_domain_analysis(...; linear = true): one lsolve! per step (analyses.jl:2741-2755), linearised about the initial state
+    (update_linearization = false, the reference's default) or about the current state."""
+    O = _oracle()
+    nb, nt = 4, 31
+    w, tvec, series = _gust(nb, nt, 0.0075)
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    st = ctx.steady_solve()
+    ctx.set_bc_series([21], [7], series)
+    rates0 = np.zeros((nb, 25, 12))
+    res = ctx.newmark_run(tvec, st["x"], rates0, api.make_opts(structural_damping=True, linear=True, update_linearization=update_linearization))
+    ctx.close()
+    assert res["converged"].all() and (res["steps_done"] == nt).all() and (res["iters_total"] == nt - 1).all()
+    for b in range(nb):
+        pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
+        dyn = O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6], structural_damping=True)
+        bct = np.tile(w["bc"][b][None], (nt, 1, 1)); bct[:, 20, 7] = series[b, :, 0]
+        ref = O.newmark_run(pk, dyn, tvec, st["x"][b], rates0[b], bct, update_linearization=update_linearization, linear=True)
+        for name, ids in _groups(O, w).items():
+            err = np.abs(res["x"][b][:, ids] - ref["x"][:, ids]).max()
+            assert err <= 1e-9 * np.abs(ref["x"][:, ids]).max(), (name, err)
