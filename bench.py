@@ -258,6 +258,15 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         B_it, F_it = algorithmic_bytes_per_iter(NELEM), algorithmic_flops_per_iter(NELEM)
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this command (first Newton round: one
+        # launch over all 4096 instances): dram__bytes_read.sum + dram__bytes_write.sum
+        traffic = None
+        try:
+            import csv
+            vals = {r[0]: float(r[2]) for r in csv.reader(open(os.path.join(ROOT, "profiles", "r1_v5_prof_factor_raw.csv"))) if r and r[0].startswith("dram__bytes")}
+            traffic = (vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]) * 1e9
+        except Exception:
+            pass
         fac_s = prof["ms_factor"] * 1e-3
         achieved = B_it * prof["newton_iters"] / fac_s / 1e9 if fac_s > 0 else None
         line = {
@@ -274,7 +283,10 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_factor_solve<2,2>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
+                         "traffic_note": "bytes per full-batch launch (4096 instances) from profiles/r1_v5_prof_factor_raw.csv: the row-block Jacobian "
+                                         "(incl. structural zeros) is read once, the U rows are written and read back once -- 0.94 MB per instance and "
+                                         "iteration, SURVEY 8d's figure for a Jacobian materialised in HBM; `achieved` uses the on-chip ideal of 109 KB",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_newton_iter": B_it, "launches": prof["n_factor"],
                          "avg_launch_ms": prof["ms_factor"] / max(prof["n_factor"], 1),
