@@ -49,7 +49,7 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_set_motion", "gxb_static_solve", "gxb_steady_solve", "gxb_steady_solve_resident", "gxb_upload_x0",
            "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction",
            "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi",
-           "gxb_initial_condition", "gxb_initial_residual_jacobian"]
+           "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns"]
 
 _lib = None
 
@@ -279,6 +279,13 @@ class Context:
         rv2 = None if rate_vars2 is None else np.ascontiguousarray(rate_vars2, np.uint8)
         self._ck(self.lib.gxb_initial_residual_jacobian(self.h, C.byref(o), _ptr(icv), _ptr(rv1), _ptr(rv2), _ptr(x), _ptr(r), _ptr(J)))
         return r, J
+
+    def body_columns(self, want_columns=True):
+        """icol_body (1-based, 0 = none) and the dense Jacobian columns [6, nb, n] of the body-acceleration states."""
+        icb = np.zeros(6, np.int64)
+        D = np.zeros((6, self.nbatch, self.n)) if want_columns else None
+        self._ck(self.lib.gxb_body_columns(self.h, _ptr(icb), _ptr(D)))
+        return icb, D
 
     # --- eigenvalue analysis ---
     def mass_matrix(self, x, opts=None):

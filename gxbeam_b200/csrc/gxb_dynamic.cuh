@@ -12,7 +12,8 @@
 // Structural damping (element.jl:165-217, 713-820; docs/src/theory.md): γ -= μ11 γdot, κ -= μ22 κdot, with the strain rates built
 // from the *velocity states* of the two end points; evaluated by damping_terms() below.
 // Point masses (point.jl:630-672, 964-1023, 1134-1200) reuse the element's inertia routines with the frame A = C(θ_p)'.
-// Not implemented on the device yet (the host refuses it): body-frame accelerations as state variables (a DOF with pd & pl).
+// Body-frame accelerations as state variables (a DOF with pd & pl): the residual reads them from x (body_accelerations); their dense
+// Jacobian columns are assembled by k_body_columns and handled by a Woodbury correction around the band solve (gxb_lib.cu).
 #pragma once
 #include "gxb_static.cuh"
 
@@ -31,7 +32,15 @@ struct DynArgs {
     const double* init;       // [b][12][N+1] udot_init, θdot_init, Vdot_init, Ωdot_init
     double c2dt;              // 2/dt
     int damping;              // structural_damping (elemS fields 82..87 hold Element.mu)
+    // body-frame accelerations that are state variables (a DOF with displacement AND load prescribed, system.jl:138-150, 167-182):
+    // ibody[i] = 0-based column of x holding linear (i < 3) / angular (i >= 3) acceleration component i, or -1
+    int ibody[6];
 };
+// body_accelerations (system.jl:167-182)
+GXD void body_accelerations(const DynArgs& A, const double* x, const double* mo, v3& ab, v3& alb) {
+    ab = mk(A.ibody[0] >= 0 ? x[A.ibody[0]] : mo[6], A.ibody[1] >= 0 ? x[A.ibody[1]] : mo[7], A.ibody[2] >= 0 ? x[A.ibody[2]] : mo[8]);
+    alb = mk(A.ibody[3] >= 0 ? x[A.ibody[3]] : mo[9], A.ibody[4] >= 0 ? x[A.ibody[4]] : mo[10], A.ibody[5] >= 0 ? x[A.ibody[5]] : mo[11]);
+}
 
 GXD void dblk(double* t, int s, const m3& B) {
 #pragma unroll
@@ -212,7 +221,8 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
     if (S.has_grav && S.grav) g = mk(S.grav[3 * b], S.grav[3 * b + 1], S.grav[3 * b + 2]);
     const double* mo = A.motion + 12 * (size_t)b;
     const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]);
-    const v3 ab = MODE == 0 ? mk(mo[6], mo[7], mo[8]) : mk(0, 0, 0), alb = MODE == 0 ? mk(mo[9], mo[10], mo[11]) : mk(0, 0, 0);
+    v3 ab = mk(0, 0, 0), alb = ab;
+    if (MODE == 0) body_accelerations(A, x, mo, ab, alb);
     const m3 wbt = tilde(wb);
     const double c2 = MODE == 1 ? A.c2dt : 0.0;
     const double* ini = (MODE == 1) ? A.init + ((size_t)b * 12) * NP : nullptr;   // field f of point p at ini[f*NP + p]

@@ -120,7 +120,9 @@ __device__ void initial_station(const InitArgs& IA, int b, int i, double* smem) 
     v3 g = mk(0, 0, 0);
     if (S.has_grav && S.grav) g = mk(S.grav[3 * b], S.grav[3 * b + 1], S.grav[3 * b + 2]);
     const double* mo = A.motion + 12 * (size_t)b;
-    const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]), ab = mk(mo[6], mo[7], mo[8]), alb = mk(mo[9], mo[10], mo[11]);
+    const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]);
+    v3 ab, alb;
+    body_accelerations(A, x, mo, ab, alb);
     const m3 wbt = tilde(wb);
 
     // ---- point i ----

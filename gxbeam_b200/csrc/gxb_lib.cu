@@ -73,7 +73,10 @@ struct gxb_ctx {
     int damping = 0;         // structural_damping of the current solve
     int mode = 0;            // 0: steady residual, 1: Newmark residual (set by the time-marching driver), 2: initial-condition residual
     double c2dt = 0.0;
-    bool body_state = false;                          // some DOF has pd & pl (body-frame acceleration would be a state)
+    bool body_state = false;                          // some DOF has pd & pl (body-frame acceleration is a state, system.jl:138-150)
+    int ibody[6] = {-1, -1, -1, -1, -1, -1};          // 0-based column of acceleration component i, or -1 (update_body_acceleration_indices!)
+    int nbody = 0;
+    double *d_D = nullptr, *d_Z = nullptr;            // [b][6][n] dense Jacobian columns of the body accelerations and B^-1 D (kind = 1)
     int W = 30, UW = 32, KLB = 2, rows_per_station = 12;
     int has_grav = 0;
     double* d_stage = nullptr; size_t stage_bytes = 0;
@@ -147,6 +150,77 @@ template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble_initial
     initial_station<WANT_J>(A, b, threadIdx.x, asm_smem);
 }
 
+// Dense Jacobian columns of the body-frame accelerations that are state variables (insert_steady_point_jacobians! point.jl:1829-1841,
+// insert_steady_element_jacobians! element.jl:2567-2583; the same terms for the initial-condition analysis, point.jl:1879-1895).
+// Column i (acceleration component i, stored at column c_i = ibody[i]) has entries in the force/moment rows of EVERY point:
+//   + (tf_x, tm_x)[:, i] / fs of the point's own mass and + 1/2 of each adjacent element's, with
+//   tf_ab = A m11 A', tf_alb = -A m11 A' tilde(dx + u) + A m12 A', tm likewise with m21, m22   (Vdot_ab = I, Vdot_alb = -tilde(dx + u), Ωdot_alb = I)
+// which does not fit the band.  The band matrix B keeps a unit entry at (c_i, c_i) instead (the force-free, displacement-free DOF
+// owns that row), and Dn[b][i][:] = column_i - e_{c_i}, so that J = B + sum_i Dn_i e_{c_i}' exactly; the solve undoes the split
+// with a Woodbury correction (k_woodbury).  One thread per station, both adjacent elements evaluated by the thread itself.
+struct BodyArgs { DynArgs d; const double* icS; const unsigned* rvm; int mode; double* Dn; };   // Dn: [6][nbatch][n]
+__global__ void __launch_bounds__(256) k_body_columns(BodyArgs B) {
+    const DynArgs& A = B.d; const StaticArgs& S = A.s;
+    const int b = blockIdx.x, p = threadIdx.x, N = S.N, NP = N + 1;
+    if (S.status && S.status[b] != S.want_status) return;
+    if (p > N) return;
+    const double rfs = 1.0 / S.fs[b];
+    const double* x = S.x + (size_t)b * S.n;
+    auto disp = [&](int q, v3& u, v3& th) {
+        const unsigned fl = S.flags[q];
+        const double* bc = S.bcS + ((size_t)b * 18) * NP + q;
+        const double* xp = x + 18 * q;
+        double t[6];
+        for (int k = 0; k < 6; k++) {
+            const bool pd = (fl >> k) & 1u;
+            if (B.mode == 2) {
+                const bool r = (B.rvm[(size_t)b * NP + q] >> k) & 1u;
+                t[k] = pd ? bc[(size_t)k * NP] : (r ? B.icS[((size_t)b * 18 + k) * NP + q] : xp[k]);
+            } else t[k] = pd ? bc[(size_t)k * NP] : xp[k];
+        }
+        u = mk(t[0], t[1], t[2]); th = mk(t[3], t[4], t[5]);
+    };
+    double G[6][6];                      // rows: F(3), M(3) of this point; columns: ab(3), alb(3)
+    for (int r = 0; r < 6; r++) for (int cc = 0; cc < 6; cc++) G[r][cc] = 0.0;
+    auto add = [&](const m3& Am, const m3& m11, const m3& m12, const m3& m21, const m3& m22, v3 rr, double w) {
+        const m3 At = transpose(Am), rt = tilde(rr);
+        const m3 A11 = (Am * m11) * At, A12 = (Am * m12) * At, A21 = (Am * m21) * At, A22 = (Am * m22) * At;
+        const m3 Fal = A12 - A11 * rt, Mal = A22 - A21 * rt;
+        for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) {
+            G[r][cc] += w * A11.a[3 * r + cc]; G[r][3 + cc] += w * Fal.a[3 * r + cc];
+            G[3 + r][cc] += w * A21.a[3 * r + cc]; G[3 + r][3 + cc] += w * Mal.a[3 * r + cc];
+        }
+    };
+    v3 up, thp; disp(p, up, thp);
+    if (S.pmS) {
+        const double* pm = S.pmS + ((size_t)b * 36) * NP + p;
+        const v3 dxp = ldv(A.pxS + ((size_t)b * 3) * NP + p, NP);
+        add(transpose(rot_C(thp)), ldm(pm, NP), ldm(pm + 9 * NP, NP), ldm(pm + 18 * NP, NP), ldm(pm + 27 * NP, NP), dxp + up, rfs);
+    }
+    for (int side = 0; side < 2; side++) {
+        const int e = p - 1 + side;
+        if (e < 0 || e >= N) continue;
+        v3 u1, t1, u2, t2; disp(e, u1, t1); disp(e + 1, u2, t2);
+        const double* es = S.elemS + ((size_t)b * S.elem_nf) * N + e;
+        const m3 Am = tmul(rot_C(0.5 * (t1 + t2)), ldm(es + N, N));
+        const v3 dxe = ldv(A.exS + ((size_t)b * 3) * N + e, N);
+        add(Am, ldm(es + 46 * N, N), ldm(es + 55 * N, N), ldm(es + 64 * N, N), ldm(es + 73 * N, N), dxe + 0.5 * (u1 + u2), 0.5 * rfs);
+    }
+    for (int i = 0; i < 6; i++) {
+        const int c = A.ibody[i];
+        if (c < 0) continue;
+        double* Di = B.Dn + ((size_t)i * gridDim.x + b) * S.n + 18 * p;
+        for (int k = 0; k < 6; k++) {
+            double v = G[k][i];
+            if (B.mode == 2 && ((B.rvm[(size_t)b * NP + p] >> (8 + k)) & 1u)) v = 0.0;    // equilibrium row replaced by Vdot_k = Vdot0_k (system.jl:756-813)
+            if (S.two_d && k >= 2 && k <= 4) v = 0.0;                                      // planar constraint rows (system.jl:1090-1100)
+            if (18 * p + k == c) v -= 1.0;
+            Di[k] = v;
+        }
+        if (c / 18 == p && S.Jrow) S.Jrow[((size_t)b * S.n + c) * GXB_DROWW + 18 + (c % 18)] = 1.0;    // the unit entry B keeps at (c_i, c_i)
+    }
+}
+
 // rate_vars of the initial-condition analysis (src/analyses.jl:1835-1873): column sums of the mass matrix at x = 0 over the V/Ω
 // columns of each point (rate_vars1), and the same with the element mass blocks replaced by the compliance blocks and the point
 // masses ignored (rate_vars2).  One thread per (instance, point).  rvm bit k: rate_vars2, bit 8+k: equilibrium row replaced
@@ -202,7 +276,7 @@ __global__ void k_initial_rate_vars(const double* __restrict__ elemS, int elem_n
 // rates udot, θdot, Vdot, Ωdot ([b][NP][12]) that seed the Newmark march.  One thread per (instance, point).
 __global__ void k_initial_output(double* __restrict__ x, const double* __restrict__ bcS, const double* __restrict__ icS, const unsigned* __restrict__ rvm,
                                  const unsigned short* __restrict__ flags, const double* __restrict__ pxS, const double* __restrict__ motion,
-                                 double* __restrict__ rates, int NP, int n, int64_t nbatch) {
+                                 double* __restrict__ rates, int NP, int n, int64_t nbatch, DynArgs body) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= nbatch * NP) return;
     const int64_t b = t / NP; const int p = (int)(t % NP);
@@ -211,7 +285,9 @@ __global__ void k_initial_output(double* __restrict__ x, const double* __restric
     const double* ic = icS + ((size_t)b * 18) * NP + p;
     double* xp = x + b * n + 18 * p;
     const double* mo = motion + 12 * b;
-    const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]), ab = mk(mo[6], mo[7], mo[8]), alb = mk(mo[9], mo[10], mo[11]);
+    const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]);
+    v3 ab, alb;
+    body_accelerations(body, x + b * n, mo, ab, alb);          // system.jl:167-182 (analyses.jl:2348)
     double ut[6], rt[6];
     for (int k = 0; k < 6; k++) {
         const bool pd = (fl >> k) & 1u, r = (rv >> k) & 1u;
@@ -274,7 +350,11 @@ struct SolveArgs {
     double maxstep; int linear;
     int direction_only;   // parity entry point: just p, no state change
     double sign;          // sol = sign * (J \ F): -1 for the Newton direction, +1 for the eigen operator
+    // Woodbury-corrected steps (body-acceleration states): F / p above are the right-hand side / solution of ONE band solve,
+    // these are the Newton residual and direction the line search works with
+    const double* Fnewton; double* pnewton;
 };
+__device__ void linesearch_start(const SolveArgs& A, int64_t b);
 
 // one warp: factorise + solve instance b, then start the line search (|p|_inf, φ0, dφ0, first trial point)
 template <int KLB, int KUB> __device__ void factor_instance(const SolveArgs& A, int64_t b, double* sm) {
@@ -285,9 +365,18 @@ template <int KLB, int KUB> __device__ void factor_instance(const SolveArgs& A, 
     double* p = A.p + b * n;
     int bad = warp_band_solve<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * n * S::UW, p, A.nb, A.sign, sm);
     __syncwarp();
-    if (A.direction_only) return;
+    if (A.direction_only == 1) return;
     if (bad) { if (lane == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
-    // |p|_inf, φ0 = ½ F'F, dφ0 = g'p with g = J'F and J p = -F  =>  dφ0 = -F'F
+    if (A.direction_only) return;        // 2: one of several solves of a Woodbury-corrected step (k_woodbury finishes it)
+    linesearch_start(A, b);
+}
+// |p|_inf, φ0 = ½ F'F, dφ0 = g'p with g = J'F and J p = -F  =>  dφ0 = -F'F; first trial point.  One warp; p is complete.
+__device__ void linesearch_start(const SolveArgs& A, int64_t b) {
+    const int lane = threadIdx.x & 31;
+    const size_t n = A.n;
+    const double* F = A.Fnewton ? A.Fnewton + b * n : A.F + b * n;
+    double* p = A.pnewton ? A.pnewton + b * n : A.p + b * n;
+    {
     double pm = 0.0, ff = 0.0;
     for (int c = lane; c < (int)n; c += 32) { pm = fmax(pm, fabs(p[c])); double f = F[c]; ff = fma(f, f, ff); }
     for (int o = 16; o; o >>= 1) { pm = fmax(pm, __shfl_xor_sync(GXB_FULL, pm, o)); ff += __shfl_xor_sync(GXB_FULL, ff, o); }
@@ -298,6 +387,7 @@ template <int KLB, int KUB> __device__ void factor_instance(const SolveArgs& A, 
         A.ns.a1[b] = a0; A.ns.a2[b] = a0; A.ns.phi0[b] = 0.5 * ff; A.ns.dphi0[b] = -ff; A.ns.phx0[b] = 0.5 * ff;
         A.ns.ls_k[b] = 0; A.ns.ls_finite[b] = 0; A.ns.status[b] = ST_TRIAL;
     }
+    }
 }
 template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? GXB_LU_MINBLOCKS : 2)) k_factor_solve(SolveArgs A) {
     using S = LuShape<KLB, KUB>;
@@ -305,8 +395,52 @@ template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? G
     const int warp = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= A.nbatch) return;
-    if (!A.direction_only && A.ns.status[b] != ST_SOLVE) return;
+    if (A.direction_only != 1 && A.ns.status[b] != ST_SOLVE) return;
     factor_instance<KLB, KUB>(A, b, smem + (size_t)warp * S::SM_DOUBLES);
+}
+
+// Woodbury correction of a Newton step whose Jacobian is J = B + sum_i D_i e_{c_i}' (body-acceleration columns, see k_body_columns):
+// with y = B^-1 F (in p) and z_i = B^-1 D_i,   J^-1 F = y - Z (I + E'Z)^-1 E'y.   One warp per instance; the k x k system (k <= 6) is
+// solved by lane 0 with partial pivoting.  Then the line search starts exactly as after an ordinary factorisation.
+struct WoodArgs { SolveArgs S; const double* Z; int ibody[6]; };
+__global__ void __launch_bounds__(128) k_woodbury(WoodArgs W) {
+    const SolveArgs& A = W.S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= A.nbatch) return;
+    if (A.ns.status[b] != ST_SOLVE) return;
+    const size_t n = A.n;
+    double* p = A.p + b * n;
+    int idx[6], k = 0;
+    for (int i = 0; i < 6; i++) if (W.ibody[i] >= 0) idx[k++] = i;
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    int bad = 0;
+    if (lane == 0) {
+        double M[6][7];
+        for (int j = 0; j < k; j++) {
+            const int cj = W.ibody[idx[j]];
+            for (int i = 0; i < k; i++) M[j][i] = (i == j ? 1.0 : 0.0) + W.Z[((size_t)idx[i] * A.nbatch + b) * n + cj];
+            M[j][k] = p[cj];
+        }
+        for (int col = 0; col < k && !bad; col++) {
+            int piv = col; double best = fabs(M[col][col]);
+            for (int r = col + 1; r < k; r++) if (fabs(M[r][col]) > best) { best = fabs(M[r][col]); piv = r; }
+            if (!(best > 0.0) || !isfinite(best)) { bad = 1; break; }
+            if (piv != col) for (int q = col; q <= k; q++) { double t = M[col][q]; M[col][q] = M[piv][q]; M[piv][q] = t; }
+            for (int r = col + 1; r < k; r++) { const double f = M[r][col] / M[col][col]; for (int q = col; q <= k; q++) M[r][q] -= f * M[col][q]; }
+        }
+        if (!bad) for (int r = k - 1; r >= 0; r--) { double v = M[r][k]; for (int q = r + 1; q < k; q++) v -= M[r][q] * a[q]; a[r] = v / M[r][r]; }
+    }
+    bad = __shfl_sync(GXB_FULL, bad, 0);
+    if (bad) { if (lane == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
+    for (int j = 0; j < 6; j++) a[j] = __shfl_sync(GXB_FULL, a[j], 0);
+    for (int c = lane; c < (int)n; c += 32) {
+        double v = p[c];
+        for (int j = 0; j < k; j++) v = fma(-W.Z[((size_t)idx[j] * A.nbatch + b) * n + c], a[j], v);
+        p[c] = -v;                       // Newton direction p = -J^-1 F
+    }
+    __syncwarp();
+    linesearch_start(A, b);
 }
 
 struct UpdateArgs {
@@ -564,6 +698,7 @@ __global__ void __launch_bounds__(256) k_arnoldi_orth(double* __restrict__ Vk, d
 static void free_batch(gxb_ctx* c) {
     cudaFree(c->d_exS); cudaFree(c->d_motion); c->d_exS = c->d_motion = nullptr;
     cudaFree(c->d_M); c->d_M = nullptr;
+    cudaFree(c->d_D); cudaFree(c->d_Z); c->d_D = c->d_Z = nullptr;
     cudaFree(c->d_icS); cudaFree(c->d_rvm); c->d_icS = nullptr; c->d_rvm = nullptr; c->have_initial = false;
     cudaFree(c->d_paug); cudaFree(c->d_rates0); cudaFree(c->d_series); cudaFree(c->d_ser_point); cudaFree(c->d_ser_field);
     c->d_paug = c->d_rates0 = c->d_series = nullptr; c->d_ser_point = c->d_ser_field = nullptr; c->ser_nt = 0; c->ser_K = 0; c->mode = 0;
@@ -723,8 +858,14 @@ int gxb_topology(gxb_ctx* c, int kind, int64_t np, int64_t ne, const int64_t* st
         c->brow.clear(); c->bcol.clear();
         for (auto& q : v) { c->brow.push_back(q.first); c->bcol.push_back(q.second); }
     }
-    c->body_state = false;
-    for (int64_t k = 0; k < np * 6; k++) if (c->pd[k] && c->pl[k]) c->body_state = true;
+    // update_body_acceleration_indices! (system.jl:138-150): the first point (ascending; the reference iterates a Dict) with pd & pl on DOF i
+    c->body_state = false; c->nbody = 0;
+    for (int i = 0; i < 6; i++) {
+        c->ibody[i] = -1;
+        if (is_static) continue;
+        for (int64_t ip = 0; ip < np; ip++)
+            if (c->pd[ip * 6 + i] && c->pl[ip * 6 + i]) { c->ibody[i] = (int)(c->icol_point[ip] - 1 + i); c->nbody++; c->body_state = true; break; }
+    }
     if (is_static) { c->W = LuShape<2, 2>::W; c->UW = LuShape<2, 2>::UW; c->KLB = 2; c->rows_per_station = 12; }
     else { c->W = LuShape<3, 4>::W; c->UW = LuShape<3, 4>::UW; c->KLB = 3; c->rows_per_station = 18; }
     std::vector<unsigned short> flags(np);
@@ -760,8 +901,6 @@ int gxb_pattern(gxb_ctx* c, int64_t* nblocks, int64_t* brow, int64_t* bcol) {
 
 static int require_chain(gxb_ctx* c, const char* who) {
     if (!c || c->kind < 0) return fail(GXB_ERR_INVALID, std::string(who) + ": call gxb_topology first");
-    if (c->kind == 1 && c->body_state)
-        return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": a DOF with both displacement and load prescribed makes a body-frame acceleration a state variable (system.jl:138-150); not implemented on the device");
     if (!c->chain) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": only chain topologies (start = 1:n, stop = 2:n+1) are implemented on the device");
     if (c->np > 256) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": more than 255 elements per assembly not supported yet (one CTA per instance, shared-memory tile per station)");
     return GXB_OK;
@@ -912,6 +1051,7 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
     } else {
         DynArgs D{};
         D.s = A; D.exS = c->d_exS; D.pxS = c->d_xyz; D.motion = c->d_motion; D.init = c->d_paug; D.c2dt = c->c2dt; D.damping = c->damping;
+        for (int i = 0; i < 6; i++) D.ibody[i] = c->ibody[i];
         // the shared-memory tile holds `chunk` stations; longer chains are flushed chunk by chunk
         const size_t budget = 200 * 1024;
         int chunk = (int)std::min<size_t>((size_t)bs, (budget - (size_t)bs * GXB_XCH * 8) / (GXB_DTILE * 8));
@@ -936,6 +1076,21 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
     }
     CK(cudaGetLastError());
     c->stats.launches++; c->stats.n_assemble++;
+    if (want_j && c->kind == 1 && c->nbody > 0 && c->mode != 1) {
+        // dense Jacobian columns of the body-acceleration states + the unit entries the band matrix keeps in their place
+        const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+        if (!c->d_D) {
+            CK(cudaMalloc(&c->d_D, 6 * nb * n * 8)); CK(cudaMalloc(&c->d_Z, 6 * nb * n * 8));
+            CK(cudaMemsetAsync(c->d_D, 0, 6 * nb * n * 8, c->stream)); CK(cudaMemsetAsync(c->d_Z, 0, 6 * nb * n * 8, c->stream));
+        }
+        BodyArgs B{};
+        B.d.s = A; B.d.exS = c->d_exS; B.d.pxS = c->d_xyz; B.d.motion = c->d_motion;
+        for (int i = 0; i < 6; i++) B.d.ibody[i] = c->ibody[i];
+        B.icS = c->d_icS; B.rvm = c->d_rvm; B.mode = c->mode; B.Dn = c->d_D;
+        k_body_columns<<<(unsigned)c->nbatch, bs, 0, c->stream>>>(B);
+        CK(cudaGetLastError());
+        c->stats.launches++;
+    }
     return GXB_OK;
 }
 template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveArgs& A) {
@@ -949,7 +1104,10 @@ template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveAr
     CK(cudaGetLastError());
     return GXB_OK;
 }
+template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveArgs& A);
+static int launch_factor_body(gxb_ctx* c, const gxb_opts* o);
 static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, double sign = -1.0) {
+    if (c->nbody > 0 && !direction_only) return launch_factor_body(c, o);
     SolveArgs A{};
     A.sign = sign;
     A.nb = (int)(c->n / 6); A.n = (int)c->n; A.nbatch = c->nbatch;
@@ -958,6 +1116,31 @@ static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, doub
     int rc = c->kind == 0 ? launch_factor_t<2, 2>(c, A) : launch_factor_t<3, 4>(c, A);
     if (rc) return rc;
     c->stats.launches++; c->stats.n_factor++;
+    return GXB_OK;
+}
+// Newton step with body-acceleration columns: 1 + nbody band solves (L is not stored, so each one re-factorises B) and the
+// Woodbury correction.  A niche path (free-flying structures): clarity over speed.
+static int launch_factor_body(gxb_ctx* c, const gxb_opts* o) {
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    SolveArgs A{};
+    A.sign = 1.0;
+    A.nb = (int)(c->n / 6); A.n = (int)c->n; A.nbatch = c->nbatch;
+    A.J = c->d_J; A.F = c->d_F; A.x = c->d_x; A.U = c->d_U; A.p = c->d_p; A.xt = c->d_xt; A.ns = c->ns;
+    A.maxstep = o->maxstep; A.linear = o->linear; A.direction_only = 2;
+    int rc;
+    if ((rc = launch_factor_t<3, 4>(c, A))) return rc;
+    for (int i = 0; i < 6; i++) {
+        if (c->ibody[i] < 0) continue;
+        SolveArgs Ai = A; Ai.F = c->d_D + (size_t)i * nb * n; Ai.p = c->d_Z + (size_t)i * nb * n;
+        if ((rc = launch_factor_t<3, 4>(c, Ai))) return rc;
+        c->stats.launches++; c->stats.n_factor++;
+    }
+    WoodArgs W{};
+    W.S = A; W.S.direction_only = 0; W.Z = c->d_Z;
+    for (int i = 0; i < 6; i++) W.ibody[i] = c->ibody[i];
+    k_woodbury<<<grid1(c->nbatch, 4), 128, 0, c->stream>>>(W);
+    CK(cudaGetLastError());
+    c->stats.launches += 2; c->stats.n_factor++;
     return GXB_OK;
 }
 static int launch_update(gxb_ctx* c, const gxb_opts* o, int mode) {
@@ -1248,7 +1431,7 @@ extern "C" {
 // (all CTAs co-resident with few warps per SM), where the multi-kernel rounds are bound by launch/synchronisation and by the
 // slowest instance of the batch.
 static bool use_persistent(const gxb_ctx* c, const gxb_opts& o, bool marching) {
-    if (c->kind != 1 || o.linear || o.profile) return false;
+    if (c->kind != 1 || o.linear || o.profile || c->nbody > 0) return false;
     if (o.persistent == 1) return true;
     if (o.persistent == 2) return false;
     // measured on B200: with every instance needing about the same number of rounds the multi-kernel path wins or
@@ -1259,7 +1442,7 @@ static bool use_persistent(const gxb_ctx* c, const gxb_opts& o, bool marching) {
 }
 // straggler hand-off: once at most this many instances are unfinished, the remaining rounds run in the persistent kernel
 static int64_t straggler_threshold(const gxb_ctx* c, const gxb_opts& o) {
-    if (c->kind != 1 || o.linear || o.profile || o.persistent == 2) return -1;
+    if (c->kind != 1 || o.linear || o.profile || o.persistent == 2 || c->nbody > 0) return -1;
     return std::min<int64_t>(c->sm_count, std::max<int64_t>(1, c->nbatch / 8));
 }
 struct MarchBuffers { int64_t nt = 0; const double* d_tvec = nullptr; int* alive = nullptr; int* steps = nullptr; int* itot = nullptr; double* hist = nullptr; int64_t nsave = 0, save_every = 1; };
@@ -1268,6 +1451,7 @@ static int launch_persistent(gxb_ctx* c, const gxb_opts& o, int mode, const Marc
     P.resume = resume;
     StaticArgs A = make_static_args(c, &o, c->d_xt, c->d_Ft, true, 0, false);
     P.D.s = A; P.D.exS = c->d_exS; P.D.pxS = c->d_xyz; P.D.motion = c->d_motion; P.D.init = c->d_paug; P.D.c2dt = c->c2dt; P.D.damping = c->damping;
+    for (int i = 0; i < 6; i++) P.D.ibody[i] = c->ibody[i];
     P.icS = c->d_icS; P.rvm = c->d_rvm;
     const int bs = (int)((c->np + 31) / 32) * 32;
     // a smaller tile chunk than the multi-kernel assembly: shared memory per CTA decides how many instances are resident per SM
@@ -1467,8 +1651,6 @@ int gxb_newmark_residual_jacobian(gxb_ctx* c, const gxb_opts* opts, const double
 // masks: computed on the device (analyses.jl:1835-1873) unless both rate_vars1 / rate_vars2 (nstates each, shared by the batch) are given
 static int initial_setup(gxb_ctx* c, const gxb_opts& o, const double* ic, const uint8_t* rv1, const uint8_t* rv2, const char* who) {
     if (c->kind != 1) return fail(GXB_ERR_INVALID, std::string(who) + ": context topology is not kind=1 (DynamicSystem)");
-    if (c->body_state) return fail(GXB_ERR_UNSUPPORTED, std::string(who) + ": a DOF with both displacement and load prescribed makes a body-frame "
-                                   "acceleration a state variable (system.jl:138-150); not implemented on the device");
     if ((rv1 == nullptr) != (rv2 == nullptr)) return fail(GXB_ERR_INVALID, std::string(who) + ": give both rate_vars1 and rate_vars2 or neither");
     const size_t nb = (size_t)c->nbatch, P = (size_t)c->np;
     if (!c->d_icS) { CK(cudaMalloc(&c->d_icS, nb * 18 * P * 8)); CK(cudaMalloc(&c->d_rvm, nb * P * 4)); }
@@ -1523,8 +1705,10 @@ int gxb_initial_condition(gxb_ctx* c, const gxb_opts* opts, const double* ic, co
     c->damping = 0;
     if (rc) return rc;
     const size_t nb = (size_t)c->nbatch, P = (size_t)c->np;
+    DynArgs body{};
+    for (int i = 0; i < 6; i++) body.ibody[i] = c->ibody[i];
     k_initial_output<<<grid1(nb * P, 128), 128, 0, c->stream>>>(c->d_x, c->d_bcS, c->d_icS, c->d_rvm, c->d_flags, c->d_xyz, c->d_motion, c->d_rates0,
-                                                                (int)P, (int)c->n, c->nbatch);
+                                                                (int)P, (int)c->n, c->nbatch, body);
     CK(cudaGetLastError());
     c->stats.launches += 1;
     c->have_initial = true;
@@ -1537,6 +1721,18 @@ int gxb_initial_condition(gxb_ctx* c, const gxb_opts* opts, const double* ic, co
             for (int k = 0; k < 6; k++) { rate_vars[12 * t + k] = (m[t] >> (16 + k)) & 1u; rate_vars[12 * t + 6 + k] = (m[t] >> k) & 1u; }
     }
     return gxb_fetch(c, x, converged, iters, resid_inf);
+}
+
+// dense Jacobian columns of the body-acceleration states as left by the last Jacobian assembly (parity tests)
+int gxb_body_columns(gxb_ctx* c, int64_t* icol_body, double* D) {
+    NEED_BATCH("gxb_body_columns");
+    if (icol_body) for (int i = 0; i < 6; i++) icol_body[i] = c->ibody[i] + 1;      // 1-based like SystemIndices, 0 = none
+    if (D) {
+        if (!c->d_D) return fail(GXB_ERR_INVALID, "gxb_body_columns: no Jacobian with body-acceleration columns has been assembled");
+        CK(cudaMemcpyAsync(D, c->d_D, (size_t)6 * c->nbatch * c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return GXB_OK;
 }
 
 // ---- eigenvalue analysis: mass matrix and the Krylov part of solve_eigensystem (src/analyses.jl:943-965) ----
@@ -1575,6 +1771,7 @@ int gxb_eigen_arnoldi(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t
     NEED_BATCH("gxb_eigen_arnoldi");
     if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_eigen_arnoldi: context topology is not kind=1 (DynamicSystem)");
     if (!x || !H || m < 1 || m > c->n) return fail(GXB_ERR_INVALID, "gxb_eigen_arnoldi: need x, H and 1 <= m <= nstates");
+    if (c->nbody > 0) return fail(GXB_ERR_UNSUPPORTED, "gxb_eigen_arnoldi: body-frame acceleration states (dense Jacobian columns) are not supported by the eigen path");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
     c->stats = gxb_stats{};

@@ -153,6 +153,13 @@ int gxb_initial_condition(gxb_ctx* ctx, const gxb_opts* opts, const double* ic, 
 int gxb_initial_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* ic, const uint8_t* rate_vars1,
                                   const uint8_t* rate_vars2, const double* x, double* r, double* Jblk);
 
+/* Body-frame accelerations as state variables (a DOF with displacement AND load prescribed):
+ * update_body_acceleration_indices! / body_accelerations (src/system.jl:138-182), their dense Jacobian columns
+ * (point.jl:1829-1841, 1879-1895; element.jl:2567-2583).  Handled inside the steady / initial-condition solves; this call returns
+ * icol_body (6 entries, 1-based, 0 = none) and, after a gxb_*residual_jacobian call, the dense columns D (6 x nbatch x nstates):
+ * J[:, icol_body[i]] = D[i] + e_{icol_body[i]}; the pattern blocks of Jblk hold the unit entry in that column. */
+int gxb_body_columns(gxb_ctx* ctx, int64_t* icol_body, double* D);
+
 /* system_mass_matrix! (src/system.jl:961-995): M = d r / d xdot at the states x, on gxb_pattern's blocks (kind=1).
  * Mblk: nbatch x nblocks x 9. */
 int gxb_mass_matrix(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* Mblk);

@@ -254,3 +254,25 @@ def massless_initial_jl():
     pms[nelem] = pm / 2
     pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0), nelem + 1: PrescribedConditions(Fz=30, My=-0.2)}
     return _pack(asm, pcs, pm=pms)
+
+
+def free_flying_beam(nelem=8, nstate_dofs=6):
+    """A free-flying beam: the root has displacements AND loads prescribed (all zero) on `nstate_dofs` DOFs, so the corresponding
+    body-frame accelerations become state variables (system.jl:138-150); a tip force accelerates the body.  Exact rigid-body check:
+    linear acceleration = F / (rho A L)."""
+    L = 2.0
+    x = np.linspace(0, L, nelem + 1)
+    points = np.stack([x, 0 * x, 0 * x], 1)
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    E, G, A_, I_, J_ = 70e9, 26e9, 1e-3, 1e-7, 2e-7
+    comp = np.diag([1 / (E * A_), 1 / (G * A_ * 0.8), 1 / (G * A_ * 0.8), 1 / (G * J_), 1 / (E * I_), 1 / (E * I_)])
+    rho = 2700.0
+    mass = np.diag([rho * A_] * 3 + [rho * J_, rho * I_, rho * I_])
+    asm = Assembly(points, start, stop, compliance=[comp] * nelem, mass=[mass] * nelem)
+    names_d = ["ux", "uy", "uz", "theta_x", "theta_y", "theta_z"]
+    names_l = ["Fx", "Fy", "Fz", "Mx", "My", "Mz"]
+    root = {k: 0 for k in names_d}
+    root.update({names_l[i]: 0 for i in range(nstate_dofs)})
+    # the DOF-2 quirk of loads.jl:121 (Fz decides for uy): keep the flags consistent by prescribing all six loads when nstate_dofs == 6
+    pcs = {1: PrescribedConditions(**root), nelem + 1: PrescribedConditions(Fz=5.0, Fx=20.0)}
+    return _pack(asm, pcs, total_mass=rho * A_ * L)

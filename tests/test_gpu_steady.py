@@ -50,12 +50,16 @@ def test_dynamic_indices_bit_exact():
         ctx.close()
 
 
-def test_body_acceleration_state_is_refused():
+def test_body_acceleration_state_is_refused_by_the_eigen_path_only():
+    """Body-frame accelerations as states are supported by the steady / initial-condition solves (tests/test_gpu_body.py); the
+    eigen path still refuses them loudly."""
     case = cases.jacobians_jl(0)
     ctx = api.Context(0)
     ctx.topology(case["start"], case["stop"], case["pd"], case["pl"], kind=1)
+    ctx.set_batch(1)
+    ctx.set_elements(case["elems"]); ctx.set_points(case["points"][None].copy()); ctx.set_bc(case["bc"]); ctx.set_body(None, np.array([case["force_scaling"]]))
     with pytest.raises(api.GXBError, match="body-frame acceleration"):
-        ctx.set_batch(1)
+        ctx.eigen_arnoldi(np.zeros((1, ctx.n)), 4)
     ctx.close()
 
 
