@@ -49,7 +49,7 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_set_motion", "gxb_static_solve", "gxb_steady_solve", "gxb_steady_solve_resident", "gxb_upload_x0",
            "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction",
            "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi",
-           "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns"]
+           "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors"]
 
 _lib = None
 
@@ -304,20 +304,32 @@ class Context:
         self._ck(self.lib.gxb_eigen_arnoldi(self.h, C.byref(o), _ptr(x), C.c_int32(m), _ptr(H), _ptr(V)))
         return H, V
 
-    def eigenvalue_analysis(self, x, nev=6, m=None, opts=None, tol=1e-9):
+    def eigenvalue_analysis(self, x, nev=6, m=None, opts=None, tol=1e-9, want_vectors=True):
         """solve_eigensystem (src/analyses.jl:943-965) at the linearisation states x: returns (lam [nb, nev] complex,
-        vec [nb, n, nev] complex, resid [nb, nev] Ritz residual estimates relative to |mu|)."""
+        vec [nb, n, nev] complex or None, resid [nb, nev] Ritz residual estimates relative to |mu|).
+        The Krylov basis never leaves the GPU: the m x m Hessenberg eigenproblems are solved on the host (stacked LAPACK call), the
+        chosen eigenvectors go back and the Ritz vectors V y are formed on the device (gxb_eigen_ritz_vectors)."""
         m = m or min(self.n, max(3 * nev + 10, 30))
-        H, V = self.eigen_arnoldi(x, m, opts)
-        lam = np.empty((self.nbatch, nev), complex); vec = np.empty((self.nbatch, self.n, nev), complex)
-        res = np.empty((self.nbatch, nev))
-        for b in range(self.nbatch):
-            mu, Y = np.linalg.eig(H[b, :m, :m])
-            order = sorted(range(m), key=lambda i: (abs(mu[i]), mu[i].imag), reverse=True)[:nev]
-            mu, Y = mu[order], Y[:, order]
-            lam[b] = -1.0 / mu
-            vec[b] = V[b, :m].T @ Y
-            res[b] = np.abs(H[b, m, m - 1] * Y[m - 1, :]) / np.abs(mu)
+        H, _ = self.eigen_arnoldi(x, m, opts, want_basis=False)
+        # stacked LAPACK dgeev, spread over host threads (numpy releases the GIL inside the gufunc loop)
+        nth = max(1, min(os.cpu_count() or 1, 32, self.nbatch // 8))
+        bounds = np.linspace(0, self.nbatch, nth + 1).astype(int)
+        Hm = np.ascontiguousarray(H[:, :m, :m])
+        with ThreadPoolExecutor(nth) as ex:
+            parts = list(ex.map(lambda k: np.linalg.eig(Hm[bounds[k]:bounds[k + 1]]), range(nth)))
+        mu = np.concatenate([q[0].astype(complex) for q in parts])            # [nb, m]
+        Y = np.concatenate([q[1].astype(complex) for q in parts])             # [nb, m, m]
+        # sort by (abs, imag) descending like `sortperm(..., by = mu -> (abs(mu), imag(mu)), rev = true)` (analyses.jl:956)
+        order = np.lexsort((-mu.imag, -np.abs(mu)), axis=1)[:, :nev]
+        mu = np.take_along_axis(mu, order, 1)
+        Y = np.take_along_axis(Y, order[:, None, :], 2)                       # [nb, m, nev]
+        lam = -1.0 / mu
+        res = np.abs(H[:, m, m - 1][:, None] * Y[:, m - 1, :]) / np.abs(mu)
+        vec = None
+        if want_vectors:
+            Yc = np.ascontiguousarray(Y.astype(complex))
+            vec = np.empty((self.nbatch, self.n, nev), complex)
+            self._ck(self.lib.gxb_eigen_ritz_vectors(self.h, C.c_int32(nev), _ptr(Yc.view(np.float64)), _ptr(vec.view(np.float64))))
         return lam, vec, res
 
     # --- time marching ---

@@ -68,6 +68,7 @@ struct gxb_ctx {
     double *d_paug = nullptr, *d_rates0 = nullptr, *d_series = nullptr; int *d_ser_point = nullptr, *d_ser_field = nullptr;
     int64_t ser_nt = 0; int ser_K = 0;
     double* d_M = nullptr;   // mass matrix in row-block storage (eigen analysis), allocated on demand
+    double* d_Vk = nullptr; int vk_m = 0;   // Krylov basis of the last gxb_eigen_arnoldi ([b][m+1][n]), kept for gxb_eigen_ritz_vectors
     double* d_icS = nullptr; unsigned* d_rvm = nullptr;   // initial-condition analysis: [b][18][NP] initial values, [b][NP] rate_vars masks
     bool have_initial = false;                            // d_x / d_rates0 hold the output of gxb_initial_condition
     int damping = 0;         // structural_damping of the current solve
@@ -639,6 +640,27 @@ __global__ void k_rowblock_spmv(const double* __restrict__ Mrow, const double* _
     y[t] = acc;
 }
 
+// out[b][c][j] = sum_k Vk[b][k][c] * Y[b][k][j]  (Y complex): thread per state c, four eigenvectors per pass
+__global__ void __launch_bounds__(128) k_ritz_vectors(const double* __restrict__ Vk, const double* __restrict__ Y, double* __restrict__ out, int n, int m, int nev) {
+    const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* V = Vk + (size_t)b * (m + 1) * n;
+    const double* Yb = Y + (size_t)b * m * nev * 2;
+    for (int j0 = 0; j0 < nev; j0 += 4) {
+        double re[4] = {0, 0, 0, 0}, im[4] = {0, 0, 0, 0};
+        if (c < n)
+            for (int k = 0; k < m; k++) {
+                const double v = V[(size_t)k * n + c];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (j0 + q < nev) { re[q] = fma(v, Yb[((size_t)k * nev + j0 + q) * 2], re[q]); im[q] = fma(v, Yb[((size_t)k * nev + j0 + q) * 2 + 1], im[q]); }
+            }
+        if (c < n)
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (j0 + q < nev) { double* o = out + (((size_t)b * n + c) * nev + j0 + q) * 2; o[0] = re[q]; o[1] = im[q]; }
+    }
+}
+
 // Arnoldi bookkeeping, one CTA per instance.  Vk: [b][m+1][n] Krylov basis, H: [b][m+1][m] (row-major), w: [b][n] = A v_j.
 __global__ void __launch_bounds__(256) k_arnoldi_start(double* __restrict__ Vk, int n, int m) {
     const int b = blockIdx.x;
@@ -698,6 +720,7 @@ __global__ void __launch_bounds__(256) k_arnoldi_orth(double* __restrict__ Vk, d
 static void free_batch(gxb_ctx* c) {
     cudaFree(c->d_exS); cudaFree(c->d_motion); c->d_exS = c->d_motion = nullptr;
     cudaFree(c->d_M); c->d_M = nullptr;
+    cudaFree(c->d_Vk); c->d_Vk = nullptr; c->vk_m = 0;
     cudaFree(c->d_D); cudaFree(c->d_Z); c->d_D = c->d_Z = nullptr;
     cudaFree(c->d_icS); cudaFree(c->d_rvm); c->d_icS = nullptr; c->d_rvm = nullptr; c->have_initial = false;
     cudaFree(c->d_paug); cudaFree(c->d_rates0); cudaFree(c->d_series); cudaFree(c->d_ser_point); cudaFree(c->d_ser_field);
@@ -1779,6 +1802,7 @@ int gxb_eigen_arnoldi(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t
     c->mode = 0;
     int rc;
     double *d_V = nullptr, *d_H = nullptr;
+    cudaFree(c->d_Vk); c->d_Vk = nullptr; c->vk_m = 0;
     CK(cudaMalloc(&d_V, nb * (size_t)(m + 1) * n * 8));
     CK(cudaMalloc(&d_H, nb * (size_t)(m + 1) * m * 8));
     CK(cudaMemsetAsync(d_H, 0, nb * (size_t)(m + 1) * m * 8, c->stream));
@@ -1803,7 +1827,30 @@ int gxb_eigen_arnoldi(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->stats.ms_total = ms;
     c->damping = 0;
-    cudaFree(d_V); cudaFree(d_H);
+    cudaFree(d_H);
+    c->d_Vk = d_V; c->vk_m = m;          // stays resident: gxb_eigen_ritz_vectors forms V y on the device
+    return GXB_OK;
+}
+
+// Ritz vectors of the last gxb_eigen_arnoldi: vec[b][:, j] = V_m[b] y[b][:, j]  (solve_eigensystem's `V = Vk * F.vectors`, analyses.jl:959).
+// Y: nbatch x m x nev complex (interleaved re, im; the eigenvectors of the Hessenberg matrices chosen by the caller),
+// vec: nbatch x nstates x nev complex.  Only nev vectors per instance cross PCIe instead of the m+1 basis vectors.
+int gxb_eigen_ritz_vectors(gxb_ctx* c, int32_t nev, const double* Y, double* vec) {
+    NEED_BATCH("gxb_eigen_ritz_vectors");
+    if (!c->d_Vk) return fail(GXB_ERR_INVALID, "gxb_eigen_ritz_vectors: call gxb_eigen_arnoldi first");
+    const int m = c->vk_m;
+    if (!Y || !vec || nev < 1 || nev > m) return fail(GXB_ERR_INVALID, "gxb_eigen_ritz_vectors: need Y, vec and 1 <= nev <= m");
+    const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    double *d_Y = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_Y, nb * m * nev * 16)); CK(cudaMalloc(&d_out, nb * n * nev * 16));
+    CK(cudaMemcpyAsync(d_Y, Y, nb * m * nev * 16, cudaMemcpyHostToDevice, c->stream));
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)nb);
+    k_ritz_vectors<<<grid, 128, 0, c->stream>>>(c->d_Vk, d_Y, d_out, (int)n, m, nev);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(vec, d_out, nb * n * nev * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_Y); cudaFree(d_out);
+    c->stats.launches += 1;
     return GXB_OK;
 }
 

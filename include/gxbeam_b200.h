@@ -153,6 +153,11 @@ int gxb_initial_condition(gxb_ctx* ctx, const gxb_opts* opts, const double* ic, 
 int gxb_initial_residual_jacobian(gxb_ctx* ctx, const gxb_opts* opts, const double* ic, const uint8_t* rate_vars1,
                                   const uint8_t* rate_vars2, const double* x, double* r, double* Jblk);
 
+/* Ritz vectors of the last gxb_eigen_arnoldi on the device: vec[b] = V_m[b] * Y[b]   (`V = Vk * F.vectors`, src/analyses.jl:959).
+ * Y: nbatch x m x nev complex (interleaved re, im) -- the caller's chosen eigenvectors of the Hessenberg matrices;
+ * vec: nbatch x nstates x nev complex.  The Krylov basis stays in HBM; only nev vectors per instance are copied back. */
+int gxb_eigen_ritz_vectors(gxb_ctx* ctx, int32_t nev, const double* Y, double* vec);
+
 /* Body-frame accelerations as state variables (a DOF with displacement AND load prescribed):
  * update_body_acceleration_indices! / body_accelerations (src/system.jl:138-182), their dense Jacobian columns
  * (point.jl:1829-1841, 1879-1895; element.jl:2567-2583).  Handled inside the steady / initial-condition solves; this call returns
