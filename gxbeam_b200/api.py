@@ -49,7 +49,7 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_set_motion", "gxb_static_solve", "gxb_steady_solve", "gxb_steady_solve_resident", "gxb_upload_x0",
            "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction",
            "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi",
-           "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors"]
+           "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors", "gxb_hint_no_gravity"]
 
 _lib = None
 
@@ -139,6 +139,10 @@ class Context:
     def set_batch(self, nbatch):
         self._ck(self.lib.gxb_set_batch(self.h, C.c_int64(nbatch)))
         self.nbatch = nbatch
+
+    def hint_no_gravity(self, on=True):
+        """Static contexts: gravity is zero, upload only the 49 doubles per element that the path reads (54 % of the PCIe bytes)."""
+        self._ck(self.lib.gxb_hint_no_gravity(self.h, int(on)))
 
     def set_elements(self, elems):
         e = _f64(elems)
@@ -393,13 +397,15 @@ class PipelinedSolver:
     Newton solve of chunk k and the device->host copy of chunk k-1: the PCIe transfer of the reference-layout inputs (728 B per
     element) is hidden behind the solve instead of preceding it."""
 
-    def __init__(self, start, stop, pd, pl, chunk, lanes=2, device=0, kind=0):
+    def __init__(self, start, stop, pd, pl, chunk, lanes=2, device=0, kind=0, no_gravity=False):
         self.chunk, self.kind = int(chunk), kind
         self.ctxs = []
         for _ in range(lanes):
             c = Context(device)
             self.indices = c.topology(start, stop, pd, pl, kind=kind)
             c.set_batch(self.chunk)
+            if kind == 0 and no_gravity:
+                c.hint_no_gravity()
             self.ctxs.append(c)
         self.n = self.ctxs[0].n
         self.pool = ThreadPoolExecutor(lanes)

@@ -72,6 +72,7 @@ struct gxb_ctx {
     double* d_icS = nullptr; unsigned* d_rvm = nullptr;   // initial-condition analysis: [b][18][NP] initial values, [b][NP] rate_vars masks
     bool have_initial = false;                            // d_x / d_rates0 hold the output of gxb_initial_condition
     int damping = 0;         // structural_damping of the current solve
+    bool skip_mass = false;  // gxb_hint_no_gravity: static context, element mass / damping / midpoint fields are not uploaded
     int mode = 0;            // 0: steady residual, 1: Newmark residual (set by the time-marching driver), 2: initial-condition residual
     double c2dt = 0.0;
     bool body_state = false;                          // some DOF has pd & pl (body-frame acceleration is a state, system.jl:138-150)
@@ -95,6 +96,25 @@ struct gxb_ctx {
 // elemS[b][f][e]: f=0 L; 1..9 Cab (row-major); 10..45 S11,S12,S21,S22 = L*compliance; 46..81 m11,m12,m21,m22 = L*mass;
 // 82..87 mu (structural damping coefficients)
 #define GXB_ELEM_NF 88
+// compact variant for static contexts without gravity: raw holds 49 doubles per element (L, x[3], compliance[36], Cab[9]) fetched with
+// two strided copies; the mass and damping fields, which that path never reads, are zero-filled
+__global__ void k_pack_elements_compact(const double* __restrict__ raw, double* __restrict__ out, int N, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * N) return;
+    int64_t b = t / N; int e = (int)(t % N);
+    const double* s = raw + t * 49;
+    double* o = out + (size_t)b * GXB_ELEM_NF * N + e;
+    const double L = s[0];
+    o[0] = L;
+    for (int k = 0; k < 6; k++) o[(size_t)(82 + k) * N] = 0.0;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[(size_t)(1 + 3 * i + j) * N] = s[40 + i + 3 * j];
+    for (int bi = 0; bi < 2; bi++) for (int bj = 0; bj < 2; bj++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        int f = 9 * (2 * bi + bj) + 3 * i + j;
+        int src = (3 * bi + i) + 6 * (3 * bj + j);
+        o[(size_t)(10 + f) * N] = s[4 + src] * L;
+        o[(size_t)(46 + f) * N] = 0.0;
+    }
+}
 __global__ void k_pack_elements(const double* __restrict__ raw, double* __restrict__ out, double* __restrict__ exS, int N, int64_t nbatch) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= nbatch * N) return;
@@ -971,6 +991,17 @@ int gxb_set_batch(gxb_ctx* c, int64_t nbatch) {
 int gxb_set_elements(gxb_ctx* c, const double* elems) {
     NEED_BATCH("gxb_set_elements");
     if (!elems) return fail(GXB_ERR_INVALID, "gxb_set_elements: null");
+    if (c->kind == 0 && c->skip_mass) {
+        // only what the static path without gravity reads: L, x, compliance (40 doubles) and Cab (9 doubles) of every 91-double record
+        const size_t ne = (size_t)c->nbatch * c->ne, bytes = ne * 49 * 8;
+        if (bytes > c->stage_bytes) { cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0; CK(cudaMalloc(&c->d_stage, bytes)); c->stage_bytes = bytes; }
+        CK(cudaMemcpy2DAsync(c->d_stage, 49 * 8, elems, GXB_ELEM_STRIDE * 8, 40 * 8, ne, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpy2DAsync(c->d_stage + 40, 49 * 8, elems + 76, GXB_ELEM_STRIDE * 8, 9 * 8, ne, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(c->evC, c->stream));
+        k_pack_elements_compact<<<grid1(c->nbatch * c->ne, 128), 128, 0, c->stream>>>(c->d_stage, c->d_elemS, (int)c->ne, c->nbatch);
+        CK(cudaGetLastError());
+        return wait_copy(c);
+    }
     int rc = stage_upload(c, elems, (size_t)c->nbatch * c->ne * GXB_ELEM_STRIDE * 8); if (rc) return rc;
     k_pack_elements<<<grid1(c->nbatch * c->ne, 128), 128, 0, c->stream>>>(c->d_stage, c->d_elemS, c->d_exS, (int)c->ne, c->nbatch);
     CK(cudaGetLastError());
@@ -1023,11 +1054,22 @@ int gxb_set_pmass(gxb_ctx* c, const double* pm) {
     CK(cudaStreamSynchronize(c->stream));
     return GXB_OK;
 }
+// The caller promises that gravity is zero in this static context, so the element mass (36), damping (6) and midpoint fields are
+// never read (46 of the 91 element doubles suffice for static analyses without gravity): gxb_set_elements then
+// fetches 49 of the 91 doubles of every element record with two strided copies -- 54 % of the PCIe bytes.
+int gxb_hint_no_gravity(gxb_ctx* c, int on) {
+    if (!c) return fail(GXB_ERR_INVALID, "gxb_hint_no_gravity: null");
+    if (on && c->kind != 0) return fail(GXB_ERR_INVALID, "gxb_hint_no_gravity: only static contexts (kind = 0) can skip the element mass");
+    if (on && c->has_grav) return fail(GXB_ERR_INVALID, "gxb_hint_no_gravity: a non-zero gravity vector is set");
+    c->skip_mass = on != 0;
+    return GXB_OK;
+}
 int gxb_set_body(gxb_ctx* c, const double* gravity, const double* force_scaling) {
     NEED_BATCH("gxb_set_body");
     c->has_grav = 0;
     if (gravity) {
         for (int64_t i = 0; i < c->nbatch * 3; i++) if (gravity[i] != 0.0) { c->has_grav = 1; break; }
+        if (c->has_grav && c->skip_mass) { c->has_grav = 0; return fail(GXB_ERR_INVALID, "gxb_set_body: non-zero gravity after gxb_hint_no_gravity (the element mass was not uploaded)"); }
         CK(cudaMemcpyAsync(c->d_grav, gravity, (size_t)c->nbatch * 24, cudaMemcpyHostToDevice, c->stream));
     } else CK(cudaMemsetAsync(c->d_grav, 0, (size_t)c->nbatch * 24, c->stream));
     if (force_scaling) {

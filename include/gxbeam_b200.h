@@ -86,6 +86,10 @@ int gxb_pattern(gxb_ctx* ctx, int64_t* nblocks, int64_t* brow, int64_t* bcol);
 /* Per-instance inputs.  All arrays are [nbatch][...] contiguous.  gxb_set_batch first. */
 int gxb_set_batch(gxb_ctx* ctx, int64_t nbatch);
 int gxb_set_elements(gxb_ctx* ctx, const double* elems);   /* nbatch x ne x 91   assembly.elements            */
+/* Static contexts only: promise that gravity is zero, so that gxb_set_elements uploads only L, x, compliance and Cab (49 of the 91
+ * doubles of an Element; static_element_properties reads nothing else without gravity, src/element.jl:62-107, 1860-1899).
+ * A later gxb_set_body with non-zero gravity fails loudly. */
+int gxb_hint_no_gravity(gxb_ctx* ctx, int on);
 int gxb_set_points(gxb_ctx* ctx, const double* xyz);       /* nbatch x np x 3    assembly.points (dynamic only) */
 int gxb_set_bc(gxb_ctx* ctx, const double* bc);            /* nbatch x np x 18   prescribed_conditions values  */
 int gxb_set_dloads(gxb_ctx* ctx, const double* dl);        /* nbatch x ne x 24 or NULL   distributed_loads     */

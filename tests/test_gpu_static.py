@@ -269,3 +269,26 @@ def test_multi_device_entry_point_single_gpu():
     w = workloads.cantilever_tipmoment_batch(32, 20)
     out = api.static_analysis_batch(w["start"], w["stop"], w["elems"], w["pd"], w["pl"], w["bc"], force_scaling=w["force_scaling"], devices=(0,))
     assert out.converged.all() and out.x.shape == (32, 12 * 20 + 6)
+
+
+def test_no_gravity_hint_uploads_less_and_changes_nothing():
+    """gxb_hint_no_gravity: only L, x, compliance, Cab of every element record cross PCIe; the solve is bit-identical, and a later
+    non-zero gravity is refused loudly."""
+    w = workloads.cantilever_tipmoment_batch(64, 30)
+    rng = np.random.default_rng(5)
+    elems = w["elems"].copy()
+    elems[:, :, 40:76] = rng.random(elems[:, :, 40:76].shape)          # junk in the mass fields must not matter without gravity
+    out = []
+    for hint in (False, True):
+        ctx = api.Context(0)
+        ctx.topology(w["start"], w["stop"], w["pd"], w["pl"])
+        ctx.set_batch(64)
+        if hint:
+            ctx.hint_no_gravity()
+        ctx.set_elements(elems); ctx.set_bc(w["bc"]); ctx.set_body(None, w["force_scaling"])
+        out.append(ctx.static_solve())
+        if hint:
+            with pytest.raises(api.GXBError, match="gravity"):
+                ctx.set_body(np.ones((64, 3)), w["force_scaling"])
+        ctx.close()
+    assert out[0]["converged"].all() and np.array_equal(out[0]["iters"], out[1]["iters"]) and np.array_equal(out[0]["x"], out[1]["x"])
