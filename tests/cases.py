@@ -276,3 +276,55 @@ def free_flying_beam(nelem=8, nstate_dofs=6):
     # the DOF-2 quirk of loads.jl:121 (Fz decides for uy): keep the flags consistent by prescribing all six loads when nstate_dofs == 6
     pcs = {1: PrescribedConditions(**root), nelem + 1: PrescribedConditions(Fz=5.0, Fx=20.0)}
     return _pack(asm, pcs, total_mass=rho * A_ * L)
+
+
+def _zeros_jl_section():
+    """Cross-section of test/issues/zeros.jl:31-56 (also test/examples/rotating.jl)."""
+    w, h = 1.0, 0.063
+    E, nu, rho = 1.06e7, 0.325, 2.51e-4
+    ky, kz, kt = 1.2000001839588001, 14.625127919304001, 65.85255016982444
+    A = h * w
+    Iyy, Izz = w * h ** 3 / 12, w ** 3 * h / 12
+    J = Iyy + Izz
+    Ay, Az, Jx = A / ky, A / kz, J / kt
+    G = E / (2 * (1 + nu))
+    comp = np.diag([1 / (E * A), 1 / (G * Ay), 1 / (G * Az), 1 / (G * Jx), 1 / (E * Iyy), 1 / (E * Izz)])
+    mass = np.diag([rho * A, rho * A, rho * A, rho * J, rho * Iyy, rho * Izz])
+    return comp, mass
+
+
+def zero_mass_jl():
+    """test/issues/zeros.jl:3-77 "Zero Mass Matrix": swept-tip blade at 750 rpm with an all-zero mass matrix; steady_state_analysis
+    must converge."""
+    sweep, rpm = 45 * np.pi / 180, 750
+    len1, xp1, xm1, Cab1 = discretize_beam(31.5, [2.5, 0, 0], 13)
+    cs, ss = np.cos(sweep), np.sin(sweep)
+    frame = np.array([[cs, ss, 0], [-ss, cs, 0], [0, 0, 1.0]])
+    len2, xp2, xm2, Cab2 = discretize_beam(6.0, [34, 0, 0], 3, frame=frame)
+    nelem = 16
+    points = np.array(list(xp1) + list(xp2[1:]))
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    comp, _ = _zeros_jl_section()
+    asm = Assembly(points, start, stop, compliance=[comp] * nelem, mass=[np.zeros((6, 6))] * nelem, frames=list(Cab1) + list(Cab2),
+                   lengths=list(len1) + list(len2), midpoints=list(xm1) + list(xm2))
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
+    return _pack(asm, pcs, angular_velocity=np.array([0, 0, rpm * 2 * np.pi / 60]))
+
+
+def zero_length_element_jl():
+    """test/issues/zeros.jl:79-168 "Zero Length Element": the same blade with its real mass matrix and a zero-length element between
+    the straight and the swept section (the joint point is duplicated); steady_state_analysis must converge."""
+    sweep, rpm = 45 * np.pi / 180, 750
+    len1, xp1, xm1, Cab1 = discretize_beam(31.5, [2.5, 0, 0], 13)
+    len12, xp12, xm12, Cab12 = discretize_beam(0.0, [34, 0, 0], 1)
+    cs, ss = np.cos(sweep), np.sin(sweep)
+    frame = np.array([[cs, ss, 0], [-ss, cs, 0], [0, 0, 1.0]])
+    len2, xp2, xm2, Cab2 = discretize_beam(6.0, [34, 0, 0], 3, frame=frame)
+    nelem = 17
+    points = np.array(list(xp1) + list(xp2))                      # vcat(xp_b1, xp_b2): the joint appears twice
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    comp, mass = _zeros_jl_section()
+    asm = Assembly(points, start, stop, compliance=[comp] * nelem, mass=[mass] * nelem, frames=list(Cab1) + list(Cab12) + list(Cab2),
+                   lengths=list(len1) + list(len12) + list(len2), midpoints=list(xm1) + list(xm12) + list(xm2))
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
+    return _pack(asm, pcs, angular_velocity=np.array([0, 0, rpm * 2 * np.pi / 60]))

@@ -223,3 +223,52 @@ def test_long_chain_chunked_tiles_parity():
     assert res["converged"].all() and ref["converged"].all() and np.array_equal(res["iters"], ref["iters"])
     for b in range(nb):
         assert np.abs(res["x"][b] - ref["x"][b]).max() <= 1e-9 * np.abs(ref["x"][b]).max()
+
+
+@pytest.mark.parametrize("builder", ["zero_mass_jl", "zero_length_element_jl"])
+def test_zeros_jl_steady_cases_parity(builder):
+    """test/issues/zeros.jl:3-168 on the device: zero mass matrix and a zero-length element (L = 0: compliance and mass blocks
+    vanish, the duplicated joint point is tied by the compatibility rows alone) converge like the oracle."""
+    O = _oracle()
+    case = getattr(cases, builder)()
+    pk = cases.oracle_packed(case)
+    mo = np.zeros((1, 12)); mo[0, 3:6] = case["angular_velocity"]
+    ctx = _ctx(case, mo)
+    res = ctx.steady_solve()
+    ctx.close()
+    ref = O.steady_solve(pk, O.make_dyn(wb=case["angular_velocity"]))
+    assert ref["converged"] and res["converged"][0] and int(res["iters"][0]) == ref["iters"]
+    scale = np.abs(ref["x"]).max()
+    assert np.abs(res["x"][0] - ref["x"]).max() <= 1e-9 * scale
+
+
+def test_edge_sizes_and_failure_isolation():
+    """Smallest chain (1 element), a batch of one, an iteration cap of one, and a NaN in one member's inputs: the bad member is
+    reported unconverged, everyone else is untouched."""
+    O = _oracle()
+    w = workloads.rotating_blade_batch(5, rpm_jitter=0.3)
+    elems = w["elems"].copy()
+    elems[3, 7, 10] = np.nan                                       # a NaN compliance entry in member 3
+    ctx = _ctx({**w, "elems": elems}, w["motion"], 5, w["points_b"])
+    res = ctx.steady_solve()
+    capped = ctx.steady_solve(api.make_opts(iterations=1))
+    ctx.close()
+    ok = np.array([True, True, True, False, True])
+    assert np.array_equal(res["converged"], ok)
+    assert not capped["converged"][ok].any() and (capped["iters"][ok] == 1).all()
+    pk = O.Packed(w["start"], w["stop"], w["elems"], w["points_b"], w["pd"], w["pl"], w["bc"])
+    dyns = [O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6]) for b in range(5)]
+    ref = O.steady_solve_batch(pk, 5, dyns, force_scaling=w["force_scaling"])
+    for b in np.nonzero(ok)[0]:
+        assert res["iters"][b] == ref["iters"][b]
+        assert np.abs(res["x"][b] - ref["x"][b]).max() <= 1e-9 * np.abs(ref["x"][b]).max()
+    # one element, one instance
+    one = cases.tipmoment(0.2, nelem=1)
+    pk1 = cases.oracle_packed(one)
+    mo = np.zeros((1, 12)); mo[0, 3:6] = [0.1, 0.2, 0.3]
+    ctx = _ctx(one, mo)
+    r1 = ctx.steady_solve()
+    ctx.close()
+    ref1 = O.steady_solve(pk1, O.make_dyn(wb=mo[0, 3:6]))
+    assert bool(r1["converged"][0]) == ref1["converged"] and int(r1["iters"][0]) == ref1["iters"]
+    assert np.abs(r1["x"][0] - ref1["x"]).max() <= 1e-9 * np.abs(ref1["x"]).max()

@@ -58,3 +58,12 @@ def test_steady_reduces_to_static_at_rest():
     for ie in range(len(ids["icol_elem"])):
         a, b = ids["icol_elem"][ie] - 1, idd["icol_elem"][ie] - 1
         assert np.allclose(rd["x"][b:b + 6], rs["x"][a:a + 6], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("builder", ["zero_mass_jl", "zero_length_element_jl"])
+def test_zeros_jl_steady_cases_converge(builder):
+    """test/issues/zeros.jl:3-168: zero mass matrix, zero-length element -- the reference asserts `converged`."""
+    case = getattr(cases, builder)()
+    pk = cases.oracle_packed(case)
+    r = O.steady_solve(pk, O.make_dyn(wb=case["angular_velocity"]))
+    assert r["converged"] and r["error"] == 0
