@@ -328,3 +328,63 @@ def zero_length_element_jl():
                    lengths=list(len1) + list(len12) + list(len2), midpoints=list(xm1) + list(xm12) + list(xm2))
     pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
     return _pack(asm, pcs, angular_velocity=np.array([0, 0, rpm * 2 * np.pi / 60]))
+
+
+def static_joined_wing(Fz=0.0, follower=False):
+    """test/examples/static-joined-wing.jl:5-100: five beams (5+5+5+5+20 elements) forming a chain clamped at BOTH ends, load Fz (dead
+    or follower) at the joint."""
+    p = [np.array(v, float) for v in ([-7.1726, -12, -3.21539], [-5.37945, -9, -2.41154], [-3.5863, -6, -1.6077],
+                                      [-1.79315, -3, -0.803848], [0, 0, 0], [7.1726, -12, 3.21539])]
+
+    def frame(q, sgn):
+        t1 = np.hypot(q[0], q[1]); c1, s1 = sgn * q[0] / t1, sgn * q[1] / t1
+        rot1 = np.array([[c1, -s1, 0], [s1, c1, 0], [0, 0, 1.0]])
+        t2 = np.linalg.norm(q); c2, s2 = t1 / t2, sgn * q[2] / t2
+        rot2 = np.array([[c2, 0, -s2], [0, 1, 0], [s2, 0, c2]])
+        return rot1 @ rot2
+    Cab_1, Cab_2 = frame(p[0], -1.0), frame(p[5], 1.0)
+    comps = [[1.05204e-9, 3.19659e-9, 2.13106e-8, 1.15475e-7, 1.52885e-7, 7.1672e-9],
+             [1.24467e-9, 3.77682e-9, 2.51788e-8, 1.90461e-7, 2.55034e-7, 1.18646e-8],
+             [1.60806e-9, 4.86724e-9, 3.24482e-8, 4.07637e-7, 5.57611e-7, 2.55684e-8],
+             [2.56482e-9, 7.60456e-9, 5.67609e-8, 1.92171e-6, 2.8757e-6, 1.02718e-7],
+             [2.77393e-9, 7.60456e-9, 1.52091e-7, 1.27757e-5, 2.7835e-5, 1.26026e-7]]
+    nel = [5, 5, 5, 5, 20]
+    lengths, points, mids, frames, comp = [], [], [], [], []
+    for k in range(5):
+        L = np.linalg.norm(p[k + 1] - p[k])
+        ln, xp, xm, cab = discretize_beam(L, p[k], nel[k], frame=Cab_1 if k < 4 else Cab_2)
+        lengths += list(ln); mids += list(xm); frames += list(cab); comp += [np.diag(comps[k])] * nel[k]
+        points += list(xp) if k == 0 else list(xp[1:])
+    nelem = sum(nel)
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    asm = Assembly(np.array(points), start, stop, compliance=comp, frames=frames, lengths=lengths, midpoints=mids)
+    clamp = dict(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)
+    load = dict(Fz_follower=Fz) if follower else dict(Fz=Fz)
+    pcs = {1: PrescribedConditions(**clamp), 21: PrescribedConditions(**load), nelem + 1: PrescribedConditions(**clamp)}
+    return _pack(asm, pcs, joint=21)
+
+
+def dynamic_joined_wing():
+    """test/examples/dynamic-joined-wing.jl:5-83: two 4-element beams joined at the origin, both outer ends clamped, time-varying loads
+    Fx = Fy = F_L(t), Fz = F_S(t) at the joint; tvec = range(0, 0.01, 201).  Returns the case at t = 0 plus the load series
+    (fields 6, 7, 8 of point 5)."""
+    p1, p2, p3 = np.zeros(3), np.array([-7.1726, -12, -3.21539]), np.array([7.1726, -12, 3.21539])
+    Cab_1 = np.array([[0.5, 0.866025, 0.0], [0.836516, -0.482963, 0.258819], [0.224144, -0.12941, -0.965926]])
+    Cab_2 = np.array([[0.5, 0.866025, 0.0], [-0.836516, 0.482963, 0.258819], [0.224144, -0.12941, 0.965926]])
+    l1, xp1, xm1, c1 = discretize_beam(np.linalg.norm(p1 - p2), p2, 4, frame=Cab_1)
+    l2, xp2, xm2, c2 = discretize_beam(np.linalg.norm(p3 - p1), p1, 4, frame=Cab_2)
+    nelem = 8
+    points = np.array(list(xp1) + list(xp2[1:]))
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    comp = np.diag([2.93944738387698e-10, 8.42991725049126e-10, 3.38313996669689e-08, 4.69246721094557e-08, 6.79584100559513e-08,
+                    1.37068861370898e-09])
+    mass = np.diag([4.86e-2, 4.86e-2, 4.86e-2, 1.0632465e-2, 2.10195e-4, 1.042227e-2])
+    asm = Assembly(points, start, stop, compliance=[comp] * nelem, mass=[mass] * nelem, frames=list(c1) + list(c2),
+                   lengths=list(l1) + list(l2), midpoints=list(xm1) + list(xm2))
+    tvec = np.linspace(0, 0.01, 201)
+    F_L = np.where(tvec < 0.01, 1e6 * tvec, np.where(tvec < 0.02, -1e6 * (tvec - 0.02), 0.0))
+    F_S = np.where(tvec < 0.02, 5e3 * (1 - np.cos(np.pi * tvec / 0.02)), 1e4)
+    clamp = dict(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)
+    pcs = {1: PrescribedConditions(**clamp), 5: PrescribedConditions(Fx=F_L[0], Fy=F_L[0], Fz=F_S[0]), nelem + 1: PrescribedConditions(**clamp)}
+    series = np.stack([F_L, F_L, F_S], 1)                      # [nt, 3] -> fields 6, 7, 8 of point 5
+    return _pack(asm, pcs, tvec=tvec, series=series)

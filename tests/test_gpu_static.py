@@ -292,3 +292,53 @@ def test_no_gravity_hint_uploads_less_and_changes_nothing():
                 ctx.set_body(np.ones((64, 3)), w["force_scaling"])
         ctx.close()
     assert out[0]["converged"].all() and np.array_equal(out[0]["iters"], out[1]["iters"]) and np.array_equal(out[0]["x"], out[1]["x"])
+
+
+def _ctx_case(case, nb=1):
+    ctx = api.Context(0)
+    ctx.topology(case["start"], case["stop"], case["pd"], case["pl"])
+    ctx.set_batch(nb)
+    return ctx
+
+
+def test_static_joined_wing_linear_sweep_as_one_batch():
+    """test/examples/static-joined-wing.jl:103-121: 141 load levels of the joined wing (a chain clamped at BOTH ends), linear = true --
+    independent solves, so they go out as ONE batch."""
+    O = _oracle()
+    Fz = np.linspace(0, 70e3, 141)
+    cs = [cases.static_joined_wing(f) for f in Fz]
+    ctx = _ctx_case(cs[0], 141)
+    ctx.set_elements(np.concatenate([c["elems"] for c in cs])); ctx.set_bc(np.concatenate([c["bc"] for c in cs]))
+    ctx.set_body(None, np.array([c["force_scaling"] for c in cs]))
+    res = ctx.static_solve(api.make_opts(linear=True))
+    ctx.close()
+    assert res["converged"].all()
+    for k in (1, 70, 140):
+        ref = O.static_solve(cases.oracle_packed(cs[k]), linear=True)
+        assert np.abs(res["x"][k] - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
+    # linear: the response scales with the load
+    assert np.abs(res["x"][140] - 2 * res["x"][70]).max() <= 1e-9 * np.abs(res["x"][140]).max()
+
+
+@pytest.mark.parametrize("follower", [False, True])
+def test_static_joined_wing_nonlinear_continuation(follower):
+    """static-joined-wing.jl:123-150: the nonlinear sweeps with reset_state = false -- every load level starts from the previous
+    solution (from zero the full load does not converge).  Dead and follower load; iteration counts must match the oracle's."""
+    O = _oracle()
+    Fz = np.linspace(0, 70e3, 141)
+    case0 = cases.static_joined_wing(0.0, follower)
+    ctx = _ctx_case(case0, 1)
+    ctx.set_elements(case0["elems"]); ctx.set_body(None, np.array([case0["force_scaling"]]))
+    x = None; xo = None
+    its, its_ref = [], []
+    for f in Fz:
+        c = cases.static_joined_wing(f, follower)
+        ctx.set_bc(c["bc"])
+        r = ctx.static_solve(x0=x)
+        ref = O.static_solve(cases.oracle_packed(c), x0=xo)
+        assert r["converged"][0] and ref["converged"]
+        x, xo = r["x"], ref["x"]
+        its.append(int(r["iters"][0])); its_ref.append(ref["iters"])
+    ctx.close()
+    assert its == its_ref
+    assert np.abs(x[0] - xo).max() <= 1e-9 * np.abs(xo).max()
