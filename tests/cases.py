@@ -388,3 +388,21 @@ def dynamic_joined_wing():
     pcs = {1: PrescribedConditions(**clamp), 5: PrescribedConditions(Fx=F_L[0], Fy=F_L[0], Fz=F_S[0]), nelem + 1: PrescribedConditions(**clamp)}
     series = np.stack([F_L, F_L, F_S], 1)                      # [nt, 3] -> fields 6, 7, 8 of point 5
     return _pack(asm, pcs, tvec=tvec, series=series)
+
+
+def rotating_swept_tip(sweep_deg, nelem_b1=20, nelem_b2=20):
+    """test/examples/rotating.jl:68-100: 31.5 in straight blade + 6 in tip swept by `sweep_deg`, 20 + 20 elements, root clamped;
+    the reference compares its eigen-frequencies with the experiment of Epps & Chandra (table at rotating.jl:139-181)."""
+    sweep = sweep_deg * np.pi / 180
+    len1, xp1, xm1, Cab1 = discretize_beam(31.5, [2.5, 0, 0], nelem_b1)
+    cs, ss = np.cos(sweep), np.sin(sweep)
+    frame = np.array([[cs, ss, 0], [-ss, cs, 0], [0, 0, 1.0]])
+    len2, xp2, xm2, Cab2 = discretize_beam(6.0, [34, 0, 0], nelem_b2, frame=frame)
+    nelem = nelem_b1 + nelem_b2
+    points = np.array(list(xp1) + list(xp2[1:]))
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    comp, mass = _zeros_jl_section()
+    asm = Assembly(points, start, stop, compliance=[comp] * nelem, mass=[mass] * nelem, frames=list(Cab1) + list(Cab2),
+                   lengths=list(len1) + list(len2), midpoints=list(xm1) + list(xm2))
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
+    return _pack(asm, pcs)
