@@ -406,3 +406,17 @@ def rotating_swept_tip(sweep_deg, nelem_b1=20, nelem_b2=20):
                    lengths=list(len1) + list(len2), midpoints=list(xm1) + list(xm2))
     pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0)}
     return _pack(asm, pcs)
+
+
+def wind_turbine_blade_jl():
+    """test/examples/wind-turbine-blade.jl:5-52: 60 m blade, 5 elements, fully populated 6x6 stiffness and mass, tip load
+    Fz = 1e5 sin(20 t), tvec = 0:0.001:0.1."""
+    from gxbeam_b200.workloads import WT_STIFFNESS, WT_MASS
+    nelem = 5
+    x = np.linspace(0, 60.0, nelem + 1)
+    points = np.stack([x, 0 * x, 0 * x], 1)
+    start, stop = np.arange(1, nelem + 1), np.arange(2, nelem + 2)
+    asm = Assembly(points, start, stop, stiffness=[WT_STIFFNESS] * nelem, mass=[WT_MASS] * nelem)
+    tvec = np.arange(0, 0.1 + 1e-12, 0.001)
+    pcs = {1: PrescribedConditions(ux=0, uy=0, uz=0, theta_x=0, theta_y=0, theta_z=0), nelem + 1: PrescribedConditions(Fz=0.0)}
+    return _pack(asm, pcs, tvec=tvec, series=(1e5 * np.sin(20 * tvec))[:, None])

@@ -182,3 +182,29 @@ def test_dynamic_joined_wing_time_domain_analysis(damping):
     for name, ids in _groups(O, case).items():
         err = np.abs(res["x"][0][:, ids] - ref["x"][::10][:, ids]).max()
         assert err <= 1e-8 * np.abs(ref["x"][:, ids]).max(), (name, err)
+
+
+@pytest.mark.parametrize("damping", [False, True])
+def test_wind_turbine_blade_time_domain_analysis(damping):
+    """test/examples/wind-turbine-blade.jl: fully populated 6x6 stiffness / mass, tip load 1e5 sin(20 t), 100 steps, with and
+    without structural damping (the reference asserts `converged`)."""
+    O = _oracle()
+    case = cases.wind_turbine_blade_jl()
+    tvec, series = case["tvec"], case["series"]
+    nt = len(tvec)
+    opts = api.make_opts(structural_damping=damping)
+    ctx = _ctx(case, np.zeros((1, 12)))
+    ini = ctx.initial_condition(opts=opts)
+    ctx.set_bc_series([6], [8], series[None])
+    res = ctx.newmark_run(tvec, opts=opts)
+    ctx.close()
+    assert ini["converged"][0] and res["converged"][0] and res["steps_done"][0] == nt
+    pk = cases.oracle_packed(case)
+    dyn = O.make_dyn(structural_damping=damping)
+    ri = O.initial_condition(pk, dyn, O.InitialConditions(pk.np, O.nstates(pk, static=False)))
+    bct = np.tile(case["bc"][0][None], (nt, 1, 1)); bct[:, 5, 8] = series[:, 0]
+    ref = O.newmark_run(pk, dyn, tvec, ri["x"], ri["rates"], bct)
+    assert ref["converged"] and int(res["iters_total"][0]) == int(ref["iters"].sum())
+    for name, ids in _groups(O, case).items():
+        err = np.abs(res["x"][0][:, ids] - ref["x"][:, ids]).max()
+        assert err <= 1e-8 * np.abs(ref["x"][:, ids]).max(), (name, err)
