@@ -1,0 +1,640 @@
+// Device side of the solver: packing kernels, the kernel wrappers of the fused assembly, body-acceleration columns, initial-condition
+// helpers, the Newton step (factorise + solve, Woodbury correction, Armijo / convergence update), mass matrix and Arnoldi kernels.
+// Host code and the C-ABI live in gxb_lib.cu.
+#pragma once
+#include "gxb_lu.cuh"
+#include "gxb_static.cuh"
+#include "gxb_dynamic.cuh"
+#include "gxb_initial.cuh"
+
+#ifndef GXB_LU_MINBLOCKS
+#define GXB_LU_MINBLOCKS 4
+#endif
+
+enum { ST_SOLVE = 0, ST_TRIAL = 1, ST_DONE = 2, ST_FAILED = 3 };
+enum { FAIL_NONE = 0, FAIL_NONFINITE = 1, FAIL_LINESEARCH = 2, FAIL_MAXITER = 3, FAIL_SINGULAR = 4 };
+
+// per-instance Newton / line-search scalars (structure of arrays)
+struct NewtonState {
+    int* status; int* failcode; int* iters; int* fcalls; int* ls_k; int* ls_finite;
+    double* a1; double* a2; double* phi0; double* dphi0; double* phx0; double* finf;
+};
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// packing kernels: caller's array-of-structs (the reference's memory layout) -> structure-of-arrays in HBM
+// elemS[b][f][e]: f=0 L; 1..9 Cab (row-major); 10..45 S11,S12,S21,S22 = L*compliance; 46..81 m11,m12,m21,m22 = L*mass;
+// 82..87 mu (structural damping coefficients)
+#define GXB_ELEM_NF 88
+// compact variant for static contexts without gravity: raw holds 49 doubles per element (L, x[3], compliance[36], Cab[9]) fetched with
+// two strided copies; the mass and damping fields, which that path never reads, are zero-filled
+__global__ void k_pack_elements_compact(const double* __restrict__ raw, double* __restrict__ out, int N, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * N) return;
+    int64_t b = t / N; int e = (int)(t % N);
+    const double* s = raw + t * 49;
+    double* o = out + (size_t)b * GXB_ELEM_NF * N + e;
+    const double L = s[0];
+    o[0] = L;
+    for (int k = 0; k < 6; k++) o[(size_t)(82 + k) * N] = 0.0;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[(size_t)(1 + 3 * i + j) * N] = s[40 + i + 3 * j];
+    for (int bi = 0; bi < 2; bi++) for (int bj = 0; bj < 2; bj++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        int f = 9 * (2 * bi + bj) + 3 * i + j;
+        int src = (3 * bi + i) + 6 * (3 * bj + j);
+        o[(size_t)(10 + f) * N] = s[4 + src] * L;
+        o[(size_t)(46 + f) * N] = 0.0;
+    }
+}
+__global__ void k_pack_elements(const double* __restrict__ raw, double* __restrict__ out, double* __restrict__ exS, int N, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * N) return;
+    int64_t b = t / N; int e = (int)(t % N);
+    const double* s = raw + t * GXB_ELEM_STRIDE;
+    double* o = out + (size_t)b * GXB_ELEM_NF * N + e;
+    const double L = s[0];
+    o[0] = L;
+    if (exS) for (int k = 0; k < 3; k++) exS[((size_t)b * 3 + k) * N + e] = s[1 + k];    // Element.x (midpoint)
+    for (int k = 0; k < 6; k++) o[(size_t)(82 + k) * N] = s[85 + k];                       // Element.mu
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[(size_t)(1 + 3 * i + j) * N] = s[76 + i + 3 * j];
+    for (int bi = 0; bi < 2; bi++) for (int bj = 0; bj < 2; bj++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        int f = 9 * (2 * bi + bj) + 3 * i + j;
+        int src = (3 * bi + i) + 6 * (3 * bj + j);
+        o[(size_t)(10 + f) * N] = s[4 + src] * L;     // compliance *= L   (element.jl:69)
+        o[(size_t)(46 + f) * N] = s[40 + src] * L;    // mass *= L         (element.jl:70)
+    }
+}
+// out[b][f][p] = raw[b][p][f]
+__global__ void k_pack_transpose(const double* __restrict__ raw, double* __restrict__ out, int P, int F, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * P * F) return;
+    int f = (int)(t % F); int64_t q = t / F; int p = (int)(q % P); int64_t b = q / P;
+    out[((size_t)b * F + f) * P + p] = raw[t];
+}
+// point masses: raw[b][p][36 col-major] -> out[b][9*(2bi+bj)+3i+j][p]
+__global__ void k_pack_pmass(const double* __restrict__ raw, double* __restrict__ out, int P, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * P * 36) return;
+    int f = (int)(t % 36); int64_t q = t / 36; int p = (int)(q % P); int64_t b = q / P;
+    int blk = f / 9, i = (f % 9) / 3, j = f % 3, bi = blk / 2, bj = blk % 2;
+    out[((size_t)b * 36 + f) * P + p] = raw[q * 36 + (3 * bi + i) + 6 * (3 * bj + j)];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble(StaticArgs A) {
+    extern __shared__ __align__(16) double asm_smem[];
+    const int b = blockIdx.x;
+    if (A.status && A.status[b] != A.want_status) return;
+    static_station<WANT_J>(A, b, threadIdx.x, asm_smem);
+}
+
+template <bool WANT_J, int MODE> __global__ void __launch_bounds__(256) k_assemble_dynamic(DynArgs A) {
+    extern __shared__ __align__(16) double asm_smem[];
+    const int b = blockIdx.x;
+    if (A.s.status && A.s.status[b] != A.s.want_status) return;
+    dynamic_station<WANT_J, MODE>(A, b, threadIdx.x, asm_smem);
+}
+
+template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble_initial(InitArgs A) {
+    extern __shared__ __align__(16) double asm_smem[];
+    const int b = blockIdx.x;
+    if (A.d.s.status && A.d.s.status[b] != A.d.s.want_status) return;
+    initial_station<WANT_J>(A, b, threadIdx.x, asm_smem);
+}
+
+// Dense Jacobian columns of the body-frame accelerations that are state variables (insert_steady_point_jacobians! point.jl:1829-1841,
+// insert_steady_element_jacobians! element.jl:2567-2583; the same terms for the initial-condition analysis, point.jl:1879-1895).
+// Column i (acceleration component i, stored at column c_i = ibody[i]) has entries in the force/moment rows of EVERY point:
+//   + (tf_x, tm_x)[:, i] / fs of the point's own mass and + 1/2 of each adjacent element's, with
+//   tf_ab = A m11 A', tf_alb = -A m11 A' tilde(dx + u) + A m12 A', tm likewise with m21, m22   (Vdot_ab = I, Vdot_alb = -tilde(dx + u), Ωdot_alb = I)
+// which does not fit the band.  The band matrix B keeps a unit entry at (c_i, c_i) instead (the force-free, displacement-free DOF
+// owns that row), and Dn[b][i][:] = column_i - e_{c_i}, so that J = B + sum_i Dn_i e_{c_i}' exactly; the solve undoes the split
+// with a Woodbury correction (k_woodbury).  One thread per station, both adjacent elements evaluated by the thread itself.
+struct BodyArgs { DynArgs d; const double* icS; const unsigned* rvm; int mode; double* Dn; };   // Dn: [6][nbatch][n]
+__global__ void __launch_bounds__(256) k_body_columns(BodyArgs B) {
+    const DynArgs& A = B.d; const StaticArgs& S = A.s;
+    const int b = blockIdx.x, p = threadIdx.x, N = S.N, NP = N + 1;
+    if (S.status && S.status[b] != S.want_status) return;
+    if (p > N) return;
+    const double rfs = 1.0 / S.fs[b];
+    const double* x = S.x + (size_t)b * S.n;
+    auto disp = [&](int q, v3& u, v3& th) {
+        const unsigned fl = S.flags[q];
+        const double* bc = S.bcS + ((size_t)b * 18) * NP + q;
+        const double* xp = x + 18 * q;
+        double t[6];
+        for (int k = 0; k < 6; k++) {
+            const bool pd = (fl >> k) & 1u;
+            if (B.mode == 2) {
+                const bool r = (B.rvm[(size_t)b * NP + q] >> k) & 1u;
+                t[k] = pd ? bc[(size_t)k * NP] : (r ? B.icS[((size_t)b * 18 + k) * NP + q] : xp[k]);
+            } else t[k] = pd ? bc[(size_t)k * NP] : xp[k];
+        }
+        u = mk(t[0], t[1], t[2]); th = mk(t[3], t[4], t[5]);
+    };
+    double G[6][6];                      // rows: F(3), M(3) of this point; columns: ab(3), alb(3)
+    for (int r = 0; r < 6; r++) for (int cc = 0; cc < 6; cc++) G[r][cc] = 0.0;
+    auto add = [&](const m3& Am, const m3& m11, const m3& m12, const m3& m21, const m3& m22, v3 rr, double w) {
+        const m3 At = transpose(Am), rt = tilde(rr);
+        const m3 A11 = (Am * m11) * At, A12 = (Am * m12) * At, A21 = (Am * m21) * At, A22 = (Am * m22) * At;
+        const m3 Fal = A12 - A11 * rt, Mal = A22 - A21 * rt;
+        for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) {
+            G[r][cc] += w * A11.a[3 * r + cc]; G[r][3 + cc] += w * Fal.a[3 * r + cc];
+            G[3 + r][cc] += w * A21.a[3 * r + cc]; G[3 + r][3 + cc] += w * Mal.a[3 * r + cc];
+        }
+    };
+    v3 up, thp; disp(p, up, thp);
+    if (S.pmS) {
+        const double* pm = S.pmS + ((size_t)b * 36) * NP + p;
+        const v3 dxp = ldv(A.pxS + ((size_t)b * 3) * NP + p, NP);
+        add(transpose(rot_C(thp)), ldm(pm, NP), ldm(pm + 9 * NP, NP), ldm(pm + 18 * NP, NP), ldm(pm + 27 * NP, NP), dxp + up, rfs);
+    }
+    for (int side = 0; side < 2; side++) {
+        const int e = p - 1 + side;
+        if (e < 0 || e >= N) continue;
+        v3 u1, t1, u2, t2; disp(e, u1, t1); disp(e + 1, u2, t2);
+        const double* es = S.elemS + ((size_t)b * S.elem_nf) * N + e;
+        const m3 Am = tmul(rot_C(0.5 * (t1 + t2)), ldm(es + N, N));
+        const v3 dxe = ldv(A.exS + ((size_t)b * 3) * N + e, N);
+        add(Am, ldm(es + 46 * N, N), ldm(es + 55 * N, N), ldm(es + 64 * N, N), ldm(es + 73 * N, N), dxe + 0.5 * (u1 + u2), 0.5 * rfs);
+    }
+    for (int i = 0; i < 6; i++) {
+        const int c = A.ibody[i];
+        if (c < 0) continue;
+        double* Di = B.Dn + ((size_t)i * gridDim.x + b) * S.n + 18 * p;
+        for (int k = 0; k < 6; k++) {
+            double v = G[k][i];
+            if (B.mode == 2 && ((B.rvm[(size_t)b * NP + p] >> (8 + k)) & 1u)) v = 0.0;    // equilibrium row replaced by Vdot_k = Vdot0_k (system.jl:756-813)
+            if (S.two_d && k >= 2 && k <= 4) v = 0.0;                                      // planar constraint rows (system.jl:1090-1100)
+            if (18 * p + k == c) v -= 1.0;
+            Di[k] = v;
+        }
+        if (c / 18 == p && S.Jrow) S.Jrow[((size_t)b * S.n + c) * GXB_DROWW + 18 + (c % 18)] = 1.0;    // the unit entry B keeps at (c_i, c_i)
+    }
+}
+
+// rate_vars of the initial-condition analysis (src/analyses.jl:1835-1873): column sums of the mass matrix at x = 0 over the V/Ω
+// columns of each point (rate_vars1), and the same with the element mass blocks replaced by the compliance blocks and the point
+// masses ignored (rate_vars2).  One thread per (instance, point).  rvm bit k: rate_vars2, bit 8+k: equilibrium row replaced
+// (!pd & !rate_vars1 & rate_vars2, system.jl:491-513), bit 16+k: rate_vars1.
+__global__ void k_initial_rate_vars(const double* __restrict__ elemS, int elem_nf, const double* __restrict__ bcS, const double* __restrict__ pmS,
+                                    const unsigned short* __restrict__ flags, int N, int two_d, unsigned* __restrict__ rvm, int64_t nbatch) {
+    const int NP = N + 1;
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * NP) return;
+    const int64_t b = t / NP; const int p = (int)(t % NP);
+    auto theta = [&](int q) {
+        const unsigned fl = flags[q];
+        const double* bc = bcS + ((size_t)b * 18) * NP + q;
+        return mk((fl & 8) ? bc[3 * NP] : 0.0, (fl & 16) ? bc[4 * NP] : 0.0, (fl & 32) ? bc[5 * NP] : 0.0);
+    };
+    double s1[6] = {0, 0, 0, 0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0};
+    auto addcols = [&](double* s, const m3& PV, const m3& PO, const m3& HV, const m3& HO, double w) {
+        for (int r = 0; r < 3; r++) {
+            const bool lin = !(two_d && r == 2), ang = !(two_d && r < 2);       // lmask = (1,1,0), amask = (0,0,1) (point.jl:2043-2049)
+            for (int cc = 0; cc < 3; cc++) {
+                if (lin) { s[cc] += w * PV.a[3 * r + cc]; s[3 + cc] += w * PO.a[3 * r + cc]; }
+                if (ang) { s[cc] += w * HV.a[3 * r + cc]; s[3 + cc] += w * HO.a[3 * r + cc]; }
+            }
+        }
+    };
+    if (pmS) {
+        const double* pm = pmS + ((size_t)b * 36) * NP + p;
+        const m3 C = rot_C(theta(p));
+        addcols(s1, tmul(C, ldm(pm, NP) * C), tmul(C, ldm(pm + 9 * NP, NP) * C), tmul(C, ldm(pm + 18 * NP, NP) * C), tmul(C, ldm(pm + 27 * NP, NP) * C), 1.0);
+    }
+    for (int side = 0; side < 2; side++) {
+        const int e = p - 1 + side;
+        if (e < 0 || e >= N) continue;
+        const double* es = elemS + ((size_t)b * elem_nf) * N + e;
+        const m3 Cab = ldm(es + N, N);
+        const m3 Am = tmul(rot_C(0.5 * (theta(e) + theta(e + 1))), Cab), At = transpose(Am);
+        // ¼ A m A' enters the rows of both end points of the element
+        addcols(s1, (Am * ldm(es + 46 * N, N)) * At, (Am * ldm(es + 55 * N, N)) * At, (Am * ldm(es + 64 * N, N)) * At, (Am * ldm(es + 73 * N, N)) * At, 0.5);
+        addcols(s2, (Am * ldm(es + 10 * N, N)) * At, (Am * ldm(es + 19 * N, N)) * At, (Am * ldm(es + 28 * N, N)) * At, (Am * ldm(es + 37 * N, N)) * At, 0.5);
+    }
+    const unsigned fl = flags[p];
+    unsigned m = 0;
+    for (int k = 0; k < 6; k++) {
+        const bool r1 = s1[k] != 0.0, r2 = s2[k] != 0.0, pd = (fl >> k) & 1u;
+        if (r2) m |= 1u << k;
+        if (!pd && !r1 && r2) m |= 1u << (8 + k);
+        if (r1) m |= 1u << (16 + k);
+    }
+    rvm[t] = m;
+}
+
+// initial_output (src/analyses.jl:2332-2390): the solved initial-condition vector -> DynamicSystem states (in place) and the point
+// rates udot, θdot, Vdot, Ωdot ([b][NP][12]) that seed the Newmark march.  One thread per (instance, point).
+__global__ void k_initial_output(double* __restrict__ x, const double* __restrict__ bcS, const double* __restrict__ icS, const unsigned* __restrict__ rvm,
+                                 const unsigned short* __restrict__ flags, const double* __restrict__ pxS, const double* __restrict__ motion,
+                                 double* __restrict__ rates, int NP, int n, int64_t nbatch, DynArgs body) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * NP) return;
+    const int64_t b = t / NP; const int p = (int)(t % NP);
+    const unsigned fl = flags[p], rv = rvm[t];
+    const double* bc = bcS + ((size_t)b * 18) * NP + p;
+    const double* ic = icS + ((size_t)b * 18) * NP + p;
+    double* xp = x + b * n + 18 * p;
+    const double* mo = motion + 12 * b;
+    const v3 vb = mk(mo[0], mo[1], mo[2]), wb = mk(mo[3], mo[4], mo[5]);
+    v3 ab, alb;
+    body_accelerations(body, x + b * n, mo, ab, alb);          // system.jl:167-182 (analyses.jl:2348)
+    double ut[6], rt[6];
+    for (int k = 0; k < 6; k++) {
+        const bool pd = (fl >> k) & 1u, r = (rv >> k) & 1u;
+        ut[k] = pd ? bc[(size_t)k * NP] : (r ? ic[(size_t)k * NP] : xp[k]);
+        rt[k] = pd ? 0.0 : (r ? xp[k] : ic[(size_t)(12 + k) * NP]);
+    }
+    const v3 u = mk(ut[0], ut[1], ut[2]);
+    const v3 udot = mk(xp[6], xp[7], xp[8]), thdot = mk(xp[9], xp[10], xp[11]);
+    const v3 dx = ldv(pxS + ((size_t)b * 3) * NP + p, NP);
+    const v3 V = ldv(ic + (size_t)6 * NP, NP) + vb + cross(wb, dx + u), Om = ldv(ic + (size_t)9 * NP, NP) + wb;
+    const v3 Vd = mk(rt[0], rt[1], rt[2]) + ab + cross(alb, dx + u) + cross(wb, udot), Od = mk(rt[3], rt[4], rt[5]) + alb;
+    double* ra = rates + ((size_t)b * NP + p) * 12;
+    for (int k = 0; k < 6; k++) if (!((fl >> k) & 1u)) xp[k] = ut[k];          // displacement where it is a state; loads stay
+    ra[0] = (fl & 1) ? 0.0 : udot.x; ra[1] = (fl & 2) ? 0.0 : udot.y; ra[2] = (fl & 4) ? 0.0 : udot.z;
+    ra[3] = (fl & 8) ? 0.0 : thdot.x; ra[4] = (fl & 16) ? 0.0 : thdot.y; ra[5] = (fl & 32) ? 0.0 : thdot.z;
+    ra[6] = Vd.x; ra[7] = Vd.y; ra[8] = Vd.z; ra[9] = Od.x; ra[10] = Od.y; ra[11] = Od.z;
+    xp[6] = V.x; xp[7] = V.y; xp[8] = V.z; xp[9] = Om.x; xp[10] = Om.y; xp[11] = Om.z;
+}
+
+// xhist[b][slot][:] = x[b][:]
+__global__ void k_save_state(const double* __restrict__ x, double* __restrict__ xhist, int n, int64_t nsave, int64_t slot, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * n) return;
+    int64_t b = t / n; int c = (int)(t % n);
+    xhist[((size_t)b * nsave + slot) * n + c] = x[t];
+}
+
+struct SolveArgs {
+    int nb, n; int64_t nbatch;
+    const double* J; const double* F; const double* x; double* U; double* p; double* xt;
+    NewtonState ns;
+    double maxstep; int linear;
+    int direction_only;   // parity entry point: just p, no state change
+    double sign;          // sol = sign * (J \ F): -1 for the Newton direction, +1 for the eigen operator
+    // Woodbury-corrected steps (body-acceleration states): F / p above are the right-hand side / solution of ONE band solve,
+    // these are the Newton residual and direction the line search works with
+    const double* Fnewton; double* pnewton;
+};
+__device__ void linesearch_start(const SolveArgs& A, int64_t b);
+
+// one warp: factorise + solve instance b, then start the line search (|p|_inf, φ0, dφ0, first trial point)
+template <int KLB, int KUB> __device__ void factor_instance(const SolveArgs& A, int64_t b, double* sm) {
+    using S = LuShape<KLB, KUB>;
+    const int lane = threadIdx.x & 31;
+    const size_t n = A.n;
+    const double* F = A.F + b * n;
+    double* p = A.p + b * n;
+    int bad = warp_band_solve<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * n * S::UW, p, A.nb, A.sign, sm);
+    __syncwarp();
+    if (A.direction_only == 1) return;
+    if (bad) { if (lane == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
+    if (A.direction_only) return;        // 2: one of several solves of a Woodbury-corrected step (k_woodbury finishes it)
+    linesearch_start(A, b);
+}
+// |p|_inf, φ0 = ½ F'F, dφ0 = g'p with g = J'F and J p = -F  =>  dφ0 = -F'F; first trial point.  One warp; p is complete.
+__device__ void linesearch_start(const SolveArgs& A, int64_t b) {
+    const int lane = threadIdx.x & 31;
+    const size_t n = A.n;
+    const double* F = A.Fnewton ? A.Fnewton + b * n : A.F + b * n;
+    double* p = A.pnewton ? A.pnewton + b * n : A.p + b * n;
+    {
+    double pm = 0.0, ff = 0.0;
+    for (int c = lane; c < (int)n; c += 32) { pm = fmax(pm, fabs(p[c])); double f = F[c]; ff = fma(f, f, ff); }
+    for (int o = 16; o; o >>= 1) { pm = fmax(pm, __shfl_xor_sync(GXB_FULL, pm, o)); ff += __shfl_xor_sync(GXB_FULL, ff, o); }
+    const double a0 = A.linear ? 1.0 : fmin(1.0, A.maxstep / pm);
+    const double* x = A.x + b * n; double* xt = A.xt + b * n;
+    for (int c = lane; c < (int)n; c += 32) xt[c] = x[c] + a0 * p[c];
+    if (lane == 0) {
+        A.ns.a1[b] = a0; A.ns.a2[b] = a0; A.ns.phi0[b] = 0.5 * ff; A.ns.dphi0[b] = -ff; A.ns.phx0[b] = 0.5 * ff;
+        A.ns.ls_k[b] = 0; A.ns.ls_finite[b] = 0; A.ns.status[b] = ST_TRIAL;
+    }
+    }
+}
+template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? GXB_LU_MINBLOCKS : 2)) k_factor_solve(SolveArgs A) {
+    using S = LuShape<KLB, KUB>;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= A.nbatch) return;
+    if (A.direction_only != 1 && A.ns.status[b] != ST_SOLVE) return;
+    factor_instance<KLB, KUB>(A, b, smem + (size_t)warp * S::SM_DOUBLES);
+}
+
+// Woodbury correction of a Newton step whose Jacobian is J = B + sum_i D_i e_{c_i}' (body-acceleration columns, see k_body_columns):
+// with y = B^-1 F (in p) and z_i = B^-1 D_i,   J^-1 F = y - Z (I + E'Z)^-1 E'y.   One warp per instance; the k x k system (k <= 6) is
+// solved by lane 0 with partial pivoting.  Then the line search starts exactly as after an ordinary factorisation.
+struct WoodArgs { SolveArgs S; const double* Z; int ibody[6]; };
+__global__ void __launch_bounds__(128) k_woodbury(WoodArgs W) {
+    const SolveArgs& A = W.S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= A.nbatch) return;
+    if (A.ns.status[b] != ST_SOLVE) return;
+    const size_t n = A.n;
+    double* p = A.p + b * n;
+    int idx[6], k = 0;
+    for (int i = 0; i < 6; i++) if (W.ibody[i] >= 0) idx[k++] = i;
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    int bad = 0;
+    if (lane == 0) {
+        double M[6][7];
+        for (int j = 0; j < k; j++) {
+            const int cj = W.ibody[idx[j]];
+            for (int i = 0; i < k; i++) M[j][i] = (i == j ? 1.0 : 0.0) + W.Z[((size_t)idx[i] * A.nbatch + b) * n + cj];
+            M[j][k] = p[cj];
+        }
+        for (int col = 0; col < k && !bad; col++) {
+            int piv = col; double best = fabs(M[col][col]);
+            for (int r = col + 1; r < k; r++) if (fabs(M[r][col]) > best) { best = fabs(M[r][col]); piv = r; }
+            if (!(best > 0.0) || !isfinite(best)) { bad = 1; break; }
+            if (piv != col) for (int q = col; q <= k; q++) { double t = M[col][q]; M[col][q] = M[piv][q]; M[piv][q] = t; }
+            for (int r = col + 1; r < k; r++) { const double f = M[r][col] / M[col][col]; for (int q = col; q <= k; q++) M[r][q] -= f * M[col][q]; }
+        }
+        if (!bad) for (int r = k - 1; r >= 0; r--) { double v = M[r][k]; for (int q = r + 1; q < k; q++) v -= M[r][q] * a[q]; a[r] = v / M[r][r]; }
+    }
+    bad = __shfl_sync(GXB_FULL, bad, 0);
+    if (bad) { if (lane == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
+    for (int j = 0; j < 6; j++) a[j] = __shfl_sync(GXB_FULL, a[j], 0);
+    for (int c = lane; c < (int)n; c += 32) {
+        double v = p[c];
+        for (int j = 0; j < k; j++) v = fma(-W.Z[((size_t)idx[j] * A.nbatch + b) * n + c], a[j], v);
+        p[c] = -v;                       // Newton direction p = -J^-1 F
+    }
+    __syncwarp();
+    linesearch_start(A, b);
+}
+
+struct UpdateArgs {
+    int n; int mode;   // mode 0: initial evaluation, 1: line-search step, 2: linear (accept unconditionally, converged)
+    double* x; double* xt; double* F; const double* Ft; const double* p;
+    NewtonState ns;
+    double ftol, c1, rho_hi, rho_lo; int64_t iterations; int ls_iterations;
+    int* counter;
+};
+
+// Armijo test / accept / convergence for instance b by the whole CTA (any block size up to 256); returns the new status
+__device__ int update_instance(const UpdateArgs& A, int b) {
+    const size_t n = A.n;
+    const double* Ft = A.Ft + b * n;
+    // all per-instance scalars are read before the reduction barrier; thread 0 rewrites them only after it
+    const double a1 = A.ns.a1[b], a2 = A.ns.a2[b], phi0 = A.ns.phi0[b], dphi0 = A.ns.dphi0[b], phx0 = A.ns.phx0[b];
+    int k = A.ns.ls_k[b], nf = A.ns.ls_finite[b];
+    int iters = A.ns.iters[b];
+    __shared__ double s_sum[8], s_max[8]; __shared__ int s_nan[8];
+    double ss = 0.0, mx = 0.0; int nan = 0;
+    for (int c = threadIdx.x; c < (int)n; c += blockDim.x) { double f = Ft[c]; ss = fma(f, f, ss); mx = fmax(mx, fabs(f)); nan |= (f != f); }
+    for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(GXB_FULL, ss, o); mx = fmax(mx, __shfl_xor_sync(GXB_FULL, mx, o)); nan |= __shfl_xor_sync(GXB_FULL, nan, o); }
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = ss; s_max[threadIdx.x >> 5] = mx; s_nan[threadIdx.x >> 5] = nan; }
+    if (threadIdx.x < 8 && threadIdx.x >= (blockDim.x >> 5)) { s_sum[threadIdx.x] = 0.0; s_max[threadIdx.x] = 0.0; s_nan[threadIdx.x] = 0; }
+    __syncthreads();
+    ss = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
+    mx = fmax(fmax(s_max[0], s_max[1]), fmax(s_max[2], s_max[3]));
+    nan = s_nan[0] | s_nan[1] | s_nan[2] | s_nan[3];
+    if (blockDim.x > 128) {      // persistent kernels run with up to 8 warps; the 4-warp order above is kept for bit-compatibility
+        ss += (s_sum[4] + s_sum[5]) + (s_sum[6] + s_sum[7]);
+        mx = fmax(mx, fmax(fmax(s_max[4], s_max[5]), fmax(s_max[6], s_max[7])));
+        nan |= s_nan[4] | s_nan[5] | s_nan[6] | s_nan[7];
+    }
+    const double phx1 = 0.5 * ss;
+    const bool finite = isfinite(ss) && !nan;
+    double* x = A.x + b * n; double* xt = A.xt + b * n; double* F = A.F + b * n; const double* p = A.p + b * n;
+    // every thread takes the same decision from the same scalars
+    bool accept = false; int newstatus = ST_TRIAL; int failcode = FAIL_NONE; double a_new = 0.0;
+    if (A.mode == 0) {
+        accept = true;
+        if (!finite) { newstatus = ST_FAILED; failcode = FAIL_NONFINITE; }     // NLsolve check_isfinite
+        else newstatus = (mx <= A.ftol) ? ST_DONE : ST_SOLVE;
+        if (newstatus == ST_SOLVE && A.iterations <= 0) { newstatus = ST_FAILED; failcode = FAIL_MAXITER; }
+    } else if (A.mode == 2) {
+        accept = true; newstatus = ST_DONE; iters = 1;
+    } else {
+        double n_a1 = a1, n_a2 = a2, n_phx0 = phx0;
+        if (k == 0 && !isfinite(phx1) && nf < 52) {                 // back off until finite (LineSearches iterfinite loop)
+            nf++; n_a1 = a2; n_a2 = a2 / 2;
+        } else if (phx1 > phi0 + A.c1 * a2 * dphi0) {               // Armijo fails -> interpolate
+            k++;
+            if (k > A.ls_iterations) { newstatus = ST_FAILED; failcode = FAIL_LINESEARCH; }
+            double at;
+            if (k == 1) at = -(dphi0 * a2 * a2) / (2 * (phx1 - phi0 - dphi0 * a2));
+            else {
+                double dv = 1.0 / (a1 * a1 * a2 * a2 * (a2 - a1));
+                double ca = (a1 * a1 * (phx1 - phi0 - dphi0 * a2) - a2 * a2 * (phx0 - phi0 - dphi0 * a1)) * dv;
+                double cb = (-a1 * a1 * a1 * (phx1 - phi0 - dphi0 * a2) + a2 * a2 * a2 * (phx0 - phi0 - dphi0 * a1)) * dv;
+                if (fabs(ca) <= 2.220446049250313e-16) at = dphi0 / (2 * cb);
+                else { double d = fmax(cb * cb - 3 * ca * dphi0, 0.0); at = (-cb + sqrt(d)) / (3 * ca); }
+            }
+            n_a1 = a2;
+            double hi = a2 * A.rho_hi, lo = a2 * A.rho_lo;
+            at = (at != at) ? hi : fmin(at, hi);
+            n_a2 = fmax(at, lo);
+            n_phx0 = phx1;
+        } else {
+            accept = true;
+        }
+        if (!accept && newstatus == ST_TRIAL) {
+            a_new = n_a2;
+            if (threadIdx.x == 0) { A.ns.a1[b] = n_a1; A.ns.a2[b] = n_a2; A.ns.phx0[b] = n_phx0; A.ns.ls_k[b] = k; A.ns.ls_finite[b] = nf; }
+        }
+        if (accept) {
+            iters++;
+            const bool fconv = mx <= A.ftol;                         // maximum(abs, F) <= ftol ; NaN compares false
+            bool stopped = nan != 0;
+            bool xzero = true;                                       // x-convergence: ||x - xold||_inf <= xtol = 0
+            for (int c = threadIdx.x; c < (int)n; c += blockDim.x) { if (xt[c] != x[c]) xzero = false; if (xt[c] != xt[c]) stopped = true; }
+            xzero = __syncthreads_and(xzero); stopped = __syncthreads_or(stopped);
+            if (fconv) newstatus = ST_DONE;
+            else if (stopped) { newstatus = ST_FAILED; failcode = FAIL_NONFINITE; }
+            else if (xzero) { newstatus = ST_FAILED; failcode = FAIL_LINESEARCH; }
+            else if (iters >= A.iterations) { newstatus = ST_FAILED; failcode = FAIL_MAXITER; }
+            else newstatus = ST_SOLVE;
+        }
+    }
+    if (accept) {
+        for (int c = threadIdx.x; c < (int)n; c += blockDim.x) { x[c] = xt[c]; F[c] = Ft[c]; }
+        if (threadIdx.x == 0) { A.ns.finf[b] = mx; A.ns.iters[b] = iters; }
+    } else if (newstatus == ST_TRIAL) {
+        for (int c = threadIdx.x; c < (int)n; c += blockDim.x) xt[c] = x[c] + a_new * p[c];
+    }
+    if (threadIdx.x == 0) {
+        A.ns.fcalls[b] += 1;
+        A.ns.status[b] = newstatus;
+        if (failcode) A.ns.failcode[b] = failcode;
+        if (A.counter && (newstatus == ST_SOLVE || newstatus == ST_TRIAL)) atomicAdd(A.counter, 1);
+    }
+    return newstatus;
+}
+__global__ void __launch_bounds__(128) k_update(UpdateArgs A) {
+    const int b = blockIdx.x;
+    if (A.ns.status[b] != ST_TRIAL) return;
+    update_instance(A, b);
+}
+
+__global__ void k_fill_int(int* p, int v, int64_t n) { int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (t < n) p[t] = v; }
+
+// Jblk[b][k][3i+j] = J[brow[k]+i, bcol[k]+j] read back from the row-block storage
+__global__ void k_extract_blocks(const double* __restrict__ Jrow, const int64_t* __restrict__ brow, const int64_t* __restrict__ bcol,
+                                 double* __restrict__ out, int64_t nblk, int n, int W, int KLB, int64_t nbatch) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * nblk * 9) return;
+    int e = (int)(t % 9); int64_t q = t / 9; int64_t k = q % nblk; int64_t b = q / nblk;
+    int64_t r = brow[k] + e / 3, c = bcol[k] + e % 3;
+    int64_t slot = c - 6 * (r / 6 - KLB);
+    out[t] = (slot >= 0 && slot < W) ? Jrow[((size_t)b * n + r) * W + slot] : 0.0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Mass matrix M = ∂r/∂ẋ in the same row-block storage as the Jacobian (system_mass_matrix!, src/system.jl:961-995;
+// point.jl:1356-1384, 2033-2061; element.jl:1408-1441, 2370-2411, 2903-2953).  One thread per station; a thread evaluates the
+// frames of element i-1 and element i itself (only C(θ) is needed), so no exchange between threads is required.
+struct MassArgs { StaticArgs s; double* Mrow; };
+__global__ void k_mass_matrix(MassArgs A) {
+    const StaticArgs& S = A.s;
+    const int b = blockIdx.x, i = threadIdx.x, N = S.N, NP = N + 1;
+    if (i > N) return;
+    const double rfs = 1.0 / S.fs[b];
+    const double* x = S.x + (size_t)b * S.n;
+    double* Mr = A.Mrow + ((size_t)b * S.n + 18 * i) * GXB_DROWW;
+    auto theta = [&](int p) {
+        const unsigned fl = S.flags[p];
+        const double* bc = S.bcS + ((size_t)b * 18) * NP + p;
+        const double* xp = x + 18 * p;
+        return mk((fl & 8) ? bc[3 * NP] : xp[3], (fl & 16) ? bc[4 * NP] : xp[4], (fl & 32) ? bc[5 * NP] : xp[5]);
+    };
+    const v3 thi = theta(i);
+    m3 FV[3], FO[3], MV[3], MO[3];       // column points i-1, i, i+1
+    for (int k = 0; k < 3; k++) { FV[k] = zero33(); FO[k] = zero33(); MV[k] = zero33(); MO[k] = zero33(); }
+    if (S.pmS) {
+        const double* pm = S.pmS + ((size_t)b * 36) * NP + i;
+        const m3 C = rot_C(thi);
+        FV[1] = rfs * tmul(C, ldm(pm, NP) * C); FO[1] = rfs * tmul(C, ldm(pm + 9 * NP, NP) * C);
+        MV[1] = rfs * tmul(C, ldm(pm + 18 * NP, NP) * C); MO[1] = rfs * tmul(C, ldm(pm + 27 * NP, NP) * C);
+    }
+    for (int side = 0; side < 2; side++) {       // element i-1 (this point is its stop), then element i (this point is its start)
+        const int e = i - 1 + side;
+        if (e < 0 || e >= N) continue;
+        const double* es = S.elemS + ((size_t)b * S.elem_nf) * N + e;
+        const m3 Cab = ldm(es + N, N);
+        const v3 th = 0.5 * (theta(e) + theta(e + 1));
+        const m3 Am = tmul(rot_C(th), Cab), At = transpose(Am);
+        const double q = 0.25 * rfs;
+        const m3 a11 = q * ((Am * ldm(es + 46 * N, N)) * At), a12 = q * ((Am * ldm(es + 55 * N, N)) * At);
+        const m3 a21 = q * ((Am * ldm(es + 64 * N, N)) * At), a22 = q * ((Am * ldm(es + 73 * N, N)) * At);
+        const int k0 = side;                     // column points (e, e+1) = (i-1, i) or (i, i+1)
+        FV[k0] = FV[k0] + a11; FV[k0 + 1] = FV[k0 + 1] + a11; FO[k0] = FO[k0] + a12; FO[k0 + 1] = FO[k0 + 1] + a12;
+        MV[k0] = MV[k0] + a21; MV[k0 + 1] = MV[k0 + 1] + a21; MO[k0] = MO[k0] + a22; MO[k0 + 1] = MO[k0 + 1] + a22;
+    }
+    const bool two_d = S.two_d != 0;
+    auto put = [&](int r0, int slot, const m3& B, bool angular) {
+        for (int r = 0; r < 3; r++) {
+            const bool zero = two_d && (angular ? r < 2 : r == 2);       // lmask = (1,1,0), amask = (0,0,1)
+            for (int cc = 0; cc < 3; cc++) Mr[(size_t)(r0 + r) * GXB_DROWW + slot + cc] = zero ? 0.0 : B.a[3 * r + cc];
+        }
+    };
+    for (int k = 0; k < 3; k++) {
+        const int p = i - 1 + k;
+        if (p < 0 || p > N) continue;
+        const int sV = 6 + 18 * k, sO = 9 + 18 * k;     // slots of (V, Ω) of points i-1, i, i+1 in an equilibrium row
+        put(0, sV, FV[k], false); put(0, sO, FO[k], false);
+        put(3, sV, MV[k], true); put(3, sO, MO[k], true);
+    }
+    const unsigned fl = S.flags[i];
+    m3 uu = zero33(), tt = zero33();
+    uu.a[0] = (fl & 1) ? 0.0 : -1.0; uu.a[4] = (fl & 2) ? 0.0 : -1.0; uu.a[8] = (fl & 4) ? 0.0 : -1.0;
+    tt.a[0] = (fl & 8) ? 0.0 : -1.0; tt.a[4] = (fl & 16) ? 0.0 : -1.0; tt.a[8] = (fl & 32) ? 0.0 : -1.0;
+    put(6, 12, uu, false);       // rV rows: -u_u
+    put(9, 15, tt, true);        // rΩ rows: -θ_θ
+}
+
+// y = M v in row-block storage: one thread per row
+__global__ void k_rowblock_spmv(const double* __restrict__ Mrow, const double* __restrict__ v, double* __restrict__ y, int n, int W, int KLB,
+                                int64_t nbatch, int64_t vstride) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * n) return;
+    const int64_t b = t / n; const int r = (int)(t % n);
+    const double* row = Mrow + (size_t)t * W;
+    const double* vb = v + b * vstride;
+    const int c0 = 6 * (r / 6 - KLB);
+    double acc = 0.0;
+    for (int j = 0; j < W; j++) { const int c = c0 + j; if (c >= 0 && c < n) acc = fma(row[j], vb[c], acc); }
+    y[t] = acc;
+}
+
+// out[b][c][j] = sum_k Vk[b][k][c] * Y[b][k][j]  (Y complex): thread per state c, four eigenvectors per pass
+__global__ void __launch_bounds__(128) k_ritz_vectors(const double* __restrict__ Vk, const double* __restrict__ Y, double* __restrict__ out, int n, int m, int nev) {
+    const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* V = Vk + (size_t)b * (m + 1) * n;
+    const double* Yb = Y + (size_t)b * m * nev * 2;
+    for (int j0 = 0; j0 < nev; j0 += 4) {
+        double re[4] = {0, 0, 0, 0}, im[4] = {0, 0, 0, 0};
+        if (c < n)
+            for (int k = 0; k < m; k++) {
+                const double v = V[(size_t)k * n + c];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (j0 + q < nev) { re[q] = fma(v, Yb[((size_t)k * nev + j0 + q) * 2], re[q]); im[q] = fma(v, Yb[((size_t)k * nev + j0 + q) * 2 + 1], im[q]); }
+            }
+        if (c < n)
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (j0 + q < nev) { double* o = out + (((size_t)b * n + c) * nev + j0 + q) * 2; o[0] = re[q]; o[1] = im[q]; }
+    }
+}
+
+// Arnoldi bookkeeping, one CTA per instance.  Vk: [b][m+1][n] Krylov basis, H: [b][m+1][m] (row-major), w: [b][n] = A v_j.
+__global__ void __launch_bounds__(256) k_arnoldi_start(double* __restrict__ Vk, int n, int m) {
+    const int b = blockIdx.x;
+    double* v0 = Vk + (size_t)b * (m + 1) * n;
+    __shared__ double red[8];
+    double ss = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        // deterministic pseudo-random start vector (the reference's ArnoldiMethod draws a random one)
+        unsigned h = (unsigned)c * 2654435761u + 12345u; h ^= h >> 13; h *= 2246822519u; h ^= h >> 16;
+        const double val = 0.5 + (double)(h & 0xffffff) / 16777216.0;
+        v0[c] = val; ss = fma(val, val, ss);
+    }
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(GXB_FULL, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    double tot = 0.0; for (int k = 0; k < (int)(blockDim.x >> 5); k++) tot += red[k];
+    const double inv = 1.0 / sqrt(tot);
+    for (int c = threadIdx.x; c < n; c += blockDim.x) v0[c] *= inv;
+}
+__global__ void __launch_bounds__(256) k_arnoldi_orth(double* __restrict__ Vk, double* __restrict__ H, const double* __restrict__ w_in, int n, int m, int j) {
+    const int b = blockIdx.x;
+    double* V = Vk + (size_t)b * (m + 1) * n;
+    double* Hb = H + (size_t)b * (m + 1) * m;
+    double* vn = V + (size_t)(j + 1) * n;            // work in place in the slot of v_{j+1}
+    const double* w = w_in + (size_t)b * n;
+    __shared__ double red[8]; __shared__ double bc;
+    const int nw = blockDim.x >> 5;
+    auto block_sum = [&](double x) {
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(GXB_FULL, x, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x == 0) { double t = 0.0; for (int k = 0; k < nw; k++) t += red[k]; bc = t; }
+        __syncthreads();
+        return bc;
+    };
+    for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] = w[c];
+    // modified Gram-Schmidt, two sweeps (the second one only corrects round-off; its coefficients are added to H)
+    for (int sweep = 0; sweep < 2; sweep++)
+        for (int i = 0; i <= j; i++) {
+            const double* vi = V + (size_t)i * n;
+            double d = 0.0;
+            for (int c = threadIdx.x; c < n; c += blockDim.x) d = fma(vi[c], vn[c], d);
+            const double h = block_sum(d);
+            for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] = fma(-h, vi[c], vn[c]);
+            if (threadIdx.x == 0) Hb[(size_t)i * m + j] = (sweep == 0 ? 0.0 : Hb[(size_t)i * m + j]) + h;
+        }
+    double d = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) d = fma(vn[c], vn[c], d);
+    const double nrm = sqrt(block_sum(d));
+    if (threadIdx.x == 0) Hb[(size_t)(j + 1) * m + j] = nrm;
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] *= inv;
+}
+
