@@ -104,3 +104,23 @@ def test_straggler_handoff_matches_plain_rounds():
     assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["converged"], b["converged"])
     assert np.abs(a["x"] - b["x"]).max() <= 1e-11 * np.abs(b["x"]).max()
     assert out["auto_stats"]["launches"] < out["rounds_stats"]["launches"]
+
+
+def test_handoff_in_the_initial_condition_solve():
+    """One member of nine crawls under the line search's maxstep clamp (cf. test_gpu_initial.py) while the others converge in one
+    iteration: the default policy hands the crawler to the persistent kernel (MODE 2, resume).  Same iterates as the plain rounds."""
+    nb, cap = 9, 12
+    w = workloads.rotating_blade_batch(nb)
+    V0 = np.zeros((nb, 25, 3)); V0[4, :, 2] = np.linspace(0, 1, 25) ** 2
+    out = {}
+    for name, flag in (("auto", 0), ("rounds", 2)):
+        ctx = _ctx(w, w["motion"], nb, w["points_b"])
+        out[name] = ctx.initial_condition(opts=api.make_opts(structural_damping=True, iterations=cap, persistent=flag), V0=V0)
+        out[name + "_launches"] = ctx.stats()["launches"]
+        ctx.close()
+    a, b = out["auto"], out["rounds"]
+    ok = np.ones(nb, bool); ok[4] = False
+    assert np.array_equal(a["converged"], ok) and np.array_equal(b["converged"], ok)
+    assert np.array_equal(a["iters"], b["iters"]) and a["iters"][4] == cap
+    assert np.abs(a["rates"] - b["rates"]).max() <= 1e-9 * np.abs(b["rates"]).max()
+    assert out["auto_launches"] < out["rounds_launches"]
