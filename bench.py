@@ -6,8 +6,11 @@
              under a tip moment, randomised stiffness/loads, zero initial guess, ftol = 1e-9)
     value  : inputs already resident in HBM (gxb_static_solve_resident), timed with CUDA events on the library's stream
     e2e    : the same step through the reference-facing C-ABI with HOST buffers (gxb_set_elements + gxb_set_bc + gxb_set_body
-             + gxb_static_solve): host->device copies of that step's inputs and device->host copy of x/converged/iters inside
-             the timed region (wall clock around the synchronous calls)
+             + gxb_static_solve): host->device copies of that step's inputs (pinned, the reference's Element layout) and
+             device->host copy of x/converged/iters inside the timed region (wall clock).  Issued through
+             gxbeam_b200.api.PipelinedSolver: 4 chunks on 4 contexts of the GPU from host threads, uploads serialised, so that one
+             chunk's transfer runs under another chunk's solve; gxb_hint_no_gravity trims the element upload to the 49 doubles
+             per element the static path reads.  The plain single-call figure is reported beside it.
     N > 1  : one process per GPU (torchrun), instances sharded by rank, no collective on the data path; NCCL is used only
              for the barrier and the max-over-ranks of the timings ("weak": 4096 instances per GPU)
 
