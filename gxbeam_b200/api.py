@@ -346,7 +346,7 @@ class Context:
         fd = np.ascontiguousarray(field, dtype=np.int32)
         self._ck(self.lib.gxb_set_bc_series(self.h, C.c_int64(nt), C.c_int32(K), _ptr(pt), _ptr(fd), _ptr(v)))
 
-    def newmark_run(self, tvec, x0=None, rates0=None, opts=None, save_every=1, want_history=True):
+    def newmark_run(self, tvec, x0=None, rates0=None, opts=None, save_every=1, want_history=True, want_rates=False):
         """time_domain_analysis! from the initial state (x0 [nb,n], rates0 [nb,np,12] = udot, θdot, Vdot, Ωdot)."""
         o = opts or make_opts()
         tvec = _f64(tvec)
@@ -357,9 +357,10 @@ class Context:
         steps = np.empty(nb, np.int32); itot = np.empty(nb, np.int32); conv = np.empty(nb, np.int32)
         x0a = None if x0 is None else _f64(x0).reshape(nb, n)              # None: march from the state gxb_initial_condition left in HBM
         r0a = None if rates0 is None else _f64(rates0).reshape(nb, self.np, 12)
+        rh = np.empty((nb, nsave, self.np, 12)) if want_rates else None      # udot, θdot, Vdot, Ωdot of every saved level (newmark_output)
         self._ck(self.lib.gxb_newmark_run(self.h, C.byref(o), C.c_int64(nt), _ptr(tvec), _ptr(x0a), _ptr(r0a), C.c_int64(save_every), _ptr(xh),
-                                          _ptr(steps), _ptr(itot), _ptr(conv)))
-        return dict(x=xh, steps_done=steps, iters_total=itot, converged=conv.astype(bool))
+                                          _ptr(steps), _ptr(itot), _ptr(conv), _ptr(rh)))
+        return dict(x=xh, rates=rh, steps_done=steps, iters_total=itot, converged=conv.astype(bool))
 
     def static_newton_direction(self, x, opts=None):
         o = opts or make_opts()

@@ -686,7 +686,7 @@ static int64_t straggler_threshold(const gxb_ctx* c, const gxb_opts& o) {
     if (c->kind != 1 || o.linear || o.profile || o.persistent == 2 || c->nbody > 0) return -1;
     return std::min<int64_t>(c->sm_count, std::max<int64_t>(1, c->nbatch / 8));
 }
-struct MarchBuffers { int64_t nt = 0; const double* d_tvec = nullptr; int* alive = nullptr; int* steps = nullptr; int* itot = nullptr; double* hist = nullptr; int64_t nsave = 0, save_every = 1; };
+struct MarchBuffers { int64_t nt = 0; const double* d_tvec = nullptr; int* alive = nullptr; int* steps = nullptr; int* itot = nullptr; double* hist = nullptr; double* rates_hist = nullptr; int64_t nsave = 0, save_every = 1; };
 static int launch_persistent(gxb_ctx* c, const gxb_opts& o, int mode, const MarchBuffers* mb, int resume) {
     PersistArgs P{};
     P.resume = resume;
@@ -709,7 +709,7 @@ static int launch_persistent(gxb_ctx* c, const gxb_opts& o, int mode, const Marc
     if (mb) {
         P.nt = mb->nt; P.tvec = mb->d_tvec; P.bcS = c->d_bcS; P.series = c->d_series; P.ser_point = c->d_ser_point; P.ser_field = c->d_ser_field;
         P.K = c->ser_K; P.ser_nt = c->ser_nt; P.paug = c->d_paug; P.rates0 = c->d_rates0;
-        P.alive = mb->alive; P.steps = mb->steps; P.itot = mb->itot; P.hist = mb->hist; P.nsave = mb->nsave; P.save_every = mb->save_every;
+        P.alive = mb->alive; P.steps = mb->steps; P.itot = mb->itot; P.hist = mb->hist; P.rates_hist = mb->rates_hist; P.nsave = mb->nsave; P.save_every = mb->save_every;
     }
     static thread_local size_t configured = 0;
     if (sm > configured) {
@@ -747,7 +747,7 @@ int gxb_set_bc_series(gxb_ctx* c, int64_t nt, int32_t K, const int32_t* point, c
 }
 
 int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* tvec, const double* x0, const double* rates0,
-                    int64_t save_every, double* x_hist, int32_t* steps_done, int32_t* iters_total, int32_t* converged) {
+                    int64_t save_every, double* x_hist, int32_t* steps_done, int32_t* iters_total, int32_t* converged, double* rates_hist) {
     NEED_BATCH("gxb_newmark_run");
     if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_newmark_run: context topology is not kind=1 (DynamicSystem)");
     if (nt < 2 || !tvec) return fail(GXB_ERR_INVALID, "gxb_newmark_run: need nt >= 2 and tvec");
@@ -767,6 +767,8 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     int *d_alive = nullptr, *d_steps = nullptr, *d_itot = nullptr; double* d_hist = nullptr;
     CK(cudaMalloc(&d_alive, nb * 4)); CK(cudaMalloc(&d_steps, nb * 4)); CK(cudaMalloc(&d_itot, nb * 4));
     if (x_hist) CK(cudaMalloc(&d_hist, nb * nsave * n * 8));
+    double* d_rhist = nullptr;
+    if (rates_hist) CK(cudaMalloc(&d_rhist, nb * nsave * P * 12 * 8));
     k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(d_alive, 1, nb);
     k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(d_steps, 1, nb);
     CK(cudaMemsetAsync(d_itot, 0, nb * 4, c->stream));
@@ -783,6 +785,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     CK(cudaMemsetAsync(c->d_paug, 0, nb * 12 * P * 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     if (d_hist) k_save_state<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_x, d_hist, (int)n, nsave, 0, c->nbatch);
+    if (d_rhist) k_save_rates<<<grid1(nb * P, 128), 128, 0, c->stream>>>(c->d_x, c->d_bcS, c->d_flags, c->d_paug, c->d_rates0, 0.0, (int)P, (int)n, nsave, 0, c->nbatch, d_rhist);
     c->mode = 1;
     for (int64_t it = 1; it < nt; it++)
         if (!(tvec[it] - tvec[it - 1] > 0.0)) { c->mode = 0; return fail(GXB_ERR_INVALID, "gxb_newmark_run: tvec must be strictly increasing"); }
@@ -791,7 +794,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     if (persistent) {
         CK(cudaMalloc(&d_tvec, nt * 8));
         CK(cudaMemcpyAsync(d_tvec, tvec, nt * 8, cudaMemcpyHostToDevice, c->stream));
-        MarchBuffers mb; mb.nt = nt; mb.d_tvec = d_tvec; mb.alive = d_alive; mb.steps = d_steps; mb.itot = d_itot; mb.hist = d_hist; mb.nsave = nsave; mb.save_every = save_every;
+        MarchBuffers mb; mb.nt = nt; mb.d_tvec = d_tvec; mb.alive = d_alive; mb.steps = d_steps; mb.itot = d_itot; mb.hist = d_hist; mb.rates_hist = d_rhist; mb.nsave = nsave; mb.save_every = save_every;
         if ((rc = launch_persistent(c, o, 1, &mb))) { c->mode = 0; cudaFree(d_tvec); return rc; }
     }
     for (int64_t it = 1; it < nt && !persistent; it++) {
@@ -807,6 +810,10 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
         k_step_end<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, c->ns.iters, d_alive, d_steps, d_itot, c->nbatch);
         c->stats.launches += 1;
         if (d_hist && it % save_every == 0) { k_save_state<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_x, d_hist, (int)n, nsave, it / save_every, c->nbatch); c->stats.launches += 1; }
+        if (d_rhist && it % save_every == 0) {
+            k_save_rates<<<grid1(nb * P, 128), 128, 0, c->stream>>>(c->d_x, c->d_bcS, c->d_flags, c->d_paug, c->d_rates0, c->c2dt, (int)P, (int)n, nsave, it / save_every, c->nbatch, d_rhist);
+            c->stats.launches += 1;
+        }
     }
     c->mode = 0;
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -820,7 +827,8 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     if (iters_total) memcpy(iters_total, itot.data(), nb * 4);
     if (steps_done) CK(cudaMemcpy(steps_done, d_steps, nb * 4, cudaMemcpyDeviceToHost));
     if (x_hist) CK(cudaMemcpy(x_hist, d_hist, nb * nsave * n * 8, cudaMemcpyDeviceToHost));
-    cudaFree(d_alive); cudaFree(d_steps); cudaFree(d_itot); cudaFree(d_hist); cudaFree(d_tvec); cudaFree(d_xlin);
+    if (rates_hist) CK(cudaMemcpy(rates_hist, d_rhist, nb * nsave * P * 12 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_alive); cudaFree(d_steps); cudaFree(d_itot); cudaFree(d_hist); cudaFree(d_rhist); cudaFree(d_tvec); cudaFree(d_xlin);
     CK(cudaGetLastError());
     return GXB_OK;
 }

@@ -28,6 +28,31 @@ __global__ void k_step_prepare(double* __restrict__ bcS, const double* __restric
     }
     if (threadIdx.x == 0) { status[b] = alive[b] ? ST_TRIAL : ST_FAILED; iters[b] = 0; fcalls[b] = 0; }
 }
+// newmark_output (src/analyses.jl:3461-3503): point rates of the current time level from the states and the initialisation terms,
+// udot = 2/dt u - udot_init etc.; udot, θdot are zeroed where the displacement is prescribed (udot_udot mask).  rates: [NP][12] of one instance.
+__device__ __forceinline__ void newmark_rates_point(const double* __restrict__ x, const double* __restrict__ bcS, const unsigned short* __restrict__ flags,
+                                                    const double* __restrict__ paug, double c2dt, int NP, int n, int64_t b, int p, double* __restrict__ out) {
+    const double* xp = x + b * n + 18 * p;
+    const double* bc = bcS + ((size_t)b * 18) * NP + p;
+    const double* pa = paug + ((size_t)b * 12) * NP + p;
+    const unsigned fl = flags[p];
+    for (int k = 0; k < 12; k++) {
+        const bool pd = k < 6 && (fl & (1u << k));
+        const double sv = pd ? bc[k * NP] : xp[k];
+        out[12 * p + k] = pd ? 0.0 : c2dt * sv - pa[(size_t)k * NP];
+    }
+}
+// rates_hist[b][slot][:] for every instance (slot 0 = the given initial rates)
+__global__ void k_save_rates(const double* __restrict__ x, const double* __restrict__ bcS, const unsigned short* __restrict__ flags,
+                             const double* __restrict__ paug, const double* __restrict__ rates0, double c2dt, int NP, int n, int64_t nsave, int64_t slot,
+                             int64_t nbatch, double* __restrict__ rates_hist) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * NP) return;
+    const int64_t b = t / NP; const int p = (int)(t % NP);
+    double* out = rates_hist + ((size_t)b * nsave + slot) * NP * 12;
+    if (slot == 0) { for (int k = 0; k < 12; k++) out[12 * p + k] = rates0[((size_t)b * NP + p) * 12 + k]; }
+    else newmark_rates_point(x, bcS, flags, paug, c2dt, NP, n, b, p, out);
+}
 __global__ void k_step_end(const int* status, const int* iters, int* alive, int* steps_done, int* iters_total, int64_t nbatch) {
     int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b >= nbatch) return;
@@ -56,7 +81,7 @@ struct PersistArgs {
     double* bcS; const double* series; const int* ser_point; const int* ser_field; int K; int64_t ser_nt;
     double* paug; const double* rates0;
     int* alive; int* steps; int* itot;
-    double* hist; int64_t nsave, save_every;
+    double* hist; double* rates_hist; int64_t nsave, save_every;
 };
 
 // separate (non-inlined) functions: each phase gets its own register allocation instead of one allocation for the fused kernel
@@ -156,6 +181,10 @@ template <int MODE> __global__ void __launch_bounds__(256) k_persistent_dynamic(
             if (P.hist && it % P.save_every == 0) {
                 double* h = P.hist + ((size_t)b * P.nsave + it / P.save_every) * n;
                 for (int c = threadIdx.x; c < n; c += blockDim.x) h[c] = x[c];
+            }
+            if (P.rates_hist && it % P.save_every == 0) {
+                double* out = P.rates_hist + ((size_t)b * P.nsave + it / P.save_every) * NP * 12;
+                for (int p = threadIdx.x; p < NP; p += blockDim.x) newmark_rates_point(P.Up.x, P.bcS, P.D.s.flags, P.paug, D.c2dt, NP, n, b, p, out);
             }
             __syncthreads();
         }

@@ -123,7 +123,8 @@ int gxb_steady_solve_resident(gxb_ctx* ctx, const gxb_opts* opts);
 int gxb_set_bc_series(gxb_ctx* ctx, int64_t nt, int32_t K, const int32_t* point /* 1-based */, const int32_t* field /* 0..17 */,
                       const double* values /* nbatch x nt x K */);
 int gxb_newmark_run(gxb_ctx* ctx, const gxb_opts* opts, int64_t nt, const double* tvec, const double* x0, const double* rates0,
-                    int64_t save_every, double* x_hist, int32_t* steps_done, int32_t* iters_total, int32_t* converged);
+                    int64_t save_every, double* x_hist, int32_t* steps_done, int32_t* iters_total, int32_t* converged,
+                    double* rates_hist /* optional: nbatch x nsave x np x 12, the dx of newmark_output (analyses.jl:3461-3503) */);
 
 /* The same solve on inputs already resident in HBM (no host<->device traffic): x0 from gxb_upload_x0 or zeros. */
 int gxb_upload_x0(gxb_ctx* ctx, const double* x0 /* or NULL */);

@@ -115,14 +115,15 @@ end
 """
     time_domain_analysis_batch(assemblies, tvec; prescribed_conditions, linear_velocity, angular_velocity,
         linear_acceleration, angular_acceleration, u0, theta0, V0, Omega0, Vdot0, Omegadot0, bc_series, ...)
-        -> (x_hist, rates0, converged)
+        -> (x_hist, dx_hist, converged)
 
 Batched counterpart of `time_domain_analysis` (src/analyses.jl:2510-2790) for chains: `initial_condition_analysis!`
 (:1695-1945) for every instance with `gxb_initial_condition`, then the Newmark march with `gxb_newmark_run` from the state left
 in HBM.  `bc_series = (points, fields, values[K, nt, nb])` holds the time-varying prescribed values evaluated by the caller from
 its `prescribed_conditions(t)` closures (field 0..17 = u, theta, F, M, Ff, Mf components).  `u0 ... Omegadot0` are `3 x np x nb`
-arrays (zeros by default, like the reference).  Returns the saved state vectors `x_hist[nstates, nsave, nb]`; each column goes
-into `AssemblyState(dx, x, system, assembly; prescribed_conditions)` exactly as at src/analyses.jl:2776.
+arrays (zeros by default, like the reference).  Returns the saved state vectors `x_hist[nstates, nsave, nb]` and point rates
+`dx_hist[12, np, nsave, nb]` (udot, thetadot, Vdot, Omegadot: the `dx` of `newmark_output`); each pair goes into
+`AssemblyState(dx, x, system, assembly; prescribed_conditions)` exactly as at src/analyses.jl:3502.
 """
 function time_domain_analysis_batch(assemblies::Vector{<:Assembly}, tvec;
         prescribed_conditions, linear_velocity=[zeros(3) for _ in assemblies], angular_velocity=[zeros(3) for _ in assemblies],
@@ -171,11 +172,11 @@ function time_domain_analysis_batch(assemblies::Vector{<:Assembly}, tvec;
                 ctx[], length(tvec), length(points), Int32.(points), Int32.(fields), values))
         end
         nt = length(tvec); nsave = (nt - 1) ÷ save_every + 1
-        xh = zeros(n, nsave, nb); steps = zeros(Int32, nb); itot = zeros(Int32, nb); conv = zeros(Int32, nb)
+        xh = zeros(n, nsave, nb); dxh = zeros(12, np, nsave, nb); steps = zeros(Int32, nb); itot = zeros(Int32, nb); conv = zeros(Int32, nb)
         check(ccall((:gxb_newmark_run, LIB), Cint,
-            (Ptr{Cvoid}, Ptr{Opts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
-            ctx[], opts, nt, collect(Float64, tvec), C_NULL, C_NULL, save_every, xh, steps, itot, conv))
-        return xh, rates0, (conv0 .!= 0) .& (conv .!= 0)
+            (Ptr{Cvoid}, Ptr{Opts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+            ctx[], opts, nt, collect(Float64, tvec), C_NULL, C_NULL, save_every, xh, steps, itot, conv, dxh))
+        return xh, dxh, (conv0 .!= 0) .& (conv .!= 0)
     finally
         ccall((:gxb_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
     end

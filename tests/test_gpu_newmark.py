@@ -208,3 +208,43 @@ def test_wind_turbine_blade_time_domain_analysis(damping):
     for name, ids in _groups(O, case).items():
         err = np.abs(res["x"][0][:, ids] - ref["x"][:, ids]).max()
         assert err <= 1e-8 * np.abs(ref["x"][:, ids]).max(), (name, err)
+
+
+@pytest.mark.parametrize("persistent", [2, 1])
+def test_rate_history_matches_newmark_output(persistent):
+    """gxb_newmark_run's rates_hist = the dx of newmark_output (analyses.jl:3461-3503) at every saved level: udot = 2/dt u - udot_init
+    etc. with the `paug` recurrence of analyses.jl:2693-2738, udot/θdot masked where the displacement is prescribed.  The expected
+    values are rebuilt in numpy from the ORACLE's state history."""
+    O = _oracle()
+    nb, nt = 3, 25
+    w, tvec, series = _gust(nb, nt, 0.006)
+    opts = api.make_opts(structural_damping=True, persistent=persistent)
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    ini = ctx.initial_condition(opts=opts)
+    ctx.set_bc_series([21], [7], series)
+    res = ctx.newmark_run(tvec, opts=opts, want_rates=True, save_every=4)
+    ctx.close()
+    assert res["converged"].all()
+    assert np.array_equal(res["rates"][:, 0], ini["rates"])
+    idx = O.indices(w["start"], w["stop"], False)
+    b = 1
+    pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
+    dyn = O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6], structural_damping=True)
+    ri = O.initial_condition(pk, dyn, O.InitialConditions(25, idx["nstates"]))
+    bct = np.tile(w["bc"][b][None], (nt, 1, 1)); bct[:, 20, 7] = series[b, :, 0]
+    ref = O.newmark_run(pk, dyn, tvec, ri["x"], ri["rates"], bct)
+
+    def states(x):                                             # [np, 12] with prescribed displacements filled in
+        s = np.stack([x[ic - 1:ic + 11] for ic in idx["icol_point"]])
+        pdm = w["pd"].astype(bool)
+        s[:, :6][pdm] = w["bc"][b][:, :6][pdm]
+        return s
+    rates = ri["rates"].copy()
+    mask = np.ones((25, 12)); mask[:, :6][w["pd"].astype(bool)] = 0.0
+    for it in range(1, nt):
+        c = 2.0 / (tvec[it] - tvec[it - 1])
+        init = c * states(ref["x"][it - 1]) + rates            # paug of this step
+        rates = c * states(ref["x"][it]) - init
+        if it % 4 == 0:
+            got = res["rates"][b, it // 4]
+            assert np.abs(got - rates * mask).max() <= 1e-7 * np.abs(rates).max(), it
