@@ -564,7 +564,7 @@ __global__ void k_rowblock_spmv(const double* __restrict__ Mrow, const double* _
 
 // out[b][c][j] = sum_k Vk[b][k][c] * Y[b][k][j]  (Y complex): thread per state c, four eigenvectors per pass
 __global__ void __launch_bounds__(128) k_ritz_vectors(const double* __restrict__ Vk, const double* __restrict__ Y, double* __restrict__ out, int n, int m, int nev) {
-    const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x, c = blockIdx.y * blockDim.x + threadIdx.x;      // batch on grid.x (no 65535 limit)
     const double* V = Vk + (size_t)b * (m + 1) * n;
     const double* Yb = Y + (size_t)b * m * nev * 2;
     for (int j0 = 0; j0 < nev; j0 += 4) {

@@ -1070,7 +1070,7 @@ int gxb_eigen_ritz_vectors(gxb_ctx* c, int32_t nev, const double* Y, double* vec
     double *d_Y = nullptr, *d_out = nullptr;
     CK(cudaMalloc(&d_Y, nb * m * nev * 16)); CK(cudaMalloc(&d_out, nb * n * nev * 16));
     CK(cudaMemcpyAsync(d_Y, Y, nb * m * nev * 16, cudaMemcpyHostToDevice, c->stream));
-    dim3 grid((unsigned)((n + 127) / 128), (unsigned)nb);
+    dim3 grid((unsigned)nb, (unsigned)((n + 127) / 128));
     k_ritz_vectors<<<grid, 128, 0, c->stream>>>(c->d_Vk, d_Y, d_out, (int)n, m, nev);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(vec, d_out, nb * n * nev * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -1083,6 +1083,7 @@ int gxb_eigen_ritz_vectors(gxb_ctx* c, int32_t nev, const double* Y, double* vec
 int gxb_newton_direction(gxb_ctx* c, const gxb_opts* opts, const double* x, double* p) {
     NEED_BATCH("gxb_newton_direction");
     if (!x || !p) return fail(GXB_ERR_INVALID, "gxb_newton_direction: null");
+    if (c->nbody > 0) return fail(GXB_ERR_UNSUPPORTED, "gxb_newton_direction: not available with body-frame acceleration states (use the solves)");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
     CK(cudaMemcpyAsync(c->d_xt, x, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
