@@ -3,6 +3,7 @@
 // Host code and the C-ABI live in gxb_lib.cu.
 #pragma once
 #include "gxb_lu.cuh"
+#include "gxb_lu_mma.cuh"
 #include "gxb_static.cuh"
 #include "gxb_dynamic.cuh"
 #include "gxb_initial.cuh"
@@ -280,13 +281,19 @@ struct SolveArgs {
 __device__ void linesearch_start(const SolveArgs& A, int64_t b);
 
 // one warp: factorise + solve instance b, then start the line search (|p|_inf, φ0, dφ0, first trial point)
-template <int KLB, int KUB> __device__ void factor_instance(const SolveArgs& A, int64_t b, double* sm) {
+template <int KLB, int KUB, int MMA = 0> __device__ void factor_instance(const SolveArgs& A, int64_t b, double* sm) {
     using S = LuShape<KLB, KUB>;
     const int lane = threadIdx.x & 31;
     const size_t n = A.n;
     const double* F = A.F + b * n;
     double* p = A.p + b * n;
-    int bad = warp_band_solve<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * n * S::UW, p, A.nb, A.sign, sm);
+    int bad;
+    if constexpr (MMA) {       // window in DMMA fragments, 8-column elimination blocks (gxb_lu_mma.cuh); U rows are wider, n padded to 8
+        using M = MmaShape<KLB, KUB>;
+        bad = warp_band_solve_mma<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * ((n + 7) & ~(size_t)7) * M::UW, p, A.nb, A.sign, sm);
+    } else {
+        bad = warp_band_solve<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * n * S::UW, p, A.nb, A.sign, sm);
+    }
     __syncwarp();
     if (A.direction_only == 1) return;
     if (bad) { if (lane == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
@@ -320,6 +327,16 @@ template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? G
     if (b >= A.nbatch) return;
     if (A.direction_only != 1 && A.ns.status[b] != ST_SOLVE) return;
     factor_instance<KLB, KUB>(A, b, smem + (size_t)warp * S::SM_DOUBLES);
+}
+// the same, with the tensor-core factorisation of gxb_lu_mma.cuh
+template <int KLB, int KUB> __global__ void __launch_bounds__(128, GXB_LU_MINBLOCKS) k_factor_solve_mma(SolveArgs A) {
+    using S = MmaShape<KLB, KUB>;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= A.nbatch) return;
+    if (A.direction_only != 1 && A.ns.status[b] != ST_SOLVE) return;
+    factor_instance<KLB, KUB, 1>(A, b, smem + (size_t)warp * S::SM_DOUBLES);
 }
 
 // Woodbury correction of a Newton step whose Jacobian is J = B + sum_i D_i e_{c_i}' (body-acceleration columns, see k_body_columns):

@@ -307,7 +307,11 @@ int gxb_set_batch(gxb_ctx* c, int64_t nbatch) {
     if ((rc = dalloc(&c->d_grav, nb * 3))) return rc;
     if ((rc = dalloc(&c->d_x, nb * n)) || (rc = dalloc(&c->d_xt, nb * n)) || (rc = dalloc(&c->d_F, nb * n)) || (rc = dalloc(&c->d_Ft, nb * n)) ||
         (rc = dalloc(&c->d_p, nb * n))) return rc;
-    if ((rc = dalloc(&c->d_J, nb * n * c->W)) || (rc = dalloc(&c->d_U, nb * n * c->UW))) return rc;
+    // U scratch: the row-per-lane factorisation stores n rows of UW doubles, the tensor-core one (static systems) n rounded up to 8 rows
+    // of MmaShape::UW doubles
+    size_t u_per_instance = n * c->UW;
+    if (c->kind == 0) u_per_instance = std::max(u_per_instance, ((n + 7) & ~(size_t)7) * (size_t)MmaShape<2, 2>::UW);
+    if ((rc = dalloc(&c->d_J, nb * n * c->W)) || (rc = dalloc(&c->d_U, nb * u_per_instance))) return rc;
     if (c->kind == 1) {
         if ((rc = dalloc(&c->d_exS, nb * 3 * N)) || (rc = dalloc(&c->d_xyz, nb * 3 * P)) || (rc = dalloc(&c->d_motion, nb * 12))) return rc;
         if ((rc = dalloc(&c->d_paug, nb * 12 * P)) || (rc = dalloc(&c->d_rates0, nb * 12 * P))) return rc;
@@ -509,6 +513,19 @@ template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveAr
     size_t sm = (size_t)wpc * S::SM_DOUBLES * 8;
     static thread_local size_t configured = 0;
     if (sm > 48 * 1024 && sm > configured) { CK(cudaFuncSetAttribute(k_factor_solve<KLB, KUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
+    if constexpr (KLB == 2) {
+        // static systems: tensor-core factorisation (gxb_lu_mma.cuh) unless GXB_LU_MMA=0 asks for the row-per-lane kernel (A/B runs)
+        static const int use_mma = []() { const char* e = getenv("GXB_LU_MMA"); return e ? atoi(e) : GXB_LU_MMA; }();
+        if (use_mma) {
+            using M = MmaShape<KLB, KUB>;
+            size_t smm = (size_t)wpc * M::SM_DOUBLES * 8;
+            static thread_local size_t configured_mma = 0;
+            if (smm > 48 * 1024 && smm > configured_mma) { CK(cudaFuncSetAttribute(k_factor_solve_mma<KLB, KUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smm)); configured_mma = smm; }
+            k_factor_solve_mma<KLB, KUB><<<grid1(c->nbatch, wpc), 32 * wpc, smm, c->stream>>>(A);
+            CK(cudaGetLastError());
+            return GXB_OK;
+        }
+    }
     k_factor_solve<KLB, KUB><<<grid1(c->nbatch, wpc), 32 * wpc, sm, c->stream>>>(A);
     CK(cudaGetLastError());
     return GXB_OK;
