@@ -47,7 +47,11 @@ template <int KLB, int KUB> struct MmaShape {
     static constexpr int SLOTS = 8 * RT;
     static constexpr int CT = (6 * (KLB + KUB) + 13 + 7) / 8;      // column tiles: window extent <= 6 (KLB + KUB) + 13 columns
     static constexpr int TW = 8 * (CT - 1);                        // trailing width
-    static constexpr int UW = ((2 + 8 + TW + 3) / 4) * 4;          // stored U row: rhs, 1/pivot, panel (8), trailing (TW)
+    // U is stored per block-row of 8 pivot rows, tile-major: [CT-1 trailing tiles: 8 rows x 8][heads: 8 rows x (rhs, 1/pivot, panel 8)],
+    // so that everything the back substitution reads is contiguous and sector-aligned
+    static constexpr int BRW = 8 * TW + 80;                        // doubles per block-row
+    static constexpr int HOFF = 8 * TW;                            // heads
+    static constexpr int UW = BRW / 8;                             // doubles per pivot row (allocation)
     static constexpr int PS = TW + 4;                              // published pivot row stride  (== 4 mod 16: conflict-free B-fragment loads)
     static constexpr int AS = 10;                                  // transposed panel row stride (conflict-free 16-byte row reads)
     static constexpr int ES = GXB_MMA_ES;                          // effective-multiplier row stride (12: conflict-free A-fragment loads; 10: smaller)
@@ -82,7 +86,7 @@ template <int KLB, int KUB>
 __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double* __restrict__ rhs, double* __restrict__ U,
                                    double* __restrict__ sol, int nb, double sign, double* sm) {
     using S = MmaShape<KLB, KUB>;
-    constexpr int W = S::W, RT = S::RT, CT = S::CT, SLOTS = S::SLOTS, UW = S::UW, PS = S::PS, AS = S::AS, ES = S::ES, RB = S::RB;
+    constexpr int W = S::W, RT = S::RT, CT = S::CT, SLOTS = S::SLOTS, BRW = S::BRW, HOFF = S::HOFF, PS = S::PS, AS = S::AS, ES = S::ES, RB = S::RB;
     constexpr int NSA = S::NSA, NSB = S::NSB;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, c2 = lane & 3;
@@ -112,15 +116,16 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
     // n to a multiple of 8 come with the last block.
     auto blocks_before = [&](int s) { const int r = KLB + 2 + s + s / 3; return r < nb ? r : nb; };
     auto rows_of = [&](int bb) { return bb >= nb ? n8 : 6 * bb; };
-    // TMA prefetch of the real rows entering after step t: a 6-row block is contiguous in the row-block storage
-    auto prefetch_rows = [&](int t) {
-        if (lane != 0) return;
-        const int b0 = blocks_before(t), b1 = blocks_before(t + 1);
-        if (b1 <= b0) return;
+    // TMA prefetch of the real rows entering after step t (blocks b0 .. b1-1): a 6-row block is contiguous in the row-block storage
+    auto prefetch_rows = [&](int t, int b0, int b1) {
+        if (lane != 0 || b1 <= b0) return;
         uint64_t* bar = bars + (t % NSB);
         mbar_expect_tx(bar, (unsigned)(b1 - b0) * (6 * W * 8));
         for (int B = b0; B < b1; B++) bulk_g2s(ring + (B % RB) * 6 * W, Jrow + (size_t)B * 6 * W, 6 * W * 8, bar);
     };
+    // right-hand sides of the rows entering after a step: lane i fetches the one of the i-th incoming row, it is handed to the slot that
+    // receives the row by a shuffle at the end of the step
+    auto prefetch_rhs = [&](int r0, int r1) { return (r0 + lane < r1 && r0 + lane < n) ? rhs[r0 + lane] : 0.0; };
 
     double c[RT][CT][2];
     double b = 0.0;            // row-lane state: right-hand side of slot `lane`
@@ -163,8 +168,13 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
         }
         if (lane < r0) { live = true; b = lane < n ? rhs[lane] : 0.0; }
     }
-#pragma unroll
-    for (int q = 0; q < NSA; q++) prefetch_rows(q);
+    // The rows entering after step s + 1 are requested in the middle of step s, in the shadow of the tensor-core update (the DMMA burst
+    // keeps the FP64 pipe busy for ~400 cycles during which the warp has nothing else to issue): one step of prefetch distance,
+    // two steps' worth of blocks in the ring.
+    static_assert(NSA == 1 && NSB == 2, "prefetch schedule");
+    int bb0 = blocks_before(0), bb1 = blocks_before(1);
+    prefetch_rows(0, bb0, bb1);
+    double rpre = prefetch_rhs(rows_of(bb0), rows_of(bb1));
 
 #ifdef GXB_LU_TIMING
     long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq = clock64(), tn;
@@ -172,16 +182,9 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
 #else
 #define GXB_MTICK(i) do { } while (0)
 #endif
-    int bb0 = blocks_before(0);
     for (int s = 0; s < nsteps; s++) {
         const int c0 = 8 * s;
-        prefetch_rows(s + NSA);
-        // rows entering after this step, and their right-hand sides (lane i fetches the one of the i-th incoming row now, it is handed
-        // to the slot that receives the row by a shuffle at the end of the step)
-        const int bb1 = blocks_before(s + 1);
-        const int rin0 = rows_of(bb0), rin1 = rows_of(bb1);
-        double rpre = 0.0;
-        if (rin0 + lane < rin1 && rin0 + lane < n) rpre = rhs[rin0 + lane];
+        const int rin0 = rows_of(bb0), rin1 = rows_of(bb1);      // rows entering after this step
         GXB_MTICK(0);
         // ---- 1. panel tile -> one row per lane ----
 #pragma unroll
@@ -232,7 +235,7 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
             for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(Lr + j) = make_double2(m[j], m[j + 1]);
             pbs[kp] = b;
             // the 8 x 8 triangle is stored scaled by 1/pivot of its row (the back substitution then has one FMA per level on its chain)
-            double* urow = U + (size_t)(c0 + kp) * UW + 2;
+            double* urow = U + (size_t)s * BRW + HOFF + kp * 10 + 2;
 #pragma unroll
             for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(urow + j) = make_double2(a[j] * myrinv, a[j + 1] * myrinv);
         }
@@ -281,7 +284,7 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
             slotkp[lane] = kp;
             slotnew[lane] = info;
         }
-        if (kp < 8) *reinterpret_cast<double2*>(U + (size_t)(c0 + kp) * UW) = make_double2(b, myrinv);   // final rhs of the U row, 1/pivot
+        if (kp < 8) *reinterpret_cast<double2*>(U + (size_t)s * BRW + HOFF + kp * 10) = make_double2(b, myrinv);   // final rhs of the U row, 1/pivot
         __syncwarp();
         GXB_MTICK(3);
         // ---- 4. pivot slots publish their unmodified trailing part ----
@@ -315,14 +318,18 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
 #pragma unroll
             for (int rt = 0; rt < RT; rt++) c[rt][CT - 1][0] = c[rt][CT - 1][1] = 0.0;
         }
+        // in the shadow of the DMMA burst: request the rows (and right-hand sides) of the next step
+        const int bb2 = blocks_before(s + 2);
+        prefetch_rows(s + 1, bb1, bb2);
+        const double rpre_next = prefetch_rhs(rin1, rows_of(bb2));
         GXB_MTICK(5);
         // ---- 6. final U rows of the pivot slots ----
 #pragma unroll
         for (int rt = 0; rt < RT; rt++) {
             if (kps[rt] < 8) {
-                double* urow = U + (size_t)(c0 + kps[rt]) * UW + 10 + 2 * c2;
+                double* urow = U + (size_t)s * BRW + kps[rt] * 8 + 2 * c2;
 #pragma unroll
-                for (int ct = 0; ct < CT - 1; ct++) *reinterpret_cast<double2*>(urow + 8 * ct) = make_double2(c[rt][ct][0], c[rt][ct][1]);
+                for (int ct = 0; ct < CT - 1; ct++) *reinterpret_cast<double2*>(urow + 64 * ct) = make_double2(c[rt][ct][0], c[rt][ct][1]);
             }
         }
         GXB_MTICK(6);
@@ -356,7 +363,7 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
             const double nbv = __shfl_sync(GXB_FULL, rpre, rank & 31);
             if (newrow >= 0) { live = true; b = nbv; }
         }
-        bb0 = bb1;
+        bb0 = bb1; bb1 = bb2; rpre = rpre_next;
         __syncwarp();
         GXB_MTICK(7);
     }
@@ -381,14 +388,15 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
         const int q = lane >> 3, k8 = lane & 7;
         auto prefetch_head = [&](int Jb) {
             if (Jb >= 0) {
-                cp_async16(hb + (Jb % HS) * 80 + (lane / 5) * 10 + 2 * (lane % 5), U + (size_t)(8 * Jb + lane / 5) * UW + 2 * (lane % 5));
-                if (lane < 8) { const int ch = 32 + lane; cp_async16(hb + (Jb % HS) * 80 + (ch / 5) * 10 + 2 * (ch % 5), U + (size_t)(8 * Jb + ch / 5) * UW + 2 * (ch % 5)); }
+                const double* hsrc = U + (size_t)Jb * BRW + HOFF;
+                cp_async16(hb + (Jb % HS) * 80 + 2 * lane, hsrc + 2 * lane);
+                if (lane < 8) cp_async16(hb + (Jb % HS) * 80 + 64 + 2 * lane, hsrc + 64 + 2 * lane);
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         };
         auto prefetch_l2 = [&](int Jb) {
             if (PD > 0 && Jb >= 0 && lane == 0)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(U + (size_t)(8 * Jb) * UW), "r"(8 * UW * 8) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(U + (size_t)Jb * BRW), "r"(BRW * 8) : "memory");
         };
         auto load_step = [&](int Jt, double2 (&f)[4], double& rin) {
             f[0] = f[1] = f[2] = f[3] = make_double2(0.0, 0.0); rin = 0.0;
@@ -396,17 +404,17 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
             int d = (Jt - q) & 3; if (d == 0) d = 4;
             const int B = Jt - d;
             if (B < 0) return;
-            const double* rp = U + (size_t)(8 * B + k8) * UW;
-            const double* ep = rp + 10 + 8 * (d - 1);
+            const double* rp = U + (size_t)B * BRW;
+            const double* ep = rp + 64 * (d - 1) + 8 * k8;
 #pragma unroll
             for (int i = 0; i < 4; i++) f[i] = *reinterpret_cast<const double2*>(ep + 2 * i);
-            if (d == 4) rin = rp[0];
+            if (d == 4) rin = rp[HOFF + 10 * k8];
         };
         const int Jl = nsteps - 1;
         double ps;
         {
             const int Bq = Jl - ((Jl - q) & 3);          // the last block congruent to q: its rows start from their right-hand sides
-            ps = Bq >= 0 ? U[(size_t)(8 * Bq + k8) * UW] : 0.0;
+            ps = Bq >= 0 ? U[(size_t)Bq * BRW + HOFF + 10 * k8] : 0.0;
         }
         double2 f_[NSET][4]; double rin_[NSET];
 #pragma unroll
