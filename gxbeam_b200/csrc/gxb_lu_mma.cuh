@@ -69,7 +69,7 @@ template <int KLB, int KUB> struct MmaShape {
     static constexpr int SM_DOUBLES = SM_P + SM_E + SM_L + SM_SLOT + SM_RING + SM_BAR;
     static_assert(SLOTS <= 32, "one lane per row slot");
     static_assert(PS % 16 == 4, "B-fragment bank layout");
-    static_assert(HS * 80 <= SM_RING, "head ring must fit the row ring");
+    static_assert(HS * 80 + 8 <= SM_RING, "head ring + x block must fit the row ring");
     static_assert(SM_DOUBLES % 2 == 0 && SM_P % 2 == 0 && SM_E % 2 == 0 && SM_SLOT % 2 == 0 && ES % 2 == 0, "16-byte alignment of the carve-up");
     static_assert(SM_P >= 72, "L11 + pivot right-hand sides alias the pivot rows");
 };
@@ -242,14 +242,19 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
         __syncwarp();
         // effective multipliers: e L11 = m, L11 unit lower triangular with L11[k][k'] = m_{pivot k}[k'];  kept negated (en = -e), which is
         // what the A fragments of D = A B + C need
+        // Row-oriented: once en[k] is final, row k of L11 (contiguous: 16-byte loads) updates every en[kk < k]; the critical path is
+        // one FMA per level.
         double en[8];
-        en[7] = -m[7];
 #pragma unroll
-        for (int kk = 6; kk >= 0; kk--) {
-            double acc = -m[kk];
+        for (int k = 0; k < 8; k++) en[k] = -m[k];
 #pragma unroll
-            for (int k = 7; k > kk; k--) acc = fma(-en[k], Lsm[k * 8 + kk], acc);    // the newest en last: 7 dependent FMAs in all
-            en[kk] = acc;
+        for (int k = 7; k >= 1; k--) {
+#pragma unroll
+            for (int kk = 0; kk < k; kk += 2) {
+                const double2 l = *reinterpret_cast<const double2*>(Lsm + k * 8 + kk);
+                en[kk] = fma(-en[k], l.x, en[kk]);
+                if (kk + 1 < k) en[kk + 1] = fma(-en[k], l.y, en[kk + 1]);
+            }
         }
         {
             double b2 = 0.0;
@@ -271,7 +276,8 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
                 newrow = rin0 + rank;
                 if (virt) info = newrow;
                 else {
-                    const int B = newrow / 6, slotB = B % RB, rr = newrow - 6 * B;
+                    const int rb = (rank >= 6) + (rank >= 12);                // rin0 is a multiple of 6, at most 18 rows enter
+                    const int B = bb0 + rb, slotB = B % RB, rr = rank - 6 * rb;
                     const int shift = 6 * (B - KLB) - (c0 + 8);            // 0, 2, 4 or 6
                     info = ((slotB * 6 + rr) * W - shift + 8) | (shift << 16);
                 }
@@ -385,6 +391,7 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
         constexpr int HS = S::HS, NSET = GXB_MMA_NSET, PD = GXB_MMA_PD;
         __syncwarp();
         double* hb = ring;                               // [HS][8][10] heads: rhs, 1/pivot, panel(8)
+        double* xs = ring + HS * 80;                     // scaled sums of the block being solved
         const int q = lane >> 3, k8 = lane & 7;
         auto prefetch_head = [&](int Jb) {
             if (Jb >= 0) {
@@ -427,12 +434,14 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
             prefetch_head(J - (HS - 1));
             asm volatile("cp.async.wait_group %0;\n" ::"n"(HS - 1) : "memory");
             __syncwarp();
+            // the owners of block J scale their finished sums by 1/pivot and hand them to everybody through shared memory
+            const double* h = hb + (J % HS) * 80;
+            if (q == (J & 3)) xs[k8] = ps * h[10 * k8 + 1];
+            __syncwarp();
             double x[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) x[k] = __shfl_sync(GXB_FULL, ps, 8 * (J & 3) + k);
-            const double* h = hb + (J % HS) * 80;
-#pragma unroll
-            for (int k = 0; k < 8; k++) x[k] *= h[10 * k + 1];
+            for (int k = 0; k < 8; k += 2) { const double2 t = *reinterpret_cast<const double2*>(xs + k); x[k] = t.x; x[k + 1] = t.y; }
+            // 8 x 8 unit upper triangle (stored scaled), the same arithmetic in every lane
 #pragma unroll
             for (int k = 7; k >= 1; k--) {
 #pragma unroll
