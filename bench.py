@@ -127,6 +127,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# dominant kernel and its committed `ncu --set full` summary: the tensor-core factorisation unless GXB_LU_MMA=0 selects the row-per-lane one
+_MMA = os.environ.get("GXB_LU_MMA", "1") != "0"
+FACTOR_KERNEL = "k_factor_solve_mma<2,2>" if _MMA else "k_factor_solve<2,2>"
+FACTOR_PROFILE = "r1_v7_prof_factor_mma_raw.csv" if _MMA else "r1_v5_prof_factor_raw.csv"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -265,11 +271,14 @@ def main():
         B_it, F_it = algorithmic_bytes_per_iter(NELEM), algorithmic_flops_per_iter(NELEM)
         # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this command (first Newton round: one
         # launch over all 4096 instances): dram__bytes_read.sum + dram__bytes_write.sum
-        traffic = None
+        traffic = capture_gbs = None
         try:
             import csv
-            vals = {r[0]: float(r[2]) for r in csv.reader(open(os.path.join(ROOT, "profiles", "r1_v5_prof_factor_raw.csv"))) if r and r[0].startswith("dram__bytes")}
-            traffic = (vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]) * 1e9
+            rows = {r[0]: r for r in csv.reader(open(os.path.join(ROOT, "profiles", FACTOR_PROFILE))) if r}
+            vals = {k: float(r[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "ms": 1e-3, "us": 1e-6}.get(r[1], 1.0) for k, r in rows.items()
+                    if k.startswith("dram__bytes") or k == "gpu__time_duration.sum"}
+            traffic = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+            capture_gbs = traffic / vals["gpu__time_duration.sum"] / 1e9
         except Exception:
             pass
         fac_s = prof["ms_factor"] * 1e-3
@@ -287,11 +296,12 @@ def main():
                     "ms_per_step": 1e3 * e2e_s_max / args.steps, "timing": e2e_how, "single_call_value_rank0": e2e_plain},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_factor_solve<2,2>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": FACTOR_KERNEL, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
-                         "traffic_note": "bytes per full-batch launch (4096 instances) from profiles/r1_v5_prof_factor_raw.csv: the row-block Jacobian "
-                                         "(incl. structural zeros) is read once, the U rows are written and read back once -- 0.94 MB per instance and "
+                         "traffic_note": f"bytes per full-batch launch (4096 instances) from profiles/{FACTOR_PROFILE}: the row-block Jacobian "
+                                         "(incl. structural zeros) is read once, the U rows are written and read back once -- ~1.1 MB per instance and "
                                          "iteration, SURVEY 8d's figure for a Jacobian materialised in HBM; `achieved` uses the on-chip ideal of 109 KB",
+                         "dram_gbs_in_capture": capture_gbs, "dram_frac_in_capture": (capture_gbs / hbm_peak) if capture_gbs else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_newton_iter": B_it, "launches": prof["n_factor"],
                          "avg_launch_ms": prof["ms_factor"] / max(prof["n_factor"], 1),
