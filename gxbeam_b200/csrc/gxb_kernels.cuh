@@ -329,7 +329,7 @@ template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? G
     factor_instance<KLB, KUB>(A, b, smem + (size_t)warp * S::SM_DOUBLES);
 }
 // the same, with the tensor-core factorisation of gxb_lu_mma.cuh
-template <int KLB, int KUB> __global__ void __launch_bounds__(128, GXB_LU_MINBLOCKS) k_factor_solve_mma(SolveArgs A) {
+template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? GXB_LU_MINBLOCKS : 2)) k_factor_solve_mma(SolveArgs A) {
     using S = MmaShape<KLB, KUB>;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;

@@ -307,10 +307,10 @@ int gxb_set_batch(gxb_ctx* c, int64_t nbatch) {
     if ((rc = dalloc(&c->d_grav, nb * 3))) return rc;
     if ((rc = dalloc(&c->d_x, nb * n)) || (rc = dalloc(&c->d_xt, nb * n)) || (rc = dalloc(&c->d_F, nb * n)) || (rc = dalloc(&c->d_Ft, nb * n)) ||
         (rc = dalloc(&c->d_p, nb * n))) return rc;
-    // U scratch: the row-per-lane factorisation stores n rows of UW doubles, the tensor-core one (static systems) n rounded up to 8 rows
-    // of MmaShape::UW doubles
+    // U scratch: the row-per-lane factorisation stores n rows of UW doubles, the tensor-core one n rounded up to 8 rows of
+    // MmaShape::UW doubles
     size_t u_per_instance = n * c->UW;
-    if (c->kind == 0) u_per_instance = std::max(u_per_instance, ((n + 7) & ~(size_t)7) * (size_t)MmaShape<2, 2>::UW);
+    u_per_instance = std::max(u_per_instance, ((n + 7) & ~(size_t)7) * (size_t)(c->kind == 0 ? MmaShape<2, 2>::UW : MmaShape<3, 4>::UW));
     if ((rc = dalloc(&c->d_J, nb * n * c->W)) || (rc = dalloc(&c->d_U, nb * u_per_instance))) return rc;
     if (c->kind == 1) {
         if ((rc = dalloc(&c->d_exS, nb * 3 * N)) || (rc = dalloc(&c->d_xyz, nb * 3 * P)) || (rc = dalloc(&c->d_motion, nb * 12))) return rc;
@@ -513,10 +513,11 @@ template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveAr
     size_t sm = (size_t)wpc * S::SM_DOUBLES * 8;
     static thread_local size_t configured = 0;
     if (sm > 48 * 1024 && sm > configured) { CK(cudaFuncSetAttribute(k_factor_solve<KLB, KUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
-    if constexpr (KLB == 2) {
-        // static systems: tensor-core factorisation (gxb_lu_mma.cuh) unless GXB_LU_MMA=0 asks for the row-per-lane kernel (A/B runs)
-        static const int use_mma = []() { const char* e = getenv("GXB_LU_MMA"); return e ? atoi(e) : GXB_LU_MMA; }();
-        if (use_mma) {
+    {
+        // tensor-core factorisation (gxb_lu_mma.cuh).  GXB_LU_MMA is a mask: bit 0 static systems, bit 1 dynamic systems; 0 keeps the
+        // row-per-lane kernel everywhere (A/B runs)
+        static const int mma_mask = []() { const char* e = getenv("GXB_LU_MMA"); return e ? atoi(e) : GXB_LU_MMA; }();
+        if (mma_mask & (KLB == 2 ? 1 : 2)) {
             using M = MmaShape<KLB, KUB>;
             size_t smm = (size_t)wpc * M::SM_DOUBLES * 8;
             static thread_local size_t configured_mma = 0;
@@ -716,7 +717,8 @@ static int launch_persistent(gxb_ctx* c, const gxb_opts& o, int mode, const Marc
     const size_t budget = 64 * 1024;
     int chunk = (int)std::min<size_t>((size_t)bs, (budget - (size_t)bs * GXB_XCH * 8) / (GXB_DTILE * 8));
     P.D.chunk = chunk;
-    size_t sm = std::max(((size_t)bs * GXB_XCH + (size_t)chunk * GXB_DTILE) * 8, (size_t)LuShape<3, 4>::SM_DOUBLES * 8);
+    size_t sm = std::max(((size_t)bs * GXB_XCH + (size_t)chunk * GXB_DTILE) * 8,
+                         (size_t)std::max(LuShape<3, 4>::SM_DOUBLES, MmaShape<3, 4>::SM_DOUBLES) * 8);
     P.S.sign = -1.0; P.S.nb = (int)(c->n / 6); P.S.n = (int)c->n; P.S.nbatch = c->nbatch;
     P.S.J = c->d_J; P.S.F = c->d_F; P.S.x = c->d_x; P.S.U = c->d_U; P.S.p = c->d_p; P.S.xt = c->d_xt; P.S.ns = c->ns;
     P.S.maxstep = o.maxstep; P.S.linear = 0; P.S.direction_only = 0;

@@ -23,7 +23,7 @@
 #include "gxb_lu.cuh"
 
 #ifndef GXB_LU_MMA
-#define GXB_LU_MMA 1
+#define GXB_LU_MMA 3        // default mask for the multi-kernel rounds: bit 0 static systems, bit 1 dynamic systems
 #endif
 // Shared memory per warp decides how much of the 256 KB per SM is left as L1 for the U rows the back substitution reads back: with a
 // six-block ring (58 KB per CTA) a launch over 4096 instances took 1.69 ms, with a four-block ring (45 KB) 1.50 ms.
@@ -380,15 +380,14 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
     const int bad = __any_sync(GXB_FULL, minkey < 32u) ? 1 : 0;
 
     // ---- back substitution, column-oriented over 8-blocks.  Row i needs x of the columns of its own block (the 8x8 triangle, solved
-    // redundantly in every lane from the 80-byte heads staged in shared memory) and of the CT-1 following blocks.  The 32 lanes hold the
-    // running sums of the 32 rows of the four blocks below the one being solved: lane (q = lane / 8, k8 = lane % 8) owns row k8 of the
-    // pending block congruent to q mod 4; entries are prefetched NSET steps ahead straight from global memory into registers. ----
-    static_assert(CT - 1 == 4, "back substitution is written for four trailing tiles");
+    // redundantly in every lane from the 80-byte heads staged in shared memory) and of the NT = CT-1 following blocks.  The lanes hold the
+    // running sums of the 8 NT rows of the NT blocks below the one being solved: slot p of lane (q = lane / 8, k8 = lane % 8) owns row k8 of
+    // the pending block congruent to q + 4 p mod NT; entries are prefetched NSET steps ahead straight from global memory into registers. ----
 #ifdef GXB_MMA_SKIP_BACKSUB
     if (false)
 #endif
     {
-        constexpr int HS = S::HS, NSET = GXB_MMA_NSET, PD = GXB_MMA_PD;
+        constexpr int HS = S::HS, NSET = GXB_MMA_NSET, PD = GXB_MMA_PD, NT = CT - 1, PEND = (8 * NT + 31) / 32;
         __syncwarp();
         double* hb = ring;                               // [HS][8][10] heads: rhs, 1/pivot, panel(8)
         double* xs = ring + HS * 80;                     // scaled sums of the block being solved
@@ -405,38 +404,48 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
             if (PD > 0 && Jb >= 0 && lane == 0)
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(U + (size_t)Jb * BRW), "r"(BRW * 8) : "memory");
         };
-        auto load_step = [&](int Jt, double2 (&f)[4], double& rin) {
-            f[0] = f[1] = f[2] = f[3] = make_double2(0.0, 0.0); rin = 0.0;
-            if (Jt < 0) return;
-            int d = (Jt - q) & 3; if (d == 0) d = 4;
-            const int B = Jt - d;
-            if (B < 0) return;
-            const double* rp = U + (size_t)B * BRW;
-            const double* ep = rp + 64 * (d - 1) + 8 * k8;
+        // distance of slot p's block from block Jt (jm = Jt mod NT): 1 .. NT
+        auto dist = [&](int jm, int p) { int d = jm - (q + 4 * p); if (d <= 0) d += NT; return d; };
+        auto wrap = [&](int jm) { return jm < 0 ? jm + NT : jm; };
+        auto load_step = [&](int Jt, int jm, double2 (&f)[PEND][4], double (&rin)[PEND]) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) f[i] = *reinterpret_cast<const double2*>(ep + 2 * i);
-            if (d == 4) rin = rp[HOFF + 10 * k8];
+            for (int p = 0; p < PEND; p++) {
+                f[p][0] = f[p][1] = f[p][2] = f[p][3] = make_double2(0.0, 0.0); rin[p] = 0.0;
+                if (Jt < 0 || q + 4 * p >= NT) continue;
+                const int d = dist(jm, p), B = Jt - d;
+                if (B < 0) continue;
+                const double* rp = U + (size_t)B * BRW;
+                const double* ep = rp + 64 * (d - 1) + 8 * k8;
+#pragma unroll
+                for (int i = 0; i < 4; i++) f[p][i] = *reinterpret_cast<const double2*>(ep + 2 * i);
+                if (d == NT) rin[p] = rp[HOFF + 10 * k8];
+            }
         };
         const int Jl = nsteps - 1;
-        double ps;
-        {
-            const int Bq = Jl - ((Jl - q) & 3);          // the last block congruent to q: its rows start from their right-hand sides
-            ps = Bq >= 0 ? U[(size_t)Bq * BRW + HOFF + 10 * k8] : 0.0;
-        }
-        double2 f_[NSET][4]; double rin_[NSET];
+        const int jml = Jl % NT;
+        double ps[PEND];
 #pragma unroll
-        for (int t = 0; t < NSET; t++) load_step(Jl - t, f_[t], rin_[t]);
+        for (int p = 0; p < PEND; p++) {
+            // the last block congruent to the slot's residue: its rows start from their right-hand sides
+            const int Bq = Jl - (dist(jml, p) % NT);
+            ps[p] = (q + 4 * p < NT && Bq >= 0) ? U[(size_t)Bq * BRW + HOFF + 10 * k8] : 0.0;
+        }
+        double2 f_[NSET][PEND][4]; double rin_[NSET][PEND];
+#pragma unroll
+        for (int t = 0; t < NSET; t++) load_step(Jl - t, wrap(jml - t), f_[t], rin_[t]);
 #pragma unroll
         for (int t = 0; t < HS - 1; t++) prefetch_head(Jl - t);
         for (int t = NSET + 1; t < PD; t++) prefetch_l2(Jl - t);
-        auto step = [&](int J, double2 (&f)[4], double& rin) {
+        auto step = [&](int J, int jm, double2 (&f)[PEND][4], double (&rin)[PEND]) {
             prefetch_l2(J - PD);
             prefetch_head(J - (HS - 1));
             asm volatile("cp.async.wait_group %0;\n" ::"n"(HS - 1) : "memory");
             __syncwarp();
             // the owners of block J scale their finished sums by 1/pivot and hand them to everybody through shared memory
             const double* h = hb + (J % HS) * 80;
-            if (q == (J & 3)) xs[k8] = ps * h[10 * k8 + 1];
+#pragma unroll
+            for (int p = 0; p < PEND; p++)
+                if (q + 4 * p == jm) xs[k8] = ps[p] * h[10 * k8 + 1];
             __syncwarp();
             double x[8];
 #pragma unroll
@@ -453,25 +462,29 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
                 for (int k = 1; k < 8; k++) xv = lane == k ? x[k] : xv;
                 sol[8 * J + lane] = sign * xv;
             }
-            {
-                int d = (J - q) & 3; if (d == 0) d = 4;
+#pragma unroll
+            for (int p = 0; p < PEND; p++) {
+                if (q + 4 * p >= NT) continue;
+                const int d = dist(jm, p);
                 if (J - d >= 0) {
-                    double acc = d == 4 ? rin : ps;
-                    double acc2 = -f[0].y * x[1];
-                    acc = fma(-f[0].x, x[0], acc); acc2 = fma(-f[1].y, x[3], acc2);
-                    acc = fma(-f[1].x, x[2], acc); acc2 = fma(-f[2].y, x[5], acc2);
-                    acc = fma(-f[2].x, x[4], acc); acc2 = fma(-f[3].y, x[7], acc2);
-                    acc = fma(-f[3].x, x[6], acc);
-                    ps = acc + acc2;
+                    double acc = d == NT ? rin[p] : ps[p];
+                    double acc2 = -f[p][0].y * x[1];
+                    acc = fma(-f[p][0].x, x[0], acc); acc2 = fma(-f[p][1].y, x[3], acc2);
+                    acc = fma(-f[p][1].x, x[2], acc); acc2 = fma(-f[p][2].y, x[5], acc2);
+                    acc = fma(-f[p][2].x, x[4], acc); acc2 = fma(-f[p][3].y, x[7], acc2);
+                    acc = fma(-f[p][3].x, x[6], acc);
+                    ps[p] = acc + acc2;
                 }
             }
-            load_step(J - NSET, f, rin);
+            int jn = jm - NSET; if (jn < 0) jn += NT;
+            load_step(J - NSET, jn, f, rin);
             __syncwarp();
         };
-        for (int J = Jl; J >= 0; J -= NSET) {
+        static_assert(NSET <= NT, "mod-NT bookkeeping");
+        for (int J = Jl, jm = jml; J >= 0; J -= NSET, jm = wrap(jm - NSET)) {
 #pragma unroll
             for (int t = 0; t < NSET; t++)
-                if (J - t >= 0) step(J - t, f_[t], rin_[t]);
+                if (J - t >= 0) step(J - t, wrap(jm - t), f_[t], rin_[t]);
         }
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }

@@ -85,7 +85,10 @@ struct PersistArgs {
 };
 
 // separate (non-inlined) functions: each phase gets its own register allocation instead of one allocation for the fused kernel
-__device__ __noinline__ void persist_factor(const SolveArgs& S, int b, double* smem) { factor_instance<3, 4>(S, b, smem); }
+#ifndef GXB_PERSIST_MMA
+#define GXB_PERSIST_MMA 1     // 1: tensor-core factorisation (gxb_lu_mma.cuh) inside the persistent kernel, 0: row-per-lane kernel
+#endif
+__device__ __noinline__ void persist_factor(const SolveArgs& S, int b, double* smem) { factor_instance<3, 4, GXB_PERSIST_MMA>(S, b, smem); }
 __device__ __noinline__ int persist_update(const UpdateArgs& U, int b) { return update_instance(U, b); }
 template <int MODE, bool WANT_J> __device__ __noinline__ void persist_assemble(const PersistArgs& P, const DynArgs& D, int b, double* smem) {
     if (MODE == 2) { InitArgs I{D, P.icS, P.rvm}; initial_station<WANT_J>(I, b, threadIdx.x, smem); }
