@@ -41,11 +41,16 @@ def algorithmic_bytes_per_iter(nelem):
     return 8 * (nelem * 91 + (nelem + 1) * 21 + 2 * n)
 
 
+# frozen by oracle/opcount.cpp (operation-counting scalar through the oracle's static residual + Jacobian, FMA = 2): one element with its
+# properties evaluated once, one free interior point
+F_ELEMENT_STATIC, F_POINT_STATIC = 3869, 2009
+
+
 def algorithmic_flops_per_iter(nelem):
-    """N·f_e + (N+1)·f_p + 2 n kl (kl+ku) + 2 n (2kl+ku), kl,ku = 14,17; f_e ≈ 4 k, f_p ≈ 0.6 k (static)."""
+    """N·f_e + (N+1)·f_p + 2 n kl (kl+ku) + 2 n (2kl+ku), kl,ku = 14,17; f_e, f_p frozen by oracle/opcount.cpp."""
     n = 12 * nelem + 6
     kl, ku = 14, 17
-    return nelem * 4000 + (nelem + 1) * 600 + 2 * n * kl * (kl + ku) + 2 * n * (2 * kl + ku)
+    return nelem * F_ELEMENT_STATIC + (nelem + 1) * F_POINT_STATIC + 2 * n * kl * (kl + ku) + 2 * n * (2 * kl + ku)
 
 
 class ClockSampler:

@@ -383,9 +383,6 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
     // redundantly in every lane from the 80-byte heads staged in shared memory) and of the NT = CT-1 following blocks.  The lanes hold the
     // running sums of the 8 NT rows of the NT blocks below the one being solved: slot p of lane (q = lane / 8, k8 = lane % 8) owns row k8 of
     // the pending block congruent to q + 4 p mod NT; entries are prefetched NSET steps ahead straight from global memory into registers. ----
-#ifdef GXB_MMA_SKIP_BACKSUB
-    if (false)
-#endif
     {
         constexpr int HS = S::HS, NSET = GXB_MMA_NSET, PD = GXB_MMA_PD, NT = CT - 1, PEND = (8 * NT + 31) / 32;
         __syncwarp();

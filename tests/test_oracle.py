@@ -140,3 +140,21 @@ def test_tipforce_converges_and_batch_matches_single():
     rb = O.static_solve_batch(pk, 4, force_scaling=fs, nthreads=2)
     for i, s in enumerate(singles):
         assert np.array_equal(rb["x"][i], s["x"]) and rb["iters"][i] == s["iters"] and rb["converged"][i] == 1
+
+
+def test_opcount_matches_bench_constants():
+    import os
+    import sys
+    """SURVEY §8(d): f_e, f_p are frozen by an operation-counting run of the oracle; bench.py's roofline uses exactly those numbers."""
+    import re
+    import subprocess
+    root0 = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root0 not in sys.path:
+        sys.path.insert(0, root0)
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(["make", "-s", "-C", os.path.join(root, "oracle"), "opcount"], capture_output=True, text=True, check=True).stdout
+    fe = int(re.search(r"f_e \(fused: properties once\)\s+= (\d+)", out).group(1))
+    fp = int(re.search(r"f_p \(residual \+ Jacobian, free interior point\)\s+= (\d+)", out).group(1))
+    assert (fe, fp) == (bench.F_ELEMENT_STATIC, bench.F_POINT_STATIC)
+    assert bench.algorithmic_flops_per_iter(100) == 100 * fe + 101 * fp + 1155348
