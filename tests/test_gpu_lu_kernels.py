@@ -1,0 +1,106 @@
+"""The two factorisation kernels behind `nlsolve!`'s linear solve (src/analyses.jl:3518, 3585): the tensor-core one (gxb_lu_mma.cuh, default)
+and the row-per-lane one (gxb_lu.cuh, GXB_LU_MMA=0).  Both are held to a dense LAPACK solve of the oracle's Jacobian on chain lengths that
+exercise every window situation of the 8-column elimination (fewer rows than slots, virtual identity rows padding n to a multiple of 8,
+6-row blocks entering one or two at a time), and to each other."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+from gxbeam_b200 import api
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_CHILD = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import cases
+import test_gpu_static as T
+out = {{}}
+for nelem in {sizes!r}:
+    case = cases.random_anisotropic(5, nelem=nelem)
+    ctx = T._ctx_for(case)
+    x = np.random.default_rng(nelem).random((1, ctx.n))
+    out[str(nelem)] = ctx.static_newton_direction(x)[0].tolist()
+    ctx.close()
+print("RESULT" + json.dumps(out))
+"""
+
+SIZES = [1, 2, 3, 5, 7, 12, 33, 100]
+
+
+def _directions(mma):
+    env = dict(os.environ, GXB_LU_MMA=str(mma))
+    code = _CHILD.format(root=ROOT, tests=os.path.join(ROOT, "tests"), sizes=SIZES)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("RESULT")][-1]
+    return {int(k): np.array(v) for k, v in json.loads(line[6:]).items()}
+
+
+def test_both_factorisations_match_dense_solve_and_each_other():
+    from oracle import pyoracle as O
+    mma, rowlane = _directions(3), _directions(0)
+    for nelem in SIZES:
+        case = cases.random_anisotropic(5, nelem=nelem)
+        pk = cases.oracle_packed(case)
+        n = 12 * nelem + 6
+        x = np.random.default_rng(nelem).random(n)
+        p_ref = -np.linalg.solve(O.static_jacobian(pk, x), O.static_residual(pk, x))
+        scale = np.abs(p_ref).max()
+        # tolerance: 1e-9 relative (BASELINE north_star), the dense solve itself carries cond(J) * eps
+        assert np.abs(mma[nelem] - p_ref).max() < 1e-9 * scale, nelem
+        assert np.abs(rowlane[nelem] - p_ref).max() < 1e-9 * scale, nelem
+        assert np.abs(mma[nelem] - rowlane[nelem]).max() < 1e-9 * scale, nelem
+
+
+_CHILD_DYN = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import cases
+import test_gpu_steady as T
+out = {{}}
+for nelem in {sizes!r}:
+    case = cases.random_anisotropic(4, nelem=nelem, pmass=True)
+    rng = np.random.default_rng(100 + nelem)
+    mo = 10 * rng.random(12)
+    ctx = T._ctx(case, mo[None])
+    x = rng.random((1, ctx.n))
+    out[str(nelem)] = ctx.newton_direction(x)[0].tolist()
+    ctx.close()
+print("RESULT" + json.dumps(out))
+"""
+
+SIZES_DYN = [1, 2, 3, 4, 8, 24]
+
+
+def _directions_dyn(mma):
+    env = dict(os.environ, GXB_LU_MMA=str(mma))
+    code = _CHILD_DYN.format(root=ROOT, tests=os.path.join(ROOT, "tests"), sizes=SIZES_DYN)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("RESULT")][-1]
+    return {int(k): np.array(v) for k, v in json.loads(line[6:]).items()}
+
+
+def test_both_factorisations_dynamic_systems():
+    """Same for DynamicSystem Jacobians (18 N + 12 states, 32 x 56 window, two pending slots per lane in the back substitution)."""
+    from oracle import pyoracle as O
+    mma, rowlane = _directions_dyn(3), _directions_dyn(0)
+    for nelem in SIZES_DYN:
+        case = cases.random_anisotropic(4, nelem=nelem, pmass=True)
+        pk = cases.oracle_packed(case)
+        rng = np.random.default_rng(100 + nelem)
+        mo = 10 * rng.random(12)
+        dyn = O.make_dyn(vb=mo[0:3], wb=mo[3:6], ab=mo[6:9], alb=mo[9:12])
+        x = rng.random(18 * nelem + 12)
+        p_ref = -np.linalg.solve(O.steady_jacobian(pk, dyn, x), O.steady_residual(pk, dyn, x))
+        scale = np.abs(p_ref).max()
+        assert np.abs(mma[nelem] - p_ref).max() < 1e-9 * scale, nelem
+        assert np.abs(rowlane[nelem] - p_ref).max() < 1e-9 * scale, nelem
+        assert np.abs(mma[nelem] - rowlane[nelem]).max() < 1e-9 * scale, nelem
