@@ -455,7 +455,9 @@ static StaticArgs make_static_args(gxb_ctx* c, const gxb_opts* o, const double* 
 static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
     int bs = (int)((c->np + 31) / 32) * 32;
     if (c->kind == 0) {
-        size_t sm = (size_t)bs * (GXB_XCH + (want_j ? GXB_TILE : 0)) * 8;
+        // exchange records for every thread, Jacobian tiles for the N + 1 stations only: a smaller footprint leaves more of the SM's
+        // 256 KB as L1 for the register spills of this 255-register kernel
+        size_t sm = ((size_t)bs * GXB_XCH + (want_j ? (size_t)c->np * GXB_TILE : 0)) * 8;
         if (want_j) {
             static thread_local size_t configured = 0;
             if (sm > configured) { CK(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }

@@ -94,7 +94,7 @@ template <bool WANT_J>
 __device__ void static_station(const StaticArgs& A, int b, int i, double* smem) {
     const int N = A.N, NP = N + 1;
     double* xch = smem;                                             // [blockDim][6]
-    double* tiles = smem + (size_t)blockDim.x * GXB_XCH;            // [blockDim][94]   (WANT_J only)
+    double* tiles = smem + (size_t)blockDim.x * GXB_XCH;            // [N + 1][94]   (WANT_J only)
     double* mytile = tiles + (size_t)threadIdx.x * GXB_TILE;
     double* nexttile = mytile + GXB_TILE;                           // station i+1 (valid when has_elem)
     const double fs = A.fs[b];
@@ -201,7 +201,7 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* smem) 
         mine[0] = F2.x * rfs; mine[1] = F2.y * rfs; mine[2] = F2.z * rfs;
         mine[3] = M2.x * rfs; mine[4] = M2.y * rfs; mine[5] = M2.z * rfs;
     }
-    if (WANT_J) tile_clear(mytile);
+    if (WANT_J && valid) tile_clear(mytile);      // tiles exist for the N + 1 stations only
     __syncthreads();
 
     // ---- residual: point rows = own term, += element i-1, -= element i ; element rows = compatibility ----
@@ -275,7 +275,7 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* smem) 
     __syncthreads();
 
     // =================== pass P2: moment-equilibrium rows of point i (rows 12i+3..5) ===================
-    tile_clear(mytile);
+    if (valid) tile_clear(mytile);
     __syncthreads();
     m3 JMa, M1F, hM;
     if (has_elem) {
@@ -330,7 +330,7 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* smem) 
     __syncthreads();
 
     // =================== pass E1: compatibility rows ru of element i (rows 12i+6..8) ===================
-    tile_clear(mytile);
+    if (valid) tile_clear(mytile);
     if (has_elem) {                                          // element.jl:1492-1505, 2507-2515
         m3 ruth = -0.5 * mul3t(R, Cab * Le1g);
         tblk(mytile, 6, colmask(-eye33(), mu1));
@@ -346,7 +346,7 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* smem) 
     __syncthreads();
 
     // =================== pass E2: compatibility rows rθ of element i (rows 12i+9..11) ===================
-    tile_clear(mytile);
+    if (valid) tile_clear(mytile);
     if (has_elem) {                                          // element.jl:1507-1518, 2517-2524
         m3 Qinv;
         m3 hd = -0.5 * rot_Qinv_dQinv_b(th, Cab * kap, Qinv);
