@@ -78,6 +78,24 @@ GXD void tile_flush(const double* tiles, double* J, int nst, int roff) {
         *reinterpret_cast<double2*>(J + (size_t)(12 * st + roff) * GXB_ROWW + 2 * q) = v;
     }
 }
+// The same flush by TMA: a station's tile (3 rows x 30 slots) is 720 contiguous bytes in shared memory AND in the row-block storage, so each
+// station thread issues ONE bulk store (cp.async.bulk shared -> global) instead of the CTA looping over 16-byte pieces (a quarter of the
+// kernel's instructions).  Contains the barriers of the pass: writes -> proxy fence -> barrier -> bulk store -> source read complete -> barrier.
+#ifndef GXB_ASM_TMA_FLUSH
+#define GXB_ASM_TMA_FLUSH 1
+#endif
+GXD void tile_flush_bulk(const double* mytile, double* J, int st, int roff, bool active) {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (active) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(mytile);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                     ::"l"(J + (size_t)(12 * st + roff) * GXB_ROWW), "r"(src), "n"(720) : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    }
+    __syncthreads();
+}
 // planar analysis (system.jl:1072-1103): rows 2,3,4 of every 6-slot become  x_k = 0
 GXD void tile_planar(double* t, int first_row_in_slot) {
 #pragma unroll
@@ -270,9 +288,13 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* smem) 
         }
         if (A.two_d) tile_planar(mytile, 0);
     }
+#if GXB_ASM_TMA_FLUSH
+    tile_flush_bulk(mytile, J, i, 0, valid);
+#else
     __syncthreads();
     tile_flush(tiles, J, NP, 0);
     __syncthreads();
+#endif
 
     // =================== pass P2: moment-equilibrium rows of point i (rows 12i+3..5) ===================
     if (valid) tile_clear(mytile);
@@ -325,9 +347,13 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* smem) 
         }
         if (A.two_d) tile_planar(mytile, 3);
     }
+#if GXB_ASM_TMA_FLUSH
+    tile_flush_bulk(mytile, J, i, 3, valid);
+#else
     __syncthreads();
     tile_flush(tiles, J, NP, 3);
     __syncthreads();
+#endif
 
     // =================== pass E1: compatibility rows ru of element i (rows 12i+6..8) ===================
     if (valid) tile_clear(mytile);
@@ -341,9 +367,13 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* smem) 
         tblk(mytile, 21, colmask(ruth, mth2));
         if (A.two_d) tile_planar(mytile, 0);
     }
+#if GXB_ASM_TMA_FLUSH
+    tile_flush_bulk(mytile, J, i, 6, has_elem);
+#else
     __syncthreads();
     tile_flush(tiles, J, N, 6);
     __syncthreads();
+#endif
 
     // =================== pass E2: compatibility rows rθ of element i (rows 12i+9..11) ===================
     if (valid) tile_clear(mytile);
@@ -357,6 +387,10 @@ __device__ void static_station(const StaticArgs& A, int b, int i, double* smem) 
         tblk(mytile, 21, colmask(hd + eye33(), mth2));
         if (A.two_d) tile_planar(mytile, 3);
     }
+#if GXB_ASM_TMA_FLUSH
+    tile_flush_bulk(mytile, J, i, 9, has_elem);
+#else
     __syncthreads();
     tile_flush(tiles, J, N, 9);
+#endif
 }
