@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nbatch", type=int, default=NBATCH, help="instances per GPU (default: BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, help="contexts per GPU sharing the resident batch (1 = one context, one stream)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -208,6 +209,45 @@ def main():
         dev_ms += st["ms_total"]; iters_total += st["newton_iters"]; launches += st["launches"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
+    # ---- the same resident batch split over `lanes` contexts (streams) of this GPU, solved concurrently from host threads: the
+    # assembly kernels (8 warps per SM, latency-bound on their loads) of one lane run under the factorisation (16 warps per SM) of the
+    # other.  Timed by one pair of CUDA events around the whole region (device idle at both ends), i.e. including every host-side gap.
+    lanes = args.lanes if (args.lanes > 1 and nb % args.lanes == 0) else 1
+    single = {"dev_ms": dev_ms, "iters": iters_total, "launches": launches, "wall_ms": wall_ms}
+    if lanes > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        per = nb // lanes
+        lctx = []
+        for i in range(lanes):
+            c = api.Context(local)
+            c.topology(w["start"], w["stop"], w["pd"], w["pl"])
+            c.set_batch(per)
+            sl = slice(i * per, (i + 1) * per)
+            c.set_elements(h_el[sl]); c.set_bc(h_bc[sl]); c.set_body(None, h_fs[sl])
+            lctx.append(c)
+        pool = ThreadPoolExecutor(lanes)
+
+        def run_lane(c):
+            c.static_solve_resident(opts_fast)        # returns when the lane's stream has finished (end event synchronised)
+            return c.stats()
+        for _ in range(args.warmup):
+            list(pool.map(run_lane, lctx))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters_total, launches = 0, 0
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            for st in pool.map(run_lane, lctx):
+                iters_total += st["newton_iters"]; launches += st["launches"]
+        e1.record(); e1.synchronize()
+        dev_ms = e0.elapsed_time(e1)
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        lane_x = np.concatenate([c.fetch()["x"] for c in lctx])
+        pool.shutdown()
+        for c in lctx:
+            c.close()
     clocks = sampler.stop() if rank == 0 else None
     # ---- kernel-class timing (profile pass, not part of `value`) ----
     prof = {"ms_assemble": 0.0, "ms_factor": 0.0, "ms_update": 0.0, "n_factor": 0, "n_assemble": 0, "newton_iters": 0, "ms_total": 0.0}
@@ -218,6 +258,8 @@ def main():
             prof[k] += st[k]
     res = ctx.fetch()
     assert res["converged"].all(), "bench workload must converge"
+    if lanes > 1:
+        assert np.array_equal(lane_x, res["x"]), "the lanes must reproduce the single-context result bit for bit"
     # ---- end-to-end through the C-ABI with host buffers ----
     for _ in range(2):
         ctx.set_elements(h_el); ctx.set_bc(h_bc); ctx.set_body(None, h_fs); ctx.static_solve(opts_fast, None, out)
@@ -296,7 +338,12 @@ def main():
                                    "randomised stiffness/loads (BASELINE configs[1])",
                        "nstates": n, "ftol": 1e-9, "seed": "1236 + 1000*rank", "parallelism": f"instances sharded over {world} GPU(s), no collective",
                        "l2": "inputs + Jacobian/U working set (~2.6 GB per step) exceed the 126 MB L2; no explicit flush",
-                       "newton_iters_per_step": iters_all / args.steps, "wall_ms_per_step": wall_ms_max / args.steps},
+                       "newton_iters_per_step": iters_all / args.steps, "wall_ms_per_step": wall_ms_max / args.steps,
+                       "resident_lanes": lanes,
+                       "resident_timing": ("one CUDA-event pair around all steps, batch split over %d contexts (streams) of the GPU driven by host "
+                                           "threads" % lanes) if lanes > 1 else "CUDA events on the library's stream, one context",
+                       "single_context_rank0": {"value": single["iters"] / (single["dev_ms"] * 1e-3), "ms_per_step": single["dev_ms"] / args.steps,
+                                                "wall_ms_per_step": single["wall_ms"] / args.steps, "gpu_launches": single["launches"]}},
             "e2e": {"value": e2e_iters_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s_max / args.steps, "timing": e2e_how, "single_call_value_rank0": e2e_plain},
             "gpu_launches": int(launches_all),
