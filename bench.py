@@ -158,10 +158,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # rank 0 prints exactly ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on fd 1 at
+    # NCCL_DEBUG=VERSION/WARN/INFO), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -376,7 +381,7 @@ def main():
             line["cpu_baseline"] = {"value": float(r["iters"].sum() / dt), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} instances of the same batch, one pass ({dt:.2f} s), C++ oracle port with a std::thread pool",
                                     "iters_equal_to_gpu": same, "max_rel_state_diff_vs_gpu": err}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     ctx.close()
     if dist:
         dist.destroy_process_group()
