@@ -32,7 +32,7 @@ for nelem in {sizes!r}:
 print("RESULT" + json.dumps(out))
 """
 
-SIZES = [1, 2, 3, 5, 7, 12, 33, 100]
+SIZES = [1, 2, 3, 5, 7, 12, 33, 100, 255]
 
 
 def _directions(mma):
@@ -77,7 +77,7 @@ for nelem in {sizes!r}:
 print("RESULT" + json.dumps(out))
 """
 
-SIZES_DYN = [1, 2, 3, 4, 8, 24]
+SIZES_DYN = [1, 2, 3, 4, 8, 24, 61]
 
 
 def _directions_dyn(mma):
