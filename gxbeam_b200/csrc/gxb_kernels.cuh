@@ -87,6 +87,13 @@ template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble(StaticA
     if (A.status && A.status[b] != A.want_status) return;
     static_station<WANT_J>(A, b, threadIdx.x, asm_smem);
 }
+// residual-only evaluation of chains of up to 127 elements: 128-thread CTAs, three of them per SM (168 registers instead of 182)
+__global__ void __launch_bounds__(128, 3) k_assemble_residual_128(StaticArgs A) {
+    extern __shared__ __align__(16) double asm_smem[];
+    const int b = blockIdx.x;
+    if (A.status && A.status[b] != A.want_status) return;
+    static_station<false>(A, b, threadIdx.x, asm_smem);
+}
 
 template <bool WANT_J, int MODE> __global__ void __launch_bounds__(256) k_assemble_dynamic(DynArgs A) {
     extern __shared__ __align__(16) double asm_smem[];

@@ -462,7 +462,8 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
             static thread_local size_t configured = 0;
             if (sm > configured) { CK(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
             k_assemble<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
-        } else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
+        } else if (bs <= 128) k_assemble_residual_128<<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
+        else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
     } else {
         DynArgs D{};
         D.s = A; D.exS = c->d_exS; D.pxS = c->d_xyz; D.motion = c->d_motion; D.init = c->d_paug; D.c2dt = c->c2dt; D.damping = c->damping;
