@@ -73,6 +73,9 @@ struct gxb_ctx {
     double* d_stage = nullptr; size_t stage_bytes = 0;
     // solver state
     double *d_x = nullptr, *d_xt = nullptr, *d_F = nullptr, *d_Ft = nullptr, *d_p = nullptr, *d_J = nullptr, *d_U = nullptr;
+    // largest dynamic shared-memory size configured (cudaFuncSetAttribute) per kernel family ON THIS CONTEXT'S DEVICE: the attribute is per
+    // device, and one host thread may drive contexts on several devices
+    size_t smem_cfg[5] = {0, 0, 0, 0, 0};
     NewtonState ns{};
     int* d_counter = nullptr; int* h_counter = nullptr;
     bool have_x0 = false;
@@ -459,7 +462,7 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
         // 256 KB as L1 for the register spills of this 255-register kernel
         size_t sm = ((size_t)bs * GXB_XCH + (want_j ? (size_t)c->np * GXB_TILE : 0)) * 8;
         if (want_j) {
-            static thread_local size_t configured = 0;
+            size_t& configured = c->smem_cfg[0];
             if (sm > configured) { CK(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
             k_assemble<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
         } else if (bs <= 128) k_assemble_residual_128<<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
@@ -474,7 +477,7 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
         D.chunk = chunk;
         size_t sm = ((size_t)bs * GXB_XCH + (want_j ? (size_t)chunk * GXB_DTILE : 0)) * 8;
         if (want_j) {
-            static thread_local size_t configured = 0;
+            size_t& configured = c->smem_cfg[1];
             if (sm > configured) {
                 CK(cudaFuncSetAttribute(k_assemble_dynamic<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                 CK(cudaFuncSetAttribute(k_assemble_dynamic<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -514,7 +517,7 @@ template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveAr
     static const int wpc_env = []() { const char* e = getenv("GXB_LU_WPC"); int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4) ? v : 4; }();
     const int wpc = wpc_env;      // warps (= instances) per CTA; the kernel is compiled for up to 128 threads per CTA
     size_t sm = (size_t)wpc * S::SM_DOUBLES * 8;
-    static thread_local size_t configured = 0;
+    size_t& configured = c->smem_cfg[2];
     if (sm > 48 * 1024 && sm > configured) { CK(cudaFuncSetAttribute(k_factor_solve<KLB, KUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
     {
         // tensor-core factorisation (gxb_lu_mma.cuh).  GXB_LU_MMA is a mask: bit 0 static systems, bit 1 dynamic systems; 0 keeps the
@@ -523,7 +526,7 @@ template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveAr
         if (mma_mask & (KLB == 2 ? 1 : 2)) {
             using M = MmaShape<KLB, KUB>;
             size_t smm = (size_t)wpc * M::SM_DOUBLES * 8;
-            static thread_local size_t configured_mma = 0;
+            size_t& configured_mma = c->smem_cfg[3];
             if (smm > 48 * 1024 && smm > configured_mma) { CK(cudaFuncSetAttribute(k_factor_solve_mma<KLB, KUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smm)); configured_mma = smm; }
             k_factor_solve_mma<KLB, KUB><<<grid1(c->nbatch, wpc), 32 * wpc, smm, c->stream>>>(A);
             CK(cudaGetLastError());
@@ -733,7 +736,7 @@ static int launch_persistent(gxb_ctx* c, const gxb_opts& o, int mode, const Marc
         P.K = c->ser_K; P.ser_nt = c->ser_nt; P.paug = c->d_paug; P.rates0 = c->d_rates0;
         P.alive = mb->alive; P.steps = mb->steps; P.itot = mb->itot; P.hist = mb->hist; P.rates_hist = mb->rates_hist; P.nsave = mb->nsave; P.save_every = mb->save_every;
     }
-    static thread_local size_t configured = 0;
+    size_t& configured = c->smem_cfg[4];
     if (sm > configured) {
         CK(cudaFuncSetAttribute(k_persistent_dynamic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         CK(cudaFuncSetAttribute(k_persistent_dynamic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
