@@ -11,6 +11,9 @@
 #ifndef GXB_LU_MINBLOCKS
 #define GXB_LU_MINBLOCKS 4
 #endif
+#ifndef GXB_LU_MINBLOCKS_DYN
+#define GXB_LU_MINBLOCKS_DYN 2      // CTAs per SM of the tensor-core factorisation for dynamic systems (218 registers)
+#endif
 
 enum { ST_SOLVE = 0, ST_TRIAL = 1, ST_DONE = 2, ST_FAILED = 3 };
 enum { FAIL_NONE = 0, FAIL_NONFINITE = 1, FAIL_LINESEARCH = 2, FAIL_MAXITER = 3, FAIL_SINGULAR = 4 };
@@ -336,7 +339,7 @@ template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? G
     factor_instance<KLB, KUB>(A, b, smem + (size_t)warp * S::SM_DOUBLES);
 }
 // the same, with the tensor-core factorisation of gxb_lu_mma.cuh
-template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? GXB_LU_MINBLOCKS : 2)) k_factor_solve_mma(SolveArgs A) {
+template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? GXB_LU_MINBLOCKS : GXB_LU_MINBLOCKS_DYN)) k_factor_solve_mma(SolveArgs A) {
     using S = MmaShape<KLB, KUB>;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;
