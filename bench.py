@@ -11,8 +11,10 @@
              gxbeam_b200.api.PipelinedSolver: 4 chunks on 4 contexts of the GPU from host threads, uploads serialised, so that one
              chunk's transfer runs under another chunk's solve; gxb_hint_no_gravity trims the element upload to the 49 doubles
              per element the static path reads.  The plain single-call figure is reported beside it.
-    N > 1  : one process per GPU (torchrun), instances sharded by rank, no collective on the data path; NCCL is used only
-             for the barrier and the max-over-ranks of the timings ("weak": 4096 instances per GPU)
+    N > 1  : one process per GPU (torchrun), the 4096 instances of BASELINE configs[1] sharded by rank ("strong": 4096 / N instances
+             per GPU -- the configuration BASELINE.json's target is quoted on: 4096 cantilevers over 8 GPUs = 512 per GPU), no
+             collective on the data path; NCCL is used only for the barrier and the max-over-ranks of the timings.
+             `--scaling weak` keeps 4096 instances per GPU instead.
 
   --impl reference : the reference's algorithm on the host cores (the CPU oracle port, oracle/ — Julia is not available so
                      the reference itself cannot run), all host threads, same config / metric.
@@ -33,6 +35,8 @@ sys.path.insert(0, ROOT)
 NBATCH, NELEM = 4096, 100
 METRIC = "batched Newton iterations/sec (systems x iters)"
 UNIT = "newton_iters/s"
+WORKLOAD = (f"{NBATCH} independent {NELEM}-element nonlinear cantilevers under tip moment (static_analysis), randomised stiffness/loads "
+            "(BASELINE configs[1])")
 
 
 def algorithmic_bytes_per_iter(nelem):
@@ -121,10 +125,11 @@ def run_reference(args):
         assert r["converged"].all()
     val = it_tot / t_tot
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{NBATCH} independent {NELEM}-element nonlinear cantilevers under tip moment (static_analysis), "
-                                   "randomised stiffness/loads (BASELINE configs[1])", "ftol": 1e-9, "seed": 1236},
+            "config": {"workload": WORKLOAD, "ftol": 1e-9, "seed": 1236,
+                       "newton_iteration_counts": "parity unpinned against NLsolve itself (its source is not in the reference tree); "
+                                                  "GPU == oracle port on every instance"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"all {NBATCH} instances per step; C++ restatement of GXBeam's static path (oracle/), std::thread pool over "
                                        "instances; Julia/GXBeam itself is not installable in this image"},
@@ -144,7 +149,12 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nbatch", type=int, default=NBATCH, help="instances per GPU (default: BASELINE config 2)")
+    ap.add_argument("--nbatch", type=int, default=None, help="instances per GPU (default: 4096 / N strong, 4096 weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: BASELINE configs[1]'s 4096 instances in total, sharded over the N GPUs; weak: 4096 per GPU")
+    ap.add_argument("--e2e-lanes", type=int, default=0, help="contexts per GPU of the pipelined host-buffer path (0 = by batch size)")
+    ap.add_argument("--lu-parts", type=int, default=0, help="warps per instance of the partitioned factorisation (0 auto, 1 off, 2/4/8)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the time-boxed configs 1/3/4 measurements (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=2, help="contexts per GPU sharing the resident batch (1 = one context, one stream)")
     args = ap.parse_args()
@@ -170,9 +180,17 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    nb = args.nbatch
-    # every rank owns its own shard of independent instances (different seed per rank): no data-path collective
-    w = workloads.cantilever_tipmoment_batch(nb, NELEM, seed=1236 + 1000 * rank)
+    # strong scaling (default): every rank generates the same seeded batch of BASELINE configs[1] and keeps its contiguous shard of
+    # 4096 / N instances; weak: 4096 instances of its own per rank.  No data-path collective either way.
+    if args.scaling == "strong":
+        nb = args.nbatch or NBATCH // world
+        wfull = workloads.cantilever_tipmoment_batch(nb * world, NELEM, seed=1236)
+        sl = slice(rank * nb, (rank + 1) * nb)
+        w = dict(wfull, elems=wfull["elems"][sl], bc=wfull["bc"][sl], force_scaling=wfull["force_scaling"][sl])
+        del wfull
+    else:
+        nb = args.nbatch or NBATCH
+        w = workloads.cantilever_tipmoment_batch(nb, NELEM, seed=1236 + 1000 * rank)
     ctx = api.Context(local)
     ctx.topology(w["start"], w["stop"], w["pd"], w["pl"])
     ctx.set_batch(nb)
@@ -197,8 +215,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    opts = api.make_opts(profile=True)
-    opts_fast = api.make_opts(profile=False)
+    opts = api.make_opts(profile=True, lu_parts=args.lu_parts)
+    opts_fast = api.make_opts(profile=False, lu_parts=args.lu_parts)
     # ---- device-resident metric ----
     for _ in range(args.warmup):
         ctx.static_solve_resident(opts_fast)
@@ -281,9 +299,12 @@ def main():
     # the same step through the pipelined service (api.PipelinedSolver): 4 chunks on 4 lanes of this GPU, uploads serialised, so the
     # PCIe transfer of chunk k+1 runs under the Newton solve of chunk k.  This is the reported e2e; the single-call figure is kept.
     e2e_plain = e2e_iters / e2e_s if e2e_s > 0 else 0.0
-    if nb % 4 == 0 and nb >= 1024:
+    e2e_lanes = args.e2e_lanes or (4 if nb >= 2048 else (2 if nb >= 256 else 1))
+    while nb % e2e_lanes:
+        e2e_lanes -= 1
+    if e2e_lanes >= 1:
         ctx.close()
-        ps = api.PipelinedSolver(w["start"], w["stop"], w["pd"], w["pl"], nb // 4, lanes=4, device=local, no_gravity=True)
+        ps = api.PipelinedSolver(w["start"], w["stop"], w["pd"], w["pl"], nb // e2e_lanes, lanes=e2e_lanes, device=local, no_gravity=True)
         for _ in range(2):
             ps.solve(h_el, h_bc, h_fs, out, opts_fast)
         barrier()
@@ -296,8 +317,8 @@ def main():
         barrier()
         assert out["converged"].all()
         ps.close()
-        e2e_how = ("wall clock around api.PipelinedSolver.solve (4 chunks x 4 lanes, host threads), pinned host buffers in the reference's "
-                   "Element layout; no-gravity hint: 49 of 91 doubles per element are fetched (strided copies)")
+        e2e_how = (f"wall clock around api.PipelinedSolver.solve ({e2e_lanes} chunks x {e2e_lanes} lanes, host threads), pinned host buffers in "
+                   "the reference's Element layout; no-gravity hint: 49 of 91 doubles per element are fetched (strided copies)")
     else:
         e2e_how = "wall clock around the synchronous C-ABI calls, pinned host buffers"
     # bytes that actually cross PCIe per step: with the no-gravity hint only 49 of the 91 doubles of every element record are read
@@ -338,11 +359,16 @@ def main():
         achieved = B_it * prof["newton_iters"] / fac_s / 1e9 if fac_s > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{nb} independent {NELEM}-element nonlinear cantilevers under tip moment per GPU (static_analysis), "
-                                   "randomised stiffness/loads (BASELINE configs[1])",
-                       "nstates": n, "ftol": 1e-9, "seed": "1236 + 1000*rank", "parallelism": f"instances sharded over {world} GPU(s), no collective",
+            "config": {"workload": WORKLOAD if (args.scaling == "strong" and nb * world == NBATCH) else
+                                   f"{nb} independent {NELEM}-element nonlinear cantilevers under tip moment per GPU (static_analysis), "
+                                   "randomised stiffness/loads (BASELINE configs[1] generator)",
+                       "instances_per_gpu": nb, "instances_total": nb * world,
+                       "nstates": n, "ftol": 1e-9, "seed": "1236" if args.scaling == "strong" else "1236 + 1000*rank",
+                       "parallelism": f"instances sharded over {world} GPU(s), no collective",
+                       "newton_iteration_counts": "parity unpinned against NLsolve itself (its source is not in the reference tree); "
+                                                  "GPU == oracle port on every instance (cpu_baseline.iters_equal_to_gpu)",
                        "l2": "inputs + Jacobian/U working set (~2.6 GB per step) exceed the 126 MB L2; no explicit flush",
                        "newton_iters_per_step": iters_all / args.steps, "wall_ms_per_step": wall_ms_max / args.steps,
                        "resident_lanes": lanes,

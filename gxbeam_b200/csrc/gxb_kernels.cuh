@@ -4,6 +4,7 @@
 #pragma once
 #include "gxb_lu.cuh"
 #include "gxb_lu_mma.cuh"
+#include "gxb_lu_part.cuh"
 #include "gxb_static.cuh"
 #include "gxb_dynamic.cuh"
 #include "gxb_initial.cuh"
@@ -347,6 +348,45 @@ template <int KLB, int KUB> __global__ void __launch_bounds__(128, (KLB == 2 ? G
     if (b >= A.nbatch) return;
     if (A.direction_only != 1 && A.ns.status[b] != ST_SOLVE) return;
     factor_instance<KLB, KUB, 1>(A, b, smem + (size_t)warp * S::SM_DOUBLES);
+}
+
+// |p|_inf, φ0, dφ0 and the first trial point by the whole CTA (the partitioned factorisation runs P warps per instance)
+__device__ void linesearch_start_cta(const SolveArgs& A, int64_t b) {
+    const size_t n = A.n;
+    const double* F = A.F + b * n; const double* p = A.p + b * n;
+    __shared__ double s_pm[8], s_ff[8];
+    double pm = 0.0, ff = 0.0;
+    for (int c = threadIdx.x; c < (int)n; c += blockDim.x) { pm = fmax(pm, fabs(p[c])); const double f = F[c]; ff = fma(f, f, ff); }
+    for (int o = 16; o; o >>= 1) { pm = fmax(pm, __shfl_xor_sync(GXB_FULL, pm, o)); ff += __shfl_xor_sync(GXB_FULL, ff, o); }
+    if ((threadIdx.x & 31) == 0) { s_pm[threadIdx.x >> 5] = pm; s_ff[threadIdx.x >> 5] = ff; }
+    __syncthreads();
+    pm = 0.0; ff = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) { pm = fmax(pm, s_pm[k]); ff += s_ff[k]; }
+    const double a0 = A.linear ? 1.0 : fmin(1.0, A.maxstep / pm);
+    const double* x = A.x + b * n; double* xt = A.xt + b * n;
+    for (int c = threadIdx.x; c < (int)n; c += blockDim.x) xt[c] = x[c] + a0 * p[c];
+    if (threadIdx.x == 0) {
+        A.ns.a1[b] = a0; A.ns.a2[b] = a0; A.ns.phi0[b] = 0.5 * ff; A.ns.dphi0[b] = -ff; A.ns.phx0[b] = 0.5 * ff;
+        A.ns.ls_k[b] = 0; A.ns.ls_finite[b] = 0; A.ns.status[b] = ST_TRIAL;
+    }
+}
+// partitioned factorisation (gxb_lu_part.cuh): one CTA of PT warps per instance, static systems; for batches too small to fill the GPU
+// with one warp per instance
+// register budget: 12 warps per SM -> 170 registers per thread (the lane-per-row window + spike are 96 registers of state; capped at
+// 128 the block step ran at half speed: 6400 instead of 3250 cycles, profiles/r2_part_timing.txt)
+#ifndef GXB_PART_MINB
+#define GXB_PART_MINB(PT) ((PT) >= 8 ? 1 : 12 / (PT))
+#endif
+template <int PT> __global__ void __launch_bounds__(32 * PT, GXB_PART_MINB(PT)) k_factor_solve_part(SolveArgs A, PartPlan plan) {
+    extern __shared__ __align__(16) double smem[];
+    const int64_t b = blockIdx.x;
+    if (A.direction_only != 1 && A.ns.status[b] != ST_SOLVE) return;
+    const size_t n = A.n;
+    const int bad = cta_part_solve(A.J + b * n * PartShape::W, A.F + b * n, A.U + b * n * PartShape::UW, A.p + b * n, plan, A.sign, smem);
+    if (A.direction_only == 1) return;
+    if (bad) { if (threadIdx.x == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
+    if (A.direction_only) return;
+    linesearch_start_cta(A, b);
 }
 
 // Woodbury correction of a Newton step whose Jacobian is J = B + sum_i D_i e_{c_i}' (body-acceleration columns, see k_body_columns):

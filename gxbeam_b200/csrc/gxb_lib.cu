@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -39,6 +41,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct gxb_ctx {
     int device = 0;
+    size_t smem_optin = 0;            // cudaDevAttrMaxSharedMemoryPerBlockOptin of the device
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     // topology
@@ -73,9 +76,6 @@ struct gxb_ctx {
     double* d_stage = nullptr; size_t stage_bytes = 0;
     // solver state
     double *d_x = nullptr, *d_xt = nullptr, *d_F = nullptr, *d_Ft = nullptr, *d_p = nullptr, *d_J = nullptr, *d_U = nullptr;
-    // largest dynamic shared-memory size configured (cudaFuncSetAttribute) per kernel family ON THIS CONTEXT'S DEVICE: the attribute is per
-    // device, and one host thread may drive contexts on several devices
-    size_t smem_cfg[5] = {0, 0, 0, 0, 0};
     NewtonState ns{};
     int* d_counter = nullptr; int* h_counter = nullptr;
     bool have_x0 = false;
@@ -117,6 +117,35 @@ static int stage_upload(gxb_ctx* c, const void* host, size_t bytes) {
 // everything that uses its output, so nobody has to wait for it on the host (this keeps a pipelined caller's upload slot short).
 static int wait_copy(gxb_ctx* c) { CK(cudaEventSynchronize(c->evC)); return GXB_OK; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function AND per device, and setting it replaces the previous value: every kernel
+// that uses dynamic shared memory is raised to the device's opt-in maximum once per device, so that contexts with different chain lengths
+// (or on different GPUs) cannot undercut each other.
+static int configure_kernels(int device, size_t* optin_out) {
+    static std::mutex mu;
+    static std::map<int, size_t> done;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(device);
+    if (it != done.end()) { *optin_out = it->second; return GXB_OK; }
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    // the limit covers static + dynamic shared memory of the kernel
+#define GXB_SMEM_MAX(k) do { cudaFuncAttributes fa_; CK(cudaFuncGetAttributes(&fa_, k)); \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa_.sharedSizeBytes)); } while (0)
+    GXB_SMEM_MAX(k_assemble<true>); GXB_SMEM_MAX(k_assemble<false>); GXB_SMEM_MAX(k_assemble_residual_128);
+    GXB_SMEM_MAX((k_assemble_dynamic<true, 0>)); GXB_SMEM_MAX((k_assemble_dynamic<true, 1>));
+    GXB_SMEM_MAX((k_assemble_dynamic<false, 0>)); GXB_SMEM_MAX((k_assemble_dynamic<false, 1>));
+    GXB_SMEM_MAX(k_assemble_initial<true>); GXB_SMEM_MAX(k_assemble_initial<false>);
+    GXB_SMEM_MAX((k_factor_solve<2, 2>)); GXB_SMEM_MAX((k_factor_solve<3, 4>));
+    GXB_SMEM_MAX((k_factor_solve_mma<2, 2>)); GXB_SMEM_MAX((k_factor_solve_mma<3, 4>));
+    GXB_SMEM_MAX(k_factor_solve_part<2>); GXB_SMEM_MAX(k_factor_solve_part<3>); GXB_SMEM_MAX(k_factor_solve_part<4>);
+    GXB_SMEM_MAX(k_factor_solve_part<6>); GXB_SMEM_MAX(k_factor_solve_part<8>);
+    GXB_SMEM_MAX(k_persistent_dynamic<0>); GXB_SMEM_MAX(k_persistent_dynamic<1>); GXB_SMEM_MAX(k_persistent_dynamic<2>);
+#undef GXB_SMEM_MAX
+    done[device] = (size_t)optin;
+    *optin_out = (size_t)optin;
+    return GXB_OK;
+}
+
 template <class T> static int dalloc(T** p, size_t count) { CK(cudaMalloc((void**)p, count * sizeof(T))); return GXB_OK; }
 
 static inline unsigned grid1(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -142,6 +171,7 @@ int gxb_create(gxb_ctx** out, int device) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    { int rc = configure_kernels(device, &c->smem_optin); if (rc) { delete c; return rc; } }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->d_counter, sizeof(int)));
     CK(cudaMallocHost(&c->h_counter, sizeof(int)));
@@ -314,6 +344,7 @@ int gxb_set_batch(gxb_ctx* c, int64_t nbatch) {
     // MmaShape::UW doubles
     size_t u_per_instance = n * c->UW;
     u_per_instance = std::max(u_per_instance, ((n + 7) & ~(size_t)7) * (size_t)(c->kind == 0 ? MmaShape<2, 2>::UW : MmaShape<3, 4>::UW));
+    if (c->kind == 0) u_per_instance = std::max(u_per_instance, n * (size_t)PartShape::UW);
     if ((rc = dalloc(&c->d_J, nb * n * c->W)) || (rc = dalloc(&c->d_U, nb * u_per_instance))) return rc;
     if (c->kind == 1) {
         if ((rc = dalloc(&c->d_exS, nb * 3 * N)) || (rc = dalloc(&c->d_xyz, nb * 3 * P)) || (rc = dalloc(&c->d_motion, nb * 12))) return rc;
@@ -462,8 +493,6 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
         // 256 KB as L1 for the register spills of this 255-register kernel
         size_t sm = ((size_t)bs * GXB_XCH + (want_j ? (size_t)c->np * GXB_TILE : 0)) * 8;
         if (want_j) {
-            size_t& configured = c->smem_cfg[0];
-            if (sm > configured) { CK(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
             k_assemble<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
         } else if (bs <= 128) k_assemble_residual_128<<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
         else k_assemble<false><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(A);
@@ -477,13 +506,6 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
         D.chunk = chunk;
         size_t sm = ((size_t)bs * GXB_XCH + (want_j ? (size_t)chunk * GXB_DTILE : 0)) * 8;
         if (want_j) {
-            size_t& configured = c->smem_cfg[1];
-            if (sm > configured) {
-                CK(cudaFuncSetAttribute(k_assemble_dynamic<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                CK(cudaFuncSetAttribute(k_assemble_dynamic<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                CK(cudaFuncSetAttribute(k_assemble_initial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                configured = sm;
-            }
             if (c->mode == 0) k_assemble_dynamic<true, 0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
             else if (c->mode == 1) k_assemble_dynamic<true, 1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
             else { InitArgs I{D, c->d_icS, c->d_rvm}; k_assemble_initial<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(I); }
@@ -517,8 +539,6 @@ template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveAr
     static const int wpc_env = []() { const char* e = getenv("GXB_LU_WPC"); int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4) ? v : 4; }();
     const int wpc = wpc_env;      // warps (= instances) per CTA; the kernel is compiled for up to 128 threads per CTA
     size_t sm = (size_t)wpc * S::SM_DOUBLES * 8;
-    size_t& configured = c->smem_cfg[2];
-    if (sm > 48 * 1024 && sm > configured) { CK(cudaFuncSetAttribute(k_factor_solve<KLB, KUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = sm; }
     {
         // tensor-core factorisation (gxb_lu_mma.cuh).  GXB_LU_MMA is a mask: bit 0 static systems, bit 1 dynamic systems; 0 keeps the
         // row-per-lane kernel everywhere (A/B runs)
@@ -526,8 +546,6 @@ template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveAr
         if (mma_mask & (KLB == 2 ? 1 : 2)) {
             using M = MmaShape<KLB, KUB>;
             size_t smm = (size_t)wpc * M::SM_DOUBLES * 8;
-            size_t& configured_mma = c->smem_cfg[3];
-            if (smm > 48 * 1024 && smm > configured_mma) { CK(cudaFuncSetAttribute(k_factor_solve_mma<KLB, KUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smm)); configured_mma = smm; }
             k_factor_solve_mma<KLB, KUB><<<grid1(c->nbatch, wpc), 32 * wpc, smm, c->stream>>>(A);
             CK(cudaGetLastError());
             return GXB_OK;
@@ -539,6 +557,41 @@ template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveAr
 }
 template <int KLB, int KUB> static int launch_factor_t(gxb_ctx* c, const SolveArgs& A);
 static int launch_factor_body(gxb_ctx* c, const gxb_opts* o);
+// Partitioned factorisation (gxb_lu_part.cuh): how many warps per instance.  One warp per instance (the tensor-core kernel) fills the GPU
+// from ~2400 instances on; for small batches the chain is cut into P partitions.  The partition kernel runs at 170 registers = 12 warps
+// per SM, and the whole batch should be resident in ONE wave: P = 12 * #SMs / nbatch, rounded down to one of 8, 6, 4, 3, 2.
+// opts.lu_parts / GXB_LU_PARTS: 0 auto, 1 off, 2 / 3 / 4 / 6 / 8 forced.
+static int choose_parts(const gxb_ctx* c, const gxb_opts* o) {
+    if (c->kind != 0) return 1;
+    static const int forced_env = []() { const char* e = getenv("GXB_LU_PARTS"); return e ? atoi(e) : 0; }();
+    const int forced = (o && o->lu_parts > 0) ? o->lu_parts : forced_env;
+    const int stations = (int)c->np;
+    static const int allowed[5] = {8, 6, 4, 3, 2};
+    int P = 1;
+    const int64_t want = forced > 0 ? forced : ((int64_t)c->sm_count * 12) / c->nbatch;
+    for (int cand : allowed) if (cand <= want) { P = cand; break; }
+    while (P > 1 && stations < 4 * P) P = P == 8 ? 6 : (P == 6 ? 4 : (P == 4 ? 3 : (P == 3 ? 2 : 1)));
+    return P;
+}
+// Cuts in front of a point (block 2 m).  The first partition carries no spike, so its block step is cheaper (measured 2400 vs 3250
+// cycles): it gets proportionally more stations.
+static PartPlan make_plan(const gxb_ctx* c, int P) {
+    PartPlan pl{};
+    pl.P = P;
+    const double w0 = 1.30;
+    const double unit = (double)c->np / (w0 + (P - 1));
+    double acc = w0 * unit;
+    pl.R0[0] = 0;
+    for (int q = 1; q < P; q++) {
+        int m = (int)(acc + 0.5);
+        const int lo = pl.R0[q - 1] / 2 + 4, hi = (int)c->np - 4 * (P - q);
+        m = std::max(lo, std::min(hi, m));
+        pl.R0[q] = 2 * m;
+        acc += unit;
+    }
+    pl.R0[P] = (int)(c->n / 6);
+    return pl;
+}
 static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, double sign = -1.0) {
     if (c->nbody > 0 && !direction_only) return launch_factor_body(c, o);
     SolveArgs A{};
@@ -546,6 +599,19 @@ static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, doub
     A.nb = (int)(c->n / 6); A.n = (int)c->n; A.nbatch = c->nbatch;
     A.J = c->d_J; A.F = direction_only ? c->d_Ft : c->d_F; A.x = c->d_x; A.U = c->d_U; A.p = c->d_p; A.xt = c->d_xt; A.ns = c->ns;
     A.maxstep = o->maxstep; A.linear = o->linear; A.direction_only = direction_only;
+    const int P = choose_parts(c, o);
+    if (P > 1) {
+        const PartPlan plan = make_plan(c, P);
+        const size_t sm = (size_t)PartShape::cta_doubles(P) * 8;
+        if (P == 2) k_factor_solve_part<2><<<(unsigned)c->nbatch, 64, sm, c->stream>>>(A, plan);
+        else if (P == 3) k_factor_solve_part<3><<<(unsigned)c->nbatch, 96, sm, c->stream>>>(A, plan);
+        else if (P == 4) k_factor_solve_part<4><<<(unsigned)c->nbatch, 128, sm, c->stream>>>(A, plan);
+        else if (P == 6) k_factor_solve_part<6><<<(unsigned)c->nbatch, 192, sm, c->stream>>>(A, plan);
+        else k_factor_solve_part<8><<<(unsigned)c->nbatch, 256, sm, c->stream>>>(A, plan);
+        CK(cudaGetLastError());
+        c->stats.launches++; c->stats.n_factor++;
+        return GXB_OK;
+    }
     int rc = c->kind == 0 ? launch_factor_t<2, 2>(c, A) : launch_factor_t<3, 4>(c, A);
     if (rc) return rc;
     c->stats.launches++; c->stats.n_factor++;
@@ -735,13 +801,6 @@ static int launch_persistent(gxb_ctx* c, const gxb_opts& o, int mode, const Marc
         P.nt = mb->nt; P.tvec = mb->d_tvec; P.bcS = c->d_bcS; P.series = c->d_series; P.ser_point = c->d_ser_point; P.ser_field = c->d_ser_field;
         P.K = c->ser_K; P.ser_nt = c->ser_nt; P.paug = c->d_paug; P.rates0 = c->d_rates0;
         P.alive = mb->alive; P.steps = mb->steps; P.itot = mb->itot; P.hist = mb->hist; P.rates_hist = mb->rates_hist; P.nsave = mb->nsave; P.save_every = mb->save_every;
-    }
-    size_t& configured = c->smem_cfg[4];
-    if (sm > configured) {
-        CK(cudaFuncSetAttribute(k_persistent_dynamic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        CK(cudaFuncSetAttribute(k_persistent_dynamic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        CK(cudaFuncSetAttribute(k_persistent_dynamic<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        configured = sm;
     }
     if (mode == 0) k_persistent_dynamic<0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(P);
     else if (mode == 1) k_persistent_dynamic<1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(P);

@@ -48,6 +48,10 @@ typedef struct gxb_opts {
                                 round-off in the line search's sums. */
     int32_t update_linearization; /* gxb_newmark_run with linear != 0: 0 = linearise every step about the initial state (the reference's
                                 default, analyses.jl:2536), 1 = about the current state */
+    int32_t lu_parts;        /* kind=0 only: warps per instance of the partitioned factorisation (the chain is cut into lu_parts sub-chains
+                                that are eliminated concurrently and coupled through a small interface system): 0 auto (by batch size),
+                                1 off, 2 / 3 / 4 / 6 / 8.  Any setting solves the same linear system; results agree to round-off. */
+    int32_t reserved_;       /* keeps sizeof(gxb_opts) a multiple of 8 */
 } gxb_opts;
 
 /* Filled by gxb_get_stats after a solve. */

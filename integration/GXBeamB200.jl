@@ -26,6 +26,8 @@ struct Opts            # mirrors gxb_opts
     structural_damping::Int32
     persistent::Int32
     update_linearization::Int32
+    lu_parts::Int32
+    reserved_::Int32
 end
 
 check(rc) = rc == 0 || error("gxbeam_b200: " * unsafe_string(ccall((:gxb_last_error, LIB), Cstring, ())))
@@ -95,7 +97,7 @@ function static_analysis_batch(assemblies::Vector{<:Assembly};
             check(ccall((:gxb_set_pmass, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], pm))
         end
         check(ccall((:gxb_set_body, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx[], grav, fs))
-        opts = Ref(Opts(linear, two_dimensional, ftol, iterations, 1e6, 1e-4, 0.5, 0.1, 0, 0, 0, 0))
+        opts = Ref(Opts(linear, two_dimensional, ftol, iterations, 1e6, 1e-4, 0.5, 0.1, 0, 0, 0, 0, 0, 0))
         x = Array{Float64}(undef, nstates[], nb); conv = zeros(Int32, nb); iters = zeros(Int32, nb); rinf = zeros(nb)
         GC.@preserve elems bc grav fs x conv iters rinf begin
             check(ccall((:gxb_static_solve, LIB), Cint,
@@ -147,7 +149,7 @@ function time_domain_analysis_batch(assemblies::Vector{<:Assembly}, tvec;
     for (k, a) in enumerate((u0, theta0, V0, Omega0, Vdot0, Omegadot0))
         isnothing(a) || (ic[3k-2:3k, :, :] .= a)
     end
-    opts = Ref(Opts(0, two_dimensional, ftol, iterations, 1e6, 1e-4, 0.5, 0.1, 0, structural_damping, 0, 0))
+    opts = Ref(Opts(0, two_dimensional, ftol, iterations, 1e6, 1e-4, 0.5, 0.1, 0, structural_damping, 0, 0, 0, 0))
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:gxb_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), ctx, device))
     try

@@ -104,3 +104,51 @@ def test_both_factorisations_dynamic_systems():
         assert np.abs(mma[nelem] - p_ref).max() < 1e-9 * scale, nelem
         assert np.abs(rowlane[nelem] - p_ref).max() < 1e-9 * scale, nelem
         assert np.abs(mma[nelem] - rowlane[nelem]).max() < 1e-9 * scale, nelem
+
+
+# ---- partitioned factorisation (gxb_lu_part.cuh): P warps per instance, static systems ----
+PART_SIZES = [15, 16, 33, 64, 100, 255]
+
+
+@pytest.mark.parametrize("parts", [2, 3, 4, 6, 8])
+def test_partitioned_factorisation_matches_dense_solve(parts):
+    """Newton direction of the partitioned (substructured) factorisation vs a dense LAPACK solve of the oracle's Jacobian and vs the
+    one-warp-per-instance kernel, on chains whose cuts fall at every position relative to the 6-row blocks / TMA ring, including the
+    shortest chain a given P accepts (4 stations per partition; shorter chains fall back to fewer partitions)."""
+    from oracle import pyoracle as O
+    import test_gpu_static as T
+    for nelem in PART_SIZES:
+        case = cases.random_anisotropic(5, nelem=nelem)
+        ctx = T._ctx_for(case)
+        n = 12 * nelem + 6
+        x = np.random.default_rng(nelem).random((1, n))
+        p_part = ctx.static_newton_direction(x, api.make_opts(lu_parts=parts))[0]
+        p_one = ctx.static_newton_direction(x, api.make_opts(lu_parts=1))[0]
+        ctx.close()
+        pk = cases.oracle_packed(case)
+        p_ref = -np.linalg.solve(O.static_jacobian(pk, x[0]), O.static_residual(pk, x[0]))
+        scale = np.abs(p_ref).max()
+        # 1e-9 relative (BASELINE north_star); both are backward-stable pivoted eliminations of the same matrix
+        assert np.abs(p_part - p_ref).max() < 1e-9 * scale, (parts, nelem)
+        assert np.abs(p_part - p_one).max() < 1e-9 * scale, (parts, nelem)
+
+
+@pytest.mark.parametrize("parts", [2, 3, 4, 6, 8])
+def test_partitioned_solve_iteration_parity(parts):
+    """Whole static_analysis of a sample of BASELINE config 2 with the partitioned factorisation: converged, Newton iteration counts
+    equal to the oracle's, states within 1e-9 (component-wise against the group scale)."""
+    from oracle import pyoracle as O
+    from gxbeam_b200 import workloads
+    nb = 48
+    w = workloads.cantilever_tipmoment_batch(nb, 100, tip_force=True)
+    ctx = api.Context(0)
+    ctx.topology(w["start"], w["stop"], w["pd"], w["pl"])
+    ctx.set_batch(nb)
+    ctx.set_elements(w["elems"]); ctx.set_bc(w["bc"]); ctx.set_body(None, w["force_scaling"])
+    res = ctx.static_solve(api.make_opts(lu_parts=parts))
+    ctx.close()
+    pk = O.Packed(w["start"], w["stop"], w["elems"], w["points"], w["pd"], w["pl"], w["bc"])
+    ref = O.static_solve_batch(pk, nb, force_scaling=w["force_scaling"])
+    assert res["converged"].all() and ref["converged"].all()
+    assert np.array_equal(res["iters"], ref["iters"])
+    assert np.abs(res["x"] - ref["x"]).max() < 1e-9 * np.abs(ref["x"]).max()
