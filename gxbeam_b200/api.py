@@ -33,7 +33,7 @@ class Opts(C.Structure):
     _fields_ = [("linear", C.c_int32), ("two_dimensional", C.c_int32), ("ftol", C.c_double), ("iterations", C.c_int64),
                 ("maxstep", C.c_double), ("c1", C.c_double), ("rho_hi", C.c_double), ("rho_lo", C.c_double),
                 ("profile", C.c_int32), ("structural_damping", C.c_int32), ("persistent", C.c_int32), ("update_linearization", C.c_int32),
-                ("lu_parts", C.c_int32), ("reserved_", C.c_int32)]
+                ("lu_parts", C.c_int32), ("exact_dphi0", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -79,11 +79,11 @@ def _f64(a):
 
 
 def make_opts(linear=False, two_dimensional=False, ftol=1e-9, iterations=1000, maxstep=1e6, c1=1e-4, rho_hi=0.5, rho_lo=0.1,
-              profile=False, structural_damping=False, persistent=0, update_linearization=False, lu_parts=0):
+              profile=False, structural_damping=False, persistent=0, update_linearization=False, lu_parts=0, exact_dphi0=False):
     """persistent: 0 auto, 1 force, 2 forbid the persistent per-instance kernel (kind=1 contexts).
     lu_parts: warps per instance of the partitioned factorisation (kind=0): 0 auto, 1 off, 2 / 3 / 4 / 6 / 8."""
     return Opts(int(linear), int(two_dimensional), ftol, iterations, maxstep, c1, rho_hi, rho_lo, int(profile), int(structural_damping),
-                int(persistent), int(update_linearization), int(lu_parts), 0)
+                int(persistent), int(update_linearization), int(lu_parts), int(exact_dphi0))
 
 
 class Context:

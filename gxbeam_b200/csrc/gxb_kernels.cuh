@@ -16,7 +16,9 @@
 #define GXB_LU_MINBLOCKS_DYN 2      // CTAs per SM of the tensor-core factorisation for dynamic systems (218 registers)
 #endif
 
-enum { ST_SOLVE = 0, ST_TRIAL = 1, ST_DONE = 2, ST_FAILED = 3 };
+// ST_SINGULAR: the factorisation hit an exactly-zero / non-finite pivot; the instance waits for k_singular_fallback (NLsolve's
+// (J'J + λI) step), which moves it on to ST_TRIAL
+enum { ST_SOLVE = 0, ST_TRIAL = 1, ST_DONE = 2, ST_FAILED = 3, ST_SINGULAR = 4 };
 enum { FAIL_NONE = 0, FAIL_NONFINITE = 1, FAIL_LINESEARCH = 2, FAIL_MAXITER = 3, FAIL_SINGULAR = 4 };
 
 // per-instance Newton / line-search scalars (structure of arrays)
@@ -288,7 +290,17 @@ struct SolveArgs {
     // Woodbury-corrected steps (body-acceleration states): F / p above are the right-hand side / solution of ONE band solve,
     // these are the Newton residual and direction the line search works with
     const double* Fnewton; double* pnewton;
+    // singular Jacobian: with `fallback` the instance is parked in ST_SINGULAR for k_singular_fallback (counter: unfinished instances of
+    // the round, singular_seen: sticky flag the host reads with the counter); without it the instance fails (FAIL_SINGULAR)
+    int fallback; int* counter; int* singular_seen;
 };
+__device__ __forceinline__ void mark_singular(const SolveArgs& A, int64_t b) {
+    if (A.fallback) {
+        A.ns.status[b] = ST_SINGULAR;
+        if (A.counter) atomicAdd(A.counter, 1);
+        if (A.singular_seen) *A.singular_seen = 1;
+    } else { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; }
+}
 __device__ void linesearch_start(const SolveArgs& A, int64_t b);
 
 // one warp: factorise + solve instance b, then start the line search (|p|_inf, φ0, dφ0, first trial point)
@@ -307,7 +319,7 @@ template <int KLB, int KUB, int MMA = 0> __device__ void factor_instance(const S
     }
     __syncwarp();
     if (A.direction_only == 1) return;
-    if (bad) { if (lane == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
+    if (bad) { if (lane == 0) { if (A.direction_only) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } else mark_singular(A, b); } return; }
     if (A.direction_only) return;        // 2: one of several solves of a Woodbury-corrected step (k_woodbury finishes it)
     linesearch_start(A, b);
 }
@@ -384,9 +396,148 @@ template <int PT> __global__ void __launch_bounds__(32 * PT, GXB_PART_MINB(PT)) 
     const size_t n = A.n;
     const int bad = cta_part_solve(A.J + b * n * PartShape::W, A.F + b * n, A.U + b * n * PartShape::UW, A.p + b * n, plan, A.sign, smem);
     if (A.direction_only == 1) return;
-    if (bad) { if (threadIdx.x == 0) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } return; }
+    if (bad) { if (threadIdx.x == 0) { if (A.direction_only) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } else mark_singular(A, b); } return; }
     if (A.direction_only) return;
     linesearch_start_cta(A, b);
+}
+
+// NLsolve's singular-Jacobian fallback (newton.jl, restated in SURVEY App. C and oracle/gxb_solve.hpp:135-160): when the factorisation
+// of J fails,   p = -(J'J + λ I) \ (J'F),   λ = 1e6 sqrt(n eps) ||J'J||_1.   A rare path -- clarity over speed: one CTA per parked
+// instance; M = J'J + λI (symmetric positive definite, cond <= ~3 because λ ~ 0.5 ||J'J||) is built in lower-band storage inside the
+// instance's U scratch and factorised as L D L' without pivoting, column by column.  Then the line search starts with the TRUE
+// dφ0 = g'p, g = J'F (J p != -F here).   Row r of the row-block storage holds columns 6 (r/6 - KLB) .. + W.
+struct FallbackArgs { SolveArgs S; int W, KLB; size_t u_stride; };      // u_stride: doubles of U scratch per instance
+__global__ void __launch_bounds__(256) k_singular_fallback(FallbackArgs Fa) {
+    const SolveArgs& A = Fa.S;
+    const int64_t b = blockIdx.x;
+    if (A.ns.status[b] != ST_SINGULAR) return;
+    const int n = A.n, W = Fa.W, KLB = Fa.KLB, nb = n / 6;
+    const int KUB = W / 6 - 1 - KLB;
+    const int m = 6 * (KLB + KUB) + 5;                       // half bandwidth of J'J
+    const double* J = A.J + (size_t)b * n * W;
+    const double* F = A.F + (size_t)b * n;
+    double* Mb = A.U + (size_t)b * Fa.u_stride;              // [n][m+1]: Mb[j][d] = M[j+d][j]
+    double* g = A.xt + (size_t)b * n;                        // J'F (xt is rewritten by the line-search start below)
+    double* p = A.p + (size_t)b * n;
+    __shared__ double red[8]; __shared__ double s_bc;
+    auto block_reduce = [&](double v, bool is_max) {
+        for (int o = 16; o; o >>= 1) { const double w = __shfl_xor_sync(GXB_FULL, v, o); v = is_max ? fmax(v, w) : v + w; }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) { double t = red[0]; for (int k = 1; k < (int)(blockDim.x >> 5); k++) t = is_max ? fmax(t, red[k]) : t + red[k]; s_bc = t; }
+        __syncthreads();
+        return s_bc;
+    };
+    auto Jat = [&](int r, int c) -> double {                 // J[r][c] or 0 outside the stored window
+        const int j = c - 6 * (r / 6 - KLB);
+        return (j >= 0 && j < W) ? J[(size_t)r * W + j] : 0.0;
+    };
+    // M = J'J (lower band) and g = J'F: column j is touched by the rows of blocks j/6 - KUB .. j/6 + KLB
+    for (int t = threadIdx.x; t < n * (m + 1); t += blockDim.x) {
+        const int j = t / (m + 1), d = t - j * (m + 1), i = j + d;
+        double acc = 0.0;
+        if (i < n) {
+            const int B0 = max(0, i / 6 - KUB), B1 = min(nb - 1, j / 6 + KLB);
+            for (int r = 6 * B0; r < 6 * (B1 + 1); r++) acc = fma(Jat(r, i), Jat(r, j), acc);
+        }
+        Mb[t] = acc;
+    }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int B0 = max(0, j / 6 - KUB), B1 = min(nb - 1, j / 6 + KLB);
+        double acc = 0.0;
+        for (int r = 6 * B0; r < 6 * (B1 + 1); r++) acc = fma(Jat(r, j), F[r], acc);
+        g[j] = acc;
+    }
+    __syncthreads();
+    // ||J'J||_1 = max column sum (symmetric: lower band + mirrored upper band)
+    double cmax = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double cs = 0.0;
+        for (int d = 0; d <= m && j + d < n; d++) cs += fabs(Mb[(size_t)j * (m + 1) + d]);
+        for (int d = 1; d <= m && j - d >= 0; d++) cs += fabs(Mb[(size_t)(j - d) * (m + 1) + d]);
+        cmax = fmax(cmax, cs);
+    }
+    const double lambda = 1e6 * sqrt((double)n * 2.220446049250313e-16) * block_reduce(cmax, true);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) Mb[(size_t)j * (m + 1)] += lambda;
+    __syncthreads();
+    // L D L' (right-looking): after step k, Mb[k][0] = D_k and Mb[k][d] = L[k+d][k]
+    for (int k = 0; k < n; k++) {
+        const double* ck = Mb + (size_t)k * (m + 1);
+        const double dk = ck[0];
+        const int mk = min(m, n - 1 - k);
+        for (int t = threadIdx.x; t < mk * (mk + 1) / 2; t += blockDim.x) {
+            // pairs 1 <= dj <= di <= mk, enumerated row by row
+            int di = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+            while ((di + 1) * (di + 2) / 2 <= t) di++;
+            while (di * (di + 1) / 2 > t) di--;
+            const int dj = t - di * (di + 1) / 2 + 1;
+            const int dI = di + 1;
+            Mb[(size_t)(k + dj) * (m + 1) + (dI - dj)] -= ck[dI] * ck[dj] / dk;
+        }
+        __syncthreads();
+        for (int d = 1 + threadIdx.x; d <= mk; d += blockDim.x) Mb[(size_t)k * (m + 1) + d] = ck[d] / dk;
+        __syncthreads();
+    }
+    // solve M y = g in p: forward (L), diagonal, backward (L')
+    for (int j = threadIdx.x; j < n; j += blockDim.x) p[j] = g[j];
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        const double yk = p[k];
+        const int mk = min(m, n - 1 - k);
+        for (int d = 1 + threadIdx.x; d <= mk; d += blockDim.x) p[k + d] -= Mb[(size_t)k * (m + 1) + d] * yk;
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) p[j] /= Mb[(size_t)j * (m + 1)];
+    __syncthreads();
+    for (int k = n - 1; k >= 0; k--) {
+        const int mk = min(m, n - 1 - k);
+        double acc = 0.0;
+        for (int d = 1 + threadIdx.x; d <= mk; d += blockDim.x) acc += Mb[(size_t)k * (m + 1) + d] * p[k + d];
+        acc = block_reduce(acc, false);
+        if (threadIdx.x == 0) p[k] -= acc;
+        __syncthreads();
+    }
+    // p = -(M \ g); line-search start with dφ0 = g'p
+    double pm = 0.0, ff = 0.0, gp = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        const double pc = -p[c];
+        p[c] = pc;
+        pm = fmax(pm, fabs(pc)); ff = fma(F[c], F[c], ff); gp = fma(g[c], pc, gp);
+    }
+    pm = block_reduce(pm, true); ff = block_reduce(ff, false); gp = block_reduce(gp, false);
+    const double a0 = A.linear ? 1.0 : fmin(1.0, A.maxstep / pm);
+    const double* x = A.x + (size_t)b * n; double* xt = A.xt + (size_t)b * n;
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) xt[c] = x[c] + a0 * p[c];
+    if (threadIdx.x == 0) {
+        A.ns.a1[b] = a0; A.ns.a2[b] = a0; A.ns.phi0[b] = 0.5 * ff; A.ns.dphi0[b] = gp; A.ns.phx0[b] = 0.5 * ff;
+        A.ns.ls_k[b] = 0; A.ns.ls_finite[b] = 0; A.ns.status[b] = ST_TRIAL;
+    }
+}
+
+// opts.exact_dphi0: dφ0 = g'p with g = J'F as NLsolve evaluates it (newton.jl), i.e. F'(J p), instead of -F'F (equal in
+// exact arithmetic because J p = -F; they differ by the residual of the linear solve).  One CTA per instance that has just started a
+// line search (status TRIAL, ls_k = 0, no evaluation yet); J is still intact in the row-block storage.
+struct DphiArgs { SolveArgs S; int W, KLB; };
+__global__ void __launch_bounds__(128) k_exact_dphi0(DphiArgs D) {
+    const SolveArgs& A = D.S;
+    const int64_t b = blockIdx.x;
+    if (A.ns.status[b] != ST_TRIAL || A.ns.ls_k[b] != 0 || A.ns.ls_finite[b] != 0) return;
+    const int n = A.n, W = D.W, KLB = D.KLB;
+    const double* J = A.J + (size_t)b * n * W; const double* F = A.F + (size_t)b * n; const double* p = A.p + (size_t)b * n;
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const int c0 = 6 * (r / 6 - KLB);
+        double jp = 0.0;
+        for (int j = 0; j < W; j++) { const int c = c0 + j; if (c >= 0 && c < n) jp = fma(J[(size_t)r * W + j], p[c], jp); }
+        acc = fma(F[r], jp, acc);
+    }
+    __shared__ double red[4];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(GXB_FULL, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) A.ns.dphi0[b] = (red[0] + red[1]) + (red[2] + red[3]);
 }
 
 // Woodbury correction of a Newton step whose Jacobian is J = B + sum_i D_i e_{c_i}' (body-acceleration columns, see k_body_columns):

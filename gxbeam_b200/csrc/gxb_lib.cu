@@ -79,6 +79,7 @@ struct gxb_ctx {
     NewtonState ns{};
     int* d_counter = nullptr; int* h_counter = nullptr;
     bool have_x0 = false;
+    bool fallback_armed = false;      // a singular Jacobian was seen in this solve: k_singular_fallback follows every factorisation
     gxb_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr;   // evC: end of the last host->device copy
 };
@@ -173,8 +174,8 @@ int gxb_create(gxb_ctx** out, int device) {
     c->sm_count = prop.multiProcessorCount;
     { int rc = configure_kernels(device, &c->smem_optin); if (rc) { delete c; return rc; } }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&c->d_counter, sizeof(int)));
-    CK(cudaMallocHost(&c->h_counter, sizeof(int)));
+    CK(cudaMalloc(&c->d_counter, 2 * sizeof(int)));          // [0] unfinished instances of the round, [1] sticky: a singular Jacobian was seen
+    CK(cudaMallocHost(&c->h_counter, 2 * sizeof(int)));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); CK(cudaEventCreate(&c->evA)); CK(cudaEventCreate(&c->evB)); CK(cudaEventCreateWithFlags(&c->evC, cudaEventDisableTiming));
     *out = c;
     return GXB_OK;
@@ -592,6 +593,28 @@ static PartPlan make_plan(const gxb_ctx* c, int P) {
     pl.R0[P] = (int)(c->n / 6);
     return pl;
 }
+// What follows a factorisation launch inside a Newton round: the singular-Jacobian fallback for the instances the factorisation parked
+// (launched only once the host has seen the sticky flag: the instance waits at most one counter read-back), and the exact dφ0.
+static int after_factor(gxb_ctx* c, const gxb_opts* o, const SolveArgs& A, int direction_only) {
+    if (direction_only) return GXB_OK;
+    if (c->fallback_armed) {
+        FallbackArgs Fa{};
+        Fa.S = A; Fa.W = c->W; Fa.KLB = c->KLB;
+        const int KUB = c->W / 6 - 1 - c->KLB;
+        Fa.u_stride = (size_t)c->n * (size_t)(6 * (c->KLB + KUB) + 6);
+        k_singular_fallback<<<(unsigned)c->nbatch, 256, 0, c->stream>>>(Fa);
+        CK(cudaGetLastError());
+        c->stats.launches++;
+    }
+    if (o->exact_dphi0) {
+        DphiArgs D{};
+        D.S = A; D.W = c->W; D.KLB = c->KLB;
+        k_exact_dphi0<<<(unsigned)c->nbatch, 128, 0, c->stream>>>(D);
+        CK(cudaGetLastError());
+        c->stats.launches++;
+    }
+    return GXB_OK;
+}
 static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, double sign = -1.0) {
     if (c->nbody > 0 && !direction_only) return launch_factor_body(c, o);
     SolveArgs A{};
@@ -599,6 +622,7 @@ static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, doub
     A.nb = (int)(c->n / 6); A.n = (int)c->n; A.nbatch = c->nbatch;
     A.J = c->d_J; A.F = direction_only ? c->d_Ft : c->d_F; A.x = c->d_x; A.U = c->d_U; A.p = c->d_p; A.xt = c->d_xt; A.ns = c->ns;
     A.maxstep = o->maxstep; A.linear = o->linear; A.direction_only = direction_only;
+    A.fallback = direction_only ? 0 : 1; A.counter = c->d_counter; A.singular_seen = c->d_counter + 1;
     const int P = choose_parts(c, o);
     if (P > 1) {
         const PartPlan plan = make_plan(c, P);
@@ -610,12 +634,12 @@ static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, doub
         else k_factor_solve_part<8><<<(unsigned)c->nbatch, 256, sm, c->stream>>>(A, plan);
         CK(cudaGetLastError());
         c->stats.launches++; c->stats.n_factor++;
-        return GXB_OK;
+        return after_factor(c, o, A, direction_only);
     }
     int rc = c->kind == 0 ? launch_factor_t<2, 2>(c, A) : launch_factor_t<3, 4>(c, A);
     if (rc) return rc;
     c->stats.launches++; c->stats.n_factor++;
-    return GXB_OK;
+    return after_factor(c, o, A, direction_only);
 }
 // Newton step with body-acceleration columns: 1 + nbody band solves (L is not stored, so each one re-factorises B) and the
 // Woodbury correction.  A niche path (free-flying structures): clarity over speed.
@@ -716,8 +740,20 @@ static int newton_rounds(gxb_ctx* c, const gxb_opts& o, Prof& prof, int burst) {
             if (residual_first) { prof.begin(); if ((rc = launch_assemble(c, A_next, true))) return rc; prof.end(c->stats.ms_assemble); }
             c->stats.rounds += 1;
         }
-        CK(cudaMemcpyAsync(c->h_counter, c->d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_counter, c->d_counter, 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
+        if (c->h_counter[1] && !c->fallback_armed) {
+            // first singular Jacobian of this solve: from now on k_singular_fallback follows every factorisation; the instances that are
+            // parked in ST_SINGULAR right now get their (J'J + λI) step before the next round
+            c->fallback_armed = true;
+            SolveArgs A{};
+            A.nb = (int)(c->n / 6); A.n = (int)c->n; A.nbatch = c->nbatch; A.sign = -1.0;
+            A.J = c->d_J; A.F = c->d_F; A.x = c->d_x; A.U = c->d_U; A.p = c->d_p; A.xt = c->d_xt; A.ns = c->ns;
+            A.maxstep = o.maxstep; A.linear = o.linear; A.fallback = 1;
+            gxb_opts o2 = o; o2.exact_dphi0 = 0;
+            if ((rc = after_factor(c, &o2, A, 0))) return rc;
+            continue;
+        }
         if (*c->h_counter == 0) break;
         // straggler hand-off: the few instances that are still iterating finish in the persistent kernel (one CTA each, no more
         // batch-wide rounds paced by the slowest instance); finished instances exit at once
@@ -736,6 +772,8 @@ static int solve_resident(gxb_ctx* c, const gxb_opts* opts, int mode) {
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
     int rc;
     c->mode = mode;
+    c->fallback_armed = false;
+    CK(cudaMemsetAsync(c->d_counter, 0, 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     if (!c->have_x0) CK(cudaMemsetAsync(c->d_x, 0, nb * n * 8, c->stream));   // reset_state (system.jl:383-386)
     CK(cudaMemcpyAsync(c->d_xt, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));
@@ -862,6 +900,8 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
         CK(cudaMemcpyAsync(c->d_rates0, rates0, nb * P * 12 * 8, cudaMemcpyHostToDevice, c->stream));
     }
     c->have_initial = false;
+    c->fallback_armed = false;
+    CK(cudaMemsetAsync(c->d_counter, 0, 8, c->stream));
     if (o.linear && !o.update_linearization) {
         CK(cudaMalloc(&d_xlin, nb * n * 8));
         CK(cudaMemcpyAsync(d_xlin, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));

@@ -122,11 +122,17 @@ WT_MASS = np.array([[258.053, 0.0, 0.0, 0.0, 7.07839, -71.6871],
                     [-71.6871, 0.0, 0.0, 0.0, 0.0, 46.418]])
 
 
-def wind_turbine_blade_batch(nbatch=1024, nelem=200, seed=1234 + 3, nspeeds=16):
+def wind_turbine_blade_batch(nbatch=1024, nelem=200, seed=1234 + 3, nspeeds=16, speed_max=0.9):
     """BASELINE config 3: rotating wind-turbine blades (straight, L = 60 m, the fully populated 6x6 stiffness / mass of
     test/examples/wind-turbine-blade.jl:19-37, root clamped), stiffness and mass scaled per design by U(0.8, 1.2), rotor-speed
-    sweep ωb = (0, 0, Ω_j), Ω_j = nspeeds values in [0, 2] rad/s; instance b = (design b // nspeeds, speed b % nspeeds).
+    sweep ωb = (0, 0, Ω_j), Ω_j = nspeeds values in [0, speed_max] rad/s; instance b = (design b // nspeeds, speed b % nspeeds).
     steady_state_analysis + linearised eigenvalue analysis (nev = 20), n = 18·nelem + 12.
+
+    speed_max = 0.9 rad/s (8.6 rpm, the operating range of a 60 m blade).  SURVEY 8d proposed [0, 2] rad/s; between 1.07 and 1.33 rad/s
+    Newton from the zero state (how the reference starts every `steady_state_analysis`, test/examples/rotating.jl:71-90) stagnates in
+    the line search for 11 of the 1024 designs x speeds -- identically in the CPU oracle, with `iterations = 1000` as with 50
+    (scratch/c3_probe.py: residuals stay at 0.1 .. 50) -- so that range measured the iteration cap, not the path.  With 0.9 rad/s all
+    1024 instances converge in at most 5 iterations in the oracle and on the device, at the reference's default `iterations = 1000`.
     """
     rng = np.random.default_rng(seed)
     L = 60.0
@@ -138,7 +144,7 @@ def wind_turbine_blade_batch(nbatch=1024, nelem=200, seed=1234 + 3, nspeeds=16):
     ks = rng.uniform(0.8, 1.2, ndes)
     ms = rng.uniform(0.8, 1.2, ndes)
     comp0 = np.linalg.inv(WT_STIFFNESS)
-    speeds = np.linspace(0.0, 2.0, nspeeds)
+    speeds = np.linspace(0.0, speed_max, nspeeds)
     elems = np.zeros((nbatch, nelem, 91))
     elems[:, :, 0] = L / nelem
     elems[:, :, 1] = ((xs[:-1] + xs[1:]) / 2)[None, :]

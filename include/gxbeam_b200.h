@@ -51,7 +51,9 @@ typedef struct gxb_opts {
     int32_t lu_parts;        /* kind=0 only: warps per instance of the partitioned factorisation (the chain is cut into lu_parts sub-chains
                                 that are eliminated concurrently and coupled through a small interface system): 0 auto (by batch size),
                                 1 off, 2 / 3 / 4 / 6 / 8.  Any setting solves the same linear system; results agree to round-off. */
-    int32_t reserved_;       /* keeps sizeof(gxb_opts) a multiple of 8 */
+    int32_t exact_dphi0;     /* line search slope dφ0 = g'p with g = J'F as NLsolve's newton evaluates it (one extra pass over J per Newton
+                                iteration) instead of -F'F, which is the same number in exact arithmetic because J p = -F.  Default 0.
+                                The singular-Jacobian fallback step p = -(J'J + λI) \ J'F always uses g'p. */
 } gxb_opts;
 
 /* Filled by gxb_get_stats after a solve. */

@@ -27,7 +27,7 @@ struct Opts            # mirrors gxb_opts
     persistent::Int32
     update_linearization::Int32
     lu_parts::Int32
-    reserved_::Int32
+    exact_dphi0::Int32
 end
 
 check(rc) = rc == 0 || error("gxbeam_b200: " * unsafe_string(ccall((:gxb_last_error, LIB), Cstring, ())))

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from gxbeam_b200 import api, workloads
+from gxbeam_b200.parity import componentwise_error
 from test_gpu_newmark import _ctx, _groups, _gust
 
 pytestmark = pytest.mark.gpu
@@ -48,8 +49,10 @@ def test_c4_full_size_time_domain_analysis():
         ref = O.newmark_run(pk, dyn, tvec, ri["x"], ri["rates"], bct)
         assert ref["converged"] and int(res["iters_total"][b]) == int(ref["iters"].sum())
         for name, ids in _groups(O, w).items():
-            err = np.abs(res["x"][b][:, ids] - ref["x"][::500][:, ids]).max()
-            assert err <= 1e-9 * np.abs(ref["x"][:, ids]).max(), (b, name, err)
+            # component-wise (gxbeam_b200/parity.py), 1e-9; the floor scale is the class's maximum over the whole history (at t = 0
+            # the undeformed blade carries no internal loads at all: that level alone would compare round-off with round-off)
+            err = componentwise_error(res["x"][b][:, ids].ravel(), ref["x"][::500][:, ids].ravel())
+            assert err <= 1e-9, (b, name, err)
 
 
 def test_c3_full_size_steady_and_eigen():
@@ -58,11 +61,11 @@ def test_c3_full_size_steady_and_eigen():
     nb, nelem, nev, m = 1024, 200, 20, 70
     w = workloads.wind_turbine_blade_batch(nb, nelem)
     ctx = _ctx(w, w["motion"], nb, w["points_b"])
-    opts = api.make_opts(iterations=50)
+    opts = api.make_opts()                      # the reference's defaults: ftol = 1e-9, iterations = 1000
     res = ctx.steady_solve(opts)
     conv = res["converged"]
-    # (1) ~1 % of the designs x speeds stagnate in the line search (identically in the oracle); all others are under ftol
-    assert conv.sum() >= 1000 and (res["resid_inf"][conv] <= 1e-9).all()
+    # (1) every design x speed converges (workloads.py: rotor speeds up to 0.9 rad/s), residuals under ftol
+    assert conv.all() and (res["resid_inf"] <= 1e-9).all()
     # (2) idempotence on the converged members
     res2 = ctx.steady_solve(opts, x0=res["x"])
     assert (res2["iters"][conv] == 0).all() and np.array_equal(res2["x"][conv], res["x"][conv])
@@ -72,14 +75,15 @@ def test_c3_full_size_steady_and_eigen():
     # conjugate pairs: the spectrum is closed under conjugation up to the cut at nev
     assert np.all(np.isfinite(lam[conv].view(float)))
     # (4) sampled members against the oracle: iteration counts, states, and (K + λ M) v = 0 with the ORACLE's K and M
-    pick = [int(i) for i in np.nonzero(conv)[0][[0, 400, -1]]]
+    pick = [0, 7, 400, 1023]
     for b in pick:
         pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
         dyn = O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6])
-        ref = O.steady_solve(pk, dyn, iterations=50)
+        ref = O.steady_solve(pk, dyn)
         assert ref["converged"] and ref["iters"] == int(res["iters"][b])
         for name, ids in _groups(O, w).items():
-            assert np.abs(res["x"][b][ids] - ref["x"][ids]).max() <= 1e-7 * np.abs(ref["x"][ids]).max(), (b, name)
+            err = componentwise_error(res["x"][b][ids], ref["x"][ids])
+            assert err <= 1e-9, (b, name, err)
         K = O.steady_jacobian(pk, dyn, res["x"][b])
         M = O.mass_matrix(pk, res["x"][b])
         for k in range(nev):
