@@ -5,7 +5,8 @@
   gust   : config 4 — 512-member gust ensemble, time_domain_analysis of 2000 Newmark steps (dt = 0.25 ms) on the same topology,
            initial state from initial_condition_analysis like benchmark/benchmarks.jl:143-216 (or --gust-init steady), structural
            damping on (the reference's default)
-Prints one JSON line per workload.
+Prints one JSON line per workload; bench.py imports the three functions and attaches their dicts to its JSON line as `secondary`
+(time-boxed CPU samples), so that the driver's own run carries these numbers with clocks.
 """
 import argparse
 import json
@@ -20,6 +21,7 @@ SAVE_EVERY = 0
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gxbeam_b200 import api, workloads  # noqa: E402
+from gxbeam_b200.parity import state_error  # noqa: E402
 
 
 def make_ctx(w, nb):
@@ -45,10 +47,10 @@ def steady(nb, cpu_sample):
     pk = O.Packed(w["start"], w["stop"], w["elems"][:ns], w["points_b"][:ns], w["pd"], w["pl"], w["bc"][:ns])
     dyns = [O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6]) for b in range(ns)]
     t0 = time.perf_counter(); ref = O.steady_solve_batch(pk, ns, dyns, force_scaling=w["force_scaling"][:ns]); dt = time.perf_counter() - t0
-    err = float(np.abs(res["x"][:ns] - ref["x"]).max() / np.abs(ref["x"]).max())
-    print(json.dumps({"workload": f"steady_state_analysis, {nb} rotating blades (config-1 topology, n=444)", "gpu_newton_iters_per_s": its / (ms * 1e-3),
-                      "gpu_ms_per_batch": ms / 10, "cpu_newton_iters_per_s": float(ref["iters"].sum() / dt), "cpu_cores": O.num_threads(),
-                      "cpu_sample": ns, "iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "max_rel_diff": err}), flush=True)
+    err = state_error(res["x"][:ns], ref["x"], 1)
+    return {"workload": f"steady_state_analysis, {nb} rotating blades (config-1 topology, n=444)", "gpu_newton_iters_per_s": its / (ms * 1e-3),
+            "gpu_ms_per_batch": ms / 10, "cpu_newton_iters_per_s": float(ref["iters"].sum() / dt), "cpu_cores": O.num_threads(),
+            "cpu_sample": ns, "iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "max_componentwise_rel_diff": err}
 
 
 def gust(nb, nt, cpu_sample, damping=True, init="ic"):
@@ -89,7 +91,7 @@ def gust(nb, nt, cpu_sample, damping=True, init="ic"):
     wall = time.perf_counter() - t0
     s = ctx.stats(); ctx.close()
     ns = min(nb, cpu_sample)
-    t0 = time.perf_counter(); cpu_iters = 0; err = 0.0
+    t0 = time.perf_counter(); cpu_iters = 0; err = 0.0; iters_equal = True
     for b in range(ns):
         pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
         dyn = O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6], structural_damping=damping)
@@ -101,17 +103,18 @@ def gust(nb, nt, cpu_sample, damping=True, init="ic"):
             cx0, cr0 = x0[b], rates0[b]
         ref = O.newmark_run(pk, dyn, tvec, cx0, cr0, bct)
         cpu_iters += int(ref["iters"].sum())
-        err = max(err, float(np.abs(res["x"][b, -1] - ref["x"][-1]).max() / np.abs(ref["x"][-1]).max()))
+        iters_equal = iters_equal and int(res["iters_total"][b]) == int(ref["iters"].sum())
+        err = max(err, state_error(res["x"][b, -1], ref["x"][-1], 1))
     dt = time.perf_counter() - t0
     gpu_ms = s["ms_total"] + ms_init
-    print(json.dumps({"workload": f"time_domain_analysis, {nb}-member gust ensemble, {nt - 1} Newmark steps (config 4), structural_damping={damping}, "
-                                  f"initial state: {'initial_condition_analysis (as benchmarks.jl:143-216)' if init == 'ic' else 'steady state'}",
-                      "gpu_newton_iters_per_s": (s["newton_iters"] + it_init) / (gpu_ms * 1e-3), "gpu_s_per_run": gpu_ms * 1e-3,
-                      "gpu_s_initial_condition": ms_init * 1e-3, "gpu_wall_s": wall, "saved_time_levels": int(res["x"].shape[1]),
-                      "gpu_launches": s["launches"] + launches_init, "newton_iters": s["newton_iters"] + it_init,
-                      "all_converged": bool(res["converged"].all()),
-                      "cpu_newton_iters_per_s_1core": cpu_iters / dt, "cpu_s_per_instance_1core": dt / ns, "cpu_sample": ns,
-                      "max_rel_diff_final_state": err}), flush=True)
+    return {"workload": f"time_domain_analysis, {nb}-member gust ensemble, {nt - 1} Newmark steps (config 4), structural_damping={damping}, "
+                        f"initial state: {'initial_condition_analysis (as benchmarks.jl:143-216)' if init == 'ic' else 'steady state'}",
+            "gpu_newton_iters_per_s": (s["newton_iters"] + it_init) / (gpu_ms * 1e-3), "gpu_s_per_run": gpu_ms * 1e-3,
+            "gpu_s_initial_condition": ms_init * 1e-3, "gpu_wall_s": wall, "saved_time_levels": int(res["x"].shape[1]),
+            "gpu_launches": s["launches"] + launches_init, "newton_iters": s["newton_iters"] + it_init,
+            "all_converged": bool(res["converged"].all()), "iters_equal": bool(iters_equal),
+            "cpu_newton_iters_per_s_1core": cpu_iters / dt, "cpu_s_per_instance_1core": dt / ns, "cpu_sample": ns,
+            "max_componentwise_rel_diff_final_state": err}
 
 
 def blades(nb, nelem, nev, m, cpu_sample):
@@ -119,9 +122,8 @@ def blades(nb, nelem, nev, m, cpu_sample):
     from oracle import pyoracle as O
     w = workloads.wind_turbine_blade_batch(nb, nelem)
     ctx = make_ctx(w, nb)
-    # ~1 % of the designs x speeds never reach ftol = 1e-9 (line search stagnates — identically in the CPU oracle, i.e. in the
-    # reference's algorithm); cap the Newton iterations so that they do not dominate the measurement and report the count
-    opts = api.make_opts(iterations=50, persistent=PERSISTENT)
+    # the reference's defaults (ftol = 1e-9, iterations = 1000); every design x speed of the generator converges (workloads.py)
+    opts = api.make_opts(persistent=PERSISTENT)
     ctx.steady_solve_resident(opts)
     ms, its = 0.0, 0
     for _ in range(3):
@@ -134,14 +136,14 @@ def blades(nb, nelem, nev, m, cpu_sample):
     ns = min(nb, cpu_sample)
     pk = O.Packed(w["start"], w["stop"], w["elems"][:ns], w["points_b"][:ns], w["pd"], w["pl"], w["bc"][:ns])
     dyns = [O.make_dyn(wb=w["motion"][b, 3:6]) for b in range(ns)]
-    t0 = time.perf_counter(); ref = O.steady_solve_batch(pk, ns, dyns, force_scaling=w["force_scaling"][:ns], iterations=50); dt = time.perf_counter() - t0
-    err = float(np.abs(res["x"][:ns] - ref["x"]).max() / np.abs(ref["x"]).max())
-    print(json.dumps({"workload": f"config 3: {nb} rotating blades x {nelem} elements (n={18 * nelem + 12}), steady_state_analysis + eigen (nev={nev}, m={m})",
+    t0 = time.perf_counter(); ref = O.steady_solve_batch(pk, ns, dyns, force_scaling=w["force_scaling"][:ns]); dt = time.perf_counter() - t0
+    err = state_error(res["x"][:ns], ref["x"], 1)
+    return ({"workload": f"config 3: {nb} rotating blades x {nelem} elements (n={18 * nelem + 12}), steady_state_analysis + eigen (nev={nev}, m={m})",
                       "steady_gpu_newton_iters_per_s": its / (ms * 1e-3), "steady_gpu_ms_per_batch": ms / 3, "steady_converged": int(res["converged"].sum()), "steady_converged_cpu_sample": int(ref["converged"].sum()),
                       "steady_cpu_newton_iters_per_s": float(ref["iters"].sum() / dt), "cpu_cores": O.num_threads(), "cpu_sample": ns,
-                      "steady_iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "steady_max_rel_diff": err,
+                      "steady_iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "steady_max_componentwise_rel_diff": err,
                       "eigen_device_s": es["ms_total"] * 1e-3, "eigen_wall_s_incl_host_ritz": t_eig, "eigen_max_ritz_residual": float(rr.max()),
-                      "lowest_freq_hz_first_instance": float(np.sort(np.abs(lam[0].imag))[0] / (2 * np.pi))}), flush=True)
+                      "lowest_freq_hz_first_instance": float(np.sort(np.abs(lam[0].imag))[0] / (2 * np.pi))})
 
 
 if __name__ == "__main__":
@@ -161,8 +163,8 @@ if __name__ == "__main__":
     globals()["SAVE_EVERY"] = a.gust_save_every
     ap2 = a
     if a.only in ("all", "steady"):
-        steady(a.steady_batch, 1024)
+        print(json.dumps(steady(a.steady_batch, 1024)), flush=True)
     if a.only in ("all", "gust"):
-        gust(a.gust_batch, a.gust_steps + 1, a.cpu_sample, init=a.gust_init)
+        print(json.dumps(gust(a.gust_batch, a.gust_steps + 1, a.cpu_sample, init=a.gust_init)), flush=True)
     if a.only in ("all", "blades"):
-        blades(a.blades_batch, a.blades_nelem, 20, 70, 256)
+        print(json.dumps(blades(a.blades_batch, a.blades_nelem, 20, 70, 256)), flush=True)

@@ -50,7 +50,8 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_set_motion", "gxb_static_solve", "gxb_steady_solve", "gxb_steady_solve_resident", "gxb_upload_x0",
            "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction",
            "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi",
-           "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors", "gxb_hint_no_gravity"]
+           "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors", "gxb_hint_no_gravity", "gxb_eigen_status", "gxb_set_bc_compact",
+           "gxb_multi_create", "gxb_multi_destroy", "gxb_multi_topology", "gxb_multi_set_batch", "gxb_multi_solve"]
 
 _lib = None
 
@@ -166,6 +167,15 @@ class Context:
         b = _f64(bc)
         assert b.size == self.nbatch * self.np * asm_mod.BC_STRIDE, "bc must be nbatch x np x 18"
         self._ck(self.lib.gxb_set_bc(self.h, _ptr(b)))
+
+    def set_bc_compact(self, base, point, field, values):
+        """base [np, 18] shared by the batch; values[b, k] -> field[k] (0..17) of point[k] (1-based): K doubles per instance cross PCIe."""
+        base = _f64(base); v = _f64(values)
+        assert base.size == self.np * asm_mod.BC_STRIDE and v.shape[0] == self.nbatch
+        pt = np.ascontiguousarray(point, dtype=np.int32); fd = np.ascontiguousarray(field, dtype=np.int32)
+        K = len(pt)
+        assert v.size == self.nbatch * K and len(fd) == K
+        self._ck(self.lib.gxb_set_bc_compact(self.h, _ptr(base), C.c_int32(K), _ptr(pt), _ptr(fd), _ptr(v)))
 
     def set_dloads(self, dl):
         d = _f64(dl)
@@ -310,12 +320,39 @@ class Context:
         self._ck(self.lib.gxb_eigen_arnoldi(self.h, C.byref(o), _ptr(x), C.c_int32(m), _ptr(H), _ptr(V)))
         return H, V
 
-    def eigenvalue_analysis(self, x, nev=6, m=None, opts=None, tol=1e-9, want_vectors=True):
+    def eigen_status(self):
+        s = np.zeros(self.nbatch, np.int32)
+        self._ck(self.lib.gxb_eigen_status(self.h, _ptr(s)))
+        return s.astype(bool)
+
+    def eigenvalue_analysis(self, x, nev=6, m=None, opts=None, tol=1e-9, want_vectors=True, max_m=None, strict=True):
         """solve_eigensystem (src/analyses.jl:943-965) at the linearisation states x: returns (lam [nb, nev] complex,
         vec [nb, n, nev] complex or None, resid [nb, nev] Ritz residual estimates relative to |mu|).
         The Krylov basis never leaves the GPU: the m x m Hessenberg eigenproblems are solved on the host (stacked LAPACK call), the
-        chosen eigenvectors go back and the Ritz vectors V y are formed on the device (gxb_eigen_ritz_vectors)."""
+        chosen eigenvectors go back and the Ritz vectors V y are formed on the device (gxb_eigen_ritz_vectors).
+
+        `tol` is enforced like `partialschur(...; tol = 1e-9)` (analyses.jl:954): if some instance's nev leading Ritz pairs have a
+        residual estimate above tol, the Krylov space is rebuilt twice as large (up to max_m, default min(n, 8 m)) until every
+        instance is under tol.  If that cannot be reached, or K is singular for some instance (`lu(K)` would throw), `strict` raises;
+        with strict = False the per-instance flags are left in `self.eigen_converged` / `self.eigen_singular`."""
         m = m or min(self.n, max(3 * nev + 10, 30))
+        max_m = min(self.n, max_m or 8 * m)
+        while True:
+            lam, vec, res, H = self._eigen_once(x, nev, m, opts, want_vectors)
+            sing = self.eigen_status()
+            ok = (res <= tol).all(axis=1) & ~sing
+            if ok.all() or sing.any() or m >= max_m:
+                break
+            m = min(2 * m, max_m)
+        self.eigen_converged, self.eigen_singular, self.eigen_m = ok, sing, m
+        if strict and sing.any():
+            raise GXBError(f"eigenvalue_analysis: K is singular for instances {np.nonzero(sing)[0][:8].tolist()} (lu(K) throws in the reference)")
+        if strict and not ok.all():
+            raise GXBError(f"eigenvalue_analysis: {int((~ok).sum())} instance(s) did not reach tol = {tol} with a Krylov space of {m} "
+                           f"(worst Ritz residual {float(res.max()):.2e}); pass a larger max_m or strict=False")
+        return lam, vec, res
+
+    def _eigen_once(self, x, nev, m, opts, want_vectors):
         H, _ = self.eigen_arnoldi(x, m, opts, want_basis=False)
         # stacked LAPACK dgeev, spread over host threads (numpy releases the GIL inside the gufunc loop)
         nth = max(1, min(os.cpu_count() or 1, 32, self.nbatch // 8))
@@ -336,7 +373,7 @@ class Context:
             Yc = np.ascontiguousarray(Y.astype(complex))
             vec = np.empty((self.nbatch, self.n, nev), complex)
             self._ck(self.lib.gxb_eigen_ritz_vectors(self.h, C.c_int32(nev), _ptr(Yc.view(np.float64)), _ptr(vec.view(np.float64))))
-        return lam, vec, res
+        return lam, vec, res, H
 
     # --- time marching ---
     def set_bc_series(self, point, field, values):
@@ -372,6 +409,64 @@ class Context:
         return p
 
     newton_direction = static_newton_direction
+
+
+class MultiContext:
+    """gxb_multi: one context + one host worker thread per GPU inside the library, contiguous shards, no collective."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        self.ngpu = len(dev)
+        rc = self.lib.gxb_multi_create(C.byref(self.h), C.c_int32(len(dev)), _ptr(dev))
+        if rc:
+            raise GXBError(f"gxbeam_b200 error {rc}: {self.lib.gxb_last_error().decode()}")
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GXBError(f"gxbeam_b200 error {rc}: {self.lib.gxb_last_error().decode()}")
+
+    def topology(self, start, stop, pd=None, pl=None, kind=0):
+        start = np.ascontiguousarray(start, dtype=np.int64); stop = np.ascontiguousarray(stop, dtype=np.int64)
+        ne = len(start); npnt = int(max(start.max(), stop.max()))
+        pd = None if pd is None else np.ascontiguousarray(pd, dtype=np.uint8)
+        pl = None if pl is None else np.ascontiguousarray(pl, dtype=np.uint8)
+        n = C.c_int64(0)
+        irp, icp, ire, ice = np.zeros(npnt, np.int64), np.zeros(npnt, np.int64), np.zeros(ne, np.int64), np.zeros(ne, np.int64)
+        self._ck(self.lib.gxb_multi_topology(self.h, int(kind), C.c_int64(npnt), C.c_int64(ne), _ptr(start), _ptr(stop), _ptr(pd), _ptr(pl),
+                                             C.byref(n), _ptr(irp), _ptr(ire), _ptr(icp), _ptr(ice)))
+        self.n, self.np, self.ne, self.kind = n.value, npnt, ne, int(kind)
+        self.indices = dict(nstates=n.value, irow_point=irp, irow_elem=ire, icol_point=icp, icol_elem=ice)
+        return self.indices
+
+    def set_batch(self, nbatch):
+        self._ck(self.lib.gxb_multi_set_batch(self.h, C.c_int64(nbatch)))
+        self.nbatch = nbatch
+
+    def solve(self, elems, bc, opts=None, points=None, dloads=None, pmass=None, gravity=None, force_scaling=None, motion=None, x0=None, out=None):
+        o = opts or make_opts()
+        nb, n = self.nbatch, self.n
+        out = out or {}
+        x = out.get("x") if out.get("x") is not None else np.empty((nb, n))
+        conv = out.get("converged") if out.get("converged") is not None else np.empty(nb, np.int32)
+        its = out.get("iters") if out.get("iters") is not None else np.empty(nb, np.int32)
+        rinf = out.get("resid_inf") if out.get("resid_inf") is not None else np.empty(nb)
+        ms = np.zeros(self.ngpu)
+        a = [_f64(v) for v in (elems, points, bc, dloads, pmass, gravity, force_scaling, motion, x0)]
+        self._ck(self.lib.gxb_multi_solve(self.h, C.byref(o), *[_ptr(v) for v in a], _ptr(x), _ptr(conv), _ptr(its), _ptr(rinf), _ptr(ms)))
+        return dict(x=x, converged=conv.astype(bool), iters=its, resid_inf=rinf, shard_ms=ms)
+
+    def close(self):
+        if self.h:
+            self.lib.gxb_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def blocks_to_dense(n, brow, bcol, Jblk):
@@ -414,9 +509,10 @@ class PipelinedSolver:
         self.pool = ThreadPoolExecutor(lanes)
         self.upload_lock = threading.Lock()
 
-    def solve(self, elements, prescribed_values, force_scaling, out, opts=None, gravity=None, points=None, motion=None):
+    def solve(self, elements, prescribed_values, force_scaling, out, opts=None, gravity=None, points=None, motion=None, bc_compact=None):
         """elements [nb, ne, 91], prescribed_values [nb, np, 18], force_scaling [nb]; out: dict of preallocated host arrays x [nb, n],
-        converged, iters (int32 [nb]), resid_inf [nb] (pinned memory makes the copies asynchronous).  nb must be a multiple of `chunk`."""
+        converged, iters (int32 [nb]), resid_inf [nb] (pinned memory makes the copies asynchronous).  nb must be a multiple of `chunk`.
+        bc_compact = (base [np, 18], point [K], field [K], values [nb, K]) replaces prescribed_values (gxb_set_bc_compact)."""
         nb = elements.shape[0]
         if nb % self.chunk:
             raise GXBError("PipelinedSolver.solve: the batch must be a multiple of the chunk size")
@@ -433,7 +529,10 @@ class PipelinedSolver:
                 # lane's Newton solve runs under the other lane's transfer instead of both alternating in lock-step
                 with self.upload_lock:
                     c.set_elements(elements[sl])
-                    c.set_bc(prescribed_values[sl])
+                    if bc_compact is not None:
+                        c.set_bc_compact(bc_compact[0], bc_compact[1], bc_compact[2], bc_compact[3][sl])
+                    else:
+                        c.set_bc(prescribed_values[sl])
                     if points is not None:
                         c.set_points(points[sl])
                     if motion is not None:
@@ -477,7 +576,7 @@ def _solve_shard(device, start, stop, pd, pl, elems, bc, dl, pm, grav, fs, x0, o
 
 def static_analysis_batch(start, stop, elements, prescribed_pd, prescribed_pl, prescribed_values, distributed_loads=None,
                           point_masses=None, gravity=None, force_scaling=None, x0=None, linear=False, two_dimensional=False,
-                          ftol=1e-9, iterations=1000, devices=(0,), profile=False) -> BatchResult:
+                          ftol=1e-9, iterations=1000, devices=(0,), profile=False, lu_parts=0) -> BatchResult:
     """Batched `static_analysis` (src/analyses.jl:66-179) over nbatch independent assemblies sharing a topology.
 
     elements: [nbatch, ne, 91]; prescribed_values: [nbatch, np, 18]; pd/pl: [np, 6]; distributed_loads: [nbatch, ne, 24] | None;
@@ -488,7 +587,7 @@ def static_analysis_batch(start, stop, elements, prescribed_pd, prescribed_pl, p
     elements = _f64(elements)
     nbatch = elements.shape[0]
     bc = _f64(prescribed_values).reshape(nbatch, -1, 18)
-    opts = make_opts(linear=linear, two_dimensional=two_dimensional, ftol=ftol, iterations=iterations, profile=profile)
+    opts = make_opts(linear=linear, two_dimensional=two_dimensional, ftol=ftol, iterations=iterations, profile=profile, lu_parts=lu_parts)
     fs = np.ones(nbatch) if force_scaling is None else _f64(force_scaling)
     bounds = np.linspace(0, nbatch, len(devices) + 1).astype(int)
     sl = [slice(bounds[i], bounds[i + 1]) for i in range(len(devices)) if bounds[i + 1] > bounds[i]]
@@ -498,8 +597,15 @@ def static_analysis_batch(start, stop, elements, prescribed_pd, prescribed_pl, p
     if len(args) == 1:
         outs = [_solve_shard(*args[0])]
     else:
-        with ThreadPoolExecutor(len(args)) as ex:
-            outs = list(ex.map(lambda a: _solve_shard(*a), args))
+        # several GPUs: the library's own multi-GPU entry (one worker thread + context per GPU inside the .so, gxb_multi_*)
+        mc = MultiContext([devices[i] for i in range(len(sl))])
+        try:
+            idx = mc.topology(start, stop, prescribed_pd, prescribed_pl)
+            mc.set_batch(nbatch)
+            r = mc.solve(elements, bc, opts, dloads=distributed_loads, pmass=point_masses, gravity=gravity, force_scaling=fs, x0=x0)
+        finally:
+            mc.close()
+        return BatchResult(r["x"], r["converged"], r["iters"], r["resid_inf"], idx, dict(shard_ms=r["shard_ms"].tolist()))
     x = np.concatenate([o[0]["x"] for o in outs])
     conv = np.concatenate([o[0]["converged"] for o in outs])
     its = np.concatenate([o[0]["iters"] for o in outs])

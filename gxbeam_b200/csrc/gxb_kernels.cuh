@@ -293,6 +293,8 @@ struct SolveArgs {
     // singular Jacobian: with `fallback` the instance is parked in ST_SINGULAR for k_singular_fallback (counter: unfinished instances of
     // the round, singular_seen: sticky flag the host reads with the counter); without it the instance fails (FAIL_SINGULAR)
     int fallback; int* counter; int* singular_seen;
+    // optional record of the factorisation for further right-hand sides (tensor-core kernel only): [nbatch][l_stride] doubles
+    double* Lst; size_t l_stride;
 };
 __device__ __forceinline__ void mark_singular(const SolveArgs& A, int64_t b) {
     if (A.fallback) {
@@ -313,12 +315,13 @@ template <int KLB, int KUB, int MMA = 0> __device__ void factor_instance(const S
     int bad;
     if constexpr (MMA) {       // window in DMMA fragments, 8-column elimination blocks (gxb_lu_mma.cuh); U rows are wider, n padded to 8
         using M = MmaShape<KLB, KUB>;
-        bad = warp_band_solve_mma<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * ((n + 7) & ~(size_t)7) * M::UW, p, A.nb, A.sign, sm);
+        bad = warp_band_solve_mma<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * ((n + 7) & ~(size_t)7) * M::UW, p, A.nb, A.sign, sm,
+                                            A.Lst ? A.Lst + b * A.l_stride : nullptr);
     } else {
         bad = warp_band_solve<KLB, KUB>(A.J + b * n * S::W, F, A.U + b * n * S::UW, p, A.nb, A.sign, sm);
     }
     __syncwarp();
-    if (A.direction_only == 1) return;
+    if (A.direction_only == 1) { if (bad && lane == 0) A.ns.failcode[b] = FAIL_SINGULAR; return; }     // the caller reads the flag (eigen path)
     if (bad) { if (lane == 0) { if (A.direction_only) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } else mark_singular(A, b); } return; }
     if (A.direction_only) return;        // 2: one of several solves of a Woodbury-corrected step (k_woodbury finishes it)
     linesearch_start(A, b);
@@ -382,6 +385,17 @@ __device__ void linesearch_start_cta(const SolveArgs& A, int64_t b) {
         A.ns.ls_k[b] = 0; A.ns.ls_finite[b] = 0; A.ns.status[b] = ST_TRIAL;
     }
 }
+// further right-hand sides with the factorisation recorded by k_factor_solve_mma (A.Lst): p = sign * (J \ F)
+template <int KLB, int KUB> __global__ void __launch_bounds__(128) k_resolve_mma(SolveArgs A) {
+    using S = MmaShape<KLB, KUB>;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= A.nbatch) return;
+    const size_t n = A.n;
+    warp_band_resolve_mma<KLB, KUB>(A.Lst + b * A.l_stride, A.F + b * n, A.U + b * ((n + 7) & ~(size_t)7) * S::UW, A.p + b * n, A.nb, A.sign,
+                                    smem + (size_t)warp * S::SM_DOUBLES);
+}
 // partitioned factorisation (gxb_lu_part.cuh): one CTA of PT warps per instance, static systems; for batches too small to fill the GPU
 // with one warp per instance
 // register budget: 12 warps per SM -> 170 registers per thread (the lane-per-row window + spike are 96 registers of state; capped at
@@ -401,7 +415,7 @@ template <int PT> __global__ void __launch_bounds__(32 * PT, GXB_PART_MINB(PT)) 
     linesearch_start_cta(A, b);
 }
 
-// NLsolve's singular-Jacobian fallback (newton.jl, restated in SURVEY App. C and oracle/gxb_solve.hpp:135-160): when the factorisation
+// NLsolve's singular-Jacobian fallback (newton.jl, restated in SURVEY App. C): when the factorisation
 // of J fails,   p = -(J'J + λ I) \ (J'F),   λ = 1e6 sqrt(n eps) ||J'J||_1.   A rare path -- clarity over speed: one CTA per parked
 // instance; M = J'J + λI (symmetric positive definite, cond <= ~3 because λ ~ 0.5 ||J'J||) is built in lower-band storage inside the
 // instance's U scratch and factorised as L D L' without pivoting, column by column.  Then the line search starts with the TRUE
@@ -766,18 +780,31 @@ __global__ void k_mass_matrix(MassArgs A) {
     put(9, 15, tt, true);        // rΩ rows: -θ_θ
 }
 
-// y = M v in row-block storage: one thread per row
-__global__ void k_rowblock_spmv(const double* __restrict__ Mrow, const double* __restrict__ v, double* __restrict__ y, int n, int W, int KLB,
-                                int64_t nbatch, int64_t vstride) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= nbatch * n) return;
-    const int64_t b = t / n; const int r = (int)(t % n);
-    const double* row = Mrow + (size_t)t * W;
-    const double* vb = v + b * vstride;
-    const int c0 = 6 * (r / 6 - KLB);
+// y = M v in row-block storage: 8 threads per row (W = 48: six doubles each, W = 30: four), so that a warp reads 4 consecutive rows as
+// one contiguous 1.5 KB piece; partial sums are combined by shuffles.  skip_stride > 0: rows r with r % skip_stride >= skip_from are
+// structurally zero and are not read (the element rows of the mass matrix: 6 of every 18, system.jl:961-995).
+__global__ void __launch_bounds__(256) k_rowblock_spmv(const double* __restrict__ Mrow, const double* __restrict__ v, double* __restrict__ y, int n, int W, int KLB,
+                                                       int64_t nbatch, int64_t vstride, int skip_stride, int skip_from) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t rg = t >> 3;                       // global row
+    const int part = (int)(t & 7);
+    const bool valid = rg < nbatch * n;
     double acc = 0.0;
-    for (int j = 0; j < W; j++) { const int c = c0 + j; if (c >= 0 && c < n) acc = fma(row[j], vb[c], acc); }
-    y[t] = acc;
+    int r = 0;
+    if (valid) {
+        const int64_t b = rg / n; r = (int)(rg % n);
+        if (!(skip_stride > 0 && r % skip_stride >= skip_from)) {
+            const int per = (W + 7) / 8;
+            const double* row = Mrow + (size_t)rg * W;
+            const double* vb = v + b * vstride;
+            const int c0 = 6 * (r / 6 - KLB);
+            for (int j = part * per; j < min(W, (part + 1) * per); j++) { const int c = c0 + j; if (c >= 0 && c < n) acc = fma(row[j], vb[c], acc); }
+        }
+    }
+    acc += __shfl_xor_sync(GXB_FULL, acc, 1);
+    acc += __shfl_xor_sync(GXB_FULL, acc, 2);
+    acc += __shfl_xor_sync(GXB_FULL, acc, 4);
+    if (valid && part == 0) y[rg] = acc;
 }
 
 // out[b][c][j] = sum_k Vk[b][k][c] * Y[b][k][j]  (Y complex): thread per state c, four eigenvectors per pass
@@ -820,39 +847,76 @@ __global__ void __launch_bounds__(256) k_arnoldi_start(double* __restrict__ Vk, 
     const double inv = 1.0 / sqrt(tot);
     for (int c = threadIdx.x; c < n; c += blockDim.x) v0[c] *= inv;
 }
+// Orthogonalisation of w = A v_j against v_0 .. v_j: classical Gram-Schmidt, h = V'w then w -= V h, repeated once when the DGKS criterion
+// ||w'|| < ||w|| / sqrt(2) detects cancellation -- what ArnoldiMethod.jl's `orthogonalize!` does (third party; partialschur is the
+// reference's eigen-solver, analyses.jl:951-954).  One CTA per instance; w is staged in shared memory, the basis is read twice per pass
+// (dots in chunks of 8 vectors with ONE block reduction per chunk, then the update), instead of four times by a two-sweep modified
+// Gram-Schmidt: the kernel is bound by the HBM traffic of the basis ((j + 1) n doubles per read).
 __global__ void __launch_bounds__(256) k_arnoldi_orth(double* __restrict__ Vk, double* __restrict__ H, const double* __restrict__ w_in, int n, int m, int j) {
+    extern __shared__ __align__(16) double orth_sm[];            // [n] w, then [m + 1] h
     const int b = blockIdx.x;
     double* V = Vk + (size_t)b * (m + 1) * n;
     double* Hb = H + (size_t)b * (m + 1) * m;
-    double* vn = V + (size_t)(j + 1) * n;            // work in place in the slot of v_{j+1}
+    double* vn = V + (size_t)(j + 1) * n;
     const double* w = w_in + (size_t)b * n;
-    __shared__ double red[8]; __shared__ double bc;
-    const int nw = blockDim.x >> 5;
-    auto block_sum = [&](double x) {
-        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(GXB_FULL, x, o);
+    double* ws = orth_sm;
+    double* hs = orth_sm + n;
+    __shared__ double red[8][8]; __shared__ double bc8[8];
+    const int nw = blockDim.x >> 5, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // sum of up to 8 values per thread over the CTA -> bc8[0..7]
+    auto block_sum8 = [&](double (&a)[8]) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) for (int o = 16; o; o >>= 1) a[q] += __shfl_xor_sync(GXB_FULL, a[q], o);
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x == 0) { double t = 0.0; for (int k = 0; k < nw; k++) t += red[k]; bc = t; }
-        __syncthreads();
-        return bc;
-    };
-    for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] = w[c];
-    // modified Gram-Schmidt, two sweeps (the second one only corrects round-off; its coefficients are added to H)
-    for (int sweep = 0; sweep < 2; sweep++)
-        for (int i = 0; i <= j; i++) {
-            const double* vi = V + (size_t)i * n;
-            double d = 0.0;
-            for (int c = threadIdx.x; c < n; c += blockDim.x) d = fma(vi[c], vn[c], d);
-            const double h = block_sum(d);
-            for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] = fma(-h, vi[c], vn[c]);
-            if (threadIdx.x == 0) Hb[(size_t)i * m + j] = (sweep == 0 ? 0.0 : Hb[(size_t)i * m + j]) + h;
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) red[wid][q] = a[q];
         }
-    double d = 0.0;
-    for (int c = threadIdx.x; c < n; c += blockDim.x) d = fma(vn[c], vn[c], d);
-    const double nrm = sqrt(block_sum(d));
+        __syncthreads();
+        if (threadIdx.x < 8) { double t = 0.0; for (int k = 0; k < nw; k++) t += red[k][threadIdx.x]; bc8[threadIdx.x] = t; }
+        __syncthreads();
+    };
+    double nrm0;
+    {
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = threadIdx.x; c < n; c += blockDim.x) { const double x = w[c]; ws[c] = x; a[0] = fma(x, x, a[0]); }
+        block_sum8(a);
+        nrm0 = sqrt(bc8[0]);
+    }
+    for (int i = threadIdx.x; i <= j; i += blockDim.x) hs[i] = 0.0;
+    double nrm = nrm0;
+    for (int pass = 0; pass < 2; pass++) {
+        // h = V' w, eight basis vectors per block reduction
+        for (int i0 = 0; i0 <= j; i0 += 8) {
+            double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int c = threadIdx.x; c < n; c += blockDim.x) {
+                const double x = ws[c];
+#pragma unroll
+                for (int q = 0; q < 8; q++) if (i0 + q <= j) a[q] = fma(V[(size_t)(i0 + q) * n + c], x, a[q]);
+            }
+            block_sum8(a);
+            if (threadIdx.x < 8 && i0 + threadIdx.x <= j) red[0][threadIdx.x] = bc8[threadIdx.x];      // keep this chunk's coefficients
+            __syncthreads();
+            // w -= V h for this chunk right away is NOT classical Gram-Schmidt (later dots would see the updated w): stash h, update below
+            if (threadIdx.x < 8 && i0 + threadIdx.x <= j) { hs[m + 1 + i0 + threadIdx.x] = red[0][threadIdx.x]; }
+            __syncthreads();
+        }
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = threadIdx.x; c < n; c += blockDim.x) {
+            double x = ws[c];
+            for (int i = 0; i <= j; i++) x = fma(-hs[m + 1 + i], V[(size_t)i * n + c], x);
+            ws[c] = x;
+            a[0] = fma(x, x, a[0]);
+        }
+        for (int i = threadIdx.x; i <= j; i += blockDim.x) hs[i] += hs[m + 1 + i];
+        block_sum8(a);
+        const double nrm_new = sqrt(bc8[0]);
+        const bool again = pass == 0 && nrm_new < 0.7071067811865476 * nrm;       // DGKS: uniform over the CTA
+        nrm = nrm_new;
+        if (!again) break;
+    }
+    for (int i = threadIdx.x; i <= j; i += blockDim.x) Hb[(size_t)i * m + j] = hs[i];
     if (threadIdx.x == 0) Hb[(size_t)(j + 1) * m + j] = nrm;
     const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
-    for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] *= inv;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) vn[c] = ws[c] * inv;
 }
-

@@ -19,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -65,6 +66,7 @@ struct gxb_ctx {
     bool have_initial = false;                            // d_x / d_rates0 hold the output of gxb_initial_condition
     int damping = 0;         // structural_damping of the current solve
     bool skip_mass = false;  // gxb_hint_no_gravity: static context, element mass / damping / midpoint fields are not uploaded
+    bool elems_compact = false;   // the last gxb_set_elements was a compact upload: d_elemS holds zeros in the mass / damping fields
     int mode = 0;            // 0: steady residual, 1: Newmark residual (set by the time-marching driver), 2: initial-condition residual
     double c2dt = 0.0;
     bool body_state = false;                          // some DOF has pd & pl (body-frame acceleration is a state, system.jl:138-150)
@@ -79,9 +81,23 @@ struct gxb_ctx {
     NewtonState ns{};
     int* d_counter = nullptr; int* h_counter = nullptr;
     bool have_x0 = false;
+    std::vector<int32_t> eig_singular;   // per instance: K's factorisation hit a zero pivot in the last gxb_eigen_arnoldi
     bool fallback_armed = false;      // a singular Jacobian was seen in this solve: k_singular_fallback follows every factorisation
     gxb_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr;   // evC: end of the last host->device copy
+};
+
+// Per-call device temporaries: freed on every exit path of the entry point that owns them (CK returns early on CUDA errors)
+struct DevTemps {
+    std::vector<void*> ptrs;
+    template <class T> cudaError_t alloc(T** p, size_t bytes) { cudaError_t e = cudaMalloc((void**)p, bytes); if (e == cudaSuccess) ptrs.push_back(*p); return e; }
+    void release(void* p) { for (auto& q : ptrs) if (q == p) q = nullptr; }      // ownership moves elsewhere
+    ~DevTemps() { for (void* q : ptrs) if (q) cudaFree(q); }
+};
+// context state that an entry point sets for the duration of one call
+struct ModeGuard {
+    gxb_ctx* c;
+    ~ModeGuard() { c->mode = 0; c->damping = 0; }
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -137,9 +153,10 @@ static int configure_kernels(int device, size_t* optin_out) {
     GXB_SMEM_MAX((k_assemble_dynamic<false, 0>)); GXB_SMEM_MAX((k_assemble_dynamic<false, 1>));
     GXB_SMEM_MAX(k_assemble_initial<true>); GXB_SMEM_MAX(k_assemble_initial<false>);
     GXB_SMEM_MAX((k_factor_solve<2, 2>)); GXB_SMEM_MAX((k_factor_solve<3, 4>));
-    GXB_SMEM_MAX((k_factor_solve_mma<2, 2>)); GXB_SMEM_MAX((k_factor_solve_mma<3, 4>));
+    GXB_SMEM_MAX((k_factor_solve_mma<2, 2>)); GXB_SMEM_MAX((k_factor_solve_mma<3, 4>)); GXB_SMEM_MAX((k_resolve_mma<3, 4>));
     GXB_SMEM_MAX(k_factor_solve_part<2>); GXB_SMEM_MAX(k_factor_solve_part<3>); GXB_SMEM_MAX(k_factor_solve_part<4>);
     GXB_SMEM_MAX(k_factor_solve_part<6>); GXB_SMEM_MAX(k_factor_solve_part<8>);
+    GXB_SMEM_MAX(k_arnoldi_orth);
     GXB_SMEM_MAX(k_persistent_dynamic<0>); GXB_SMEM_MAX(k_persistent_dynamic<1>); GXB_SMEM_MAX(k_persistent_dynamic<2>);
 #undef GXB_SMEM_MAX
     done[device] = (size_t)optin;
@@ -383,8 +400,10 @@ int gxb_set_elements(gxb_ctx* c, const double* elems) {
         CK(cudaEventRecord(c->evC, c->stream));
         k_pack_elements_compact<<<grid1(c->nbatch * c->ne, 128), 128, 0, c->stream>>>(c->d_stage, c->d_elemS, (int)c->ne, c->nbatch);
         CK(cudaGetLastError());
+        c->elems_compact = true;
         return wait_copy(c);
     }
+    c->elems_compact = false;
     int rc = stage_upload(c, elems, (size_t)c->nbatch * c->ne * GXB_ELEM_STRIDE * 8); if (rc) return rc;
     k_pack_elements<<<grid1(c->nbatch * c->ne, 128), 128, 0, c->stream>>>(c->d_stage, c->d_elemS, c->d_exS, (int)c->ne, c->nbatch);
     CK(cudaGetLastError());
@@ -452,7 +471,11 @@ int gxb_set_body(gxb_ctx* c, const double* gravity, const double* force_scaling)
     c->has_grav = 0;
     if (gravity) {
         for (int64_t i = 0; i < c->nbatch * 3; i++) if (gravity[i] != 0.0) { c->has_grav = 1; break; }
-        if (c->has_grav && c->skip_mass) { c->has_grav = 0; return fail(GXB_ERR_INVALID, "gxb_set_body: non-zero gravity after gxb_hint_no_gravity (the element mass was not uploaded)"); }
+        if (c->has_grav && (c->skip_mass || c->elems_compact)) {
+            c->has_grav = 0;
+            return fail(GXB_ERR_INVALID, "gxb_set_body: non-zero gravity, but the elements were uploaded under gxb_hint_no_gravity (the element mass was "
+                                         "not uploaded): switch the hint off and call gxb_set_elements again first");
+        }
         CK(cudaMemcpyAsync(c->d_grav, gravity, (size_t)c->nbatch * 24, cudaMemcpyHostToDevice, c->stream));
     } else CK(cudaMemsetAsync(c->d_grav, 0, (size_t)c->nbatch * 24, c->stream));
     if (force_scaling) {
@@ -615,10 +638,14 @@ static int after_factor(gxb_ctx* c, const gxb_opts* o, const SolveArgs& A, int d
     }
     return GXB_OK;
 }
-static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, double sign = -1.0) {
+static bool mma_enabled(const gxb_ctx* c) {
+    static const int mma_mask = []() { const char* e = getenv("GXB_LU_MMA"); return e ? atoi(e) : GXB_LU_MMA; }();
+    return (mma_mask & (c->kind == 0 ? 1 : 2)) != 0;
+}
+static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, double sign = -1.0, double* Lst = nullptr, size_t l_stride = 0) {
     if (c->nbody > 0 && !direction_only) return launch_factor_body(c, o);
     SolveArgs A{};
-    A.sign = sign;
+    A.sign = sign; A.Lst = Lst; A.l_stride = l_stride;
     A.nb = (int)(c->n / 6); A.n = (int)c->n; A.nbatch = c->nbatch;
     A.J = c->d_J; A.F = direction_only ? c->d_Ft : c->d_F; A.x = c->d_x; A.U = c->d_U; A.p = c->d_p; A.xt = c->d_xt; A.ns = c->ns;
     A.maxstep = o->maxstep; A.linear = o->linear; A.direction_only = direction_only;
@@ -876,10 +903,15 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     if ((x0 == nullptr) != (rates0 == nullptr)) return fail(GXB_ERR_INVALID, "gxb_newmark_run: give both x0 and the initial rates, or neither");
     if (!x0 && !c->have_initial) return fail(GXB_ERR_INVALID, "gxb_newmark_run: no initial state (pass x0 and rates0, or call gxb_initial_condition first)");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
+    if (c->ser_K && c->ser_nt < nt) return fail(GXB_ERR_INVALID, "gxb_newmark_run: the bc series has fewer time levels than tvec");
+    // every argument is validated before any allocation or state change
+    for (int64_t it = 1; it < nt; it++)
+        if (!(tvec[it] - tvec[it - 1] > 0.0)) return fail(GXB_ERR_INVALID, "gxb_newmark_run: tvec must be strictly increasing");
+    DevTemps tmp;
+    ModeGuard guard{c};                     // c->mode / c->damping are reset on every exit path
     c->damping = o.structural_damping ? 1 : 0;
     // linear=true: one lsolve! per step, about the current state (update_linearization) or about the initial state (analyses.jl:2741-2755)
     double* d_xlin = nullptr;
-    if (c->ser_K && c->ser_nt < nt) return fail(GXB_ERR_INVALID, "gxb_newmark_run: the bc series has fewer time levels than tvec");
     if (save_every < 1) save_every = 1;
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n, P = (size_t)c->np;
     const int64_t nsave = (nt - 1) / save_every + 1;      // time levels 0, save_every, 2 save_every, ...
@@ -887,10 +919,10 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     Prof prof{c, o.profile != 0};
     int rc;
     int *d_alive = nullptr, *d_steps = nullptr, *d_itot = nullptr; double* d_hist = nullptr;
-    CK(cudaMalloc(&d_alive, nb * 4)); CK(cudaMalloc(&d_steps, nb * 4)); CK(cudaMalloc(&d_itot, nb * 4));
-    if (x_hist) CK(cudaMalloc(&d_hist, nb * nsave * n * 8));
+    CK(tmp.alloc(&d_alive, nb * 4)); CK(tmp.alloc(&d_steps, nb * 4)); CK(tmp.alloc(&d_itot, nb * 4));
+    if (x_hist) CK(tmp.alloc(&d_hist, nb * nsave * n * 8));
     double* d_rhist = nullptr;
-    if (rates_hist) CK(cudaMalloc(&d_rhist, nb * nsave * P * 12 * 8));
+    if (rates_hist) CK(tmp.alloc(&d_rhist, nb * nsave * P * 12 * 8));
     k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(d_alive, 1, nb);
     k_fill_int<<<grid1(nb, 256), 256, 0, c->stream>>>(d_steps, 1, nb);
     CK(cudaMemsetAsync(d_itot, 0, nb * 4, c->stream));
@@ -903,7 +935,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     c->fallback_armed = false;
     CK(cudaMemsetAsync(c->d_counter, 0, 8, c->stream));
     if (o.linear && !o.update_linearization) {
-        CK(cudaMalloc(&d_xlin, nb * n * 8));
+        CK(tmp.alloc(&d_xlin, nb * n * 8));
         CK(cudaMemcpyAsync(d_xlin, c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
     CK(cudaMemsetAsync(c->d_paug, 0, nb * 12 * P * 8, c->stream));
@@ -911,15 +943,13 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     if (d_hist) k_save_state<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_x, d_hist, (int)n, nsave, 0, c->nbatch);
     if (d_rhist) k_save_rates<<<grid1(nb * P, 128), 128, 0, c->stream>>>(c->d_x, c->d_bcS, c->d_flags, c->d_paug, c->d_rates0, 0.0, (int)P, (int)n, nsave, 0, c->nbatch, d_rhist);
     c->mode = 1;
-    for (int64_t it = 1; it < nt; it++)
-        if (!(tvec[it] - tvec[it - 1] > 0.0)) { c->mode = 0; return fail(GXB_ERR_INVALID, "gxb_newmark_run: tvec must be strictly increasing"); }
     double* d_tvec = nullptr;
     const bool persistent = use_persistent(c, o, true);
     if (persistent) {
-        CK(cudaMalloc(&d_tvec, nt * 8));
+        CK(tmp.alloc(&d_tvec, nt * 8));
         CK(cudaMemcpyAsync(d_tvec, tvec, nt * 8, cudaMemcpyHostToDevice, c->stream));
         MarchBuffers mb; mb.nt = nt; mb.d_tvec = d_tvec; mb.alive = d_alive; mb.steps = d_steps; mb.itot = d_itot; mb.hist = d_hist; mb.rates_hist = d_rhist; mb.nsave = nsave; mb.save_every = save_every;
-        if ((rc = launch_persistent(c, o, 1, &mb))) { c->mode = 0; cudaFree(d_tvec); return rc; }
+        if ((rc = launch_persistent(c, o, 1, &mb))) return rc;
     }
     for (int64_t it = 1; it < nt && !persistent; it++) {
         const double dt = tvec[it] - tvec[it - 1];
@@ -930,7 +960,7 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
                                                            c->ns.status, c->ns.iters, c->ns.fcalls, d_alive);
         CK(cudaMemcpyAsync(c->d_xt, d_xlin ? d_xlin : c->d_x, nb * n * 8, cudaMemcpyDeviceToDevice, c->stream));   // initial guess = previous state (analyses.jl:3592)
         c->stats.launches += 1;
-        if ((rc = newton_rounds(c, o, prof, 2))) { c->mode = 0; return rc; }
+        if ((rc = newton_rounds(c, o, prof, 2))) return rc;
         k_step_end<<<grid1(nb, 256), 256, 0, c->stream>>>(c->ns.status, c->ns.iters, d_alive, d_steps, d_itot, c->nbatch);
         c->stats.launches += 1;
         if (d_hist && it % save_every == 0) { k_save_state<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_x, d_hist, (int)n, nsave, it / save_every, c->nbatch); c->stats.launches += 1; }
@@ -952,7 +982,6 @@ int gxb_newmark_run(gxb_ctx* c, const gxb_opts* opts, int64_t nt, const double* 
     if (steps_done) CK(cudaMemcpy(steps_done, d_steps, nb * 4, cudaMemcpyDeviceToHost));
     if (x_hist) CK(cudaMemcpy(x_hist, d_hist, nb * nsave * n * 8, cudaMemcpyDeviceToHost));
     if (rates_hist) CK(cudaMemcpy(rates_hist, d_rhist, nb * nsave * P * 12 * 8, cudaMemcpyDeviceToHost));
-    cudaFree(d_alive); cudaFree(d_steps); cudaFree(d_itot); cudaFree(d_hist); cudaFree(d_rhist); cudaFree(d_tvec); cudaFree(d_xlin);
     CK(cudaGetLastError());
     return GXB_OK;
 }
@@ -1152,22 +1181,39 @@ int gxb_eigen_arnoldi(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t
     c->mode = 0;
     int rc;
     double *d_V = nullptr, *d_H = nullptr;
+    DevTemps tmp;
+    ModeGuard guard{c};
     cudaFree(c->d_Vk); c->d_Vk = nullptr; c->vk_m = 0;
-    CK(cudaMalloc(&d_V, nb * (size_t)(m + 1) * n * 8));
-    CK(cudaMalloc(&d_H, nb * (size_t)(m + 1) * m * 8));
+    CK(tmp.alloc(&d_V, nb * (size_t)(m + 1) * n * 8));
+    CK(tmp.alloc(&d_H, nb * (size_t)(m + 1) * m * 8));
     CK(cudaMemsetAsync(d_H, 0, nb * (size_t)(m + 1) * m * 8, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     // K = steady Jacobian at x (steady_jacobian!, analyses.jl:1358), M = mass matrix at x (mass_matrix!, analyses.jl:1359)
     CK(cudaMemcpyAsync(c->d_x, x, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
     StaticArgs A = make_static_args(c, &o, c->d_x, c->d_F, true, 0, false);
-    if ((rc = launch_assemble(c, A, true))) { cudaFree(d_V); cudaFree(d_H); return rc; }
-    if ((rc = assemble_mass_matrix(c, o, c->d_x))) { cudaFree(d_V); cudaFree(d_H); return rc; }
+    if ((rc = launch_assemble(c, A, true))) return rc;
+    if ((rc = assemble_mass_matrix(c, o, c->d_x))) return rc;
     k_arnoldi_start<<<(unsigned)nb, 256, 0, c->stream>>>(d_V, (int)n, m);
+    // `Kfact = lu(K)` once (analyses.jl:948): the tensor-core factorisation records its multipliers in d_L during the first application;
+    // every further application of K^-1 replays them on the new right-hand side and back-substitutes (k_resolve_mma).  With the
+    // row-per-lane kernel (GXB_LU_MMA without bit 1) L is not recorded and every application factorises again.
+    double* d_L = nullptr;
+    const size_t l_stride = (size_t)(((n + 7) & ~(size_t)7) / 8) * GXB_MMA_LSTEP;
+    if (mma_enabled(c)) CK(tmp.alloc(&d_L, nb * l_stride * 8));
+    CK(cudaMemsetAsync(c->ns.failcode, 0, nb * 4, c->stream));
     for (int j = 0; j < m; j++) {
         // w = K^{-1} (M v_j)   (f! of analyses.jl:949)
-        k_rowblock_spmv<<<grid1(nb * n, 256), 256, 0, c->stream>>>(c->d_M, d_V + (size_t)j * n, c->d_Ft, (int)n, c->W, c->KLB, c->nbatch, (int64_t)(m + 1) * n);
-        if ((rc = launch_factor(c, &o, 1, 1.0))) { cudaFree(d_V); cudaFree(d_H); return rc; }
-        k_arnoldi_orth<<<(unsigned)nb, 256, 0, c->stream>>>(d_V, d_H, c->d_p, (int)n, m, j);
+        k_rowblock_spmv<<<grid1(nb * n * 8, 256), 256, 0, c->stream>>>(c->d_M, d_V + (size_t)j * n, c->d_Ft, (int)n, c->W, c->KLB, c->nbatch, (int64_t)(m + 1) * n, 18, 12);
+        if (d_L && j > 0) {
+            SolveArgs R{};
+            R.sign = 1.0; R.nb = (int)(c->n / 6); R.n = (int)c->n; R.nbatch = c->nbatch;
+            R.F = c->d_Ft; R.U = c->d_U; R.p = c->d_p; R.Lst = d_L; R.l_stride = l_stride;
+            const int wpc = 4;
+            k_resolve_mma<3, 4><<<grid1(c->nbatch, wpc), 32 * wpc, (size_t)wpc * MmaShape<3, 4>::SM_DOUBLES * 8, c->stream>>>(R);
+            CK(cudaGetLastError());
+            c->stats.launches++;
+        } else if ((rc = launch_factor(c, &o, 1, 1.0, d_L, l_stride))) return rc;
+        k_arnoldi_orth<<<(unsigned)nb, 256, (n + 2 * (size_t)(m + 1)) * 8, c->stream>>>(d_V, d_H, c->d_p, (int)n, m, j);
         c->stats.launches += 2;
     }
     CK(cudaGetLastError());
@@ -1176,9 +1222,21 @@ int gxb_eigen_arnoldi(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t
     if (V) CK(cudaMemcpyAsync(V, d_V, nb * (size_t)(m + 1) * n * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->stats.ms_total = ms;
-    c->damping = 0;
-    cudaFree(d_H);
+    {
+        std::vector<int> fc(nb);
+        CK(cudaMemcpy(fc.data(), c->ns.failcode, nb * 4, cudaMemcpyDeviceToHost));
+        c->eig_singular.assign(nb, 0);
+        for (size_t i = 0; i < nb; i++) c->eig_singular[i] = fc[i] == FAIL_SINGULAR;
+    }
+    tmp.release(d_V);
     c->d_Vk = d_V; c->vk_m = m;          // stays resident: gxb_eigen_ritz_vectors forms V y on the device
+    return GXB_OK;
+}
+
+int gxb_eigen_status(gxb_ctx* c, int32_t* singular) {
+    NEED_BATCH("gxb_eigen_status");
+    if (!singular || c->eig_singular.size() != (size_t)c->nbatch) return fail(GXB_ERR_INVALID, "gxb_eigen_status: call gxb_eigen_arnoldi first");
+    memcpy(singular, c->eig_singular.data(), (size_t)c->nbatch * 4);
     return GXB_OK;
 }
 
@@ -1192,14 +1250,14 @@ int gxb_eigen_ritz_vectors(gxb_ctx* c, int32_t nev, const double* Y, double* vec
     if (!Y || !vec || nev < 1 || nev > m) return fail(GXB_ERR_INVALID, "gxb_eigen_ritz_vectors: need Y, vec and 1 <= nev <= m");
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
     double *d_Y = nullptr, *d_out = nullptr;
-    CK(cudaMalloc(&d_Y, nb * m * nev * 16)); CK(cudaMalloc(&d_out, nb * n * nev * 16));
+    DevTemps tmp;
+    CK(tmp.alloc(&d_Y, nb * m * nev * 16)); CK(tmp.alloc(&d_out, nb * n * nev * 16));
     CK(cudaMemcpyAsync(d_Y, Y, nb * m * nev * 16, cudaMemcpyHostToDevice, c->stream));
     dim3 grid((unsigned)nb, (unsigned)((n + 127) / 128));
     k_ritz_vectors<<<grid, 128, 0, c->stream>>>(c->d_Vk, d_Y, d_out, (int)n, m, nev);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(vec, d_out, nb * n * nev * 16, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_Y); cudaFree(d_out);
     c->stats.launches += 1;
     return GXB_OK;
 }
@@ -1210,6 +1268,8 @@ int gxb_newton_direction(gxb_ctx* c, const gxb_opts* opts, const double* x, doub
     if (c->nbody > 0) return fail(GXB_ERR_UNSUPPORTED, "gxb_newton_direction: not available with body-frame acceleration states (use the solves)");
     gxb_opts o; if (opts) o = *opts; else gxb_default_opts(&o);
     const size_t nb = (size_t)c->nbatch, n = (size_t)c->n;
+    ModeGuard guard{c};
+    c->damping = (c->kind == 1 && o.structural_damping) ? 1 : 0;
     CK(cudaMemcpyAsync(c->d_xt, x, nb * n * 8, cudaMemcpyHostToDevice, c->stream));
     StaticArgs A = make_static_args(c, &o, c->d_xt, c->d_Ft, true, 0, false);
     int rc = launch_assemble(c, A, true); if (rc) return rc;
@@ -1217,6 +1277,127 @@ int gxb_newton_direction(gxb_ctx* c, const gxb_opts* opts, const double* x, doub
     CK(cudaMemcpyAsync(p, c->d_p, nb * n * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return GXB_OK;
+}
+
+
+// expand the shared base record and overwrite the K per-instance fields: bcS[b][f][p] layout
+__global__ void k_bc_compact(const double* __restrict__ base, const double* __restrict__ vals, const int* __restrict__ point, const int* __restrict__ field,
+                             int K, int P, int64_t nbatch, double* __restrict__ bcS) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * 18 * P) return;
+    const int p = (int)(t % P); const int64_t q = t / P; const int f = (int)(q % 18); const int64_t b = q / 18;
+    double v = base[p * 18 + f];
+    for (int k = 0; k < K; k++) if (point[k] == p && field[k] == f) v = vals[b * K + k];
+    bcS[t] = v;
+}
+
+int gxb_set_bc_compact(gxb_ctx* c, const double* base, int32_t K, const int32_t* point, const int32_t* field, const double* values) {
+    NEED_BATCH("gxb_set_bc_compact");
+    if (!base || K < 0 || (K > 0 && (!point || !field || !values))) return fail(GXB_ERR_INVALID, "gxb_set_bc_compact: bad arguments");
+    std::vector<int> pf(2 * (size_t)std::max(K, 1));
+    for (int k = 0; k < K; k++) {
+        if (point[k] < 1 || point[k] > c->np || field[k] < 0 || field[k] >= 18) return fail(GXB_ERR_INVALID, "gxb_set_bc_compact: point is 1-based, field in 0..17");
+        pf[k] = point[k] - 1; pf[K + k] = field[k];
+    }
+    const size_t nb = (size_t)c->nbatch, P = (size_t)c->np;
+    const size_t bytes = P * 18 * 8 + nb * K * 8 + 2 * (size_t)K * 4 + 64;
+    if (bytes > c->stage_bytes) { cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0; CK(cudaMalloc(&c->d_stage, bytes)); c->stage_bytes = bytes; }
+    double* d_base = c->d_stage; double* d_vals = d_base + P * 18; int* d_pf = reinterpret_cast<int*>(d_vals + nb * K);
+    CK(cudaMemcpyAsync(d_base, base, P * 18 * 8, cudaMemcpyHostToDevice, c->stream));
+    if (K) {
+        CK(cudaMemcpyAsync(d_vals, values, nb * K * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_pf, pf.data(), 2 * (size_t)K * 4, cudaMemcpyHostToDevice, c->stream));     // pageable: staged before the call returns
+    }
+    CK(cudaEventRecord(c->evC, c->stream));
+    k_bc_compact<<<grid1(nb * 18 * P, 256), 256, 0, c->stream>>>(d_base, d_vals, d_pf, d_pf + K, K, (int)P, c->nbatch, c->d_bcS);
+    CK(cudaGetLastError());
+    return wait_copy(c);
+}
+
+}  // extern "C"
+
+// ---- several GPUs of one box: one context + one worker thread per GPU, contiguous shards, no collective ----
+struct gxb_multi {
+    std::vector<gxb_ctx*> ctx;
+    std::vector<int64_t> off;          // shard b-range [off[g], off[g+1])
+    int kind = -1; int64_t np = 0, ne = 0, n = 0, nbatch = 0;
+};
+// run f(g) on one host thread per GPU; the first failure's code and message are reported
+template <class F> static int multi_fanout(gxb_multi* m, F&& f) {
+    const size_t G = m->ctx.size();
+    std::vector<int> rc(G, 0); std::vector<std::string> msg(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++)
+        th.emplace_back([&, g]() { rc[g] = f((int)g); if (rc[g]) msg[g] = g_err; });        // g_err is thread-local: copy it out
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < G; g++) if (rc[g]) return fail(rc[g], "GPU shard " + std::to_string(g) + ": " + msg[g]);
+    return GXB_OK;
+}
+extern "C" {
+
+int gxb_multi_create(gxb_multi** out, int32_t ngpu, const int32_t* device_ids) {
+    if (!out || ngpu < 1) return fail(GXB_ERR_INVALID, "gxb_multi_create: need ngpu >= 1");
+    gxb_multi* m = new gxb_multi();
+    for (int g = 0; g < ngpu; g++) {
+        gxb_ctx* c = nullptr;
+        int rc = gxb_create(&c, device_ids ? device_ids[g] : g);
+        if (rc) { for (auto* q : m->ctx) gxb_destroy(q); delete m; return rc; }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return GXB_OK;
+}
+void gxb_multi_destroy(gxb_multi* m) {
+    if (!m) return;
+    for (auto* c : m->ctx) gxb_destroy(c);
+    delete m;
+}
+int gxb_multi_topology(gxb_multi* m, int kind, int64_t np, int64_t ne, const int64_t* start, const int64_t* stop, const uint8_t* pd, const uint8_t* pl,
+                       int64_t* nstates, int64_t* irow_point, int64_t* irow_elem, int64_t* icol_point, int64_t* icol_elem) {
+    if (!m) return fail(GXB_ERR_INVALID, "gxb_multi_topology: null");
+    for (size_t g = 0; g < m->ctx.size(); g++) {
+        const bool first = g == 0;
+        int rc = gxb_topology(m->ctx[g], kind, np, ne, start, stop, pd, pl, first ? nstates : nullptr, first ? irow_point : nullptr,
+                              first ? irow_elem : nullptr, first ? icol_point : nullptr, first ? icol_elem : nullptr);
+        if (rc) return rc;
+    }
+    m->kind = kind; m->np = np; m->ne = ne; m->n = m->ctx[0]->n; m->nbatch = 0;
+    return GXB_OK;
+}
+int gxb_multi_set_batch(gxb_multi* m, int64_t nbatch) {
+    if (!m || m->kind < 0) return fail(GXB_ERR_INVALID, "gxb_multi_set_batch: call gxb_multi_topology first");
+    const int64_t G = (int64_t)m->ctx.size();
+    if (nbatch < G) return fail(GXB_ERR_INVALID, "gxb_multi_set_batch: fewer instances than GPUs");
+    m->off.assign(G + 1, 0);
+    for (int64_t g = 0; g <= G; g++) m->off[g] = nbatch * g / G;
+    int rc = multi_fanout(m, [&](int g) { return gxb_set_batch(m->ctx[g], m->off[g + 1] - m->off[g]); });
+    if (rc) return rc;
+    m->nbatch = nbatch;
+    return GXB_OK;
+}
+int gxb_multi_solve(gxb_multi* m, const gxb_opts* opts, const double* elems, const double* points, const double* bc, const double* dloads,
+                    const double* pmass, const double* gravity, const double* force_scaling, const double* motion, const double* x0,
+                    double* x, int32_t* converged, int32_t* iters, double* resid_inf, double* shard_ms) {
+    if (!m || m->nbatch < 1) return fail(GXB_ERR_INVALID, "gxb_multi_solve: call gxb_multi_set_batch first");
+    if (!elems || !bc) return fail(GXB_ERR_INVALID, "gxb_multi_solve: elems and bc are required");
+    const int64_t P = m->np, N = m->ne, n = m->n;
+    return multi_fanout(m, [&](int g) {
+        gxb_ctx* c = m->ctx[g];
+        const int64_t b0 = m->off[g];
+        int rc;
+        if ((rc = gxb_set_elements(c, elems + b0 * N * GXB_ELEM_STRIDE))) return rc;
+        if (m->kind == 1 && points && (rc = gxb_set_points(c, points + b0 * P * 3))) return rc;
+        if ((rc = gxb_set_bc(c, bc + b0 * P * 18))) return rc;
+        if ((rc = gxb_set_dloads(c, dloads ? dloads + b0 * N * 24 : nullptr))) return rc;
+        if ((rc = gxb_set_pmass(c, pmass ? pmass + b0 * P * 36 : nullptr))) return rc;
+        if ((rc = gxb_set_body(c, gravity ? gravity + b0 * 3 : nullptr, force_scaling ? force_scaling + b0 : nullptr))) return rc;
+        if (m->kind == 1 && (rc = gxb_set_motion(c, motion ? motion + b0 * 12 : nullptr))) return rc;
+        auto solve = m->kind == 0 ? gxb_static_solve : gxb_steady_solve;
+        rc = solve(c, opts, x0 ? x0 + b0 * n : nullptr, x ? x + b0 * n : nullptr, converged ? converged + b0 : nullptr, iters ? iters + b0 : nullptr,
+                   resid_inf ? resid_inf + b0 : nullptr);
+        if (!rc && shard_ms) shard_ms[g] = c->stats.ms_total;
+        return rc;
+    });
 }
 
 }  // extern "C"

@@ -80,11 +80,20 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
 
+template <int KLB, int KUB>
+__device__ void mma_back_substitute(const double* __restrict__ U, double* __restrict__ sol, int n, int nsteps, double sign, double* ring);
+
+// doubles of L storage per elimination step (optional, see Lst below): 8 negated effective multipliers + the pivot index for each of 32 lanes
+#define GXB_MMA_LSTEP (9 * 32)
+
 // Solve J y = rhs for one instance; writes sol = sign * y.  Returns 0, or 1 if an exactly-zero / non-finite pivot was hit.
 //   Jrow : [n][W] row-block storage      rhs : [n]      U : [n8][UW] scratch, n8 = n rounded up to 8      sol : [n]
+//   Lst  : NULL, or [n8 / 8][GXB_MMA_LSTEP]: the factorisation records, per step and row slot, the negated effective multipliers and
+//          which pivot the slot became, so that warp_band_resolve_mma can eliminate further right-hand sides without factorising again
+//          (the eigen operator K^-1 M applies one factorisation ~70 times, src/analyses.jl:948-951)
 template <int KLB, int KUB>
 __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double* __restrict__ rhs, double* __restrict__ U,
-                                   double* __restrict__ sol, int nb, double sign, double* sm) {
+                                   double* __restrict__ sol, int nb, double sign, double* sm, double* __restrict__ Lst = nullptr) {
     using S = MmaShape<KLB, KUB>;
     constexpr int W = S::W, RT = S::RT, CT = S::CT, SLOTS = S::SLOTS, BRW = S::BRW, HOFF = S::HOFF, PS = S::PS, AS = S::AS, ES = S::ES, RB = S::RB;
     constexpr int NSA = S::NSA, NSB = S::NSB;
@@ -290,6 +299,12 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
             slotkp[lane] = kp;
             slotnew[lane] = info;
         }
+        if (Lst) {
+            double* Ls = Lst + (size_t)s * GXB_MMA_LSTEP + lane;
+#pragma unroll
+            for (int k = 0; k < 8; k++) Ls[32 * k] = en[k];
+            Ls[32 * 8] = (double)kp;
+        }
         if (kp < 8) *reinterpret_cast<double2*>(U + (size_t)s * BRW + HOFF + kp * 10) = make_double2(b, myrinv);   // final rhs of the U row, 1/pivot
         __syncwarp();
         GXB_MTICK(3);
@@ -379,10 +394,33 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
     // an exactly-zero / sub-float-denormal pivot column (key without magnitude bits) or a non-finite 1/pivot
     const int bad = __any_sync(GXB_FULL, minkey < 32u) ? 1 : 0;
 
+    __syncwarp();
+    mma_back_substitute<KLB, KUB>(U, sol, n, nsteps, sign, ring);
+#ifdef GXB_LU_TIMING
+    if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && threadIdx.x == 0)
+        printf("[mma lu timing blk=%d steps=%d] cycles/step: prefetch %lld, transpose %lld, panel %lld, publish+e %lld, pubP %lld, dmma %lld, ustore %lld, newrows %lld | back-subst/block %lld\n",
+               blockIdx.x, nsteps, tph[0] / nsteps, tph[1] / nsteps, tph[2] / nsteps, tph[3] / nsteps, tph[4] / nsteps, tph[5] / nsteps, tph[6] / nsteps, tph[7] / nsteps,
+               (clock64() - tfac_end) / nsteps);
+#endif
+    // the shared memory is reused by the caller: retire the barrier objects
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NSB; q++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bars + q)) : "memory");
+    }
+    __syncwarp();
+    return bad;
+}
+
     // ---- back substitution, column-oriented over 8-blocks.  Row i needs x of the columns of its own block (the 8x8 triangle, solved
     // redundantly in every lane from the 80-byte heads staged in shared memory) and of the NT = CT-1 following blocks.  The lanes hold the
     // running sums of the 8 NT rows of the NT blocks below the one being solved: slot p of lane (q = lane / 8, k8 = lane % 8) owns row k8 of
     // the pending block congruent to q + 4 p mod NT; entries are prefetched NSET steps ahead straight from global memory into registers. ----
+template <int KLB, int KUB>
+__device__ void mma_back_substitute(const double* __restrict__ U, double* __restrict__ sol, int n, int nsteps, double sign, double* ring) {
+    using S = MmaShape<KLB, KUB>;
+    constexpr int CT = S::CT, BRW = S::BRW, HOFF = S::HOFF;
+    const int lane = threadIdx.x & 31;
     {
         constexpr int HS = S::HS, NSET = GXB_MMA_NSET, PD = GXB_MMA_PD, NT = CT - 1, PEND = (8 * NT + 31) / 32;
         __syncwarp();
@@ -485,18 +523,67 @@ __device__ int warp_band_solve_mma(const double* __restrict__ Jrow, const double
         }
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
-#ifdef GXB_LU_TIMING
-    if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && threadIdx.x == 0)
-        printf("[mma lu timing blk=%d steps=%d] cycles/step: prefetch %lld, transpose %lld, panel %lld, publish+e %lld, pubP %lld, dmma %lld, ustore %lld, newrows %lld | back-subst/block %lld\n",
-               blockIdx.x, nsteps, tph[0] / nsteps, tph[1] / nsteps, tph[2] / nsteps, tph[3] / nsteps, tph[4] / nsteps, tph[5] / nsteps, tph[6] / nsteps, tph[7] / nsteps,
-               (clock64() - tfac_end) / nsteps);
-#endif
-    // the shared memory is reused by the caller: retire the barrier objects
-    __syncwarp();
-    if (lane == 0) {
+}
+
+// Further right-hand sides with a recorded factorisation (Lst written by warp_band_solve_mma, U rows still in place): replays the
+// elimination of the right-hand side step by step -- pivot slots publish their b, every slot adds its recorded -e . b_pivot, pivot slots
+// write the final right-hand side of their U row, free slots take the incoming rows -- then back-substitutes.  sol = sign * (J \ rhs).
+template <int KLB, int KUB>
+__device__ void warp_band_resolve_mma(const double* __restrict__ Lst, const double* __restrict__ rhs, double* __restrict__ U,
+                                      double* __restrict__ sol, int nb, double sign, double* sm) {
+    using S = MmaShape<KLB, KUB>;
+    constexpr int SLOTS = S::SLOTS, BRW = S::BRW, HOFF = S::HOFF;
+    const int lane = threadIdx.x & 31;
+    const int n = 6 * nb, n8 = (n + 7) & ~7, nsteps = n8 >> 3;
+    double* pbs = sm;                                  // [8] right-hand sides of the step's pivot rows
+    double* ring = sm + S::SM_P + S::SM_E + S::SM_SLOT;
+    auto blocks_before = [&](int s) { const int r = KLB + 2 + s + s / 3; return r < nb ? r : nb; };
+    auto rows_of = [&](int bb) { return bb >= nb ? n8 : 6 * bb; };
+    double b = 0.0;
+    bool live = false;
+    {
+        const int r0 = rows_of(blocks_before(0));
+        if (lane < r0) { live = true; b = lane < n ? rhs[lane] : 0.0; }
+    }
+    int bb0 = blocks_before(0), bb1 = blocks_before(1);
+    double en[8], kpd;
+    auto load_l = [&](int s, double (&e)[8], double& k) {
+        const double* Ls = Lst + (size_t)s * GXB_MMA_LSTEP + lane;
 #pragma unroll
-        for (int q = 0; q < NSB; q++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bars + q)) : "memory");
+        for (int q = 0; q < 8; q++) e[q] = Ls[32 * q];
+        k = Ls[32 * 8];
+    };
+    load_l(0, en, kpd);
+    for (int s = 0; s < nsteps; s++) {
+        const int rin0 = rows_of(bb0), rin1 = rows_of(bb1);
+        // the incoming rows' right-hand sides and the next step's record are requested before this step's dependent chain
+        const double rnew = (rin0 + lane < rin1 && rin0 + lane < n) ? rhs[rin0 + lane] : 0.0;
+        double en_n[8], kpd_n = 8.0;
+        if (s + 1 < nsteps) load_l(s + 1, en_n, kpd_n);
+        const int kp = (int)kpd;
+        if (kp < 8) { pbs[kp] = b; live = false; }
+        __syncwarp();
+        {
+            double b2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                const double2 pb = *reinterpret_cast<const double2*>(pbs + k);
+                b = fma(en[k], pb.x, b); b2 = fma(en[k + 1], pb.y, b2);
+            }
+            b += b2;
+        }
+        if (kp < 8) U[(size_t)s * BRW + HOFF + kp * 10] = b;
+        const unsigned freem = __ballot_sync(GXB_FULL, !live) & ((SLOTS == 32) ? 0xffffffffu : ((1u << SLOTS) - 1u));
+        const int rank = __popc(freem & ((1u << lane) - 1u));
+        const double nbv = __shfl_sync(GXB_FULL, rnew, rank & 31);
+        if (!live && lane < SLOTS && rin0 + rank < rin1) { live = true; b = nbv; }
+        else if (!live) b = 0.0;
+        bb0 = bb1; bb1 = blocks_before(s + 2);
+#pragma unroll
+        for (int q = 0; q < 8; q++) en[q] = en_n[q];
+        kpd = kpd_n;
+        __syncwarp();
     }
     __syncwarp();
-    return bad;
+    mma_back_substitute<KLB, KUB>(U, sol, n, nsteps, sign, ring);
 }

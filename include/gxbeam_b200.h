@@ -182,15 +182,47 @@ int gxb_mass_matrix(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double*
 
 /* The Krylov part of solve_eigensystem (src/analyses.jl:943-965): K = steady Jacobian and M = mass matrix at the states x
  * (what eigenvalue_analysis! builds at src/analyses.jl:1358-1359), then m Arnoldi steps with the operator v -> K^{-1} (M v)
- * (the LinearMap `f!` of analyses.jl:949; every application re-runs the batched pivoted block-banded LU).
+ * (the LinearMap `f!` of analyses.jl:949).  K is factorised ONCE, like `Kfact = lu(K)` (analyses.jl:948): the first application records the
+ * multipliers of the batched pivoted block-banded LU, every further application replays them on the new right-hand side.
  * Outputs: H, nbatch x (m+1) x m row-major upper Hessenberg with H[j+1][j] the residual norms; V (may be NULL),
  * nbatch x (m+1) x nstates, the orthonormal Krylov basis.  The caller finishes like the reference: mu = eig(H[:m,:m]),
  * sort by (abs, imag) descending, lambda = -1/mu, eigenvectors V[:m]' y   (Julia: `eigen`, Python: numpy.linalg.eig). */
 int gxb_eigen_arnoldi(gxb_ctx* ctx, const gxb_opts* opts, const double* x, int32_t m, double* H, double* V);
+/* Per instance (nbatch flags): 1 if the factorisation of K in the last gxb_eigen_arnoldi hit an exactly-zero / non-finite pivot -- where
+ * the reference's `lu(K)` (src/analyses.jl:948) throws SingularException; that instance's H is meaningless. */
+int gxb_eigen_status(gxb_ctx* ctx, int32_t* singular);
 
 /* One Newton direction p = -(J(x) \ r(x)) per instance (the `linsolve` of analyses.jl:3585), for parity tests of the
  * batched pivoted block-banded LU in isolation.  p: nbatch x nstates. */
 int gxb_newton_direction(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* p);
+
+/* Compact upload of the prescribed conditions (the e2e path of design sweeps): a PrescribedConditions record is 18 doubles of which
+ * all but a handful are NaN / zero and identical across the batch (src/loads.jl:16-25, :94).  `base` (np x 18, shared by the batch, NaN
+ * where unused exactly like gxb_set_bc) is replicated on the device; `values` (nbatch x K) then overwrites field[k] (0..17: u, theta, F,
+ * M, Ff, Mf) of point[k] (1-based) per instance.  Equivalent to gxb_set_bc with the expanded array; K * 8 bytes per instance cross PCIe
+ * instead of np * 144. */
+int gxb_set_bc_compact(gxb_ctx* ctx, const double* base, int32_t K, const int32_t* point, const int32_t* field, const double* values);
+
+/* ---- one box, several GPUs: SURVEY 8(e) ----------------------------------------------------------------------------------------
+ * A gxb_multi owns one gxb_ctx and one host worker thread per GPU.  The batch is cut into contiguous shards (instances are
+ * independent: no collective, no peer traffic); every call fans out to the workers, each of which uploads ITS slice of the caller's
+ * host arrays and writes ITS slice of the caller's output arrays -- the "final host gather" is the caller's single array.
+ * Results are bit-identical to a single-GPU solve of the same batch (an instance never sees its neighbours) as long as opts.lu_parts is
+ * fixed: its automatic choice depends on the shard size, and different partitionings agree to round-off only. */
+typedef struct gxb_multi gxb_multi;
+int gxb_multi_create(gxb_multi** m, int32_t ngpu, const int32_t* device_ids);
+void gxb_multi_destroy(gxb_multi* m);
+/* gxb_topology on every GPU (outputs as there, may be NULL), then gxb_set_batch with the shard sizes */
+int gxb_multi_topology(gxb_multi* m, int kind, int64_t np, int64_t ne, const int64_t* start, const int64_t* stop, const uint8_t* pd,
+                       const uint8_t* pl, int64_t* nstates, int64_t* irow_point, int64_t* irow_elem, int64_t* icol_point,
+                       int64_t* icol_elem);
+int gxb_multi_set_batch(gxb_multi* m, int64_t nbatch);
+/* static_analysis (kind = 0) / steady_state_analysis (kind = 1) of the whole batch.  Arrays are the full-batch versions of the
+ * gxb_set_* / gxb_static_solve arguments; dloads, pmass, gravity, force_scaling, x0 may be NULL; points / motion are read for kind = 1
+ * only.  shard_ms (optional, ngpu doubles): device time of each shard's solve. */
+int gxb_multi_solve(gxb_multi* m, const gxb_opts* opts, const double* elems, const double* points, const double* bc, const double* dloads,
+                    const double* pmass, const double* gravity, const double* force_scaling, const double* motion, const double* x0,
+                    double* x, int32_t* converged, int32_t* iters, double* resid_inf, double* shard_ms);
 
 #ifdef __cplusplus
 }

@@ -125,3 +125,41 @@ def test_rotating_swept_tip_frequencies_against_experiment():
         f = freq[3 * j + 2]
         for row in exp_750:
             assert np.min(np.abs(f - row[j])) <= 0.1 * row[j], (sweeps[j], row[j], f)
+
+
+def test_c3_sample_eigenvalues_against_dense_oracle():
+    """BASELINE config 3 physics (fully populated wind-turbine 6x6 matrices, rotor-speed sweep) on a 40-element discretisation so that a
+    dense eigen-solve of the oracle's K and M is affordable: the nev = 20 eigenvalues of every instance at 1e-9.  The factorisation of K
+    is recorded once and replayed for every further Krylov step (k_resolve_mma), so this also pins the stored-L path."""
+    O = _oracle()
+    nb, nelem, nev = 8, 40, 20
+    w = workloads.wind_turbine_blade_batch(nb, nelem, nspeeds=8)
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    st = ctx.steady_solve()
+    assert st["converged"].all()
+    lam, vec, res = ctx.eigenvalue_analysis(st["x"], nev=nev, m=70)
+    ctx.close()
+    assert res.max() <= 1e-9
+    for b in range(nb):
+        pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
+        dyn = O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6])
+        K = O.steady_jacobian(pk, dyn, st["x"][b])
+        M = O.mass_matrix(pk, st["x"][b])
+        lam_ref, _ = O.eigenvalues_dense(K, M, nev)
+        for l in lam_ref[:nev - 1]:                    # the last one may be half of a conjugate pair cut at nev
+            assert np.min(np.abs(lam[b] - l)) <= 1e-9 * abs(l), (b, l)
+
+
+def test_eigen_tolerance_is_enforced_by_growing_the_krylov_space():
+    """`tol` of solve_eigensystem (partialschur(...; tol = 1e-9), analyses.jl:954): a Krylov space that is too small for nev converged
+    pairs is rebuilt larger until the Ritz residuals are under tol; with strict = True an unreachable tol raises instead of returning
+    unconverged pairs silently."""
+    nb, nev = 2, 12
+    w = workloads.rotating_blade_batch(nb, rpm_jitter=0.2)
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    st = ctx.steady_solve()
+    lam, _, res = ctx.eigenvalue_analysis(st["x"], nev=nev, m=16, want_vectors=False)
+    assert ctx.eigen_m > 16 and res.max() <= 1e-9 and ctx.eigen_converged.all() and not ctx.eigen_singular.any()
+    with pytest.raises(api.GXBError, match="did not reach tol"):
+        ctx.eigenvalue_analysis(st["x"], nev=nev, m=16, max_m=16, want_vectors=False)
+    ctx.close()

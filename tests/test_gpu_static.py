@@ -403,3 +403,47 @@ def test_exact_dphi0_option_agrees_on_iteration_counts():
     assert a["converged"].all() and b["converged"].all()
     assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(b["iters"], ref["iters"])
     assert state_error(b["x"], ref["x"], 0) <= 1e-9 and state_error(a["x"], b["x"], 0) <= 1e-9
+
+
+def test_bc_compact_upload_is_equivalent_to_the_full_records():
+    """gxb_set_bc_compact: one shared np x 18 record + K per-instance values must leave exactly the bytes gxb_set_bc leaves (NaN pattern
+    included): the solves are bit-identical."""
+    w = workloads.cantilever_tipmoment_batch(40, 24, tip_force=True)
+    ctx = _ctx_for(w)
+    a = ctx.static_solve()
+    ctx.set_bc_compact(w["bc"][0], [25, 25], [11, 8], np.ascontiguousarray(w["bc"][:, 24, [11, 8]]))
+    b = ctx.static_solve()
+    with pytest.raises(api.GXBError, match="1-based"):
+        ctx.set_bc_compact(w["bc"][0], [0], [11], np.zeros((40, 1)))
+    ctx.close()
+    assert a["converged"].all() and np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["x"], b["x"])
+
+
+def test_multi_gpu_entry_is_bit_identical_to_one_gpu():
+    """gxb_multi_* (one context + worker thread per GPU inside the library): the sharded solve returns exactly the single-context
+    result.  With one visible GPU the two shards run as two contexts of the same device (same code path); under the 2-GPU lease they
+    run on devices 0 and 1."""
+    import ctypes
+    ndev = ctypes.c_int(0)
+    ctypes.CDLL("libcudart.so").cudaGetDeviceCount(ctypes.byref(ndev))
+    devices = (0, 1) if ndev.value >= 2 else (0, 0)
+    w = workloads.cantilever_tipmoment_batch(50, 40, tip_force=True)
+    # lu_parts fixed: the automatic choice depends on the shard size, and different partitionings agree to round-off only
+    one = api.static_analysis_batch(w["start"], w["stop"], w["elems"], w["pd"], w["pl"], w["bc"], force_scaling=w["force_scaling"], devices=(0,), lu_parts=4)
+    two = api.static_analysis_batch(w["start"], w["stop"], w["elems"], w["pd"], w["pl"], w["bc"], force_scaling=w["force_scaling"], devices=devices, lu_parts=4)
+    assert two.converged.all() and np.array_equal(one.iters, two.iters) and np.array_equal(one.x, two.x)
+    assert len(two.stats["shard_ms"]) == 2 and all(t > 0 for t in two.stats["shard_ms"])
+    # steady_state_analysis through the same entry
+    wb = workloads.rotating_blade_batch(6, rpm_jitter=0.3)
+    mc = api.MultiContext(devices)
+    mc.topology(wb["start"], wb["stop"], wb["pd"], wb["pl"], kind=1)
+    mc.set_batch(6)
+    r2 = mc.solve(wb["elems"], wb["bc"], points=wb["points_b"], force_scaling=wb["force_scaling"], motion=wb["motion"])
+    mc.close()
+    ctx = api.Context(0)
+    ctx.topology(wb["start"], wb["stop"], wb["pd"], wb["pl"], kind=1)
+    ctx.set_batch(6)
+    ctx.set_elements(wb["elems"]); ctx.set_points(wb["points_b"]); ctx.set_bc(wb["bc"]); ctx.set_body(None, wb["force_scaling"]); ctx.set_motion(wb["motion"])
+    r1 = ctx.steady_solve()
+    ctx.close()
+    assert r2["converged"].all() and np.array_equal(r1["iters"], r2["iters"]) and np.array_equal(r1["x"], r2["x"])
