@@ -174,6 +174,18 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local)
+    # N ranks share one host: give every rank its own slice of the cores (its lane threads, the CUDA driver's threads and its NCCL
+    # proxy thread then stop migrating across the other ranks' cores).  One rank: leave the scheduler alone.
+    affinity = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            affinity = [mine[0], mine[-1]]
+        except OSError:
+            affinity = None
     dist = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -378,6 +390,7 @@ def main():
                        "instances_per_gpu": nb, "instances_total": nb * world,
                        "nstates": n, "ftol": 1e-9, "seed": "1236" if args.scaling == "strong" else "1236 + 1000*rank",
                        "parallelism": f"instances sharded over {world} GPU(s), no collective",
+                       "host_core_range_rank0": affinity,
                        "newton_iteration_counts": "parity unpinned against NLsolve itself (its source is not in the reference tree); "
                                                   "GPU == oracle port on every instance (cpu_baseline.iters_equal_to_gpu)",
                        "l2": "inputs + Jacobian/U working set (~2.6 GB per step) exceed the 126 MB L2; no explicit flush",
