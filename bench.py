@@ -137,10 +137,39 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-# dominant kernel and its committed `ncu --set full` summary: the tensor-core factorisation unless GXB_LU_MMA=0 selects the row-per-lane one
-_MMA = os.environ.get("GXB_LU_MMA", "1") != "0"
-FACTOR_KERNEL = "k_factor_solve_mma<2,2>" if _MMA else "k_factor_solve<2,2>"
-FACTOR_PROFILE = "r1_v7_prof_factor_mma_raw.csv" if _MMA else "r1_v5_prof_factor_raw.csv"
+# dominant kernel and its committed `ncu --set full` summary: the tensor-core factorisation (one warp per instance) for large per-GPU
+# batches, the partitioned one for small ones.  profiles/r2_prof_meta.json records which source files each capture was taken from: a
+# capture whose sources have changed since is reported as stale (traffic = null) instead of being quoted.
+def dominant_kernel(nb, forced=0, sm_count=148):
+    """mirrors choose_parts() of gxbeam_b200/csrc/gxb_lib.cu"""
+    want = forced if forced > 0 else (12 * sm_count) // nb
+    for cand in (8, 6, 4, 3, 2):
+        if cand <= want:
+            return f"k_factor_solve_part<{cand}>", "r2_prof_factor_part_raw.csv"
+    if os.environ.get("GXB_LU_MMA", "1") == "0":
+        return "k_factor_solve<2,2>", "r1_v5_prof_factor_raw.csv"
+    return "k_factor_solve_mma<2,2>", "r2_prof_factor_mma_raw.csv"
+
+
+def capture_traffic(profile, kernel, nb):
+    """(DRAM bytes per launch, GB/s in the capture, note) from the committed ncu summary, or (None, None, why)."""
+    import csv
+    import hashlib
+    try:
+        meta = json.load(open(os.path.join(ROOT, "profiles", "r2_prof_meta.json"))).get(profile)
+        if meta:
+            if meta["kernel"] != kernel or meta["instances_in_launch"] != nb:
+                return None, None, f"no capture of {kernel} at {nb} instances per launch (committed: {meta['kernel']} at {meta['instances_in_launch']})"
+            for f, h in meta["sources"].items():
+                if hashlib.sha1(open(os.path.join(ROOT, f), "rb").read()).hexdigest() != h:
+                    return None, None, f"capture profiles/{profile} is stale: {f} changed since it was taken"
+        rows = {r[0]: r for r in csv.reader(open(os.path.join(ROOT, "profiles", profile))) if r}
+        v = {k: float(r[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "ms": 1e-3, "us": 1e-6}.get(r[1], 1.0) for k, r in rows.items()
+             if k.startswith("dram__bytes") or k == "gpu__time_duration.sum"}
+        t = v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"]
+        return t, t / v["gpu__time_duration.sum"] / 1e9, f"profiles/{profile} (sources unchanged since the capture)"
+    except Exception as e:
+        return None, None, f"capture unavailable: {e!r}"
 
 
 def main():
@@ -367,17 +396,9 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         B_it, F_it = algorithmic_bytes_per_iter(NELEM), algorithmic_flops_per_iter(NELEM)
         # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this command (first Newton round: one
-        # launch over all 4096 instances): dram__bytes_read.sum + dram__bytes_write.sum
-        traffic = capture_gbs = None
-        try:
-            import csv
-            rows = {r[0]: r for r in csv.reader(open(os.path.join(ROOT, "profiles", FACTOR_PROFILE))) if r}
-            vals = {k: float(r[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "ms": 1e-3, "us": 1e-6}.get(r[1], 1.0) for k, r in rows.items()
-                    if k.startswith("dram__bytes") or k == "gpu__time_duration.sum"}
-            traffic = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
-            capture_gbs = traffic / vals["gpu__time_duration.sum"] / 1e9
-        except Exception:
-            pass
+        # launch over the whole per-GPU batch): dram__bytes_read.sum + dram__bytes_write.sum
+        FACTOR_KERNEL, FACTOR_PROFILE = dominant_kernel(nb, args.lu_parts)
+        traffic, capture_gbs, traffic_src = capture_traffic(FACTOR_PROFILE, FACTOR_KERNEL, nb)
         fac_s = prof["ms_factor"] * 1e-3
         achieved = B_it * prof["newton_iters"] / fac_s / 1e9 if fac_s > 0 else None
         line = {
@@ -406,7 +427,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": FACTOR_KERNEL, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
-                         "traffic_note": f"bytes per full-batch launch (4096 instances) from profiles/{FACTOR_PROFILE}: the row-block Jacobian "
+                         "traffic_note": f"bytes per launch over the per-GPU batch ({nb} instances), {traffic_src}: the row-block Jacobian "
                                          "(incl. structural zeros) is read once, the U rows are written and read back once -- ~1.1 MB per instance and "
                                          "iteration, SURVEY 8d's figure for a Jacobian materialised in HBM; `achieved` uses the on-chip ideal of 109 KB",
                          "dram_gbs_in_capture": capture_gbs, "dram_frac_in_capture": (capture_gbs / hbm_peak) if capture_gbs else None,
@@ -416,10 +437,11 @@ def main():
                          "kernel_share_of_step": prof["ms_factor"] / prof["ms_total"] if prof["ms_total"] else None,
                          "fp64": {"algorithmic_flops_per_newton_iter": F_it,
                                   "achieved_tflops_whole_step": F_it * prof["newton_iters"] / (prof["ms_total"] * 1e-3) / 1e12 if prof["ms_total"] else None,
-                                  "nominal_peak_tflops": 37.0},
+                                  "measured_peak_tflops": {"dfma": 33.76, "dmma": 37.03, "source": "profiles/r2_fp64_peak_microbench.txt (1965 MHz, no throttle)"},
+                                  "frac_of_measured_dfma_peak_whole_step": (F_it * prof["newton_iters"] / (prof["ms_total"] * 1e-3) / 1e12 / 33.76) if prof["ms_total"] else None},
                          "ms_by_class": {k: prof[k] / args.steps for k in ("ms_assemble", "ms_factor", "ms_update", "ms_total")}},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # a reported baseline, rank 0 at N = 1 only (the N > 1 reference arm is --impl reference)
             from oracle import pyoracle as O
             cores = O.num_threads()
             sample = min(nb, 4096)
