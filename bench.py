@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: BASELINE configs[1]'s 4096 instances in total, sharded over the N GPUs; weak: 4096 per GPU")
     ap.add_argument("--e2e-lanes", type=int, default=0, help="contexts per GPU of the pipelined host-buffer path (0 = by batch size)")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks the pipelined host-buffer path cuts the per-GPU batch into (0 = one per lane)")
     ap.add_argument("--lu-parts", type=int, default=0, help="warps per instance of the partitioned factorisation (0 auto, 1 off, 2/4/8)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the time-boxed configs 1/3/4 measurements (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -343,9 +344,12 @@ def main():
     e2e_lanes = args.e2e_lanes or (4 if nb >= 2048 else (2 if nb >= 256 else 1))
     while nb % e2e_lanes:
         e2e_lanes -= 1
+    e2e_chunks = args.e2e_chunks or e2e_lanes
+    while nb % e2e_chunks:
+        e2e_chunks -= 1
     if e2e_lanes >= 1:
         ctx.close()
-        ps = api.PipelinedSolver(w["start"], w["stop"], w["pd"], w["pl"], nb // e2e_lanes, lanes=e2e_lanes, device=local, no_gravity=True)
+        ps = api.PipelinedSolver(w["start"], w["stop"], w["pd"], w["pl"], nb // e2e_chunks, lanes=e2e_lanes, device=local, no_gravity=True)
         # prescribed conditions in compact form (gxb_set_bc_compact): the 18-double PrescribedConditions records of this workload differ
         # between instances in the tip loads only (Mz, and Fz when present); everything else (NaN / zero, the root clamp) is one shared
         # np x 18 base record
@@ -367,7 +371,7 @@ def main():
         barrier()
         assert out["converged"].all()
         ps.close()
-        e2e_how = (f"wall clock around api.PipelinedSolver.solve ({e2e_lanes} chunks x {e2e_lanes} lanes, host threads), pinned host buffers in "
+        e2e_how = (f"wall clock around api.PipelinedSolver.solve ({e2e_chunks} chunks on {e2e_lanes} lanes, host threads), pinned host buffers in "
                    "the reference's Element layout; no-gravity hint: 49 of 91 doubles per element are fetched (strided copies); prescribed "
                    "conditions as one shared np x 18 record + 2 per-instance values (gxb_set_bc_compact)")
     else:

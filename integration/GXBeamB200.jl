@@ -1,7 +1,8 @@
 # GXBeamB200.jl — Julia glue a GXBeam maintainer would add next to src/analyses.jl.
 #
 # It leaves the public API intact (Assembly, PrescribedConditions, DistributedLoads, PointMass, static_analysis,
-# AssemblyState) and adds one batched entry point, `static_analysis_batch`, that packs the inputs of many independent
+# AssemblyState) and adds batched entry points (`static_analysis_batch`, `steady_state_analysis_batch`, `eigenvalue_analysis_batch`,
+# `time_domain_analysis_batch`, `static_analysis_multi_gpu`) that pack the inputs of many independent
 # assemblies sharing a topology, `ccall`s libgxbeam_b200.so (include/gxbeam_b200.h), and rebuilds one AssemblyState per
 # instance with the *existing* constructor (src/output.jl:106).
 #
@@ -9,7 +10,7 @@
 # C symbols are exercised by the Python ctypes binding (gxbeam_b200/api.py) in tests/ and bench.py.
 module GXBeamB200
 
-using GXBeam, StaticArrays
+using GXBeam, StaticArrays, LinearAlgebra
 
 const LIB = get(ENV, "GXBEAM_B200_LIB", "libgxbeam_b200.so")
 
@@ -181,6 +182,165 @@ function time_domain_analysis_batch(assemblies::Vector{<:Assembly}, tvec;
         return xh, dxh, (conv0 .!= 0) .& (conv .!= 0)
     finally
         ccall((:gxb_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
+    end
+end
+
+# ---- shared set-up of a kind = 1 (DynamicSystem) context: topology, batch, elements, points, conditions, body motion ----
+function dynamic_context(assemblies, prescribed_conditions, point_masses, gravity, linear_velocity, angular_velocity,
+        linear_acceleration, angular_acceleration, device)
+    nb = length(assemblies); a1 = assemblies[1]
+    np, ne = length(a1.points), length(a1.elements)
+    start = collect(Int64, a1.start); stop = collect(Int64, a1.stop)
+    pd, pl, _ = pack_conditions(np, prescribed_conditions[1])
+    bc = Array{Float64}(undef, 18, np, nb)
+    for i in 1:nb
+        pdi, pli, bci = pack_conditions(np, prescribed_conditions[i])
+        (pdi == pd && pli == pl) || error("all instances of a batch must share the pd/pl pattern")
+        bc[:, :, i] .= bci
+    end
+    elems = pack_elements(assemblies)
+    pts = reduce(vcat, [reinterpret(Float64, a.points) for a in assemblies])
+    fs = [GXBeam.default_force_scaling(a) for a in assemblies]
+    motion = reduce(hcat, [vcat(linear_velocity[i], angular_velocity[i], linear_acceleration[i], angular_acceleration[i]) for i in 1:nb])
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gxb_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), ctx, device))
+    nstates = Ref{Int64}(0)
+    check(ccall((:gxb_topology, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+        ctx[], 1, np, ne, start, stop, pd, pl, nstates, C_NULL, C_NULL, C_NULL, C_NULL))
+    check(ccall((:gxb_set_batch, LIB), Cint, (Ptr{Cvoid}, Int64), ctx[], nb))
+    check(ccall((:gxb_set_elements, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], elems))
+    check(ccall((:gxb_set_points, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], pts))
+    check(ccall((:gxb_set_bc, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], bc))
+    if point_masses !== nothing
+        pm = zeros(36, np, nb)
+        for i in 1:nb, (ip, m) in point_masses[i]
+            pm[:, ip, i] .= vec(m.mass)
+        end
+        check(ccall((:gxb_set_pmass, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], pm))
+    end
+    check(ccall((:gxb_set_body, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx[], reduce(hcat, gravity), fs))
+    check(ccall((:gxb_set_motion, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], motion))
+    return ctx, nstates[], fs
+end
+
+"""
+    steady_state_analysis_batch(assemblies; prescribed_conditions, point_masses, gravity, linear_velocity, angular_velocity,
+        linear_acceleration, angular_acceleration, structural_damping, two_dimensional, ftol, iterations, device, keep_context)
+        -> (states::Vector{AssemblyState}, converged::Vector{Bool}, iters, x)
+
+Batched counterpart of `steady_state_analysis` (src/analyses.jl:300-520): `gxb_steady_solve` runs `nlsolve!` (:3556) on the
+`steady_system_residual!/jacobian!` pair (src/system.jl:427-455, 693-720) of every instance.  `x[:, i]` is instance i's DynamicSystem
+state vector, fed to the EXISTING `AssemblyState(x, system, assembly; prescribed_conditions)` (src/output.jl:106).
+"""
+function steady_state_analysis_batch(assemblies::Vector{<:Assembly};
+        prescribed_conditions, point_masses=nothing, gravity=[zeros(3) for _ in assemblies],
+        linear_velocity=[zeros(3) for _ in assemblies], angular_velocity=[zeros(3) for _ in assemblies],
+        linear_acceleration=[zeros(3) for _ in assemblies], angular_acceleration=[zeros(3) for _ in assemblies],
+        structural_damping=false, two_dimensional=false, ftol=1e-9, iterations=1000, device=0, keep_context=false)
+    nb = length(assemblies)
+    ctx, n, fs = dynamic_context(assemblies, prescribed_conditions, point_masses, gravity, linear_velocity, angular_velocity,
+        linear_acceleration, angular_acceleration, device)
+    try
+        opts = Ref(Opts(0, two_dimensional, ftol, iterations, 1e6, 1e-4, 0.5, 0.1, 0, structural_damping, 0, 0, 0, 0))
+        x = Array{Float64}(undef, n, nb); conv = zeros(Int32, nb); iters = zeros(Int32, nb); rinf = zeros(nb)
+        check(ccall((:gxb_steady_solve, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Opts}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+            ctx[], opts, C_NULL, x, conv, iters, rinf))
+        states = map(1:nb) do i
+            system = DynamicSystem(assemblies[i]; force_scaling=fs[i])
+            AssemblyState(view(x, :, i), system, assemblies[i]; prescribed_conditions=prescribed_conditions[i])
+        end
+        keep_context && return states, conv .!= 0, iters, x, ctx, opts
+        return states, conv .!= 0, iters, x
+    finally
+        keep_context || ccall((:gxb_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
+    end
+end
+
+"""
+    eigenvalue_analysis_batch(assemblies; nev = 6, m = max(3nev + 10, 30), tol = 1e-9, kwargs...) -> (λ, V, converged)
+
+Batched counterpart of `eigenvalue_analysis` (src/analyses.jl:1180-1380): a steady-state analysis of every instance, then
+`solve_eigensystem` (:943-965) about each steady state.  The device builds K (steady Jacobian) and M (`system_mass_matrix!`,
+src/system.jl:961-995), factorises K once and runs m Arnoldi steps of v -> K^-1 (M v) (`gxb_eigen_arnoldi`); Julia finishes like
+the reference does -- `eigen` of the m x m Hessenberg matrices, sort by (abs, imag) descending (:956), λ = -1/μ -- and
+`gxb_eigen_ritz_vectors` forms the eigenvectors `Vk * F.vectors` (:959) on the device.  As with `partialschur(...; tol)` (:954), the
+Krylov space is rebuilt larger until the nev leading Ritz pairs of every instance have residual estimates under `tol`.
+λ: nev x nb, V: nstates x nev x nb (complex), converged: steady-state convergence flags.
+"""
+function eigenvalue_analysis_batch(assemblies::Vector{<:Assembly}; nev=6, m=max(3nev + 10, 30), tol=1e-9, kwargs...)
+    nb = length(assemblies)
+    _, conv, _, x, ctx, opts = steady_state_analysis_batch(assemblies; kwargs..., keep_context=true)
+    try
+        n = size(x, 1)
+        m = min(m, n); mmax = min(n, 8m)
+        while true
+            H = Array{Float64}(undef, m, m + 1, nb)            # row-major (m+1) x m per instance = column-major m x (m+1)
+            check(ccall((:gxb_eigen_arnoldi, LIB), Cint, (Ptr{Cvoid}, Ptr{Opts}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}),
+                ctx[], opts, x, m, H, C_NULL))
+            singular = zeros(Int32, nb)
+            check(ccall((:gxb_eigen_status, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx[], singular))
+            any(!=(0), singular) && throw(LinearAlgebra.SingularException(findfirst(!=(0), singular)))   # what `lu(K)` does at :948
+            λ = Array{ComplexF64}(undef, nev, nb); Y = Array{ComplexF64}(undef, nev, m, nb); worst = 0.0
+            for i in 1:nb
+                Hi = permutedims(view(H, :, :, i))             # (m+1) x m
+                F = eigen(Hi[1:m, :])
+                perm = sortperm(F.values, by=(μ) -> (abs(μ), imag(μ)), rev=true)[1:nev]
+                μ = F.values[perm]
+                λ[:, i] .= -1 ./ μ
+                Y[:, :, i] .= transpose(F.vectors[:, perm])    # Y[j, k, i]: the device wants nb x m x nev, nev fastest
+                worst = max(worst, maximum(abs.(Hi[m + 1, m] .* F.vectors[m, perm]) ./ abs.(μ)))
+            end
+            if worst <= tol || m >= mmax
+                V = Array{ComplexF64}(undef, nev, n, nb)       # nb x nstates x nev row-major
+                check(ccall((:gxb_eigen_ritz_vectors, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx[], nev, Y, V))
+                worst <= tol || @warn "eigenvalue_analysis_batch: tol = $tol not reached with a Krylov space of $m (worst Ritz residual $worst)"
+                return λ, permutedims(V, (2, 1, 3)), conv
+            end
+            m = min(2m, mmax)
+        end
+    finally
+        ccall((:gxb_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
+    end
+end
+
+"""
+    static_analysis_multi_gpu(assemblies, devices; prescribed_conditions, ...) -> (x, converged, iters)
+
+`static_analysis_batch` over several GPUs of one box through the library's own multi-GPU entry (`gxb_multi_*`): one context and one
+host worker thread per GPU live INSIDE the library, the batch is cut into contiguous shards, every worker reads its slice of these
+host arrays and writes its slice of `x` -- no Julia threads, no collective.
+"""
+function static_analysis_multi_gpu(assemblies::Vector{<:Assembly}, devices::Vector{<:Integer}; prescribed_conditions,
+        gravity=[zeros(3) for _ in assemblies], linear=false, two_dimensional=false, ftol=1e-9, iterations=1000)
+    nb = length(assemblies); a1 = assemblies[1]
+    np, ne = length(a1.points), length(a1.elements)
+    start = collect(Int64, a1.start); stop = collect(Int64, a1.stop)
+    pd, pl, _ = pack_conditions(np, prescribed_conditions[1])
+    bc = Array{Float64}(undef, 18, np, nb)
+    for i in 1:nb
+        bc[:, :, i] .= pack_conditions(np, prescribed_conditions[i])[3]
+    end
+    elems = pack_elements(assemblies)
+    fs = [GXBeam.default_force_scaling(a) for a in assemblies]
+    m = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gxb_multi_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Int32, Ptr{Int32}), m, length(devices), Int32.(devices)))
+    try
+        nstates = Ref{Int64}(0)
+        check(ccall((:gxb_multi_topology, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+            m[], 0, np, ne, start, stop, pd, pl, nstates, C_NULL, C_NULL, C_NULL, C_NULL))
+        check(ccall((:gxb_multi_set_batch, LIB), Cint, (Ptr{Cvoid}, Int64), m[], nb))
+        opts = Ref(Opts(linear, two_dimensional, ftol, iterations, 1e6, 1e-4, 0.5, 0.1, 0, 0, 0, 0, 0, 0))
+        x = Array{Float64}(undef, nstates[], nb); conv = zeros(Int32, nb); iters = zeros(Int32, nb); rinf = zeros(nb)
+        check(ccall((:gxb_multi_solve, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Opts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+            m[], opts, elems, C_NULL, bc, C_NULL, C_NULL, reduce(hcat, gravity), fs, C_NULL, C_NULL, x, conv, iters, rinf, C_NULL))
+        return x, conv .!= 0, iters
+    finally
+        ccall((:gxb_multi_destroy, LIB), Cvoid, (Ptr{Cvoid},), m[])
     end
 end
 
