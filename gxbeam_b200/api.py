@@ -50,7 +50,7 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_set_motion", "gxb_static_solve", "gxb_steady_solve", "gxb_steady_solve_resident", "gxb_upload_x0",
            "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction",
            "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi",
-           "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors", "gxb_hint_no_gravity", "gxb_eigen_status", "gxb_set_bc_compact",
+           "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors", "gxb_hint_no_gravity", "gxb_eigen_status", "gxb_set_bc_compact", "gxb_assembly_state", "gxb_eigen_arnoldi_left",
            "gxb_multi_create", "gxb_multi_destroy", "gxb_multi_topology", "gxb_multi_set_batch", "gxb_multi_solve"]
 
 _lib = None
@@ -227,6 +227,14 @@ class Context:
         self._ck(self.lib.gxb_fetch(self.h, _ptr(x), _ptr(conv), _ptr(its), _ptr(rinf)))
         return dict(x=x, converged=conv.astype(bool), iters=its, resid_inf=rinf)
 
+    def assembly_state(self, rates=None):
+        """PointState / ElementState records of the resident states: (points [nb, np, 30], elements [nb, ne, 30]); field order u, udot,
+        theta, thetadot, V, Vdot, Omega, Omegadot, F, M (the reference's struct layout)."""
+        pts = np.empty((self.nbatch, self.np, 30)); els = np.empty((self.nbatch, self.ne, 30))
+        r = None if rates is None else _f64(rates).reshape(self.nbatch, self.np, 12)
+        self._ck(self.lib.gxb_assembly_state(self.h, _ptr(r), _ptr(pts), _ptr(els)))
+        return pts, els
+
     def stats(self):
         st = Stats()
         self._ck(self.lib.gxb_get_stats(self.h, C.byref(st)))
@@ -352,6 +360,49 @@ class Context:
                            f"(worst Ritz residual {float(res.max()):.2e}); pass a larger max_m or strict=False")
         return lam, vec, res
 
+    def mass_times(self, x, vec, opts=None, chunk=64):
+        """M v for complex vectors vec [nb, n, k], M = system_mass_matrix! at the states x (device assembly, host product)."""
+        brow, bcol = self.pattern()
+        Mb = self.mass_matrix(x, opts).reshape(self.nbatch, -1, 3, 3)
+        out = np.zeros_like(vec)
+        cols = bcol[:, None] + np.arange(3)[None, :]
+        rows = (brow[:, None] + np.arange(3)[None, :]).ravel()
+        for b0 in range(0, self.nbatch, chunk):
+            sl = slice(b0, min(self.nbatch, b0 + chunk))
+            prod = np.einsum("bkij,bkjn->bkin", Mb[sl], vec[sl][:, cols, :])
+            acc = np.zeros((prod.shape[0], self.n, vec.shape[2]), complex)
+            np.add.at(acc, (slice(None), rows), prod.reshape(prod.shape[0], -1, vec.shape[2]))
+            out[sl] = acc
+        return out
+
+    def left_eigenvectors(self, x, lam, V, m=None, opts=None):
+        """left_eigenvectors(system, λ, V) (src/analyses.jl:966-1079): U [nb, nev, n] complex, row k the left eigenvector of λ_k, normalised
+        like the reference so that U M V = I.  The reference runs three passes of inverse iteration with a complex shifted factorisation
+        per mode; here the left eigenvectors come out of ONE Arnoldi process on the transposed pencil (gxb_eigen_arnoldi_left), are matched
+        to the given eigenvalues and scaled by 1 / (u_k' M v_k).  Returns (U, match) with match [nb, nev] = |λ_left - λ| / |λ| of the pairing."""
+        nb, nev = lam.shape
+        m = m or min(self.n, max(3 * nev + 10, 30))
+        o = opts or make_opts()
+        xs = _f64(x).reshape(nb, self.n)
+        H = np.empty((nb, m + 1, m))
+        self._ck(self.lib.gxb_eigen_arnoldi_left(self.h, C.byref(o), _ptr(xs), C.c_int32(m), _ptr(H), None))
+        mu, Y = np.linalg.eig(np.ascontiguousarray(H[:, :m, :m]))
+        lam_l = -1.0 / mu
+        order = np.zeros((nb, nev), int); match = np.zeros((nb, nev))
+        for b in range(nb):
+            free = np.ones(m, bool)
+            for k in range(nev):
+                d = np.where(free, np.abs(lam_l[b] - lam[b, k]), np.inf)
+                j = int(np.argmin(d))
+                order[b, k] = j; free[j] = False; match[b, k] = d[j] / abs(lam[b, k])
+        Yc = np.ascontiguousarray(np.take_along_axis(Y.astype(complex), order[:, None, :], 2))
+        Ul = np.empty((nb, self.n, nev), complex)
+        self._ck(self.lib.gxb_eigen_ritz_vectors(self.h, C.c_int32(nev), _ptr(Yc.view(np.float64)), _ptr(Ul.view(np.float64))))
+        MV = self.mass_times(xs, V, o)                                        # [nb, n, nev]
+        unorm = np.einsum("bnk,bnk->bk", Ul, MV)                              # u_k' M v_k (plain transpose: rows of U are conj(u) in the reference)
+        U = np.transpose(Ul / unorm[:, None, :], (0, 2, 1))
+        return np.ascontiguousarray(U), match
+
     def _eigen_once(self, x, nev, m, opts, want_vectors):
         H, _ = self.eigen_arnoldi(x, m, opts, want_basis=False)
         # stacked LAPACK dgeev, spread over host threads (numpy releases the GIL inside the gufunc loop)
@@ -467,6 +518,24 @@ class MultiContext:
             self.close()
         except Exception:
             pass
+
+
+def correlate_eigenmodes(Cm):
+    """correlate_eigenmodes(C) (src/analyses.jl:1114-1142), restated: for every row of the correlation matrix (C = U_p M V etc.) the
+    best-fitting mode that is not assigned yet, and the corruption index = largest magnitude not chosen / magnitude chosen.
+    Returns (perm, corruption), perm 0-based."""
+    Cm = np.asarray(Cm)
+    nev = Cm.shape[0]
+    perm = -np.ones(nev, int)
+    corruption = np.zeros(nev)
+    for i in range(nev):
+        tmp = np.abs(Cm[i])
+        ranked = np.argsort(-tmp, kind="stable")
+        i1 = next(j for j in ranked if j not in perm)
+        i2 = ranked[1] if i1 == ranked[0] else ranked[0]
+        perm[i] = i1
+        corruption[i] = tmp[i2] / tmp[i1]
+    return perm, corruption
 
 
 def blocks_to_dense(n, brow, bcol, Jblk):

@@ -272,6 +272,69 @@ __global__ void k_initial_output(double* __restrict__ x, const double* __restric
     xp[6] = V.x; xp[7] = V.y; xp[8] = V.z; xp[9] = Om.x; xp[10] = Om.y; xp[11] = Om.z;
 }
 
+// AssemblyState extraction on the device (src/output.jl:146-203 extract_point_state, :317-403 extract_element_state): one thread per
+// (instance, station) writes the PointState of point i and the ElementState of element i as 30 doubles each, in the field order of the
+// reference's structs (u, udot, theta, thetadot, V, Vdot, Omega, Omegadot, F, M), so that a Julia caller can reinterpret the arrays as
+// Vector{PointState{Float64}} / Vector{ElementState{Float64}}.  theta is returned as Wiener-Milenkovic parameters (θ · scaling,
+// output.jl:166-167).  rates ([b][NP][12]: udot, θdot, Vdot, Ωdot per point, the dx of newmark_output) may be null: zeros for a
+// StaticSystem, NaN for a DynamicSystem (the reference's FillArrays.Fill(NaN) for `AssemblyState(x, system, ...)`).
+struct StateArgs {
+    int kind, N, n; int64_t nbatch;
+    const double* x; const double* bcS; const unsigned short* flags; const double* fs; const double* rates;
+    double* points; double* elems;          // [b][NP][30], [b][N][30]
+};
+__global__ void __launch_bounds__(128) k_assembly_state(StateArgs A) {
+    const int N = A.N, NP = N + 1, stride = A.kind == 0 ? 12 : 18;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= A.nbatch * NP) return;
+    const int64_t b = t / NP; const int i = (int)(t % NP);
+    const double* x = A.x + b * A.n;
+    const double fs = A.fs[b];
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    struct P { v3 u, th, udot, thdot, V, Om, Vd, Od; };
+    auto point = [&](int p) {
+        P r;
+        const unsigned fl = A.flags[p];
+        const double* bc = A.bcS + ((size_t)b * 18) * NP + p;
+        const double* xp = x + (size_t)stride * p;
+        r.u = mk((fl & 1) ? bc[0] : xp[0], (fl & 2) ? bc[NP] : xp[1], (fl & 4) ? bc[2 * NP] : xp[2]);
+        r.th = mk((fl & 8) ? bc[3 * NP] : xp[3], (fl & 16) ? bc[4 * NP] : xp[4], (fl & 32) ? bc[5 * NP] : xp[5]);
+        r.V = r.Om = mk(0, 0, 0);
+        if (A.kind == 1) { r.V = mk(xp[6], xp[7], xp[8]); r.Om = mk(xp[9], xp[10], xp[11]); }
+        const double dflt = A.kind == 0 ? 0.0 : qnan;
+        double d[12];
+        for (int k = 0; k < 12; k++) d[k] = A.rates ? A.rates[((size_t)b * NP + p) * 12 + k] : dflt;
+        // point_displacement_rates (point.jl:265-281): zero where the displacement is prescribed
+        for (int k = 0; k < 6; k++) if ((fl >> k) & 1u) d[k] = 0.0;
+        r.udot = mk(d[0], d[1], d[2]); r.thdot = mk(d[3], d[4], d[5]); r.Vd = mk(d[6], d[7], d[8]); r.Od = mk(d[9], d[10], d[11]);
+        return r;
+    };
+    auto put = [&](double* o, v3 u, v3 ud, v3 th, v3 thd, v3 V, v3 Vd, v3 Om, v3 Od, v3 F, v3 M) {
+        const double s = rot_scaling(th);
+        const v3 a[10] = {u, ud, s * th, thd, V, Vd, Om, Od, F, M};
+        for (int k = 0; k < 10; k++) { o[3 * k] = a[k].x; o[3 * k + 1] = a[k].y; o[3 * k + 2] = a[k].z; }
+    };
+    const P p1 = point(i);
+    {
+        // point_loads (point.jl:20-39): prescribed load + follower part rotated by C(θ)', or the state variable times force_scaling
+        const unsigned fl = A.flags[i];
+        const double* bc = A.bcS + ((size_t)b * 18) * NP + i;
+        const double* xp = x + (size_t)stride * i;
+        const m3 C = rot_C(p1.th);
+        const v3 F = ldv(bc + 6 * NP, NP) + tmul(C, ldv(bc + 12 * NP, NP)), M = ldv(bc + 9 * NP, NP) + tmul(C, ldv(bc + 15 * NP, NP));
+        const v3 Fo = mk((fl & 64) ? F.x : xp[0] * fs, (fl & 128) ? F.y : xp[1] * fs, (fl & 256) ? F.z : xp[2] * fs);
+        const v3 Mo = mk((fl & 512) ? M.x : xp[3] * fs, (fl & 1024) ? M.y : xp[4] * fs, (fl & 2048) ? M.z : xp[5] * fs);
+        put(A.points + ((size_t)b * NP + i) * 30, p1.u, p1.udot, p1.th, p1.thdot, p1.V, p1.Vd, p1.Om, p1.Od, Fo, Mo);
+    }
+    if (i < N) {
+        const P p2 = point(i + 1);
+        const double* xe = x + (size_t)stride * i + (stride - 6);
+        const v3 F = mk(xe[0] * fs, xe[1] * fs, xe[2] * fs), M = mk(xe[3] * fs, xe[4] * fs, xe[5] * fs);
+        put(A.elems + ((size_t)b * N + i) * 30, 0.5 * (p1.u + p2.u), 0.5 * (p1.udot + p2.udot), 0.5 * (p1.th + p2.th), 0.5 * (p1.thdot + p2.thdot),
+            0.5 * (p1.V + p2.V), 0.5 * (p1.Vd + p2.Vd), 0.5 * (p1.Om + p2.Om), 0.5 * (p1.Od + p2.Od), F, M);
+    }
+}
+
 // xhist[b][slot][:] = x[b][:]
 __global__ void k_save_state(const double* __restrict__ x, double* __restrict__ xhist, int n, int64_t nsave, int64_t slot, int64_t nbatch) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -805,6 +868,21 @@ __global__ void __launch_bounds__(256) k_rowblock_spmv(const double* __restrict_
     acc += __shfl_xor_sync(GXB_FULL, acc, 2);
     acc += __shfl_xor_sync(GXB_FULL, acc, 4);
     if (valid && part == 0) y[rg] = acc;
+}
+
+// Transpose in row-block storage: in has block bandwidths KLB / KUB (row r: columns 6 (r/6 - KLB) ..), out has KUB / KLB.
+// One thread per stored entry of the output.
+__global__ void k_rowblock_transpose(const double* __restrict__ in, double* __restrict__ out, int n, int W, int KLB, int KUB, int64_t nbatch) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nbatch * n * W) return;
+    const int j = (int)(t % W); const int64_t q = t / W; const int r = (int)(q % n); const int64_t b = q / n;
+    const int c = 6 * (r / 6 - KUB) + j;                       // out[r][c] = in[c][r]
+    double v = 0.0;
+    if (c >= 0 && c < n) {
+        const int jj = r - 6 * (c / 6 - KLB);
+        if (jj >= 0 && jj < W) v = in[((size_t)b * n + c) * W + jj];
+    }
+    out[t] = v;
 }
 
 // out[b][c][j] = sum_k Vk[b][k][c] * Y[b][k][j]  (Y complex): thread per state c, four eigenvectors per pass

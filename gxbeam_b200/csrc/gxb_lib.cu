@@ -152,7 +152,7 @@ static int configure_kernels(int device, size_t* optin_out) {
     GXB_SMEM_MAX((k_assemble_dynamic<true, 0>)); GXB_SMEM_MAX((k_assemble_dynamic<true, 1>));
     GXB_SMEM_MAX((k_assemble_dynamic<false, 0>)); GXB_SMEM_MAX((k_assemble_dynamic<false, 1>));
     GXB_SMEM_MAX(k_assemble_initial<true>); GXB_SMEM_MAX(k_assemble_initial<false>);
-    GXB_SMEM_MAX((k_factor_solve<2, 2>)); GXB_SMEM_MAX((k_factor_solve<3, 4>));
+    GXB_SMEM_MAX((k_factor_solve<2, 2>)); GXB_SMEM_MAX((k_factor_solve<3, 4>)); GXB_SMEM_MAX((k_factor_solve<4, 3>));
     GXB_SMEM_MAX((k_factor_solve_mma<2, 2>)); GXB_SMEM_MAX((k_factor_solve_mma<3, 4>)); GXB_SMEM_MAX((k_resolve_mma<3, 4>));
     GXB_SMEM_MAX(k_factor_solve_part<2>); GXB_SMEM_MAX(k_factor_solve_part<3>); GXB_SMEM_MAX(k_factor_solve_part<4>);
     GXB_SMEM_MAX(k_factor_solve_part<6>); GXB_SMEM_MAX(k_factor_solve_part<8>);
@@ -999,6 +999,26 @@ int gxb_fetch(gxb_ctx* c, double* x, int32_t* converged, int32_t* iters, double*
     return GXB_OK;
 }
 
+int gxb_assembly_state(gxb_ctx* c, const double* rates, double* points, double* elements) {
+    NEED_BATCH("gxb_assembly_state");
+    if (!points || !elements) return fail(GXB_ERR_INVALID, "gxb_assembly_state: null output");
+    const size_t nb = (size_t)c->nbatch, P = (size_t)c->np, N = (size_t)c->ne;
+    DevTemps tmp;
+    double *d_rates = nullptr, *d_pts = nullptr, *d_el = nullptr;
+    CK(tmp.alloc(&d_pts, nb * P * 30 * 8)); CK(tmp.alloc(&d_el, nb * N * 30 * 8));
+    if (rates) { CK(tmp.alloc(&d_rates, nb * P * 12 * 8)); CK(cudaMemcpyAsync(d_rates, rates, nb * P * 12 * 8, cudaMemcpyHostToDevice, c->stream)); }
+    StateArgs A{};
+    A.kind = c->kind; A.N = (int)N; A.n = (int)c->n; A.nbatch = c->nbatch;
+    A.x = c->d_x; A.bcS = c->d_bcS; A.flags = c->d_flags; A.fs = c->d_fs; A.rates = d_rates; A.points = d_pts; A.elems = d_el;
+    k_assembly_state<<<grid1(nb * P, 128), 128, 0, c->stream>>>(A);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(points, d_pts, nb * P * 30 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(elements, d_el, nb * N * 30 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.launches += 1;
+    return GXB_OK;
+}
+
 int gxb_get_stats(gxb_ctx* c, gxb_stats* st) {
     if (!c || !st) return fail(GXB_ERR_INVALID, "gxb_get_stats: null");
     *st = c->stats;
@@ -1169,7 +1189,14 @@ int gxb_mass_matrix(gxb_ctx* c, const gxb_opts* opts, const double* x, double* M
     return GXB_OK;
 }
 
+static int eigen_arnoldi_impl(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t m, double* H, double* V, bool transposed);
 int gxb_eigen_arnoldi(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t m, double* H, double* V) {
+    return eigen_arnoldi_impl(c, opts, x, m, H, V, false);
+}
+int gxb_eigen_arnoldi_left(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t m, double* H, double* V) {
+    return eigen_arnoldi_impl(c, opts, x, m, H, V, true);
+}
+static int eigen_arnoldi_impl(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t m, double* H, double* V, bool transposed) {
     NEED_BATCH("gxb_eigen_arnoldi");
     if (c->kind != 1) return fail(GXB_ERR_INVALID, "gxb_eigen_arnoldi: context topology is not kind=1 (DynamicSystem)");
     if (!x || !H || m < 1 || m > c->n) return fail(GXB_ERR_INVALID, "gxb_eigen_arnoldi: need x, H and 1 <= m <= nstates");
@@ -1199,10 +1226,36 @@ int gxb_eigen_arnoldi(gxb_ctx* c, const gxb_opts* opts, const double* x, int32_t
     // row-per-lane kernel (GXB_LU_MMA without bit 1) L is not recorded and every application factorises again.
     double* d_L = nullptr;
     const size_t l_stride = (size_t)(((n + 7) & ~(size_t)7) / 8) * GXB_MMA_LSTEP;
-    if (mma_enabled(c)) CK(tmp.alloc(&d_L, nb * l_stride * 8));
+    // Left eigenvectors are the right eigenvectors of the transposed pencil (K', M'): the same Arnoldi process with K' and M' in
+    // row-block storage of swapped block bandwidths (4 / 3); K' goes through the row-per-lane factorisation (its window needs 30 row
+    // slots; the tensor-core kernel's fragment layout has no shape for it), which factorises on every application.
+    double *d_KT = nullptr, *d_MT = nullptr;
+    if (transposed) {
+        CK(tmp.alloc(&d_KT, nb * n * c->W * 8)); CK(tmp.alloc(&d_MT, nb * n * c->W * 8));
+        const int KUB = c->W / 6 - 1 - c->KLB;
+        k_rowblock_transpose<<<grid1(nb * n * c->W, 256), 256, 0, c->stream>>>(c->d_J, d_KT, (int)n, c->W, c->KLB, KUB, c->nbatch);
+        k_rowblock_transpose<<<grid1(nb * n * c->W, 256), 256, 0, c->stream>>>(c->d_M, d_MT, (int)n, c->W, c->KLB, KUB, c->nbatch);
+        CK(cudaGetLastError());
+        c->stats.launches += 2;
+    }
+    if (mma_enabled(c) && !transposed) CK(tmp.alloc(&d_L, nb * l_stride * 8));
     CK(cudaMemsetAsync(c->ns.failcode, 0, nb * 4, c->stream));
     for (int j = 0; j < m; j++) {
         // w = K^{-1} (M v_j)   (f! of analyses.jl:949)
+        if (transposed) {
+            const int KUB = c->W / 6 - 1 - c->KLB;
+            k_rowblock_spmv<<<grid1(nb * n * 8, 256), 256, 0, c->stream>>>(d_MT, d_V + (size_t)j * n, c->d_Ft, (int)n, c->W, KUB, c->nbatch, (int64_t)(m + 1) * n, 0, 0);
+            SolveArgs T{};
+            T.sign = 1.0; T.nb = (int)(c->n / 6); T.n = (int)c->n; T.nbatch = c->nbatch; T.direction_only = 1;
+            T.J = d_KT; T.F = c->d_Ft; T.x = c->d_x; T.U = c->d_U; T.p = c->d_p; T.xt = c->d_xt; T.ns = c->ns;
+            const int wpc = 4;
+            k_factor_solve<4, 3><<<grid1(c->nbatch, wpc), 32 * wpc, (size_t)wpc * LuShape<4, 3>::SM_DOUBLES * 8, c->stream>>>(T);
+            CK(cudaGetLastError());
+            c->stats.launches++; c->stats.n_factor++;
+            k_arnoldi_orth<<<(unsigned)nb, 256, (n + 2 * (size_t)(m + 1)) * 8, c->stream>>>(d_V, d_H, c->d_p, (int)n, m, j);
+            c->stats.launches += 2;
+            continue;
+        }
         k_rowblock_spmv<<<grid1(nb * n * 8, 256), 256, 0, c->stream>>>(c->d_M, d_V + (size_t)j * n, c->d_Ft, (int)n, c->W, c->KLB, c->nbatch, (int64_t)(m + 1) * n, 18, 12);
         if (d_L && j > 0) {
             SolveArgs R{};

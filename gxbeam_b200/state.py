@@ -70,3 +70,32 @@ def assembly_state(x, start, stop, icol_point, icol_elem, pd, pl, bc, force_scal
         eF[ie] = x[ic:ic + 3] * force_scaling
         eM[ie] = x[ic + 3:ic + 6] * force_scaling
     return AssemblyState(pu, pt, pF, pM, eu, et, eF, eM)
+
+
+def assembly_state_records(x, kind, pd, pl, bc, force_scaling, rates=None):
+    """The 30-double PointState / ElementState records of a chain (src/output.jl:18-28, 54-64, 146-203, 317-403), host-side numpy
+    restatement used by the tests of gxb_assembly_state.  x: nstates; pd/pl: [np, 6]; bc: [np, 18]; rates: [np, 12] or None."""
+    x = np.asarray(x, float)
+    stride = 12 if kind == 0 else 18
+    npnt = pd.shape[0]; ne = npnt - 1
+    pts = np.zeros((npnt, 30)); els = np.zeros((ne, 30))
+    raw = []
+    for ip in range(npnt):
+        xp = x[stride * ip:stride * ip + stride]
+        u = np.where(pd[ip, :3] != 0, bc[ip, 0:3], xp[0:3]); th = np.where(pd[ip, 3:] != 0, bc[ip, 3:6], xp[3:6])
+        C = get_C(th)
+        with np.errstate(invalid="ignore"):
+            F = bc[ip, 6:9] + C.T @ bc[ip, 12:15]; M = bc[ip, 9:12] + C.T @ bc[ip, 15:18]
+        F = np.where(pl[ip, :3] != 0, F, xp[0:3] * force_scaling); M = np.where(pl[ip, 3:] != 0, M, xp[3:6] * force_scaling)
+        V = xp[6:9] if kind == 1 else np.zeros(3); Om = xp[9:12] if kind == 1 else np.zeros(3)
+        d = np.full(12, 0.0 if kind == 0 else np.nan) if rates is None else np.array(rates[ip], float)
+        d[:6] = np.where(pd[ip] != 0, 0.0, d[:6])
+        raw.append((u, d[0:3], th, d[3:6], V, d[6:9], Om, d[9:12]))
+        pts[ip] = np.concatenate([u, d[0:3], th * rotation_parameter_scaling(th), d[3:6], V, d[6:9], Om, d[9:12], F, M])
+    for ie in range(ne):
+        a, b = raw[ie], raw[ie + 1]
+        avg = [(p + q) / 2 for p, q in zip(a, b)]
+        xe = x[stride * ie + stride - 6:stride * ie + stride]
+        avg[2] = avg[2] * rotation_parameter_scaling(avg[2])
+        els[ie] = np.concatenate(avg + [xe[0:3] * force_scaling, xe[3:6] * force_scaling])
+    return pts, els

@@ -188,6 +188,11 @@ int gxb_mass_matrix(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double*
  * nbatch x (m+1) x nstates, the orthonormal Krylov basis.  The caller finishes like the reference: mu = eig(H[:m,:m]),
  * sort by (abs, imag) descending, lambda = -1/mu, eigenvectors V[:m]' y   (Julia: `eigen`, Python: numpy.linalg.eig). */
 int gxb_eigen_arnoldi(gxb_ctx* ctx, const gxb_opts* opts, const double* x, int32_t m, double* H, double* V);
+/* The same Arnoldi process for the TRANSPOSED pencil, v -> K'^{-1} (M' v): its Ritz vectors are the left eigenvectors of the system,
+ * the rows of the matrix `U` of left_eigenvectors (src/analyses.jl:966-1079; the reference gets them by three passes of inverse
+ * iteration with a complex shifted factorisation per mode -- the same vectors up to the normalisation U M V = I, which the caller
+ * applies).  H, V and gxb_eigen_ritz_vectors as for gxb_eigen_arnoldi (the retained Krylov basis is replaced). */
+int gxb_eigen_arnoldi_left(gxb_ctx* ctx, const gxb_opts* opts, const double* x, int32_t m, double* H, double* V);
 /* Per instance (nbatch flags): 1 if the factorisation of K in the last gxb_eigen_arnoldi hit an exactly-zero / non-finite pivot -- where
  * the reference's `lu(K)` (src/analyses.jl:948) throws SingularException; that instance's H is meaningless. */
 int gxb_eigen_status(gxb_ctx* ctx, int32_t* singular);
@@ -195,6 +200,14 @@ int gxb_eigen_status(gxb_ctx* ctx, int32_t* singular);
 /* One Newton direction p = -(J(x) \ r(x)) per instance (the `linsolve` of analyses.jl:3585), for parity tests of the
  * batched pivoted block-banded LU in isolation.  p: nbatch x nstates. */
 int gxb_newton_direction(gxb_ctx* ctx, const gxb_opts* opts, const double* x, double* p);
+
+/* AssemblyState(x, system, assembly; prescribed_conditions) on the device (src/output.jl:106, extract_point_state :146-203,
+ * extract_element_state :317-403) for the states of the last solve, still resident in HBM: points = nbatch x np x 30 and
+ * elements = nbatch x ne x 30 doubles, each record in the field order of the reference's PointState / ElementState structs
+ * (u, udot, theta, thetadot, V, Vdot, Omega, Omegadot, F, M; theta as Wiener-Milenkovic parameters), so Julia can
+ * `reinterpret(PointState{Float64}, points)`.  rates (optional): nbatch x np x 12 = udot, thetadot, Vdot, Omegadot per point (the dx of
+ * newmark_output / gxb_newmark_run's rates_hist); NULL = zeros (StaticSystem) or NaN (DynamicSystem), as the reference fills them. */
+int gxb_assembly_state(gxb_ctx* ctx, const double* rates, double* points, double* elements);
 
 /* Compact upload of the prescribed conditions (the e2e path of design sweeps): a PrescribedConditions record is 18 doubles of which
  * all but a handful are NaN / zero and identical across the batch (src/loads.jl:16-25, :94).  `base` (np x 18, shared by the batch, NaN

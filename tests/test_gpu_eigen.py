@@ -163,3 +163,52 @@ def test_eigen_tolerance_is_enforced_by_growing_the_krylov_space():
     with pytest.raises(api.GXBError, match="did not reach tol"):
         ctx.eigenvalue_analysis(st["x"], nev=nev, m=16, max_m=16, want_vectors=False)
     ctx.close()
+
+
+def _left_eigenvectors_reference(K, M, lam, V):
+    """left_eigenvectors(K, M, λ, V) as the reference computes them (src/analyses.jl:988-1031): three passes of inverse iteration with
+    the factorisation of (K + (λ + 1e-9) M)' per mode, normalised so that u' M v = 1; rows of U are conj(u).  Dense numpy."""
+    rng = np.random.default_rng(0)
+    n, nev = V.shape
+    U = np.zeros((nev, n), complex)
+    for k in range(nev):
+        A = (K + (lam[k] + 1e-9) * M).conj().T
+        u = rng.random(n) + 1j * rng.random(n)
+        for _ in range(3):
+            u = np.linalg.solve(A, M @ u)
+            u = u / np.conj(np.conj(u) @ M @ V[:, k])
+        U[k] = np.conj(u)
+    return U
+
+
+def test_left_eigenvectors_and_mode_correlation():
+    """left eigenvectors (U M V = I) from the transposed-pencil Arnoldi process on the device against the reference's
+    inverse-iteration algorithm restated densely, and correlate_eigenmodes across two neighbouring rotor speeds."""
+    O = _oracle()
+    nb, nev = 2, 8
+    w = workloads.rotating_blade_batch(nb)
+    w["motion"][1, 5] *= 1.04; w["motion"][1, 1] *= 1.04            # second instance: 4 % faster rotor
+    ctx = _ctx(w, w["motion"], nb, w["points_b"])
+    st = ctx.steady_solve()
+    lam, V, res = ctx.eigenvalue_analysis(st["x"], nev=nev, m=70)
+    U, match = ctx.left_eigenvectors(st["x"], lam, V, m=70)
+    ctx.close()
+    assert match.max() <= 1e-8                                        # the transposed pencil has the same spectrum
+    Ms = []
+    for b in range(nb):
+        pk = O.Packed(w["start"], w["stop"], w["elems"][b], w["points"], w["pd"], w["pl"], w["bc"][b], force_scaling=w["force_scaling"][b])
+        dyn = O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6])
+        K = O.steady_jacobian(pk, dyn, st["x"][b]); M = O.mass_matrix(pk, st["x"][b]); Ms.append(M)
+        G = U[b] @ M @ V[b]                                           # M-orthogonality, analyses.jl:975-979
+        assert np.abs(G - np.eye(nev)).max() <= 1e-7
+        for k in range(nev):                                          # u_k' (K + λ_k M) = 0
+            assert np.abs(U[b, k] @ (K + lam[b, k] * M)).max() <= 1e-7 * np.abs(U[b, k] @ K).max()
+        Uref = _left_eigenvectors_reference(K, M, lam[b], V[b])
+        assert np.abs(U[b] - Uref).max() <= 1e-6 * np.abs(Uref).max()
+    # mode tracking between the two rotor speeds: C = U_p M V (the preferred form, analyses.jl:1094)
+    perm, corruption = api.correlate_eigenmodes(U[0] @ Ms[1] @ V[1])
+    assert sorted(perm.tolist()) == list(range(nev)) and corruption.max() < 0.5
+    assert np.abs(lam[1][perm] - lam[0]).max() <= 0.1 * np.abs(lam[0]).max()
+    # the restated algorithm on a hand-made matrix: row 1's best fit (column 0) is taken, it falls back to column 1 with corruption > 1
+    p2, c2 = api.correlate_eigenmodes(np.array([[0.9, 0.1, 0.0], [0.8, 0.3, 0.1], [0.0, 0.1, 1.0]]))
+    assert p2.tolist() == [0, 1, 2] and abs(c2[1] - 0.8 / 0.3) < 1e-12 and abs(c2[0] - 0.1 / 0.9) < 1e-12

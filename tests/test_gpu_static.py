@@ -447,3 +447,24 @@ def test_multi_gpu_entry_is_bit_identical_to_one_gpu():
     r1 = ctx.steady_solve()
     ctx.close()
     assert r2["converged"].all() and np.array_equal(r1["iters"], r2["iters"]) and np.array_equal(r1["x"], r2["x"])
+
+
+def test_device_assembly_state_matches_host_restatement():
+    """gxb_assembly_state: AssemblyState(x, system, assembly; prescribed_conditions) on the device (src/output.jl:146-203, 317-403) --
+    PointState / ElementState records of every instance against the numpy restatement (gxbeam_b200/state.py), follower loads, prescribed
+    displacements and reaction unknowns included.  Same formulas on both sides: agreement to round-off (1e-13)."""
+    from gxbeam_b200.state import assembly_state_records
+    case = cases.random_anisotropic(3, nelem=9)
+    ctx = _ctx_for(case)
+    res = ctx.static_solve()
+    pts, els = ctx.assembly_state()
+    ctx.close()
+    # (the extraction is a function of the state vector alone: this stiff random case need not have converged)
+    rp, re_ = assembly_state_records(res["x"][0], 0, case["pd"], case["pl"], case["bc"][0], float(np.ravel(case["force_scaling"])[0]))
+    assert np.abs(pts[0] - rp).max() <= 1e-13 * np.abs(rp).max() and np.abs(els[0] - re_).max() <= 1e-13 * np.abs(re_).max()
+    # the same observables as the dataclass the solve tests use
+    a = assembly_state(res["x"][0], case["start"], case["stop"], ctx.indices["icol_point"], ctx.indices["icol_elem"], case["pd"], case["pl"],
+                       case["bc"][0], float(np.ravel(case["force_scaling"])[0]))
+    assert np.allclose(pts[0][:, 0:3], a.point_u, rtol=0, atol=1e-13 * np.abs(a.point_u).max())
+    assert np.allclose(pts[0][:, 24:27], a.point_F, rtol=1e-13, atol=1e-13 * np.abs(a.point_F).max())
+    assert np.allclose(els[0][:, 27:30], a.elem_Mi, rtol=1e-13, atol=1e-13 * np.abs(a.elem_Mi).max())

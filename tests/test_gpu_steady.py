@@ -275,3 +275,22 @@ def test_edge_sizes_and_failure_isolation():
     ref1 = O.steady_solve(pk1, O.make_dyn(wb=mo[0, 3:6]))
     assert bool(r1["converged"][0]) == ref1["converged"] and int(r1["iters"][0]) == ref1["iters"]
     assert np.abs(r1["x"][0] - ref1["x"]).max() <= 1e-9 * np.abs(ref1["x"]).max()
+
+
+def test_device_assembly_state_dynamic_system():
+    """gxb_assembly_state for a DynamicSystem: velocities from the states, rates NaN without dx (the reference's Fill(NaN), output.jl:140)
+    and taken from the given point rates otherwise (prescribed displacements: zero rate, point.jl:265-281)."""
+    from gxbeam_b200.state import assembly_state_records
+    w = workloads.rotating_blade_batch(3, rpm_jitter=0.3)
+    ctx = _ctx(w, w["motion"], 3, w["points_b"])
+    res = ctx.steady_solve()
+    pts, els = ctx.assembly_state()
+    rates = np.random.default_rng(0).random((3, 25, 12))
+    pts2, els2 = ctx.assembly_state(rates)
+    ctx.close()
+    for b in range(3):
+        rp, re_ = assembly_state_records(res["x"][b], 1, w["pd"], w["pl"], w["bc"][b], w["force_scaling"][b])
+        assert np.array_equal(np.isnan(pts[b]), np.isnan(rp)) and np.array_equal(np.isnan(els[b]), np.isnan(re_))
+        assert np.nanmax(np.abs(pts[b] - rp)) <= 1e-13 * np.nanmax(np.abs(rp)) and np.nanmax(np.abs(els[b] - re_)) <= 1e-13 * np.nanmax(np.abs(re_))
+        rp, re_ = assembly_state_records(res["x"][b], 1, w["pd"], w["pl"], w["bc"][b], w["force_scaling"][b], rates[b])
+        assert np.abs(pts2[b] - rp).max() <= 1e-13 * np.abs(rp).max() and np.abs(els2[b] - re_).max() <= 1e-13 * np.abs(re_).max()
