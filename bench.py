@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 NBATCH, NELEM = 4096, 100
 METRIC = "batched Newton iterations/sec (systems x iters)"
 UNIT = "newton_iters/s"
+E2E_SIZES_512 = None        # unequal pipelined chunks for the 512-instance shard (None: equal chunks)
 WORKLOAD = (f"{NBATCH} independent {NELEM}-element nonlinear cantilevers under tip moment (static_analysis), randomised stiffness/loads "
             "(BASELINE configs[1])")
 
@@ -183,6 +184,7 @@ def main():
                     help="strong: BASELINE configs[1]'s 4096 instances in total, sharded over the N GPUs; weak: 4096 per GPU")
     ap.add_argument("--e2e-lanes", type=int, default=0, help="contexts per GPU of the pipelined host-buffer path (0 = by batch size)")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks the pipelined host-buffer path cuts the per-GPU batch into (0 = one per lane)")
+    ap.add_argument("--e2e-sizes", default="", help="comma-separated chunk sizes of the pipelined host-buffer path, one lane each (overrides lanes/chunks)")
     ap.add_argument("--lu-parts", type=int, default=0, help="warps per instance of the partitioned factorisation (0 auto, 1 off, 2/4/8)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the time-boxed configs 1/3/4 measurements (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -349,7 +351,14 @@ def main():
         e2e_chunks -= 1
     if e2e_lanes >= 1:
         ctx.close()
-        ps = api.PipelinedSolver(w["start"], w["stop"], w["pd"], w["pl"], nb // e2e_chunks, lanes=e2e_lanes, device=local, no_gravity=True)
+        sizes = [int(v) for v in args.e2e_sizes.split(",")] if args.e2e_sizes else None
+        if sizes is None and nb == 512:
+            sizes = E2E_SIZES_512
+        if sizes is not None:
+            assert sum(sizes) == nb
+            e2e_lanes = e2e_chunks = len(sizes)
+        ps = api.PipelinedSolver(w["start"], w["stop"], w["pd"], w["pl"], nb // e2e_chunks, lanes=e2e_lanes, device=local, no_gravity=True,
+                                 chunk_sizes=sizes)
         # prescribed conditions in compact form (gxb_set_bc_compact): the 18-double PrescribedConditions records of this workload differ
         # between instances in the tip loads only (Mz, and Fz when present); everything else (NaN / zero, the root clamp) is one shared
         # np x 18 base record

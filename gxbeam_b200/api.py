@@ -564,18 +564,22 @@ class PipelinedSolver:
     Newton solve of chunk k and the device->host copy of chunk k-1: the PCIe transfer of the reference-layout inputs (728 B per
     element) is hidden behind the solve instead of preceding it."""
 
-    def __init__(self, start, stop, pd, pl, chunk, lanes=2, device=0, kind=0, no_gravity=False):
+    def __init__(self, start, stop, pd, pl, chunk, lanes=2, device=0, kind=0, no_gravity=False, chunk_sizes=None):
+        """chunk_sizes: optional list, one lane per entry, each lane sized to its own chunk (unequal cuts: a small LAST chunk shortens
+        the tail after the last upload); otherwise `lanes` lanes take chunks of `chunk` instances round-robin."""
         self.chunk, self.kind = int(chunk), kind
+        self.chunk_sizes = None if chunk_sizes is None else [int(v) for v in chunk_sizes]
+        sizes = self.chunk_sizes if self.chunk_sizes is not None else [self.chunk] * lanes
         self.ctxs = []
-        for _ in range(lanes):
+        for sz in sizes:
             c = Context(device)
             self.indices = c.topology(start, stop, pd, pl, kind=kind)
-            c.set_batch(self.chunk)
+            c.set_batch(sz)
             if kind == 0 and no_gravity:
                 c.hint_no_gravity()
             self.ctxs.append(c)
         self.n = self.ctxs[0].n
-        self.pool = ThreadPoolExecutor(lanes)
+        self.pool = ThreadPoolExecutor(len(sizes))
         self.upload_lock = threading.Lock()
 
     def solve(self, elements, prescribed_values, force_scaling, out, opts=None, gravity=None, points=None, motion=None, bc_compact=None):
@@ -583,17 +587,23 @@ class PipelinedSolver:
         converged, iters (int32 [nb]), resid_inf [nb] (pinned memory makes the copies asynchronous).  nb must be a multiple of `chunk`.
         bc_compact = (base [np, 18], point [K], field [K], values [nb, K]) replaces prescribed_values (gxb_set_bc_compact)."""
         nb = elements.shape[0]
-        if nb % self.chunk:
-            raise GXBError("PipelinedSolver.solve: the batch must be a multiple of the chunk size")
         o = opts or make_opts()
-        nchunks = nb // self.chunk
+        if self.chunk_sizes is not None:
+            if sum(self.chunk_sizes) != nb:
+                raise GXBError("PipelinedSolver.solve: the chunk sizes must add up to the batch")
+            bounds = np.concatenate([[0], np.cumsum(self.chunk_sizes)])
+            slices = [[slice(int(bounds[k]), int(bounds[k + 1]))] for k in range(len(self.ctxs))]
+        else:
+            if nb % self.chunk:
+                raise GXBError("PipelinedSolver.solve: the batch must be a multiple of the chunk size")
+            nchunks = nb // self.chunk
+            slices = [[slice(k * self.chunk, (k + 1) * self.chunk) for k in range(lane, nchunks, len(self.ctxs))] for lane in range(len(self.ctxs))]
         stats = [None] * len(self.ctxs)
 
         def run(lane):
             c = self.ctxs[lane]
             acc = {}
-            for k in range(lane, nchunks, len(self.ctxs)):
-                sl = slice(k * self.chunk, (k + 1) * self.chunk)
+            for sl in slices[lane]:
                 # one upload at a time: the PCIe link is the shared resource; serialising the uploads staggers the lanes so that one
                 # lane's Newton solve runs under the other lane's transfer instead of both alternating in lock-step
                 with self.upload_lock:
