@@ -765,7 +765,25 @@ __global__ void __launch_bounds__(128) k_update(UpdateArgs A) {
     if (A.ns.status[b] != ST_TRIAL) return;
     update_instance(A, b);
 }
+// Residual at the trial point AND the Armijo / convergence update in one launch (static chains of up to 127 elements): the CTA that
+// evaluated Ft = r(xt) of its instance applies update_instance to it right away -- one launch per Newton round less (the rounds of a
+// small batch are latency-bound: 25 us per launch at 512 instances).
+__global__ void __launch_bounds__(128, 3) k_residual_update_128(StaticArgs A, UpdateArgs Up) {
+    extern __shared__ __align__(16) double asm_smem[];
+    const int b = blockIdx.x;
+    if (A.status[b] != ST_TRIAL) return;
+    static_station<false>(A, b, threadIdx.x, asm_smem);
+    __threadfence_block();
+    __syncthreads();                 // Ft of this instance is complete and visible to the whole CTA
+    update_instance(Up, b);
+}
 
+__global__ void k_sum_counts(const int* __restrict__ iters, const int* __restrict__ fcalls, long long* __restrict__ tot, int64_t n) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    long long a = t < n ? iters[t] : 0, b = t < n ? fcalls[t] : 0;
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(GXB_FULL, a, o); b += __shfl_xor_sync(GXB_FULL, b, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(tot), (unsigned long long)a); atomicAdd(reinterpret_cast<unsigned long long*>(tot) + 1, (unsigned long long)b); }
+}
 __global__ void k_fill_int(int* p, int v, int64_t n) { int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (t < n) p[t] = v; }
 
 // Jblk[b][k][3i+j] = J[brow[k]+i, bcol[k]+j] read back from the row-block storage
