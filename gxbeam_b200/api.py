@@ -51,7 +51,8 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_static_solve_resident", "gxb_fetch", "gxb_get_stats", "gxb_residual_jacobian", "gxb_newton_direction",
            "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi",
            "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors", "gxb_hint_no_gravity", "gxb_eigen_status", "gxb_set_bc_compact", "gxb_assembly_state", "gxb_eigen_arnoldi_left",
-           "gxb_multi_create", "gxb_multi_destroy", "gxb_multi_topology", "gxb_multi_set_batch", "gxb_multi_solve"]
+           "gxb_multi_create", "gxb_multi_destroy", "gxb_multi_topology", "gxb_multi_set_batch", "gxb_multi_solve",
+           "gxb_section_create", "gxb_section_destroy", "gxb_section_info", "gxb_section_properties", "gxb_section_element_matrices"]
 
 _lib = None
 
@@ -460,6 +461,57 @@ class Context:
         return p
 
     newton_direction = static_newton_direction
+
+
+class Section:
+    """Batched cross-section analysis (src/section.jl: compliance_matrix :641-783, mass_matrix :840-890) for layups sharing one quad mesh.
+    conn: [ne, 4] node numbers, 1-based, counterclockwise from the bottom-left node (MeshElement.nodenum)."""
+
+    def __init__(self, nn, conn, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        conn = np.ascontiguousarray(conn, dtype=np.int64)
+        self.nn, self.ne = int(nn), conn.shape[0]
+        self._ck(self.lib.gxb_section_create(C.byref(self.h), int(device), C.c_int64(self.nn), C.c_int64(self.ne), _ptr(conn)))
+        hb, sz = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.gxb_section_info(self.h, C.byref(hb), C.byref(sz)))
+        self.half_bandwidth, self.scratch_doubles = hb.value, sz.value
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GXBError(f"gxbeam_b200 error {rc}: {self.lib.gxb_last_error().decode()}")
+
+    def _inputs(self, nodes, materials, theta):
+        nodes = _f64(nodes); materials = _f64(materials); theta = _f64(theta)
+        nb = theta.shape[0]
+        assert nodes.shape == (nb, self.nn, 2) and materials.shape == (nb, self.ne, 10) and theta.shape == (nb, self.ne)
+        return nb, nodes, materials, theta
+
+    def properties(self, nodes, materials, theta, gxbeam_order=True, shear_center=True):
+        """nodes [nb, nn, 2], materials [nb, ne, 10], theta [nb, ne] -> dict(S [nb,6,6], sc, tc [nb,2], M [nb,6,6], mc [nb,2], ok, device_ms)."""
+        nb, nodes, materials, theta = self._inputs(nodes, materials, theta)
+        S = np.empty((nb, 6, 6)); sc = np.empty((nb, 2)); tc = np.empty((nb, 2)); M = np.empty((nb, 6, 6)); mc = np.empty((nb, 2))
+        ok = np.empty(nb, np.int32); ms = C.c_double(0)
+        self._ck(self.lib.gxb_section_properties(self.h, C.c_int64(nb), _ptr(nodes), _ptr(materials), _ptr(theta), int(gxbeam_order), int(shear_center),
+                                                 _ptr(S), _ptr(sc), _ptr(tc), _ptr(M), _ptr(mc), _ptr(ok), C.byref(ms)))
+        return dict(S=S, sc=sc, tc=tc, M=M, mc=mc, ok=ok.astype(bool), device_ms=ms.value)
+
+    def element_matrices(self, nodes, materials, theta):
+        nb, nodes, materials, theta = self._inputs(nodes, materials, theta)
+        out = np.empty((nb, self.ne, 612))
+        self._ck(self.lib.gxb_section_element_matrices(self.h, C.c_int64(nb), _ptr(nodes), _ptr(materials), _ptr(theta), _ptr(out)))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.gxb_section_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class MultiContext:

@@ -33,6 +33,7 @@
 // ------------------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int gxb_fail_(int code, const std::string& msg) { return fail(code, msg); }      // for the other translation units of the library
 #define CK(call)                                                                                             \
     do {                                                                                                     \
         cudaError_t e_ = (call);                                                                             \

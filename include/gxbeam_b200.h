@@ -237,6 +237,25 @@ int gxb_multi_solve(gxb_multi* m, const gxb_opts* opts, const double* elems, con
                     const double* pmass, const double* gravity, const double* force_scaling, const double* motion, const double* x0,
                     double* x, int32_t* converged, int32_t* iters, double* resid_inf, double* shard_ms);
 
+/* ---- cross-section analysis (src/section.jl; BASELINE config 5) ---------------------------------------------------------------------
+ * compliance_matrix(nodes, elements; gxbeam_order, shear_center) (src/section.jl:641-783) and mass_matrix(nodes, elements) (:840-890)
+ * for nbatch layups that share one quad-mesh topology.  A gxb_section holds the topology: conn = ne x 4 node numbers, 1-based and
+ * counterclockwise from the bottom-left node exactly like MeshElement.nodenum (:101-105); the nodes are renumbered once (reverse
+ * Cuthill-McKee) so that the global matrices E, C, M of :661-677 are banded.
+ * Per instance: nodes nbatch x nn x 2 (Node.x, Node.y), materials nbatch x ne x 10 (E1, E2, E3, G12, G13, G23, nu12, nu13, nu23, rho: the
+ * first ten fields of Material, :18-28), theta nbatch x ne (MeshElement.theta).
+ * Outputs (any may be NULL): S nbatch x 36 (row-major 6 x 6), sc / tc nbatch x 2 (shear / tension centre), M nbatch x 36, mc nbatch x 2
+ * (mass centre), ok nbatch (0 where the elimination met a non-positive pivot: degenerate mesh), device_ms: kernel time. */
+typedef struct gxb_section gxb_section;
+int gxb_section_create(gxb_section** s, int device, int64_t nn, int64_t ne, const int64_t* conn);
+void gxb_section_destroy(gxb_section* s);
+int gxb_section_info(gxb_section* s, int64_t* half_bandwidth, int64_t* scratch_doubles_per_instance);
+int gxb_section_properties(gxb_section* s, int64_t nbatch, const double* nodes, const double* materials, const double* theta, int gxbeam_order,
+                           int shear_center, double* S, double* sc, double* tc, double* M, double* mc, int32_t* ok, double* device_ms);
+/* parity entry: element_submatrix (src/section.jl:486-501) of every element: out = nbatch x ne x 612 doubles = Ae (6x6), Re (12x6),
+ * Ee (12x12), Ce (12x12), Le (12x6), Me (12x12), row-major. */
+int gxb_section_element_matrices(gxb_section* s, int64_t nbatch, const double* nodes, const double* materials, const double* theta, double* out);
+
 #ifdef __cplusplus
 }
 #endif
