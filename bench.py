@@ -481,7 +481,8 @@ def main():
             t_sec = time.perf_counter()
             for key, fn in (("config1_steady_4096_blades", lambda: S.steady(4096, 512)),
                             ("config4_gust_512x2000", lambda: S.gust(512, 2001, 2)),
-                            ("config3_blades_1024x200_steady_eigen", lambda: S.blades(1024, 200, 20, 70, 64))):
+                            ("config3_blades_1024x200_steady_eigen", lambda: S.blades(1024, 200, 20, 70, 64)),
+                            ("config5_sections_2048_layups", lambda: S.sections(2048, 2))):
                 try:
                     sec[key] = fn()
                 except Exception as e:      # a secondary failure must not cost the headline line

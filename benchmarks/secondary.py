@@ -146,6 +146,31 @@ def blades(nb, nelem, nev, m, cpu_sample):
                       "lowest_freq_hz_first_instance": float(np.sort(np.abs(lam[0].imag))[0] / (2 * np.pi))})
 
 
+def sections(nb, cpu_sample):
+    """BASELINE config 5: compliance_matrix + mass_matrix (src/section.jl) of `nb` parameterised airfoil layups sharing one quad mesh."""
+    from oracle import section_oracle as SO
+    w = workloads.airfoil_layup_batch(nb)
+    sec = api.Section(w["nn"], w["conn"])
+    sec.properties(w["nodes"][:64], w["materials"][:64], w["theta"][:64])           # warm-up
+    t0 = time.perf_counter()
+    r = sec.properties(w["nodes"], w["materials"], w["theta"])
+    wall = time.perf_counter() - t0
+    hb = sec.half_bandwidth
+    sec.close()
+    ns = min(nb, cpu_sample)
+    t0 = time.perf_counter(); err = 0.0
+    for b in range(ns):
+        Sref, sc, tc = SO.compliance_matrix(w["nodes"][b], w["conn"] - 1, w["materials"][b], w["theta"][b])
+        d = np.sqrt(np.abs(np.diag(Sref)))
+        err = max(err, float((np.abs(r["S"][b] - Sref) / np.outer(d, d)).max()))
+    dt = time.perf_counter() - t0
+    return {"workload": f"config 5: compliance_matrix + mass_matrix of {nb} airfoil layups (quad mesh: {w['nn']} nodes, {w['ne']} elements, "
+                        f"KKT system of {3 * w['nn'] + 12}, half bandwidth {hb} after reverse Cuthill-McKee)",
+            "gpu_layups_per_s": nb / (r["device_ms"] * 1e-3), "gpu_device_s": r["device_ms"] * 1e-3, "gpu_wall_s_incl_transfers": wall,
+            "all_ok": bool(r["ok"].all()), "cpu_s_per_layup_numpy_oracle_1core": dt / ns, "cpu_sample": ns,
+            "max_scaled_diff_S_vs_oracle": err}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steady-batch", type=int, default=4096)
@@ -157,7 +182,8 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-sample", type=int, default=4)
     ap.add_argument("--blades-batch", type=int, default=1024)
     ap.add_argument("--blades-nelem", type=int, default=200)
-    ap.add_argument("--only", default="all", choices=["all", "steady", "gust", "blades"])
+    ap.add_argument("--sections-batch", type=int, default=2048)
+    ap.add_argument("--only", default="all", choices=["all", "steady", "gust", "blades", "sections"])
     a = ap.parse_args()
     globals()["PERSISTENT"] = a.persistent
     globals()["SAVE_EVERY"] = a.gust_save_every
@@ -168,3 +194,5 @@ if __name__ == "__main__":
         print(json.dumps(gust(a.gust_batch, a.gust_steps + 1, a.cpu_sample, init=a.gust_init)), flush=True)
     if a.only in ("all", "blades"):
         print(json.dumps(blades(a.blades_batch, a.blades_nelem, 20, 70, 256)), flush=True)
+    if a.only in ("all", "sections"):
+        print(json.dumps(sections(a.sections_batch, 2)), flush=True)

@@ -19,6 +19,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdio.h>
 #include <algorithm>
 #include <queue>
 #include <string>
@@ -128,7 +129,7 @@ struct SecArgs {
     const double* theta;    // [b][ne]
     double* scratch;        // [b][per_instance]
     double* elem_out;       // debug: [b][ne][612] or null
-    int gxbeam_order, shear_center;
+    int gxbeam_order, shear_center, pair_table, smem_window;
     double* S; double* sc; double* tc; double* M; double* mc; int* status;
 };
 
@@ -239,6 +240,82 @@ __device__ void sec_kkt_solve(const double* Eb, const double* Bd, const double* 
     }
 }
 
+// The same solve with the active part of the right-hand sides in shared memory: forward, rows k .. k + hb and the 12 border rows; backward,
+// the solved rows k + 1 .. k + hb; the columns of L are prefetched one step ahead.  sm: hw * 6 + 72 + 2 (hw + 12) doubles.
+__device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const double* Ts, const int* piv, double* z, int ndof, int hb, double* sm) {
+    const int hw = hb + 1, n1 = ndof - SEC_MTAIL, tid = threadIdx.x, lw = hw + 12;
+    double* zw = sm; double* zb = zw + hw * 6; double* Lc = zb + 72;
+    for (int t = tid; t < hw * 6; t += blockDim.x) { const int r = t / 6; zw[t] = r < ndof ? z[(size_t)r * 6 + t % 6] : 0.0; }
+    for (int t = tid; t < 72; t += blockDim.x) zb[t] = z[(size_t)ndof * 6 + t];
+    for (int t = tid; t < lw; t += blockDim.x) Lc[t] = t < hw ? Eb[t] : Bd[t - hw];
+    __syncthreads();
+    int ks = 0;
+    for (int k = 0; k < n1; k++, ks = (ks + 1 == hw ? 0 : ks + 1)) {
+        const double* cur = Lc + (k & 1) * lw;
+        double* nxt = Lc + ((k + 1) & 1) * lw;
+        double pre[2] = {0.0, 0.0};
+        if (k + 1 < n1) for (int t = tid, u = 0; t < lw && u < 2; t += blockDim.x, u++) pre[u] = t < hw ? Eb[(size_t)(k + 1) * hw + t] : Bd[(size_t)(k + 1) * 12 + (t - hw)];
+        const double zin = (tid < 6 && k + hw < ndof) ? z[(size_t)(k + hw) * 6 + tid] : 0.0;      // the row that takes over slot ks
+        const int mk = min(hb, ndof - 1 - k);
+        for (int t = tid; t < (mk + 12) * 6; t += blockDim.x) {
+            const int q = t / 6, c = t - 6 * q;
+            const double zk = zw[ks * 6 + c];
+            if (q < mk) { int sl = ks + 1 + q; if (sl >= hw) sl -= hw; zw[sl * 6 + c] -= cur[1 + q] * zk; }
+            else zb[(q - mk) * 6 + c] -= cur[hw + (q - mk)] * zk;
+        }
+        __syncthreads();
+        if (tid < 6) {
+            z[(size_t)k * 6 + tid] = zw[ks * 6 + tid] / cur[0];
+            zw[ks * 6 + tid] = zin;
+        }
+        for (int t = tid, u = 0; t < lw && u < 2; t += blockDim.x, u++) nxt[t] = pre[u];
+        __syncthreads();
+    }
+    for (int t = tid; t < SEC_MTAIL * 6; t += blockDim.x) { const int r = n1 + t / 6; z[(size_t)r * 6 + t % 6] = zw[(r % hw) * 6 + t % 6]; }
+    for (int t = tid; t < 72; t += blockDim.x) z[(size_t)ndof * 6 + t] = zb[t];
+    __syncthreads();
+    if (tid < 6) {
+        const int c = tid;
+        double v[SEC_NT];
+        for (int i = 0; i < SEC_NT; i++) v[i] = z[(size_t)(n1 + i) * 6 + c];
+        for (int k = 0; k < SEC_NT; k++) { const int p = piv[k]; const double tmp = v[k]; v[k] = v[p]; v[p] = tmp; }
+        for (int k = 0; k < SEC_NT; k++)
+            for (int i = k + 1; i < SEC_NT; i++) v[i] -= Ts[i * SEC_NT + k] * v[k];
+        for (int k = SEC_NT - 1; k >= 0; k--) { double a = v[k]; for (int j = k + 1; j < SEC_NT; j++) a -= Ts[k * SEC_NT + j] * v[j]; v[k] = a / Ts[k * SEC_NT + k]; }
+        for (int i = 0; i < SEC_NT; i++) z[(size_t)(n1 + i) * 6 + c] = v[i];
+    }
+    __syncthreads();
+    // backward: window = solved rows k + 1 .. k + hb (rows >= ndof do not exist: zero), border = the 12 solved multipliers
+    for (int t = tid; t < hw * 6; t += blockDim.x) { const int r = n1 + t / 6; zw[(r % hw) * 6 + t % 6] = r < ndof ? z[(size_t)r * 6 + t % 6] : 0.0; }
+    for (int t = tid; t < 72; t += blockDim.x) zb[t] = z[(size_t)ndof * 6 + t];
+    if (n1 > 0) for (int t = tid; t < lw; t += blockDim.x) Lc[((n1 - 1) & 1) * lw + t] = t < hw ? Eb[(size_t)(n1 - 1) * hw + t] : Bd[(size_t)(n1 - 1) * 12 + (t - hw)];
+    __syncthreads();
+    const int c = tid / 32, lane = tid % 32;
+    double ynext = (c < 6 && lane == 0 && n1 > 0) ? z[(size_t)(n1 - 1) * 6 + c] : 0.0;
+    for (int k = n1 - 1; k >= 0; k--) {
+        const double* cur = Lc + (k & 1) * lw;
+        double* nxt = Lc + ((k + 1) & 1) * lw;
+        double pre[2] = {0.0, 0.0};
+        if (k > 0) for (int t = tid, u = 0; t < lw && u < 2; t += blockDim.x, u++) pre[u] = t < hw ? Eb[(size_t)(k - 1) * hw + t] : Bd[(size_t)(k - 1) * 12 + (t - hw)];
+        const double yk = ynext;
+        if (c < 6 && lane == 0 && k > 0) ynext = z[(size_t)(k - 1) * 6 + c];
+        const int mk = min(hb, ndof - 1 - k);
+        double acc = 0.0;
+        if (c < 6) {
+            const int k1 = (k + 1) % hw;
+            for (int q = lane; q < mk + 12; q += 32) {
+                if (q < mk) { int sl = k1 + q; if (sl >= hw) sl -= hw; acc = fma(cur[1 + q], zw[sl * 6 + c], acc); }
+                else acc = fma(cur[hw + (q - mk)], zb[(q - mk) * 6 + c], acc);
+            }
+        }
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        __syncthreads();                     // every read of the slot that row k takes over (row k + hw) is done
+        if (c < 6 && lane == 0) { const double v = yk - acc; z[(size_t)k * 6 + c] = v; zw[(k % hw) * 6 + c] = v; }
+        for (int t = tid, u = 0; t < lw && u < 2; t += blockDim.x, u++) nxt[t] = pre[u];
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
     const int64_t b = blockIdx.x;
     const SecDims& D = A.d;
@@ -248,8 +325,30 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
     double *X1 = s + D.oX1, *X2 = s + D.oX2, *T1 = s + D.oT1, *T2 = s + D.oT2;
     const double* xy = A.nodes + (size_t)b * nn * 2;
     __shared__ double Ts[SEC_NT * SEC_NT]; __shared__ int piv[SEC_NT]; __shared__ double red[8 * 36]; __shared__ double G[36]; __shared__ int bad;
+    // (row offset, column offset) of the t-th pair 1 <= dj <= dI <= hb of the rank-1 update, enumerated row by row (so that the first
+    // mk (mk + 1) / 2 entries are the pairs of a shorter column): a table in dynamic shared memory when it fits (A.pair_table), else decoded
+    extern __shared__ __align__(16) double sec_dyn[];
+    const int hw = hb + 1;
+    double* win = sec_dyn;                                     // [hw][hw]: slot c % hw holds column c of the band (window mode)
+    double* bwin = win + (A.smem_window ? hw * hw : 0);        // [hw][12] border entries of the same columns
+    double* c22s = bwin + (A.smem_window ? hw * 12 : 0);       // [144] corner
+    double* stg = c22s + (A.smem_window ? 144 : 0);            // [4][hw + 12] staged incoming columns
+    unsigned short* pair_tab = reinterpret_cast<unsigned short*>(stg + (A.smem_window ? 4 * (hw + 12) : 0));
+    if (A.pair_table)
+        for (int t = threadIdx.x; t < hb * (hb + 1) / 2; t += blockDim.x) {
+            int di = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+            while ((di + 1) * (di + 2) / 2 <= t) di++;
+            while (di * (di + 1) / 2 > t) di--;
+            pair_tab[2 * t] = (unsigned short)(di + 1); pair_tab[2 * t + 1] = (unsigned short)(t - di * (di + 1) / 2 + 1);
+        }
+#ifdef SEC_TIMING
+    long long tq = clock64(), tn, tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define SEC_TICK(i) do { __syncthreads(); tn = clock64(); tph[i] += tn - tq; tq = tn; } while (0)
+#else
+#define SEC_TICK(i) do { } while (0)
+#endif
     // ---- border [R | D] (constraint columns of section.jl:683-692, in the renumbered dof), corner [A 0; 0 0], working copy of E ----
-    for (int t = threadIdx.x; t < ndof * (hb + 1); t += blockDim.x) Eb[t] = Eb0[t];
+    if (!A.smem_window) for (int t = threadIdx.x; t < ndof * (hb + 1); t += blockDim.x) Eb[t] = Eb0[t];
     for (int i = threadIdx.x; i < nn; i += blockDim.x) {
         const int p = A.perm[i];
         const double x = xy[2 * i], y = xy[2 * i + 1];
@@ -263,7 +362,97 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
     for (int t = threadIdx.x; t < 144; t += blockDim.x) { const int i = t / 12, j = t % 12; C22[t] = (i < 6 && j < 6) ? Am[6 * i + j] : 0.0; }
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
+    SEC_TICK(0);
     // ---- partial L D L' of the bordered band matrix: the first n1 columns (E11 is positive definite) ----
+    // Window mode: the hb + 1 columns the rank-1 update of column k can touch live in shared memory (ring of column slots); a column is
+    // read from global memory once, when the window reaches it, and written back once, when it has become a column of L.  (Updating the
+    // band in global memory costs a DRAM round trip per read-modify-write: 24 us per column instead of ~0.3 us.)
+    if (A.smem_window) {
+        for (int t = threadIdx.x; t < hw * hw; t += blockDim.x) { const int c = t / hw, d = t % hw; win[t] = c < ndof ? Eb0[(size_t)c * hw + d] : 0.0; }
+        for (int t = threadIdx.x; t < hw * 12; t += blockDim.x) { const int c = t / 12; bwin[t] = c < ndof ? Bd[(size_t)c * 12 + t % 12] : 0.0; }
+        for (int t = threadIdx.x; t < 144; t += blockDim.x) c22s[t] = C22[t];
+        __syncthreads();
+        // incoming columns (k + hw) are staged three steps ahead by cp.async into a ring of four buffers: one step of lead (~1000 cycles)
+        // is shorter than a DRAM round trip with two CTAs per SM
+        auto stage_col = [&](int cn) {
+            if (cn < ndof && threadIdx.x < hw + 12) {
+                const int t = threadIdx.x;
+                const double* src = t < hw ? Eb0 + (size_t)cn * hw + t : Bd + (size_t)cn * 12 + (t - hw);
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + (cn & 3) * (hw + 12) + t);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src));
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
+        stage_col(hw); stage_col(hw + 1); stage_col(hw + 2);
+        int ks = 0;                                   // k % hw, kept incrementally
+        for (int k = 0; k < n1; k++, ks = (ks + 1 == hw ? 0 : ks + 1)) {
+            double* ck = win + ks * hw;
+            double* bk = bwin + ks * 12;
+            const double dk = ck[0];
+            if (!(dk > 0.0) && threadIdx.x == 0) bad = 1;
+            const double rd = 1.0 / dk;
+            const int mk = min(hb, ndof - 1 - k);
+            const int npair = mk * (mk + 1) / 2, nbb = 12 * mk;
+            const int cn = k + hw;                    // the column that takes over this slot
+            stage_col(cn + 3);
+            // band-band pairs four at a time per thread: all operands are read before the first store (every pair has its own target, but
+            // the compiler cannot know that ck and the targets do not alias: one read-modify-write at a time ran at 235 cycles per pair)
+            for (int t0 = threadIdx.x; t0 < npair; t0 += 4 * blockDim.x) {
+                int idx[4]; double nv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int t = t0 + u * blockDim.x;
+                    idx[u] = -1;
+                    if (t < npair) {
+                        const int dI = pair_tab[2 * t], dj = pair_tab[2 * t + 1];
+                        int sl = ks + dj; if (sl >= hw) sl -= hw;
+                        idx[u] = sl * hw + (dI - dj);
+                        nv[u] = win[idx[u]] - ck[dI] * ck[dj] * rd;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (idx[u] >= 0) win[idx[u]] = nv[u];
+            }
+            for (int t = npair + threadIdx.x; t < npair + nbb + 78; t += blockDim.x) {
+                if (t < npair + nbb) {
+                    const int u = t - npair, dj = u / 12 + 1, j = u - 12 * (dj - 1);
+                    int sl = ks + dj; if (sl >= hw) sl -= hw;
+                    bwin[sl * 12 + j] -= bk[j] * ck[dj] * rd;
+                } else {
+                    const int u = t - npair - nbb;
+                    int i = (int)((sqrt(8.0 * u + 1.0) - 1.0) * 0.5);
+                    while ((i + 1) * (i + 2) / 2 <= u) i++;
+                    while (i * (i + 1) / 2 > u) i--;
+                    const int j = u - i * (i + 1) / 2;
+                    const double v = bk[i] * bk[j] * rd;
+                    c22s[12 * i + j] -= v; if (i != j) c22s[12 * j + i] -= v;
+                }
+            }
+            __syncthreads();
+            // column k is final: scale to L, write it out, refill its slot with column k + hw (Bd row cn is still untouched: the
+            // border entries of a column are first modified when the column is in the window)
+            asm volatile("cp.async.wait_group 3;\n" ::: "memory");      // this thread's piece of column k + hw has landed
+            if (threadIdx.x < hw + 12) {
+                const int t = threadIdx.x;
+                const double in = cn < ndof ? stg[(cn & 3) * (hw + 12) + t] : 0.0;
+                if (t < hw) {
+                    const double v = t == 0 ? dk : (t <= mk ? ck[t] * rd : 0.0);
+                    Eb[(size_t)k * hw + t] = v;
+                    ck[t] = in;
+                } else {
+                    const int j = t - hw;
+                    Bd[(size_t)k * 12 + j] = bk[j] * rd;
+                    bk[j] = in;
+                }
+            }
+            __syncthreads();
+        }
+        // the tail columns (dof of the last two nodes) and the corner go back to global memory for the dense trailing block
+        for (int t = threadIdx.x; t < SEC_MTAIL * hw; t += blockDim.x) { const int c = n1 + t / hw; Eb[(size_t)c * hw + t % hw] = win[(c % hw) * hw + t % hw]; }
+        for (int t = threadIdx.x; t < SEC_MTAIL * 12; t += blockDim.x) { const int c = n1 + t / 12; Bd[(size_t)c * 12 + t % 12] = bwin[(c % hw) * 12 + t % 12]; }
+        for (int t = threadIdx.x; t < 144; t += blockDim.x) C22[t] = c22s[t];
+        __syncthreads();
+    } else
     for (int k = 0; k < n1; k++) {
         double* ck = Eb + (size_t)k * (hb + 1);
         double* bk = Bd + (size_t)k * 12;
@@ -274,10 +463,14 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
         const int npair = mk * (mk + 1) / 2, nbb = 12 * mk;
         for (int t = threadIdx.x; t < npair + nbb + 78; t += blockDim.x) {
             if (t < npair) {
-                int di = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-                while ((di + 1) * (di + 2) / 2 <= t) di++;
-                while (di * (di + 1) / 2 > t) di--;
-                const int dj = t - di * (di + 1) / 2 + 1, dI = di + 1;
+                int dI, dj;
+                if (A.pair_table) { dI = pair_tab[2 * t]; dj = pair_tab[2 * t + 1]; }
+                else {
+                    int di = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                    while ((di + 1) * (di + 2) / 2 <= t) di++;
+                    while (di * (di + 1) / 2 > t) di--;
+                    dj = t - di * (di + 1) / 2 + 1; dI = di + 1;
+                }
                 Eb[(size_t)(k + dj) * (hb + 1) + (dI - dj)] -= ck[dI] * ck[dj] * rd;
             } else if (t < npair + nbb) {
                 const int u = t - npair, dj = u / 12 + 1, j = u % 12;
@@ -296,6 +489,7 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
         for (int t = threadIdx.x; t < mk + 12; t += blockDim.x) { if (t < mk) ck[1 + t] *= rd; else bk[t - mk] *= rd; }
         __syncthreads();
     }
+    SEC_TICK(1);
     // ---- trailing block: [Schur complement of the last two nodes | their border rows; border' | corner], dense LU with partial pivoting ----
     for (int t = threadIdx.x; t < SEC_NT * SEC_NT; t += blockDim.x) {
         const int i = t / SEC_NT, j = t % SEC_NT;
@@ -322,12 +516,14 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
         }
     }
     __syncthreads();
+    SEC_TICK(2);
     // ---- first solve: B2 = [0; Tr'; 0] (section.jl:694-697) -> dX, dY ----
     for (int t = threadIdx.x; t < (ndof + 12) * 6; t += blockDim.x) X2[t] = 0.0;
     __syncthreads();
     if (threadIdx.x == 0) { X2[(size_t)(ndof + 4) * 6 + 0] = -1.0; X2[(size_t)(ndof + 3) * 6 + 1] = 1.0; }
     __syncthreads();
-    sec_kkt_solve(Eb, Bd, Ts, piv, X2, ndof, hb);
+    if (A.smem_window) sec_kkt_solve_win(Eb, Bd, Ts, piv, X2, ndof, hb, win); else sec_kkt_solve(Eb, Bd, Ts, piv, X2, ndof, hb);
+    SEC_TICK(3);
     // ---- second right-hand side: B1 = [C' dX - C dX + L dY; I - L' dX; 0] (section.jl:712-724) ----
     const double* dX = X2; const double* dY = X2 + (size_t)ndof * 6;
     sec_band_mv(Cb, false, true, dX, X1, ndof, hb, 1.0, false);
@@ -344,7 +540,9 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
     sec_gram(L, dX, ndof, G, red);                       // L' dX
     for (int t = threadIdx.x; t < 72; t += blockDim.x) { const int i = t / 6, j = t % 6; X1[(size_t)(ndof + i) * 6 + j] = i < 6 ? ((i == j) - G[6 * i + j]) : 0.0; }
     __syncthreads();
-    sec_kkt_solve(Eb, Bd, Ts, piv, X1, ndof, hb);
+    SEC_TICK(4);
+    if (A.smem_window) sec_kkt_solve_win(Eb, Bd, Ts, piv, X1, ndof, hb, win); else sec_kkt_solve(Eb, Bd, Ts, piv, X1, ndof, hb);
+    SEC_TICK(5);
     // ---- S = X'(E X + C dX + R Y) + dX'(C' X + M dX + L Y) + Y'(R' X + L' dX + A Y)   (section.jl:736-757) ----
     const double* X = X1; const double* Y = X1 + (size_t)ndof * 6;
     sec_band_mv(Eb0, true, false, X, T1, ndof, hb, 1.0, false);
@@ -373,6 +571,7 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
     __syncthreads();
     if (threadIdx.x < 36) { const int i = threadIdx.x / 6, j = threadIdx.x % 6; double acc = G[threadIdx.x]; for (int k = 0; k < 6; k++) acc = fma(Y[k * 6 + i], W[6 * k + j], acc); G[threadIdx.x] = acc; }
     __syncthreads();
+    SEC_TICK(6);
     // ---- centres, transformation to the shear centre, GXBeam ordering (section.jl:759-781); mass matrix (:840-890) ----
     if (threadIdx.x == 0) {
         double Sm[6][6];
@@ -427,6 +626,12 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
             A.mc[2 * b] = xm; A.mc[2 * b + 1] = ym;
         }
     }
+#ifdef SEC_TIMING
+    SEC_TICK(7);
+    if (b == 0 && threadIdx.x == 0)
+        printf("[section timing] cycles: init %lld, factor %lld, tail LU %lld, solve1 %lld, rhs2 %lld, solve2 %lld, products %lld, centres+mass %lld\n",
+               tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------ host side
@@ -547,7 +752,17 @@ static int section_run(gxb_section* s, int64_t nbatch, const double* nodes, cons
         if (elem_out) {
             SCK(cudaMemcpyAsync(elem_out + (size_t)b0 * d.ne * SEC_ELEM, d_elem, (size_t)nb * d.ne * SEC_ELEM * 8, cudaMemcpyDeviceToHost, s->stream));
         } else {
-            k_section_solve<<<(unsigned)nb, 256, 0, s->stream>>>(A);
+            // shared memory: the band window ((hb+1)^2 + 12 (hb+1) + 144 doubles) and the pair table when they fit the opt-in maximum
+            int optin = 0;
+            SCK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+            const size_t tab = (size_t)d.hb * (d.hb + 1) / 2 * 4;
+            const size_t winb = ((size_t)(d.hb + 1) * (d.hb + 1) + (size_t)(d.hb + 1) * 12 + 144 + 4 * (size_t)(d.hb + 13)) * 8;
+            const size_t statics = 8 * 1024;
+            A.smem_window = winb + tab + statics <= (size_t)optin && d.hb + 13 <= 256;      // one thread per entry of an incoming column
+            A.pair_table = A.smem_window || (tab + statics <= (size_t)optin && d.hb < 65535);
+            const size_t dyn = (A.smem_window ? winb : 0) + (A.pair_table ? tab : 0);
+            if (dyn > 40 * 1024) SCK(cudaFuncSetAttribute(k_section_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            k_section_solve<<<(unsigned)nb, 256, dyn, s->stream>>>(A);
             SCK(cudaGetLastError());
             SCK(cudaEventRecord(e1, s->stream));
             if (S) SCK(cudaMemcpyAsync(S + (size_t)b0 * 36, A.S, (size_t)nb * 36 * 8, cudaMemcpyDeviceToHost, s->stream));

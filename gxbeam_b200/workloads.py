@@ -167,3 +167,48 @@ def wind_turbine_blade_batch(nbatch=1024, nelem=200, seed=1234 + 3, nspeeds=16, 
     pts = np.tile(points[None], (nbatch, 1, 1))
     return dict(start=start, stop=stop, points=points, points_b=pts, pd=pd, pl=pl, elems=elems, bc=bc, motion=motion, force_scaling=fs,
                 nelem=nelem, nbatch=nbatch)
+
+
+def airfoil_layup_batch(nbatch=2048, ns=120, nplies=6, seed=1234 + 5, chord=1.0):
+    """BASELINE config 5: `nbatch` parameterised layups of one closed thin-walled airfoil-shaped section (src/section.jl
+    compliance_matrix + mass_matrix).  The outer contour is a NACA 0015 outline (blunt trailing edge closed by the last segment),
+    `ns` segments around, `nplies` plies through the wall, every ply one layer of 4-node quads: nn = ns (nplies + 1) nodes,
+    ne = ns nplies elements, counterclockwise node order per element like MeshElement.nodenum.  The topology is shared; per instance
+    vary the wall thickness (geometry: the inner surface is the contour scaled by 1 - 0.12 U(0.7, 1.3) about mid-chord), the ply angles (per ply U(-60, 60) degrees), the ply material
+    scale (U(0.8, 1.2) on the moduli of a glass/epoxy-like orthotropic material) and the density.
+    Returns dict(conn [ne, 4] 1-based, nodes [nb, nn, 2], materials [nb, ne, 10], theta [nb, ne])."""
+    rng = np.random.default_rng(seed)
+    # contour, counterclockwise, starting at the trailing edge upper side
+    beta = np.linspace(0.0, 2 * np.pi, ns, endpoint=False)
+    xc = 0.5 * chord * (1 + np.cos(beta))
+    tt = 0.15
+    yt = 5 * tt * chord * (0.2969 * np.sqrt(xc / chord) - 0.1260 * (xc / chord) - 0.3516 * (xc / chord) ** 2 + 0.2843 * (xc / chord) ** 3 - 0.1015 * (xc / chord) ** 4)
+    yc = np.where(beta <= np.pi, yt, -yt)
+    outer = np.stack([xc, yc], 1)
+    # inner surface: the contour scaled about the mid-chord point (the section is star-shaped about it, so the plies never cross, also at
+    # the sharp trailing edge); wall fraction tau_i per instance
+    nr = nplies + 1
+    centre = np.array([0.5 * chord, 0.0])
+    tau = 0.12 * rng.uniform(0.7, 1.3, nbatch)
+    frac = np.linspace(0.0, 1.0, nr)                         # 0 = outer surface
+    scale = 1.0 - tau[:, None, None, None] * frac[None, None, :, None]
+    nodes = centre[None, None, None, :] + scale * (outer - centre)[None, :, None, :]
+    nodes = nodes.reshape(nbatch, ns * nr, 2)                # node (i, j) = i nr + j, j through the wall (0 = outside)
+    conn = []
+    for i in range(ns):
+        ip = (i + 1) % ns
+        for j in range(nplies):
+            # counterclockwise in the local frame (x along the contour, y inward): (i, j), (ip, j), (ip, j+1), (i, j+1)
+            conn.append([i * nr + j, ip * nr + j, ip * nr + j + 1, i * nr + j + 1])
+    conn = np.array(conn, np.int64) + 1
+    ne = len(conn)
+    base = np.array([37.0e9, 9.0e9, 9.0e9, 4.0e9, 4.0e9, 3.0e9, 0.28, 0.28, 0.4, 1860.0])
+    ply_scale = rng.uniform(0.8, 1.2, (nbatch, nplies))
+    ply_angle = rng.uniform(-np.pi / 3, np.pi / 3, (nbatch, nplies))
+    ply_rho = rng.uniform(0.9, 1.1, (nbatch, nplies))
+    materials = np.tile(base[None, None, :], (nbatch, ne, 1))
+    ply_of = np.tile(np.arange(nplies), ns)
+    materials[:, :, 0:6] *= ply_scale[:, ply_of][:, :, None]
+    materials[:, :, 9] *= ply_rho[:, ply_of]
+    theta = ply_angle[:, ply_of]
+    return dict(conn=conn, nodes=nodes, materials=materials, theta=theta, nn=ns * nr, ne=ne)

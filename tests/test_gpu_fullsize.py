@@ -90,3 +90,31 @@ def test_c3_full_size_steady_and_eigen():
             v = vec[b][:, k]
             assert np.abs((K + lam[b, k] * M) @ v).max() <= 1e-6 * np.abs(K @ v).max(), (b, k)
     ctx.close()
+
+
+def test_c5_full_size_section_properties():
+    """BASELINE config 5: 2048 parameterised airfoil layups (840 nodes, 720 quads, KKT system of 2532 unknowns each).  Size-independent
+    properties over the whole batch (every elimination succeeded; S and M symmetric, S positive definite; mass = sum of rho * area) plus
+    sampled instances against the numpy oracle at 1e-9 of the entry scale."""
+    from oracle import section_oracle as SO
+    nb = 2048
+    w = workloads.airfoil_layup_batch(nb)
+    sec = api.Section(w["nn"], w["conn"])
+    r = sec.properties(w["nodes"], w["materials"], w["theta"])
+    sec.close()
+    assert r["ok"].all()
+    S, M = r["S"], r["M"]
+    d = np.sqrt(np.abs(np.einsum("bii->bi", S)))
+    assert (np.abs(S - np.transpose(S, (0, 2, 1))) / (d[:, :, None] * d[:, None, :])).max() <= 1e-9
+    assert np.linalg.eigvalsh(0.5 * (S + np.transpose(S, (0, 2, 1)))).min() > 0
+    assert np.array_equal(M, np.transpose(M, (0, 2, 1)))
+    c = w["conn"] - 1
+    xy = w["nodes"][:, c]                                                                     # [nb, ne, 4, 2]
+    area = 0.5 * sum(xy[:, :, i, 0] * xy[:, :, (i + 1) % 4, 1] - xy[:, :, (i + 1) % 4, 0] * xy[:, :, i, 1] for i in range(4))
+    mass = (w["materials"][:, :, 9] * area).sum(1)
+    assert np.abs(M[:, 0, 0] - mass).max() <= 1e-12 * mass.max()
+    for b in (0, 1023, 2047):
+        Sref, sc, tc = SO.compliance_matrix(w["nodes"][b], c, w["materials"][b], w["theta"][b])
+        dd = np.sqrt(np.abs(np.diag(Sref)))
+        assert (np.abs(S[b] - Sref) / np.outer(dd, dd)).max() <= 1e-9, b
+        assert np.abs(r["sc"][b] - sc).max() <= 1e-9 and np.abs(r["tc"][b] - tc).max() <= 1e-9
