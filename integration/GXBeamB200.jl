@@ -344,4 +344,39 @@ function static_analysis_multi_gpu(assemblies::Vector{<:Assembly}, devices::Vect
     end
 end
 
+"""
+    section_properties_batch(nodes, elements; gxbeam_order = true, shear_center = true, device = 0) -> (S, sc, tc, M, mc)
+
+Batched counterpart of `compliance_matrix(nodes, elements)` and `mass_matrix(nodes, elements)` (src/section.jl:641-783, 840-890) for
+layups that share one mesh topology: `nodes[i]::Vector{Node{Float64}}` and `elements[i]::Vector{MeshElement{Float64}}` are instance
+i's mesh (same `nodenum` everywhere; coordinates, materials and ply angles may differ).  `S[:, :, i]`, `M[:, :, i]` are returned in
+Julia's column-major order (the library writes row-major 6 x 6 blocks: transposed on the way out).
+"""
+function section_properties_batch(nodes::Vector{<:Vector}, elements::Vector{<:Vector}; gxbeam_order=true, shear_center=true, device=0)
+    nb = length(nodes); nn = length(nodes[1]); ne = length(elements[1])
+    conn = Matrix{Int64}(undef, 4, ne)
+    for (e, el) in enumerate(elements[1]); conn[:, e] .= el.nodenum; end
+    xy = Array{Float64}(undef, 2, nn, nb); mats = Array{Float64}(undef, 10, ne, nb); theta = Array{Float64}(undef, ne, nb)
+    for i in 1:nb
+        for (k, n) in enumerate(nodes[i]); xy[1, k, i] = n.x; xy[2, k, i] = n.y; end
+        for (e, el) in enumerate(elements[i])
+            m = el.material
+            mats[:, e, i] .= (m.E1, m.E2, m.E3, m.G12, m.G13, m.G23, m.nu12, m.nu13, m.nu23, m.rho)
+            theta[e, i] = el.theta
+        end
+    end
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gxb_section_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint, Int64, Int64, Ptr{Int64}), h, device, nn, ne, conn))
+    try
+        S = Array{Float64}(undef, 6, 6, nb); M = similar(S); sc = zeros(2, nb); tc = zeros(2, nb); mc = zeros(2, nb); ok = zeros(Int32, nb)
+        check(ccall((:gxb_section_properties, LIB), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),
+            h[], nb, xy, mats, theta, gxbeam_order, shear_center, S, sc, tc, M, mc, ok, C_NULL))
+        all(!=(0), ok) || error("section_properties_batch: degenerate mesh in instance $(findfirst(==(0), ok))")
+        return permutedims(S, (2, 1, 3)), sc, tc, permutedims(M, (2, 1, 3)), mc
+    finally
+        ccall((:gxb_section_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+end
+
 end # module
