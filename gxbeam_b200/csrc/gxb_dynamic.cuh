@@ -203,7 +203,13 @@ GXD void inertia_jacobians(const m3& A, const m3& Cab, const Rot& R, const m3& m
 
 // MODE 0: steady state (udot = θdot = 0, Vdot = ab + αb x (Δx + u), Ωdot = αb)
 // MODE 1: Newmark step  (xdot = 2/dt x - xdot_init for u, θ, V, Ω; point.jl:766-795, element.jl:381-412)
-template <bool WANT_J, int MODE>
+// PASSES selects which row passes of the Jacobian this call produces (bit 0: point force rows, 1: point moment rows, 2: the two velocity
+// row passes, 3: the two element compatibility passes) and whether it stores the residual (bit 4).  The default does everything in one
+// thread per station; k_assemble_dynamic_split gives the three groups {residual + force rows}, {moment rows}, {velocity + element rows}
+// to three CTAs per instance, each repeating the shared core evaluation, so that a SMALL batch sees a third of the serial chain
+// (the rounds of a time-domain run are latency-bound: 152 us per Jacobian launch with one thread per station).
+#define GXB_DPASS_ALL 31
+template <bool WANT_J, int MODE, int PASSES = GXB_DPASS_ALL>
 __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
     const StaticArgs& S = A.s;
     const int N = S.N, NP = N + 1;
@@ -364,7 +370,7 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
             if (i > 0) v += prev[k];
             if (has_elem) v -= sub[k];
             if (S.two_d && k >= 2 && k <= 4) v = x[18 * i + k];
-            rp[k] = v;
+            if (PASSES & 16) rp[k] = v;
         }
         // velocity rows (point.jl:1658-1666): rV = V - vb - ωb x (Δx + u),  rΩ = Qinv C (Ω - ωb)
         v3 rV = V1 - vb - cross(wb, dxp) - cross(wb, u1);
@@ -375,8 +381,8 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         }
         double rv[6] = {rV.x, rV.y, rV.z, rO.x, rO.y, rO.z};
 #pragma unroll
-        for (int k = 0; k < 6; k++) rp[6 + k] = (S.two_d && k >= 2 && k <= 4) ? x[18 * i + 6 + k] : rv[k];
-        if (has_elem) {
+        for (int k = 0; k < 6; k++) if (PASSES & 16) rp[6 + k] = (S.two_d && k >= 2 && k <= 4) ? x[18 * i + 6 + k] : rv[k];
+        if (has_elem && (PASSES & 16)) {
             double re[6] = {ru.x, ru.y, ru.z, rth.x, rth.y, rth.z};
 #pragma unroll
             for (int k = 0; k < 6; k++) rp[12 + k] = (S.two_d && k >= 2 && k <= 4) ? x[18 * i + 12 + k] : re[k];
@@ -388,7 +394,7 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
     // "h" quantities are the ½·½ inertial terms that enter BOTH end points with the same sign:
     //   rows of the start point:  -= F1_x / fs = + hF_x / fs ;  rows of the stop point: += F2_x / fs = + hF_x / fs
     m3 hFu, hFth, hFV, hFO, hMu, hMth, hMV, hMO;
-    if (has_elem) {
+    if (has_elem && (PASSES & 3)) {
         const m3 m11 = ldm(es + 46 * N, N), m12 = ldm(es + 55 * N, N), m21 = ldm(es + 64 * N, N), m22 = ldm(es + 73 * N, N);
         InertiaJac ij;
         inertia_jacobians<MODE>(CtCab, Cab, R, m11, m12, m21, m22, V, Om, Vdot, Omdot, wb, alb, Pm, c2, ij);
@@ -397,6 +403,7 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
     }
 
     // =================== pass P1: force rows of point i (rows 18i+0..2) ===================
+    if constexpr ((PASSES & 1) != 0) {
     m3 JFa = zero33(), JFb = zero33();
     if (has_elem) {
         m3 Fth = 0.5 * mul3t(R, Cab * F);
@@ -470,8 +477,10 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         dtile_flush(tiles, J, c0, cnt_, 0);
         __syncthreads();
     GXB_PASS_END
+    }
 
     // =================== pass P2: moment rows of point i (rows 18i+3..5) ===================
+    if constexpr ((PASSES & 2) != 0) {
     m3 JMa = zero33(), JMb = zero33(), M1F = zero33(), hM = zero33();
     m3 dMu1 = zero33(), dMV1 = zero33(), dMO = zero33();      // structural-damping parts (u2, V2 carry the opposite sign)
     if (has_elem) {
@@ -559,7 +568,9 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         dtile_flush(tiles, J, c0, cnt_, 3);
         __syncthreads();
     GXB_PASS_END
+    }
 
+    if constexpr ((PASSES & 4) != 0) {
     // =================== passes V1/V2: velocity rows of point i (rows 18i+6..8, 18i+9..11; block 3i+1) ===================
     // row block 3i+1 stores column blocks 3i-2 ..: point i u/θ at slots 12..17, V/Ω at 18..23   (point.jl:1728-1739, 1928-1932)
     GXB_PASS_BEGIN(c0)
@@ -595,7 +606,9 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         dtile_flush(tiles, J, c0, cnt_, 9);
         __syncthreads();
     GXB_PASS_END
+    }
 
+    if constexpr ((PASSES & 8) != 0) {
     // =================== passes E1/E2: compatibility rows of element i (rows 18i+12..14, 18i+15..17; block 3i+2) ===================
     // row block 3i+2 stores column blocks 3i-1 ..: point i u/θ at slots 6..11, V/Ω 12..17, element 18..23, point i+1 u/θ 24..29
     GXB_PASS_BEGIN(c0)
@@ -648,4 +661,5 @@ __device__ void dynamic_station(const DynArgs& A, int b, int i, double* smem) {
         dtile_flush(tiles, J, c0, min(cnt_, N - c0), 15);
         __syncthreads();
     GXB_PASS_END
+    }
 }

@@ -108,6 +108,16 @@ template <bool WANT_J, int MODE> __global__ void __launch_bounds__(256) k_assemb
     dynamic_station<WANT_J, MODE>(A, b, threadIdx.x, asm_smem);
 }
 
+// pass-parallel Jacobian assembly for small batches: three CTAs per instance (blockIdx.y), see dynamic_station
+template <int MODE> __global__ void __launch_bounds__(256) k_assemble_dynamic_split(DynArgs A) {
+    extern __shared__ __align__(16) double asm_smem[];
+    const int b = blockIdx.x;
+    if (A.s.status && A.s.status[b] != A.s.want_status) return;
+    if (blockIdx.y == 0) dynamic_station<true, MODE, 1 | 16>(A, b, threadIdx.x, asm_smem);
+    else if (blockIdx.y == 1) dynamic_station<true, MODE, 2>(A, b, threadIdx.x, asm_smem);
+    else dynamic_station<true, MODE, 4 | 8>(A, b, threadIdx.x, asm_smem);
+}
+
 template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble_initial(InitArgs A) {
     extern __shared__ __align__(16) double asm_smem[];
     const int b = blockIdx.x;

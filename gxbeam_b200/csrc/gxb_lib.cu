@@ -152,6 +152,7 @@ static int configure_kernels(int device, size_t* optin_out) {
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa_.sharedSizeBytes)); } while (0)
     GXB_SMEM_MAX(k_assemble<true>); GXB_SMEM_MAX(k_assemble<false>); GXB_SMEM_MAX(k_assemble_residual_128); GXB_SMEM_MAX(k_residual_update_128);
     GXB_SMEM_MAX((k_assemble_dynamic<true, 0>)); GXB_SMEM_MAX((k_assemble_dynamic<true, 1>));
+    GXB_SMEM_MAX(k_assemble_dynamic_split<0>); GXB_SMEM_MAX(k_assemble_dynamic_split<1>);
     GXB_SMEM_MAX((k_assemble_dynamic<false, 0>)); GXB_SMEM_MAX((k_assemble_dynamic<false, 1>));
     GXB_SMEM_MAX(k_assemble_initial<true>); GXB_SMEM_MAX(k_assemble_initial<false>);
     GXB_SMEM_MAX((k_factor_solve<2, 2>)); GXB_SMEM_MAX((k_factor_solve<3, 4>)); GXB_SMEM_MAX((k_factor_solve<4, 3>));
@@ -533,7 +534,13 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
         D.chunk = chunk;
         size_t sm = ((size_t)bs * GXB_XCH + (want_j ? (size_t)chunk * GXB_DTILE : 0)) * 8;
         if (want_j) {
-            if (c->mode == 0) k_assemble_dynamic<true, 0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
+            // small batches: three CTAs per instance, one per group of row passes (GXB_DYN_SPLIT=0 / 1 forces it off / on)
+            static const int split_env = []() { const char* e = getenv("GXB_DYN_SPLIT"); return e ? atoi(e) : -1; }();
+            const bool split = c->mode != 2 && (split_env >= 0 ? split_env != 0 : 3 * c->nbatch <= (int64_t)8 * c->sm_count);      // one wave of 255-register warps
+            const dim3 grid3((unsigned)c->nbatch, 3);
+            if (split && c->mode == 0) k_assemble_dynamic_split<0><<<grid3, bs, sm, c->stream>>>(D);
+            else if (split && c->mode == 1) k_assemble_dynamic_split<1><<<grid3, bs, sm, c->stream>>>(D);
+            else if (c->mode == 0) k_assemble_dynamic<true, 0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
             else if (c->mode == 1) k_assemble_dynamic<true, 1><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
             else { InitArgs I{D, c->d_icS, c->d_rvm}; k_assemble_initial<true><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(I); }
         } else {

@@ -102,7 +102,7 @@ __device__ __forceinline__ void lu_block_step(double (&a)[W], double (&spk)[SPK 
                 for (int j = 0; j < SPK; j += 2) *reinterpret_cast<double2*>(Pr + T + 2 + j) = make_double2(spk[j], spk[j + 1]);
             }
         }
-        double* urow = ubase + (size_t)kp * ustride + 2;
+        double* urow = ubase + (ptrdiff_t)kp * ustride + 2;      // ustride may be negative (mirrored sweep of gxb_lu_two.cuh)
 #pragma unroll
         for (int j = 0; j < 6; j += 2) *reinterpret_cast<double2*>(urow + j) = make_double2(a[j], a[j + 1]);
     }

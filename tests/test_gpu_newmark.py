@@ -252,3 +252,40 @@ def test_rate_history_matches_newmark_output(persistent):
         if it % 4 == 0:
             got = res["rates"][b, it // 4]
             assert np.abs(got - rates * mask).max() <= 1e-7 * np.abs(rates).max(), it
+
+
+def test_pass_parallel_jacobian_assembly_is_bit_identical():
+    """k_assemble_dynamic_split (three CTAs per instance, one per group of row passes; the default for small batches) must write exactly
+    the Jacobian and residual of the one-thread-per-station kernel: same arithmetic, different distribution.  GXB_DYN_SPLIT is read once
+    per process, so the two variants run in child processes."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import cases
+from test_gpu_newmark import _ctx
+from gxbeam_b200 import api
+out = {}
+for mode in ("steady", "newmark"):
+    case = cases.random_anisotropic(4, nelem=7, pmass=True)
+    rng = np.random.default_rng(3)
+    mo = 10 * rng.random((1, 12))
+    ctx = _ctx(case, mo)
+    x = rng.random((1, ctx.n))
+    opts = api.make_opts(structural_damping=True)
+    if mode == "steady":
+        r, J = ctx.residual_jacobian(x, opts)
+    else:
+        r, J = ctx.newmark_residual_jacobian(rng.random((1, 8, 12)), 1e-3, x, opts)
+    ctx.close()
+    out[mode] = [r.tolist(), J.tolist()]
+print("RESULT" + json.dumps(out))
+""" % (root, os.path.join(root, "tests"))
+    res = {}
+    for v in ("0", "1"):
+        o = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, GXB_DYN_SPLIT=v), capture_output=True, text=True, check=True).stdout
+        res[v] = json.loads([l for l in o.splitlines() if l.startswith("RESULT")][-1][6:])
+    for mode in ("steady", "newmark"):
+        assert res["0"][mode] == res["1"][mode], mode

@@ -30,7 +30,8 @@ def test_steady_persistent_equals_multikernel_and_oracle(damping):
     assert a["converged"].all() and b["converged"].all()
     assert np.array_equal(a["iters"], b["iters"])
     assert np.abs(a["x"] - b["x"]).max() <= 1e-11 * np.abs(b["x"]).max()
-    assert out["persistent_launches"] == 1 and out["rounds_launches"] > 5
+    # the persistent kernel + the kernel that sums the iteration counts for the statistics
+    assert out["persistent_launches"] == 2 and out["rounds_launches"] > 5
     for i in (0, nb - 1):
         pk = O.Packed(w["start"], w["stop"], w["elems"][i], w["points"], w["pd"], w["pl"], w["bc"][i], force_scaling=w["force_scaling"][i])
         ref = O.steady_solve(pk, O.make_dyn(vb=w["motion"][i, 0:3], wb=w["motion"][i, 3:6], structural_damping=damping))
