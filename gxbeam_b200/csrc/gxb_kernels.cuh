@@ -5,6 +5,7 @@
 #include "gxb_lu.cuh"
 #include "gxb_lu_mma.cuh"
 #include "gxb_lu_part.cuh"
+#include "gxb_lu_two.cuh"
 #include "gxb_static.cuh"
 #include "gxb_dynamic.cuh"
 #include "gxb_initial.cuh"
@@ -109,13 +110,20 @@ template <bool WANT_J, int MODE> __global__ void __launch_bounds__(256) k_assemb
 }
 
 // pass-parallel Jacobian assembly for small batches: three CTAs per instance (blockIdx.y), see dynamic_station
+// (gridDim.y = 3: {residual + force rows}, {moment rows}, {velocity + element rows};  gridDim.y = 2: {force + moment rows},
+//  {residual + velocity + element rows} -- for batches whose 3 nbatch CTAs would not be resident in one wave)
 template <int MODE> __global__ void __launch_bounds__(256) k_assemble_dynamic_split(DynArgs A) {
     extern __shared__ __align__(16) double asm_smem[];
     const int b = blockIdx.x;
     if (A.s.status && A.s.status[b] != A.s.want_status) return;
-    if (blockIdx.y == 0) dynamic_station<true, MODE, 1 | 16>(A, b, threadIdx.x, asm_smem);
-    else if (blockIdx.y == 1) dynamic_station<true, MODE, 2>(A, b, threadIdx.x, asm_smem);
-    else dynamic_station<true, MODE, 4 | 8>(A, b, threadIdx.x, asm_smem);
+    if (gridDim.y == 3) {
+        if (blockIdx.y == 0) dynamic_station<true, MODE, 1 | 16>(A, b, threadIdx.x, asm_smem);
+        else if (blockIdx.y == 1) dynamic_station<true, MODE, 2>(A, b, threadIdx.x, asm_smem);
+        else dynamic_station<true, MODE, 4 | 8>(A, b, threadIdx.x, asm_smem);
+    } else {
+        if (blockIdx.y == 0) dynamic_station<true, MODE, 1 | 2>(A, b, threadIdx.x, asm_smem);
+        else dynamic_station<true, MODE, 4 | 8 | 16>(A, b, threadIdx.x, asm_smem);
+    }
 }
 
 template <bool WANT_J> __global__ void __launch_bounds__(256) k_assemble_initial(InitArgs A) {
@@ -457,6 +465,20 @@ __device__ void linesearch_start_cta(const SolveArgs& A, int64_t b) {
         A.ns.a1[b] = a0; A.ns.a2[b] = a0; A.ns.phi0[b] = 0.5 * ff; A.ns.dphi0[b] = -ff; A.ns.phx0[b] = 0.5 * ff;
         A.ns.ls_k[b] = 0; A.ns.ls_finite[b] = 0; A.ns.status[b] = ST_TRIAL;
     }
+}
+// two-sided factorisation (gxb_lu_two.cuh): one CTA of two warps per instance, top-down + bottom-up sweeps meeting at row block R
+template <int KLB, int KUB, int AB, int BB> __global__ void __launch_bounds__(64) k_factor_solve_two(SolveArgs A, int R) {
+    using S = LuShape<KLB, KUB>;
+    using T2 = TwoShape<KLB, KUB, AB, BB>;
+    extern __shared__ __align__(16) double smem[];
+    const int64_t b = blockIdx.x;
+    if (A.direction_only != 1 && A.ns.status[b] != ST_SOLVE) return;
+    const size_t n = A.n;
+    const int bad = cta_two_sided_solve<KLB, KUB, AB, BB>(A.J + b * n * S::W, A.F + b * n, A.U + b * n * T2::UW, A.p + b * n, A.nb, R, A.sign, smem);
+    if (A.direction_only == 1) { if (bad && threadIdx.x == 0) A.ns.failcode[b] = FAIL_SINGULAR; return; }
+    if (bad) { if (threadIdx.x == 0) { if (A.direction_only) { A.ns.status[b] = ST_FAILED; A.ns.failcode[b] = FAIL_SINGULAR; } else mark_singular(A, b); } return; }
+    if (A.direction_only) return;
+    linesearch_start_cta(A, b);
 }
 // further right-hand sides with the factorisation recorded by k_factor_solve_mma (A.Lst): p = sign * (J \ F)
 template <int KLB, int KUB> __global__ void __launch_bounds__(128) k_resolve_mma(SolveArgs A) {

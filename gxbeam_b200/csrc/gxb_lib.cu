@@ -157,6 +157,7 @@ static int configure_kernels(int device, size_t* optin_out) {
     GXB_SMEM_MAX(k_assemble_initial<true>); GXB_SMEM_MAX(k_assemble_initial<false>);
     GXB_SMEM_MAX((k_factor_solve<2, 2>)); GXB_SMEM_MAX((k_factor_solve<3, 4>)); GXB_SMEM_MAX((k_factor_solve<4, 3>));
     GXB_SMEM_MAX((k_factor_solve_mma<2, 2>)); GXB_SMEM_MAX((k_factor_solve_mma<3, 4>)); GXB_SMEM_MAX((k_resolve_mma<3, 4>));
+    GXB_SMEM_MAX((k_factor_solve_two<3, 4, 3, 2>)); GXB_SMEM_MAX((k_factor_solve_two<2, 2, 2, 1>));
     GXB_SMEM_MAX(k_factor_solve_part<2>); GXB_SMEM_MAX(k_factor_solve_part<3>); GXB_SMEM_MAX(k_factor_solve_part<4>);
     GXB_SMEM_MAX(k_factor_solve_part<6>); GXB_SMEM_MAX(k_factor_solve_part<8>);
     GXB_SMEM_MAX(k_arnoldi_orth);
@@ -536,8 +537,12 @@ static int launch_assemble(gxb_ctx* c, const StaticArgs& A, bool want_j) {
         if (want_j) {
             // small batches: three CTAs per instance, one per group of row passes (GXB_DYN_SPLIT=0 / 1 forces it off / on)
             static const int split_env = []() { const char* e = getenv("GXB_DYN_SPLIT"); return e ? atoi(e) : -1; }();
-            const bool split = c->mode != 2 && (split_env >= 0 ? split_env != 0 : 3 * c->nbatch <= (int64_t)8 * c->sm_count);      // one wave of 255-register warps
-            const dim3 grid3((unsigned)c->nbatch, 3);
+            // measured on config 4's topology (B200): 64 instances 0.239 -> 0.215 s per 400 steps with three CTAs per instance; 256 instances
+            // 0.294 -> 0.304 s, 512 instances 1.21 -> 1.59 s (three-way) / 1.37 s (two-way): the repeated core evaluation outweighs the
+            // shorter chain as soon as the extra CTAs compete for SMs -- tiny batches only
+            const int ways = split_env > 0 ? (split_env >= 3 ? 3 : 2) : (c->nbatch <= 128 ? 3 : 1);
+            const bool split = c->mode != 2 && split_env != 0 && ways > 1;
+            const dim3 grid3((unsigned)c->nbatch, ways);
             if (split && c->mode == 0) k_assemble_dynamic_split<0><<<grid3, bs, sm, c->stream>>>(D);
             else if (split && c->mode == 1) k_assemble_dynamic_split<1><<<grid3, bs, sm, c->stream>>>(D);
             else if (c->mode == 0) k_assemble_dynamic<true, 0><<<(unsigned)c->nbatch, bs, sm, c->stream>>>(D);
@@ -660,6 +665,28 @@ static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, doub
     A.J = c->d_J; A.F = direction_only ? c->d_Ft : c->d_F; A.x = c->d_x; A.U = c->d_U; A.p = c->d_p; A.xt = c->d_xt; A.ns = c->ns;
     A.maxstep = o->maxstep; A.linear = o->linear; A.direction_only = direction_only;
     A.fallback = direction_only ? 0 : 1; A.counter = c->d_counter; A.singular_seen = c->d_counter + 1;
+    // dynamic systems, small batches: two warps per instance from both ends (gxb_lu_two.cuh).  GXB_LU_TWO = 0 / 1 forces it off / on;
+    // opts.lu_parts = 1 switches it off like the partitioned kernel, = 2 forces it (static systems: the spike-free P = 2 variant).
+    {
+        static const int two_env = []() { const char* e = getenv("GXB_LU_TWO"); return e ? atoi(e) : -1; }();
+        const int forced = o ? o->lu_parts : 0;
+        bool two = c->np >= 6 && (forced == 2 || (forced == 0 && c->kind == 1 && (two_env >= 0 ? two_env != 0 : 2 * c->nbatch <= (int64_t)10 * c->sm_count)));      // 194 registers: 10 warps per SM, one wave
+        if (two_env == 0 && forced != 2) two = false;
+        if (Lst) two = false;                         // the eigen operator records the factorisation: tensor-core kernel only
+        if (two && !(c->kind == 0 && forced != 2)) {
+            const int m = (int)((c->np + 1) / 2);                 // cut in front of point m: halves of (almost) equal numbers of block steps
+            if (c->kind == 1) {
+                using T2 = TwoShape<3, 4, 3, 2>;
+                k_factor_solve_two<3, 4, 3, 2><<<(unsigned)c->nbatch, 64, (size_t)T2::CTA_DOUBLES * 8, c->stream>>>(A, 3 * m);
+            } else {
+                using T2 = TwoShape<2, 2, 2, 1>;
+                k_factor_solve_two<2, 2, 2, 1><<<(unsigned)c->nbatch, 64, (size_t)T2::CTA_DOUBLES * 8, c->stream>>>(A, 2 * m);
+            }
+            CK(cudaGetLastError());
+            c->stats.launches++; c->stats.n_factor++;
+            return after_factor(c, o, A, direction_only);
+        }
+    }
     const int P = choose_parts(c, o);
     if (P > 1) {
         const PartPlan plan = make_plan(c, P);

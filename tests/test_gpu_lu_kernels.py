@@ -80,8 +80,8 @@ print("RESULT" + json.dumps(out))
 SIZES_DYN = [1, 2, 3, 4, 8, 24, 61]
 
 
-def _directions_dyn(mma):
-    env = dict(os.environ, GXB_LU_MMA=str(mma))
+def _directions_dyn(mma, two=0):
+    env = dict(os.environ, GXB_LU_MMA=str(mma), GXB_LU_TWO=str(two))
     code = _CHILD_DYN.format(root=ROOT, tests=os.path.join(ROOT, "tests"), sizes=SIZES_DYN)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
     line = [l for l in out.splitlines() if l.startswith("RESULT")][-1]
@@ -91,7 +91,7 @@ def _directions_dyn(mma):
 def test_both_factorisations_dynamic_systems():
     """Same for DynamicSystem Jacobians (18 N + 12 states, 32 x 56 window, two pending slots per lane in the back substitution)."""
     from oracle import pyoracle as O
-    mma, rowlane = _directions_dyn(3), _directions_dyn(0)
+    mma, rowlane, two = _directions_dyn(3), _directions_dyn(0), _directions_dyn(3, two=1)
     for nelem in SIZES_DYN:
         case = cases.random_anisotropic(4, nelem=nelem, pmass=True)
         pk = cases.oracle_packed(case)
@@ -104,6 +104,8 @@ def test_both_factorisations_dynamic_systems():
         assert np.abs(mma[nelem] - p_ref).max() < 1e-9 * scale, nelem
         assert np.abs(rowlane[nelem] - p_ref).max() < 1e-9 * scale, nelem
         assert np.abs(mma[nelem] - rowlane[nelem]).max() < 1e-9 * scale, nelem
+        # the two-sided factorisation (gxb_lu_two.cuh; chains of fewer than 5 elements fall back to one warp per instance)
+        assert np.abs(two[nelem] - p_ref).max() < 1e-9 * scale, nelem
 
 
 # ---- partitioned factorisation (gxb_lu_part.cuh): P warps per instance, static systems ----
