@@ -143,6 +143,8 @@ def run_reference(args):
 # capture whose sources have changed since is reported as stale (traffic = null) instead of being quoted.
 def dominant_kernel(nb, forced=0, sm_count=148):
     """mirrors choose_parts() of gxbeam_b200/csrc/gxb_lib.cu"""
+    if forced == 2 or (forced == 0 and 3 * sm_count < nb <= 6 * sm_count):
+        return "k_factor_solve_two<2,2,2,1>", "r2_prof_factor_two_raw.csv"
     want = forced if forced > 0 else (12 * sm_count) // nb
     for cand in (8, 6, 4, 3, 2):
         if cand <= want:

@@ -670,10 +670,20 @@ static int launch_factor(gxb_ctx* c, const gxb_opts* o, int direction_only, doub
     {
         static const int two_env = []() { const char* e = getenv("GXB_LU_TWO"); return e ? atoi(e) : -1; }();
         const int forced = o ? o->lu_parts : 0;
-        bool two = c->np >= 6 && (forced == 2 || (forced == 0 && c->kind == 1 && (two_env >= 0 ? two_env != 0 : 2 * c->nbatch <= (int64_t)10 * c->sm_count)));      // 194 registers: 10 warps per SM, one wave
-        if (two_env == 0 && forced != 2) two = false;
-        if (Lst) two = false;                         // the eigen operator records the factorisation: tensor-core kernel only
-        if (two && !(c->kind == 0 && forced != 2)) {
+        // automatic choice: dynamic systems up to 740 instances (194 registers: 10 warps per SM, one wave); static systems between 3 and
+        // 6 instances per SM, where it beats both the three-partition kernel (512 instances: 1.56 vs 1.60 ms per solve, no spike work) and
+        // one warp per instance (800 instances: 2.05 vs 2.55 ms; at 1024 the tensor-core kernel is back in front, 2.70 vs 2.76 ms);
+        // smaller static batches take more partitions (gxb_lu_part.cuh)
+        const bool auto_two = c->kind == 1 ? 2 * c->nbatch <= (int64_t)10 * c->sm_count
+                                           : (c->nbatch > (int64_t)3 * c->sm_count && c->nbatch <= (int64_t)6 * c->sm_count);
+        bool two;
+        if (forced == 2) two = true;                       // explicit
+        else if (forced != 0) two = false;                 // another explicit choice (1 = one warp per instance, 3 .. 8 = partitions)
+        else if (two_env == 0) two = false;
+        else if (two_env > 0) two = c->kind == 1 || auto_two;
+        else two = auto_two;
+        two = two && c->np >= 6 && !Lst;                   // the eigen operator records the factorisation: tensor-core kernel only
+        if (two) {
             const int m = (int)((c->np + 1) / 2);                 // cut in front of point m: halves of (almost) equal numbers of block steps
             if (c->kind == 1) {
                 using T2 = TwoShape<3, 4, 3, 2>;
