@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--lu-parts", type=int, default=0, help="warps per instance of the partitioned factorisation (0 auto, 1 off, 2/4/8)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the time-boxed configs 1/3/4 measurements (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-lane-batch", type=int, default=2048, help="smallest per-lane batch for which the resident batch is split over lanes")
     ap.add_argument("--lanes", type=int, default=2, help="contexts per GPU sharing the resident batch (1 = one context, one stream)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -282,7 +283,7 @@ def main():
     # assembly kernels (8 warps per SM, latency-bound on their loads) of one lane run under the factorisation (16 warps per SM) of the
     # other.  Timed by one pair of CUDA events around the whole region (device idle at both ends), i.e. including every host-side gap.
     # (pays off for large resident batches only: 4096 instances 7.36 -> 6.92 ms, 1024 instances 2.66 -> 2.90 ms)
-    lanes = args.lanes if (args.lanes > 1 and nb % args.lanes == 0 and nb // args.lanes >= 2048) else 1
+    lanes = args.lanes if (args.lanes > 1 and nb % args.lanes == 0 and nb // args.lanes >= args.min_lane_batch) else 1
     single = {"dev_ms": dev_ms, "iters": iters_total, "launches": launches, "wall_ms": wall_ms}
     if lanes > 1:
         from concurrent.futures import ThreadPoolExecutor
