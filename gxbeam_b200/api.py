@@ -52,7 +52,8 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_set_bc_series", "gxb_newmark_run", "gxb_newmark_residual_jacobian", "gxb_mass_matrix", "gxb_eigen_arnoldi",
            "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors", "gxb_hint_no_gravity", "gxb_eigen_status", "gxb_set_bc_compact", "gxb_assembly_state", "gxb_eigen_arnoldi_left",
            "gxb_multi_create", "gxb_multi_destroy", "gxb_multi_topology", "gxb_multi_set_batch", "gxb_multi_solve",
-           "gxb_section_create", "gxb_section_destroy", "gxb_section_info", "gxb_section_properties", "gxb_section_element_matrices"]
+           "gxb_section_create", "gxb_section_destroy", "gxb_section_info", "gxb_section_properties", "gxb_section_element_matrices",
+           "gxb_section_strain_recovery"]
 
 _lib = None
 
@@ -495,6 +496,23 @@ class Section:
         self._ck(self.lib.gxb_section_properties(self.h, C.c_int64(nb), _ptr(nodes), _ptr(materials), _ptr(theta), int(gxbeam_order), int(shear_center),
                                                  _ptr(S), _ptr(sc), _ptr(tc), _ptr(M), _ptr(mc), _ptr(ok), C.byref(ms)))
         return dict(S=S, sc=sc, tc=tc, M=M, mc=mc, ok=ok.astype(bool), device_ms=ms.value)
+
+    def strain_recovery(self, nodes, materials, theta, F, M, strengths=None, gxbeam_order=True):
+        """strain_recovery (src/section.jl:952-1040) and, with `strengths` [nb, ne, 9], tsai_wu (:1108-1131) of every layup under its section loads
+        F, M [nb, 3] -> dict(strain_b, stress_b, strain_p, stress_p [nb, ne, 6], failure [nb, ne] or None, S [nb, 6, 6], ok, device_ms)."""
+        nb, nodes, materials, theta = self._inputs(nodes, materials, theta)
+        F = _f64(F); M = _f64(M)
+        assert F.shape == (nb, 3) and M.shape == (nb, 3)
+        st = None if strengths is None else _f64(strengths)
+        assert st is None or st.shape == (nb, self.ne, 9)
+        out = {k: np.empty((nb, self.ne, 6)) for k in ("strain_b", "stress_b", "strain_p", "stress_p")}
+        fail = None if st is None else np.empty((nb, self.ne))
+        S = np.empty((nb, 6, 6)); ok = np.empty(nb, np.int32); ms = C.c_double(0)
+        self._ck(self.lib.gxb_section_strain_recovery(self.h, C.c_int64(nb), _ptr(nodes), _ptr(materials), _ptr(theta), _ptr(st), _ptr(F), _ptr(M),
+                                                      int(gxbeam_order), _ptr(out["strain_b"]), _ptr(out["stress_b"]), _ptr(out["strain_p"]),
+                                                      _ptr(out["stress_p"]), _ptr(fail), _ptr(S), _ptr(ok), C.byref(ms)))
+        out.update(failure=fail, S=S, ok=ok.astype(bool), device_ms=ms.value)
+        return out
 
     def element_matrices(self, nodes, materials, theta):
         nb, nodes, materials, theta = self._inputs(nodes, materials, theta)

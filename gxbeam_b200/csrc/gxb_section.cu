@@ -64,25 +64,25 @@ __device__ void sec_congruence(const double (&T)[6][6], double (&Q)[6][6]) {    
     for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { double s = 0; for (int k = 0; k < 6; k++) s += T[i][k] * Q[k][j]; t[i][j] = s; }
     for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { double s = 0; for (int k = 0; k < 6; k++) s += t[i][k] * T[j][k]; Q[i][j] = s; }
 }
+__device__ void sec_Ttheta(double theta, double (&T)[6][6]) {      // get_Ttheta (:260-278)
+    double s, c; sincos(theta, &s, &c);
+    const double c2 = c * c, s2 = s * s, sc = s * c;
+    const double t[6][6] = {{c2, 0, 0, 2 * sc, 0, s2}, {0, 1, 0, 0, 0, 0}, {0, 0, c, 0, s, 0}, {-sc, 0, 0, c2 - s2, 0, sc}, {0, 0, -s, 0, c, 0}, {s2, 0, 0, -2 * sc, 0, c2}};
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) T[i][j] = t[i][j];
+}
+__device__ void sec_Tbeta(const double (&xy)[4][2], double (&T)[6][6]) {      // element_orientation (:331-345), get_Tbeta (:293-309)
+    const double dx = 0.5 * (xy[1][0] + xy[2][0]) - 0.5 * (xy[0][0] + xy[3][0]), dy = 0.5 * (xy[1][1] + xy[2][1]) - 0.5 * (xy[0][1] + xy[3][1]);
+    const double ds = sqrt(dx * dx + dy * dy), c = dx / ds, s = dy / ds;
+    const double c2 = c * c, s2 = s * s, sc = s * c;
+    const double t[6][6] = {{c2, s2, -2 * sc, 0, 0, 0}, {s2, c2, 2 * sc, 0, 0, 0}, {sc, -sc, c2 - s2, 0, 0, 0}, {0, 0, 0, c, -s, 0}, {0, 0, 0, s, c, 0}, {0, 0, 0, 0, 0, 1}};
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) T[i][j] = t[i][j];
+}
 // element_submatrix: out[612] = Ae | Re | Ee | Ce | Le | Me, row-major.  xy: the four corner nodes (counterclockwise from bottom left)
 __device__ void sec_element(const double* mat, double theta, const double (&xy)[4][2], double* out) {
     double Q[6][6], T[6][6];
     sec_stiffness(mat, Q);
-    {   // rotate_ply_to_element, get_Ttheta (:253-278)
-        double s, c; sincos(theta, &s, &c);
-        const double c2 = c * c, s2 = s * s, sc = s * c;
-        const double t[6][6] = {{c2, 0, 0, 2 * sc, 0, s2}, {0, 1, 0, 0, 0, 0}, {0, 0, c, 0, s, 0}, {-sc, 0, 0, c2 - s2, 0, sc}, {0, 0, -s, 0, c, 0}, {s2, 0, 0, -2 * sc, 0, c2}};
-        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) T[i][j] = t[i][j];
-        sec_congruence(T, Q);
-    }
-    {   // element_orientation (:331-345), rotate_element_to_beam, get_Tbeta (:286-309)
-        const double dx = 0.5 * (xy[1][0] + xy[2][0]) - 0.5 * (xy[0][0] + xy[3][0]), dy = 0.5 * (xy[1][1] + xy[2][1]) - 0.5 * (xy[0][1] + xy[3][1]);
-        const double ds = sqrt(dx * dx + dy * dy), c = dx / ds, s = dy / ds;
-        const double c2 = c * c, s2 = s * s, sc = s * c;
-        const double t[6][6] = {{c2, s2, -2 * sc, 0, 0, 0}, {s2, c2, 2 * sc, 0, 0, 0}, {sc, -sc, c2 - s2, 0, 0, 0}, {0, 0, 0, c, -s, 0}, {0, 0, 0, s, c, 0}, {0, 0, 0, 0, 0, 1}};
-        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) T[i][j] = t[i][j];
-        sec_congruence(T, Q);
-    }
+    sec_Ttheta(theta, T); sec_congruence(T, Q);        // rotate_ply_to_element (:253-258)
+    sec_Tbeta(xy, T); sec_congruence(T, Q);            // rotate_element_to_beam (:286-291)
     for (int i = 0; i < SEC_ELEM; i++) out[i] = 0.0;
     double* Ae = out; double* Re = out + 36; double* Ee = out + 108; double* Ce = out + 252; double* Le = out + 396; double* Me = out + 468;
     const double gp = 0.5773502691896258;      // 1 / sqrt(3)
@@ -164,6 +164,86 @@ __global__ void __launch_bounds__(64) k_section_assemble(SecArgs A) {
 
 // y[ndof][6] (+)= op(B) x[ndof][6] for a band matrix; sym: lower band, column-oriented (hb + 1 per column); else full band, row-oriented
 // (2 hb + 1 per row), transposed optionally.  One thread per (row, column-of-x) pair; sign: y = sgn * B x (+ y if accumulate).
+// strain_recovery (section.jl:952-1040) + tsai_wu (:1108-1131): one thread per (layup, element), after k_section_solve has left X, Y (oX1)
+// and dX (oX2) of the layup in its scratch (the reference's SectionCache).  Outputs [b][ne][6] = the memory layout of the reference's 6 x ne
+// Julia matrices; any may be null.
+struct SecRecoverArgs {
+    const double* F; const double* Mo;      // [b][3] each
+    const double* strengths;                // [b][ne][9] (S1t, S1c, S2t, S2c, S3t, S3c, S12, S13, S23: Material fields 11-19, :29-37) or null
+    int gxbeam_order;
+    double *strain_b, *stress_b, *strain_p, *stress_p, *failure;
+};
+__global__ void __launch_bounds__(64) k_section_recover(SecArgs A, SecRecoverArgs Rv) {
+    const SecDims& D = A.d;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.nbatch * D.ne) return;
+    const int64_t b = t / D.ne; const int e = (int)(t % D.ne);
+    const int* cn = A.conn + 4 * e;
+    double xy[4][2];
+    for (int i = 0; i < 4; i++) { xy[i][0] = A.nodes[((size_t)b * D.nn + cn[i]) * 2]; xy[i][1] = A.nodes[((size_t)b * D.nn + cn[i]) * 2 + 1]; }
+    const double* mat = A.mats + ((size_t)b * D.ne + e) * 10;
+    const double theta = A.theta[(size_t)b * D.ne + e];
+    // loads in the section's axes (z along the beam): GXBeam's x, y, z = the section's z, x, y
+    double ld[6];
+    {
+        const double* F = Rv.F + 3 * b; const double* Mo = Rv.Mo + 3 * b;
+        if (Rv.gxbeam_order) { ld[0] = F[1]; ld[1] = F[2]; ld[2] = F[0]; ld[3] = Mo[1]; ld[4] = Mo[2]; ld[5] = Mo[0]; }
+        else { for (int i = 0; i < 3; i++) { ld[i] = F[i]; ld[3 + i] = Mo[i]; } }
+    }
+    const double* s = A.scratch + (size_t)b * D.per_instance;
+    const double* X = s + D.oX1; const double* Y = X + (size_t)D.ndof * 6; const double* dX = s + D.oX2;
+    double yl[6], xe[12], dxe[12];
+    for (int i = 0; i < 6; i++) { double a = 0; for (int k = 0; k < 6; k++) a = fma(Y[6 * i + k], ld[k], a); yl[i] = a; }
+    for (int i = 0; i < 4; i++) for (int d = 0; d < 3; d++) {
+        const size_t row = (size_t)(3 * A.perm[cn[i]] + d) * 6;
+        double a = 0, c = 0;
+        for (int k = 0; k < 6; k++) { a = fma(X[row + k], ld[k], a); c = fma(dX[row + k], ld[k], c); }
+        xe[3 * i + d] = a; dxe[3 * i + d] = c;
+    }
+    // element_matrices(0, 0, ...) (:347-462): shape functions 1/4 each at the element centre
+    const double Nk[4] = {-0.25, 0.25, 0.25, -0.25}, Ne[4] = {-0.25, -0.25, 0.25, 0.25};
+    double x = 0, y = 0, xk = 0, xet = 0, yk = 0, yet = 0;
+    for (int i = 0; i < 4; i++) { x += 0.25 * xy[i][0]; y += 0.25 * xy[i][1]; xk += Nk[i] * xy[i][0]; xet += Ne[i] * xy[i][0]; yk += Nk[i] * xy[i][1]; yet += Ne[i] * xy[i][1]; }
+    const double det = xk * yet - yk * xet;
+    const double j00 = yet / det, j01 = -yk / det, j10 = -xet / det, j11 = xk / det;
+    double eps[6] = {0, 0, 0, yl[0] - y * yl[5], yl[1] + x * yl[5], yl[2] + y * yl[3] - x * yl[4]};      // SZ Y theta
+    for (int i = 0; i < 4; i++) {
+        const double gx = j00 * Nk[i] + j01 * Ne[i], gy = j10 * Nk[i] + j11 * Ne[i];
+        eps[0] = fma(gx, xe[3 * i], eps[0]); eps[1] = fma(gy, xe[3 * i + 1], eps[1]);
+        eps[2] = fma(gy, xe[3 * i], fma(gx, xe[3 * i + 1], eps[2]));
+        eps[3] = fma(gx, xe[3 * i + 2], eps[3]); eps[4] = fma(gy, xe[3 * i + 2], eps[4]);                  // BN Xe theta
+        eps[3] = fma(0.25, dxe[3 * i], eps[3]); eps[4] = fma(0.25, dxe[3 * i + 1], eps[4]); eps[5] = fma(0.25, dxe[3 * i + 2], eps[5]);   // SN dXe theta
+    }
+    double Q[6][6], Qm[6][6], Tth[6][6], Tbe[6][6];
+    sec_stiffness(mat, Qm);
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Q[i][j] = Qm[i][j];
+    sec_Ttheta(theta, Tth); sec_congruence(Tth, Q);
+    sec_Tbeta(xy, Tbe); sec_congruence(Tbe, Q);
+    double sig[6], tmp[6], epl[6], spl[6];
+    for (int i = 0; i < 6; i++) { double a = 0; for (int k = 0; k < 6; k++) a = fma(Q[i][k], eps[k], a); sig[i] = a; }
+    for (int i = 0; i < 6; i++) { double a = 0; for (int k = 0; k < 6; k++) a = fma(Tbe[k][i], eps[k], a); tmp[i] = a; }
+    for (int i = 0; i < 6; i++) { double a = 0; for (int k = 0; k < 6; k++) a = fma(Tth[k][i], tmp[k], a); epl[i] = a; }
+    for (int i = 0; i < 6; i++) { double a = 0; for (int k = 0; k < 6; k++) a = fma(Qm[i][k], epl[k], a); spl[i] = a; }
+    // conventional orders (:1001-1008, :1033-1036): beam xx yy zz xy xz yz (GXBeam axes if asked), ply 11 22 33 12 13 23
+    const int ib_g[6] = {5, 0, 1, 4, 2, 3}, ib_s[6] = {0, 1, 5, 2, 3, 4}, ip[6] = {5, 0, 1, 3, 4, 2};
+    const int* ib = Rv.gxbeam_order ? ib_g : ib_s;
+    const size_t o = (size_t)t * 6;
+    for (int i = 0; i < 6; i++) {
+        if (Rv.strain_b) Rv.strain_b[o + i] = eps[ib[i]];
+        if (Rv.stress_b) Rv.stress_b[o + i] = sig[ib[i]];
+        if (Rv.strain_p) Rv.strain_p[o + i] = epl[ip[i]];
+        if (Rv.stress_p) Rv.stress_p[o + i] = spl[ip[i]];
+    }
+    if (Rv.failure && Rv.strengths) {
+        const double* m = Rv.strengths + (size_t)t * 9;
+        const double S1t = m[0], S1c = m[1], S2t = m[2], S2c = m[3], S3t = m[4], S3c = m[5], S12 = m[6], S13 = m[7], S23 = m[8];
+        const double s1 = spl[ip[0]], s2 = spl[ip[1]], s3 = spl[ip[2]], s4 = spl[ip[3]], s5 = spl[ip[4]], s6 = spl[ip[5]];
+        Rv.failure[t] = s1 * s1 / (S1t * S1c) + s2 * s2 / (S2t * S2c) + s3 * s3 / (S3t * S3c) + s4 * s4 / (S12 * S12) + s5 * s5 / (S13 * S13)
+                        + s6 * s6 / (S23 * S23) + s1 * (1 / S1t - 1 / S1c) + s2 * (1 / S2t - 1 / S2c) + s3 * (1 / S3t - 1 / S3c)
+                        - s1 * s2 / sqrt(S1t * S1c * S2t * S2c) - s1 * s3 / sqrt(S1t * S1c * S3t * S3c) - s2 * s3 / sqrt(S2t * S2c * S3t * S3c);
+    }
+}
+
 __device__ void sec_band_mv(const double* Bm, bool sym, bool trans, const double* x, double* y, int ndof, int hb, double sgn, bool accumulate) {
     for (int t = threadIdx.x; t < ndof * 6; t += blockDim.x) {
         const int r = t / 6, k = t % 6;
@@ -718,7 +798,8 @@ int gxb_section_info(gxb_section* s, int64_t* half_bandwidth, int64_t* scratch_d
 }
 
 static int section_run(gxb_section* s, int64_t nbatch, const double* nodes, const double* materials, const double* theta, int gxbeam_order,
-                       int shear_center, double* S, double* sc, double* tc, double* M, double* mc, int32_t* ok, double* elem_out, float* ms_out) {
+                       int shear_center, double* S, double* sc, double* tc, double* M, double* mc, int32_t* ok, double* elem_out, float* ms_out,
+                       const SecRecoverArgs* rec = nullptr /* HOST pointers */) {
     if (!s || nbatch < 1 || !nodes || !materials || !theta) return gxb_fail_(GXB_ERR_INVALID, "gxb_section: bad arguments");
     SCK(cudaSetDevice(s->device));
     const SecDims& d = s->d;
@@ -733,6 +814,11 @@ static int section_run(gxb_section* s, int64_t nbatch, const double* nodes, cons
     SCK(alloc(&d_nodes, (size_t)chunk * d.nn * 2)); SCK(alloc(&d_mats, (size_t)chunk * d.ne * 10)); SCK(alloc(&d_theta, (size_t)chunk * d.ne));
     SCK(alloc(&d_out, (size_t)chunk * 80));
     if (elem_out) SCK(alloc(&d_elem, (size_t)chunk * d.ne * SEC_ELEM)); else SCK(alloc(&d_scratch, (size_t)chunk * d.per_instance));
+    double *d_F = nullptr, *d_Mo = nullptr, *d_str = nullptr, *d_rec = nullptr;
+    if (rec) {
+        SCK(alloc(&d_F, (size_t)chunk * 3)); SCK(alloc(&d_Mo, (size_t)chunk * 3)); SCK(alloc(&d_rec, (size_t)chunk * d.ne * 25));
+        if (rec->strengths) SCK(alloc(&d_str, (size_t)chunk * d.ne * 9));
+    }
     { cudaError_t e = cudaMalloc((void**)&d_status, chunk * sizeof(int)); if (e != cudaSuccess) return gxb_fail_(GXB_ERR_CUDA, cudaGetErrorString(e)); g.p.push_back(d_status); }
     cudaEvent_t e0, e1; SCK(cudaEventCreate(&e0)); SCK(cudaEventCreate(&e1));
     float ms_total = 0.f;
@@ -764,7 +850,25 @@ static int section_run(gxb_section* s, int64_t nbatch, const double* nodes, cons
             if (dyn > 40 * 1024) SCK(cudaFuncSetAttribute(k_section_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             k_section_solve<<<(unsigned)nb, 256, dyn, s->stream>>>(A);
             SCK(cudaGetLastError());
+            const size_t per = (size_t)nb * d.ne;
+            if (rec) {
+                SCK(cudaMemcpyAsync(d_F, rec->F + (size_t)b0 * 3, (size_t)nb * 24, cudaMemcpyHostToDevice, s->stream));
+                SCK(cudaMemcpyAsync(d_Mo, rec->Mo + (size_t)b0 * 3, (size_t)nb * 24, cudaMemcpyHostToDevice, s->stream));
+                if (d_str) SCK(cudaMemcpyAsync(d_str, rec->strengths + (size_t)b0 * d.ne * 9, per * 72, cudaMemcpyHostToDevice, s->stream));
+                SecRecoverArgs Rv{};
+                Rv.F = d_F; Rv.Mo = d_Mo; Rv.strengths = d_str; Rv.gxbeam_order = rec->gxbeam_order;
+                Rv.strain_b = d_rec; Rv.stress_b = d_rec + per * 6; Rv.strain_p = d_rec + per * 12; Rv.stress_p = d_rec + per * 18;
+                Rv.failure = d_str ? d_rec + per * 24 : nullptr;
+                k_section_recover<<<(unsigned)((per + 63) / 64), 64, 0, s->stream>>>(A, Rv);
+                SCK(cudaGetLastError());
+            }
             SCK(cudaEventRecord(e1, s->stream));
+            if (rec) {
+                double* const dst[4] = {rec->strain_b, rec->stress_b, rec->strain_p, rec->stress_p};
+                for (int k = 0; k < 4; k++)
+                    if (dst[k]) SCK(cudaMemcpyAsync(dst[k] + (size_t)b0 * d.ne * 6, d_rec + per * 6 * k, per * 48, cudaMemcpyDeviceToHost, s->stream));
+                if (rec->failure && d_str) SCK(cudaMemcpyAsync(rec->failure + (size_t)b0 * d.ne, d_rec + per * 24, per * 8, cudaMemcpyDeviceToHost, s->stream));
+            }
             if (S) SCK(cudaMemcpyAsync(S + (size_t)b0 * 36, A.S, (size_t)nb * 36 * 8, cudaMemcpyDeviceToHost, s->stream));
             if (sc) SCK(cudaMemcpyAsync(sc + (size_t)b0 * 2, A.sc, (size_t)nb * 16, cudaMemcpyDeviceToHost, s->stream));
             if (tc) SCK(cudaMemcpyAsync(tc + (size_t)b0 * 2, A.tc, (size_t)nb * 16, cudaMemcpyDeviceToHost, s->stream));
@@ -787,6 +891,20 @@ int gxb_section_properties(gxb_section* s, int64_t nbatch, const double* nodes, 
                            int shear_center, double* S, double* sc, double* tc, double* M, double* mc, int32_t* ok, double* device_ms) {
     float ms = 0.f;
     int rc = section_run(s, nbatch, nodes, materials, theta, gxbeam_order, shear_center, S, sc, tc, M, mc, ok, nullptr, &ms);
+    if (device_ms) *device_ms = ms;
+    return rc;
+}
+
+int gxb_section_strain_recovery(gxb_section* s, int64_t nbatch, const double* nodes, const double* materials, const double* theta,
+                                const double* strengths, const double* F, const double* M, int gxbeam_order, double* strain_b, double* stress_b,
+                                double* strain_p, double* stress_p, double* failure, double* S, int32_t* ok, double* device_ms) {
+    if (!F || !M) return gxb_fail_(GXB_ERR_INVALID, "gxb_section_strain_recovery: F and M are required");
+    if (failure && !strengths) return gxb_fail_(GXB_ERR_INVALID, "gxb_section_strain_recovery: the Tsai-Wu index needs the material strengths");
+    SecRecoverArgs rec{};
+    rec.F = F; rec.Mo = M; rec.strengths = strengths; rec.gxbeam_order = gxbeam_order;
+    rec.strain_b = strain_b; rec.stress_b = stress_b; rec.strain_p = strain_p; rec.stress_p = stress_p; rec.failure = failure;
+    float ms = 0.f;
+    int rc = section_run(s, nbatch, nodes, materials, theta, gxbeam_order, 1, S, nullptr, nullptr, nullptr, nullptr, ok, nullptr, &ms, &rec);
     if (device_ms) *device_ms = ms;
     return rc;
 }

@@ -252,6 +252,16 @@ void gxb_section_destroy(gxb_section* s);
 int gxb_section_info(gxb_section* s, int64_t* half_bandwidth, int64_t* scratch_doubles_per_instance);
 int gxb_section_properties(gxb_section* s, int64_t nbatch, const double* nodes, const double* materials, const double* theta, int gxbeam_order,
                            int shear_center, double* S, double* sc, double* tc, double* M, double* mc, int32_t* ok, double* device_ms);
+/* strain_recovery(F, M, nodes, elements, cache; gxbeam_order) (src/section.jl:952-1040) + tsai_wu(stress_p, elements) (:1108-1131) for every
+ * layup: the compliance solve of gxb_section_properties (its X, dX, Y are the reference's SectionCache and never leave the GPU) followed by the
+ * element-centre strains and stresses under the section loads F, M (nbatch x 3 each; GXBeam axes, x along the beam, if gxbeam_order).
+ * strengths: nbatch x ne x 9 (S1t, S1c, S2t, S2c, S3t, S3c, S12, S13, S23: Material fields 11-19, :29-37), NULL if failure is NULL.
+ * Outputs (any may be NULL): strain_b, stress_b (beam axes: xx yy zz xy xz yz), strain_p, stress_p (ply axes: 11 22 33 12 13 23), each
+ * nbatch x ne x 6 = the memory of the reference's 6 x ne matrices; failure nbatch x ne (Tsai-Wu index, fails if >= 1); S nbatch x 36
+ * (compliance matrix about the shear centre, as gxb_section_properties with shear_center = 1); ok, device_ms as there. */
+int gxb_section_strain_recovery(gxb_section* s, int64_t nbatch, const double* nodes, const double* materials, const double* theta,
+                                const double* strengths, const double* F, const double* M, int gxbeam_order, double* strain_b, double* stress_b,
+                                double* strain_p, double* stress_p, double* failure, double* S, int32_t* ok, double* device_ms);
 /* parity entry: element_submatrix (src/section.jl:486-501) of every element: out = nbatch x ne x 612 doubles = Ae (6x6), Re (12x6),
  * Ee (12x12), Ce (12x12), Le (12x6), Me (12x12), row-major. */
 int gxb_section_element_matrices(gxb_section* s, int64_t nbatch, const double* nodes, const double* materials, const double* theta, double* out);

@@ -379,4 +379,45 @@ function section_properties_batch(nodes::Vector{<:Vector}, elements::Vector{<:Ve
     end
 end
 
+"""
+    strain_recovery_batch(F, M, nodes, elements; gxbeam_order = true, failure = true, device = 0)
+        -> (strain_b, stress_b, strain_p, stress_p, tsai_wu)
+
+Batched counterpart of `strain_recovery(F, M, nodes, elements, cache; gxbeam_order)` (src/section.jl:952-1040) followed by
+`tsai_wu(stress_p, elements)` (:1108-1131): `F[i]`, `M[i]` are the section loads of layup i.  The compliance solve that fills the
+reference's `SectionCache` runs on the device and stays there.  Every output is `6 x ne x nb` (`ne x nb` for the Tsai-Wu index), i.e.
+`strain_b[:, :, i]` is what the reference returns for layup i.
+"""
+function strain_recovery_batch(F::Vector, M::Vector, nodes::Vector{<:Vector}, elements::Vector{<:Vector}; gxbeam_order=true, failure=true, device=0)
+    nb = length(nodes); nn = length(nodes[1]); ne = length(elements[1])
+    conn = Matrix{Int64}(undef, 4, ne)
+    for (e, el) in enumerate(elements[1]); conn[:, e] .= el.nodenum; end
+    xy = Array{Float64}(undef, 2, nn, nb); mats = Array{Float64}(undef, 10, ne, nb); theta = Array{Float64}(undef, ne, nb)
+    str = Array{Float64}(undef, 9, ne, nb); Fm = Array{Float64}(undef, 3, nb); Mm = similar(Fm)
+    for i in 1:nb
+        Fm[:, i] .= F[i]; Mm[:, i] .= M[i]
+        for (k, n) in enumerate(nodes[i]); xy[1, k, i] = n.x; xy[2, k, i] = n.y; end
+        for (e, el) in enumerate(elements[i])
+            m = el.material
+            mats[:, e, i] .= (m.E1, m.E2, m.E3, m.G12, m.G13, m.G23, m.nu12, m.nu13, m.nu23, m.rho)
+            str[:, e, i] .= (m.S1t, m.S1c, m.S2t, m.S2c, m.S3t, m.S3c, m.S12, m.S13, m.S23)
+            theta[e, i] = el.theta
+        end
+    end
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gxb_section_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint, Int64, Int64, Ptr{Int64}), h, device, nn, ne, conn))
+    try
+        eb = Array{Float64}(undef, 6, ne, nb); sb = similar(eb); ep = similar(eb); sp = similar(eb); tw = Array{Float64}(undef, ne, nb)
+        ok = zeros(Int32, nb)
+        check(ccall((:gxb_section_strain_recovery, LIB), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),
+            h[], nb, xy, mats, theta, failure ? pointer(str) : C_NULL, Fm, Mm, gxbeam_order, eb, sb, ep, sp, failure ? pointer(tw) : C_NULL, C_NULL, ok, C_NULL))
+        all(!=(0), ok) || error("strain_recovery_batch: degenerate mesh in instance $(findfirst(==(0), ok))")
+        return eb, sb, ep, sp, (failure ? tw : nothing)
+    finally
+        ccall((:gxb_section_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+end
+
 end # module

@@ -4,6 +4,7 @@ by tests/, never by the product package.
 numpy restatement, function by function, of /root/reference/src/section.jl (citations are relative to that file):
     stiffness :216-249, get_Ttheta :260-278, get_Tbeta :293-309, elementQ :317-322, element_orientation :331-345,
     element_matrices :347-462, element_integrand :464-484, element_submatrix :486-501 (2 x 2 Gauss), node2idx :508-538,
+    strain_recovery :952-1040, tsai_wu :1108-1131,
     compliance_matrix :641-783 (scatter, KKT system [E R D; R' A 0; D' 0 0], two solves with 6 right-hand sides, the nine products
     that form S, shear / tension centre, optional transformation to the shear centre, reorder :540-551), mass_matrix :840-890.
 The reference factorises the sparse KKT matrix with UMFPACK (`factorize`, :553); here scipy.sparse.linalg.splu (SuperLU) -- any
@@ -73,8 +74,8 @@ def element_orientation(xy):
     return dx / ds, dy / ds
 
 
-def element_integrand(ksi, eta, mat, theta, xy):
-    """section.jl:347-484: (Ae 6x6, Re 12x6, Ee 12x12, Ce 12x12, Le 12x6, Me 12x12) at one Gauss point."""
+def element_matrices(ksi, eta, mat, theta, xy):
+    """section.jl:347-462: Q, J, SZ, SN, BN at one point of the element."""
     mk, pk, me, pe = 1 - ksi, 1 + ksi, 1 - eta, 1 + eta
     N = np.array([mk * me, pk * me, pk * pe, mk * pe]) / 4
     x, y = N @ xy[:, 0], N @ xy[:, 1]
@@ -99,6 +100,12 @@ def element_integrand(ksi, eta, mat, theta, xy):
         for d in range(3):
             NMk[d, 3 * i + d] = N_ksi[i]; NMe[d, 3 * i + d] = N_eta[i]
     BN = Bksi @ NMk + Beta @ NMe
+    return Q, J, SZ, SN, BN
+
+
+def element_integrand(ksi, eta, mat, theta, xy):
+    """section.jl:464-484: (Ae 6x6, Re 12x6, Ee 12x12, Ce 12x12, Le 12x6, Me 12x12) at one Gauss point."""
+    Q, J, SZ, SN, BN = element_matrices(ksi, eta, mat, theta, xy)
     dJ = np.linalg.det(J)
     return (SZ.T @ Q @ SZ * dJ, BN.T @ Q @ SZ * dJ, BN.T @ Q @ BN * dJ, BN.T @ Q @ SN * dJ, SN.T @ Q @ SZ * dJ, SN.T @ Q @ SN * dJ)
 
@@ -172,6 +179,45 @@ def compliance_matrix(nodes, conn, mats, thetas, gxbeam_order=True, shear_center
     if return_parts:
         return S, np.array([xs, ys]), np.array([xt, yt]), dict(A=A, R=R, E=E, C=Cm, L=L, M=M, X=X, Y=Y, dX=dX, dY=dY, S_raw=S_raw)
     return S, np.array([xs, ys]), np.array([xt, yt])
+
+
+def strain_recovery(F, M, nodes, conn, mats, thetas, parts, gxbeam_order=True):
+    """section.jl:952-1040.  parts: the X, dX, Y of compliance_matrix(..., return_parts=True) (the reference's SectionCache).
+    Returns strain_b, stress_b, strain_p, stress_p, each [6, ne]."""
+    nodes = np.asarray(nodes, float); conn = np.asarray(conn, int); mats = np.asarray(mats, float); thetas = np.asarray(thetas, float)
+    F = np.asarray(F, float); M = np.asarray(M, float)
+    if gxbeam_order:
+        new = [1, 2, 0]
+        load = np.concatenate([F[new], M[new]])
+        idx_b = [5, 0, 1, 4, 2, 3]
+    else:
+        load = np.concatenate([F, M])
+        idx_b = [0, 1, 5, 2, 3, 4]
+    idx_p = [5, 0, 1, 3, 4, 2]
+    ne = len(conn)
+    eb = np.zeros((6, ne)); sb = np.zeros((6, ne)); ep = np.zeros((6, ne)); sp_ = np.zeros((6, ne))
+    X, dX, Y = parts["X"], parts["dX"], parts["Y"]
+    for e in range(ne):
+        xy = nodes[conn[e]]
+        Q, _, SZ, SN, BN = element_matrices(0.0, 0.0, mats[e], thetas[e], xy)
+        idx = (3 * conn[e][:, None] + np.arange(3)[None, :]).ravel()
+        eps = SZ @ (Y @ load) + BN @ (X[idx] @ load) + SN @ (dX[idx] @ load)
+        sig = Q @ eps
+        cb, sbeta = element_orientation(xy)
+        epl = get_Ttheta(thetas[e]).T @ (get_Tbeta(cb, sbeta).T @ eps)
+        spl = stiffness(mats[e]) @ epl
+        eb[:, e] = eps[idx_b]; sb[:, e] = sig[idx_b]; ep[:, e] = epl[idx_p]; sp_[:, e] = spl[idx_p]
+    return eb, sb, ep, sp_
+
+
+def tsai_wu(stress_p, strengths):
+    """section.jl:1108-1131.  stress_p [6, ne]; strengths [ne, 9] = (S1t, S1c, S2t, S2c, S3t, S3c, S12, S13, S23) of each element's material."""
+    s = np.asarray(stress_p, float); m = np.asarray(strengths, float)
+    S1t, S1c, S2t, S2c, S3t, S3c, S12, S13, S23 = m.T
+    return (s[0] ** 2 / (S1t * S1c) + s[1] ** 2 / (S2t * S2c) + s[2] ** 2 / (S3t * S3c) + s[3] ** 2 / S12 ** 2 + s[4] ** 2 / S13 ** 2
+            + s[5] ** 2 / S23 ** 2 + s[0] * (1 / S1t - 1 / S1c) + s[1] * (1 / S2t - 1 / S2c) + s[2] * (1 / S3t - 1 / S3c)
+            - s[0] * s[1] / np.sqrt(S1t * S1c * S2t * S2c) - s[0] * s[2] / np.sqrt(S1t * S1c * S3t * S3c)
+            - s[1] * s[2] / np.sqrt(S2t * S2c * S3t * S3c))
 
 
 def area_and_centroid(xy):

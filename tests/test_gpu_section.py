@@ -96,3 +96,53 @@ def test_section_argument_errors():
     nodes, conn = SO.square_mesh(2, 0.05)
     with pytest.raises(api.GXBError, match="1-based"):
         api.Section(len(nodes), conn)                  # 0-based connectivity is refused
+
+
+@pytest.mark.parametrize("gxbeam_order", [True, False])
+def test_strain_recovery_and_tsai_wu_match_oracle(gxbeam_order):
+    """strain_recovery (src/section.jl:952-1040) and tsai_wu (:1108-1131) of random layups of a closed multi-ply ring under random section loads,
+    element by element against the oracle: every strain / stress within 1e-9 of the largest entry of its array (per layup), the Tsai-Wu index to
+    1e-9 absolute-or-relative; S comes back with it (shear-centre form) and equals gxb_section_properties'."""
+    nodes, conn = SO.ring_mesh(0.1, 0.012, 4, 48)
+    nb, ne, nn = 5, len(conn), len(nodes)
+    mats, theta = _random_layups(nb, ne, 21)
+    rng = np.random.default_rng(22)
+    nb_nodes = np.tile(nodes[None], (nb, 1, 1)) * rng.uniform(0.9, 1.1, (nb, 1, 1))
+    F = rng.standard_normal((nb, 3)) * 50.0
+    M = rng.standard_normal((nb, 3)) * 5.0
+    strengths = np.tile(np.array([1500.0, 1200.0, 50.0, 250.0, 50.0, 250.0, 70.0, 70.0, 40.0])[None, None], (nb, ne, 1)) * rng.uniform(0.8, 1.2, (nb, ne, 1))
+    sec = api.Section(nn, conn + 1)
+    r = sec.strain_recovery(nb_nodes, mats, theta, F, M, strengths=strengths, gxbeam_order=gxbeam_order)
+    p = sec.properties(nb_nodes, mats, theta, gxbeam_order=gxbeam_order)
+    sec.close()
+    # the global matrices are summed with floating-point atomics: two runs agree to round-off, not bit for bit
+    assert r["ok"].all() and max(_scaled_err(r["S"][b], p["S"][b]) for b in range(nb)) <= 1e-11
+    for b in range(nb):
+        _, _, _, parts = SO.compliance_matrix(nb_nodes[b], conn, mats[b], theta[b], gxbeam_order=False, shear_center=False, return_parts=True)
+        ref = SO.strain_recovery(F[b], M[b], nb_nodes[b], conn, mats[b], theta[b], parts, gxbeam_order=gxbeam_order)
+        for name, want in zip(("strain_b", "stress_b", "strain_p", "stress_p"), ref):
+            got = r[name][b].T
+            assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max(), (b, name, np.abs(got - want).max() / np.abs(want).max())
+        fw = SO.tsai_wu(ref[3], strengths[b])
+        assert np.abs(r["failure"][b] - fw).max() <= 1e-9 * max(1.0, np.abs(fw).max()), b
+
+
+def test_strain_recovery_beam_theory_on_the_device():
+    """The isotropic square under axial force and bending: the DEVICE's axial stress is Fz / A + Mx y / Ixx - My x / Iyy (the same check that pins
+    the oracle, tests/test_oracle_section.py); without strengths no Tsai-Wu index is returned, and asking for one without strengths is refused."""
+    nodes, conn = SO.square_mesh()
+    mats = np.tile(np.array(ISO1)[None, None], (2, 100, 1)); theta = np.zeros((2, 100))
+    F = np.array([[0, 0, 3.0], [0, 0, 1.0]]); M = np.array([[0, 0, 0], [0.7, 0.4, 0]])
+    sec = api.Section(len(nodes), conn + 1)
+    r = sec.strain_recovery(np.tile(nodes[None], (2, 1, 1)), mats, theta, F, M, gxbeam_order=False)
+    assert r["failure"] is None
+    cen = nodes[conn].mean(axis=1)
+    for b, tol in ((0, 1e-9), (1, 1e-3)):
+        want = F[b, 2] / 0.01 + M[b, 0] * cen[:, 1] / (1e-4 / 12) - M[b, 1] * cen[:, 0] / (1e-4 / 12)
+        assert np.abs(r["stress_b"][b][:, 2] - want).max() <= tol * np.abs(want).max()
+    import ctypes as C
+    out = np.empty((2, 100))
+    rc = sec.lib.gxb_section_strain_recovery(sec.h, C.c_int64(2), api._ptr(np.tile(nodes[None], (2, 1, 1))), api._ptr(mats), api._ptr(theta), None,
+                                             api._ptr(F), api._ptr(M), 0, None, None, None, None, api._ptr(out), None, None, None)
+    assert rc != 0 and b"strengths" in sec.lib.gxb_last_error()
+    sec.close()

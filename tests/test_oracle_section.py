@@ -90,3 +90,37 @@ def test_circular_tube_gxbeam_order():
     area = np.pi * (R ** 2 - (R - t) ** 2)
     assert abs(M[0, 0] - 2800.0 * area) <= 2e-3 * 2800.0 * area and np.abs(mc).max() <= 1e-12
     assert np.allclose(M, M.T)
+
+
+def test_strain_recovery_isotropic_square_beam_theory():
+    """strain_recovery (section.jl:952-1040) on the homogeneous isotropic square: axial force and pure bending reproduce the Euler-Bernoulli
+    stress field szz = Fz / A + Mx y / Ixx - My x / Iyy at the element centres, torsion-free loads leave the shear stresses at zero, and the ply
+    frame of an unrotated element on a horizontal edge is the beam frame with the fibre (1) axis along z."""
+    nodes, conn = S.square_mesh()
+    mats = np.array([ISO1] * 100); th = np.zeros(100)
+    _, _, _, parts = S.compliance_matrix(nodes, conn, mats, th, gxbeam_order=False, shear_center=False, return_parts=True)
+    side = 0.1; area = side ** 2; inertia = side ** 4 / 12
+    cen = nodes[conn].mean(axis=1)
+    for F, M in (([0, 0, 3.0], [0, 0, 0]), ([0, 0, 0], [2.0, 0, 0]), ([0, 0, 0], [0, -1.5, 0]), ([0, 0, 1.0], [0.7, 0.4, 0])):
+        eb, sb, ep, sp_ = S.strain_recovery(F, M, nodes, conn, mats, th, parts, gxbeam_order=False)
+        want = F[2] / area + M[0] * cen[:, 1] / inertia - M[1] * cen[:, 0] / inertia
+        scale = np.abs(want).max()
+        # exact for the axial load; bending carries the 10 x 10 bilinear mesh's discretisation error (anticlastic in-plane warping), 5.5e-4
+        tol = 1e-9 if not any(M) else 1e-3
+        assert np.abs(sb[2] - want).max() <= tol * scale, np.abs(sb[2] - want).max() / scale
+        assert np.abs(sb[[0, 1, 3, 4, 5]]).max() <= tol * scale                  # uniaxial stress state
+        assert np.allclose(eb[2], want / 100.0, rtol=0, atol=tol * scale / 100)  # ezz = szz / E
+        assert np.allclose(eb[0], -0.2 * eb[2], rtol=0, atol=tol * scale / 100)  # Poisson contraction
+        assert np.allclose(sp_[0], sb[2], rtol=0, atol=1e-9 * scale)              # ply 11 = beam zz for theta = 0
+    # the GXBeam axis order permutes loads (x along the beam) and outputs: the same physical load gives the same field, xx first
+    eb2, sb2, _, _ = S.strain_recovery([1.0, 0, 0], [0, 0.7, 0.4], nodes, conn, mats, th, parts, gxbeam_order=True)
+    assert np.allclose(sb2[0], sb[2], rtol=0, atol=1e-12 * scale) and np.allclose(eb2[0], eb[2], rtol=0, atol=1e-14)
+
+
+def test_tsai_wu_known_values():
+    """tsai_wu (section.jl:1108-1131): uniaxial stress at the tensile / compressive strength sits exactly on the failure surface."""
+    st = np.array([[1500.0, 1200.0, 50.0, 250.0, 50.0, 250.0, 70.0, 70.0, 40.0]] * 4)
+    s = np.zeros((6, 4))
+    s[0, 0] = 1500.0; s[0, 1] = -1200.0; s[1, 2] = 50.0; s[3, 3] = 70.0
+    f = S.tsai_wu(s, st)
+    assert np.allclose(f, 1.0, rtol=1e-13)
