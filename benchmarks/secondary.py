@@ -60,9 +60,13 @@ def gust(nb, nt, cpu_sample, damping=True, init="ic"):
     rng = np.random.default_rng(1234 + 4)
     w = workloads.rotating_blade_batch(nb)
     tvec = np.linspace(0.0, 0.5 * (nt - 1) / 2000, nt)
+    # amplitude A_i = 100 U(0.5, 1.5), duration and onset of the 1 - cos gust (benchmarks.jl:198) jittered by 10 %
     amp = 100 * rng.uniform(0.5, 1.5, nb)
-    tf1 = np.where(tvec < 0.2, 0.1 * (1 - np.sin(2 * np.pi * (tvec / 0.4 + 0.25))), 0.0)
-    series = (amp[:, None] * tf1[None, :])[:, :, None]
+    period = 0.4 * rng.uniform(0.9, 1.1, nb)[:, None]
+    onset = 0.02 * rng.uniform(0.0, 1.0, nb)[:, None]
+    tt = tvec[None, :] - onset
+    tf1 = np.where((tt >= 0) & (tt < 0.5 * period), 0.1 * (1 - np.sin(2 * np.pi * (tt / period + 0.25))), 0.0)
+    series = (amp[:, None] * tf1)[:, :, None]
     ctx = make_ctx(w, nb)
     opts = api.make_opts(structural_damping=damping, persistent=PERSISTENT)
     rates0 = np.zeros((nb, 25, 12))
