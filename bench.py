@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: BASELINE configs[1]'s 4096 instances in total, sharded over the N GPUs; weak: 4096 per GPU")
     ap.add_argument("--e2e-lanes", type=int, default=0, help="contexts per GPU of the pipelined host-buffer path (0 = by batch size)")
+    ap.add_argument("--e2e-impl", default="multi", choices=["pipelined", "multi"],
+                    help="host-buffer path: api.PipelinedSolver (Python host threads) or gxb_multi_solve_compact (one C call, threads inside the library)")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks the pipelined host-buffer path cuts the per-GPU batch into (0 = one per lane)")
     ap.add_argument("--e2e-sizes", default="", help="comma-separated chunk sizes of the pipelined host-buffer path, one lane each (overrides lanes/chunks)")
     ap.add_argument("--lu-parts", type=int, default=0, help="warps per instance of the partitioned factorisation (0 auto, 1 off, 2/4/8)")
@@ -373,23 +375,43 @@ def main():
         bcc = (bc_base, bc_point, bc_field, t_bcv.numpy())
         for _ in range(2):
             ps.solve(h_el, None, h_fs, out, opts_fast, bc_compact=bcc)
+        use_multi = args.e2e_impl == "multi" and sizes is None and e2e_chunks == e2e_lanes
+        if use_multi:
+            # the same pipeline inside the library: ONE C call (gxb_multi_solve_compact), the lanes are shards that share this GPU
+            ps.close()
+            mc = api.MultiContext([local] * e2e_lanes)
+            mc.topology(w["start"], w["stop"], w["pd"], w["pl"])
+            mc.set_batch(nb)
+            mc.hint_no_gravity()
+            run_e2e = lambda: mc.solve_compact(h_el, bc_base, bc_point, bc_field, t_bcv.numpy(), opts_fast, force_scaling=h_fs, out=out)
+            for _ in range(2):
+                run_e2e()
+            assert out["converged"].all() and np.array_equal(out["iters"], res["iters"])
+        else:
+            run_e2e = lambda: ps.solve(h_el, None, h_fs, out, opts_fast, bc_compact=bcc)
         barrier()
         e2e_s, e2e_iters = 0.0, 0
         for _ in range(args.steps):
             t1 = time.perf_counter()
-            ps.solve(h_el, None, h_fs, out, opts_fast, bc_compact=bcc)
+            run_e2e()
             e2e_s += time.perf_counter() - t1
             e2e_iters += int(out["iters"].sum())
         barrier()
         assert out["converged"].all()
-        ps.close()
-        e2e_how = (f"wall clock around api.PipelinedSolver.solve ({e2e_chunks} chunks on {e2e_lanes} lanes, host threads), pinned host buffers in "
+        if use_multi:
+            mc.close()
+        else:
+            ps.close()
+        e2e_how = ((f"wall clock around ONE C-ABI call, gxb_multi_solve_compact ({e2e_lanes} shards sharing this GPU as pipeline lanes, worker threads "
+                    "and ordered uploads inside the library)" if use_multi else
+                    f"wall clock around api.PipelinedSolver.solve ({e2e_chunks} chunks on {e2e_lanes} lanes, host threads)") +
+                   ", pinned host buffers in "
                    "the reference's Element layout; no-gravity hint: 49 of 91 doubles per element are fetched (strided copies); prescribed "
                    "conditions as one shared np x 18 record + 2 per-instance values (gxb_set_bc_compact)")
     else:
         e2e_how = "wall clock around the synchronous C-ABI calls, pinned host buffers"
     # bytes that actually cross PCIe per step: with the no-gravity hint only 49 of the 91 doubles of every element record are read
-    pipelined = e2e_how.startswith("wall clock around api.PipelinedSolver")
+    pipelined = e2e_how.startswith("wall clock around api.PipelinedSolver") or e2e_how.startswith("wall clock around ONE C-ABI call")
     h2d = (h_el.nbytes * 49 // 91 + t_bcv.numpy().nbytes + e2e_lanes * bc_base.nbytes if pipelined else h_el.nbytes + h_bc.nbytes) + h_fs.nbytes
     d2h = out["x"].nbytes + out["iters"].nbytes + out["resid_inf"].nbytes + 4 * nb
 

@@ -53,7 +53,7 @@ EXPORTS = ["gxb_default_opts", "gxb_create", "gxb_destroy", "gxb_last_error", "g
            "gxb_initial_condition", "gxb_initial_residual_jacobian", "gxb_body_columns", "gxb_eigen_ritz_vectors", "gxb_hint_no_gravity", "gxb_eigen_status", "gxb_set_bc_compact", "gxb_assembly_state", "gxb_eigen_arnoldi_left",
            "gxb_multi_create", "gxb_multi_destroy", "gxb_multi_topology", "gxb_multi_set_batch", "gxb_multi_solve",
            "gxb_section_create", "gxb_section_destroy", "gxb_section_info", "gxb_section_properties", "gxb_section_element_matrices",
-           "gxb_section_strain_recovery"]
+           "gxb_section_strain_recovery", "gxb_multi_hint_no_gravity", "gxb_multi_solve_compact"]
 
 _lib = None
 
@@ -577,6 +577,28 @@ class MultiContext:
         a = [_f64(v) for v in (elems, points, bc, dloads, pmass, gravity, force_scaling, motion, x0)]
         self._ck(self.lib.gxb_multi_solve(self.h, C.byref(o), *[_ptr(v) for v in a], _ptr(x), _ptr(conv), _ptr(its), _ptr(rinf), _ptr(ms)))
         return dict(x=x, converged=conv.astype(bool), iters=its, resid_inf=rinf, shard_ms=ms)
+
+    def hint_no_gravity(self, on=True):
+        self._ck(self.lib.gxb_multi_hint_no_gravity(self.h, int(on)))
+
+    def solve_compact(self, elems, bc_base, bc_point, bc_field, bc_values, opts=None, gravity=None, force_scaling=None, x0=None, out=None):
+        """gxb_multi_solve_compact: static_analysis of the whole batch from host buffers, prescribed conditions as one shared [np, 18] record
+        plus K varying entries per instance; shards that share a GPU act as pipeline lanes (ordered uploads)."""
+        o = opts or make_opts()
+        nb, n = self.nbatch, self.n
+        out = out or {}
+        x = out.get("x") if out.get("x") is not None else np.empty((nb, n))
+        conv = out.get("converged") if out.get("converged") is not None else np.empty(nb, np.int32)
+        its = out.get("iters") if out.get("iters") is not None else np.empty(nb, np.int32)
+        rinf = out.get("resid_inf") if out.get("resid_inf") is not None else np.empty(nb)
+        ms = np.zeros(self.ngpu)
+        pt = np.ascontiguousarray(bc_point, np.int32); fd = np.ascontiguousarray(bc_field, np.int32)
+        vals = _f64(bc_values)
+        assert vals.shape == (nb, len(pt))
+        self._ck(self.lib.gxb_multi_solve_compact(self.h, C.byref(o), _ptr(_f64(elems)), _ptr(_f64(bc_base)), C.c_int32(len(pt)), _ptr(pt), _ptr(fd),
+                                                  _ptr(vals), _ptr(_f64(gravity)), _ptr(_f64(force_scaling)), _ptr(_f64(x0)), _ptr(x), _ptr(conv),
+                                                  _ptr(its), _ptr(rinf), _ptr(ms)))
+        return dict(x=x, converged=conv.astype(bool) if conv.dtype != bool else conv, iters=its, resid_inf=rinf, shard_ms=ms)
 
     def close(self):
         if self.h:

@@ -20,6 +20,8 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <condition_variable>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -1451,8 +1453,12 @@ int gxb_set_bc_compact(gxb_ctx* c, const double* base, int32_t K, const int32_t*
 // ---- several GPUs of one box: one context + one worker thread per GPU, contiguous shards, no collective ----
 struct gxb_multi {
     std::vector<gxb_ctx*> ctx;
+    std::vector<int> device;           // device of every shard (several shards may share one GPU: "lanes")
     std::vector<int64_t> off;          // shard b-range [off[g], off[g+1])
     int kind = -1; int64_t np = 0, ne = 0, n = 0, nbatch = 0;
+    // shards on the same GPU share one PCIe link: their uploads are taken one after the other, in shard order, so that the first shard's
+    // Newton solve starts under the second shard's transfer instead of all transfers finishing together
+    std::mutex up_mu; std::condition_variable up_cv; std::vector<int> up_next;      // per device: next shard allowed to upload
 };
 // run f(g) on one host thread per GPU; the first failure's code and message are reported
 template <class F> static int multi_fanout(gxb_multi* m, F&& f) {
@@ -1474,7 +1480,7 @@ int gxb_multi_create(gxb_multi** out, int32_t ngpu, const int32_t* device_ids) {
         gxb_ctx* c = nullptr;
         int rc = gxb_create(&c, device_ids ? device_ids[g] : g);
         if (rc) { for (auto* q : m->ctx) gxb_destroy(q); delete m; return rc; }
-        m->ctx.push_back(c);
+        m->ctx.push_back(c); m->device.push_back(device_ids ? device_ids[g] : g);
     }
     *out = m;
     return GXB_OK;
@@ -1527,6 +1533,54 @@ int gxb_multi_solve(gxb_multi* m, const gxb_opts* opts, const double* elems, con
         auto solve = m->kind == 0 ? gxb_static_solve : gxb_steady_solve;
         rc = solve(c, opts, x0 ? x0 + b0 * n : nullptr, x ? x + b0 * n : nullptr, converged ? converged + b0 : nullptr, iters ? iters + b0 : nullptr,
                    resid_inf ? resid_inf + b0 : nullptr);
+        if (!rc && shard_ms) shard_ms[g] = c->stats.ms_total;
+        return rc;
+    });
+}
+int gxb_multi_hint_no_gravity(gxb_multi* m, int on) {
+    if (!m) return fail(GXB_ERR_INVALID, "gxb_multi_hint_no_gravity: null");
+    for (auto* c : m->ctx) { int rc = gxb_hint_no_gravity(c, on); if (rc) return rc; }
+    return GXB_OK;
+}
+int gxb_multi_solve_compact(gxb_multi* m, const gxb_opts* opts, const double* elems, const double* bc_base, int32_t K, const int32_t* bc_point,
+                            const int32_t* bc_field, const double* bc_values, const double* gravity, const double* force_scaling, const double* x0,
+                            double* x, int32_t* converged, int32_t* iters, double* resid_inf, double* shard_ms) {
+    if (!m || m->nbatch < 1) return fail(GXB_ERR_INVALID, "gxb_multi_solve_compact: call gxb_multi_set_batch first");
+    if (m->kind != 0) return fail(GXB_ERR_INVALID, "gxb_multi_solve_compact: static contexts (kind = 0) only");
+    if (!elems || !bc_base || K < 0 || (K > 0 && (!bc_point || !bc_field || !bc_values)))
+        return fail(GXB_ERR_INVALID, "gxb_multi_solve_compact: elems, bc_base and the K varying entries are required");
+    const int64_t N = m->ne, n = m->n;
+    const size_t G = m->ctx.size();
+    // shard order per device
+    std::vector<int> order(G, 0);
+    {
+        int maxdev = 0; for (int d : m->device) maxdev = std::max(maxdev, d);
+        std::vector<int> cnt(maxdev + 1, 0);
+        for (size_t g = 0; g < G; g++) order[g] = cnt[m->device[g]]++;
+        std::lock_guard<std::mutex> lk(m->up_mu);
+        m->up_next.assign(maxdev + 1, 0);
+    }
+    return multi_fanout(m, [&](int g) {
+        gxb_ctx* c = m->ctx[g];
+        const int64_t b0 = m->off[g];
+        const int dev = m->device[g];
+        int rc = 0;
+        {
+            std::unique_lock<std::mutex> lk(m->up_mu);
+            m->up_cv.wait(lk, [&] { return m->up_next[dev] == order[g]; });
+        }
+        // gxb_set_* return once the host buffers have been consumed (the copies are complete), so the next shard may start its transfer
+        if (!rc) rc = gxb_set_elements(c, elems + b0 * N * GXB_ELEM_STRIDE);
+        if (!rc) rc = gxb_set_bc_compact(c, bc_base, K, bc_point, bc_field, bc_values + b0 * K);
+        if (!rc) rc = gxb_set_body(c, gravity ? gravity + b0 * 3 : nullptr, force_scaling ? force_scaling + b0 : nullptr);
+        {
+            std::lock_guard<std::mutex> lk(m->up_mu);
+            m->up_next[dev] = order[g] + 1;
+        }
+        m->up_cv.notify_all();
+        if (rc) return rc;
+        rc = gxb_static_solve(c, opts, x0 ? x0 + b0 * n : nullptr, x ? x + b0 * n : nullptr, converged ? converged + b0 : nullptr,
+                              iters ? iters + b0 : nullptr, resid_inf ? resid_inf + b0 : nullptr);
         if (!rc && shard_ms) shard_ms[g] = c->stats.ms_total;
         return rc;
     });

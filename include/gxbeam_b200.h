@@ -237,6 +237,15 @@ int gxb_multi_solve(gxb_multi* m, const gxb_opts* opts, const double* elems, con
                     const double* pmass, const double* gravity, const double* force_scaling, const double* motion, const double* x0,
                     double* x, int32_t* converged, int32_t* iters, double* resid_inf, double* shard_ms);
 
+/* Design sweeps through host buffers (what bench.py times as `e2e`): gxb_hint_no_gravity on every shard, and gxb_multi_solve with the
+ * prescribed conditions in the compact form of gxb_set_bc_compact (bc_base np x 18 shared, bc_values nbatch x K).  device_ids may name
+ * the same GPU several times: the shards then act as pipeline lanes of that GPU -- their uploads are taken one after the other in
+ * shard order (one PCIe link), so that shard k solves while shard k + 1 is being transferred and shard k - 1 is copied back. */
+int gxb_multi_hint_no_gravity(gxb_multi* m, int on);
+int gxb_multi_solve_compact(gxb_multi* m, const gxb_opts* opts, const double* elems, const double* bc_base, int32_t K, const int32_t* bc_point,
+                            const int32_t* bc_field, const double* bc_values, const double* gravity, const double* force_scaling, const double* x0,
+                            double* x, int32_t* converged, int32_t* iters, double* resid_inf, double* shard_ms);
+
 /* ---- cross-section analysis (src/section.jl; BASELINE config 5) ---------------------------------------------------------------------
  * compliance_matrix(nodes, elements; gxbeam_order, shear_center) (src/section.jl:641-783) and mass_matrix(nodes, elements) (:840-890)
  * for nbatch layups that share one quad-mesh topology.  A gxb_section holds the topology: conn = ne x 4 node numbers, 1-based and

@@ -449,6 +449,29 @@ def test_multi_gpu_entry_is_bit_identical_to_one_gpu():
     assert r2["converged"].all() and np.array_equal(r1["iters"], r2["iters"]) and np.array_equal(r1["x"], r2["x"])
 
 
+def test_multi_solve_compact_pipeline_lanes_match_one_context():
+    """gxb_multi_solve_compact: three shards that share GPU 0 (pipeline lanes with ordered uploads), no-gravity hint, prescribed conditions
+    as one shared record + 2 varying entries per instance -- bit-identical to one context fed the full arrays (lu_parts fixed: the
+    automatic kernel choice depends on the shard size)."""
+    w = workloads.cantilever_tipmoment_batch(90, 24, tip_force=True)
+    opts = api.make_opts(lu_parts=1)
+    ctx = _ctx_for(w)
+    ref = ctx.static_solve(opts)
+    ctx.close()
+    mc = api.MultiContext((0, 0, 0))
+    mc.topology(w["start"], w["stop"], w["pd"], w["pl"])
+    mc.set_batch(90)
+    mc.hint_no_gravity()
+    vals = np.ascontiguousarray(w["bc"][:, 24, [11, 8]])
+    for _ in range(2):          # the second call reuses the shards' device buffers
+        r = mc.solve_compact(w["elems"], w["bc"][0], [25, 25], [11, 8], vals, opts, force_scaling=w["force_scaling"])
+        assert r["converged"].all() and np.array_equal(r["iters"], ref["iters"]) and np.array_equal(r["x"], ref["x"])
+        assert len(r["shard_ms"]) == 3 and all(t > 0 for t in r["shard_ms"])
+    with pytest.raises(api.GXBError, match="1-based"):
+        mc.solve_compact(w["elems"], w["bc"][0], [0, 25], [11, 8], vals, opts, force_scaling=w["force_scaling"])
+    mc.close()
+
+
 def test_device_assembly_state_matches_host_restatement():
     """gxb_assembly_state: AssemblyState(x, system, assembly; prescribed_conditions) on the device (src/output.jl:146-203, 317-403) --
     PointState / ElementState records of every instance against the numpy restatement (gxbeam_b200/state.py), follower loads, prescribed
