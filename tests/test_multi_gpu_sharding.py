@@ -26,12 +26,27 @@ WORKER = textwrap.dedent("""
     t = torch.tensor([1.0 + rank], dtype=torch.float64)           # pretend per-rank time
     dist.all_reduce(units, op=dist.ReduceOp.SUM)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # strong scaling (bench.py's default): every rank generates the SAME seeded batch and keeps its contiguous shard; the shards' Newton
+    # iteration counts, gathered, are the full batch's
+    nb = 5
+    wfull = workloads.cantilever_tipmoment_batch(nb * world, 8, seed=1236)
+    sl = slice(rank * nb, (rank + 1) * nb)
+    pks = O.Packed(wfull["start"], wfull["stop"], wfull["elems"][sl], wfull["points"], wfull["pd"], wfull["pl"], wfull["bc"][sl])
+    rs = O.static_solve_batch(pks, nb, force_scaling=wfull["force_scaling"][sl], nthreads=1)
+    mine = torch.tensor(rs["iters"].astype(np.float64))
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    strong_ok = None
+    if rank == 0:
+        pkf = O.Packed(wfull["start"], wfull["stop"], wfull["elems"], wfull["points"], wfull["pd"], wfull["pl"], wfull["bc"])
+        rf = O.static_solve_batch(pkf, nb * world, force_scaling=wfull["force_scaling"], nthreads=1)
+        strong_ok = bool(np.array_equal(torch.cat(parts).numpy(), rf["iters"].astype(np.float64)))
     chk = torch.tensor([float(np.abs(w["bc"][:, -1, 11]).sum())], dtype=torch.float64)
     gathered = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(gathered, chk)
     if rank == 0:
         print(json.dumps({"units": units.item(), "tmax": t.item(), "own_iters": int(r["iters"].sum()),
-                          "shards_differ": bool(gathered[0].item() != gathered[1].item())}))
+                          "shards_differ": bool(gathered[0].item() != gathered[1].item()), "strong_ok": strong_ok}))
     dist.destroy_process_group()
 """) % ROOT
 
@@ -48,7 +63,8 @@ def test_sharded_job_aggregates_with_gloo(tmp_path):
     d = json.loads(line)
     assert d["tmax"] == 2.0                      # max over ranks
     assert d["units"] > d["own_iters"]           # sum over ranks
-    assert d["shards_differ"]                    # each rank solved different instances
+    assert d["shards_differ"]                    # weak mode: each rank solved different instances
+    assert d["strong_ok"] is True                # strong mode: the gathered shards are the full seeded batch
 
 
 def test_api_shard_bounds():
