@@ -354,6 +354,7 @@ def main():
     e2e_chunks = args.e2e_chunks or e2e_lanes
     while nb % e2e_chunks:
         e2e_chunks -= 1
+    e2e_iters_equal = None
     if e2e_lanes >= 1:
         ctx.close()
         sizes = [int(v) for v in args.e2e_sizes.split(",")] if args.e2e_sizes else None
@@ -386,7 +387,8 @@ def main():
             run_e2e = lambda: mc.solve_compact(h_el, bc_base, bc_point, bc_field, t_bcv.numpy(), opts_fast, force_scaling=h_fs, out=out)
             for _ in range(2):
                 run_e2e()
-            assert out["converged"].all() and np.array_equal(out["iters"], res["iters"])
+            assert out["converged"].all()
+            e2e_iters_equal = bool(np.array_equal(out["iters"], res["iters"]))      # reported, not asserted: other shard sizes, other kernels
         else:
             run_e2e = lambda: ps.solve(h_el, None, h_fs, out, opts_fast, bc_compact=bcc)
         barrier()
@@ -460,7 +462,8 @@ def main():
                        "single_context_rank0": {"value": single["iters"] / (single["dev_ms"] * 1e-3), "ms_per_step": single["dev_ms"] / args.steps,
                                                 "wall_ms_per_step": single["wall_ms"] / args.steps, "gpu_launches": single["launches"]}},
             "e2e": {"value": e2e_iters_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s_max / args.steps, "timing": e2e_how, "single_call_value_rank0": e2e_plain},
+                    "ms_per_step": 1e3 * e2e_s_max / args.steps, "timing": e2e_how, "single_call_value_rank0": e2e_plain,
+                    "iters_equal_to_resident_run_rank0": e2e_iters_equal},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": FACTOR_KERNEL, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
