@@ -48,9 +48,11 @@ typedef struct gxb_opts {
                                 round-off in the line search's sums. */
     int32_t update_linearization; /* gxb_newmark_run with linear != 0: 0 = linearise every step about the initial state (the reference's
                                 default, analyses.jl:2536), 1 = about the current state */
-    int32_t lu_parts;        /* kind=0 only: warps per instance of the partitioned factorisation (the chain is cut into lu_parts sub-chains
-                                that are eliminated concurrently and coupled through a small interface system): 0 auto (by batch size),
-                                1 off, 2 / 3 / 4 / 6 / 8.  Any setting solves the same linear system; results agree to round-off. */
+    int32_t lu_parts;        /* warps per instance of the factorisation: 0 auto (by batch size), 1 one warp per instance (tensor-core kernel),
+                                2 the two-sided kernel (top-down + mirrored bottom-up sweep meeting in a dense interface; static and dynamic
+                                systems), 3 / 4 / 6 / 8 (kind = 0 only) the partitioned kernel: the chain is cut into lu_parts sub-chains that
+                                are eliminated concurrently and coupled through a small interface system.  Any setting solves the same
+                                linear system; results agree to round-off. */
     int32_t exact_dphi0;     /* line search slope dφ0 = g'p with g = J'F as NLsolve's newton evaluates it (one extra pass over J per Newton
                                 iteration) instead of -F'F, which is the same number in exact arithmetic because J p = -F.  Default 0.
                                 The singular-Jacobian fallback step p = -(J'J + λI) \ J'F always uses g'p. */
