@@ -323,19 +323,31 @@ __device__ void sec_kkt_solve(const double* Eb, const double* Bd, const double* 
 // The same solve with the active part of the right-hand sides in shared memory: forward, rows k .. k + hb and the 12 border rows; backward,
 // the solved rows k + 1 .. k + hb; the columns of L are prefetched one step ahead.  sm: hw * 6 + 72 + 2 (hw + 12) doubles.
 __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const double* Ts, const int* piv, double* z, int ndof, int hb, double* sm) {
+    // columns of L (hw band entries + 12 border entries) come through a ring of SEC_SR buffers filled SEC_SP columns ahead by cp.async: the
+    // factor does not fit the L2 next to the other resident instances, and a column's own work is shorter than a DRAM round trip
+    constexpr int SEC_SR = 8, SEC_SP = 6;
     const int hw = hb + 1, n1 = ndof - SEC_MTAIL, tid = threadIdx.x, lw = hw + 12;
-    double* zw = sm; double* zb = zw + hw * 6; double* Lc = zb + 72;
+    double* zw = sm; double* zb = zw + hw * 6; double* Lc = zb + 72;            // Lc: [SEC_SR][lw]
+    auto stage = [&](int col) {
+        if (col >= 0 && col < n1 && tid < lw) {
+            const double* src = tid < hw ? Eb + (size_t)col * hw + tid : Bd + (size_t)col * 12 + (tid - hw);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Lc + (col % SEC_SR) * lw + tid);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src));
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
     for (int t = tid; t < hw * 6; t += blockDim.x) { const int r = t / 6; zw[t] = r < ndof ? z[(size_t)r * 6 + t % 6] : 0.0; }
     for (int t = tid; t < 72; t += blockDim.x) zb[t] = z[(size_t)ndof * 6 + t];
-    for (int t = tid; t < lw; t += blockDim.x) Lc[t] = t < hw ? Eb[t] : Bd[t - hw];
-    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < SEC_SP; q++) stage(q);
+    double zin = (tid < 6 && hw < ndof) ? z[(size_t)hw * 6 + tid] : 0.0;         // the row that takes over slot ks after column k = 0
     int ks = 0;
     for (int k = 0; k < n1; k++, ks = (ks + 1 == hw ? 0 : ks + 1)) {
-        const double* cur = Lc + (k & 1) * lw;
-        double* nxt = Lc + ((k + 1) & 1) * lw;
-        double pre[2] = {0.0, 0.0};
-        if (k + 1 < n1) for (int t = tid, u = 0; t < lw && u < 2; t += blockDim.x, u++) pre[u] = t < hw ? Eb[(size_t)(k + 1) * hw + t] : Bd[(size_t)(k + 1) * 12 + (t - hw)];
-        const double zin = (tid < 6 && k + hw < ndof) ? z[(size_t)(k + hw) * 6 + tid] : 0.0;      // the row that takes over slot ks
+        stage(k + SEC_SP);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(SEC_SP) : "memory");      // this thread's piece of column k has landed
+        __syncthreads();                                                         // ... and everybody's; the previous column's hand-over is visible
+        const double* cur = Lc + (k % SEC_SR) * lw;
+        const double zin_next = (tid < 6 && k + 1 + hw < ndof) ? z[(size_t)(k + 1 + hw) * 6 + tid] : 0.0;
         const int mk = min(hb, ndof - 1 - k);
         for (int t = tid; t < (mk + 12) * 6; t += blockDim.x) {
             const int q = t / 6, c = t - 6 * q;
@@ -348,9 +360,10 @@ __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const doub
             z[(size_t)k * 6 + tid] = zw[ks * 6 + tid] / cur[0];
             zw[ks * 6 + tid] = zin;
         }
-        for (int t = tid, u = 0; t < lw && u < 2; t += blockDim.x, u++) nxt[t] = pre[u];
-        __syncthreads();
+        zin = zin_next;
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
     for (int t = tid; t < SEC_MTAIL * 6; t += blockDim.x) { const int r = n1 + t / 6; z[(size_t)r * 6 + t % 6] = zw[(r % hw) * 6 + t % 6]; }
     for (int t = tid; t < 72; t += blockDim.x) z[(size_t)ndof * 6 + t] = zb[t];
     __syncthreads();
@@ -368,17 +381,20 @@ __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const doub
     // backward: window = solved rows k + 1 .. k + hb (rows >= ndof do not exist: zero), border = the 12 solved multipliers
     for (int t = tid; t < hw * 6; t += blockDim.x) { const int r = n1 + t / 6; zw[(r % hw) * 6 + t % 6] = r < ndof ? z[(size_t)r * 6 + t % 6] : 0.0; }
     for (int t = tid; t < 72; t += blockDim.x) zb[t] = z[(size_t)ndof * 6 + t];
-    if (n1 > 0) for (int t = tid; t < lw; t += blockDim.x) Lc[((n1 - 1) & 1) * lw + t] = t < hw ? Eb[(size_t)(n1 - 1) * hw + t] : Bd[(size_t)(n1 - 1) * 12 + (t - hw)];
-    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < SEC_SP; q++) stage(n1 - 1 - q);
     const int c = tid / 32, lane = tid % 32;
-    double ynext = (c < 6 && lane == 0 && n1 > 0) ? z[(size_t)(n1 - 1) * 6 + c] : 0.0;
+    const bool owner = c < 6 && lane == 0;
+    double y0 = (owner && n1 > 0) ? z[(size_t)(n1 - 1) * 6 + c] : 0.0;            // forward-solved values of rows k, k - 1: two columns of lead
+    double y1 = (owner && n1 > 1) ? z[(size_t)(n1 - 2) * 6 + c] : 0.0;
     for (int k = n1 - 1; k >= 0; k--) {
-        const double* cur = Lc + (k & 1) * lw;
-        double* nxt = Lc + ((k + 1) & 1) * lw;
-        double pre[2] = {0.0, 0.0};
-        if (k > 0) for (int t = tid, u = 0; t < lw && u < 2; t += blockDim.x, u++) pre[u] = t < hw ? Eb[(size_t)(k - 1) * hw + t] : Bd[(size_t)(k - 1) * 12 + (t - hw)];
-        const double yk = ynext;
-        if (c < 6 && lane == 0 && k > 0) ynext = z[(size_t)(k - 1) * 6 + c];
+        stage(k - SEC_SP);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(SEC_SP) : "memory");
+        __syncthreads();                     // column k staged; row k + 1 written by the previous step is visible
+        const double* cur = Lc + (k % SEC_SR) * lw;
+        const double yk = y0;
+        y0 = y1;
+        y1 = (owner && k > 1) ? z[(size_t)(k - 2) * 6 + c] : 0.0;
         const int mk = min(hb, ndof - 1 - k);
         double acc = 0.0;
         if (c < 6) {
@@ -390,10 +406,10 @@ __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const doub
         }
         for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         __syncthreads();                     // every read of the slot that row k takes over (row k + hw) is done
-        if (c < 6 && lane == 0) { const double v = yk - acc; z[(size_t)k * 6 + c] = v; zw[(k % hw) * 6 + c] = v; }
-        for (int t = tid, u = 0; t < lw && u < 2; t += blockDim.x, u++) nxt[t] = pre[u];
-        __syncthreads();
+        if (owner) { const double v = yk - acc; z[(size_t)k * 6 + c] = v; zw[(k % hw) * 6 + c] = v; }
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
