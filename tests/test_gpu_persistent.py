@@ -125,3 +125,37 @@ def test_handoff_in_the_initial_condition_solve():
     assert np.array_equal(a["iters"], b["iters"]) and a["iters"][4] == cap
     assert np.abs(a["rates"] - b["rates"]).max() <= 1e-9 * np.abs(b["rates"]).max()
     assert out["auto_launches"] < out["rounds_launches"]
+
+
+def test_contexts_release_all_device_memory():
+    """Create / use / destroy every kind of handle several times (static with every factorisation kernel, dynamic with steady, eigen,
+    initial-condition and Newmark runs, a two-shard gxb_multi, a section topology): free device memory returns to its starting value --
+    the RAII holders of the C-ABI leave nothing behind on any path."""
+    import torch
+    from gxbeam_b200 import workloads
+
+    def free():
+        torch.cuda.synchronize()
+        return torch.cuda.mem_get_info()[0]
+    torch.zeros(1, device="cuda")
+    w = workloads.cantilever_tipmoment_batch(64, 40, tip_force=True)
+    wb = workloads.rotating_blade_batch(16, rpm_jitter=0.2)
+    ws = workloads.airfoil_layup_batch(4)
+
+    def cycle():
+        ctx = api.Context(0); ctx.topology(w["start"], w["stop"], w["pd"], w["pl"]); ctx.set_batch(64)
+        ctx.set_elements(w["elems"]); ctx.set_bc(w["bc"]); ctx.set_body(None, w["force_scaling"])
+        for lp in (0, 1, 2, 4):
+            assert ctx.static_solve(api.make_opts(lu_parts=lp))["converged"].all()
+        ctx.assembly_state(); ctx.close()
+        c = api.Context(0); c.topology(wb["start"], wb["stop"], wb["pd"], wb["pl"], kind=1); c.set_batch(16)
+        c.set_elements(wb["elems"]); c.set_points(wb["points_b"]); c.set_bc(wb["bc"]); c.set_body(None, wb["force_scaling"]); c.set_motion(wb["motion"])
+        st = c.steady_solve(); c.eigenvalue_analysis(st["x"], nev=4); c.initial_condition(); c.newmark_run(np.linspace(0, 0.005, 6)); c.close()
+        mc = api.MultiContext((0, 0)); mc.topology(w["start"], w["stop"], w["pd"], w["pl"]); mc.set_batch(64)
+        mc.solve(w["elems"], w["bc"], force_scaling=w["force_scaling"]); mc.close()
+        s = api.Section(ws["nn"], ws["conn"]); s.properties(ws["nodes"], ws["materials"], ws["theta"]); s.close()
+    cycle()
+    f0 = free()
+    for _ in range(3):
+        cycle()
+    assert free() == f0
