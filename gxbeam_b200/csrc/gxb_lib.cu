@@ -39,8 +39,10 @@ int gxb_fail_(int code, const std::string& msg) { return fail(code, msg); }     
 #define CK(call)                                                                                             \
     do {                                                                                                     \
         cudaError_t e_ = (call);                                                                             \
-        if (e_ != cudaSuccess)                                                                               \
+        if (e_ != cudaSuccess) {                                                                             \
+            cudaGetLastError(); /* a non-sticky error (e.g. a failed cudaMalloc) must not be reported again by the next launch check */ \
             return fail(GXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+        }                                                                                                    \
     } while (0)
 
 struct gxb_ctx {
@@ -351,12 +353,27 @@ static int require_chain(gxb_ctx* c, const char* who) {
     return GXB_OK;
 }
 
+static int set_batch_impl(gxb_ctx* c, int64_t nbatch);
 int gxb_set_batch(gxb_ctx* c, int64_t nbatch) {
     int rc = require_chain(c, "gxb_set_batch"); if (rc) return rc;
     if (nbatch < 1) return fail(GXB_ERR_INVALID, "gxb_set_batch: nbatch < 1");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     free_batch(c);
+    rc = set_batch_impl(c, nbatch);
+    if (rc) {
+        // a batch that does not fit (or any other failure half-way): give back what was allocated, leave the context without a batch but
+        // usable, and clear CUDA's last-error slot (a failed cudaMalloc stays there and would be reported by the next launch check)
+        const std::string msg = g_err;
+        free_batch(c);
+        c->nbatch = 0;
+        cudaGetLastError();
+        g_err = msg;
+    }
+    return rc;
+}
+static int set_batch_impl(gxb_ctx* c, int64_t nbatch) {
+    int rc;
     c->nbatch = nbatch;
     const size_t nb = (size_t)nbatch, n = (size_t)c->n, N = (size_t)c->ne, P = (size_t)c->np;
     if ((rc = dalloc(&c->d_elemS, nb * GXB_ELEM_NF * N))) return rc;

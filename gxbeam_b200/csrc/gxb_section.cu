@@ -31,8 +31,10 @@ int gxb_fail_(int code, const std::string& msg);      // gxb_lib.cu: sets the th
 #define SCK(call)                                                                                                                  \
     do {                                                                                                                           \
         cudaError_t e_ = (call);                                                                                                   \
-        if (e_ != cudaSuccess)                                                                                                     \
+        if (e_ != cudaSuccess) {                                                                                                   \
+            cudaGetLastError();                                                                                                    \
             return gxb_fail_(GXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (gxb_section.cu:" + std::to_string(__LINE__) + ")"); \
+        }                                                                                                                          \
     } while (0)
 
 #define SEC_ELEM 612          // doubles per element: Ae 36, Re 72, Ee 144, Ce 144, Le 72, Me 144 (row-major)

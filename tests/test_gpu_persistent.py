@@ -159,3 +159,27 @@ def test_contexts_release_all_device_memory():
     for _ in range(3):
         cycle()
     assert free() == f0
+
+
+def test_batch_that_does_not_fit_fails_loudly_and_leaves_the_context_usable():
+    """gxb_set_batch with a batch far beyond device memory: an error code with CUDA's message, every partial allocation given back, no stale
+    error in CUDA's last-error slot -- the same context then takes a normal batch and solves it."""
+    import torch
+    from gxbeam_b200 import workloads
+    torch.zeros(1, device="cuda")
+
+    def free():
+        torch.cuda.synchronize()
+        return torch.cuda.mem_get_info()[0]
+    w = workloads.cantilever_tipmoment_batch(8, 100)
+    ctx = api.Context(0)
+    ctx.topology(w["start"], w["stop"], w["pd"], w["pl"])
+    f0 = free()
+    with pytest.raises(api.GXBError, match="out of memory"):
+        ctx.set_batch(2_000_000)                       # ~1.4 TB of Jacobian and U storage
+    assert f0 - free() < (64 << 20)                    # nothing of the failed batch is left
+    assert ctx.lib.gxb_set_elements(ctx.h, api._ptr(w["elems"])) != 0 and b"gxb_set_batch first" in ctx.lib.gxb_last_error()
+    ctx.set_batch(8)
+    ctx.set_elements(w["elems"]); ctx.set_bc(w["bc"]); ctx.set_body(None, w["force_scaling"])
+    assert ctx.static_solve()["converged"].all()
+    ctx.close()
