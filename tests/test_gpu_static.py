@@ -491,3 +491,23 @@ def test_device_assembly_state_matches_host_restatement():
     assert np.allclose(pts[0][:, 0:3], a.point_u, rtol=0, atol=1e-13 * np.abs(a.point_u).max())
     assert np.allclose(pts[0][:, 24:27], a.point_F, rtol=1e-13, atol=1e-13 * np.abs(a.point_F).max())
     assert np.allclose(els[0][:, 27:30], a.elem_Mi, rtol=1e-13, atol=1e-13 * np.abs(a.elem_Mi).max())
+
+
+@pytest.mark.parametrize("parts", [0, 1, 2, 4, 8])
+def test_nan_member_is_isolated_under_every_factorisation_kernel(parts):
+    """A NaN compliance entry in one member of a static batch: that member is reported unconverged (NLsolve would throw on the non-finite
+    residual), every other member takes exactly the oracle's iterations and lands on its state -- with one warp per instance, the
+    two-sided kernel and the partitioned kernel alike (the NaN must not leak through shared memory or the interface systems)."""
+    O = _oracle()
+    w = workloads.cantilever_tipmoment_batch(12, 40, tip_force=True)
+    elems = w["elems"].copy()
+    elems[5, 17, 4] = np.nan
+    ctx = _ctx_for({**w, "elems": elems})
+    res = ctx.static_solve(api.make_opts(lu_parts=parts))
+    ctx.close()
+    ok = np.ones(12, bool); ok[5] = False
+    assert np.array_equal(res["converged"], ok)
+    pk = O.Packed(w["start"], w["stop"], w["elems"], w["points"], w["pd"], w["pl"], w["bc"])
+    ref = O.static_solve_batch(pk, 12, force_scaling=w["force_scaling"])
+    assert np.array_equal(res["iters"][ok], ref["iters"][ok])
+    assert state_error(res["x"][ok], ref["x"][ok], 0) <= 1e-9
