@@ -327,7 +327,7 @@ __device__ void sec_kkt_solve(const double* Eb, const double* Bd, const double* 
 __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const double* Ts, const int* piv, double* z, int ndof, int hb, double* sm) {
     // columns of L (hw band entries + 12 border entries) come through a ring of SEC_SR buffers filled SEC_SP columns ahead by cp.async: the
     // factor does not fit the L2 next to the other resident instances, and a column's own work is shorter than a DRAM round trip
-    constexpr int SEC_SR = 8, SEC_SP = 6;
+    constexpr int SEC_SR = 16, SEC_SP = 6;         // two columns per step: SEC_SP + 2 columns in flight, none of them in a slot still being read
     const int hw = hb + 1, n1 = ndof - SEC_MTAIL, tid = threadIdx.x, lw = hw + 12;
     double* zw = sm; double* zb = zw + hw * 6; double* Lc = zb + 72;            // Lc: [SEC_SR][lw]
     auto stage = [&](int col) {
@@ -342,14 +342,56 @@ __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const doub
     for (int t = tid; t < 72; t += blockDim.x) zb[t] = z[(size_t)ndof * 6 + t];
 #pragma unroll
     for (int q = 0; q < SEC_SP; q++) stage(q);
-    double zin = (tid < 6 && hw < ndof) ? z[(size_t)hw * 6 + tid] : 0.0;         // the row that takes over slot ks after column k = 0
+    // forward substitution, TWO columns per barrier pair: z_k is final, z_{k+1} needs L[k+1,k] z_k only (every thread forms both locally),
+    // then each pending row takes both columns' contributions in one read-modify-write
+    const int sa = tid / 6, ca = tid - 6 * sa;          // tid < 12: (which of the two columns, right-hand side) in the hand-over
+    double zin = (tid < 12 && sa + hw < ndof) ? z[(size_t)(sa + hw) * 6 + ca] : 0.0;      // rows hw, hw + 1 take over the slots of columns 0, 1
     int ks = 0;
-    for (int k = 0; k < n1; k++, ks = (ks + 1 == hw ? 0 : ks + 1)) {
+    int k = 0;
+    for (; k + 1 < n1; k += 2, ks = (ks + 2 >= hw ? ks + 2 - hw : ks + 2)) {
+        stage(k + SEC_SP); stage(k + 1 + SEC_SP);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(SEC_SP) : "memory");      // this thread's pieces of columns k, k + 1 have landed
+        __syncthreads();
+        const double* c0 = Lc + (k % SEC_SR) * lw;
+        const double* c1 = Lc + ((k + 1) % SEC_SR) * lw;
+        const int ks1 = ks + 1 == hw ? 0 : ks + 1;
+        const double zin_next = (tid < 12 && k + 2 + sa + hw < ndof) ? z[(size_t)(k + 2 + sa + hw) * 6 + ca] : 0.0;
+        const int mk0 = min(hb, ndof - 1 - k), mk1 = min(hb, ndof - 2 - k);
+        const int nwin = min(mk1, hb - 1);               // pending rows k + 2 .. k + 1 + nwin are in the window; row k + hw (reached by column
+        const double l10 = c0[1];                        // k + 1 only) enters it at the hand-over below
+        for (int t = tid; t < (nwin + 12) * 6; t += blockDim.x) {
+            const int q = t / 6, c = t - 6 * q;
+            const double z0 = zw[ks * 6 + c];
+            const double z1 = zw[ks1 * 6 + c] - l10 * z0;
+            if (q < nwin) {
+                int sl = ks + 2 + q; if (sl >= hw) sl -= hw;
+                const double a0 = q + 2 <= mk0 ? c0[q + 2] : 0.0;             // L[k + 2 + q, k]
+                zw[sl * 6 + c] -= a0 * z0 + c1[q + 1] * z1;                    // L[k + 2 + q, k + 1]
+            } else {
+                const int j = q - nwin;
+                zb[j * 6 + c] -= c0[hw + j] * z0 + c1[hw + j] * z1;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double newv = 0.0;
+            if (tid < 12) {
+                const double z0 = zw[ks * 6 + ca];
+                const double z1 = zw[ks1 * 6 + ca] - l10 * z0;
+                z[(size_t)(k + sa) * 6 + ca] = (sa == 0 ? z0 : z1) / (sa == 0 ? c0[0] : c1[0]);
+                // slot of row k -> row k + hw, which column k + 1 reaches with L[k + hw, k + 1] = c1[hb]; slot of row k + 1 -> row k + 1 + hw
+                newv = (sa == 0 && mk1 == hb) ? zin - c1[hb] * z1 : zin;
+            }
+            __syncwarp();                                 // both final values are read before either slot is handed over
+            if (tid < 12) zw[(sa == 0 ? ks : ks1) * 6 + ca] = newv;
+        }
+        zin = zin_next;
+    }
+    if (k < n1) {                                          // odd number of columns: the last one alone
         stage(k + SEC_SP);
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(SEC_SP) : "memory");      // this thread's piece of column k has landed
-        __syncthreads();                                                         // ... and everybody's; the previous column's hand-over is visible
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(SEC_SP - 1) : "memory");
+        __syncthreads();
         const double* cur = Lc + (k % SEC_SR) * lw;
-        const double zin_next = (tid < 6 && k + 1 + hw < ndof) ? z[(size_t)(k + 1 + hw) * 6 + tid] : 0.0;
         const int mk = min(hb, ndof - 1 - k);
         for (int t = tid; t < (mk + 12) * 6; t += blockDim.x) {
             const int q = t / 6, c = t - 6 * q;
@@ -360,9 +402,8 @@ __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const doub
         __syncthreads();
         if (tid < 6) {
             z[(size_t)k * 6 + tid] = zw[ks * 6 + tid] / cur[0];
-            zw[ks * 6 + tid] = zin;
+            zw[ks * 6 + tid] = (k + hw < ndof) ? z[(size_t)(k + hw) * 6 + tid] : 0.0;
         }
-        zin = zin_next;
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
@@ -385,30 +426,65 @@ __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const doub
     for (int t = tid; t < 72; t += blockDim.x) zb[t] = z[(size_t)ndof * 6 + t];
 #pragma unroll
     for (int q = 0; q < SEC_SP; q++) stage(n1 - 1 - q);
+    // backward substitution, TWO rows per barrier pair: the dot products of rows k and k - 1 with the solved rows k + 1 .. run side by side,
+    // row k - 1 then takes L[k, k-1] x_k
     const int c = tid / 32, lane = tid % 32;
     const bool owner = c < 6 && lane == 0;
-    double y0 = (owner && n1 > 0) ? z[(size_t)(n1 - 1) * 6 + c] : 0.0;            // forward-solved values of rows k, k - 1: two columns of lead
-    double y1 = (owner && n1 > 1) ? z[(size_t)(n1 - 2) * 6 + c] : 0.0;
-    for (int k = n1 - 1; k >= 0; k--) {
-        stage(k - SEC_SP);
+    k = n1 - 1;
+    double ya = (owner && k >= 0) ? z[(size_t)k * 6 + c] : 0.0;                   // forward-solved values of rows k, k - 1
+    double yb = (owner && k >= 1) ? z[(size_t)(k - 1) * 6 + c] : 0.0;
+    for (; k >= 1; k -= 2) {
+        stage(k - SEC_SP); stage(k - 1 - SEC_SP);
         asm volatile("cp.async.wait_group %0;\n" ::"n"(SEC_SP) : "memory");
-        __syncthreads();                     // column k staged; row k + 1 written by the previous step is visible
-        const double* cur = Lc + (k % SEC_SR) * lw;
-        const double yk = y0;
-        y0 = y1;
-        y1 = (owner && k > 1) ? z[(size_t)(k - 2) * 6 + c] : 0.0;
-        const int mk = min(hb, ndof - 1 - k);
-        double acc = 0.0;
+        __syncthreads();                     // columns k, k - 1 staged; the rows written by the previous step are visible
+        const double* c0 = Lc + (k % SEC_SR) * lw;
+        const double* c1 = Lc + ((k - 1) % SEC_SR) * lw;
+        const double l10 = c1[1];                                                  // L[k, k - 1]
+        const double y0 = ya, y1 = yb;
+        ya = (owner && k >= 2) ? z[(size_t)(k - 2) * 6 + c] : 0.0;
+        yb = (owner && k >= 3) ? z[(size_t)(k - 3) * 6 + c] : 0.0;
+        const int mk0 = min(hb, ndof - 1 - k), mk1 = min(hb, ndof - k);
+        double acc0 = 0.0, acc1 = 0.0;
         if (c < 6) {
             const int k1 = (k + 1) % hw;
+            for (int q = lane; q < mk0 + 12; q += 32) {
+                if (q < mk0) {
+                    int sl = k1 + q; if (sl >= hw) sl -= hw;
+                    const double xv = zw[sl * 6 + c];                              // x of row k + 1 + q
+                    acc0 = fma(c0[1 + q], xv, acc0);
+                    if (q + 2 <= mk1) acc1 = fma(c1[2 + q], xv, acc1);             // L[k + 1 + q, k - 1]
+                } else {
+                    const double bv = zb[(q - mk0) * 6 + c];
+                    acc0 = fma(c0[hw + (q - mk0)], bv, acc0);
+                    acc1 = fma(c1[hw + (q - mk0)], bv, acc1);
+                }
+            }
+        }
+        for (int o = 16; o; o >>= 1) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, o); acc1 += __shfl_xor_sync(0xffffffffu, acc1, o); }
+        __syncthreads();                     // every read of the slots that rows k, k - 1 take over (rows k + hw, k - 1 + hw) is done
+        if (owner) {
+            const double x0 = y0 - acc0;
+            const double x1 = y1 - acc1 - l10 * x0;
+            z[(size_t)k * 6 + c] = x0; z[(size_t)(k - 1) * 6 + c] = x1;
+            zw[(k % hw) * 6 + c] = x0; zw[((k - 1) % hw) * 6 + c] = x1;
+        }
+    }
+    if (k == 0) {                            // odd number of rows: row 0 alone
+        stage(-1);
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        const double* cur = Lc;
+        const int mk = min(hb, ndof - 1);
+        double acc = 0.0;
+        if (c < 6) {
+            const int k1 = 1 % hw;
             for (int q = lane; q < mk + 12; q += 32) {
                 if (q < mk) { int sl = k1 + q; if (sl >= hw) sl -= hw; acc = fma(cur[1 + q], zw[sl * 6 + c], acc); }
                 else acc = fma(cur[hw + (q - mk)], zb[(q - mk) * 6 + c], acc);
             }
         }
         for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        __syncthreads();                     // every read of the slot that row k takes over (row k + hw) is done
-        if (owner) { const double v = yk - acc; z[(size_t)k * 6 + c] = v; zw[(k % hw) * 6 + c] = v; }
+        if (owner) z[(size_t)0 * 6 + c] = ya - acc;
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
@@ -862,7 +938,7 @@ static int section_run(gxb_section* s, int64_t nbatch, const double* nodes, cons
             const size_t tab = (size_t)d.hb * (d.hb + 1) / 2 * 4;
             const size_t winb = ((size_t)(d.hb + 1) * (d.hb + 1) + (size_t)(d.hb + 1) * 12 + 144 + 4 * (size_t)(d.hb + 13)) * 8;
             const size_t statics = 8 * 1024;
-            A.smem_window = winb + tab + statics <= (size_t)optin && d.hb + 13 <= 256;      // one thread per entry of an incoming column
+            A.smem_window = winb + tab + statics <= (size_t)optin && d.hb + 13 <= 256 && d.hb >= 11;      // one thread per entry of an incoming column; the solves' 16-column ring needs hb >= 11 to fit the window's bytes
             A.pair_table = A.smem_window || (tab + statics <= (size_t)optin && d.hb < 65535);
             const size_t dyn = (A.smem_window ? winb : 0) + (A.pair_table ? tab : 0);
             if (dyn > 40 * 1024) SCK(cudaFuncSetAttribute(k_section_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
