@@ -247,17 +247,22 @@ __global__ void __launch_bounds__(64) k_section_recover(SecArgs A, SecRecoverArg
 }
 
 __device__ void sec_band_mv(const double* Bm, bool sym, bool trans, const double* x, double* y, int ndof, int hb, double sgn, bool accumulate) {
-    for (int t = threadIdx.x; t < ndof * 6; t += blockDim.x) {
-        const int r = t / 6, k = t % 6;
-        double acc = 0.0;
+    // one thread per row, all six right-hand sides at once: a band entry is read once for six FMAs (x rows are 48 contiguous bytes)
+    for (int r = threadIdx.x; r < ndof; r += blockDim.x) {
+        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         const int c0 = max(0, r - hb), c1 = min(ndof - 1, r + hb);
         for (int c = c0; c <= c1; c++) {
             double v;
             if (sym) v = (r >= c) ? Bm[(size_t)c * (hb + 1) + (r - c)] : Bm[(size_t)r * (hb + 1) + (c - r)];
             else v = trans ? Bm[(size_t)c * (2 * hb + 1) + (r - c + hb)] : Bm[(size_t)r * (2 * hb + 1) + (c - r + hb)];
-            acc = fma(v, x[(size_t)c * 6 + k], acc);
+            const double2* xc = reinterpret_cast<const double2*>(x + (size_t)c * 6);
+            const double2 x0 = xc[0], x1 = xc[1], x2 = xc[2];
+            acc[0] = fma(v, x0.x, acc[0]); acc[1] = fma(v, x0.y, acc[1]); acc[2] = fma(v, x1.x, acc[2]);
+            acc[3] = fma(v, x1.y, acc[3]); acc[4] = fma(v, x2.x, acc[4]); acc[5] = fma(v, x2.y, acc[5]);
         }
-        y[t] = accumulate ? y[t] + sgn * acc : sgn * acc;
+        double* yr = y + (size_t)r * 6;
+#pragma unroll
+        for (int k = 0; k < 6; k++) yr[k] = accumulate ? yr[k] + sgn * acc[k] : sgn * acc[k];
     }
 }
 // G[6][6] (+)= P' Q for P, Q of ndof x 6 (row-major): CTA-wide reduction, result in shared red36
