@@ -504,6 +504,12 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
     double *X1 = s + D.oX1, *X2 = s + D.oX2, *T1 = s + D.oT1, *T2 = s + D.oT2;
     const double* xy = A.nodes + (size_t)b * nn * 2;
     __shared__ double Ts[SEC_NT * SEC_NT]; __shared__ int piv[SEC_NT]; __shared__ double red[8 * 36]; __shared__ double G[36]; __shared__ int bad;
+    __shared__ unsigned char c22_i[78], c22_j[78];            // (i >= j) of the u-th entry of the 12 x 12 corner's lower triangle
+    if (threadIdx.x < 78) {
+        const int u = threadIdx.x;
+        int i = 0; while ((i + 1) * (i + 2) / 2 <= u) i++;
+        c22_i[u] = (unsigned char)i; c22_j[u] = (unsigned char)(u - i * (i + 1) / 2);
+    }
     // (row offset, column offset) of the t-th pair 1 <= dj <= dI <= hb of the rank-1 update, enumerated row by row (so that the first
     // mk (mk + 1) / 2 entries are the pairs of a shorter column): a table in dynamic shared memory when it fits (A.pair_table), else decoded
     extern __shared__ __align__(16) double sec_dyn[];
@@ -599,10 +605,7 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
                     bwin[sl * 12 + j] -= bk[j] * ck[dj] * rd;
                 } else {
                     const int u = t - npair - nbb;
-                    int i = (int)((sqrt(8.0 * u + 1.0) - 1.0) * 0.5);
-                    while ((i + 1) * (i + 2) / 2 <= u) i++;
-                    while (i * (i + 1) / 2 > u) i--;
-                    const int j = u - i * (i + 1) / 2;
+                    const int i = c22_i[u], j = c22_j[u];
                     const double v = bk[i] * bk[j] * rd;
                     c22s[12 * i + j] -= v; if (i != j) c22s[12 * j + i] -= v;
                 }
