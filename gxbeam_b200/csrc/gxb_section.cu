@@ -517,8 +517,8 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
     double* win = sec_dyn;                                     // [hw][hw]: slot c % hw holds column c of the band (window mode)
     double* bwin = win + (A.smem_window ? hw * hw : 0);        // [hw][12] border entries of the same columns
     double* c22s = bwin + (A.smem_window ? hw * 12 : 0);       // [144] corner
-    double* stg = c22s + (A.smem_window ? 144 : 0);            // [4][hw + 12] staged incoming columns
-    unsigned short* pair_tab = reinterpret_cast<unsigned short*>(stg + (A.smem_window ? 4 * (hw + 12) : 0));
+    double* stg = c22s + (A.smem_window ? 144 : 0);            // [8][hw + 12] staged incoming columns
+    unsigned short* pair_tab = reinterpret_cast<unsigned short*>(stg + (A.smem_window ? 8 * (hw + 12) : 0));
     if (A.pair_table)
         for (int t = threadIdx.x; t < hb * (hb + 1) / 2; t += blockDim.x) {
             int di = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
@@ -557,49 +557,124 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
         for (int t = threadIdx.x; t < hw * 12; t += blockDim.x) { const int c = t / 12; bwin[t] = c < ndof ? Bd[(size_t)c * 12 + t % 12] : 0.0; }
         for (int t = threadIdx.x; t < 144; t += blockDim.x) c22s[t] = C22[t];
         __syncthreads();
-        // incoming columns (k + hw) are staged three steps ahead by cp.async into a ring of four buffers: one step of lead (~1000 cycles)
-        // is shorter than a DRAM round trip with two CTAs per SM
+        // TWO columns per step.  Column k first updates column k + 1 (phase A), which is then final too; every other target in the window
+        // takes both columns' contributions in one read-modify-write (phase B: the pair enumeration relative to column k + 1, plus the
+        // term of column k where it reaches); phase C scales and writes both columns of L and hands their slots to the incoming columns
+        // k + hw, k + hw + 1.  Column k + 1 reaches one row further than the window: its contribution to column k + hw (diagonal entry
+        // and border) is applied to the incoming column at the hand-over.  Incoming columns are staged six columns ahead by cp.async
+        // into a ring of eight buffers (a step is shorter than a DRAM round trip with two CTAs per SM).
+        const int lw = hw + 12;
         auto stage_col = [&](int cn) {
-            if (cn < ndof && threadIdx.x < hw + 12) {
+            if (cn < ndof && threadIdx.x < lw) {
                 const int t = threadIdx.x;
                 const double* src = t < hw ? Eb0 + (size_t)cn * hw + t : Bd + (size_t)cn * 12 + (t - hw);
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + (cn & 3) * (hw + 12) + t);
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + (cn & 7) * lw + t);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src));
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         };
-        stage_col(hw); stage_col(hw + 1); stage_col(hw + 2);
-        int ks = 0;                                   // k % hw, kept incrementally
-        for (int k = 0; k < n1; k++, ks = (ks + 1 == hw ? 0 : ks + 1)) {
-            double* ck = win + ks * hw;
-            double* bk = bwin + ks * 12;
-            const double dk = ck[0];
-            if (!(dk > 0.0) && threadIdx.x == 0) bad = 1;
-            const double rd = 1.0 / dk;
-            const int mk = min(hb, ndof - 1 - k);
-            const int npair = mk * (mk + 1) / 2, nbb = 12 * mk;
-            const int cn = k + hw;                    // the column that takes over this slot
-            stage_col(cn + 3);
-            // band-band pairs four at a time per thread: all operands are read before the first store (every pair has its own target, but
-            // the compiler cannot know that ck and the targets do not alias: one read-modify-write at a time ran at 235 cycles per pair)
-            for (int t0 = threadIdx.x; t0 < npair; t0 += 4 * blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) stage_col(hw + q);
+        const int tid = threadIdx.x;
+        int ks = 0, k = 0;                            // ks = k % hw, kept incrementally
+        for (; k + 1 < n1; k += 2, ks = (ks + 2 >= hw ? ks + 2 - hw : ks + 2)) {
+            const int ks1 = ks + 1 == hw ? 0 : ks + 1;
+            double* ck = win + ks * hw; double* c1 = win + ks1 * hw;
+            double* bk0 = bwin + ks * 12; double* bk1 = bwin + ks1 * 12;
+            const double d0 = ck[0];
+            const double rd0 = 1.0 / d0;
+            const int mk0 = min(hb, ndof - 1 - k), mk1 = min(hb, ndof - 2 - k);
+            stage_col(k + hw + 6); stage_col(k + hw + 7);
+            // phase A: column k -> column k + 1 (rows k + 1 .. k + mk0) and its border entries
+            {
+                const double l1 = ck[1] * rd0;
+                if (tid < mk0) c1[tid] -= ck[1 + tid] * l1;
+                else if (tid >= 128 && tid < 140) bk1[tid - 128] -= bk0[tid - 128] * l1;
+            }
+            __syncthreads();
+            const double d1 = c1[0];
+            if ((!(d0 > 0.0) || !(d1 > 0.0)) && tid == 0) bad = 1;
+            const double rd1 = 1.0 / d1;
+            const bool reach_out = mk1 == hb;         // column k + 1 reaches row k + hw: the pair (hb, hb) and the border entry b = hb are not in the window
+            const int npair = mk1 * (mk1 + 1) / 2 - (reach_out ? 1 : 0);
+            const int nbb = 12 * (mk1 - (reach_out ? 1 : 0));
+            // correction of the incoming column k + hw, formed now from the final column k + 1 (phase C overwrites that slot)
+            double corr = 0.0;
+            if (reach_out && tid < lw) {
+                const double lh = c1[hb] * rd1;
+                corr = tid == 0 ? c1[hb] * lh : (tid >= hw ? bk1[tid - hw] * lh : 0.0);
+            }
+            // phase B: four targets at a time per thread, all operands read before the first store
+            for (int t0 = tid; t0 < npair; t0 += 4 * blockDim.x) {
                 int idx[4]; double nv[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int t = t0 + u * blockDim.x;
                     idx[u] = -1;
                     if (t < npair) {
-                        const int dI = pair_tab[2 * t], dj = pair_tab[2 * t + 1];
-                        int sl = ks + dj; if (sl >= hw) sl -= hw;
-                        idx[u] = sl * hw + (dI - dj);
-                        nv[u] = win[idx[u]] - ck[dI] * ck[dj] * rd;
+                        const int a = pair_tab[2 * t], b = pair_tab[2 * t + 1];      // rows / columns relative to column k + 1
+                        int sl = ks1 + b; if (sl >= hw) sl -= hw;
+                        idx[u] = sl * hw + (a - b);
+                        double upd = c1[a] * c1[b] * rd1;
+                        if (a + 1 <= mk0) upd = fma(ck[a + 1] * ck[b + 1], rd0, upd);
+                        nv[u] = win[idx[u]] - upd;
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) if (idx[u] >= 0) win[idx[u]] = nv[u];
             }
-            for (int t = npair + threadIdx.x; t < npair + nbb + 78; t += blockDim.x) {
+            for (int t = npair + tid; t < npair + nbb + 78; t += blockDim.x) {
                 if (t < npair + nbb) {
+                    const int u = t - npair, b = u / 12 + 1, j = u - 12 * (b - 1);
+                    int sl = ks1 + b; if (sl >= hw) sl -= hw;
+                    double upd = bk1[j] * c1[b] * rd1;
+                    if (b + 1 <= mk0) upd = fma(bk0[j] * ck[b + 1], rd0, upd);
+                    bwin[sl * 12 + j] -= upd;
+                } else {
+                    const int u = t - npair - nbb;
+                    const int i = c22_i[u], j = c22_j[u];
+                    const double v = bk0[i] * bk0[j] * rd0 + bk1[i] * bk1[j] * rd1;
+                    c22s[12 * i + j] -= v; if (i != j) c22s[12 * j + i] -= v;
+                }
+            }
+            __syncthreads();
+            // phase C: columns k, k + 1 are final: scale to L, write them out, refill their slots with columns k + hw, k + hw + 1 (Bd
+            // rows of incoming columns are still untouched: border entries are first modified when the column is in the window)
+            asm volatile("cp.async.wait_group 6;\n" ::: "memory");      // this thread's pieces of columns k + hw, k + hw + 1 have landed
+            if (tid < 2 * lw) {
+                const int which = tid >= lw ? 1 : 0, t = tid - which * lw;
+                const int cn = k + hw + which;
+                double in = cn < ndof ? stg[(cn & 7) * lw + t] : 0.0;
+                if (which == 0) in -= corr;
+                double* col = which ? c1 : ck; double* bcol = which ? bk1 : bk0;
+                const double rd = which ? rd1 : rd0, dd = which ? d1 : d0;
+                const int mk = which ? mk1 : mk0;
+                if (t < hw) {
+                    Eb[(size_t)(k + which) * hw + t] = t == 0 ? dd : (t <= mk ? col[t] * rd : 0.0);
+                    col[t] = in;
+                } else {
+                    const int j = t - hw;
+                    Bd[(size_t)(k + which) * 12 + j] = bcol[j] * rd;
+                    bcol[j] = in;
+                }
+            }
+            __syncthreads();
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        if (k < n1) {                                 // odd number of columns: the last one alone (nothing comes in any more: k + hw >= ndof)
+            double* ck = win + ks * hw;
+            double* bk = bwin + ks * 12;
+            const double dk = ck[0];
+            if (!(dk > 0.0) && tid == 0) bad = 1;
+            const double rd = 1.0 / dk;
+            const int mk = min(hb, ndof - 1 - k);
+            const int npair = mk * (mk + 1) / 2, nbb = 12 * mk;
+            for (int t = tid; t < npair + nbb + 78; t += blockDim.x) {
+                if (t < npair) {
+                    const int dI = pair_tab[2 * t], dj = pair_tab[2 * t + 1];
+                    int sl = ks + dj; if (sl >= hw) sl -= hw;
+                    win[sl * hw + (dI - dj)] -= ck[dI] * ck[dj] * rd;
+                } else if (t < npair + nbb) {
                     const int u = t - npair, dj = u / 12 + 1, j = u - 12 * (dj - 1);
                     int sl = ks + dj; if (sl >= hw) sl -= hw;
                     bwin[sl * 12 + j] -= bk[j] * ck[dj] * rd;
@@ -611,21 +686,10 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
                 }
             }
             __syncthreads();
-            // column k is final: scale to L, write it out, refill its slot with column k + hw (Bd row cn is still untouched: the
-            // border entries of a column are first modified when the column is in the window)
-            asm volatile("cp.async.wait_group 3;\n" ::: "memory");      // this thread's piece of column k + hw has landed
-            if (threadIdx.x < hw + 12) {
-                const int t = threadIdx.x;
-                const double in = cn < ndof ? stg[(cn & 3) * (hw + 12) + t] : 0.0;
-                if (t < hw) {
-                    const double v = t == 0 ? dk : (t <= mk ? ck[t] * rd : 0.0);
-                    Eb[(size_t)k * hw + t] = v;
-                    ck[t] = in;
-                } else {
-                    const int j = t - hw;
-                    Bd[(size_t)k * 12 + j] = bk[j] * rd;
-                    bk[j] = in;
-                }
+            if (tid < lw) {
+                const int t = tid;
+                if (t < hw) { Eb[(size_t)k * hw + t] = t == 0 ? dk : (t <= mk ? ck[t] * rd : 0.0); ck[t] = 0.0; }
+                else { Bd[(size_t)k * 12 + (t - hw)] = bk[t - hw] * rd; bk[t - hw] = 0.0; }
             }
             __syncthreads();
         }
@@ -944,9 +1008,9 @@ static int section_run(gxb_section* s, int64_t nbatch, const double* nodes, cons
             int optin = 0;
             SCK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
             const size_t tab = (size_t)d.hb * (d.hb + 1) / 2 * 4;
-            const size_t winb = ((size_t)(d.hb + 1) * (d.hb + 1) + (size_t)(d.hb + 1) * 12 + 144 + 4 * (size_t)(d.hb + 13)) * 8;
+            const size_t winb = ((size_t)(d.hb + 1) * (d.hb + 1) + (size_t)(d.hb + 1) * 12 + 144 + 8 * (size_t)(d.hb + 13)) * 8;
             const size_t statics = 8 * 1024;
-            A.smem_window = winb + tab + statics <= (size_t)optin && d.hb + 13 <= 256 && d.hb >= 11;      // one thread per entry of an incoming column; the solves' 16-column ring needs hb >= 11 to fit the window's bytes
+            A.smem_window = winb + tab + statics <= (size_t)optin && 2 * (d.hb + 13) <= 256 && d.hb >= 11;      // one thread per entry of an incoming column; the solves' 16-column ring needs hb >= 11 to fit the window's bytes
             A.pair_table = A.smem_window || (tab + statics <= (size_t)optin && d.hb < 65535);
             const size_t dyn = (A.smem_window ? winb : 0) + (A.pair_table ? tab : 0);
             if (dyn > 40 * 1024) SCK(cudaFuncSetAttribute(k_section_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
