@@ -361,6 +361,7 @@ __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const doub
         const double* c1 = Lc + ((k + 1) % SEC_SR) * lw;
         const int ks1 = ks + 1 == hw ? 0 : ks + 1;
         const double zin_next = (tid < 12 && k + 2 + sa + hw < ndof) ? z[(size_t)(k + 2 + sa + hw) * 6 + ca] : 0.0;
+        const double rdiag = tid < 12 ? 1.0 / (sa == 0 ? c0[0] : c1[0]) : 0.0;     // issued early: the division's latency hides under the update loop
         const int mk0 = min(hb, ndof - 1 - k), mk1 = min(hb, ndof - 2 - k);
         const int nwin = min(mk1, hb - 1);               // pending rows k + 2 .. k + 1 + nwin are in the window; row k + hw (reached by column
         const double l10 = c0[1];                        // k + 1 only) enters it at the hand-over below
@@ -383,7 +384,7 @@ __device__ void sec_kkt_solve_win(const double* Eb, const double* Bd, const doub
             if (tid < 12) {
                 const double z0 = zw[ks * 6 + ca];
                 const double z1 = zw[ks1 * 6 + ca] - l10 * z0;
-                z[(size_t)(k + sa) * 6 + ca] = (sa == 0 ? z0 : z1) / (sa == 0 ? c0[0] : c1[0]);
+                z[(size_t)(k + sa) * 6 + ca] = (sa == 0 ? z0 : z1) * rdiag;
                 // slot of row k -> row k + hw, which column k + 1 reaches with L[k + hw, k + 1] = c1[hb]; slot of row k + 1 -> row k + 1 + hw
                 newv = (sa == 0 && mk1 == hb) ? zin - c1[hb] * z1 : zin;
             }
@@ -585,16 +586,15 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
             const double rd0 = 1.0 / d0;
             const int mk0 = min(hb, ndof - 1 - k), mk1 = min(hb, ndof - 2 - k);
             stage_col(k + hw + 6); stage_col(k + hw + 7);
-            // phase A: column k -> column k + 1 (rows k + 1 .. k + mk0) and its border entries
-            {
-                const double l1 = ck[1] * rd0;
-                if (tid < mk0) c1[tid] -= ck[1 + tid] * l1;
-                else if (tid >= 128 && tid < 140) bk1[tid - 128] -= bk0[tid - 128] * l1;
-            }
-            __syncthreads();
-            const double d1 = c1[0];
-            if ((!(d0 > 0.0) || !(d1 > 0.0)) && tid == 0) bad = 1;
+            // phase A: column k -> column k + 1 (rows k + 1 .. k + mk0) and its border entries.  Every thread forms the second pivot
+            // d1 = c1[0] - ck[1]^2 / d0 itself (the same arithmetic as the thread that updates c1[0]), so that 1 / d1 is under way before the barrier
+            const double l1 = ck[1] * rd0;
+            const double d1 = c1[0] - ck[1] * l1;
             const double rd1 = 1.0 / d1;
+            if (tid >= 1 && tid < mk0) c1[tid] -= ck[1 + tid] * l1;       // c1[0] stays as it came: nobody reads it after this point (d1 is in registers)
+            else if (tid >= 128 && tid < 140) bk1[tid - 128] -= bk0[tid - 128] * l1;
+            __syncthreads();
+            if ((!(d0 > 0.0) || !(d1 > 0.0)) && tid == 0) bad = 1;
             const bool reach_out = mk1 == hb;         // column k + 1 reaches row k + hw: the pair (hb, hb) and the border entry b = hb are not in the window
             const int npair = mk1 * (mk1 + 1) / 2 - (reach_out ? 1 : 0);
             const int nbb = 12 * (mk1 - (reach_out ? 1 : 0));
