@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
             const double d1 = c1[0] - ck[1] * l1;
             const double rd1 = 1.0 / d1;
             if (tid >= 1 && tid < mk0) c1[tid] -= ck[1 + tid] * l1;       // c1[0] stays as it came: nobody reads it after this point (d1 is in registers)
-            else if (tid >= 128 && tid < 140) bk1[tid - 128] -= bk0[tid - 128] * l1;
+            else if (tid >= 244) bk1[tid - 244] -= bk0[tid - 244] * l1;   // (hb <= 243: the window needs (hb + 1)^2 doubles of shared memory anyway)
             __syncthreads();
             if ((!(d0 > 0.0) || !(d1 > 0.0)) && tid == 0) bad = 1;
             const bool reach_out = mk1 == hb;         // column k + 1 reaches row k + hw: the pair (hb, hb) and the border entry b = hb are not in the window
@@ -641,8 +641,8 @@ __global__ void __launch_bounds__(256) k_section_solve(SecArgs A) {
             // phase C: columns k, k + 1 are final: scale to L, write them out, refill their slots with columns k + hw, k + hw + 1 (Bd
             // rows of incoming columns are still untouched: border entries are first modified when the column is in the window)
             asm volatile("cp.async.wait_group 6;\n" ::: "memory");      // this thread's pieces of columns k + hw, k + hw + 1 have landed
-            if (tid < 2 * lw) {
-                const int which = tid >= lw ? 1 : 0, t = tid - which * lw;
+            for (int tt = tid; tt < 2 * lw; tt += blockDim.x) {             // lw <= 256: an item of column k (tt < lw) is its thread's first
+                const int which = tt >= lw ? 1 : 0, t = tt - which * lw;
                 const int cn = k + hw + which;
                 double in = cn < ndof ? stg[(cn & 7) * lw + t] : 0.0;
                 if (which == 0) in -= corr;
@@ -1010,7 +1010,7 @@ static int section_run(gxb_section* s, int64_t nbatch, const double* nodes, cons
             const size_t tab = (size_t)d.hb * (d.hb + 1) / 2 * 4;
             const size_t winb = ((size_t)(d.hb + 1) * (d.hb + 1) + (size_t)(d.hb + 1) * 12 + 144 + 8 * (size_t)(d.hb + 13)) * 8;
             const size_t statics = 8 * 1024;
-            A.smem_window = winb + tab + statics <= (size_t)optin && 2 * (d.hb + 13) <= 256 && d.hb >= 11;      // one thread per entry of an incoming column; the solves' 16-column ring needs hb >= 11 to fit the window's bytes
+            A.smem_window = winb + tab + statics <= (size_t)optin && d.hb + 13 <= 256 && d.hb >= 11;      // one thread per entry of an incoming column; the solves' 16-column ring needs hb >= 11 to fit the window's bytes
             A.pair_table = A.smem_window || (tab + statics <= (size_t)optin && d.hb < 65535);
             const size_t dyn = (A.smem_window ? winb : 0) + (A.pair_table ? tab : 0);
             if (dyn > 40 * 1024) SCK(cudaFuncSetAttribute(k_section_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));

@@ -146,3 +146,21 @@ def test_strain_recovery_beam_theory_on_the_device():
                                              api._ptr(F), api._ptr(M), 0, None, None, None, None, api._ptr(out), None, None, None)
     assert rc != 0 and b"strengths" in sec.lib.gxb_last_error()
     sec.close()
+
+
+def test_wide_band_section_matches_oracle():
+    """A thick ring (20 layers through the wall): the renumbered half bandwidth exceeds 115, so the two columns of a factorisation step are
+    handed over by more items than the CTA has threads and the border lanes sit above the widest column -- same parity bar as the thin
+    meshes."""
+    nodes, conn = SO.ring_mesh(0.1, 0.03, 20, 40)
+    nb, ne, nn = 2, len(conn), len(nodes)
+    mats, theta = _random_layups(nb, ne, 31)
+    sec = api.Section(nn, conn + 1)
+    assert sec.half_bandwidth > 115
+    r = sec.properties(np.tile(nodes[None], (nb, 1, 1)), mats, theta, gxbeam_order=False, shear_center=False)
+    sec.close()
+    assert r["ok"].all()
+    for b in range(nb):
+        Sref, sc, tc = SO.compliance_matrix(nodes, conn, mats[b], theta[b], gxbeam_order=False, shear_center=False)
+        assert _scaled_err(r["S"][b], Sref) <= 1e-9, (b, _scaled_err(r["S"][b], Sref))
+        assert np.abs(r["sc"][b] - sc).max() <= 1e-9 * 0.1 and np.abs(r["tc"][b] - tc).max() <= 1e-9 * 0.1
