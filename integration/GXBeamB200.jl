@@ -345,6 +345,68 @@ function static_analysis_multi_gpu(assemblies::Vector{<:Assembly}, devices::Vect
 end
 
 """
+    compact_conditions(bc) -> (base, points, fields, values)
+
+Split packed prescribed conditions `bc[18, np, nb]` into the record all instances share and the entries that differ between instances
+(`gxb_set_bc_compact`): `points` / `fields` are 1-based point numbers and 0-based field numbers (u, theta, F, M, Ff, Mf components),
+`values[K, nb]` the per-instance entries.  NaN (unused) entries compare equal.
+"""
+function compact_conditions(bc::Array{Float64,3})
+    np, nb = size(bc, 2), size(bc, 3)
+    points = Int32[]; fields = Int32[]
+    for p in 1:np, f in 1:18
+        any(i -> !isequal(bc[f, p, i], bc[f, p, 1]), 2:nb) && (push!(points, p); push!(fields, f - 1))
+    end
+    values = Matrix{Float64}(undef, length(points), nb)
+    for i in 1:nb, k in eachindex(points)
+        values[k, i] = bc[fields[k] + 1, points[k], i]
+    end
+    return bc[:, :, 1], points, fields, values
+end
+
+"""
+    static_analysis_pipelined(assemblies; prescribed_conditions, lanes = 4, device = 0, ...) -> (x, converged, iters)
+
+`static_analysis_batch` for a design sweep without gravity, through ONE call of `gxb_multi_solve_compact`: `lanes` shards share GPU `device`
+as pipeline lanes (shard k solves while shard k + 1 crosses PCIe and shard k - 1 is copied back), only the fields of `Element` that the
+static path reads are fetched (`gxb_multi_hint_no_gravity`), and the prescribed conditions travel as one shared record plus the entries
+that differ between instances.  This is the call `bench.py` times as its end-to-end figure.
+"""
+function static_analysis_pipelined(assemblies::Vector{<:Assembly}; prescribed_conditions, lanes=4, device=0,
+        linear=false, two_dimensional=false, ftol=1e-9, iterations=1000)
+    nb = length(assemblies); a1 = assemblies[1]
+    np, ne = length(a1.points), length(a1.elements)
+    start = collect(Int64, a1.start); stop = collect(Int64, a1.stop)
+    pd, pl, _ = pack_conditions(np, prescribed_conditions[1])
+    bc = Array{Float64}(undef, 18, np, nb)
+    for i in 1:nb
+        bc[:, :, i] .= pack_conditions(np, prescribed_conditions[i])[3]
+    end
+    base, points, fields, values = compact_conditions(bc)
+    elems = pack_elements(assemblies)
+    fs = [GXBeam.default_force_scaling(a) for a in assemblies]
+    m = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gxb_multi_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Int32, Ptr{Int32}), m, lanes, fill(Int32(device), lanes)))
+    try
+        nstates = Ref{Int64}(0)
+        check(ccall((:gxb_multi_topology, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+            m[], 0, np, ne, start, stop, pd, pl, nstates, C_NULL, C_NULL, C_NULL, C_NULL))
+        check(ccall((:gxb_multi_set_batch, LIB), Cint, (Ptr{Cvoid}, Int64), m[], nb))
+        check(ccall((:gxb_multi_hint_no_gravity, LIB), Cint, (Ptr{Cvoid}, Cint), m[], 1))
+        opts = Ref(Opts(linear, two_dimensional, ftol, iterations, 1e6, 1e-4, 0.5, 0.1, 0, 0, 0, 0, 0, 0))
+        x = Array{Float64}(undef, nstates[], nb); conv = zeros(Int32, nb); iters = zeros(Int32, nb); rinf = zeros(nb)
+        check(ccall((:gxb_multi_solve_compact, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Opts}, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+            m[], opts, elems, base, length(points), points, fields, values, C_NULL, fs, C_NULL, x, conv, iters, rinf, C_NULL))
+        return x, conv .!= 0, iters
+    finally
+        ccall((:gxb_multi_destroy, LIB), Cvoid, (Ptr{Cvoid},), m[])
+    end
+end
+
+"""
     section_properties_batch(nodes, elements; gxbeam_order = true, shear_center = true, device = 0) -> (S, sc, tc, M, mc)
 
 Batched counterpart of `compliance_matrix(nodes, elements)` and `mass_matrix(nodes, elements)` (src/section.jl:641-783, 840-890) for
