@@ -48,9 +48,15 @@ def steady(nb, cpu_sample):
     dyns = [O.make_dyn(vb=w["motion"][b, 0:3], wb=w["motion"][b, 3:6]) for b in range(ns)]
     t0 = time.perf_counter(); ref = O.steady_solve_batch(pk, ns, dyns, force_scaling=w["force_scaling"][:ns]); dt = time.perf_counter() - t0
     err = state_error(res["x"][:ns], ref["x"], 1)
+    # sanity anchor: the restatement's one-core time per instance next to the published single-core Julia figure
+    n1 = min(ns, 16)
+    pk1 = O.Packed(w["start"], w["stop"], w["elems"][:n1], w["points_b"][:n1], w["pd"], w["pl"], w["bc"][:n1])
+    t0 = time.perf_counter(); O.steady_solve_batch(pk1, n1, dyns[:n1], force_scaling=w["force_scaling"][:n1], nthreads=1); dt1 = time.perf_counter() - t0
     return {"workload": f"steady_state_analysis, {nb} rotating blades (config-1 topology, n=444)", "gpu_newton_iters_per_s": its / (ms * 1e-3),
             "gpu_ms_per_batch": ms / 10, "cpu_newton_iters_per_s": float(ref["iters"].sum() / dt), "cpu_cores": O.num_threads(),
-            "cpu_sample": ns, "iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "max_componentwise_rel_diff": err}
+            "cpu_sample": ns, "iters_equal": bool(np.array_equal(ref["iters"], res["iters"][:ns])), "max_componentwise_rel_diff": err,
+            "cpu_ms_per_instance_1core": 1e3 * dt1 / n1,
+            "published_julia_ms_per_instance_1core": 4.716, "published_source": "benchmark/benchmarks.jl:221-223 (i7-5500U, whole analysis)"}
 
 
 def gust(nb, nt, cpu_sample, damping=True, init="ic"):
@@ -118,6 +124,7 @@ def gust(nb, nt, cpu_sample, damping=True, init="ic"):
             "gpu_launches": s["launches"] + launches_init, "newton_iters": s["newton_iters"] + it_init,
             "all_converged": bool(res["converged"].all()), "iters_equal": bool(iters_equal),
             "cpu_newton_iters_per_s_1core": cpu_iters / dt, "cpu_s_per_instance_1core": dt / ns, "cpu_sample": ns,
+            "published_julia_s_per_instance_1core": 9.019, "published_source": "benchmark/benchmarks.jl:235-237 (i7-5500U, whole analysis)",
             "max_componentwise_rel_diff_final_state": err}
 
 
