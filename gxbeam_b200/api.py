@@ -612,6 +612,16 @@ class MultiContext:
             pass
 
 
+def compact_conditions(bc):
+    """Split packed prescribed conditions bc [nb, np, 18] into what gxb_set_bc_compact / gxb_multi_solve_compact take: the record all
+    instances share (base [np, 18] = instance 0), the 1-based point numbers and 0-based field numbers of the entries that differ between
+    instances, and their per-instance values [nb, K].  NaN (unused) entries compare equal."""
+    bc = np.asarray(bc, float)
+    same = (bc == bc[:1]) | (np.isnan(bc) & np.isnan(bc[:1]))
+    p, f = np.nonzero(~same.all(axis=0))
+    return bc[0].copy(), (p + 1).astype(np.int32), f.astype(np.int32), np.ascontiguousarray(bc[:, p, f])
+
+
 def correlate_eigenmodes(Cm):
     """correlate_eigenmodes(C) (src/analyses.jl:1114-1142), restated: for every row of the correlation matrix (C = U_p M V etc.) the
     best-fitting mode that is not assigned yet, and the corruption index = largest magnitude not chosen / magnitude chosen.

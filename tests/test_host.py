@@ -54,3 +54,20 @@ def test_c2_workload_is_seeded_and_shaped():
     assert np.array_equal(a["elems"], b["elems"]) and np.array_equal(a["bc"], b["bc"], equal_nan=True)
     assert a["elems"].shape == (8, 10, 91) and a["bc"].shape == (8, 11, 18)
     assert np.all(a["force_scaling"] == 2.0 ** np.round(np.log2(a["force_scaling"])))
+
+
+def test_compact_conditions_round_trip():
+    """api.compact_conditions: the shared record + the varying entries reproduce the packed prescribed conditions exactly (NaN pattern
+    included) -- the expansion gxb_set_bc_compact performs on the device, restated on the host."""
+    from gxbeam_b200 import api, workloads
+    w = workloads.cantilever_tipmoment_batch(7, 12, tip_force=True)
+    bc = w["bc"]
+    base, pts, fld, vals = api.compact_conditions(bc)
+    assert base.shape == bc.shape[1:] and vals.shape == (7, len(pts)) and len(pts) == len(fld) == 2
+    assert set(zip(pts.tolist(), fld.tolist())) == {(13, 11), (13, 8)}            # tip point: Mz and Fz vary
+    rebuilt = np.tile(base[None], (7, 1, 1))
+    rebuilt[:, pts - 1, fld] = vals
+    assert np.array_equal(np.isnan(rebuilt), np.isnan(bc)) and np.array_equal(np.nan_to_num(rebuilt), np.nan_to_num(bc))
+    # identical instances: nothing varies
+    b2, p2, f2, v2 = api.compact_conditions(np.tile(bc[:1], (3, 1, 1)))
+    assert len(p2) == 0 and v2.shape == (3, 0)
